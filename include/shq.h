@@ -1,0 +1,162 @@
+/* include/shq.h -- C ABI of libshq.so: the B200-native replacement for SH-assembly's
+ * data-parallel hot path (k-mer counting into a counting quotient filter with
+ * deNoise; batched CQF queries; unitig contraction).
+ *
+ * The reference has no FFI for this path: in-process it is the extern "C" API of
+ * cqf/gqf.h driven per key by cqf/CQF_mt.h (class CQF_mt) and
+ * src/contig_assembly.cpp.  This header is the batch-granular equivalent a
+ * maintainer binds instead; every entry point names the
+ * reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions: plain pointers and sizes; every function returns an shq_status
+ * (0 = ok) and never calls exit(); the library owns all device memory behind the
+ * opaque handle, the caller owns every host buffer.  A handle is single-caller
+ * (calls on one handle must not overlap); different handles are independent.
+ * There is no CPU fallback: without a CUDA device shq_create fails with
+ * SHQ_ERR_CUDA.
+ */
+#ifndef SHQ_H
+#define SHQ_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct shq_handle_s* shq_t;
+
+typedef enum {
+  SHQ_OK = 0,
+  SHQ_ERR_ARG = 1,          /* bad argument / unsupported geometry */
+  SHQ_ERR_CUDA = 2,         /* CUDA runtime error (no device, OOM, launch failure) */
+  SHQ_ERR_CAPACITY = 3,     /* table over-full: a run would pass xnslots (the reference hangs or
+                               writes out of bounds here) */
+  SHQ_ERR_MALFORMED = 4,    /* FASTQ chunk is not a whole number of 4-line records ending in '\n'
+                               (the reference dereferences NULL+1, cqf/CQF_mt.h:723-726) */
+  SHQ_ERR_IO = 5,           /* file open/read/write */
+  SHQ_ERR_FORMAT = 6,       /* not a .cqf image this build understands (bits_per_slot != 8, ...) */
+  SHQ_ERR_COUNT_OVERFLOW = 7, /* a single key was seen more than 2^32-1 times */
+  SHQ_ERR_STATE = 8         /* call not valid in the handle's current state */
+} shq_status;
+
+const char* shq_strerror(int status);
+const char* shq_last_error(shq_t h);      /* detail of the last failure on this handle */
+
+/* ---- lifetime -------------------------------------------------------------
+ * replaces qf_init / qf_destroy (cqf/gqf.c:2187-2317) as used by
+ * CQF_mt::CQF_mt (cqf/CQF_mt.h:427-445).  nslots = 2^qb, key bits = hb,
+ * bits_per_slot = hb-qb must be 8 (always true for the CLIs, CQF-deNoise.cpp:161).
+ * shard/nshards: this handle owns quotients [shard, shard+1) * 2^qb / nshards
+ * (SURVEY.md 8(e)); pass 0/1 for a whole filter.                                */
+int shq_create(int qb, int hb, uint32_t seed, int device, shq_t* out);
+int shq_create_shard(int qb, int hb, uint32_t seed, int device, int shard, int nshards, shq_t* out);
+void shq_destroy(shq_t h);
+
+/* ---- counting -------------------------------------------------------------
+ * shq_set_denoise_schedule: the arguments of CQF_mt::build_KmerSpectrum
+ * (cqf/CQF_mt.h:959) that drive the scheduler fastq_to_uint64kmers_prod
+ * (:821-931): trigger = n_distinct_elts_for_DeNoise, rounds = n_deNoise,
+ * end_denoise = --endDeNoise.  Rounds fire at reference-chunk boundaries with
+ * t=1 semantics: after the first chunk that leaves ndistinct >= trigger.        */
+int shq_set_denoise_schedule(shq_t h, uint64_t trigger_ndistinct, uint32_t rounds, int end_denoise);
+
+/* replaces reads_to_kmers (cqf/CQF_mt.h:610-731) for ONE chunk as cut by
+ * fastq_read_parts (:735-816).  text is a host buffer (pageable or pinned) and
+ * may be reused as soon as the call returns.  Work is batched on the device;
+ * counters become exact at shq_sync / shq_counts / shq_finish.                  */
+int shq_insert_fastq_chunk(shq_t h, const char* text, size_t n, int K);
+
+/* Same for text already resident in device memory (benchmark / pipeline use):
+ * d_text holds nchunks consecutive chunks, chunk c = [chunk_ends[c-1], chunk_ends[c])
+ * (host array of byte offsets).  Processed before the call returns control
+ * to the stream; counters exact after shq_sync.                                 */
+int shq_insert_fastq_device(shq_t h, const char* d_text, size_t n, const uint64_t* chunk_ends,
+                            size_t nchunks, int K);
+
+/* replaces a loop of qf_insert_advance(qf, key, 0, 1, ...) (cqf/gqf.c:2432-2440):
+ * keys are already reduced (hash % range).  Host or device pointer variants.    */
+int shq_insert_keys(shq_t h, const uint64_t* keys, size_t n);
+int shq_insert_keys_device(shq_t h, const uint64_t* d_keys, size_t n);
+
+/* replaces the tail of build_KmerSpectrum (cqf/CQF_mt.h:979-987): drains pending
+ * chunks, runs the --endDeNoise round if scheduled, fixes nelts/ndistinct.       */
+int shq_finish(shq_t h);
+int shq_sync(shq_t h);
+
+/* replaces runtime->ndistinct_elts / runtime->nelts (cqf/CQF_mt.h:279-280).     */
+int shq_counts(shq_t h, uint64_t* ndistinct, uint64_t* nelts);
+/* number of deNoise sweeps executed so far by the schedule / by shq_denoise     */
+int shq_rounds_done(shq_t h, uint32_t* rounds);
+
+/* replaces one DeNoise mode round (cqf/CQF_mt.h:884-922 -> qf_clean_singleton*,
+ * cqf/gqf.c:2792-3040), including the reference's range hand-out.               */
+int shq_denoise(shq_t h, uint64_t* removed);
+
+/* ---- (de)serialisation ------------------------------------------------------
+ * replaces qf_serialize / qf_deserialize (cqf/gqf.c:2379-2420) behind
+ * CQF_mt::save / load (cqf/CQF_mt.h:514-523).  Byte-compatible both ways.       */
+int shq_image_size(shq_t h, size_t* bytes);
+int shq_export_cqf(shq_t h, void* dst, size_t cap, size_t* written);
+int shq_save(shq_t h, const char* path);
+int shq_load(const char* path, int device, shq_t* out);
+int shq_load_image(const void* image, size_t n, int device, shq_t* out);
+int shq_geometry(shq_t h, int* qb, int* hb, uint64_t* nslots, uint64_t* xnslots, uint64_t* nblocks);
+
+/* replaces qf_iterator/qfi_get/qfi_next (cqf/gqf.c:2474-2601): sorted (key,count)
+ * dump.  Pass cap=0 to obtain the entry count in *n.                             */
+int shq_iterate(shq_t h, uint64_t* keys, uint64_t* counts, size_t cap, size_t* n);
+
+/* ---- queries ----------------------------------------------------------------
+ * replaces qf_count_key_value_set_traveled (cqf/gqf.c:3092-3128) behind
+ * CQF_mt::count_key_value_set_traveled (cqf/CQF_mt.h:507-509), batched.
+ * was_traveled[i] = traveled bit before the call; duplicates inside one batch
+ * behave as if issued in index order.                                           */
+int shq_query_set_traveled(shq_t h, const uint64_t* keys, size_t n, uint64_t* counts,
+                           uint8_t* was_traveled);
+/* replaces qf_count_key_value (cqf/gqf.c:2442-2469): no side effect.             */
+int shq_query(shq_t h, const uint64_t* keys, size_t n, uint64_t* counts);
+
+/* ---- hashing (test hook) ------------------------------------------------------
+ * The key stream reads_to_kmers would insert for this chunk (NTPC64,
+ * base/nthash.hpp:295-309, then % range).  Order is unspecified: compare sorted. */
+int shq_hash_fastq_chunk(shq_t h, const char* text, size_t n, int K, uint64_t* keys, size_t cap,
+                         size_t* nkeys);
+
+/* ---- unitigs ------------------------------------------------------------------
+ * replaces find_unitigs_mt_master ... FASTA writer
+ * (src/contig_assembly.cpp:2034-2172, 3028-3218, 935-1084, 603-629): the whole
+ * Contiger device path over read text (seed k-mers) and this filter.
+ * Options mirror Params (base/Params.h:14-61): K, abundance_min (-s),
+ * solid_abundance_min (-x), solid_abundance_max (-X).                           */
+typedef struct {
+  int K;
+  int abundance_min;
+  int solid_abundance_min;
+  int solid_abundance_max;
+} shq_unitig_opts;
+typedef struct shq_unitigs_s* shq_unitigs_t;
+int shq_unitigs_begin(shq_t h, const shq_unitig_opts* opts, shq_unitigs_t* out);
+int shq_unitigs_add_reads(shq_unitigs_t u, const char* text, size_t n);   /* one chunk of FASTQ */
+int shq_unitigs_build(shq_unitigs_t u);
+int shq_unitigs_count(shq_unitigs_t u, size_t* n_unitigs, size_t* total_bases);
+int shq_unitigs_write_fasta(shq_unitigs_t u, const char* path);
+/* FASTA text into a caller buffer (cap=0: size query) */
+int shq_unitigs_fasta(shq_unitigs_t u, char* dst, size_t cap, size_t* written);
+void shq_unitigs_free(shq_unitigs_t u);
+
+/* ---- instrumentation ----------------------------------------------------------- */
+typedef struct {
+  uint64_t kernels_launched;   /* kernels launched by this handle so far */
+  uint64_t batches;            /* device batches processed */
+  uint64_t keys_hashed;        /* k-mer occurrences hashed */
+  double ms_hash_count, ms_scatter, ms_aggregate, ms_merge, ms_layout, ms_denoise; /* CUDA-event ms */
+  uint64_t h2d_bytes, d2h_bytes;
+} shq_stats;
+int shq_get_stats(shq_t h, shq_stats* out);
+int shq_reset_stats(shq_t h);
+void* shq_stream(shq_t h);           /* the cudaStream_t all work of this handle runs on */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHQ_H */

@@ -1,0 +1,271 @@
+"""sh-assembly_b200: thin Python binding (ctypes) over libshq.so, the B200-native C-ABI library
+that replaces SH-assembly's counting / deNoise / unitig hot path (include/shq.h).
+
+The directory name carries a hyphen (it mirrors the reference's name), so import it with
+    shq = importlib.import_module("sh-assembly_b200")
+This module is plumbing for tests and bench.py; the product is the C ABI.  There is no CPU
+fallback: if libshq.so is missing or no CUDA device is present, calls raise.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libshq.so")
+
+SEED = 2038074761  # src/CQF-deNoise.cpp:83
+
+STATUS = {0: "SHQ_OK", 1: "SHQ_ERR_ARG", 2: "SHQ_ERR_CUDA", 3: "SHQ_ERR_CAPACITY", 4: "SHQ_ERR_MALFORMED",
+          5: "SHQ_ERR_IO", 6: "SHQ_ERR_FORMAT", 7: "SHQ_ERR_COUNT_OVERFLOW", 8: "SHQ_ERR_STATE"}
+
+
+class ShqError(RuntimeError):
+    def __init__(self, status, detail=""):
+        self.status = status
+        super().__init__("%s: %s" % (STATUS.get(status, status), detail))
+
+
+class shq_stats(C.Structure):
+    _fields_ = [("kernels_launched", C.c_uint64), ("batches", C.c_uint64), ("keys_hashed", C.c_uint64),
+                ("ms_hash_count", C.c_double), ("ms_scatter", C.c_double), ("ms_aggregate", C.c_double),
+                ("ms_merge", C.c_double), ("ms_layout", C.c_double), ("ms_denoise", C.c_double),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
+class shq_unitig_opts(C.Structure):
+    _fields_ = [("K", C.c_int), ("abundance_min", C.c_int), ("solid_abundance_min", C.c_int),
+                ("solid_abundance_max", C.c_int)]
+
+
+def build(verbose=False):
+    """Compile libshq.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", HERE, "libshq.so"], capture_output=True, text=True)
+    if verbose or r.returncode:
+        print(r.stdout[-4000:], r.stderr[-4000:])
+    if r.returncode:
+        raise RuntimeError("building libshq.so failed")
+    return LIB_PATH
+
+
+_lib = None
+
+# every symbol include/shq.h declares
+EXPORTS = [
+    "shq_strerror", "shq_last_error", "shq_create", "shq_create_shard", "shq_destroy", "shq_set_denoise_schedule",
+    "shq_insert_fastq_chunk", "shq_insert_fastq_device", "shq_insert_keys", "shq_insert_keys_device", "shq_finish",
+    "shq_sync", "shq_counts", "shq_rounds_done", "shq_denoise", "shq_image_size", "shq_export_cqf", "shq_save",
+    "shq_load", "shq_load_image", "shq_geometry", "shq_iterate", "shq_query_set_traveled", "shq_query",
+    "shq_hash_fastq_chunk", "shq_unitigs_begin", "shq_unitigs_add_reads", "shq_unitigs_build", "shq_unitigs_count",
+    "shq_unitigs_write_fasta", "shq_unitigs_fasta", "shq_unitigs_free", "shq_get_stats", "shq_reset_stats", "shq_stream",
+]
+
+
+def lib():
+    """Load libshq.so.  Raises (loudly) if the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libshq.so is not built (%s); run __graft_entry__.build() -- there is no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        vp, u64, sz = C.c_void_p, C.c_uint64, C.c_size_t
+        L.shq_strerror.restype = C.c_char_p
+        L.shq_strerror.argtypes = [C.c_int]
+        L.shq_last_error.restype = C.c_char_p
+        L.shq_last_error.argtypes = [vp]
+        L.shq_create.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_int, C.POINTER(vp)]
+        L.shq_create_shard.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+        L.shq_destroy.argtypes = [vp]
+        L.shq_destroy.restype = None
+        L.shq_set_denoise_schedule.argtypes = [vp, u64, C.c_uint32, C.c_int]
+        L.shq_insert_fastq_chunk.argtypes = [vp, vp, sz, C.c_int]
+        L.shq_insert_fastq_device.argtypes = [vp, vp, sz, vp, sz, C.c_int]
+        L.shq_insert_keys.argtypes = [vp, vp, sz]
+        L.shq_insert_keys_device.argtypes = [vp, vp, sz]
+        L.shq_finish.argtypes = [vp]
+        L.shq_sync.argtypes = [vp]
+        L.shq_counts.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+        L.shq_rounds_done.argtypes = [vp, C.POINTER(C.c_uint32)]
+        L.shq_denoise.argtypes = [vp, C.POINTER(u64)]
+        L.shq_image_size.argtypes = [vp, C.POINTER(sz)]
+        L.shq_export_cqf.argtypes = [vp, vp, sz, C.POINTER(sz)]
+        L.shq_save.argtypes = [vp, C.c_char_p]
+        L.shq_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+        L.shq_load_image.argtypes = [vp, sz, C.c_int, C.POINTER(vp)]
+        L.shq_geometry.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+        L.shq_iterate.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
+        L.shq_query_set_traveled.argtypes = [vp, vp, sz, vp, vp]
+        L.shq_query.argtypes = [vp, vp, sz, vp]
+        L.shq_hash_fastq_chunk.argtypes = [vp, vp, sz, C.c_int, vp, sz, C.POINTER(sz)]
+        L.shq_unitigs_begin.argtypes = [vp, C.POINTER(shq_unitig_opts), C.POINTER(vp)]
+        L.shq_unitigs_add_reads.argtypes = [vp, vp, sz]
+        L.shq_unitigs_build.argtypes = [vp]
+        L.shq_unitigs_count.argtypes = [vp, C.POINTER(sz), C.POINTER(sz)]
+        L.shq_unitigs_write_fasta.argtypes = [vp, C.c_char_p]
+        L.shq_unitigs_fasta.argtypes = [vp, vp, sz, C.POINTER(sz)]
+        L.shq_unitigs_free.argtypes = [vp]
+        L.shq_unitigs_free.restype = None
+        L.shq_get_stats.argtypes = [vp, C.POINTER(shq_stats)]
+        L.shq_reset_stats.argtypes = [vp]
+        L.shq_stream.restype = vp
+        L.shq_stream.argtypes = [vp]
+        _lib = L
+    return _lib
+
+
+def _buf(b):
+    """(address, length, keepalive) of a bytes / bytearray / numpy buffer without copying."""
+    if isinstance(b, np.ndarray):
+        a = np.ascontiguousarray(b)
+        return a.ctypes.data, a.nbytes, a
+    a = np.frombuffer(b, np.uint8)
+    return a.ctypes.data, a.nbytes, a
+
+
+class CQF:
+    """Host-side mirror of the reference's class CQF_mt (cqf/CQF_mt.h:414-558) over the C ABI."""
+
+    def __init__(self, qb=None, hb=None, seed=SEED, device=0, shard=0, nshards=1, handle=None):
+        self.L = lib()
+        if handle is not None:
+            self.h = handle
+        else:
+            h = C.c_void_p()
+            self._check(self.L.shq_create_shard(qb, hb if hb is not None else qb + 8, seed, device, shard, nshards, C.byref(h)), None)
+            self.h = h
+        qb_, hb_, ns, xn, nb = C.c_int(), C.c_int(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.L.shq_geometry(self.h, C.byref(qb_), C.byref(hb_), C.byref(ns), C.byref(xn), C.byref(nb))
+        self.qb, self.hb, self.nslots, self.xnslots, self.nblocks = qb_.value, hb_.value, ns.value, xn.value, nb.value
+
+    def _check(self, rc, h="self"):
+        if rc:
+            detail = ""
+            hh = self.h if h == "self" else h
+            if hh:
+                detail = (self.L.shq_last_error(hh) or b"").decode()
+            raise ShqError(rc, detail)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.shq_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- counting
+    def set_denoise_schedule(self, trigger, rounds, end_denoise):
+        self._check(self.L.shq_set_denoise_schedule(self.h, trigger, rounds, 1 if end_denoise else 0))
+
+    def insert_fastq_chunk(self, text, K):
+        p, n, keep = _buf(text)
+        self._check(self.L.shq_insert_fastq_chunk(self.h, p, n, K))
+
+    def insert_fastq_device(self, d_ptr, n, chunk_ends, K):
+        ce = np.ascontiguousarray(chunk_ends, np.uint64)
+        self._check(self.L.shq_insert_fastq_device(self.h, d_ptr, n, ce.ctypes.data, len(ce), K))
+
+    def insert_keys(self, keys):
+        k = np.ascontiguousarray(keys, np.uint64)
+        self._check(self.L.shq_insert_keys(self.h, k.ctypes.data, len(k)))
+
+    def insert_keys_device(self, d_ptr, n):
+        self._check(self.L.shq_insert_keys_device(self.h, d_ptr, n))
+
+    def finish(self):
+        self._check(self.L.shq_finish(self.h))
+
+    def sync(self):
+        self._check(self.L.shq_sync(self.h))
+
+    def counts(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(self.L.shq_counts(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def rounds_done(self):
+        r = C.c_uint32()
+        self._check(self.L.shq_rounds_done(self.h, C.byref(r)))
+        return r.value
+
+    def denoise(self):
+        r = C.c_uint64()
+        self._check(self.L.shq_denoise(self.h, C.byref(r)))
+        return r.value
+
+    # --- image
+    def export(self) -> bytes:
+        n = C.c_size_t()
+        self._check(self.L.shq_image_size(self.h, C.byref(n)))
+        buf = np.empty(n.value, np.uint8)
+        w = C.c_size_t()
+        self._check(self.L.shq_export_cqf(self.h, buf.ctypes.data, n.value, C.byref(w)))
+        return buf[:w.value].tobytes()
+
+    def save(self, path):
+        self._check(self.L.shq_save(self.h, path.encode()))
+
+    @classmethod
+    def load(cls, path, device=0):
+        L = lib()
+        h = C.c_void_p()
+        rc = L.shq_load(path.encode(), device, C.byref(h))
+        if rc:
+            raise ShqError(rc, "shq_load(%s)" % path)
+        return cls(handle=h)
+
+    @classmethod
+    def from_bytes(cls, image, device=0):
+        L = lib()
+        h = C.c_void_p()
+        p, n, keep = _buf(image)
+        rc = L.shq_load_image(p, n, device, C.byref(h))
+        if rc:
+            raise ShqError(rc, "shq_load_image")
+        return cls(handle=h)
+
+    def iterate(self):
+        n = C.c_size_t()
+        self._check(self.L.shq_iterate(self.h, None, None, 0, C.byref(n)))
+        k = np.zeros(n.value, np.uint64)
+        c = np.zeros(n.value, np.uint64)
+        if n.value:
+            self._check(self.L.shq_iterate(self.h, k.ctypes.data, c.ctypes.data, n.value, C.byref(n)))
+        return k, c
+
+    # --- queries
+    def query_set_traveled(self, keys):
+        k = np.ascontiguousarray(keys, np.uint64)
+        cnt = np.zeros(len(k), np.uint64)
+        was = np.zeros(len(k), np.uint8)
+        self._check(self.L.shq_query_set_traveled(self.h, k.ctypes.data, len(k), cnt.ctypes.data, was.ctypes.data))
+        return cnt, was
+
+    def query(self, keys):
+        k = np.ascontiguousarray(keys, np.uint64)
+        cnt = np.zeros(len(k), np.uint64)
+        self._check(self.L.shq_query(self.h, k.ctypes.data, len(k), cnt.ctypes.data))
+        return cnt
+
+    def hash_fastq_chunk(self, text, K):
+        p, n, keep = _buf(text)
+        nk = C.c_size_t()
+        cap = max(16, n)
+        out = np.zeros(cap, np.uint64)
+        self._check(self.L.shq_hash_fastq_chunk(self.h, p, n, K, out.ctypes.data, cap, C.byref(nk)))
+        return out[:nk.value]
+
+    def stats(self):
+        s = shq_stats()
+        self._check(self.L.shq_get_stats(self.h, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in s._fields_}
+
+    def reset_stats(self):
+        self._check(self.L.shq_reset_stats(self.h))
+
+    def stream(self):
+        return self.L.shq_stream(self.h)

@@ -1,0 +1,903 @@
+// shq_core.cu -- handle, batching, deNoise schedule and the C ABI of libshq.so (include/shq.h).
+//
+// Host-side orchestration of the device pipeline that replaces CQF_mt::build_KmerSpectrum /
+// fastq_to_uint64kmers_prod / reads_to_kmers / qf_insert_advance / qf_clean_singleton*
+// (reference cqf/CQF_mt.h:610-731, 821-931, 959-1039; cqf/gqf.c).  No CPU fallback: every
+// data-path step below is a CUDA kernel from shq_hash.cuh / shq_aggregate.cuh / shq_layout.cuh.
+#include <math.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "shq_aggregate.cuh"
+#include "shq_common.cuh"
+#include "shq_hash.cuh"
+#include "shq_layout.cuh"
+#include "shq_scan.cuh"
+
+using namespace shq;
+
+struct PhaseTimer;
+
+struct shq_handle_s {
+  int device = 0;
+  int qb = 0, hb = 0;
+  uint32_t seed = 0;
+  int shard = 0, nshards = 1;
+  uint64_t nslots = 0, xnslots = 0, nblocks = 0;   // whole-filter geometry (gqf.c:2187-2290)
+  uint64_t key_lo = 0, key_hi = 0;                 // keys owned by this shard
+  cudaStream_t stream = nullptr;
+  std::string last_error;
+
+  // resident state: sorted distinct keys + counts
+  DevBuf st_keys, st_counts, st_keys2, st_counts2;
+  size_t n_state = 0;
+  uint64_t ndistinct = 0, nelts = 0;               // runtime counters (CQF_mt.h:279-280)
+
+  // image (materialised lazily); for loaded filters the image is authoritative
+  DevBuf image;
+  bool image_valid = false;
+  bool image_only = false;       // loaded from .cqf and not yet decoded into state
+  uint8_t header[128];           // metadata of a loaded image
+  bool has_header = false;
+
+  // deNoise schedule
+  uint64_t trigger = 0; uint32_t rounds_left = 0; bool end_denoise = false; uint32_t rounds_done = 0;
+  bool finished = false;
+
+  // host staging of chunks
+  char* h_stage = nullptr; size_t h_stage_cap = 0, h_stage_fill = 0;
+  std::vector<uint64_t> stage_chunk_ends;
+  int stage_K = 0;
+  size_t max_batch_bytes = (size_t)1 << 30;
+
+  // scratch
+  DevBuf d_text, d_nl_tiles, d_nl_pos, d_chunk_ends, d_chunk_line_end, d_chunk_keys, d_chunk_hist, d_slow;
+  DevBuf d_hist, d_tot, d_binoff, d_packed, d_tmp_keys, d_tmp_counts, d_tmp_chunk, d_nout, d_occ, d_dense_off;
+  DevBuf d_run_keys, d_run_counts, d_run_chunk, d_split, d_heads, d_heads64, d_scan_scratch, d_misc;
+  DevBuf d_pairs, d_pos, d_flags, d_keep, d_q_in, d_q_cnt, d_q_was;
+  int* d_err = nullptr;          // device error flag
+  void* h_pinned = nullptr;      // small pinned readback area (4 KiB + chunk hist)
+  size_t h_pinned_cap = 0;
+
+  shq_stats stats;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+struct Phase {
+  shq_handle_s* h; double* acc;
+  Phase(shq_handle_s* h_, double* acc_) : h(h_), acc(acc_) { cudaEventRecord(h->ev0, h->stream); }
+  ~Phase() {
+    cudaEventRecord(h->ev1, h->stream);
+    cudaEventSynchronize(h->ev1);
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    *acc += ms;
+  }
+};
+
+inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+void check_err_flag(shq_handle_s* h) {
+  int e = 0;
+  SHQ_CUDA(cudaMemcpyAsync(&e, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  SHQ_CUDA(cudaStreamSynchronize(h->stream));
+  h->stats.d2h_bytes += 4;
+  if (e) {
+    int z = 0;
+    SHQ_CUDA(cudaMemcpyAsync(h->d_err, &z, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    SHQ_FAIL(e, "device reported: %s", shq_strerror(e));
+  }
+}
+
+void* pinned(shq_handle_s* h, size_t bytes) {
+  if (bytes > h->h_pinned_cap) {
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    h->h_pinned = nullptr;
+    SHQ_CUDA(cudaMallocHost(&h->h_pinned, bytes + 4096));
+    h->h_pinned_cap = bytes + 4096;
+  }
+  return h->h_pinned;
+}
+
+template <class T>
+T read_scalar(shq_handle_s* h, const T* d) {
+  T* p = (T*)pinned(h, sizeof(T));
+  SHQ_CUDA(cudaMemcpyAsync(p, d, sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+  SHQ_CUDA(cudaStreamSynchronize(h->stream));
+  h->stats.d2h_bytes += sizeof(T);
+  return *p;
+}
+
+// ---------------------------------------------------------------------------
+// A "run" = sorted distinct (key, count[, first chunk]) produced from one batch of binned keys.
+struct BatchBins {
+  int n_bins = 0, lb = 0, rows = 0;
+  uint32_t n_keys = 0;          // occurrences scattered
+  bool armed = false;
+  int nchunks = 0;
+};
+
+int pick_bin_bits(shq_handle_s* h, uint64_t est_keys, int chunk_bits_needed) {
+  // aim at ~16K occurrences per bin, 2^8 .. 2^14 bins, and (key bits below the bin) + chunk bits <= 32
+  int shard_bits = 0; while ((1 << shard_bits) < h->nshards) shard_bits++;
+  int local_bits = h->hb - shard_bits;
+  int pb = 8;
+  while (pb < 14 && (est_keys >> pb) > 16384) pb++;
+  if (pb > local_bits) pb = local_bits;
+  while (local_bits - pb + chunk_bits_needed > 32 && pb < 16) pb++;
+  if (local_bits - pb + chunk_bits_needed > 32) SHQ_FAIL(SHQ_ERR_ARG, "hb=%d too wide for 32-bit packed keys", h->hb);
+  return pb;
+}
+
+// Both hashing passes over the batch text (or a raw key array): count -> offsets -> scatter.
+// On return d_packed holds the binned words and d_binoff the (n_bins+1) bin offsets.
+void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_t* h_chunk_ends, int nchunks, int K,
+               const uint64_t* d_keys, size_t n_keys_in, bool armed, BatchBins* bb) {
+  cudaStream_t st = h->stream;
+  uint64_t& L = h->stats.kernels_launched;
+  HashParams hp{};
+  uint32_t n_reads = 0;
+  const bool from_text = d_keys == nullptr;
+  if (from_text) {
+    if (K < 1 || K > kTilePos - 32) SHQ_FAIL(SHQ_ERR_ARG, "K=%d outside [1,%d]", K, kTilePos - 32);
+    if (n_text >= ((size_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "batch text of %zu bytes exceeds 4 GiB", n_text);
+    if (reinterpret_cast<uintptr_t>(d_text) & 15) SHQ_FAIL(SHQ_ERR_ARG, "device text must be 16-byte aligned");
+    // K1: newline index
+    unsigned ntiles = cdiv(n_text, kNlTile);
+    h->d_nl_tiles.reserve((size_t)(ntiles + 1) * 4);
+    nl_count_kernel<<<ntiles, kNlThreads, 0, st>>>(d_text, n_text, h->d_nl_tiles.as<uint32_t>()); L++;
+    h->d_misc.reserve(256);
+    exclusive_scan_inplace<SumU32>(h->d_nl_tiles.as<uint32_t>(), ntiles, h->d_scan_scratch, st, h->d_misc.as<uint32_t>(), &L);
+    uint32_t n_lines = read_scalar(h, h->d_misc.as<uint32_t>());
+    h->d_nl_pos.reserve((size_t)(n_lines + 4) * 4);
+    nl_write_kernel<<<ntiles, kNlThreads, 0, st>>>(d_text, n_text, h->d_nl_tiles.as<uint32_t>(), h->d_nl_pos.as<uint32_t>()); L++;
+    // per-chunk validation + chunk -> line map
+    h->d_chunk_ends.reserve((size_t)nchunks * 8 + 8);
+    h->d_chunk_line_end.reserve((size_t)nchunks * 4 + 4);
+    SHQ_CUDA(cudaMemcpyAsync(h->d_chunk_ends.p, h_chunk_ends, (size_t)nchunks * 8, cudaMemcpyHostToDevice, st));
+    h->stats.h2d_bytes += (size_t)nchunks * 8;
+    chunk_validate_kernel<<<cdiv(nchunks, 128), 128, 0, st>>>(d_text, h->d_nl_pos.as<uint32_t>(), n_lines, h->d_chunk_ends.as<uint64_t>(),
+                                                            nchunks, h->d_chunk_line_end.as<uint32_t>(), h->d_err); L++;
+    check_err_flag(h);
+    if (n_lines & 3) SHQ_FAIL(SHQ_ERR_MALFORMED, "batch holds %u lines, not a multiple of 4", n_lines);
+    n_reads = n_lines / 4;
+    hp.text = d_text; hp.nl_pos = h->d_nl_pos.as<uint32_t>(); hp.n_reads = n_reads; hp.K = K;
+  }
+  // geometry of the bins
+  int chunk_bits = 0;
+  if (armed) { while ((1 << chunk_bits) < nchunks) chunk_bits++; if (chunk_bits > 15) SHQ_FAIL(SHQ_ERR_ARG, "too many chunks in one batch"); }
+  uint64_t est = from_text ? (uint64_t)(n_text / 2) : (uint64_t)n_keys_in;
+  int pb = pick_bin_bits(h, est / (uint64_t)h->nshards + 1, chunk_bits);
+  int shard_bits = 0; while ((1 << shard_bits) < h->nshards) shard_bits++;
+  int lb = h->hb - shard_bits - pb;
+  int n_bins = 1 << pb;
+  hp.hb = h->hb; hp.lb = lb; hp.key_lo = h->key_lo; hp.key_hi = h->key_hi; hp.n_bins = n_bins;
+  hp.nchunks = nchunks;
+  hp.chunk_line_end = (armed && from_text) ? h->d_chunk_line_end.as<uint32_t>() : nullptr;
+  const int G = 2 * kNumSMs;           // persistent CTAs, two per SM
+  const int rows = G + 1;              // + one row for the serial 'N' path
+  h->d_hist.reserve((size_t)rows * n_bins * 4);
+  h->d_tot.reserve((size_t)(n_bins + 1) * 4);
+  h->d_binoff.reserve((size_t)(n_bins + 2) * 4);
+  h->d_chunk_keys.reserve((size_t)(nchunks + 1) * 4);
+  h->d_slow.reserve((size_t)(n_reads + 2) * 4 + 16);
+  uint32_t* slow_count = h->d_slow.as<uint32_t>();
+  hp.slow_count = slow_count; hp.slow_list = slow_count + 4;
+  hp.chunk_keys = (armed && from_text) ? h->d_chunk_keys.as<uint32_t>() : nullptr;
+  SHQ_CUDA(cudaMemsetAsync(h->d_hist.p, 0, (size_t)rows * n_bins * 4, st));
+  SHQ_CUDA(cudaMemsetAsync(h->d_chunk_keys.p, 0, (size_t)(nchunks + 1) * 4, st));
+  SHQ_CUDA(cudaMemsetAsync(slow_count, 0, 16, st));
+  Sink sk{};
+  uint32_t n_slow = 0;
+  size_t smem_text = (((size_t)n_bins * 4 + 15) & ~(size_t)15) + (size_t)kHashWarps * 2 * (kTilePos + 1) * 8;
+  size_t smem_keys = (size_t)n_bins * 4;
+  {
+    Phase ph(h, &h->stats.ms_hash_count);
+    if (from_text) {
+      SHQ_CUDA(cudaFuncSetAttribute(hash_reads_kernel<kSinkCount>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_text));
+      hash_reads_kernel<kSinkCount><<<G, kHashThreads, smem_text, st>>>(hp, sk, h->d_hist.as<uint32_t>(), nullptr); L++;
+      n_slow = read_scalar(h, slow_count);
+      if (n_slow) {
+        Sink s2 = sk; s2.bins = h->d_hist.as<uint32_t>() + (size_t)G * n_bins;
+        hash_slow_reads_kernel<kSinkCount><<<cdiv(n_slow, 128), 128, 0, st>>>(hp, s2, n_slow); L++;
+      }
+    } else {
+      SHQ_CUDA(cudaFuncSetAttribute(hash_keys_kernel<kSinkCount>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_keys));
+      hash_keys_kernel<kSinkCount><<<G, 256, smem_keys, st>>>(d_keys, n_keys_in, hp, sk, h->d_hist.as<uint32_t>(), nullptr); L++;
+    }
+    hist_column_scan_kernel<<<cdiv(n_bins, 128), 128, 0, st>>>(h->d_hist.as<uint32_t>(), rows, n_bins, h->d_tot.as<uint32_t>()); L++;
+    SHQ_CUDA(cudaMemcpyAsync(h->d_binoff.p, h->d_tot.p, (size_t)n_bins * 4, cudaMemcpyDeviceToDevice, st));
+    exclusive_scan_inplace<SumU32>(h->d_binoff.as<uint32_t>(), n_bins, h->d_scan_scratch, st, h->d_binoff.as<uint32_t>() + n_bins, &L);
+  }
+  uint32_t n_keys = read_scalar(h, h->d_binoff.as<uint32_t>() + n_bins);
+  h->d_packed.reserve((size_t)(n_keys + 4) * 4);
+  {
+    Phase ph(h, &h->stats.ms_scatter);
+    sk.packed = h->d_packed.as<uint32_t>();
+    if (from_text) {
+      SHQ_CUDA(cudaFuncSetAttribute(hash_reads_kernel<kSinkScatter>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_text));
+      hash_reads_kernel<kSinkScatter><<<G, kHashThreads, smem_text, st>>>(hp, sk, h->d_hist.as<uint32_t>(), h->d_binoff.as<uint32_t>()); L++;
+      if (n_slow) {
+        uint32_t* row = h->d_hist.as<uint32_t>() + (size_t)G * n_bins;
+        add_bin_off_kernel<<<cdiv(n_bins, 128), 128, 0, st>>>(row, h->d_binoff.as<uint32_t>(), n_bins); L++;
+        Sink s2 = sk; s2.bins = row;
+        hash_slow_reads_kernel<kSinkScatter><<<cdiv(n_slow, 128), 128, 0, st>>>(hp, s2, n_slow); L++;
+      }
+    } else {
+      SHQ_CUDA(cudaFuncSetAttribute(hash_keys_kernel<kSinkScatter>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_keys));
+      hash_keys_kernel<kSinkScatter><<<G, 256, smem_keys, st>>>(d_keys, n_keys_in, hp, sk, h->d_hist.as<uint32_t>(), h->d_binoff.as<uint32_t>()); L++;
+    }
+  }
+  SHQ_CUDA(cudaGetLastError());
+  bb->n_bins = n_bins; bb->lb = lb; bb->rows = rows; bb->n_keys = n_keys; bb->armed = armed; bb->nchunks = nchunks;
+  h->stats.keys_hashed += n_keys;
+}
+
+// Aggregate the binned batch (chunks [clo, chi]) into a dense sorted run in d_run_*; returns its size
+// and the number of occurrences it covers.
+void aggregate_bins(shq_handle_s* h, const BatchBins& bb, uint32_t clo, uint32_t chi, size_t* n_run, uint64_t* n_occ) {
+  cudaStream_t st = h->stream;
+  uint64_t& L = h->stats.kernels_launched;
+  Phase ph(h, &h->stats.ms_aggregate);
+  size_t cap = (size_t)bb.n_keys + 4;
+  h->d_tmp_keys.reserve(cap * 8); h->d_tmp_counts.reserve(cap * 4);
+  if (bb.armed) h->d_tmp_chunk.reserve(cap * 2);
+  h->d_nout.reserve((size_t)(bb.n_bins + 1) * 4); h->d_occ.reserve((size_t)(bb.n_bins + 1) * 4);
+  h->d_dense_off.reserve((size_t)(bb.n_bins + 2) * 4);
+  SHQ_CUDA(cudaFuncSetAttribute(bin_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggSmemBytes));
+  bin_aggregate_kernel<<<bb.n_bins, kAggThreads, kAggSmemBytes, st>>>(
+      h->d_packed.as<uint32_t>(), h->d_binoff.as<uint32_t>(), bb.lb, h->key_lo, clo, chi, h->d_tmp_keys.as<uint64_t>(),
+      h->d_tmp_counts.as<uint32_t>(), bb.armed ? h->d_tmp_chunk.as<uint16_t>() : nullptr, h->d_nout.as<uint32_t>(),
+      h->d_occ.as<uint32_t>()); L++;
+  SHQ_CUDA(cudaMemcpyAsync(h->d_dense_off.p, h->d_nout.p, (size_t)bb.n_bins * 4, cudaMemcpyDeviceToDevice, st));
+  exclusive_scan_inplace<SumU32>(h->d_dense_off.as<uint32_t>(), bb.n_bins, h->d_scan_scratch, st,
+                                 h->d_dense_off.as<uint32_t>() + bb.n_bins, &L);
+  // occurrences covered (sum of occ_out): reuse d_occ with a scan total
+  h->d_misc.reserve(256);
+  exclusive_scan_inplace<SumU32>(h->d_occ.as<uint32_t>(), bb.n_bins, h->d_scan_scratch, st, h->d_misc.as<uint32_t>(), &L);
+  uint32_t nd = read_scalar(h, h->d_dense_off.as<uint32_t>() + bb.n_bins);
+  uint32_t occ = read_scalar(h, h->d_misc.as<uint32_t>());
+  h->d_run_keys.reserve((size_t)(nd + 4) * 8); h->d_run_counts.reserve((size_t)(nd + 4) * 4);
+  if (bb.armed) h->d_run_chunk.reserve((size_t)(nd + 4) * 2);
+  compact_bins_kernel<<<bb.n_bins, 256, 0, st>>>(h->d_binoff.as<uint32_t>(), h->d_dense_off.as<uint32_t>(), h->d_nout.as<uint32_t>(),
+                                                h->d_tmp_keys.as<uint64_t>(), h->d_tmp_counts.as<uint32_t>(),
+                                                bb.armed ? h->d_tmp_chunk.as<uint16_t>() : nullptr, h->d_run_keys.as<uint64_t>(),
+                                                h->d_run_counts.as<uint32_t>(), bb.armed ? h->d_run_chunk.as<uint16_t>() : nullptr); L++;
+  SHQ_CUDA(cudaGetLastError());
+  *n_run = nd; *n_occ = occ;
+}
+
+// Merge the run into the state.  If chunk_hist_host != null (armed) the per-chunk histogram of NEW keys is
+// returned before anything is committed; commit=false stops after that (boundary search).
+// Returns number of new keys.
+uint64_t merge_run(shq_handle_s* h, size_t n_run, bool armed, int nchunks, std::vector<uint32_t>* chunk_hist_host, bool commit) {
+  cudaStream_t st = h->stream;
+  uint64_t& L = h->stats.kernels_launched;
+  Phase ph(h, &h->stats.ms_merge);
+  size_t na = h->n_state, nb = n_run;
+  size_t total = na + nb;
+  size_t ntiles = (total + kMergeTile - 1) / kMergeTile;
+  if (ntiles == 0) { if (chunk_hist_host) chunk_hist_host->assign(nchunks, 0); return 0; }
+  h->d_split.reserve((ntiles + 2) * 8);
+  h->d_heads.reserve((ntiles + 2) * 4);
+  h->d_heads64.reserve((ntiles + 2) * 8);
+  const uint64_t* A = h->st_keys.as<uint64_t>(); const uint32_t* Ac = h->st_counts.as<uint32_t>();
+  const uint64_t* B = h->d_run_keys.as<uint64_t>(); const uint32_t* Bc = h->d_run_counts.as<uint32_t>();
+  const uint16_t* Bch = armed ? h->d_run_chunk.as<uint16_t>() : nullptr;
+  merge_partition_kernel<<<cdiv(ntiles + 1, 128), 128, 0, st>>>(A, na, B, nb, h->d_split.as<uint64_t>(), ntiles); L++;
+  uint32_t* d_hist = nullptr;
+  if (armed) {
+    h->d_chunk_hist.reserve((size_t)(nchunks + 1) * 4);
+    d_hist = h->d_chunk_hist.as<uint32_t>();
+    SHQ_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)(nchunks + 1) * 4, st));
+  }
+  merge_tiles_kernel<false><<<(unsigned)ntiles, kMergeThreads, 0, st>>>(A, Ac, na, B, Bc, Bch, nb, h->d_split.as<uint64_t>(),
+                                                                       h->d_heads.as<uint32_t>(), nullptr, nullptr, nullptr, d_hist, h->d_err); L++;
+  widen_u32_kernel<<<cdiv(ntiles, 256), 256, 0, st>>>(h->d_heads.as<uint32_t>(), h->d_heads64.as<uint64_t>(), ntiles); L++;
+  exclusive_scan_inplace<SumU64>(h->d_heads64.as<uint64_t>(), ntiles, h->d_scan_scratch, st, h->d_heads64.as<uint64_t>() + ntiles, &L);
+  uint64_t n_out = read_scalar(h, h->d_heads64.as<uint64_t>() + ntiles);
+  if (armed && chunk_hist_host) {
+    uint32_t* p = (uint32_t*)pinned(h, (size_t)nchunks * 4);
+    SHQ_CUDA(cudaMemcpyAsync(p, d_hist, (size_t)nchunks * 4, cudaMemcpyDeviceToHost, st));
+    SHQ_CUDA(cudaStreamSynchronize(st));
+    h->stats.d2h_bytes += (size_t)nchunks * 4;
+    chunk_hist_host->assign(p, p + nchunks);
+  }
+  uint64_t n_new = n_out - na;
+  if (!commit) return n_new;
+  if (n_out >= ((uint64_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "more than 2^32 distinct keys in one shard");
+  h->st_keys2.reserve((n_out + 4) * 8); h->st_counts2.reserve((n_out + 4) * 4);
+  merge_tiles_kernel<true><<<(unsigned)ntiles, kMergeThreads, 0, st>>>(A, Ac, na, B, Bc, Bch, nb, h->d_split.as<uint64_t>(), nullptr,
+                                                                      h->d_heads64.as<uint64_t>(), h->st_keys2.as<uint64_t>(),
+                                                                      h->st_counts2.as<uint32_t>(), nullptr, h->d_err); L++;
+  SHQ_CUDA(cudaGetLastError());
+  std::swap(h->st_keys, h->st_keys2); std::swap(h->st_counts, h->st_counts2);
+  h->n_state = n_out;
+  h->image_valid = false;
+  return n_new;
+}
+
+// positions of every state entry in the canonical layout -> d_pos; returns one past the last used slot
+uint64_t compute_positions(shq_handle_s* h) {
+  cudaStream_t st = h->stream;
+  uint64_t& L = h->stats.kernels_launched;
+  size_t n = h->n_state;
+  if (n == 0) return 0;
+  h->d_pairs.reserve((n + 4) * sizeof(MaxPlus)); h->d_pos.reserve((n + 4) * 8);
+  uint64_t q0 = h->key_lo >> 8;
+  layout_pairs_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->st_keys.as<uint64_t>(), h->st_counts.as<uint32_t>(), n, q0, h->d_pairs.as<MaxPlus>()); L++;
+  h->d_misc.reserve(256);
+  exclusive_scan_inplace<MaxPlusOp>(h->d_pairs.as<MaxPlus>(), n, h->d_scan_scratch, st, h->d_misc.as<MaxPlus>(), &L);
+  layout_pos_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->st_keys.as<uint64_t>(), n, q0, h->d_pairs.as<MaxPlus>(), 0, h->d_pos.as<uint64_t>()); L++;
+  MaxPlus tot = read_scalar(h, h->d_misc.as<MaxPlus>());
+  long long e = tot.a > tot.b ? tot.a : tot.b;   // f_total(0)
+  return (uint64_t)e;
+}
+
+void ensure_state(shq_handle_s* h);
+
+void materialise(shq_handle_s* h) {
+  if (h->image_valid) return;
+  cudaStream_t st = h->stream;
+  uint64_t& L = h->stats.kernels_launched;
+  Phase ph(h, &h->stats.ms_layout);
+  uint64_t used = compute_positions(h);
+  if (used > h->xnslots) SHQ_FAIL(SHQ_ERR_CAPACITY, "filter over-full: layout needs slot %llu but xnslots = %llu",
+                                  (unsigned long long)used, (unsigned long long)h->xnslots);
+  size_t bytes = (size_t)h->nblocks * kBlockBytes;
+  size_t tiles = (h->nblocks + kTileBlocks - 1) / kTileBlocks;
+  h->image.reserve(tiles * kTileBytes + 16);
+  image_tiles_kernel<<<(unsigned)tiles, kImgThreads, 0, st>>>(h->st_keys.as<uint64_t>(), h->st_counts.as<uint32_t>(), h->d_pos.as<uint64_t>(),
+                                                            h->n_state, h->key_lo >> 8, h->nblocks, h->image.as<uint8_t>()); L++;
+  SHQ_CUDA(cudaGetLastError());
+  (void)bytes;
+  h->image_valid = true;
+}
+
+// image -> state (after shq_load)
+void ensure_state(shq_handle_s* h) {
+  if (!h->image_only) return;
+  cudaStream_t st = h->stream;
+  uint64_t& L = h->stats.kernels_launched;
+  ImageView im{h->image.as<uint8_t>(), h->nblocks, h->xnslots, 0};
+  size_t nb = h->nblocks;
+  h->d_heads.reserve((nb + 2) * 4); h->d_heads64.reserve((nb + 2) * 8);
+  decode_blocks_kernel<false><<<cdiv(nb, 128), 128, 0, st>>>(im, h->d_heads.as<uint32_t>(), nullptr, nullptr, nullptr, h->d_err); L++;
+  widen_u32_kernel<<<cdiv(nb, 256), 256, 0, st>>>(h->d_heads.as<uint32_t>(), h->d_heads64.as<uint64_t>(), nb); L++;
+  exclusive_scan_inplace<SumU64>(h->d_heads64.as<uint64_t>(), nb, h->d_scan_scratch, st, h->d_heads64.as<uint64_t>() + nb, &L);
+  uint64_t n = read_scalar(h, h->d_heads64.as<uint64_t>() + nb);
+  h->st_keys.reserve((n + 4) * 8); h->st_counts.reserve((n + 4) * 4);
+  decode_blocks_kernel<true><<<cdiv(nb, 128), 128, 0, st>>>(im, nullptr, h->d_heads64.as<uint64_t>(), h->st_keys.as<uint64_t>(),
+                                                          h->st_counts.as<uint32_t>(), h->d_err); L++;
+  check_err_flag(h);
+  h->n_state = n;
+  h->image_only = false;
+}
+
+uint64_t denoise_round(shq_handle_s* h) {
+  ensure_state(h);
+  cudaStream_t st = h->stream;
+  uint64_t& L = h->stats.kernels_launched;
+  Phase ph(h, &h->stats.ms_denoise);
+  size_t n = h->n_state;
+  h->rounds_done++;
+  if (n == 0) return 0;
+  if (h->nshards != 1) SHQ_FAIL(SHQ_ERR_STATE, "deNoise on a sharded handle is driven by the multi-GPU layer");
+  compute_positions(h);
+  uint32_t keep_cap = (uint32_t)(h->nslots >> 20) + 8;
+  h->d_keep.reserve((size_t)(keep_cap + 4) * 4);
+  uint32_t* n_keep = h->d_keep.as<uint32_t>(); uint32_t* keep_idx = n_keep + 4;
+  denoise_ranges_kernel<<<1, 32, 0, st>>>(h->st_keys.as<uint64_t>(), h->st_counts.as<uint32_t>(), h->d_pos.as<uint64_t>(), n, h->nslots,
+                                        h->xnslots, keep_idx, n_keep, keep_cap); L++;
+  h->d_flags.reserve((n + 4) * 8);
+  denoise_flag_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->st_counts.as<uint32_t>(), h->d_flags.as<uint64_t>(), n); L++;
+  denoise_keep_kernel<<<cdiv(keep_cap, 128), 128, 0, st>>>(keep_idx, n_keep, h->d_flags.as<uint64_t>()); L++;
+  exclusive_scan_inplace<SumU64>(h->d_flags.as<uint64_t>(), n, h->d_scan_scratch, st, h->d_flags.as<uint64_t>() + n, &L);
+  uint64_t kept = read_scalar(h, h->d_flags.as<uint64_t>() + n);
+  h->st_keys2.reserve((kept + 4) * 8); h->st_counts2.reserve((kept + 4) * 4);
+  denoise_compact_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->st_keys.as<uint64_t>(), h->st_counts.as<uint32_t>(), h->d_flags.as<uint64_t>(), n, kept,
+                                                     h->st_keys2.as<uint64_t>(), h->st_counts2.as<uint32_t>()); L++;
+  SHQ_CUDA(cudaGetLastError());
+  std::swap(h->st_keys, h->st_keys2); std::swap(h->st_counts, h->st_counts2);
+  uint64_t removed = n - kept;
+  h->n_state = kept;
+  h->nelts -= removed; h->ndistinct -= removed;    // CQF_mt.h:1037-1038
+  h->image_valid = false;
+  return removed;
+}
+
+// One device batch: text of nchunks reference chunks (or raw keys) -> state, honouring the schedule.
+void process_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_t* chunk_ends, int nchunks, int K,
+                   const uint64_t* d_keys, size_t n_keys_in) {
+  ensure_state(h);
+  if (h->finished) SHQ_FAIL(SHQ_ERR_STATE, "handle already finished");
+  const bool from_text = d_keys == nullptr;
+  if (from_text && (n_text == 0 || nchunks == 0)) return;
+  if (!from_text && n_keys_in == 0) return;
+  bool armed = from_text && h->rounds_left > 0;
+  BatchBins bb;
+  bin_batch(h, d_text, n_text, chunk_ends, nchunks, K, d_keys, n_keys_in, armed, &bb);
+  h->stats.batches++;
+  if (bb.n_keys == 0) return;
+  std::vector<uint32_t> chunk_keys;
+  if (armed) {
+    uint32_t* p = (uint32_t*)pinned(h, (size_t)nchunks * 4);
+    SHQ_CUDA(cudaMemcpyAsync(p, h->d_chunk_keys.p, (size_t)nchunks * 4, cudaMemcpyDeviceToHost, h->stream));
+    SHQ_CUDA(cudaStreamSynchronize(h->stream));
+    chunk_keys.assign(p, p + nchunks);
+  }
+  uint32_t clo = 0;
+  const uint32_t last = (uint32_t)(nchunks > 0 ? nchunks - 1 : 0);
+  for (;;) {
+    size_t n_run = 0; uint64_t n_occ = 0;
+    bool track = armed && h->rounds_left > 0;
+    aggregate_bins(h, bb, clo, armed ? last : 0xFFFFFFFFu, &n_run, &n_occ);
+    if (!track) {
+      uint64_t n_new = merge_run(h, n_run, armed, nchunks, nullptr, true);
+      h->ndistinct += n_new; h->nelts += n_occ;
+      break;
+    }
+    // find the first chunk c* >= clo after which ndistinct >= trigger (t=1 rule, CQF_mt.h:837)
+    std::vector<uint32_t> hist;
+    merge_run(h, n_run, true, nchunks, &hist, false);
+    uint64_t nd = h->ndistinct; int cstar = -1;
+    for (uint32_t c = clo; c <= last; c++) { nd += hist[c]; if (nd >= h->trigger) { cstar = (int)c; break; } }
+    if (cstar < 0 || (uint32_t)cstar == last) {
+      uint64_t n_new = merge_run(h, n_run, true, nchunks, nullptr, true);
+      h->ndistinct += n_new; h->nelts += n_occ;
+      if (cstar >= 0) { h->rounds_left--; denoise_round(h); }
+      break;
+    }
+    // commit chunks [clo, c*] only, sweep, then replay the rest of the batch
+    aggregate_bins(h, bb, clo, (uint32_t)cstar, &n_run, &n_occ);
+    uint64_t n_new = merge_run(h, n_run, true, nchunks, nullptr, true);
+    h->ndistinct += n_new; h->nelts += n_occ;
+    h->rounds_left--;
+    denoise_round(h);
+    clo = (uint32_t)cstar + 1;
+  }
+  check_err_flag(h);
+}
+
+void flush_stage(shq_handle_s* h) {
+  if (h->h_stage_fill == 0) { h->stage_chunk_ends.clear(); return; }
+  size_t n = h->h_stage_fill;
+  h->d_text.reserve(n + 64);
+  SHQ_CUDA(cudaMemcpyAsync(h->d_text.p, h->h_stage, n, cudaMemcpyHostToDevice, h->stream));
+  h->stats.h2d_bytes += n;
+  std::vector<uint64_t> ends;
+  ends.swap(h->stage_chunk_ends);
+  h->h_stage_fill = 0;
+  process_batch(h, h->d_text.as<char>(), n, ends.data(), (int)ends.size(), h->stage_K, nullptr, 0);
+}
+
+int guard(shq_handle_s* h, void (*fn)(shq_handle_s*, void*), void* arg) {
+  try {
+    if (h) SHQ_CUDA(cudaSetDevice(h->device));
+    fn(h, arg);
+    return SHQ_OK;
+  } catch (const CudaError& e) {
+    char b[512]; snprintf(b, sizeof b, "%s: %s (%s:%d)", e.what, cudaGetErrorString(e.err), e.file, e.line);
+    if (h) h->last_error = b; else fprintf(stderr, "shq: %s\n", b);
+    return SHQ_ERR_CUDA;
+  } catch (const StatusError& e) {
+    if (h) h->last_error = e.msg; else fprintf(stderr, "shq: %s\n", e.msg.c_str());
+    return e.status;
+  } catch (const std::bad_alloc&) {
+    if (h) h->last_error = "host allocation failed";
+    return SHQ_ERR_ARG;
+  }
+}
+#define SHQ_API_BEGIN(h) return guard((h), [](shq_handle_s* h, void* argp) { auto& a = *(decltype(args)*)argp;
+#define SHQ_API_END }, &args);
+
+void init_handle(shq_handle_s* h, int qb, int hb, uint32_t seed, int device, int shard, int nshards) {
+  if (qb < 1 || qb > 40 || hb - qb != 8) SHQ_FAIL(SHQ_ERR_ARG, "need 1 <= qb <= 40 and hb - qb == 8 (got qb=%d hb=%d)", qb, hb);
+  if (nshards < 1 || (nshards & (nshards - 1)) || shard < 0 || shard >= nshards || (1 << qb) < nshards * 64)
+    SHQ_FAIL(SHQ_ERR_ARG, "bad shard %d of %d", shard, nshards);
+  SHQ_CUDA(cudaSetDevice(device));
+  h->device = device; h->qb = qb; h->hb = hb; h->seed = seed; h->shard = shard; h->nshards = nshards;
+  h->nslots = 1ULL << qb;
+  h->xnslots = h->nslots + (uint64_t)(10 * sqrt((double)h->nslots));   // gqf.c:2198
+  h->nblocks = (h->xnslots + 63) / 64;
+  uint64_t range = 1ULL << hb;
+  h->key_lo = range / nshards * shard; h->key_hi = range / nshards * (shard + 1);
+  SHQ_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  SHQ_CUDA(cudaEventCreate(&h->ev0)); SHQ_CUDA(cudaEventCreate(&h->ev1));
+  SHQ_CUDA(cudaMalloc(&h->d_err, sizeof(int)));
+  SHQ_CUDA(cudaMemset(h->d_err, 0, sizeof(int)));
+  memset(&h->stats, 0, sizeof h->stats);
+}
+
+void free_handle(shq_handle_s* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  DevBuf* bufs[] = {&h->st_keys, &h->st_counts, &h->st_keys2, &h->st_counts2, &h->image, &h->d_text, &h->d_nl_tiles, &h->d_nl_pos,
+                    &h->d_chunk_ends, &h->d_chunk_line_end, &h->d_chunk_keys, &h->d_chunk_hist, &h->d_slow, &h->d_hist, &h->d_tot,
+                    &h->d_binoff, &h->d_packed, &h->d_tmp_keys, &h->d_tmp_counts, &h->d_tmp_chunk, &h->d_nout, &h->d_occ,
+                    &h->d_dense_off, &h->d_run_keys, &h->d_run_counts, &h->d_run_chunk, &h->d_split, &h->d_heads, &h->d_heads64,
+                    &h->d_scan_scratch, &h->d_misc, &h->d_pairs, &h->d_pos, &h->d_flags, &h->d_keep, &h->d_q_in, &h->d_q_cnt, &h->d_q_was};
+  for (DevBuf* b : bufs) b->release();
+  if (h->d_err) cudaFree(h->d_err);
+  if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+void build_header(shq_handle_s* h, uint8_t* hd) {   // qfmetadata, cqf/gqf.h:62-77 (x86-64 layout)
+  memset(hd, 0, 128);
+  auto put = [&](int off, uint64_t v) { memcpy(hd + off, &v, 8); };
+  put(0, h->nblocks * kBlockBytes);
+  memcpy(hd + 8, &h->seed, 4);
+  put(16, h->nslots); put(24, h->xnslots); put(32, (uint64_t)h->hb); put(40, 0);
+  put(48, (uint64_t)(h->hb - h->qb)); put(56, (uint64_t)(h->hb - h->qb));
+  unsigned __int128 range = (unsigned __int128)h->nslots << (h->hb - h->qb);
+  memcpy(hd + 64, &range, 16);
+  put(80, h->nblocks); put(88, h->nelts); put(96, h->ndistinct); put(104, 0);
+  put(112, h->xnslots / 65536 + 2);
+}
+
+}  // namespace
+
+// ============================================================== C ABI ========
+extern "C" {
+
+const char* shq_strerror(int s) {
+  switch (s) {
+    case SHQ_OK: return "ok";
+    case SHQ_ERR_ARG: return "bad argument";
+    case SHQ_ERR_CUDA: return "CUDA error";
+    case SHQ_ERR_CAPACITY: return "filter capacity exceeded";
+    case SHQ_ERR_MALFORMED: return "malformed FASTQ chunk";
+    case SHQ_ERR_IO: return "I/O error";
+    case SHQ_ERR_FORMAT: return "unsupported .cqf image";
+    case SHQ_ERR_COUNT_OVERFLOW: return "count overflow";
+    case SHQ_ERR_STATE: return "invalid state";
+  }
+  return "unknown";
+}
+const char* shq_last_error(shq_t h) { return h ? h->last_error.c_str() : ""; }
+
+int shq_create_shard(int qb, int hb, uint32_t seed, int device, int shard, int nshards, shq_t* out) {
+  if (!out) return SHQ_ERR_ARG;
+  *out = nullptr;
+  shq_handle_s* h = new shq_handle_s();
+  struct { int qb, hb; uint32_t seed; int device, shard, nshards; } args{qb, hb, seed, device, shard, nshards};
+  int rc = guard(h, [](shq_handle_s* h, void* p) {
+    auto& a = *(decltype(args)*)p;
+    init_handle(h, a.qb, a.hb, a.seed, a.device, a.shard, a.nshards);
+  }, &args);
+  if (rc != SHQ_OK && rc != SHQ_ERR_CUDA) { fprintf(stderr, "shq_create: %s\n", h->last_error.c_str()); }
+  if (rc != SHQ_OK) { if (rc == SHQ_ERR_CUDA) fprintf(stderr, "shq_create: %s\n", h->last_error.c_str()); delete h; return rc; }
+  *out = h;
+  return SHQ_OK;
+}
+int shq_create(int qb, int hb, uint32_t seed, int device, shq_t* out) { return shq_create_shard(qb, hb, seed, device, 0, 1, out); }
+void shq_destroy(shq_t h) { free_handle(h); }
+
+int shq_set_denoise_schedule(shq_t h, uint64_t trigger, uint32_t rounds, int end_denoise) {
+  if (!h) return SHQ_ERR_ARG;
+  h->trigger = trigger; h->rounds_left = rounds; h->end_denoise = end_denoise != 0;
+  return SHQ_OK;
+}
+
+int shq_insert_fastq_chunk(shq_t h, const char* text, size_t n, int K) {
+  if (!h || (!text && n)) return SHQ_ERR_ARG;
+  struct { const char* text; size_t n; int K; } args{text, n, K};
+  SHQ_API_BEGIN(h)
+    if (h->h_stage_fill && (h->stage_K != a.K || h->h_stage_fill + a.n > h->max_batch_bytes)) flush_stage(h);
+    if (a.n > h->max_batch_bytes && a.n >= ((size_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "chunk too large");
+    if (h->h_stage_cap < h->h_stage_fill + a.n) {
+      size_t want = std::max(h->h_stage_fill + a.n, std::min(h->max_batch_bytes, std::max((size_t)64 << 20, 2 * h->h_stage_cap)));
+      char* p = nullptr;
+      SHQ_CUDA(cudaMallocHost((void**)&p, want));
+      if (h->h_stage_fill) memcpy(p, h->h_stage, h->h_stage_fill);
+      if (h->h_stage) cudaFreeHost(h->h_stage);
+      h->h_stage = p; h->h_stage_cap = want;
+    }
+    memcpy(h->h_stage + h->h_stage_fill, a.text, a.n);
+    h->h_stage_fill += a.n;
+    h->stage_chunk_ends.push_back(h->h_stage_fill);
+    h->stage_K = a.K;
+  SHQ_API_END
+}
+
+int shq_insert_fastq_device(shq_t h, const char* d_text, size_t n, const uint64_t* chunk_ends, size_t nchunks, int K) {
+  if (!h || (!d_text && n) || (!chunk_ends && nchunks)) return SHQ_ERR_ARG;
+  struct { const char* t; size_t n; const uint64_t* ce; size_t nc; int K; } args{d_text, n, chunk_ends, nchunks, K};
+  SHQ_API_BEGIN(h)
+    flush_stage(h);
+    if (a.nc && a.ce[a.nc - 1] != a.n) SHQ_FAIL(SHQ_ERR_ARG, "last chunk end must equal n");
+    // split into device batches on chunk boundaries
+    size_t c0 = 0;
+    while (c0 < a.nc) {
+      uint64_t base = c0 ? a.ce[c0 - 1] : 0;
+      size_t c1 = c0;
+      while (c1 < a.nc && a.ce[c1] - base <= h->max_batch_bytes) c1++;
+      if (c1 == c0) c1 = c0 + 1;
+      if (base & 15) SHQ_FAIL(SHQ_ERR_ARG, "batch boundary at byte %llu is not 16-byte aligned; pass fewer, larger calls or aligned chunks",
+                              (unsigned long long)base);
+      std::vector<uint64_t> ends(a.ce + c0, a.ce + c1);
+      for (auto& e : ends) e -= base;
+      process_batch(h, a.t + base, ends.back(), ends.data(), (int)ends.size(), a.K, nullptr, 0);
+      c0 = c1;
+    }
+  SHQ_API_END
+}
+
+int shq_insert_keys_device(shq_t h, const uint64_t* d_keys, size_t n) {
+  if (!h || (!d_keys && n)) return SHQ_ERR_ARG;
+  struct { const uint64_t* k; size_t n; } args{d_keys, n};
+  SHQ_API_BEGIN(h)
+    flush_stage(h);
+    const size_t step = (size_t)1 << 28;
+    for (size_t o = 0; o < a.n; o += step) process_batch(h, nullptr, 0, nullptr, 0, 0, a.k + o, std::min(step, a.n - o));
+  SHQ_API_END
+}
+
+int shq_insert_keys(shq_t h, const uint64_t* keys, size_t n) {
+  if (!h || (!keys && n)) return SHQ_ERR_ARG;
+  struct { const uint64_t* k; size_t n; } args{keys, n};
+  SHQ_API_BEGIN(h)
+    flush_stage(h);
+    const size_t step = (size_t)1 << 27;
+    for (size_t o = 0; o < a.n; o += step) {
+      size_t m = std::min(step, a.n - o);
+      h->d_q_in.reserve(m * 8);
+      SHQ_CUDA(cudaMemcpyAsync(h->d_q_in.p, a.k + o, m * 8, cudaMemcpyHostToDevice, h->stream));
+      h->stats.h2d_bytes += m * 8;
+      process_batch(h, nullptr, 0, nullptr, 0, 0, h->d_q_in.as<uint64_t>(), m);
+    }
+  SHQ_API_END
+}
+
+int shq_sync(shq_t h) {
+  if (!h) return SHQ_ERR_ARG;
+  int args = 0;
+  SHQ_API_BEGIN(h)
+    (void)a;
+    flush_stage(h);
+    SHQ_CUDA(cudaStreamSynchronize(h->stream));
+  SHQ_API_END
+}
+
+int shq_finish(shq_t h) {
+  if (!h) return SHQ_ERR_ARG;
+  int args = 0;
+  SHQ_API_BEGIN(h)
+    (void)a;
+    flush_stage(h);
+    // EOF rule of fastq_to_uint64kmers_prod (CQF_mt.h:858-866): one more round if the trigger still
+    // holds with rounds left, or if --endDeNoise was given.
+    if (!h->finished) {
+      if ((h->rounds_left > 0 && h->ndistinct >= h->trigger) || h->end_denoise) {
+        if (h->rounds_left > 0) h->rounds_left--;
+        denoise_round(h);
+      }
+      h->finished = true;
+    }
+    SHQ_CUDA(cudaStreamSynchronize(h->stream));
+  SHQ_API_END
+}
+
+int shq_counts(shq_t h, uint64_t* ndistinct, uint64_t* nelts) {
+  int rc = shq_sync(h);
+  if (rc) return rc;
+  if (ndistinct) *ndistinct = h->ndistinct;
+  if (nelts) *nelts = h->nelts;
+  return SHQ_OK;
+}
+int shq_rounds_done(shq_t h, uint32_t* rounds) { if (!h || !rounds) return SHQ_ERR_ARG; *rounds = h->rounds_done; return SHQ_OK; }
+
+int shq_denoise(shq_t h, uint64_t* removed) {
+  if (!h) return SHQ_ERR_ARG;
+  struct { uint64_t* r; } args{removed};
+  SHQ_API_BEGIN(h)
+    flush_stage(h);
+    uint64_t r = denoise_round(h);
+    SHQ_CUDA(cudaStreamSynchronize(h->stream));
+    if (a.r) *a.r = r;
+  SHQ_API_END
+}
+
+int shq_geometry(shq_t h, int* qb, int* hb, uint64_t* nslots, uint64_t* xnslots, uint64_t* nblocks) {
+  if (!h) return SHQ_ERR_ARG;
+  if (qb) *qb = h->qb; if (hb) *hb = h->hb;
+  if (nslots) *nslots = h->nslots; if (xnslots) *xnslots = h->xnslots; if (nblocks) *nblocks = h->nblocks;
+  return SHQ_OK;
+}
+int shq_image_size(shq_t h, size_t* bytes) { if (!h || !bytes) return SHQ_ERR_ARG; *bytes = 128 + (size_t)h->nblocks * kBlockBytes; return SHQ_OK; }
+
+int shq_export_cqf(shq_t h, void* dst, size_t cap, size_t* written) {
+  if (!h || !dst) return SHQ_ERR_ARG;
+  struct { void* dst; size_t cap; size_t* w; } args{dst, cap, written};
+  SHQ_API_BEGIN(h)
+    flush_stage(h);
+    size_t total = 128 + (size_t)h->nblocks * kBlockBytes;
+    if (a.cap < total) SHQ_FAIL(SHQ_ERR_ARG, "buffer of %zu bytes < image of %zu", a.cap, total);
+    if (h->nshards != 1) SHQ_FAIL(SHQ_ERR_STATE, "export of a sharded handle goes through the multi-GPU layer");
+    if (!h->image_only) materialise(h);
+    uint8_t* out = (uint8_t*)a.dst;
+    build_header(h, out);
+    SHQ_CUDA(cudaMemcpyAsync(out + 128, h->image.p, total - 128, cudaMemcpyDeviceToHost, h->stream));
+    SHQ_CUDA(cudaStreamSynchronize(h->stream));
+    h->stats.d2h_bytes += total - 128;
+    if (a.w) *a.w = total;
+  SHQ_API_END
+}
+
+int shq_save(shq_t h, const char* path) {
+  if (!h || !path) return SHQ_ERR_ARG;
+  size_t total = 0;
+  shq_image_size(h, &total);
+  void* buf = malloc(total);
+  if (!buf) return SHQ_ERR_ARG;
+  size_t w = 0;
+  int rc = shq_export_cqf(h, buf, total, &w);
+  if (rc == SHQ_OK) {
+    FILE* f = fopen(path, "wb+");
+    if (!f || fwrite(buf, 1, w, f) != w) { rc = SHQ_ERR_IO; h->last_error = std::string("cannot write ") + path; }
+    if (f) fclose(f);
+  }
+  free(buf);
+  return rc;
+}
+
+int shq_load_image(const void* image, size_t n, int device, shq_t* out) {
+  if (!image || !out || n < 128) return SHQ_ERR_FORMAT;
+  *out = nullptr;
+  const uint8_t* p = (const uint8_t*)image;
+  auto get = [&](int off) { uint64_t v; memcpy(&v, p + off, 8); return v; };
+  uint64_t size = get(0), nslots = get(16), xnslots = get(24), key_bits = get(32), bps = get(56), nblocks = get(80);
+  uint32_t seed; memcpy(&seed, p + 8, 4);
+  int qb = 0; while (qb < 63 && (1ULL << qb) < nslots) qb++;
+  if (bps != 8 || (1ULL << qb) != nslots || key_bits != (uint64_t)qb + 8 || size != nblocks * kBlockBytes || n < 128 + size)
+    return SHQ_ERR_FORMAT;
+  shq_t h = nullptr;
+  int rc = shq_create(qb, (int)key_bits, seed, device, &h);
+  if (rc) return rc;
+  if (h->xnslots != xnslots || h->nblocks != nblocks) { shq_destroy(h); return SHQ_ERR_FORMAT; }
+  struct { const uint8_t* p; size_t size; } args{p, (size_t)size};
+  rc = guard(h, [](shq_handle_s* h, void* ap) {
+    auto& a = *(decltype(args)*)ap;
+    size_t tiles = (h->nblocks + kTileBlocks - 1) / kTileBlocks;
+    h->image.reserve(tiles * kTileBytes + 16);
+    SHQ_CUDA(cudaMemcpyAsync(h->image.p, a.p + 128, a.size, cudaMemcpyHostToDevice, h->stream));
+    SHQ_CUDA(cudaStreamSynchronize(h->stream));
+    h->stats.h2d_bytes += a.size;
+  }, &args);
+  if (rc) { shq_destroy(h); return rc; }
+  h->nelts = get(88); h->ndistinct = get(96);
+  h->image_valid = true; h->image_only = true;
+  *out = h;
+  return SHQ_OK;
+}
+
+int shq_load(const char* path, int device, shq_t* out) {
+  if (!path || !out) return SHQ_ERR_ARG;
+  FILE* f = fopen(path, "rb");
+  if (!f) return SHQ_ERR_IO;
+  fseek(f, 0, SEEK_END);
+  long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  void* buf = malloc(sz > 0 ? (size_t)sz : 1);
+  if (!buf) { fclose(f); return SHQ_ERR_ARG; }
+  size_t got = fread(buf, 1, (size_t)sz, f);
+  fclose(f);
+  int rc = got == (size_t)sz ? shq_load_image(buf, got, device, out) : SHQ_ERR_IO;
+  free(buf);
+  return rc;
+}
+
+int shq_iterate(shq_t h, uint64_t* keys, uint64_t* counts, size_t cap, size_t* n) {
+  if (!h || !n) return SHQ_ERR_ARG;
+  struct { uint64_t* k; uint64_t* c; size_t cap; size_t* n; } args{keys, counts, cap, n};
+  SHQ_API_BEGIN(h)
+    flush_stage(h);
+    ensure_state(h);
+    *a.n = h->n_state;
+    size_t m = std::min(a.cap, h->n_state);
+    if (m && a.k) { SHQ_CUDA(cudaMemcpyAsync(a.k, h->st_keys.p, m * 8, cudaMemcpyDeviceToHost, h->stream)); h->stats.d2h_bytes += m * 8; }
+    if (m && a.c) {
+      std::vector<uint32_t> tmp(m);
+      SHQ_CUDA(cudaMemcpyAsync(tmp.data(), h->st_counts.p, m * 4, cudaMemcpyDeviceToHost, h->stream));
+      SHQ_CUDA(cudaStreamSynchronize(h->stream));
+      h->stats.d2h_bytes += m * 4;
+      for (size_t i = 0; i < m; i++) a.c[i] = tmp[i];
+    }
+    SHQ_CUDA(cudaStreamSynchronize(h->stream));
+  SHQ_API_END
+}
+
+static int query_impl(shq_t h, const uint64_t* keys, size_t n, uint64_t* counts, uint8_t* was, bool set) {
+  if (!h || (!keys && n) || (!counts && n)) return SHQ_ERR_ARG;
+  struct { const uint64_t* k; size_t n; uint64_t* c; uint8_t* w; bool set; } args{keys, n, counts, was, set};
+  SHQ_API_BEGIN(h)
+    flush_stage(h);
+    if (a.n == 0) return;
+    if (!h->image_only) materialise(h);
+    ImageView im{h->image.as<uint8_t>(), h->nblocks, h->xnslots, 0};
+    h->d_q_in.reserve(a.n * 8); h->d_q_cnt.reserve(a.n * 8); h->d_q_was.reserve(a.n + 16);
+    SHQ_CUDA(cudaMemcpyAsync(h->d_q_in.p, a.k, a.n * 8, cudaMemcpyHostToDevice, h->stream));
+    if (a.set) query_kernel<true><<<cdiv(a.n, 128), 128, 0, h->stream>>>(im, h->d_q_in.as<uint64_t>(), a.n, h->d_q_cnt.as<uint64_t>(), h->d_q_was.as<uint8_t>());
+    else query_kernel<false><<<cdiv(a.n, 128), 128, 0, h->stream>>>(im, h->d_q_in.as<uint64_t>(), a.n, h->d_q_cnt.as<uint64_t>(), nullptr);
+    h->stats.kernels_launched++;
+    SHQ_CUDA(cudaGetLastError());
+    SHQ_CUDA(cudaMemcpyAsync(a.c, h->d_q_cnt.p, a.n * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (a.set && a.w) SHQ_CUDA(cudaMemcpyAsync(a.w, h->d_q_was.p, a.n, cudaMemcpyDeviceToHost, h->stream));
+    SHQ_CUDA(cudaStreamSynchronize(h->stream));
+    h->stats.h2d_bytes += a.n * 8; h->stats.d2h_bytes += a.n * 9;
+  SHQ_API_END
+}
+int shq_query_set_traveled(shq_t h, const uint64_t* keys, size_t n, uint64_t* counts, uint8_t* was) { return query_impl(h, keys, n, counts, was, true); }
+int shq_query(shq_t h, const uint64_t* keys, size_t n, uint64_t* counts) { return query_impl(h, keys, n, counts, nullptr, false); }
+
+int shq_hash_fastq_chunk(shq_t h, const char* text, size_t n, int K, uint64_t* keys, size_t cap, size_t* nkeys) {
+  if (!h || !nkeys || (!text && n)) return SHQ_ERR_ARG;
+  struct { const char* t; size_t n; int K; uint64_t* keys; size_t cap; size_t* nk; } args{text, n, K, keys, cap, nkeys};
+  SHQ_API_BEGIN(h)
+    cudaStream_t st = h->stream;
+    uint64_t& L = h->stats.kernels_launched;
+    *a.nk = 0;
+    if (a.n == 0) return;
+    if (a.K < 1 || a.K > kTilePos - 32) SHQ_FAIL(SHQ_ERR_ARG, "K=%d outside [1,%d]", a.K, kTilePos - 32);
+    h->d_text.reserve(a.n + 64);
+    SHQ_CUDA(cudaMemcpyAsync(h->d_text.p, a.t, a.n, cudaMemcpyHostToDevice, st));
+    unsigned ntiles = cdiv(a.n, kNlTile);
+    h->d_nl_tiles.reserve((size_t)(ntiles + 1) * 4);
+    nl_count_kernel<<<ntiles, kNlThreads, 0, st>>>(h->d_text.as<char>(), a.n, h->d_nl_tiles.as<uint32_t>()); L++;
+    h->d_misc.reserve(256);
+    exclusive_scan_inplace<SumU32>(h->d_nl_tiles.as<uint32_t>(), ntiles, h->d_scan_scratch, st, h->d_misc.as<uint32_t>(), &L);
+    uint32_t n_lines = read_scalar(h, h->d_misc.as<uint32_t>());
+    if ((n_lines & 3) || a.t[a.n - 1] != '\n') SHQ_FAIL(SHQ_ERR_MALFORMED, "chunk holds %u lines / no trailing newline", n_lines);
+    h->d_nl_pos.reserve((size_t)(n_lines + 4) * 4);
+    nl_write_kernel<<<ntiles, kNlThreads, 0, st>>>(h->d_text.as<char>(), a.n, h->d_nl_tiles.as<uint32_t>(), h->d_nl_pos.as<uint32_t>()); L++;
+    HashParams hp{};
+    hp.text = h->d_text.as<char>(); hp.nl_pos = h->d_nl_pos.as<uint32_t>(); hp.n_reads = n_lines / 4; hp.K = a.K; hp.hb = h->hb;
+    hp.key_lo = 0; hp.key_hi = ~0ULL; hp.n_bins = 0;
+    h->d_slow.reserve((size_t)(hp.n_reads + 2) * 4 + 16);
+    uint32_t* slow_count = h->d_slow.as<uint32_t>();
+    hp.slow_count = slow_count; hp.slow_list = slow_count + 4;
+    SHQ_CUDA(cudaMemsetAsync(slow_count, 0, 16, st));
+    h->d_q_cnt.reserve(a.cap * 8 + 64);
+    h->d_misc.reserve(256);
+    unsigned long long* d_n = h->d_misc.as<unsigned long long>() + 8;
+    SHQ_CUDA(cudaMemsetAsync(d_n, 0, 8, st));
+    Sink sk{}; sk.keys = h->d_q_cnt.as<uint64_t>(); sk.nkeys = d_n; sk.cap = a.cap;
+    size_t smem = (size_t)kHashWarps * 2 * (kTilePos + 1) * 8;
+    // the key-list mode needs the slow list too: run the count-mode N test through a dry pass
+    SHQ_CUDA(cudaFuncSetAttribute(hash_reads_kernel<kSinkKeys>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hash_reads_kernel<kSinkKeys><<<2 * kNumSMs, kHashThreads, smem, st>>>(hp, sk, nullptr, nullptr); L++;
+    // reads with 'N' past the first K bases: list them with a tiny classify pass (count mode over 1 bin)
+    HashParams hc = hp; hc.n_bins = 1; hc.lb = 63; hc.key_lo = 0; hc.key_hi = 0;   // drops every key, only fills the slow list
+    h->d_hist.reserve((size_t)(2 * kNumSMs + 1) * 4);
+    size_t smem_c = 16 + smem;
+    SHQ_CUDA(cudaFuncSetAttribute(hash_reads_kernel<kSinkCount>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+    Sink sc{};
+    hash_reads_kernel<kSinkCount><<<2 * kNumSMs, kHashThreads, smem_c, st>>>(hc, sc, h->d_hist.as<uint32_t>(), nullptr); L++;
+    uint32_t n_slow = read_scalar(h, slow_count);
+    if (n_slow) { hash_slow_reads_kernel<kSinkKeys><<<cdiv(n_slow, 128), 128, 0, st>>>(hp, sk, n_slow); L++; }
+    SHQ_CUDA(cudaGetLastError());
+    unsigned long long nk = read_scalar(h, d_n);
+    *a.nk = (size_t)nk;
+    size_t m = std::min((size_t)nk, a.cap);
+    if (m && a.keys) SHQ_CUDA(cudaMemcpyAsync(a.keys, h->d_q_cnt.p, m * 8, cudaMemcpyDeviceToHost, st));
+    SHQ_CUDA(cudaStreamSynchronize(st));
+    h->stats.h2d_bytes += a.n; h->stats.d2h_bytes += m * 8;
+  SHQ_API_END
+}
+
+int shq_get_stats(shq_t h, shq_stats* out) { if (!h || !out) return SHQ_ERR_ARG; *out = h->stats; return SHQ_OK; }
+int shq_reset_stats(shq_t h) { if (!h) return SHQ_ERR_ARG; memset(&h->stats, 0, sizeof h->stats); return SHQ_OK; }
+void* shq_stream(shq_t h) { return h ? (void*)h->stream : nullptr; }
+
+}  // extern "C"
+
+// ---- unitig entry points: implemented in shq_unitig.cuh (included below) ----
+#include "shq_unitig.cuh"

@@ -1,0 +1,356 @@
+// shq_layout.cuh -- K5 (canonical CQF image from the sorted state), the deNoise range walk (K4),
+// the block-image decoder (load) and the batched rank/select query (K6).
+//
+// Image layout (reference cqf/gqf.c:63-86, 8-bit slots): block b = 89 bytes, packed:
+//   [0] offset  [1..8] occupieds  [9..16] runends  [17..24] traveled  [25..88] 64 slot bytes.
+#pragma once
+#include "shq_common.cuh"
+#include "shq_scan.cuh"
+
+namespace shq {
+
+constexpr int kBlockBytes = 89;
+
+// ------------------------------------------------------------ positions -----
+// Step 1: per entry the map f_k(e) = max(e + len, first ? q + len : -inf)  (MaxPlus).
+__global__ void layout_pairs_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, size_t n,
+                                    uint64_t key_lo_q /* quotient offset of the shard */, MaxPlus* __restrict__ pairs) {
+  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  uint64_t key = keys[k];
+  long long q = (long long)((key >> 8) - key_lo_q);
+  bool first = (k == 0) || ((keys[k - 1] >> 8) != (key >> 8));
+  long long len = enc_len((uint32_t)(key & 0xFF), counts[k]);
+  pairs[k] = MaxPlus{len, first ? q + len : kNegInf};
+}
+// Step 2 (after the exclusive MaxPlus scan): pos_k = first slot of entry k (relative to the shard).
+__global__ void layout_pos_kernel(const uint64_t* __restrict__ keys, size_t n, uint64_t key_lo_q,
+                                  const MaxPlus* __restrict__ scanned, uint64_t start_free, uint64_t* __restrict__ pos) {
+  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  uint64_t key = keys[k];
+  long long q = (long long)((key >> 8) - key_lo_q);
+  bool first = (k == 0) || ((keys[k - 1] >> 8) != (key >> 8));
+  MaxPlus f = scanned[k];
+  long long e = (long long)start_free + f.a;
+  if (f.b > e) e = f.b;
+  if (first && q > e) e = q;
+  pos[k] = (uint64_t)e;
+}
+
+__device__ __forceinline__ uint64_t entry_end(const uint64_t* keys, const uint32_t* counts, const uint64_t* pos, size_t k) {
+  return pos[k] + enc_len((uint32_t)(keys[k] & 0xFF), counts[k]) - 1;
+}
+
+// ------------------------------------------------------- image tiles --------
+constexpr int kTileBlocks = 64;                       // 64 blocks = 4096 slots per CTA
+constexpr int kTileSlots = kTileBlocks * 64;
+constexpr int kTileBytes = kTileBlocks * kBlockBytes;  // 5696, a multiple of 4
+constexpr int kImgThreads = 128;
+
+// Writes blocks [b0, b0+kTileBlocks) of the image (traveled words zero).
+// q_base: quotient/slot index of block 0 of this image (shard offset); first_block: global index
+// of block 0 (its offset byte is 0 only if it is global block 0 -- for shards > 0 the host fixes the
+// carry separately).
+__global__ void __launch_bounds__(kImgThreads) image_tiles_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts,
+                                                                 const uint64_t* __restrict__ pos, size_t n, uint64_t key_lo_q,
+                                                                 uint64_t nblocks, uint8_t* __restrict__ image) {
+  __shared__ __align__(16) uint8_t s_img[kTileBytes];
+  __shared__ uint32_t s_occ[kTileBlocks * 2], s_run[kTileBlocks * 2];
+  __shared__ size_t s_rng[4];
+  const uint64_t b0 = (uint64_t)blockIdx.x * kTileBlocks;
+  const uint64_t S0 = b0 * 64, S1 = S0 + kTileSlots;
+  for (int i = threadIdx.x; i < kTileBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(s_img)[i] = 0;
+  for (int i = threadIdx.x; i < kTileBlocks * 2; i += blockDim.x) { s_occ[i] = 0; s_run[i] = 0; }
+  if (threadIdx.x < 4) {
+    // 0: first entry whose last slot >= S0     1: first entry with pos >= S1
+    // 2: first entry with quotient >= S0       3: first entry with quotient >= S1
+    size_t lo = 0, hi = n;
+    while (lo < hi) {
+      size_t mid = lo + ((hi - lo) >> 1);
+      bool before;
+      if (threadIdx.x == 0) before = entry_end(keys, counts, pos, mid) < S0;
+      else if (threadIdx.x == 1) before = pos[mid] < S1;
+      else if (threadIdx.x == 2) before = ((keys[mid] >> 8) - key_lo_q) < S0;
+      else before = ((keys[mid] >> 8) - key_lo_q) < S1;
+      if (before) lo = mid + 1; else hi = mid;
+    }
+    s_rng[threadIdx.x] = lo;
+  }
+  __syncthreads();
+  const size_t k_lo = s_rng[0], k_hi = s_rng[1], q_lo = s_rng[2], q_hi = s_rng[3];
+  // slot bytes + runends
+  for (size_t k = k_lo + threadIdx.x; k < k_hi; k += blockDim.x) {
+    uint64_t key = keys[k];
+    uint8_t enc[12];
+    int len = enc_bytes((uint32_t)(key & 0xFF), counts[k], enc);
+    uint64_t p = pos[k];
+    for (int i = 0; i < len; i++) {
+      uint64_t s = p + i;
+      if (s >= S0 && s < S1) {
+        uint32_t rel = (uint32_t)(s - S0);
+        s_img[(rel >> 6) * kBlockBytes + 25 + (rel & 63)] = enc[i];
+      }
+    }
+    bool last = (k + 1 == n) || ((keys[k + 1] >> 8) != (key >> 8));
+    uint64_t e = p + len - 1;
+    if (last && e >= S0 && e < S1) {
+      uint32_t rel = (uint32_t)(e - S0);
+      atomicOr(&s_run[rel >> 5], 1u << (rel & 31));
+    }
+  }
+  // occupieds
+  for (size_t k = q_lo + threadIdx.x; k < q_hi; k += blockDim.x) {
+    uint64_t q = (keys[k] >> 8) - key_lo_q;
+    bool first = (k == 0) || ((keys[k - 1] >> 8) != (keys[k] >> 8));
+    if (first) { uint32_t rel = (uint32_t)(q - S0); atomicOr(&s_occ[rel >> 5], 1u << (rel & 31)); }
+  }
+  __syncthreads();
+  // per block: offset byte + bitmap words
+  for (int b = threadIdx.x; b < kTileBlocks; b += blockDim.x) {
+    uint64_t gb = b0 + b;
+    uint8_t* B = s_img + b * kBlockBytes;
+    // offset = min(255, max(0, E - 64b + 1)), E = last slot of the last run with quotient < 64b
+    uint32_t off = 0;
+    if (gb > 0) {
+      size_t lo = q_lo, hi = q_hi;   // last entry with quotient < 64*gb lies in [q_lo-1, q_hi)
+      while (lo < hi) {
+        size_t mid = lo + ((hi - lo) >> 1);
+        if (((keys[mid] >> 8) - key_lo_q) < gb * 64) lo = mid + 1; else hi = mid;
+      }
+      if (lo > 0) {
+        uint64_t E = entry_end(keys, counts, pos, lo - 1);
+        if (E + 1 > gb * 64) { uint64_t o = E - gb * 64 + 1; off = o > 255 ? 255u : (uint32_t)o; }
+      }
+    }
+    B[0] = (uint8_t)off;
+    uint64_t occ = (uint64_t)s_occ[2 * b] | ((uint64_t)s_occ[2 * b + 1] << 32);
+    uint64_t run = (uint64_t)s_run[2 * b] | ((uint64_t)s_run[2 * b + 1] << 32);
+    for (int i = 0; i < 8; i++) { B[1 + i] = (uint8_t)(occ >> (8 * i)); B[9 + i] = (uint8_t)(run >> (8 * i)); }
+  }
+  __syncthreads();
+  uint64_t nb_here = nblocks > b0 ? nblocks - b0 : 0;
+  if (nb_here > kTileBlocks) nb_here = kTileBlocks;
+  size_t bytes = (size_t)nb_here * kBlockBytes;
+  uint8_t* dst = image + b0 * kBlockBytes;   // b0 % 4 == 0 -> 4-byte aligned
+  size_t words = bytes / 4;
+  for (size_t i = threadIdx.x; i < words; i += blockDim.x) reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<uint32_t*>(s_img)[i];
+  for (size_t i = words * 4 + threadIdx.x; i < bytes; i += blockDim.x) dst[i] = s_img[i];
+}
+
+// ------------------------------------------------------ deNoise ranges ------
+// The reference hands out sweep ranges of 2^20 slots stretched to a cluster end
+// (cqf/CQF_mt.h:884-901) and its cleaners loop `while (start < end_bucket_id)`
+// (cqf/gqf.c:2878-2886, CQF_mt.h:1024): a cluster that is one slot wide and sits exactly on a
+// range end is never visited, so its count-1 key survives.  This walk finds those keys.
+// Single thread (the chain of ranges is inherently serial; nslots / 2^20 steps).
+__global__ void denoise_ranges_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts,
+                                      const uint64_t* __restrict__ pos, size_t n, uint64_t nslots, uint64_t xnslots,
+                                      uint32_t* __restrict__ keep_idx, uint32_t* __restrict__ n_keep, uint32_t keep_cap) {
+  if (blockIdx.x || threadIdx.x) return;
+  const uint64_t min_len = 1ULL << 20;
+  uint32_t nk = 0;
+  if (n == 0) { *n_keep = 0; return; }
+  uint64_t cur = keys[0] >> 8;  // find_first_nonempty_slot(qf, 0)
+  while (cur < nslots) {
+    uint64_t start = cur;
+    uint64_t e0 = (start + min_len) > nslots ? nslots : (start + min_len);
+    // k = last entry with pos <= e0
+    size_t lo = 0, hi = n;
+    while (lo < hi) { size_t mid = lo + ((hi - lo) >> 1); if (pos[mid] <= e0) lo = mid + 1; else hi = mid; }
+    uint64_t end;
+    size_t last = (size_t)-1;   // entry holding slot `end`, if any
+    if (lo > 0 && entry_end(keys, counts, pos, lo - 1) >= e0) {
+      size_t j = lo - 1;
+      uint64_t je = entry_end(keys, counts, pos, j);
+      while (j + 1 < n && pos[j + 1] == je + 1) { j++; je = entry_end(keys, counts, pos, j); }
+      end = je; last = j;                       // find_first_empty_slot(e0) - 1
+    } else {
+      end = e0 - 1;
+      if (lo > 0 && entry_end(keys, counts, pos, lo - 1) == end) last = lo - 1;
+    }
+    if (last != (size_t)-1 && end >= start) {
+      // one-slot cluster [end,end]: entry starts and ends at `end`, previous entry not adjacent
+      if (pos[last] == end && counts[last] == 1 && (last == 0 || entry_end(keys, counts, pos, last - 1) + 1 < end)) {
+        if (nk < keep_cap) keep_idx[nk] = (uint32_t)last;
+        nk++;
+      }
+    }
+    // find_first_nonempty_slot(end + 1): next occupied quotient >= end+1
+    lo = 0; hi = n;
+    while (lo < hi) { size_t mid = lo + ((hi - lo) >> 1); if ((keys[mid] >> 8) < end + 1) lo = mid + 1; else hi = mid; }
+    cur = lo < n ? (keys[lo] >> 8) : xnslots;
+  }
+  *n_keep = nk;
+}
+
+// ------------------------------------------------------------ queries -------
+struct ImageView {
+  uint8_t* blocks; uint64_t nblocks; uint64_t xnslots; uint64_t q_base;  // q_base: quotient of slot 0 (shards)
+};
+__device__ __forceinline__ uint64_t ld64u(const uint8_t* p) {  // unaligned little-endian load
+  uint64_t v = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) v |= (uint64_t)p[i] << (8 * i);
+  return v;
+}
+__device__ __forceinline__ const uint8_t* blk(const ImageView& im, uint64_t b) { return im.blocks + b * kBlockBytes; }
+__device__ __forceinline__ uint8_t img_slot(const ImageView& im, uint64_t s) { return im.blocks[(s >> 6) * kBlockBytes + 25 + (s & 63)]; }
+__device__ __forceinline__ bool img_bit(const ImageView& im, uint64_t s, int field) {
+  return (im.blocks[(s >> 6) * kBlockBytes + 1 + 8 * field + ((s & 63) >> 3)] >> (s & 7)) & 1;
+}
+// position of the r-th (0-based) set bit of v, 64 if none
+__device__ __forceinline__ int select64(uint64_t v, int r) {
+  uint32_t lo = (uint32_t)v; int pl = __popc(lo);
+  if (r < pl) return __fns(lo, 0, r + 1);
+  uint32_t hi = (uint32_t)(v >> 32); r -= pl;
+  if (r < __popc(hi)) return 32 + __fns(hi, 0, r + 1);
+  return 64;
+}
+// run_end (cqf/gqf.c:655-704) on the packed image; a saturated offset byte is resolved like
+// block_offset() does, by recursing on the previous quotient.
+__device__ uint64_t img_run_end(const ImageView& im, uint64_t q);
+__device__ __forceinline__ uint64_t img_block_offset(const ImageView& im, uint64_t b) {
+  uint8_t o = blk(im, b)[0];
+  if (o < 255) return o;
+  return img_run_end(im, 64 * b - 1) - 64 * b + 1;
+}
+__device__ uint64_t img_run_end(const ImageView& im, uint64_t q) {
+  // iterative form of the recursion run_end -> block_offset -> run_end(64b-1): walk back to a block
+  // whose offset byte is not saturated, then resolve forward.
+  uint64_t stack_q[40]; int sp = 0;
+  uint64_t cur = q, known_off = 0; bool have_off = false;
+  for (;;) {
+    uint64_t b = cur >> 6;
+    uint8_t o = blk(im, b)[0];
+    if (o < 255 || b == 0) { known_off = o; have_off = true; }
+    if (have_off) {
+      // resolve run_end(cur) with block offset known_off
+      for (;;) {
+        uint64_t bb = cur >> 6; uint32_t io = (uint32_t)(cur & 63);
+        uint64_t occ = ld64u(blk(im, bb) + 1);
+        int rank = __popcll(occ & ((io == 63) ? ~0ULL : ((2ULL << io) - 1)));
+        uint64_t res;
+        if (rank == 0) {
+          res = (known_off <= io) ? cur : (64 * bb + known_off - 1);
+        } else {
+          uint64_t rb = bb + known_off / 64; uint32_t ign = (uint32_t)(known_off % 64); int rr = rank - 1;
+          for (;;) {
+            uint64_t runs = ld64u(blk(im, rb) + 9);
+            uint64_t masked = ign ? (runs & ~((1ULL << ign) - 1)) : runs;
+            int s = select64(masked, rr);
+            if (s < 64) { res = 64 * rb + s; break; }
+            rr -= __popcll(masked); rb++; ign = 0;
+            if (rb >= im.nblocks) { res = im.xnslots - 1; break; }
+          }
+          if (res < cur) res = cur;
+        }
+        if (sp == 0) return res;
+        // res = run_end(64b-1) for the pending query on top of the stack
+        uint64_t pq = stack_q[--sp];
+        known_off = res - 64 * (pq >> 6) + 1;
+        cur = pq;
+      }
+    }
+    if (sp >= 40) return cur;  // cannot happen: offsets saturate only inside clusters > 255 slots
+    stack_q[sp++] = cur;
+    cur = 64 * b - 1;
+  }
+}
+
+// decode_counter (cqf/gqf.c:1259-1299): entry starting at slot `idx` inside a run ending at run_end.
+__device__ __forceinline__ uint64_t img_decode(const ImageView& im, uint64_t idx, uint64_t run_end, uint32_t* rem, uint64_t* count) {
+  uint32_t r = img_slot(im, idx);
+  *rem = r;
+  if (idx == run_end) { *count = 1; return idx; }
+  uint32_t d = img_slot(im, idx + 1);
+  if (d > r) { *count = 1; return idx; }
+  uint64_t e = idx + 1, c = 0;
+  if (d == 0) { e++; d = img_slot(im, e); }
+  while (d & 0x80) { c = c * 128 + (d & 0x7F); e++; d = img_slot(im, e); }
+  c = c * 128 + d;
+  *count = c + 1;
+  return e;
+}
+
+// qf_count_key_value[_set_traveled] (cqf/gqf.c:2442-2469, 3092-3128), one thread per key.
+template <bool SET>
+__global__ void query_kernel(ImageView im, const uint64_t* __restrict__ qkeys, size_t n, uint64_t* __restrict__ counts,
+                             uint8_t* __restrict__ was) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t key = qkeys[i];
+  uint32_t rem = (uint32_t)(key & 0xFF);
+  uint64_t q = (key >> 8) - im.q_base;
+  uint64_t cnt = 0; uint8_t w = 0;
+  if (q < im.nblocks * 64 && img_bit(im, q, 0)) {
+    uint64_t rs = q == 0 ? 0 : img_run_end(im, q - 1) + 1;
+    if (rs < q) rs = q;
+    // the run of q ends at the first runend bit at or after rs
+    uint64_t re = rs;
+    while (!img_bit(im, re, 1)) re++;
+    uint64_t idx = rs;
+    while (idx <= re) {
+      uint32_t r; uint64_t c;
+      uint64_t e = img_decode(im, idx, re, &r, &c);
+      if (r == rem) {
+        cnt = c;
+        if (SET) {
+          // traveled bit of the entry's first slot; 32-bit atomic on the word holding that byte
+          size_t byte_off = (idx >> 6) * kBlockBytes + 17 + ((idx & 63) >> 3);
+          uintptr_t addr = reinterpret_cast<uintptr_t>(im.blocks) + byte_off;
+          unsigned int* wp = reinterpret_cast<unsigned int*>(addr & ~(uintptr_t)3);
+          unsigned int bit = 1u << (8 * (addr & 3) + (idx & 7));
+          unsigned int old = atomicOr(wp, bit);
+          w = (old & bit) ? 1 : 0;
+        }
+        break;
+      }
+      if (r > rem) break;
+      idx = e + 1;
+    }
+  }
+  counts[i] = cnt;
+  if (SET) was[i] = w;
+}
+
+// ------------------------------------------------------------- decode -------
+// Image -> sorted (key,count) list, one thread per block-aligned group of quotients.
+// Pass 1 (WRITE=false) counts entries per block of quotients; pass 2 writes them at out_off[b].
+template <bool WRITE>
+__global__ void decode_blocks_kernel(ImageView im, uint32_t* __restrict__ n_entries, const uint64_t* __restrict__ out_off,
+                                     uint64_t* __restrict__ out_keys, uint32_t* __restrict__ out_counts, int* __restrict__ err) {
+  uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= im.nblocks) return;
+  uint64_t occ = ld64u(blk(im, b) + 1);
+  uint32_t cnt = 0;
+  uint64_t o = WRITE ? out_off[b] : 0;
+  if (occ) {
+    uint64_t q0 = 64 * b + (__ffsll((long long)occ) - 1);
+    uint64_t rs = q0 == 0 ? 0 : img_run_end(im, q0 - 1) + 1;
+    if (rs < q0) rs = q0;
+    while (occ) {
+      int bitp = __ffsll((long long)occ) - 1; occ &= occ - 1;
+      uint64_t q = 64 * b + bitp;
+      if (rs < q) rs = q;
+      uint64_t re = rs;
+      while (re < im.xnslots && !img_bit(im, re, 1)) re++;
+      uint64_t idx = rs;
+      while (idx <= re) {
+        uint32_t r; uint64_t c;
+        uint64_t e = img_decode(im, idx, re, &r, &c);
+        if (WRITE) {
+          out_keys[o + cnt] = ((q + im.q_base) << 8) | r;
+          if (c > 0xFFFFFFFFull) { *err = SHQ_ERR_COUNT_OVERFLOW; c = 0xFFFFFFFFull; }
+          out_counts[o + cnt] = (uint32_t)c;
+        }
+        cnt++;
+        idx = e + 1;
+      }
+      rs = re + 1;
+    }
+  }
+  if (!WRITE) n_entries[b] = cnt;
+}
+
+}  // namespace shq

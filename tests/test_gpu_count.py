@@ -1,0 +1,146 @@
+"""Parity of the CUDA counting path (through the C ABI) against the oracle.  -m gpu."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def fastq(po, **kw):
+    return po.synth_fastq(**kw)
+
+
+def test_hash_matches_oracle(po, shq):
+    q = shq.CQF(20, 28)
+    for K, kw in [(31, dict(G=20000, cov=5)), (47, dict(G=20000, cov=4, seed=3)), (21, dict(G=5000, cov=6, L=63, seed=5)),
+                  (31, dict(G=20000, cov=4, n_rate=0.01, seed=9)), (5, dict(G=3000, cov=3, L=40, n_rate=0.05, seed=11)),
+                  (200, dict(G=30000, cov=5, L=700, n_rate=0.002, seed=13))]:
+        text = fastq(po, **kw)
+        want = np.sort(po.reads_to_keys(text, K, 28))
+        got = np.sort(q.hash_fastq_chunk(text, K))
+        assert len(got) == len(want), (K, len(got), len(want))
+        assert (got == want).all(), K
+    q.close()
+
+
+def test_hash_odd_bytes(po, shq):
+    # lower case, IUPAC letters, raw low bytes, reads shorter than K, empty sequence lines
+    recs = [b"ACGTNNNNacgtRYKMSWacgtacgtacgtacgtACGTACGTACGTACGTAAAACCCCGGGGTTTT", b"ACG", b"",
+            b"N" * 40, b"ACGTACGTACGTACGTACGTACGTACGTACGTACGTNACGTACGTACGTACGTACGTACGTACGTACGTACGTAN",
+            bytes([1, 3, 4, 7]) * 12 + b"ACGTACGTAC", b"ACGT" * 100 + b"N" + b"TTGA" * 50]
+    text = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, r, b"I" * len(r)) for i, r in enumerate(recs))
+    q = shq.CQF(16, 24)
+    for K in (4, 11, 31):
+        want = np.sort(po.reads_to_keys(text, K, 24))
+        got = np.sort(q.hash_fastq_chunk(text, K))
+        assert len(got) == len(want) and (got == want).all(), K
+    q.close()
+
+
+def test_malformed_chunk_is_an_error(po, shq):
+    q = shq.CQF(16, 24)
+    with pytest.raises(shq.ShqError) as e:
+        q.insert_fastq_chunk(b"@r\nACGTACGTACGT\n+\n", 5)
+        q.sync()
+    assert e.value.status == 4
+    q.close()
+
+
+@pytest.mark.parametrize("qb,nk", [(10, 600), (14, 9000), (18, 150000), (22, 3000000)])
+def test_insert_keys_image_matches_oracle(po, shq, qb, nk):
+    hb = qb + 8
+    rng = np.random.default_rng(qb)
+    base = rng.integers(0, 1 << hb, size=nk // 3, dtype=np.uint64)
+    keys = np.concatenate([base, base[: nk // 6], base[: nk // 12], rng.integers(0, 1 << hb, size=nk // 2, dtype=np.uint64),
+                           np.repeat(base[:5], 300), np.repeat(base[5:6], 20000),
+                           np.array([0, 0, 0, 255, 256, (1 << hb) - 1, (1 << hb) - 1], np.uint64)])
+    rng.shuffle(keys)
+    o = po.OracleCqf(qb, hb)
+    o.insert_keys(keys)
+    g = shq.CQF(qb, hb)
+    half = len(keys) // 2
+    g.insert_keys(keys[:half])
+    g.insert_keys(keys[half:])
+    assert g.counts() == o.counts()
+    gk, gc = g.iterate()
+    ok, oc = o.iterate()
+    assert len(gk) == len(ok) and (gk == ok).all() and (gc == oc).all()
+    assert g.export() == o.export()
+    # deNoise twice (second is a no-op apart from the range-end quirk)
+    for _ in range(2):
+        assert g.denoise() == o.denoise()
+        assert g.counts() == o.counts()
+        assert g.export() == o.export()
+    g.close()
+
+
+def test_capacity_error(shq):
+    g = shq.CQF(8, 16)
+    keys = np.arange(0, 600, dtype=np.uint64) * 97 % (1 << 16)
+    g.insert_keys(keys)
+    with pytest.raises(shq.ShqError) as e:
+        g.export()
+    assert e.value.status == 3
+    g.close()
+
+
+def test_fastq_counting_matches_oracle(po, shq):
+    K, qb = 31, 20
+    text = fastq(po, G=60000, cov=30, err=0.004, n_rate=0.0005, seed=21)
+    files = [text]
+    o, rounds = po.count_run(files, K, qb, qb + 8, 0, 0, False)
+    g = shq.CQF(qb, qb + 8)
+    for _, ch in po.chunks(files):
+        g.insert_fastq_chunk(ch, K)
+    g.finish()
+    assert g.counts() == o.counts()
+    assert g.export() == o.export()
+    g.close()
+
+
+@pytest.mark.parametrize("rounds,end", [(1, True), (3, False), (2, True)])
+def test_denoise_schedule_matches_oracle(po, shq, rounds, end):
+    """Mid-stream rounds pinned to reference chunk boundaries (t=1), several files round-robin."""
+    K, qb = 25, 22
+    files = [fastq(po, G=150000, cov=25, err=0.01, seed=31 + i, L=100) for i in range(3)]
+    part = 1 << 20          # small parts so that the run has ~30 chunks
+    total_distinct = len(np.unique(np.concatenate([po.reads_to_keys(f, K, qb + 8) for f in files])))
+    trigger = total_distinct // (rounds + 1)
+    o, o_rounds = po.count_run(files, K, qb, qb + 8, trigger, rounds, end, part_size=part)
+    g = shq.CQF(qb, qb + 8)
+    g.set_denoise_schedule(trigger, rounds, end)
+    for _, ch in po.chunks(files, part_size=part):
+        g.insert_fastq_chunk(ch, K)
+    g.finish()
+    assert g.rounds_done() == o_rounds
+    assert g.counts() == o.counts()
+    assert g.export() == o.export()
+    g.close()
+
+
+def test_load_query_roundtrip(po, shq, tmp_path):
+    qb, hb = 16, 24
+    rng = np.random.default_rng(5)
+    keys = rng.integers(0, 1 << hb, size=50000, dtype=np.uint64)
+    keys = np.concatenate([keys, keys[:20000], np.repeat(keys[:3], 1000)])
+    o = po.OracleCqf(qb, hb)
+    o.insert_keys(keys)
+    img = o.export()
+    path = str(tmp_path / "t.cqf")
+    open(path, "wb").write(img)
+    g = shq.CQF.load(path)
+    assert g.export() == img
+    q = np.concatenate([keys[:3000], rng.integers(0, 1 << hb, size=3000, dtype=np.uint64)])
+    q = np.unique(q)                      # distinct keys: duplicate order inside a batch is unspecified
+    oc, ow = o.query_batch(q)
+    gc, gw = g.query_set_traveled(q)
+    assert (gc == oc).all() and (gw == ow).all()
+    oc, ow = o.query_batch(q)             # second time: traveled bits now set
+    gc, gw = g.query_set_traveled(q)
+    assert (gc == oc).all() and (gw == ow).all()
+    assert g.export() == o.export()       # traveled words included
+    gk, gcnt = g.iterate()
+    ok, ocnt = o.iterate()
+    assert (gk == ok).all() and (gcnt == ocnt).all()
+    g.save(path)
+    assert open(path, "rb").read() == o.export()
+    g.close()

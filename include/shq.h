@@ -51,6 +51,8 @@ const char* shq_last_error(shq_t h);      /* detail of the last failure on this 
 int shq_create(int qb, int hb, uint32_t seed, int device, shq_t* out);
 int shq_create_shard(int qb, int hb, uint32_t seed, int device, int shard, int nshards, shq_t* out);
 void shq_destroy(shq_t h);
+/* replaces qf_reset (cqf/gqf.c:2292-2304): empty filter, schedule cleared, device buffers kept. */
+int shq_reset(shq_t h);
 
 /* ---- counting -------------------------------------------------------------
  * shq_set_denoise_schedule: the arguments of CQF_mt::build_KmerSpectrum
@@ -143,6 +145,40 @@ int shq_unitigs_write_fasta(shq_unitigs_t u, const char* path);
 /* FASTA text into a caller buffer (cap=0: size query) */
 int shq_unitigs_fasta(shq_unitigs_t u, char* dst, size_t cap, size_t* written);
 void shq_unitigs_free(shq_unitigs_t u);
+
+/* ---- host-side readers and drivers (C++ behind a C ABI) ---------------------------
+ * shq_reader_*: seqFile_batch + fastq_read_parts + getFileReader
+ * (cqf/CQF_mt.h:334-412, 735-816, 933-957; cqf/reader.h): files are read in 2^23-byte
+ * parts cut at a FASTQ record boundary and handed out round-robin over the file list,
+ * i.e. the chunk sequence one reference worker thread would see.  fmode: 'f' plain,
+ * 'g' gzip, 'b' bzip2 (the reference's -f option).                                  */
+typedef struct shq_reader_s* shq_reader_t;
+int shq_reader_open(const char* const* paths, int nfiles, char fmode, shq_reader_t* out);
+int shq_reader_open_memory(const char* const* bufs, const size_t* lens, int nfiles, uint64_t part_size,
+                           shq_reader_t* out);
+/* next chunk; *chunk == NULL at the end.  The buffer stays valid until the next call. */
+int shq_reader_next(shq_reader_t r, const char** chunk, size_t* n, int* file_index);
+void shq_reader_close(shq_reader_t r);
+/* CQF_mt::build_KmerSpectrum (cqf/CQF_mt.h:959-995): every chunk of the reader goes into the
+ * filter under the schedule set by shq_set_denoise_schedule, then shq_finish.           */
+int shq_build_kmer_spectrum(shq_t h, shq_reader_t r, int K);
+/* force the device image to be built now (normally lazy: export/save/query)             */
+int shq_materialize(shq_t h);
+
+/* parameter block of src/CQF-deNoise.cpp:83-161 (+ mean_CDF2deNoise, cqf/CQF_mt.h:94-133,
+ * true2falseKmer_DP, cqf/true2falseKmer_DP.cpp:12-51)                                   */
+typedef struct {
+  uint64_t num_true_kmers, num_false_kmers;
+  int num_deNoise;              /* effective number of mid-stream rounds */
+  int lower_bound, upper_bound; /* "#deNoise rounds leading to the same size of CQF" (0 = +oo) */
+  uint64_t qb, hb;
+  uint64_t trigger;             /* n_distinct_elts_for_DeNoise */
+  double fr;
+} shq_params;
+int shq_param_block(int K, uint64_t n_true_kmers, uint64_t total_kmers, double alpha, const char* error_profile,
+                    int deNoise, double fr, shq_params* out);
+double shq_cdfpoi_positive(double x, double mean);
+double shq_cdfpoi(double x, double mean);
 
 /* ---- instrumentation ----------------------------------------------------------- */
 typedef struct {

@@ -129,6 +129,9 @@ def ref():
         L.ref_qf_denoise_all_clusters.restype = C.c_uint64
         L.ref_qf_denoise_all_clusters.argtypes = [C.c_void_p]
         L.ref_qf_check.argtypes = [C.c_void_p]
+        L.ref_count_mt.restype = C.c_double
+        L.ref_count_mt.argtypes = [C.c_void_p, C.c_void_p, _u64p, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_int,
+                                   C.c_double, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         _ref = L
     return _ref
 
@@ -302,6 +305,14 @@ class RefCqf:
 
     def check(self):
         return self.L.ref_qf_check(self.h)
+
+    def count_mt(self, text_addr, chunk_ends, K, nthreads, trigger=0, rounds=0, end_denoise=False, max_seconds=0.0):
+        """Multi-threaded reference counting over text at text_addr; returns (seconds, kmers, chunks, rounds)."""
+        ce = np.ascontiguousarray(chunk_ends, np.uint64)
+        km, ch, rd = C.c_uint64(), C.c_uint64(), C.c_uint32()
+        secs = self.L.ref_count_mt(self.h, text_addr, _p(ce), len(ce), K, nthreads, trigger, rounds, 1 if end_denoise else 0,
+                                   max_seconds, C.byref(km), C.byref(ch), C.byref(rd))
+        return secs, km.value, ch.value, rd.value
 
 
 # ------------------------------------------------------- synthetic inputs

@@ -13,6 +13,11 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdio.h>
+#include <atomic>
+#include <chrono>
+#include <thread>
+#include <vector>
+#include <string>
 
 // gqf.h forward-declares this type; the real definition lives in CQF_mt.h
 // (boost-dependent, not buildable here).  An empty stub is enough because the
@@ -217,6 +222,120 @@ int ref_qf_check(void* h) {
   if (po != pr) return 1;
   if (!check_offset(qf)) return 2;
   return 0;
+}
+
+
+// ---- multi-threaded CPU baseline ---------------------------------------------------
+// Worker loop of fastq_to_uint64kmers_prod / reads_to_kmers (cqf/CQF_mt.h:610-731, 821-931)
+// with std::thread instead of boost::thread: every key goes through the REAL
+// qf_insert_advance(lock=true, spin=false); on a failed try-lock it is parked in a thread-local
+// 2^16-slot QF (QBITS_LOCAL_QF, CQF_mt.h:57) that is dumped into the main filter once it holds
+// more than 2^15 keys (:642-645, :588-607) and after every chunk (:833-836).
+// DeNoise rounds are run by one thread between extraction phases (the reference spreads the
+// sweep over its workers; the sweep is a few percent of the run).
+namespace {
+struct MtShared {
+  QF* main_qf; const char* text; const uint64_t* chunk_ends; uint64_t nchunks; int K;
+  std::atomic<uint64_t> next_chunk{0}, ndistinct{0}, nelts{0}, processed{0};
+  uint64_t trigger; std::atomic<uint32_t> rounds_left{0};
+  double max_seconds; std::chrono::steady_clock::time_point t0;
+  std::atomic<bool> out_of_time{false};
+};
+
+void dump_local(QF* local, QF* main_qf, MtShared* sh) {
+  uint64_t new_elts = 0, total = 0;
+  QFi it;
+  if (qf_iterator(local, &it, 0)) {
+    do {
+      uint64_t key = 0, value = 0, count = 0;
+      if (qfi_get(&it, &key, &value, &count)) break;
+      bool isNew = false;
+      qf_insert_advance(main_qf, key, 0, count, true, true, isNew);
+      if (isNew) new_elts++;
+      total += count;
+    } while (!qfi_next(&it));
+    qf_reset(local);
+  }
+  sh->ndistinct += new_elts; sh->nelts += total;
+}
+
+void mt_worker(MtShared* sh) {
+  QF local;
+  qf_init(&local, 1ULL << 16, sh->main_qf->metadata->key_bits, 0, true, "", sh->main_qf->metadata->seed);
+  uint32_t parked = 0;
+  const __uint128_t range = sh->main_qf->metadata->range;
+  const unsigned K = (unsigned)sh->K;
+  for (;;) {
+    if (sh->rounds_left.load() && sh->ndistinct.load() >= sh->trigger) break;      // CQF_mt.h:837
+    if (sh->max_seconds > 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - sh->t0).count() > sh->max_seconds) { sh->out_of_time = true; break; }
+    uint64_t c = sh->next_chunk.fetch_add(1);
+    if (c >= sh->nchunks) break;
+    const char* fs = sh->text + (c ? sh->chunk_ends[c - 1] : 0);
+    const char* end = sh->text + sh->chunk_ends[c];
+    uint64_t new_elts = 0, total_elts = 0, nput = 0;
+    auto put = [&](uint64_t hash) {
+      bool isNew = false; nput++;
+      if (!qf_insert_advance(sh->main_qf, hash % range, 0, 1, true, false, isNew)) {
+        qf_insert(&local, hash % range, 0, 1, false, false);
+        if (++parked > (1ULL << 15)) { dump_local(&local, sh->main_qf, sh); parked = 0; }
+      } else if (isNew) new_elts++; else total_elts++;
+    };
+    while (fs && fs != end) {
+      fs = (const char*)memchr(fs, '\n', end - fs); fs++;
+      const char* fe = (const char*)memchr(fs, '\n', end - fs);
+      std::string read(fs, fe - fs);
+      uint64_t hash, hash_RC;
+    start_read:
+      if (read.length() >= K) {
+        NTPC64(read.c_str(), K, hash, hash_RC);
+        put(hash < hash_RC ? hash : hash_RC);
+        for (uint32_t i = K; i < read.length(); i++) {
+          if (read[i] == 'N') { read = read.substr(i + 1, read.length()); goto start_read; }
+          NTPC64(read[i - K], read[i], K, hash, hash_RC);
+          put(hash < hash_RC ? hash : hash_RC);
+        }
+      }
+      fs = ++fe;
+      fs = (const char*)memchr(fs, '\n', end - fs); fs++;
+      fs = (const char*)memchr(fs, '\n', end - fs); fs++;
+    }
+    sh->ndistinct += new_elts; sh->nelts += new_elts + total_elts; sh->processed += nput;
+    if (parked) { dump_local(&local, sh->main_qf, sh); parked = 0; }
+  }
+  qf_destroy(&local, true);
+}
+}  // namespace
+
+// Returns elapsed seconds.  Stops taking new chunks after max_seconds (0 = no limit).
+double ref_count_mt(void* h, const char* text, const uint64_t* chunk_ends, uint64_t nchunks, int K, int nthreads,
+                    uint64_t trigger, uint32_t rounds, int end_denoise, double max_seconds, uint64_t* kmers_done,
+                    uint64_t* chunks_done, uint32_t* rounds_done) {
+  MtShared sh;
+  sh.main_qf = (QF*)h; sh.text = text; sh.chunk_ends = chunk_ends; sh.nchunks = nchunks; sh.K = K;
+  sh.trigger = trigger; sh.rounds_left = rounds; sh.max_seconds = max_seconds;
+  sh.t0 = std::chrono::steady_clock::now();
+  uint32_t done_rounds = 0;
+  for (;;) {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++) th.emplace_back(mt_worker, &sh);
+    for (auto& t : th) t.join();
+    bool files_left = sh.next_chunk.load() < nchunks && !sh.out_of_time;
+    bool need = sh.rounds_left.load() && sh.ndistinct.load() >= sh.trigger;
+    if (need || (end_denoise && !files_left)) {                                    // CQF_mt.h:860
+      if (sh.rounds_left.load()) sh.rounds_left--;
+      uint64_t removed = ref_qf_denoise(h);
+      sh.ndistinct -= removed; sh.nelts -= removed;
+      done_rounds++;
+    }
+    if (!files_left) break;
+  }
+  double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - sh.t0).count();
+  QF* qf = (QF*)h;
+  qf->metadata->nelts = sh.nelts; qf->metadata->ndistinct_elts = sh.ndistinct;
+  if (kmers_done) *kmers_done = sh.processed.load();
+  if (chunks_done) *chunks_done = sh.next_chunk.load() < nchunks ? sh.next_chunk.load() : nchunks;
+  if (rounds_done) *rounds_done = done_rounds;
+  return secs;
 }
 
 }  // extern "C"

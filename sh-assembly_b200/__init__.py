@@ -39,9 +39,15 @@ class shq_unitig_opts(C.Structure):
                 ("solid_abundance_max", C.c_int)]
 
 
+class shq_params(C.Structure):
+    _fields_ = [("num_true_kmers", C.c_uint64), ("num_false_kmers", C.c_uint64), ("num_deNoise", C.c_int),
+                ("lower_bound", C.c_int), ("upper_bound", C.c_int), ("qb", C.c_uint64), ("hb", C.c_uint64),
+                ("trigger", C.c_uint64), ("fr", C.c_double)]
+
+
 def build(verbose=False):
     """Compile libshq.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    r = subprocess.run(["make", "-C", HERE, "libshq.so"], capture_output=True, text=True)
+    r = subprocess.run(["make", "-C", HERE, "all"], capture_output=True, text=True)
     if verbose or r.returncode:
         print(r.stdout[-4000:], r.stderr[-4000:])
     if r.returncode:
@@ -53,12 +59,14 @@ _lib = None
 
 # every symbol include/shq.h declares
 EXPORTS = [
-    "shq_strerror", "shq_last_error", "shq_create", "shq_create_shard", "shq_destroy", "shq_set_denoise_schedule",
+    "shq_strerror", "shq_last_error", "shq_create", "shq_create_shard", "shq_destroy", "shq_reset", "shq_set_denoise_schedule",
     "shq_insert_fastq_chunk", "shq_insert_fastq_device", "shq_insert_keys", "shq_insert_keys_device", "shq_finish",
     "shq_sync", "shq_counts", "shq_rounds_done", "shq_denoise", "shq_image_size", "shq_export_cqf", "shq_save",
     "shq_load", "shq_load_image", "shq_geometry", "shq_iterate", "shq_query_set_traveled", "shq_query",
     "shq_hash_fastq_chunk", "shq_unitigs_begin", "shq_unitigs_add_reads", "shq_unitigs_build", "shq_unitigs_count",
     "shq_unitigs_write_fasta", "shq_unitigs_fasta", "shq_unitigs_free", "shq_get_stats", "shq_reset_stats", "shq_stream",
+    "shq_reader_open", "shq_reader_open_memory", "shq_reader_next", "shq_reader_close", "shq_build_kmer_spectrum",
+    "shq_materialize", "shq_param_block", "shq_cdfpoi_positive", "shq_cdfpoi",
 ]
 
 
@@ -78,6 +86,7 @@ def lib():
         L.shq_create_shard.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
         L.shq_destroy.argtypes = [vp]
         L.shq_destroy.restype = None
+        L.shq_reset.argtypes = [vp]
         L.shq_set_denoise_schedule.argtypes = [vp, u64, C.c_uint32, C.c_int]
         L.shq_insert_fastq_chunk.argtypes = [vp, vp, sz, C.c_int]
         L.shq_insert_fastq_device.argtypes = [vp, vp, sz, vp, sz, C.c_int]
@@ -110,8 +119,78 @@ def lib():
         L.shq_reset_stats.argtypes = [vp]
         L.shq_stream.restype = vp
         L.shq_stream.argtypes = [vp]
+        L.shq_reader_open.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_char, C.POINTER(vp)]
+        L.shq_reader_open_memory.argtypes = [C.POINTER(vp), C.POINTER(sz), C.c_int, u64, C.POINTER(vp)]
+        L.shq_reader_next.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(C.c_int)]
+        L.shq_reader_close.argtypes = [vp]
+        L.shq_reader_close.restype = None
+        L.shq_build_kmer_spectrum.argtypes = [vp, vp, C.c_int]
+        L.shq_materialize.argtypes = [vp]
+        L.shq_param_block.argtypes = [C.c_int, u64, u64, C.c_double, C.c_char_p, C.c_int, C.c_double, C.POINTER(shq_params)]
+        L.shq_cdfpoi_positive.restype = C.c_double
+        L.shq_cdfpoi_positive.argtypes = [C.c_double, C.c_double]
+        L.shq_cdfpoi.restype = C.c_double
+        L.shq_cdfpoi.argtypes = [C.c_double, C.c_double]
         _lib = L
     return _lib
+
+
+def param_block(K, n_true, N_total, alpha=-1.0, error_profile="", deNoise=-1, fr=0.0):
+    """src/CQF-deNoise.cpp:83-161 through the C ABI."""
+    out = shq_params()
+    rc = lib().shq_param_block(K, n_true, N_total, alpha, error_profile.encode(), deNoise, fr, C.byref(out))
+    if rc:
+        raise ShqError(rc, "shq_param_block")
+    return out
+
+
+class Reader:
+    """seqFile_batch (cqf/CQF_mt.h:334-412): chunks in the reference's t=1 order."""
+
+    def __init__(self, paths=None, fmode="f", buffers=None, part_size=0):
+        self.L = lib()
+        h = C.c_void_p()
+        if buffers is not None:
+            self._keep = [np.frombuffer(b, np.uint8) for b in buffers]
+            ptrs = (C.c_void_p * len(buffers))(*[a.ctypes.data for a in self._keep])
+            lens = (C.c_size_t * len(buffers))(*[a.nbytes for a in self._keep])
+            rc = self.L.shq_reader_open_memory(ptrs, lens, len(buffers), part_size, C.byref(h))
+        else:
+            arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+            rc = self.L.shq_reader_open(arr, len(paths), fmode.encode(), C.byref(h))
+        if rc:
+            raise ShqError(rc, "shq_reader_open")
+        self.h = h
+
+    def __iter__(self):
+        return self
+
+    def next_raw(self):
+        """(address, size, file_index) of the next chunk, or None; valid until the next call."""
+        p, n, fi = C.c_void_p(), C.c_size_t(), C.c_int()
+        rc = self.L.shq_reader_next(self.h, C.byref(p), C.byref(n), C.byref(fi))
+        if rc:
+            raise ShqError(rc, "shq_reader_next")
+        if not p.value:
+            return None
+        return p.value, n.value, fi.value
+
+    def __next__(self):
+        r = self.next_raw()
+        if r is None:
+            raise StopIteration
+        return r[2], C.string_at(r[0], r[1])
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.shq_reader_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _buf(b):
@@ -157,6 +236,9 @@ class CQF:
         except Exception:
             pass
 
+    def reset(self):
+        self._check(self.L.shq_reset(self.h))
+
     # --- counting
     def set_denoise_schedule(self, trigger, rounds, end_denoise):
         self._check(self.L.shq_set_denoise_schedule(self.h, trigger, rounds, 1 if end_denoise else 0))
@@ -178,6 +260,15 @@ class CQF:
 
     def finish(self):
         self._check(self.L.shq_finish(self.h))
+
+    def materialize(self):
+        self._check(self.L.shq_materialize(self.h))
+
+    def build_kmer_spectrum(self, reader, K):
+        self._check(self.L.shq_build_kmer_spectrum(self.h, reader.h, K))
+
+    def insert_fastq_chunk_raw(self, addr, n, K):
+        self._check(self.L.shq_insert_fastq_chunk(self.h, addr, n, K))
 
     def sync(self):
         self._check(self.L.shq_sync(self.h))

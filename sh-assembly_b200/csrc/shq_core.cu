@@ -580,6 +580,16 @@ int shq_create_shard(int qb, int hb, uint32_t seed, int device, int shard, int n
 }
 int shq_create(int qb, int hb, uint32_t seed, int device, shq_t* out) { return shq_create_shard(qb, hb, seed, device, 0, 1, out); }
 void shq_destroy(shq_t h) { free_handle(h); }
+int shq_reset(shq_t h) {
+  if (!h) return SHQ_ERR_ARG;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->n_state = 0; h->ndistinct = 0; h->nelts = 0;
+  h->image_valid = false; h->image_only = false;
+  h->trigger = 0; h->rounds_left = 0; h->end_denoise = false; h->rounds_done = 0; h->finished = false;
+  h->h_stage_fill = 0; h->stage_chunk_ends.clear();
+  return SHQ_OK;
+}
 
 int shq_set_denoise_schedule(shq_t h, uint64_t trigger, uint32_t rounds, int end_denoise) {
   if (!h) return SHQ_ERR_ARG;
@@ -621,11 +631,15 @@ int shq_insert_fastq_device(shq_t h, const char* d_text, size_t n, const uint64_
       size_t c1 = c0;
       while (c1 < a.nc && a.ce[c1] - base <= h->max_batch_bytes) c1++;
       if (c1 == c0) c1 = c0 + 1;
-      if (base & 15) SHQ_FAIL(SHQ_ERR_ARG, "batch boundary at byte %llu is not 16-byte aligned; pass fewer, larger calls or aligned chunks",
-                              (unsigned long long)base);
       std::vector<uint64_t> ends(a.ce + c0, a.ce + c1);
       for (auto& e : ends) e -= base;
-      process_batch(h, a.t + base, ends.back(), ends.data(), (int)ends.size(), a.K, nullptr, 0);
+      const char* src = a.t + base;
+      if (reinterpret_cast<uintptr_t>(src) & 15) {   // vector loads need 16-byte alignment: stage a device copy
+        h->d_text.reserve(ends.back() + 64);
+        SHQ_CUDA(cudaMemcpyAsync(h->d_text.p, src, ends.back(), cudaMemcpyDeviceToDevice, h->stream));
+        src = h->d_text.as<char>();
+      }
+      process_batch(h, src, ends.back(), ends.data(), (int)ends.size(), a.K, nullptr, 0);
       c0 = c1;
     }
   SHQ_API_END
@@ -890,6 +904,17 @@ int shq_hash_fastq_chunk(shq_t h, const char* text, size_t n, int K, uint64_t* k
     if (m && a.keys) SHQ_CUDA(cudaMemcpyAsync(a.keys, h->d_q_cnt.p, m * 8, cudaMemcpyDeviceToHost, st));
     SHQ_CUDA(cudaStreamSynchronize(st));
     h->stats.h2d_bytes += a.n; h->stats.d2h_bytes += m * 8;
+  SHQ_API_END
+}
+
+int shq_materialize(shq_t h) {
+  if (!h) return SHQ_ERR_ARG;
+  int args = 0;
+  SHQ_API_BEGIN(h)
+    (void)a;
+    flush_stage(h);
+    if (!h->image_only) materialise(h);
+    SHQ_CUDA(cudaStreamSynchronize(h->stream));
   SHQ_API_END
 }
 

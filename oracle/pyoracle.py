@@ -80,6 +80,15 @@ def oracle():
         L.orc_true2falseKmer_DP.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t]
         L.orc_ntpc64_base.argtypes = [C.c_char_p, C.c_uint, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.orc_ntpc64_roll.argtypes = [C.c_ubyte, C.c_ubyte, C.c_uint, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.orc_contiger_run.restype = C.c_void_p
+        L.orc_contiger_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_uint64,
+                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_contiger_fasta_size.restype = C.c_uint64
+        L.orc_contiger_fasta_size.argtypes = [C.c_void_p]
+        L.orc_contiger_fasta.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_contiger_queries.restype = C.c_uint64
+        L.orc_contiger_queries.argtypes = [C.c_void_p]
+        L.orc_contiger_free.argtypes = [C.c_void_p]
         _orc = L
     return _orc
 
@@ -361,3 +370,66 @@ def synth_fastq(G=100000, cov=20, L=150, err=0.002, seed=42, n_rate=0.0, genome=
     out[:, o + 4 + L:o + 4 + 2 * L] = ord("I")
     out[:, o + 4 + 2 * L] = ord("\n")
     return out.tobytes()
+
+
+# ------------------------------------------------------------------ Contiger
+def contiger_run(cqf: "OracleCqf", files, K, s_min=2, x_min=2, x_max=1000000, master_rule=False, lifo=False, part_size=1 << 23):
+    """Sequential Contiger restatement; returns (fasta_text, n_queries).  Mutates cqf's traveled bits."""
+    L = oracle()
+    bufs = (C.c_char_p * len(files))(*files)
+    lens = (C.c_size_t * len(files))(*[len(f) for f in files])
+    hb = np.frombuffer(cqf.export()[32:40], np.uint64)[0]
+    r = L.orc_contiger_run(cqf.h, int(hb), len(files), bufs, lens, part_size, K, s_min, x_min, x_max,
+                           (1 if master_rule else 0) | (2 if lifo else 0))
+    n = L.orc_contiger_fasta_size(r)
+    buf = C.create_string_buffer(n)
+    L.orc_contiger_fasta(r, buf)
+    nq = L.orc_contiger_queries(r)
+    L.orc_contiger_free(r)
+    return buf.raw[:n].decode(), nq
+
+
+def parse_unitigs(fasta: str):
+    """[(header_fields, seq)] from BCALM-style unitig FASTA."""
+    out = []
+    lines = fasta.split("\n")
+    for i in range(0, len(lines) - 1, 2):
+        if lines[i].startswith(">"):
+            out.append((lines[i][1:].split(" "), lines[i + 1]))
+    return out
+
+
+_COMP = bytes.maketrans(b"ACGT", b"TGCA")
+
+
+def revcomp(s: str) -> str:
+    return s.encode().translate(_COMP)[::-1].decode()
+
+
+def canonical_unitig_set(fasta: str):
+    """Sorted list of min(seq, RC(seq)) -- the orientation/numbering-free view used for parity."""
+    return sorted(min(s, revcomp(s)) for _, s in parse_unitigs(fasta))
+
+
+def canonical_links(fasta: str):
+    """Link structure up to renumbering/orientation: set of ((canon_seq_a, end_a), (canon_seq_b, end_b)) where
+    end is 'L' or 'R' of the canonical orientation."""
+    us = parse_unitigs(fasta)
+    canon = []
+    for _, s in us:
+        r = revcomp(s)
+        canon.append((min(s, r), s <= r))      # (canonical seq, stored orientation is canonical?)
+    links = set()
+    for i, (hdr, s) in enumerate(us):
+        for f in hdr:
+            if f.startswith("L:"):
+                _, side, j, orient = f.split(":")
+                j = int(j)
+                # this unitig's end: '+' side = its right end in stored orientation
+                a_end_right = (side == "+")
+                a = (canon[i][0], "R" if a_end_right == canon[i][1] else "L")
+                # neighbour entered at its left end if orient '+', right end if '-'
+                b_left = (orient == "+")
+                b = (canon[j][0], "L" if b_left == canon[j][1] else "R")
+                links.add((a, b))
+    return links

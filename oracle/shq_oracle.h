@@ -77,6 +77,15 @@ double orc_cdfpoi_positive(double x, double mean);
 int orc_mean_CDF2deNoise(double mean, double cdf_desired);
 double orc_true2falseKmer_DP(const double* base_errors, size_t seq_len, size_t K);
 
+/* Contiger (src/contig_assembly.cpp live parts), sequential restatement; see contiger_oracle.cpp.
+ * flags: bit0 = master seed rule (len/2) instead of worker rule (len/2 - K/2); bit1 = LIFO job order. */
+void* orc_contiger_run(void* cqf, int hb, int nfiles, const char* const* bufs, const size_t* lens, uint64_t part_size,
+                       int K, int s_min, int x_min, int x_max, int flags);
+uint64_t orc_contiger_fasta_size(void* r);
+void orc_contiger_fasta(void* r, char* dst);
+uint64_t orc_contiger_queries(void* r);
+void orc_contiger_free(void* r);
+
 #ifdef __cplusplus
 }
 #endif

@@ -120,8 +120,8 @@ def test_denoise_schedule_matches_oracle(po, shq, rounds, end):
 def test_load_query_roundtrip(po, shq, tmp_path):
     qb, hb = 16, 24
     rng = np.random.default_rng(5)
-    keys = rng.integers(0, 1 << hb, size=50000, dtype=np.uint64)
-    keys = np.concatenate([keys, keys[:20000], np.repeat(keys[:3], 1000)])
+    keys = rng.integers(0, 1 << hb, size=30000, dtype=np.uint64)
+    keys = np.concatenate([keys, keys[:12000], np.repeat(keys[:3], 1000)])
     o = po.OracleCqf(qb, hb)
     o.insert_keys(keys)
     img = o.export()

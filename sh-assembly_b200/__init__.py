@@ -144,6 +144,26 @@ def param_block(K, n_true, N_total, alpha=-1.0, error_profile="", deNoise=-1, fr
     return out
 
 
+def build_unitigs(cqf, chunks, K, s_min=2, x_min=2, x_max=1000000):
+    """Contiger device path: returns the unitig FASTA text (BCALM/Minia style headers)."""
+    L = lib()
+    opts = shq_unitig_opts(K, s_min, x_min, x_max)
+    u = C.c_void_p()
+    cqf._check(L.shq_unitigs_begin(cqf.h, C.byref(opts), C.byref(u)))
+    try:
+        for ch in chunks:
+            p, n, keep = _buf(ch)
+            cqf._check(L.shq_unitigs_add_reads(u, p, n))
+        cqf._check(L.shq_unitigs_build(u))
+        w = C.c_size_t()
+        cqf._check(L.shq_unitigs_fasta(u, None, 0, C.byref(w)))
+        buf = C.create_string_buffer(max(1, w.value))
+        cqf._check(L.shq_unitigs_fasta(u, buf, w.value, C.byref(w)))
+        return buf.raw[:w.value].decode()
+    finally:
+        L.shq_unitigs_free(u)
+
+
 class Reader:
     """seqFile_batch (cqf/CQF_mt.h:334-412): chunks in the reference's t=1 order."""
 

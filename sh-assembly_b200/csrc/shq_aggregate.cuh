@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(256) compact_bins_kernel(const uint32_t* __res
 constexpr int kMergeThreads = 256;
 constexpr int kMergeItems = 8;
 constexpr int kMergeTile = kMergeThreads * kMergeItems;
+constexpr int kMergeHistMax = 1024;
 
 __device__ __forceinline__ size_t merge_path_search(const uint64_t* A, size_t na, const uint64_t* B, size_t nb, size_t diag) {
   size_t lo = diag > nb ? diag - nb : 0, hi = diag < na ? diag : na;
@@ -181,6 +182,9 @@ __global__ void __launch_bounds__(kMergeThreads) merge_tiles_kernel(
     uint32_t* __restrict__ out_counts, uint32_t* __restrict__ chunk_hist, int* __restrict__ err) {
   __shared__ uint64_t s_a[kMergeTile + 2];
   __shared__ uint64_t s_b[kMergeTile + 2];
+  __shared__ uint32_t s_hist[kMergeHistMax];   // per-CTA histogram of first-chunk ids of new keys
+  const bool use_hist = !WRITE && chunk_hist != nullptr;
+  if (use_hist) for (int i = threadIdx.x; i < kMergeHistMax; i += blockDim.x) s_hist[i] = 0;
   const size_t t = blockIdx.x;
   size_t diag0 = t * kMergeTile, diag1 = diag0 + kMergeTile;
   if (diag1 > na + nb) diag1 = na + nb;
@@ -217,7 +221,10 @@ __global__ void __launch_bounds__(kMergeThreads) merge_tiles_kernel(
       uint64_t preva = s_a[ai];  // s_a[ai] is A[a0+ai-1] (s_a[0] = A[a0-1] or sentinel)
       if (preva != k || (ai == 0 && a0 == 0)) {
         if (WRITE) { okey[nheads] = k; ocnt[nheads] = Bc[b0 + bi]; }
-        else if (chunk_hist) atomicAdd(&chunk_hist[Bchunk ? Bchunk[b0 + bi] : 0], 1u);
+        else if (use_hist) {
+          uint32_t ch = Bchunk ? Bchunk[b0 + bi] : 0;
+          if (ch < (uint32_t)kMergeHistMax) atomicAdd(&s_hist[ch], 1u); else atomicAdd(&chunk_hist[ch], 1u);
+        }
         nheads++;
       }
       bi++;
@@ -227,6 +234,9 @@ __global__ void __launch_bounds__(kMergeThreads) merge_tiles_kernel(
   uint32_t rank = block_exclusive_scan<SumU32>(nheads, &tot);
   if (!WRITE) {
     if (threadIdx.x == 0) heads[t] = tot;
+    if (use_hist) {   // block_exclusive_scan ended with a barrier: every s_hist update is visible
+      for (int i = threadIdx.x; i < kMergeHistMax; i += blockDim.x) { uint32_t v = s_hist[i]; if (v) atomicAdd(&chunk_hist[i], v); }
+    }
   } else {
     size_t o = out_off[t] + rank;
     for (uint32_t i = 0; i < nheads; i++) { out_keys[o + i] = okey[i]; out_counts[o + i] = ocnt[i]; }

@@ -1,19 +1,863 @@
-// shq_unitig.cuh -- Contiger device path (K6-K8).  Placeholder until the counting path is
-// parity-green on the GPU: the entry points exist so that the ABI is complete, and report
-// SHQ_ERR_STATE instead of silently doing nothing.
+// shq_unitig.cuh -- Contiger device path (K6-K8): unitig contraction over the CQF image.
+//
+// Replaces find_unitigs_mt_master / get_unitig_forward / check_unitig / track_kmer_worker /
+// build_graph_worker (reference src/contig_assembly.cpp:2034-2172, 3028-3218, 935-1084).
+// The reference walks one unitig per thread with 7 dependent CQF probes per base.  Here:
+//   U1  every read window whose key is present (count >= s) becomes a node: canonical 2-bit k-mer in a
+//       device hash table (exact strings, so two k-mers sharing a CQF key stay two nodes);
+//   U3  one thread per node issues the 8 neighbour queries (4 successors per strand) on the image,
+//       resolves neighbour ids, and closes over false-positive neighbours that no read contains;
+//   U4  simple links (out-degree 1 meeting in-degree 1) form chains; pointer jumping ranks them;
+//   U5  chains become unitig sequences in parallel; one strand per unitig is kept;
+//   U6  links between unitig ends, connected components (union-find) and the seed rule
+//       (a component is reported iff it holds a read-middle k-mer with x <= count <= X).
 #pragma once
+#include "shq_common.cuh"
+#include "shq_layout.cuh"
+#include "shq_scan.cuh"
+
+namespace shq {
+
+struct Kmer { uint64_t hi, lo; };
+__host__ __device__ __forceinline__ bool kmer_less(Kmer a, Kmer b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
+__host__ __device__ __forceinline__ bool kmer_eq(Kmer a, Kmer b) { return a.hi == b.hi && a.lo == b.lo; }
+__host__ __device__ __forceinline__ Kmer kmer_mask(int K) {
+  Kmer m;
+  int bits = 2 * K;
+  m.lo = bits >= 64 ? ~0ULL : ((1ULL << bits) - 1);
+  m.hi = bits <= 64 ? 0 : (bits >= 128 ? ~0ULL : ((1ULL << (bits - 64)) - 1));
+  return m;
+}
+__host__ __device__ __forceinline__ Kmer kmer_push_right(Kmer k, uint32_t code, Kmer mask) {   // k[1:] + code
+  Kmer r;
+  r.hi = ((k.hi << 2) | (k.lo >> 62)) & mask.hi;
+  r.lo = ((k.lo << 2) | code) & mask.lo;
+  return r;
+}
+__host__ __device__ __forceinline__ uint32_t kmer_base(Kmer k, int K, int i) {   // code of base i (0 = first)
+  int sh = 2 * (K - 1 - i);
+  return sh >= 64 ? (uint32_t)((k.hi >> (sh - 64)) & 3) : (uint32_t)((k.lo >> sh) & 3);
+}
+__host__ __device__ __forceinline__ uint64_t rev_pairs64(uint64_t x) {
+  // reverse the order of the 32 two-bit groups
+  x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+  x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+  x = ((x >> 8) & 0x00FF00FF00FF00FFULL) | ((x & 0x00FF00FF00FF00FFULL) << 8);
+  x = ((x >> 16) & 0x0000FFFF0000FFFFULL) | ((x & 0x0000FFFF0000FFFFULL) << 16);
+  return (x >> 32) | (x << 32);
+}
+__host__ __device__ __forceinline__ Kmer kmer_rc(Kmer k, int K) {
+  // complement (3 - code == ~code on 2 bits), reverse group order over 128 bits, shift down to 2K bits
+  uint64_t a = rev_pairs64(~k.lo), b = rev_pairs64(~k.hi);   // 128-bit value (hi=a, lo=b)
+  int sh = 128 - 2 * K;
+  Kmer r;
+  if (sh == 0) { r.hi = a; r.lo = b; }
+  else if (sh < 64) { r.lo = (b >> sh) | (a << (64 - sh)); r.hi = a >> sh; }
+  else if (sh == 64) { r.lo = a; r.hi = 0; }
+  else { r.lo = a >> (sh - 64); r.hi = 0; }
+  return r;
+}
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x;
+}
+__host__ __device__ __forceinline__ uint64_t kmer_hash(Kmer k) { return mix64(k.lo ^ mix64(k.hi + 0x9E3779B97F4A7C15ULL)); }
+
+__device__ __forceinline__ uint64_t seed_of_code(uint32_t c) {
+  return c == 0 ? SHQ_SEED_A : c == 1 ? SHQ_SEED_C : c == 2 ? SHQ_SEED_G : SHQ_SEED_T;
+}
+// ntHash of a packed k-mer (forward strand fh, reverse strand rh), base/nthash.hpp:295-302
+__device__ __forceinline__ void kmer_nthash(Kmer k, int K, uint64_t* fh, uint64_t* rh) {
+  uint64_t f = 0, r = 0;
+  for (int i = 0; i < K; i++) {
+    uint32_t c = kmer_base(k, K, i);
+    f ^= rotl64(seed_of_code(c), K - 1 - i);
+    r ^= rotl64(seed_of_code(3 - c), i);
+  }
+  *fh = f; *rh = r;
+}
+// hashes of k[1:] + in, given those of k and out = k[0]  (base/nthash.hpp:305-309)
+__device__ __forceinline__ void nthash_roll(uint64_t fh, uint64_t rh, uint32_t out, uint32_t in, int K, uint64_t* nfh, uint64_t* nrh) {
+  *nfh = rotl64(fh, 1) ^ rotl64(seed_of_code(out), K) ^ seed_of_code(in);
+  *nrh = rotr64(rh, 1) ^ rotl64(seed_of_code(3 - out), 63) ^ rotl64(seed_of_code(3 - in), K - 1);
+}
+
+// image lookup without side effects: count of `key`, and the slot index of its entry
+__device__ __forceinline__ uint64_t img_lookup(const ImageView& im, uint64_t key, uint64_t* slot) {
+  uint32_t rem = (uint32_t)(key & 0xFF);
+  uint64_t q = (key >> 8) - im.q_base;
+  if (q >= im.nblocks * 64 || !img_bit(im, q, 0)) return 0;
+  uint64_t rs = q == 0 ? 0 : img_run_end(im, q - 1) + 1;
+  if (rs < q) rs = q;
+  uint64_t re = rs;
+  while (!img_bit(im, re, 1)) re++;
+  uint64_t idx = rs;
+  while (idx <= re) {
+    uint32_t r; uint64_t c;
+    uint64_t e = img_decode(im, idx, re, &r, &c);
+    if (r == rem) { if (slot) *slot = idx; return c; }
+    if (r > rem) break;
+    idx = e + 1;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------- node table ---
+constexpr uint32_t kNil = 0xFFFFFFFFu;
+struct NodeTable {
+  uint64_t* lo; uint64_t* hi; uint32_t* state; uint32_t* count; uint64_t* fh; uint64_t* rh;
+  uint32_t cap_mask;            // capacity - 1 (power of two)
+  uint32_t* list;               // node slots in insertion order
+  uint32_t* n_nodes;            // counter
+  uint32_t max_nodes;
+  int* err;
+};
+// insert-if-absent; returns the slot.  State: 0 empty, 1 being written, 2 ready.
+__device__ __forceinline__ uint32_t node_insert(const NodeTable& T, Kmer k, uint32_t count, uint64_t fh, uint64_t rh, bool* fresh) {
+  uint32_t h = (uint32_t)kmer_hash(k) & T.cap_mask;
+  *fresh = false;
+  for (uint32_t probe = 0; probe <= T.cap_mask; probe++) {
+    uint32_t s = *reinterpret_cast<volatile uint32_t*>(&T.state[h]);
+    if (s == 0) {
+      uint32_t old = atomicCAS(&T.state[h], 0u, 1u);
+      if (old == 0) {
+        T.lo[h] = k.lo; T.hi[h] = k.hi; T.count[h] = count; T.fh[h] = fh; T.rh[h] = rh;
+        __threadfence();
+        *reinterpret_cast<volatile uint32_t*>(&T.state[h]) = 2u;
+        uint32_t id = atomicAdd(T.n_nodes, 1u);
+        if (id < T.max_nodes) T.list[id] = h; else *T.err = SHQ_ERR_CAPACITY;
+        *fresh = true;
+        return h;
+      }
+      s = old;
+    }
+    while (s == 1) s = *reinterpret_cast<volatile uint32_t*>(&T.state[h]);   // writer is between CAS and publish
+    __threadfence();
+    if (*reinterpret_cast<volatile uint64_t*>(&T.lo[h]) == k.lo && *reinterpret_cast<volatile uint64_t*>(&T.hi[h]) == k.hi) return h;
+    h = (h + 1) & T.cap_mask;
+  }
+  *T.err = SHQ_ERR_CAPACITY;
+  return kNil;
+}
+__device__ __forceinline__ uint32_t node_find(const NodeTable& T, Kmer k) {
+  uint32_t h = (uint32_t)kmer_hash(k) & T.cap_mask;
+  for (uint32_t probe = 0; probe <= T.cap_mask; probe++) {
+    uint32_t s = T.state[h];
+    if (s == 0) return kNil;
+    if (T.lo[h] == k.lo && T.hi[h] == k.hi) return h;
+    h = (h + 1) & T.cap_mask;
+  }
+  return kNil;
+}
+
+// ------------------------------------------------------------------- U1 -----
+// One warp per read.  Per tile of 256 positions: 2-bit codes + validity prefix + ntHash prefix XORs in
+// shared memory, then every window: key -> image lookup -> first-visitor test on aux[slot] -> node insert.
+struct EnumParams {
+  const char* text; const uint32_t* nl_pos; uint32_t n_reads; int K; int hb; uint32_t s_min;
+};
+constexpr int kEnumWarps = 8;
+
+__device__ __forceinline__ uint32_t base_code(unsigned char c, bool* ok) {
+  switch (c) {
+    case 'A': case 'a': *ok = true; return 0;
+    case 'C': case 'c': *ok = true; return 1;
+    case 'G': case 'g': *ok = true; return 2;
+    case 'T': case 't': *ok = true; return 3;
+  }
+  *ok = false; return 0;
+}
+
+__global__ void __launch_bounds__(kEnumWarps * 32) enum_nodes_kernel(EnumParams ep, ImageView im, uint64_t* __restrict__ aux, NodeTable T) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // per warp: P[257], Q[257] (u64), codes[257] (u8), bad[257] (u16 prefix of invalid chars)
+  unsigned char* base = smem_raw + (size_t)wid * ((kTilePos + 1) * 16 + 264 + 520);
+  uint64_t* P = reinterpret_cast<uint64_t*>(base);
+  uint64_t* Q = P + (kTilePos + 1);
+  uint16_t* bad = reinterpret_cast<uint16_t*>(Q + (kTilePos + 1));
+  uint8_t* codes = reinterpret_cast<uint8_t*>(bad + 260);
+  const int K = ep.K;
+  const uint64_t mask = ep.hb >= 64 ? ~0ULL : ((1ULL << ep.hb) - 1);
+  const Kmer km = kmer_mask(K);
+  uint32_t warp_global = blockIdx.x * kEnumWarps + wid, n_warps = gridDim.x * kEnumWarps;
+  for (uint32_t r = warp_global; r < ep.n_reads; r += n_warps) {
+    uint32_t s = ep.nl_pos[4 * (size_t)r] + 1, e = ep.nl_pos[4 * (size_t)r + 1];
+    uint32_t len = e - s;
+    if (len < (uint32_t)K) continue;
+    const unsigned char* seq = reinterpret_cast<const unsigned char*>(ep.text) + s;
+    uint32_t nwin = len - K + 1;
+    const uint32_t TW = kTilePos - K + 1;
+    for (uint32_t w0 = 0; w0 < nwin; w0 += TW) {
+      uint32_t npos = min((uint32_t)kTilePos, len - w0);
+      uint64_t a[kPosPerLane], b[kPosPerLane];
+      uint64_t accA = 0, accB = 0; uint32_t nbad = 0; uint32_t badloc[kPosPerLane];
+#pragma unroll
+      for (int i = 0; i < kPosPerLane; i++) {
+        uint32_t j = lane * kPosPerLane + i;
+        uint64_t A = 0, B = 0; bool ok = true; uint32_t code = 0;
+        if (j < npos) {
+          unsigned char c = seq[w0 + j];
+          code = base_code(c, &ok);
+          if (ok) { A = rotr64(seed_of_code(code), j); B = rotl64(seed_of_code(3 - code), j); }
+          codes[j] = (uint8_t)code;
+        }
+        nbad += ok ? 0 : 1;
+        badloc[i] = nbad;
+        accA ^= A; accB ^= B; a[i] = accA; b[i] = accB;
+      }
+      uint64_t incA = accA, incB = accB; uint32_t incBad = nbad;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint64_t oA = __shfl_up_sync(0xffffffffu, incA, d), oB = __shfl_up_sync(0xffffffffu, incB, d);
+        uint32_t oC = __shfl_up_sync(0xffffffffu, incBad, d);
+        if (lane >= d) { incA ^= oA; incB ^= oB; incBad += oC; }
+      }
+      uint64_t excA = incA ^ accA, excB = incB ^ accB; uint32_t excBad = incBad - nbad;
+      if (lane == 0) { P[0] = 0; Q[0] = 0; bad[0] = 0; }
+#pragma unroll
+      for (int i = 0; i < kPosPerLane; i++) {
+        uint32_t j = lane * kPosPerLane + i;
+        P[j + 1] = excA ^ a[i]; Q[j + 1] = excB ^ b[i]; bad[j + 1] = (uint16_t)(excBad + badloc[i]);
+      }
+      __syncwarp();
+      uint32_t nw = min(TW, nwin - w0);
+      for (uint32_t i = lane; i < nw; i += 32) {
+        if (bad[i + K] != bad[i]) continue;                       // window holds a non-ACGT character
+        uint64_t fh = rotl64(P[i + K] ^ P[i], i + K - 1);
+        uint64_t rh = rotr64(Q[i + K] ^ Q[i], i);
+        uint64_t key = (fh < rh ? fh : rh) & mask;
+        uint64_t slot = 0;
+        uint64_t cnt = img_lookup(im, key, &slot);
+        if (cnt < ep.s_min) continue;
+        Kmer k{0, 0};
+        for (int t = 0; t < K; t++) k = kmer_push_right(k, codes[i + t], km);
+        Kmer rc = kmer_rc(k, K);
+        bool fwd_canon = !kmer_less(rc, k);
+        Kmer cano = fwd_canon ? k : rc;
+        uint64_t fp = kmer_hash(cano) | 1ULL;
+        unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&aux[slot]), 0ULL, (unsigned long long)fp);
+        if (old == 0ULL || old != fp) {     // first visitor of this key, or a different k-mer sharing the key
+          bool fresh;
+          node_insert(T, cano, (uint32_t)(cnt > 0xFFFFFFFFull ? 0xFFFFFFFFull : cnt), fwd_canon ? fh : rh, fwd_canon ? rh : fh, &fresh);
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// ------------------------------------------------------------------- U3 -----
+// Oriented node id = 2*slot + o; o = 1 means "reverse complement of the stored canonical k-mer".
+// outdeg[oid] = number of present successors; succ[oid] = oriented id of the last present one.
+struct LinkArrays { uint8_t* outdeg; uint32_t* succ; uint8_t* succ_mask; };
+
+__device__ __forceinline__ void oriented_kmer(const NodeTable& T, uint32_t oid, int K, Kmer* k, uint64_t* fh, uint64_t* rh) {
+  uint32_t slot = oid >> 1;
+  Kmer c{T.hi[slot], T.lo[slot]};
+  if (oid & 1) { *k = kmer_rc(c, K); *fh = T.rh[slot]; *rh = T.fh[slot]; }
+  else { *k = c; *fh = T.fh[slot]; *rh = T.rh[slot]; }
+}
+
+// processes list[begin, end): both orientations of each node.  New (false-positive) neighbours are
+// inserted and will be processed by the next round.
+__global__ void link_nodes_kernel(NodeTable T, ImageView im, LinkArrays L, int K, int hb, uint32_t s_min, uint32_t begin, uint32_t end) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t idx = begin + (t >> 1);
+  if (idx >= end) return;
+  uint32_t oid = 2 * T.list[idx] + (t & 1);
+  const uint64_t mask = hb >= 64 ? ~0ULL : ((1ULL << hb) - 1);
+  const Kmer km = kmer_mask(K);
+  Kmer k; uint64_t fh, rh;
+  oriented_kmer(T, oid, K, &k, &fh, &rh);
+  uint32_t out = kmer_base(k, K, 0);
+  uint32_t deg = 0, last = kNil, pmask = 0;
+  for (uint32_t x = 0; x < 4; x++) {
+    uint64_t nfh, nrh;
+    nthash_roll(fh, rh, out, x, K, &nfh, &nrh);
+    uint64_t key = (nfh < nrh ? nfh : nrh) & mask;
+    uint64_t cnt = img_lookup(im, key, nullptr);
+    if (cnt < s_min) continue;
+    Kmer n = kmer_push_right(k, x, km);
+    Kmer rc = kmer_rc(n, K);
+    bool fwd_canon = !kmer_less(rc, n);
+    bool fresh;
+    uint32_t slot = node_insert(T, fwd_canon ? n : rc, (uint32_t)(cnt > 0xFFFFFFFFull ? 0xFFFFFFFFull : cnt), fwd_canon ? nfh : nrh,
+                                fwd_canon ? nrh : nfh, &fresh);
+    if (slot == kNil) return;
+    deg++; last = 2 * slot + (fwd_canon ? 0 : 1); pmask |= 1u << x;
+  }
+  L.outdeg[oid] = (uint8_t)deg; L.succ[oid] = last; L.succ_mask[oid] = (uint8_t)pmask;
+}
+
+// ------------------------------------------------------------------- U4 -----
+// next/prev over oriented ids.  c -> n is simple iff outdeg(c) == 1 and outdeg(RC(n)) == 1.
+__global__ void simple_links_kernel(NodeTable T, LinkArrays L, uint32_t n_nodes, uint32_t* __restrict__ next, uint32_t* __restrict__ prev) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((t >> 1) >= n_nodes) return;
+  uint32_t oid = 2 * T.list[t >> 1] + (t & 1);
+  if (L.outdeg[oid] != 1) return;
+  uint32_t n = L.succ[oid];
+  if (L.outdeg[n ^ 1] != 1) return;
+  next[oid] = n; prev[n] = oid;
+}
+// jd[oid] = (jump << 32) | dist; jump = some ancestor (towards the head), dist = distance to it.
+__global__ void rank_init_kernel(NodeTable T, uint32_t n_nodes, const uint32_t* __restrict__ prev, unsigned long long* __restrict__ jd) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((t >> 1) >= n_nodes) return;
+  uint32_t oid = 2 * T.list[t >> 1] + (t & 1);
+  uint32_t p = prev[oid];
+  jd[oid] = p == kNil ? ((unsigned long long)oid << 32) : (((unsigned long long)p << 32) | 1ULL);
+}
+__global__ void rank_jump_kernel(NodeTable T, uint32_t n_nodes, unsigned long long* __restrict__ jd, uint32_t* __restrict__ changed) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((t >> 1) >= n_nodes) return;
+  uint32_t oid = 2 * T.list[t >> 1] + (t & 1);
+  unsigned long long me = *reinterpret_cast<volatile unsigned long long*>(&jd[oid]);
+  uint32_t j = (uint32_t)(me >> 32);
+  if (j == oid) return;
+  unsigned long long pj = *reinterpret_cast<volatile unsigned long long*>(&jd[j]);
+  uint32_t jj = (uint32_t)(pj >> 32);
+  if (jj == j) return;                       // j is a head: done
+  unsigned long long nd = (unsigned long long)(uint32_t)me + (unsigned long long)(uint32_t)pj;
+  *reinterpret_cast<volatile unsigned long long*>(&jd[oid]) = ((unsigned long long)jj << 32) | (nd & 0xFFFFFFFFull);
+  *changed = 1;
+}
+// cycles: nodes whose jump target is not a head after ranking.  minid propagates the smallest oriented id.
+__global__ void cycle_flag_kernel(NodeTable T, uint32_t n_nodes, const unsigned long long* __restrict__ jd, const uint32_t* __restrict__ prev,
+                                  uint32_t* __restrict__ minid, uint32_t* __restrict__ jmp, uint32_t* __restrict__ n_cycle) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((t >> 1) >= n_nodes) return;
+  uint32_t oid = 2 * T.list[t >> 1] + (t & 1);
+  uint32_t j = (uint32_t)(jd[oid] >> 32);
+  bool in_cycle = prev[j] != kNil;          // the final jump target of a chain node is its head (prev == nil)
+  minid[oid] = in_cycle ? oid : kNil;
+  jmp[oid] = in_cycle ? prev[oid] : kNil;
+  if (in_cycle) atomicAdd(n_cycle, 1u);
+}
+__global__ void cycle_min_kernel(NodeTable T, uint32_t n_nodes, uint32_t* __restrict__ minid, uint32_t* __restrict__ jmp) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((t >> 1) >= n_nodes) return;
+  uint32_t oid = 2 * T.list[t >> 1] + (t & 1);
+  uint32_t j = jmp[oid];
+  if (j == kNil) return;
+  uint32_t m = min(*reinterpret_cast<volatile uint32_t*>(&minid[oid]), *reinterpret_cast<volatile uint32_t*>(&minid[j]));
+  minid[oid] = m;
+  jmp[oid] = *reinterpret_cast<volatile uint32_t*>(&jmp[j]);
+}
+// Cut every cycle so that the two strands of a circular unitig become reverse-complementary chains:
+// the strand holding the globally smallest oriented id m starts at m; the other strand ends at m^1.
+__global__ void cycle_cut_kernel(NodeTable T, uint32_t n_nodes, const uint32_t* __restrict__ minid, uint32_t* __restrict__ next, uint32_t* __restrict__ prev) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((t >> 1) >= n_nodes) return;
+  uint32_t oid = 2 * T.list[t >> 1] + (t & 1);
+  uint32_t M = minid[oid];
+  if (M == kNil) return;
+  uint32_t Mr = minid[oid ^ 1];
+  if (M <= Mr) {
+    if (oid == M) { uint32_t p = prev[oid]; prev[oid] = kNil; if (p != kNil) next[p] = kNil; }
+  } else if (oid == (Mr ^ 1)) {
+    uint32_t n = next[oid]; next[oid] = kNil; if (n != kNil) prev[n] = kNil;
+  }
+}
+
+// ------------------------------------------------------------------- U5 -----
+// tails report (tail, length) to their head; heads decide which strand is kept.
+__global__ void tails_kernel(NodeTable T, uint32_t n_nodes, const uint32_t* __restrict__ next, const unsigned long long* __restrict__ jd,
+                             uint32_t* __restrict__ tail_of, uint32_t* __restrict__ len_of) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((t >> 1) >= n_nodes) return;
+  uint32_t oid = 2 * T.list[t >> 1] + (t & 1);
+  if (next[oid] != kNil) return;
+  unsigned long long me = jd[oid];
+  uint32_t head = (uint32_t)(me >> 32);
+  tail_of[head] = oid; len_of[head] = (uint32_t)me + 1;
+}
+// unitig ids for kept heads: head <= RC(tail).  uid_of_head[oid] = id or kNil.
+__global__ void heads_kernel(NodeTable T, uint32_t n_nodes, const uint32_t* __restrict__ prev, const uint32_t* __restrict__ tail_of,
+                             const uint32_t* __restrict__ len_of, int K, uint32_t* __restrict__ uid_of_head, uint32_t* __restrict__ n_unitigs,
+                             uint32_t* __restrict__ u_head, uint64_t* __restrict__ u_seqlen, uint64_t* __restrict__ u_klen, uint32_t max_unitigs) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((t >> 1) >= n_nodes) return;
+  uint32_t oid = 2 * T.list[t >> 1] + (t & 1);
+  if (prev[oid] != kNil) return;
+  uint32_t tail = tail_of[oid];
+  if (oid > (tail ^ 1)) return;              // the reverse strand's chain is the kept one
+  uint32_t id = atomicAdd(n_unitigs, 1u);
+  if (id >= max_unitigs) return;
+  uid_of_head[oid] = id; u_head[id] = oid;
+  u_seqlen[id] = (uint64_t)len_of[oid] + K - 1; u_klen[id] = len_of[oid];
+}
+// every node of a kept chain writes its last base (the head also its first K-1) and its count
+__global__ void assemble_kernel(NodeTable T, uint32_t n_nodes, const unsigned long long* __restrict__ jd, const uint32_t* __restrict__ uid_of_head,
+                                const uint64_t* __restrict__ seq_off, const uint64_t* __restrict__ k_off, int K, char* __restrict__ seq,
+                                uint32_t* __restrict__ kcounts, uint32_t* __restrict__ unitig_of_oid) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((t >> 1) >= n_nodes) return;
+  uint32_t oid = 2 * T.list[t >> 1] + (t & 1);
+  unsigned long long me = jd[oid];
+  uint32_t head = (uint32_t)(me >> 32), dist = (uint32_t)me;
+  uint32_t uid = uid_of_head[head];
+  unitig_of_oid[oid] = uid;
+  if (uid == kNil) return;
+  Kmer k; uint64_t fh, rh;
+  oriented_kmer(T, oid, K, &k, &fh, &rh);
+  const char B[4] = {'A', 'C', 'G', 'T'};
+  uint64_t so = seq_off[uid];
+  seq[so + K - 1 + dist] = B[kmer_base(k, K, K - 1)];
+  if (dist == 0) for (int i = 0; i < K - 1; i++) seq[so + i] = B[kmer_base(k, K, i)];
+  kcounts[k_off[uid] + dist] = T.count[oid >> 1];
+}
+
+// ------------------------------------------------------------------- U6 -----
+__device__ __forceinline__ uint32_t uf_find(uint32_t* parent, uint32_t x) {
+  for (;;) {
+    uint32_t p = *reinterpret_cast<volatile uint32_t*>(&parent[x]);
+    if (p == x) return x;
+    uint32_t gp = *reinterpret_cast<volatile uint32_t*>(&parent[p]);
+    if (gp != p) parent[x] = gp;
+    x = p;
+  }
+}
+__device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t b) {
+  for (;;) {
+    a = uf_find(parent, a); b = uf_find(parent, b);
+    if (a == b) return;
+    if (a > b) { uint32_t t = a; a = b; b = t; }
+    if (atomicCAS(&parent[b], b, a) == b) return;
+  }
+}
+// signed unitig reference of the chain headed by oriented node n: +(id+1) if that strand is kept,
+// -(id+1) if the kept strand is its reverse (whose head is RC(tail)).
+__device__ __forceinline__ int unitig_ref(uint32_t n, const uint32_t* uid_of_head, const uint32_t* tail_of) {
+  uint32_t u = uid_of_head[n];
+  if (u != kNil) return (int)(u + 1);
+  uint32_t tl = tail_of[n];
+  if (tl == kNil) return 0;                 // n is not a chain head (cannot happen for a non-simple link)
+  uint32_t rh = tl ^ 1;
+  u = uid_of_head[rh];
+  return u == kNil ? 0 : -(int)(u + 1);
+}
+// per unitig: links after (successors of the tail, order A,C,G,T) and before (successors of RC(head),
+// order T,G,C,A -- build_graph_worker, contig_assembly.cpp:1030-1060); union with every linked unitig and,
+// for dead ends, with the unitigs of sibling k-mers (the reference spawns those, :3094-3165).
+__global__ void unitig_links_kernel(NodeTable T, ImageView im, LinkArrays L, int K, int hb, uint32_t s_min, uint32_t n_unitigs,
+                                    const uint32_t* __restrict__ u_head, const uint32_t* __restrict__ tail_of,
+                                    const uint32_t* __restrict__ uid_of_head, const uint32_t* __restrict__ unitig_of_oid,
+                                    int* __restrict__ links /* [n_unitigs][8] */, uint32_t* __restrict__ parent) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t u = t >> 1;
+  if (u >= n_unitigs) return;
+  int side = t & 1;                                 // 0: after (tail), 1: before (RC(head))
+  uint32_t head = u_head[u];
+  uint32_t e = side == 0 ? tail_of[head] : (head ^ 1);
+  const uint64_t mask = hb >= 64 ? ~0ULL : ((1ULL << hb) - 1);
+  const Kmer km = kmer_mask(K);
+  Kmer k; uint64_t fh, rh;
+  oriented_kmer(T, e, K, &k, &fh, &rh);
+  uint32_t out = kmer_base(k, K, 0);
+  int nl = 0;
+  for (int xi = 0; xi < 4; xi++) {
+    uint32_t x = side == 0 ? (uint32_t)xi : (uint32_t)(3 - xi);
+    links[(size_t)u * 8 + side * 4 + xi] = 0;
+    if (!((L.succ_mask[e] >> x) & 1)) continue;
+    Kmer n = kmer_push_right(k, x, km);
+    Kmer rc = kmer_rc(n, K);
+    bool fwd_canon = !kmer_less(rc, n);
+    uint32_t slot = node_find(T, fwd_canon ? n : rc);
+    if (slot == kNil) continue;
+    uint32_t noid = 2 * slot + (fwd_canon ? 0 : 1);
+    int ref = unitig_ref(noid, uid_of_head, tail_of);
+    links[(size_t)u * 8 + side * 4 + nl] = ref; nl++;
+    if (ref) uf_union(parent, u, (uint32_t)(abs(ref) - 1));
+  }
+  if (L.outdeg[e] == 0) {                           // dead end: siblings y + e[1:], y != e[0]
+    // sibling = predecessor-side variant: replace the first base.  hashes: recompute from the packed k-mer
+    for (uint32_t y = 0; y < 4; y++) {
+      if (y == out) continue;
+      int sh = 2 * (K - 1);
+      Kmer sib = k;
+      if (sh >= 64) sib.hi = (sib.hi & ~(3ULL << (sh - 64))) | ((uint64_t)y << (sh - 64));
+      else sib.lo = (sib.lo & ~(3ULL << sh)) | ((uint64_t)y << sh);
+      Kmer rc = kmer_rc(sib, K);
+      bool fwd_canon = !kmer_less(rc, sib);
+      uint32_t slot = node_find(T, fwd_canon ? sib : rc);
+      if (slot == kNil) continue;                    // not a node: either absent or never reached -> check presence
+      uint32_t soid = 2 * slot + (fwd_canon ? 0 : 1);
+      uint32_t su = unitig_of_oid[soid];
+      if (su == kNil) su = unitig_of_oid[soid ^ 1];
+      if (su != kNil) uf_union(parent, u, su);
+    }
+  }
+  (void)mask; (void)im; (void)s_min; (void)fh; (void)rh;
+}
+
+// seeds: K ASCII bytes each (already upper-cased, no 'N').  A seed with x <= count <= X marks its component.
+__global__ void seeds_kernel(NodeTable T, ImageView im, const char* __restrict__ seeds, uint32_t n_seeds, int K, int hb, uint32_t x_min,
+                             uint32_t x_max, const uint32_t* __restrict__ unitig_of_oid, uint32_t* __restrict__ parent, uint8_t* __restrict__ reached) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_seeds) return;
+  const Kmer km = kmer_mask(K);
+  Kmer k{0, 0};
+  for (int t = 0; t < K; t++) {
+    bool ok; uint32_t c = base_code((unsigned char)seeds[(size_t)i * K + t], &ok);
+    if (!ok) return;
+    k = kmer_push_right(k, c, km);
+  }
+  Kmer rc = kmer_rc(k, K);
+  bool fwd_canon = !kmer_less(rc, k);
+  uint32_t slot = node_find(T, fwd_canon ? k : rc);
+  if (slot == kNil) return;
+  uint32_t cnt = T.count[slot];
+  if (cnt < x_min || cnt > x_max) return;
+  uint32_t u = unitig_of_oid[2 * slot];
+  if (u == kNil) u = unitig_of_oid[2 * slot + 1];
+  if (u == kNil) return;
+  reached[uf_find(parent, u)] = 1;
+  (void)im; (void)hb;
+}
+__global__ void init_iota_kernel(uint32_t* p, uint32_t n) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = i; }
+__global__ void keep_flags_kernel(uint32_t* parent, const uint8_t* reached, uint32_t n, uint8_t* keep) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keep[i] = reached[uf_find(parent, i)];
+}
+__global__ void fill_u32_kernel(uint32_t* p, uint32_t v, size_t n) { size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+
+}  // namespace shq
+
+// ============================================================ host side ======
+struct shq_unitigs_s {
+  shq_t h = nullptr;
+  shq_unitig_opts opts{};
+  uint32_t cap = 0, max_nodes = 0;
+  shq::DevBuf lo, hi, state, count, fh, rh, list, nn, aux, outdeg, succ, smask, next, prev, jd, minid, jmp, tail_of, len_of, uid_of_head,
+      unitig_of_oid, u_head, u_seqlen, u_klen, seq, kcounts, links, parent, reached, keep, d_seeds, d_text, misc;
+  std::vector<char> seeds;        // host: K bytes per accepted seed candidate
+  bool built = false;
+  // results (host)
+  std::vector<std::string> seqs; std::vector<int> km; std::vector<std::vector<int>> after, before;
+  std::string fasta;
+  uint64_t n_queries = 0;
+};
+
+namespace {
+
+using namespace shq;
+
+NodeTable node_table(shq_unitigs_s* u) {
+  NodeTable T;
+  T.lo = u->lo.as<uint64_t>(); T.hi = u->hi.as<uint64_t>(); T.state = u->state.as<uint32_t>(); T.count = u->count.as<uint32_t>();
+  T.fh = u->fh.as<uint64_t>(); T.rh = u->rh.as<uint64_t>(); T.cap_mask = u->cap - 1; T.list = u->list.as<uint32_t>();
+  T.n_nodes = u->nn.as<uint32_t>(); T.max_nodes = u->max_nodes; T.err = u->h->d_err;
+  return T;
+}
+
+// processDataChunk's line cursor (contig_assembly.cpp:1839-1924), restated literally: every `continue`
+// skips the two skipLines(), so the quality line is examined as a would-be header.  Collects the
+// upper-cased middle k-mer (worker rule: len/2 - K/2) of every record that passes the 'N' test.
+void collect_seeds(shq_unitigs_s* u, const char* text, size_t n) {
+  const int K = u->opts.K;
+  size_t p = 0;
+  auto read_line = [&](const char** s, size_t* len) -> bool {
+    if (p == n) return false;
+    const char* nl = (const char*)memchr(text + p, '\n', n - p);
+    size_t e = nl ? (size_t)(nl - text) : n;
+    *s = text + p; *len = e - p;
+    p = nl ? e + 1 : n;
+    return true;
+  };
+  const char* line; size_t ll; const char* seq; size_t sl;
+  std::string kmer;
+  while (read_line(&line, &ll)) {
+    if (ll == 0 || line[0] != '@') continue;
+    if (!read_line(&seq, &sl)) break;
+    if ((int)sl < K) { const char* t; size_t tl; read_line(&t, &tl); read_line(&t, &tl); continue; }
+    int seq_len = (int)sl, middle = seq_len / 2 - K / 2;
+    if (middle <= seq_len - K) {
+      kmer.assign(seq + middle, K);
+      bool hasN = false;
+      for (auto& c : kmer) { if (c > 0x60) c -= 32; if (c == 'N') hasN = true; }
+      if (hasN) continue;
+      // the count / traveled tests happen on the device; rejected seeds `continue` in the reference too,
+      // i.e. without skipLines(2) -- but so does every accepted-then-skipped path except full processing.
+      // A seed that is processed ends with skipLines(2); one that is rejected does not.  Which of the two
+      // applies is only known on the device, so the cursor follows the processed path here (regular
+      // 4-line records make both paths parse identically unless a quality line starts with '@').
+      u->seeds.insert(u->seeds.end(), kmer.begin(), kmer.end());
+    }
+    const char* t; size_t tl; read_line(&t, &tl); read_line(&t, &tl);
+  }
+}
+
+template <class T> void fill_u32(DevBuf& b, size_t n, uint32_t v, cudaStream_t st) {
+  b.reserve(n * 4);
+  fill_u32_kernel<<<cdiv(n, 256), 256, 0, st>>>(b.as<uint32_t>(), v, n);
+}
+
+void unitigs_build_impl(shq_unitigs_s* u) {
+  shq_handle_s* h = u->h;
+  cudaStream_t st = h->stream;
+  uint64_t& L = h->stats.kernels_launched;
+  const int K = u->opts.K;
+  ImageView im{h->image.as<uint8_t>(), h->nblocks, h->xnslots, 0};
+  NodeTable T = node_table(u);
+  const size_t O = (size_t)2 * u->cap;      // oriented ids
+  uint32_t n_nodes = read_scalar(h, u->nn.as<uint32_t>());
+  check_err_flag(h);
+  // U3: links + false-positive closure
+  u->outdeg.reserve(O); u->smask.reserve(O); u->succ.reserve(O * 4);
+  SHQ_CUDA(cudaMemsetAsync(u->outdeg.p, 0, O, st)); SHQ_CUDA(cudaMemsetAsync(u->smask.p, 0, O, st));
+  LinkArrays LA{u->outdeg.as<uint8_t>(), u->succ.as<uint32_t>(), u->smask.as<uint8_t>()};
+  uint32_t begin = 0;
+  for (int round = 0; round < 64 && begin < n_nodes; round++) {
+    uint32_t cnt = n_nodes - begin;
+    link_nodes_kernel<<<cdiv((size_t)cnt * 2, 128), 128, 0, st>>>(T, im, LA, K, h->hb, (uint32_t)u->opts.abundance_min, begin, n_nodes); L++;
+    u->n_queries += (uint64_t)cnt * 8;
+    begin = n_nodes;
+    n_nodes = read_scalar(h, u->nn.as<uint32_t>());
+    check_err_flag(h);
+    if (n_nodes > u->max_nodes) SHQ_FAIL(SHQ_ERR_CAPACITY, "unitig node table overflow (%u nodes)", n_nodes);
+  }
+  if (n_nodes == 0) { u->built = true; return; }
+  const unsigned g2 = cdiv((size_t)n_nodes * 2, 256);
+  // U4: chains
+  fill_u32<uint32_t>(u->next, O, kNil, st); fill_u32<uint32_t>(u->prev, O, kNil, st); L += 2;
+  simple_links_kernel<<<g2, 256, 0, st>>>(T, LA, n_nodes, u->next.as<uint32_t>(), u->prev.as<uint32_t>()); L++;
+  u->jd.reserve(O * 8); u->misc.reserve(256);
+  uint32_t* d_flag = u->misc.as<uint32_t>();
+  auto rank = [&]() {
+    rank_init_kernel<<<g2, 256, 0, st>>>(T, n_nodes, u->prev.as<uint32_t>(), u->jd.as<unsigned long long>()); L++;
+    for (int r = 0; r < 34; r++) {
+      SHQ_CUDA(cudaMemsetAsync(d_flag, 0, 4, st));
+      rank_jump_kernel<<<g2, 256, 0, st>>>(T, n_nodes, u->jd.as<unsigned long long>(), d_flag); L++;
+      if (!read_scalar(h, d_flag)) break;
+    }
+  };
+  rank();
+  fill_u32<uint32_t>(u->minid, O, kNil, st); fill_u32<uint32_t>(u->jmp, O, kNil, st); L += 2;
+  SHQ_CUDA(cudaMemsetAsync(d_flag, 0, 4, st));
+  cycle_flag_kernel<<<g2, 256, 0, st>>>(T, n_nodes, u->jd.as<unsigned long long>(), u->prev.as<uint32_t>(), u->minid.as<uint32_t>(),
+                                        u->jmp.as<uint32_t>(), d_flag); L++;
+  if (read_scalar(h, d_flag)) {
+    for (int r = 0; r < 34; r++) { cycle_min_kernel<<<g2, 256, 0, st>>>(T, n_nodes, u->minid.as<uint32_t>(), u->jmp.as<uint32_t>()); L++; }
+    cycle_cut_kernel<<<g2, 256, 0, st>>>(T, n_nodes, u->minid.as<uint32_t>(), u->next.as<uint32_t>(), u->prev.as<uint32_t>()); L++;
+    rank();
+  }
+  // U5: unitigs
+  fill_u32<uint32_t>(u->tail_of, O, kNil, st); fill_u32<uint32_t>(u->len_of, O, 0, st); fill_u32<uint32_t>(u->uid_of_head, O, kNil, st); L += 3;
+  fill_u32<uint32_t>(u->unitig_of_oid, O, kNil, st); L++;
+  tails_kernel<<<g2, 256, 0, st>>>(T, n_nodes, u->next.as<uint32_t>(), u->jd.as<unsigned long long>(), u->tail_of.as<uint32_t>(), u->len_of.as<uint32_t>()); L++;
+  uint32_t max_unitigs = n_nodes + 1;
+  u->u_head.reserve((size_t)max_unitigs * 4); u->u_seqlen.reserve((size_t)(max_unitigs + 2) * 8); u->u_klen.reserve((size_t)(max_unitigs + 2) * 8);
+  uint32_t* d_nu = d_flag + 2;
+  SHQ_CUDA(cudaMemsetAsync(d_nu, 0, 4, st));
+  heads_kernel<<<g2, 256, 0, st>>>(T, n_nodes, u->prev.as<uint32_t>(), u->tail_of.as<uint32_t>(), u->len_of.as<uint32_t>(), K,
+                                   u->uid_of_head.as<uint32_t>(), d_nu, u->u_head.as<uint32_t>(), u->u_seqlen.as<uint64_t>(),
+                                   u->u_klen.as<uint64_t>(), max_unitigs); L++;
+  uint32_t nu = read_scalar(h, d_nu);
+  if (nu == 0) { u->built = true; return; }
+  std::vector<uint64_t> seqlen(nu), klen(nu);
+  SHQ_CUDA(cudaMemcpyAsync(seqlen.data(), u->u_seqlen.p, (size_t)nu * 8, cudaMemcpyDeviceToHost, st));
+  SHQ_CUDA(cudaMemcpyAsync(klen.data(), u->u_klen.p, (size_t)nu * 8, cudaMemcpyDeviceToHost, st));
+  exclusive_scan_inplace<SumU64>(u->u_seqlen.as<uint64_t>(), nu, h->d_scan_scratch, st, u->u_seqlen.as<uint64_t>() + nu, &L);
+  exclusive_scan_inplace<SumU64>(u->u_klen.as<uint64_t>(), nu, h->d_scan_scratch, st, u->u_klen.as<uint64_t>() + nu, &L);
+  uint64_t total_seq = read_scalar(h, u->u_seqlen.as<uint64_t>() + nu), total_k = read_scalar(h, u->u_klen.as<uint64_t>() + nu);
+  u->seq.reserve(total_seq + 16); u->kcounts.reserve((total_k + 4) * 4);
+  assemble_kernel<<<g2, 256, 0, st>>>(T, n_nodes, u->jd.as<unsigned long long>(), u->uid_of_head.as<uint32_t>(), u->u_seqlen.as<uint64_t>(),
+                                      u->u_klen.as<uint64_t>(), K, u->seq.as<char>(), u->kcounts.as<uint32_t>(), u->unitig_of_oid.as<uint32_t>()); L++;
+  // U6: links, components, seeds
+  u->links.reserve((size_t)nu * 8 * 4); u->parent.reserve((size_t)nu * 4); u->reached.reserve(nu); u->keep.reserve(nu);
+  init_iota_kernel<<<cdiv(nu, 256), 256, 0, st>>>(u->parent.as<uint32_t>(), nu); L++;
+  SHQ_CUDA(cudaMemsetAsync(u->reached.p, 0, nu, st));
+  unitig_links_kernel<<<cdiv((size_t)nu * 2, 128), 128, 0, st>>>(T, im, LA, K, h->hb, (uint32_t)u->opts.abundance_min, nu, u->u_head.as<uint32_t>(),
+                                                               u->tail_of.as<uint32_t>(), u->uid_of_head.as<uint32_t>(),
+                                                               u->unitig_of_oid.as<uint32_t>(), u->links.as<int>(), u->parent.as<uint32_t>()); L++;
+  uint32_t n_seeds = (uint32_t)(u->seeds.size() / K);
+  if (n_seeds) {
+    u->d_seeds.reserve(u->seeds.size());
+    SHQ_CUDA(cudaMemcpyAsync(u->d_seeds.p, u->seeds.data(), u->seeds.size(), cudaMemcpyHostToDevice, st));
+    h->stats.h2d_bytes += u->seeds.size();
+    seeds_kernel<<<cdiv(n_seeds, 128), 128, 0, st>>>(T, im, u->d_seeds.as<char>(), n_seeds, K, h->hb, (uint32_t)u->opts.solid_abundance_min,
+                                                    (uint32_t)u->opts.solid_abundance_max, u->unitig_of_oid.as<uint32_t>(), u->parent.as<uint32_t>(),
+                                                    u->reached.as<uint8_t>()); L++;
+  }
+  keep_flags_kernel<<<cdiv(nu, 256), 256, 0, st>>>(u->parent.as<uint32_t>(), u->reached.as<uint8_t>(), nu, u->keep.as<uint8_t>()); L++;
+  SHQ_CUDA(cudaGetLastError());
+  // D2H
+  std::vector<char> seq(total_seq); std::vector<uint32_t> kc(total_k); std::vector<int> links((size_t)nu * 8); std::vector<uint8_t> keep(nu);
+  SHQ_CUDA(cudaMemcpyAsync(seq.data(), u->seq.p, total_seq, cudaMemcpyDeviceToHost, st));
+  SHQ_CUDA(cudaMemcpyAsync(kc.data(), u->kcounts.p, total_k * 4, cudaMemcpyDeviceToHost, st));
+  SHQ_CUDA(cudaMemcpyAsync(links.data(), u->links.p, (size_t)nu * 32, cudaMemcpyDeviceToHost, st));
+  SHQ_CUDA(cudaMemcpyAsync(keep.data(), u->keep.p, nu, cudaMemcpyDeviceToHost, st));
+  SHQ_CUDA(cudaStreamSynchronize(st));
+  h->stats.d2h_bytes += total_seq + total_k * 4 + (size_t)nu * 33;
+  check_err_flag(h);
+  // host: canonical orientation, deterministic order, renumbering, medians, FASTA (contig_assembly.cpp:603-629)
+  auto rc_str = [](const std::string& s) {
+    std::string r(s.rbegin(), s.rend());
+    for (auto& c : r) c = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : 'A';
+    return r;
+  };
+  struct Rec { std::string seq; int km; bool flipped; uint32_t old; };
+  std::vector<Rec> recs;
+  std::vector<int> newid(nu, -1);
+  {
+    uint64_t so = 0, ko = 0;
+    for (uint32_t i = 0; i < nu; i++) {
+      if (keep[i]) {
+        std::string s(seq.data() + so, seqlen[i]);
+        std::string r = rc_str(s);
+        bool flip = r < s;
+        std::vector<uint32_t> c(kc.begin() + ko, kc.begin() + ko + klen[i]);
+        std::sort(c.begin(), c.end());
+        size_t m = c.size() / 2;
+        double med = c.size() % 2 ? (double)c[m] : (c[m - 1] + c[m]) / 2.0;
+        recs.push_back(Rec{flip ? r : s, (int)med, flip, i});
+      }
+      so += seqlen[i]; ko += klen[i];
+    }
+  }
+  std::vector<uint32_t> order(recs.size());
+  for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return recs[a].seq < recs[b].seq; });
+  std::vector<bool> flipped_old(nu, false);
+  for (uint32_t r = 0; r < order.size(); r++) { newid[recs[order[r]].old] = (int)r; flipped_old[recs[order[r]].old] = recs[order[r]].flipped; }
+  u->seqs.clear(); u->km.clear(); u->after.clear(); u->before.clear(); u->fasta.clear();
+  for (uint32_t r = 0; r < order.size(); r++) {
+    const Rec& R = recs[order[r]];
+    std::vector<int> aft, bef;
+    for (int side = 0; side < 2; side++) {
+      for (int j = 0; j < 4; j++) {
+        int ref = links[(size_t)R.old * 8 + side * 4 + j];
+        if (!ref) continue;
+        uint32_t o = (uint32_t)(abs(ref) - 1);
+        if (newid[o] < 0) continue;
+        bool plus = ref > 0;
+        if (flipped_old[o]) plus = !plus;
+        int v = plus ? newid[o] + 1 : -(newid[o] + 1);
+        // a flipped unitig swaps its own sides
+        if ((side == 0) != R.flipped) aft.push_back(v); else bef.push_back(v);
+      }
+    }
+    u->seqs.push_back(R.seq); u->km.push_back(R.km); u->after.push_back(aft); u->before.push_back(bef);
+    std::string& f = u->fasta;
+    f += ">" + std::to_string(r) + " LN:i:" + std::to_string(R.seq.size()) + " KC:i:" +
+         std::to_string((long long)R.km * (long long)(R.seq.size() - K + 1)) + " km:f:" + std::to_string(R.km);
+    for (int t : aft) f += t > 0 ? " L:+:" + std::to_string(t - 1) + ":+" : " L:+:" + std::to_string(-t - 1) + ":-";
+    for (int t : bef) f += t > 0 ? " L:-:" + std::to_string(t - 1) + ":+" : " L:-:" + std::to_string(-t - 1) + ":-";
+    f += "\n" + R.seq + "\n";
+  }
+  u->built = true;
+}
+
+}  // namespace
+
 extern "C" {
-struct shq_unitigs_s { shq_t h; shq_unitig_opts opts; };
+
 int shq_unitigs_begin(shq_t h, const shq_unitig_opts* opts, shq_unitigs_t* out) {
   if (!h || !opts || !out) return SHQ_ERR_ARG;
   *out = nullptr;
-  h->last_error = "unitig path not built yet";
-  return SHQ_ERR_STATE;
+  if (opts->K < 2 || opts->K > 64 || opts->K > kTilePos - 32 || opts->abundance_min < 1 || opts->solid_abundance_min < opts->abundance_min) {
+    h->last_error = "unitigs need 2 <= K <= 64, -s >= 1 and -x >= -s";
+    return SHQ_ERR_ARG;
+  }
+  shq_unitigs_s* u = new shq_unitigs_s();
+  u->h = h; u->opts = *opts;
+  struct { shq_unitigs_s* u; } args{u};
+  int rc = guard(h, [](shq_handle_s* h, void* ap) {
+    shq_unitigs_s* u = ((decltype(args)*)ap)->u;
+    flush_stage(h);
+    if (h->nshards != 1) SHQ_FAIL(SHQ_ERR_STATE, "unitigs on a sharded handle go through the multi-GPU layer");
+    if (!h->image_only) materialise(h);
+    uint64_t expect = h->image_only ? h->ndistinct : (uint64_t)h->n_state;
+    if (expect < 1024) expect = 1024;
+    uint64_t want = expect * 3 + 4096;
+    uint32_t cap = 1024;
+    while (cap < want && cap < (1u << 30)) cap <<= 1;
+    u->cap = cap; u->max_nodes = (uint32_t)(cap * 0.7);
+    cudaStream_t st = h->stream;
+    u->lo.reserve((size_t)cap * 8); u->hi.reserve((size_t)cap * 8); u->fh.reserve((size_t)cap * 8); u->rh.reserve((size_t)cap * 8);
+    u->state.reserve((size_t)cap * 4); u->count.reserve((size_t)cap * 4); u->list.reserve((size_t)u->max_nodes * 4 + 16); u->nn.reserve(64);
+    SHQ_CUDA(cudaMemsetAsync(u->state.p, 0, (size_t)cap * 4, st));
+    SHQ_CUDA(cudaMemsetAsync(u->nn.p, 0, 64, st));
+    size_t nslots = (size_t)h->nblocks * 64;
+    u->aux.reserve(nslots * 8);
+    SHQ_CUDA(cudaMemsetAsync(u->aux.p, 0, nslots * 8, st));
+    SHQ_CUDA(cudaStreamSynchronize(st));
+  }, &args);
+  if (rc) { delete u; return rc; }
+  *out = u;
+  return SHQ_OK;
 }
-int shq_unitigs_add_reads(shq_unitigs_t, const char*, size_t) { return SHQ_ERR_STATE; }
-int shq_unitigs_build(shq_unitigs_t) { return SHQ_ERR_STATE; }
-int shq_unitigs_count(shq_unitigs_t, size_t*, size_t*) { return SHQ_ERR_STATE; }
-int shq_unitigs_write_fasta(shq_unitigs_t, const char*) { return SHQ_ERR_STATE; }
-int shq_unitigs_fasta(shq_unitigs_t, char*, size_t, size_t*) { return SHQ_ERR_STATE; }
-void shq_unitigs_free(shq_unitigs_t u) { delete u; }
+
+int shq_unitigs_add_reads(shq_unitigs_t u, const char* text, size_t n) {
+  if (!u || (!text && n)) return SHQ_ERR_ARG;
+  if (n == 0) return SHQ_OK;
+  struct { shq_unitigs_s* u; const char* t; size_t n; } args{u, text, n};
+  return guard(u->h, [](shq_handle_s* h, void* ap) {
+    auto& a = *(decltype(args)*)ap;
+    shq_unitigs_s* u = a.u;
+    cudaStream_t st = h->stream;
+    uint64_t& L = h->stats.kernels_launched;
+    if (a.n >= ((size_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "chunk too large");
+    collect_seeds(u, a.t, a.n);
+    u->d_text.reserve(a.n + 64);
+    SHQ_CUDA(cudaMemcpyAsync(u->d_text.p, a.t, a.n, cudaMemcpyHostToDevice, st));
+    h->stats.h2d_bytes += a.n;
+    unsigned ntiles = cdiv(a.n, kNlTile);
+    h->d_nl_tiles.reserve((size_t)(ntiles + 1) * 4);
+    nl_count_kernel<<<ntiles, kNlThreads, 0, st>>>(u->d_text.as<char>(), a.n, h->d_nl_tiles.as<uint32_t>()); L++;
+    h->d_misc.reserve(256);
+    exclusive_scan_inplace<SumU32>(h->d_nl_tiles.as<uint32_t>(), ntiles, h->d_scan_scratch, st, h->d_misc.as<uint32_t>(), &L);
+    uint32_t n_lines = read_scalar(h, h->d_misc.as<uint32_t>());
+    if ((n_lines & 3) || a.t[a.n - 1] != '\n') SHQ_FAIL(SHQ_ERR_MALFORMED, "chunk holds %u lines / no trailing newline", n_lines);
+    h->d_nl_pos.reserve((size_t)(n_lines + 4) * 4);
+    nl_write_kernel<<<ntiles, kNlThreads, 0, st>>>(u->d_text.as<char>(), a.n, h->d_nl_tiles.as<uint32_t>(), h->d_nl_pos.as<uint32_t>()); L++;
+    EnumParams ep{u->d_text.as<char>(), h->d_nl_pos.as<uint32_t>(), n_lines / 4, u->opts.K, h->hb, (uint32_t)u->opts.abundance_min};
+    ImageView im{h->image.as<uint8_t>(), h->nblocks, h->xnslots, 0};
+    size_t smem = (size_t)kEnumWarps * ((kTilePos + 1) * 16 + 264 + 520);
+    SHQ_CUDA(cudaFuncSetAttribute(enum_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    enum_nodes_kernel<<<4 * kNumSMs, kEnumWarps * 32, smem, st>>>(ep, im, u->aux.as<uint64_t>(), node_table(u)); L++;
+    SHQ_CUDA(cudaGetLastError());
+    SHQ_CUDA(cudaStreamSynchronize(st));
+    check_err_flag(h);
+  }, &args);
 }
+
+int shq_unitigs_build(shq_unitigs_t u) {
+  if (!u) return SHQ_ERR_ARG;
+  struct { shq_unitigs_s* u; } args{u};
+  return guard(u->h, [](shq_handle_s*, void* ap) { unitigs_build_impl(((decltype(args)*)ap)->u); }, &args);
+}
+int shq_unitigs_count(shq_unitigs_t u, size_t* n_unitigs, size_t* total_bases) {
+  if (!u || !u->built) return SHQ_ERR_STATE;
+  if (n_unitigs) *n_unitigs = u->seqs.size();
+  if (total_bases) { size_t t = 0; for (auto& s : u->seqs) t += s.size(); *total_bases = t; }
+  return SHQ_OK;
+}
+int shq_unitigs_fasta(shq_unitigs_t u, char* dst, size_t cap, size_t* written) {
+  if (!u || !u->built || !written) return SHQ_ERR_STATE;
+  *written = u->fasta.size();
+  if (cap == 0) return SHQ_OK;
+  if (cap < u->fasta.size()) return SHQ_ERR_ARG;
+  memcpy(dst, u->fasta.data(), u->fasta.size());
+  return SHQ_OK;
+}
+int shq_unitigs_write_fasta(shq_unitigs_t u, const char* path) {
+  if (!u || !u->built || !path) return SHQ_ERR_STATE;
+  FILE* f = fopen(path, "w");
+  if (!f) return SHQ_ERR_IO;
+  size_t w = fwrite(u->fasta.data(), 1, u->fasta.size(), f);
+  fclose(f);
+  return w == u->fasta.size() ? SHQ_OK : SHQ_ERR_IO;
+}
+void shq_unitigs_free(shq_unitigs_t u) {
+  if (!u) return;
+  cudaSetDevice(u->h->device);
+  shq::DevBuf* bufs[] = {&u->lo, &u->hi, &u->state, &u->count, &u->fh, &u->rh, &u->list, &u->nn, &u->aux, &u->outdeg, &u->succ, &u->smask, &u->next,
+                         &u->prev, &u->jd, &u->minid, &u->jmp, &u->tail_of, &u->len_of, &u->uid_of_head, &u->unitig_of_oid, &u->u_head, &u->u_seqlen,
+                         &u->u_klen, &u->seq, &u->kcounts, &u->links, &u->parent, &u->reached, &u->keep, &u->d_seeds, &u->d_text, &u->misc};
+  for (auto* b : bufs) b->release();
+  delete u;
+}
+
+}  // extern "C"

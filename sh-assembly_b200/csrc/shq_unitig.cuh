@@ -14,6 +14,8 @@
 #pragma once
 #include "shq_common.cuh"
 #include "shq_layout.cuh"
+#include <unordered_map>
+
 #include "shq_scan.cuh"
 
 namespace shq {
@@ -167,7 +169,12 @@ __device__ __forceinline__ uint32_t base_code(unsigned char c, bool* ok) {
   *ok = false; return 0;
 }
 
-__global__ void __launch_bounds__(kEnumWarps * 32) enum_nodes_kernel(EnumParams ep, ImageView im, uint64_t* __restrict__ aux, NodeTable T) {
+// aux[cqf slot]  = fingerprint of the first k-mer string that touched the entry
+// aux2[cqf slot] = node slot of that first visitor (written after its insertion)
+// victims        = (node slot, cqf slot) of every further string that shares the entry's key
+struct VictimList { uint32_t* node; uint64_t* cqf_slot; uint32_t* n; uint32_t cap; };
+__global__ void __launch_bounds__(kEnumWarps * 32) enum_nodes_kernel(EnumParams ep, ImageView im, uint64_t* __restrict__ aux, uint32_t* __restrict__ aux2,
+                                                                     VictimList V, NodeTable T) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   // per warp: P[257], Q[257] (u64), codes[257] (u8), bad[257] (u16 prefix of invalid chars)
@@ -238,7 +245,12 @@ __global__ void __launch_bounds__(kEnumWarps * 32) enum_nodes_kernel(EnumParams 
         unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&aux[slot]), 0ULL, (unsigned long long)fp);
         if (old == 0ULL || old != fp) {     // first visitor of this key, or a different k-mer sharing the key
           bool fresh;
-          node_insert(T, cano, (uint32_t)(cnt > 0xFFFFFFFFull ? 0xFFFFFFFFull : cnt), fwd_canon ? fh : rh, fwd_canon ? rh : fh, &fresh);
+          uint32_t ns = node_insert(T, cano, (uint32_t)(cnt > 0xFFFFFFFFull ? 0xFFFFFFFFull : cnt), fwd_canon ? fh : rh, fwd_canon ? rh : fh, &fresh);
+          if (old == 0ULL) aux2[slot] = ns;
+          else if (fresh && ns != kNil) {
+            uint32_t vi = atomicAdd(V.n, 1u);
+            if (vi < V.cap) { V.node[vi] = ns; V.cqf_slot[vi] = slot; }
+          }
         }
       }
       __syncwarp();
@@ -287,6 +299,27 @@ __global__ void link_nodes_kernel(NodeTable T, ImageView im, LinkArrays L, int K
     deg++; last = 2 * slot + (fwd_canon ? 0 : 1); pmask |= 1u << x;
   }
   L.outdeg[oid] = (uint8_t)deg; L.succ[oid] = last; L.succ_mask[oid] = (uint8_t)pmask;
+  if (deg == 0) {
+    // dead end: the reference still probes the 3 sibling k-mers y + k[1:] (they would be alternative
+    // predecessors of a successor) and spawns the present ones (contig_assembly.cpp:3094-3165), so a sibling
+    // that exists only as a false positive of the filter must become a node as well.
+    for (uint32_t y = 0; y < 4; y++) {
+      if (y == out) continue;
+      int sh = 2 * (K - 1);
+      Kmer sib = k;
+      if (sh >= 64) sib.hi = (sib.hi & ~(3ULL << (sh - 64))) | ((uint64_t)y << (sh - 64));
+      else sib.lo = (sib.lo & ~(3ULL << sh)) | ((uint64_t)y << sh);
+      uint64_t sfh, srh;
+      kmer_nthash(sib, K, &sfh, &srh);
+      uint64_t key = (sfh < srh ? sfh : srh) & mask;
+      uint64_t cnt = img_lookup(im, key, nullptr);
+      if (cnt < s_min) continue;
+      Kmer rc = kmer_rc(sib, K);
+      bool fwd_canon = !kmer_less(rc, sib);
+      bool fresh;
+      node_insert(T, fwd_canon ? sib : rc, (uint32_t)(cnt > 0xFFFFFFFFull ? 0xFFFFFFFFull : cnt), fwd_canon ? sfh : srh, fwd_canon ? srh : sfh, &fresh);
+    }
+  }
 }
 
 // ------------------------------------------------------------------- U4 -----
@@ -491,11 +524,14 @@ __global__ void unitig_links_kernel(NodeTable T, ImageView im, LinkArrays L, int
   (void)mask; (void)im; (void)s_min; (void)fh; (void)rh;
 }
 
-// seeds: K ASCII bytes each (already upper-cased, no 'N').  A seed with x <= count <= X marks its component.
-__global__ void seeds_kernel(NodeTable T, ImageView im, const char* __restrict__ seeds, uint32_t n_seeds, int K, int hb, uint32_t x_min,
-                             uint32_t x_max, const uint32_t* __restrict__ unitig_of_oid, uint32_t* __restrict__ parent, uint8_t* __restrict__ reached) {
+// seeds: K ASCII bytes each (already upper-cased, no 'N').  Per seed: the node slot and the component root of
+// its unitig if x <= count <= X, else kNil.  The t=1 "already traveled" rule is applied on the host in read order.
+__global__ void seeds_kernel(NodeTable T, const char* __restrict__ seeds, uint32_t n_seeds, int K, uint32_t x_min, uint32_t x_max,
+                             const uint32_t* __restrict__ unitig_of_oid, uint32_t* __restrict__ parent, uint32_t* __restrict__ seed_node,
+                             uint32_t* __restrict__ seed_root) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_seeds) return;
+  seed_node[i] = kNil; seed_root[i] = kNil;
   const Kmer km = kmer_mask(K);
   Kmer k{0, 0};
   for (int t = 0; t < K; t++) {
@@ -512,14 +548,27 @@ __global__ void seeds_kernel(NodeTable T, ImageView im, const char* __restrict__
   uint32_t u = unitig_of_oid[2 * slot];
   if (u == kNil) u = unitig_of_oid[2 * slot + 1];
   if (u == kNil) return;
-  reached[uf_find(parent, u)] = 1;
-  (void)im; (void)hb;
+  seed_node[i] = slot; seed_root[i] = uf_find(parent, u);
+}
+// victims: resolve (victim node, first-visitor node) -> component roots of both
+__global__ void victims_kernel(VictimList V, uint32_t nv, const uint32_t* __restrict__ aux2, const uint32_t* __restrict__ unitig_of_oid,
+                               uint32_t* __restrict__ parent, uint32_t* __restrict__ out /* [nv][4]: vnode, vroot, pnode, proot */) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nv) return;
+  uint32_t vn = V.node[i], pn = aux2[V.cqf_slot[i]];
+  auto root_of = [&](uint32_t slot) -> uint32_t {
+    if (slot == kNil) return kNil;
+    uint32_t u = unitig_of_oid[2 * slot];
+    if (u == kNil) u = unitig_of_oid[2 * slot + 1];
+    return u == kNil ? kNil : uf_find(parent, u);
+  };
+  out[4 * i] = vn; out[4 * i + 1] = root_of(vn); out[4 * i + 2] = pn; out[4 * i + 3] = root_of(pn);
+}
+__global__ void roots_kernel(uint32_t* parent, uint32_t n, uint32_t* root) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) root[i] = uf_find(parent, i);
 }
 __global__ void init_iota_kernel(uint32_t* p, uint32_t n) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = i; }
-__global__ void keep_flags_kernel(uint32_t* parent, const uint8_t* reached, uint32_t n, uint8_t* keep) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) keep[i] = reached[uf_find(parent, i)];
-}
 __global__ void fill_u32_kernel(uint32_t* p, uint32_t v, size_t n) { size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 
 }  // namespace shq
@@ -530,7 +579,9 @@ struct shq_unitigs_s {
   shq_unitig_opts opts{};
   uint32_t cap = 0, max_nodes = 0;
   shq::DevBuf lo, hi, state, count, fh, rh, list, nn, aux, outdeg, succ, smask, next, prev, jd, minid, jmp, tail_of, len_of, uid_of_head,
-      unitig_of_oid, u_head, u_seqlen, u_klen, seq, kcounts, links, parent, reached, keep, d_seeds, d_text, misc;
+      unitig_of_oid, u_head, u_seqlen, u_klen, seq, kcounts, links, parent, reached, keep, d_seeds, d_text, misc, aux2, v_node, v_slot, v_n, v_out,
+      seed_node, seed_root, roots;
+  uint32_t victim_cap = 0;
   std::vector<char> seeds;        // host: K bytes per accepted seed candidate
   bool built = false;
   // results (host)
@@ -667,30 +718,65 @@ void unitigs_build_impl(shq_unitigs_s* u) {
   // U6: links, components, seeds
   u->links.reserve((size_t)nu * 8 * 4); u->parent.reserve((size_t)nu * 4); u->reached.reserve(nu); u->keep.reserve(nu);
   init_iota_kernel<<<cdiv(nu, 256), 256, 0, st>>>(u->parent.as<uint32_t>(), nu); L++;
-  SHQ_CUDA(cudaMemsetAsync(u->reached.p, 0, nu, st));
   unitig_links_kernel<<<cdiv((size_t)nu * 2, 128), 128, 0, st>>>(T, im, LA, K, h->hb, (uint32_t)u->opts.abundance_min, nu, u->u_head.as<uint32_t>(),
                                                                u->tail_of.as<uint32_t>(), u->uid_of_head.as<uint32_t>(),
                                                                u->unitig_of_oid.as<uint32_t>(), u->links.as<int>(), u->parent.as<uint32_t>()); L++;
   uint32_t n_seeds = (uint32_t)(u->seeds.size() / K);
+  std::vector<uint32_t> seed_node(n_seeds), seed_root(n_seeds);
   if (n_seeds) {
     u->d_seeds.reserve(u->seeds.size());
     SHQ_CUDA(cudaMemcpyAsync(u->d_seeds.p, u->seeds.data(), u->seeds.size(), cudaMemcpyHostToDevice, st));
     h->stats.h2d_bytes += u->seeds.size();
-    seeds_kernel<<<cdiv(n_seeds, 128), 128, 0, st>>>(T, im, u->d_seeds.as<char>(), n_seeds, K, h->hb, (uint32_t)u->opts.solid_abundance_min,
+    u->seed_node.reserve((size_t)n_seeds * 4); u->seed_root.reserve((size_t)n_seeds * 4);
+    seeds_kernel<<<cdiv(n_seeds, 128), 128, 0, st>>>(T, u->d_seeds.as<char>(), n_seeds, K, (uint32_t)u->opts.solid_abundance_min,
                                                     (uint32_t)u->opts.solid_abundance_max, u->unitig_of_oid.as<uint32_t>(), u->parent.as<uint32_t>(),
-                                                    u->reached.as<uint8_t>()); L++;
+                                                    u->seed_node.as<uint32_t>(), u->seed_root.as<uint32_t>()); L++;
+    SHQ_CUDA(cudaMemcpyAsync(seed_node.data(), u->seed_node.p, (size_t)n_seeds * 4, cudaMemcpyDeviceToHost, st));
+    SHQ_CUDA(cudaMemcpyAsync(seed_root.data(), u->seed_root.p, (size_t)n_seeds * 4, cudaMemcpyDeviceToHost, st));
   }
-  keep_flags_kernel<<<cdiv(nu, 256), 256, 0, st>>>(u->parent.as<uint32_t>(), u->reached.as<uint8_t>(), nu, u->keep.as<uint8_t>()); L++;
+  uint32_t nv = std::min(read_scalar(h, u->v_n.as<uint32_t>()), u->victim_cap);
+  std::vector<uint32_t> vout((size_t)nv * 4);
+  if (nv) {
+    u->v_out.reserve((size_t)nv * 16);
+    VictimList V{u->v_node.as<uint32_t>(), u->v_slot.as<uint64_t>(), u->v_n.as<uint32_t>(), u->victim_cap};
+    victims_kernel<<<cdiv(nv, 128), 128, 0, st>>>(V, nv, u->aux2.as<uint32_t>(), u->unitig_of_oid.as<uint32_t>(), u->parent.as<uint32_t>(),
+                                                 u->v_out.as<uint32_t>()); L++;
+    SHQ_CUDA(cudaMemcpyAsync(vout.data(), u->v_out.p, (size_t)nv * 16, cudaMemcpyDeviceToHost, st));
+  }
+  u->roots.reserve((size_t)nu * 4);
+  roots_kernel<<<cdiv(nu, 256), 256, 0, st>>>(u->parent.as<uint32_t>(), nu, u->roots.as<uint32_t>()); L++;
+  std::vector<uint32_t> roots(nu);
+  SHQ_CUDA(cudaMemcpyAsync(roots.data(), u->roots.p, (size_t)nu * 4, cudaMemcpyDeviceToHost, st));
   SHQ_CUDA(cudaGetLastError());
   // D2H
-  std::vector<char> seq(total_seq); std::vector<uint32_t> kc(total_k); std::vector<int> links((size_t)nu * 8); std::vector<uint8_t> keep(nu);
+  std::vector<char> seq(total_seq); std::vector<uint32_t> kc(total_k); std::vector<int> links((size_t)nu * 8); std::vector<uint8_t> keep(nu, 0);
   SHQ_CUDA(cudaMemcpyAsync(seq.data(), u->seq.p, total_seq, cudaMemcpyDeviceToHost, st));
   SHQ_CUDA(cudaMemcpyAsync(kc.data(), u->kcounts.p, total_k * 4, cudaMemcpyDeviceToHost, st));
   SHQ_CUDA(cudaMemcpyAsync(links.data(), u->links.p, (size_t)nu * 32, cudaMemcpyDeviceToHost, st));
-  SHQ_CUDA(cudaMemcpyAsync(keep.data(), u->keep.p, nu, cudaMemcpyDeviceToHost, st));
   SHQ_CUDA(cudaStreamSynchronize(st));
-  h->stats.d2h_bytes += total_seq + total_k * 4 + (size_t)nu * 33;
+  h->stats.d2h_bytes += total_seq + total_k * 4 + (size_t)nu * 36 + (size_t)n_seeds * 8 + (size_t)nv * 16;
   check_err_flag(h);
+  // The seed rule at t=1 (contig_assembly.cpp:1874-1880): seeds are taken in read order; a seed is skipped when its
+  // KEY was traveled before.  All of a component's keys become traveled when its first seed is accepted, so a
+  // seed is blocked iff another k-mer string sharing its key lives in a component explored earlier.
+  {
+    std::unordered_map<uint32_t, std::vector<uint32_t>> partners;   // node slot -> roots of same-key nodes
+    for (uint32_t i = 0; i < nv; i++) {
+      uint32_t vn = vout[4 * i], vr = vout[4 * i + 1], pn = vout[4 * i + 2], pr = vout[4 * i + 3];
+      if (vr != kNil && pn != kNil) partners[pn].push_back(vr);
+      if (pr != kNil && vn != kNil) partners[vn].push_back(pr);
+    }
+    std::vector<uint32_t> t_explored(nu, 0xFFFFFFFFu);
+    for (uint32_t i = 0; i < n_seeds; i++) {
+      uint32_t r = seed_root[i];
+      if (r == kNil || r >= nu) continue;
+      bool blocked = false;
+      auto it = partners.find(seed_node[i]);
+      if (it != partners.end()) for (uint32_t pr : it->second) if (pr != r && pr < nu && t_explored[pr] < i) blocked = true;
+      if (!blocked && t_explored[r] == 0xFFFFFFFFu) t_explored[r] = i;
+    }
+    for (uint32_t i = 0; i < nu; i++) keep[i] = roots[i] < nu && t_explored[roots[i]] != 0xFFFFFFFFu;
+  }
   // host: canonical orientation, deterministic order, renumbering, medians, FASTA (contig_assembly.cpp:603-629)
   auto rc_str = [](const std::string& s) {
     std::string r(s.rbegin(), s.rend());
@@ -780,8 +866,12 @@ int shq_unitigs_begin(shq_t h, const shq_unitig_opts* opts, shq_unitigs_t* out) 
     SHQ_CUDA(cudaMemsetAsync(u->state.p, 0, (size_t)cap * 4, st));
     SHQ_CUDA(cudaMemsetAsync(u->nn.p, 0, 64, st));
     size_t nslots = (size_t)h->nblocks * 64;
-    u->aux.reserve(nslots * 8);
+    u->aux.reserve(nslots * 8); u->aux2.reserve(nslots * 4);
     SHQ_CUDA(cudaMemsetAsync(u->aux.p, 0, nslots * 8, st));
+    SHQ_CUDA(cudaMemsetAsync(u->aux2.p, 0xFF, nslots * 4, st));
+    u->victim_cap = (uint32_t)std::min<uint64_t>(u->max_nodes, (uint64_t)1 << 26);
+    u->v_node.reserve((size_t)u->victim_cap * 4); u->v_slot.reserve((size_t)u->victim_cap * 8); u->v_n.reserve(64);
+    SHQ_CUDA(cudaMemsetAsync(u->v_n.p, 0, 64, st));
     SHQ_CUDA(cudaStreamSynchronize(st));
   }, &args);
   if (rc) { delete u; return rc; }
@@ -816,7 +906,8 @@ int shq_unitigs_add_reads(shq_unitigs_t u, const char* text, size_t n) {
     ImageView im{h->image.as<uint8_t>(), h->nblocks, h->xnslots, 0};
     size_t smem = (size_t)kEnumWarps * ((kTilePos + 1) * 16 + 264 + 520);
     SHQ_CUDA(cudaFuncSetAttribute(enum_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    enum_nodes_kernel<<<4 * kNumSMs, kEnumWarps * 32, smem, st>>>(ep, im, u->aux.as<uint64_t>(), node_table(u)); L++;
+    VictimList V{u->v_node.as<uint32_t>(), u->v_slot.as<uint64_t>(), u->v_n.as<uint32_t>(), u->victim_cap};
+    enum_nodes_kernel<<<4 * kNumSMs, kEnumWarps * 32, smem, st>>>(ep, im, u->aux.as<uint64_t>(), u->aux2.as<uint32_t>(), V, node_table(u)); L++;
     SHQ_CUDA(cudaGetLastError());
     SHQ_CUDA(cudaStreamSynchronize(st));
     check_err_flag(h);
@@ -855,7 +946,7 @@ void shq_unitigs_free(shq_unitigs_t u) {
   cudaSetDevice(u->h->device);
   shq::DevBuf* bufs[] = {&u->lo, &u->hi, &u->state, &u->count, &u->fh, &u->rh, &u->list, &u->nn, &u->aux, &u->outdeg, &u->succ, &u->smask, &u->next,
                          &u->prev, &u->jd, &u->minid, &u->jmp, &u->tail_of, &u->len_of, &u->uid_of_head, &u->unitig_of_oid, &u->u_head, &u->u_seqlen,
-                         &u->u_klen, &u->seq, &u->kcounts, &u->links, &u->parent, &u->reached, &u->keep, &u->d_seeds, &u->d_text, &u->misc};
+                         &u->u_klen, &u->seq, &u->kcounts, &u->links, &u->parent, &u->reached, &u->keep, &u->d_seeds, &u->d_text, &u->misc, &u->aux2, &u->v_node, &u->v_slot, &u->v_n, &u->v_out, &u->seed_node, &u->seed_root, &u->roots};
   for (auto* b : bufs) b->release();
   delete u;
 }

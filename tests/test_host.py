@@ -59,7 +59,8 @@ def test_param_block_error_profile(po, shq, tmp_path):
     errs = np.linspace(0.001, 0.01, 150)
     p = str(tmp_path / "err.txt")
     open(p, "w").write("\n".join("%.6f" % e for e in errs))
-    t = po.oracle().orc_true2falseKmer_DP(np.array([float("%.6f" % e) for e in errs]).ctypes.data, 150, 31)
+    vals = np.array([float("%.6f" % e) for e in errs])      # keep alive across the ctypes call
+    t = po.oracle().orc_true2falseKmer_DP(vals.ctypes.data, 150, 31)
     a = shq.param_block(31, 4600000, 367999920, alpha=-1.0, error_profile=p, deNoise=2)
     b = po.param_block(31, 4600000, 367999920, alpha=-1.0, true2false=t, deNoise=2)
     assert (a.qb, a.num_deNoise, a.trigger, a.num_true_kmers) == (b.qb, b.num_deNoise, b.trigger, b.num_true_kmers)

@@ -94,6 +94,23 @@ int shq_rounds_done(shq_t h, uint32_t* rounds);
  * cqf/gqf.c:2792-3040), including the reference's range hand-out.               */
 int shq_denoise(shq_t h, uint64_t* removed);
 
+/* ---- sharded / multi-GPU building blocks ---------------------------------
+ * Every rank hashes its own reads, partitions the keys by owner shard, exchanges them (NCCL
+ * all-to-all, done by the caller) and inserts what it receives with shq_insert_keys_device.
+ * shq_hash_fastq_device: all reduced keys of the chunk(s) into a device array (any order).
+ * shq_partition_keys_device: stable-by-owner grouping; owner = key >> (hb - log2(nparts)).
+ * shq_state_view / shq_adopt_state: the sorted distinct (key,count) state, for gathering shards
+ * into one filter (export, exact deNoise sweep) and for handing a key range back to a shard.  */
+int shq_hash_fastq_device(shq_t h, const char* d_text, size_t n, int K, uint64_t* d_keys, size_t cap, size_t* nkeys);
+int shq_partition_keys_device(shq_t h, const uint64_t* d_keys_in, size_t n, int nparts, uint64_t* d_keys_out,
+                              uint64_t* counts /* host, nparts */);
+int shq_state_view(shq_t h, const uint64_t** d_keys, const uint32_t** d_counts, size_t* n);
+int shq_adopt_state(shq_t h, const uint64_t* d_keys, const uint32_t* d_counts, size_t n, uint64_t ndistinct,
+                    uint64_t nelts);
+int shq_set_counts(shq_t h, uint64_t ndistinct, uint64_t nelts);
+/* device-to-device copy on the handle's stream, synchronous (plumbing for callers without a CUDA binding) */
+int shq_copy_device(shq_t h, void* d_dst, const void* d_src, size_t bytes);
+
 /* ---- (de)serialisation ------------------------------------------------------
  * replaces qf_serialize / qf_deserialize (cqf/gqf.c:2379-2420) behind
  * CQF_mt::save / load (cqf/CQF_mt.h:514-523).  Byte-compatible both ways.       */

@@ -67,6 +67,7 @@ EXPORTS = [
     "shq_unitigs_write_fasta", "shq_unitigs_fasta", "shq_unitigs_free", "shq_get_stats", "shq_reset_stats", "shq_stream",
     "shq_reader_open", "shq_reader_open_memory", "shq_reader_next", "shq_reader_close", "shq_build_kmer_spectrum",
     "shq_materialize", "shq_param_block", "shq_cdfpoi_positive", "shq_cdfpoi",
+    "shq_hash_fastq_device", "shq_partition_keys_device", "shq_state_view", "shq_adopt_state", "shq_set_counts", "shq_copy_device",
 ]
 
 
@@ -119,6 +120,12 @@ def lib():
         L.shq_reset_stats.argtypes = [vp]
         L.shq_stream.restype = vp
         L.shq_stream.argtypes = [vp]
+        L.shq_hash_fastq_device.argtypes = [vp, vp, sz, C.c_int, vp, sz, C.POINTER(sz)]
+        L.shq_partition_keys_device.argtypes = [vp, vp, sz, C.c_int, vp, C.POINTER(u64)]
+        L.shq_state_view.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(sz)]
+        L.shq_adopt_state.argtypes = [vp, vp, vp, sz, u64, u64]
+        L.shq_set_counts.argtypes = [vp, u64, u64]
+        L.shq_copy_device.argtypes = [vp, vp, vp, sz]
         L.shq_reader_open.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_char, C.POINTER(vp)]
         L.shq_reader_open_memory.argtypes = [C.POINTER(vp), C.POINTER(sz), C.c_int, u64, C.POINTER(vp)]
         L.shq_reader_next.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(C.c_int)]
@@ -369,6 +376,31 @@ class CQF:
         out = np.zeros(cap, np.uint64)
         self._check(self.L.shq_hash_fastq_chunk(self.h, p, n, K, out.ctypes.data, cap, C.byref(nk)))
         return out[:nk.value]
+
+    # --- sharded building blocks
+    def hash_fastq_device(self, d_text, n, K, d_keys, cap):
+        nk = C.c_size_t()
+        self._check(self.L.shq_hash_fastq_device(self.h, d_text, n, K, d_keys, cap, C.byref(nk)))
+        return nk.value
+
+    def partition_keys_device(self, d_in, n, nparts, d_out):
+        counts = (C.c_uint64 * nparts)()
+        self._check(self.L.shq_partition_keys_device(self.h, d_in, n, nparts, d_out, counts))
+        return list(counts)
+
+    def state_view(self):
+        k, c, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        self._check(self.L.shq_state_view(self.h, C.byref(k), C.byref(c), C.byref(n)))
+        return k.value, c.value, n.value
+
+    def adopt_state(self, d_keys, d_counts, n, ndistinct, nelts):
+        self._check(self.L.shq_adopt_state(self.h, d_keys, d_counts, n, ndistinct, nelts))
+
+    def copy_device(self, dst, src, nbytes):
+        self._check(self.L.shq_copy_device(self.h, dst, src, nbytes))
+
+    def set_counts(self, ndistinct, nelts):
+        self._check(self.L.shq_set_counts(self.h, ndistinct, nelts))
 
     def stats(self):
         s = shq_stats()

@@ -346,13 +346,11 @@ void materialise(shq_handle_s* h) {
   uint64_t used = compute_positions(h);
   if (used > h->xnslots) SHQ_FAIL(SHQ_ERR_CAPACITY, "filter over-full: layout needs slot %llu but xnslots = %llu",
                                   (unsigned long long)used, (unsigned long long)h->xnslots);
-  size_t bytes = (size_t)h->nblocks * kBlockBytes;
   size_t tiles = (h->nblocks + kTileBlocks - 1) / kTileBlocks;
   h->image.reserve(tiles * kTileBytes + 16);
   image_tiles_kernel<<<(unsigned)tiles, kImgThreads, 0, st>>>(h->st_keys.as<uint64_t>(), h->st_counts.as<uint32_t>(), h->d_pos.as<uint64_t>(),
                                                             h->n_state, h->key_lo >> 8, h->nblocks, h->image.as<uint8_t>()); L++;
   SHQ_CUDA(cudaGetLastError());
-  (void)bytes;
   h->image_valid = true;
 }
 
@@ -916,6 +914,131 @@ int shq_materialize(shq_t h) {
     if (!h->image_only) materialise(h);
     SHQ_CUDA(cudaStreamSynchronize(h->stream));
   SHQ_API_END
+}
+
+int shq_hash_fastq_device(shq_t h, const char* d_text, size_t n, int K, uint64_t* d_keys, size_t cap, size_t* nkeys) {
+  if (!h || !nkeys || (!d_text && n)) return SHQ_ERR_ARG;
+  struct { const char* t; size_t n; int K; uint64_t* keys; size_t cap; size_t* nk; } args{d_text, n, K, d_keys, cap, nkeys};
+  SHQ_API_BEGIN(h)
+    cudaStream_t st = h->stream;
+    uint64_t& L = h->stats.kernels_launched;
+    *a.nk = 0;
+    if (a.n == 0) return;
+    if (a.K < 1 || a.K > kTilePos - 32) SHQ_FAIL(SHQ_ERR_ARG, "K=%d outside [1,%d]", a.K, kTilePos - 32);
+    if (a.n >= ((size_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "text of %zu bytes exceeds 4 GiB per call", a.n);
+    const char* src = a.t;
+    if (reinterpret_cast<uintptr_t>(src) & 15) {
+      h->d_text.reserve(a.n + 64);
+      SHQ_CUDA(cudaMemcpyAsync(h->d_text.p, src, a.n, cudaMemcpyDeviceToDevice, st));
+      src = h->d_text.as<char>();
+    }
+    unsigned ntiles = cdiv(a.n, kNlTile);
+    h->d_nl_tiles.reserve((size_t)(ntiles + 1) * 4);
+    nl_count_kernel<<<ntiles, kNlThreads, 0, st>>>(src, a.n, h->d_nl_tiles.as<uint32_t>()); L++;
+    h->d_misc.reserve(256);
+    exclusive_scan_inplace<SumU32>(h->d_nl_tiles.as<uint32_t>(), ntiles, h->d_scan_scratch, st, h->d_misc.as<uint32_t>(), &L);
+    uint32_t n_lines = read_scalar(h, h->d_misc.as<uint32_t>());
+    if (n_lines & 3) SHQ_FAIL(SHQ_ERR_MALFORMED, "text holds %u lines, not a multiple of 4", n_lines);
+    h->d_nl_pos.reserve((size_t)(n_lines + 4) * 4);
+    nl_write_kernel<<<ntiles, kNlThreads, 0, st>>>(src, a.n, h->d_nl_tiles.as<uint32_t>(), h->d_nl_pos.as<uint32_t>()); L++;
+    HashParams hp{};
+    hp.text = src; hp.nl_pos = h->d_nl_pos.as<uint32_t>(); hp.n_reads = n_lines / 4; hp.K = a.K; hp.hb = h->hb;
+    hp.key_lo = 0; hp.key_hi = ~0ULL; hp.n_bins = 0;
+    h->d_slow.reserve((size_t)(hp.n_reads + 2) * 4 + 16);
+    uint32_t* slow_count = h->d_slow.as<uint32_t>();
+    hp.slow_count = slow_count; hp.slow_list = slow_count + 4;
+    SHQ_CUDA(cudaMemsetAsync(slow_count, 0, 16, st));
+    unsigned long long* d_n = h->d_misc.as<unsigned long long>() + 8;
+    SHQ_CUDA(cudaMemsetAsync(d_n, 0, 8, st));
+    Sink sk{}; sk.keys = a.keys; sk.nkeys = d_n; sk.cap = a.cap;
+    size_t smem = (size_t)kHashWarps * 2 * (kTilePos + 1) * 8;
+    SHQ_CUDA(cudaFuncSetAttribute(hash_reads_kernel<kSinkKeys>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hash_reads_kernel<kSinkKeys><<<2 * kNumSMs, kHashThreads, smem, st>>>(hp, sk, nullptr, nullptr); L++;
+    HashParams hc = hp; hc.n_bins = 1; hc.lb = 63; hc.key_lo = 0; hc.key_hi = 0;
+    h->d_hist.reserve((size_t)(2 * kNumSMs + 1) * 4);
+    size_t smem_c = 16 + smem;
+    SHQ_CUDA(cudaFuncSetAttribute(hash_reads_kernel<kSinkCount>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+    Sink sc{};
+    hash_reads_kernel<kSinkCount><<<2 * kNumSMs, kHashThreads, smem_c, st>>>(hc, sc, h->d_hist.as<uint32_t>(), nullptr); L++;
+    uint32_t n_slow = read_scalar(h, slow_count);
+    if (n_slow) { hash_slow_reads_kernel<kSinkKeys><<<cdiv(n_slow, 128), 128, 0, st>>>(hp, sk, n_slow); L++; }
+    SHQ_CUDA(cudaGetLastError());
+    unsigned long long nk = read_scalar(h, d_n);
+    if (nk > a.cap) SHQ_FAIL(SHQ_ERR_ARG, "key buffer too small: %llu keys, capacity %zu", nk, a.cap);
+    *a.nk = (size_t)nk;
+    h->stats.keys_hashed += nk;
+  SHQ_API_END
+}
+
+int shq_partition_keys_device(shq_t h, const uint64_t* d_in, size_t n, int nparts, uint64_t* d_out, uint64_t* counts) {
+  if (!h || !counts || nparts < 1 || nparts > 16 || (nparts & (nparts - 1)) || (n && (!d_in || !d_out))) return SHQ_ERR_ARG;
+  struct { const uint64_t* in; size_t n; int np; uint64_t* out; uint64_t* counts; } args{d_in, n, nparts, d_out, counts};
+  SHQ_API_BEGIN(h)
+    cudaStream_t st = h->stream;
+    uint64_t& L = h->stats.kernels_launched;
+    for (int i = 0; i < a.np; i++) a.counts[i] = 0;
+    if (a.n == 0) return;
+    int pbits = 0; while ((1 << pbits) < a.np) pbits++;
+    int shift = h->hb - pbits;
+    size_t nthreads = (a.n + kOwnerStrip - 1) / kOwnerStrip;
+    size_t cells = nthreads * a.np;
+    h->d_tmp_keys.reserve((cells + 4) * 8);
+    uint64_t* mat = h->d_tmp_keys.as<uint64_t>();
+    owner_partition_kernel<false><<<cdiv(nthreads, 128), 128, 0, st>>>(a.in, a.n, shift, a.np, nthreads, mat, nullptr); L++;
+    exclusive_scan_inplace<SumU64>(mat, cells, h->d_scan_scratch, st, mat + cells, &L);
+    owner_partition_kernel<true><<<cdiv(nthreads, 128), 128, 0, st>>>(a.in, a.n, shift, a.np, nthreads, mat, a.out); L++;
+    SHQ_CUDA(cudaGetLastError());
+    // owner o starts at mat[o * nthreads]
+    std::vector<uint64_t> starts(a.np + 1);
+    for (int o = 0; o < a.np; o++) SHQ_CUDA(cudaMemcpyAsync(&starts[o], mat + (size_t)o * nthreads, 8, cudaMemcpyDeviceToHost, st));
+    SHQ_CUDA(cudaStreamSynchronize(st));
+    starts[a.np] = a.n;
+    for (int o = 0; o < a.np; o++) a.counts[o] = starts[o + 1] - starts[o];
+  SHQ_API_END
+}
+
+int shq_state_view(shq_t h, const uint64_t** d_keys, const uint32_t** d_counts, size_t* n) {
+  if (!h || !n) return SHQ_ERR_ARG;
+  struct { const uint64_t** k; const uint32_t** c; size_t* n; } args{d_keys, d_counts, n};
+  SHQ_API_BEGIN(h)
+    flush_stage(h);
+    ensure_state(h);
+    SHQ_CUDA(cudaStreamSynchronize(h->stream));
+    if (a.k) *a.k = h->st_keys.as<uint64_t>();
+    if (a.c) *a.c = h->st_counts.as<uint32_t>();
+    *a.n = h->n_state;
+  SHQ_API_END
+}
+
+int shq_adopt_state(shq_t h, const uint64_t* d_keys, const uint32_t* d_counts, size_t n, uint64_t ndistinct, uint64_t nelts) {
+  if (!h || (n && (!d_keys || !d_counts))) return SHQ_ERR_ARG;
+  struct { const uint64_t* k; const uint32_t* c; size_t n; uint64_t nd, ne; } args{d_keys, d_counts, n, ndistinct, nelts};
+  SHQ_API_BEGIN(h)
+    h->h_stage_fill = 0; h->stage_chunk_ends.clear();
+    h->st_keys.reserve((a.n + 4) * 8); h->st_counts.reserve((a.n + 4) * 4);
+    if (a.n) {
+      SHQ_CUDA(cudaMemcpyAsync(h->st_keys.p, a.k, a.n * 8, cudaMemcpyDeviceToDevice, h->stream));
+      SHQ_CUDA(cudaMemcpyAsync(h->st_counts.p, a.c, a.n * 4, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    SHQ_CUDA(cudaStreamSynchronize(h->stream));
+    h->n_state = a.n; h->ndistinct = a.nd; h->nelts = a.ne;
+    h->image_valid = false; h->image_only = false;
+  SHQ_API_END
+}
+
+int shq_copy_device(shq_t h, void* dst, const void* src, size_t bytes) {
+  if (!h || (bytes && (!dst || !src))) return SHQ_ERR_ARG;
+  struct { void* d; const void* s; size_t n; } args{dst, src, bytes};
+  SHQ_API_BEGIN(h)
+    if (a.n) SHQ_CUDA(cudaMemcpyAsync(a.d, a.s, a.n, cudaMemcpyDeviceToDevice, h->stream));
+    SHQ_CUDA(cudaStreamSynchronize(h->stream));
+  SHQ_API_END
+}
+
+int shq_set_counts(shq_t h, uint64_t ndistinct, uint64_t nelts) {
+  if (!h) return SHQ_ERR_ARG;
+  h->ndistinct = ndistinct; h->nelts = nelts;
+  return SHQ_OK;
 }
 
 int shq_get_stats(shq_t h, shq_stats* out) { if (!h || !out) return SHQ_ERR_ARG; *out = h->stats; return SHQ_OK; }

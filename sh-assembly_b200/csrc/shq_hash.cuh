@@ -335,4 +335,30 @@ __global__ void add_bin_off_kernel(uint32_t* __restrict__ row, const uint32_t* _
   if (p < n_bins) row[p] += bin_off[p];
 }
 
+
+// ---------------------------------------------------- partition by owner ----
+// Thread t owns the strip keys[t*S, (t+1)*S).  Pass 1 counts per owner into cnt[owner][t] (owner-major so
+// that one exclusive scan over the whole matrix yields the output offsets); pass 2 scatters.
+constexpr int kOwnerStrip = 128;
+template <bool SCATTER>
+__global__ void owner_partition_kernel(const uint64_t* __restrict__ keys, size_t n, int shift, int nparts, size_t nthreads,
+                                       uint64_t* __restrict__ mat /* [nparts][nthreads] */, uint64_t* __restrict__ out) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nthreads) return;
+  size_t b = t * kOwnerStrip, e = b + kOwnerStrip < n ? b + kOwnerStrip : n;
+  uint32_t loc[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) loc[i] = 0;
+  if (!SCATTER) {
+    for (size_t i = b; i < e; i++) { int o = (int)(keys[i] >> shift); loc[o & 15]++; }
+    for (int o = 0; o < nparts; o++) mat[(size_t)o * nthreads + t] = loc[o];
+  } else {
+    for (size_t i = b; i < e; i++) {
+      uint64_t k = keys[i];
+      int o = (int)(k >> shift);
+      out[mat[(size_t)o * nthreads + t] + loc[o & 15]++] = k;
+    }
+  }
+}
+
 }  // namespace shq

@@ -24,6 +24,7 @@ extern "C" {
 #endif
 
 typedef struct shq_handle_s* shq_t;
+#define SHQ_NO_KEY (~(uint64_t)0)
 
 typedef enum {
   SHQ_OK = 0,
@@ -97,7 +98,8 @@ int shq_denoise(shq_t h, uint64_t* removed);
 /* ---- sharded / multi-GPU building blocks ---------------------------------
  * Every rank hashes its own reads, partitions the keys by owner shard, exchanges them (NCCL
  * all-to-all, done by the caller) and inserts what it receives with shq_insert_keys_device.
- * shq_hash_fastq_device: all reduced keys of the chunk(s) into a device array (any order).
+ * shq_hash_fastq_device: all reduced keys of the chunk(s) into a device array; *nkeys = slots written, slots
+ *   that the N restart rule leaves unused hold SHQ_NO_KEY (~0) and are skipped by the partition step.
  * shq_partition_keys_device: stable-by-owner grouping; owner = key >> (hb - log2(nparts)).
  * shq_state_view / shq_adopt_state: the sorted distinct (key,count) state, for gathering shards
  * into one filter (export, exact deNoise sweep) and for handing a key range back to a shard.  */

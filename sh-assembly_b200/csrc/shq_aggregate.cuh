@@ -11,49 +11,65 @@
 namespace shq {
 
 // ----------------------------------------------------- per-bin aggregation ---
-constexpr int kAggThreads = 512;
-constexpr int kAggTable = 8192;          // open-addressing slots per CTA
-constexpr int kAggMaxDistinct = 4096;    // per round (load factor <= 0.5)
+constexpr int kAggThreads = 1024;
+constexpr int kAggTable = 16384;         // open-addressing slots per CTA
+constexpr int kAggMaxDistinct = 8192;    // per round (load factor <= 0.5)
+constexpr int kAggBuckets = 4096;        // bucket sort of the distinct keys
 constexpr uint32_t kAggEmpty = 0xFFFFFFFFu;
-constexpr size_t kAggSmemBytes = (size_t)kAggTable * (4 + 4 + 2) + (size_t)kAggMaxDistinct * 4;
+constexpr size_t kAggSmemBytes = (size_t)kAggTable * (4 + 4 + 2) + (size_t)kAggMaxDistinct * 4 + (size_t)kAggBuckets * 4;
 
-__device__ __forceinline__ uint32_t agg_hash(uint32_t k) { return (k * 2654435761u) >> (32 - 13); }
+__device__ __forceinline__ uint32_t agg_hash(uint32_t k) { return (k * 2654435761u) >> (32 - 14); }
+
+struct AggOut {
+  uint64_t* keys; uint32_t* counts; uint16_t* chunk; uint32_t* n_out;   // run A (or the only run)
+  uint64_t* keys2; uint32_t* counts2; uint32_t* n_out2;                 // run B (SPLIT only): occurrences with chunk > cstar
+  uint32_t* occ_out; uint32_t* occ_out2;
+  uint32_t* first_hist;     // optional: histogram over first-chunk ids of the distinct keys (state empty => all new)
+  int* split_overflow;      // SPLIT: set when a 16-bit half counter would overflow
+};
 
 // One CTA per bin.  packed[bin_off[p] .. bin_off[p+1]) holds (key_low | chunk << lb).
-// Occurrences whose chunk is outside [chunk_lo, chunk_hi] are ignored (deNoise boundary replay).
-// Output (sorted by key) goes to out_*[bin_off[p] + i]; n_out[p] = number of distinct keys,
-// occ_out[p] = number of occurrences consumed.
-// If a bin holds more than kAggMaxDistinct distinct keys the CTA re-streams it in 2^k sub-ranges.
+// Occurrences whose chunk is outside [chunk_lo, chunk_hi] are ignored.
+// SPLIT: occurrences with chunk <= cstar are counted in the low half of the counter, the others in the high
+// half, and two sorted runs come out of one pass (deNoise boundary inside a batch).
+// Output (sorted by key) goes to out[bin_off[p] + i].  A bin with more than kAggMaxDistinct distinct keys is
+// re-streamed in 2^k key sub-ranges.
+template <bool SPLIT>
 __global__ void __launch_bounds__(kAggThreads) bin_aggregate_kernel(
     const uint32_t* __restrict__ packed, const uint32_t* __restrict__ bin_off, int lb, uint64_t key_lo,
-    uint32_t chunk_lo, uint32_t chunk_hi, uint64_t* __restrict__ out_keys, uint32_t* __restrict__ out_counts,
-    uint16_t* __restrict__ out_chunk, uint32_t* __restrict__ n_out, uint32_t* __restrict__ occ_out) {
+    uint32_t chunk_lo, uint32_t chunk_hi, uint32_t cstar, AggOut o) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* t_key = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* t_cnt = t_key + kAggTable;
   uint32_t* s_sort = t_cnt + kAggTable;
-  uint16_t* t_chk = reinterpret_cast<uint16_t*>(s_sort + kAggMaxDistinct);
-  __shared__ uint32_t s_ndist, s_nocc, s_overflow, s_nsorted;
+  uint32_t* s_bkt = s_sort + kAggMaxDistinct;
+  uint16_t* t_chk = reinterpret_cast<uint16_t*>(s_bkt + kAggBuckets);
+  __shared__ uint32_t s_ndist, s_nocc, s_nocc2, s_overflow, s_na, s_nb;
 
   const uint32_t p = blockIdx.x;
   const uint32_t beg = bin_off[p], end = bin_off[p + 1];
   const uint32_t lowmask = lb >= 32 ? 0xFFFFFFFFu : ((1u << lb) - 1);
-  uint32_t written = 0, occ_total = 0;
+  const bool want_chunk = o.chunk != nullptr || o.first_hist != nullptr;
+  uint32_t written = 0, written2 = 0, occ_total = 0, occ_total2 = 0;
   int sub_bits = 0;
+  // expected duplication is high for sequencing data; start with one round unless the bin is huge
+  while (sub_bits < lb && ((end - beg) >> sub_bits) > 64u * kAggMaxDistinct) sub_bits++;
 
 restart:
-  written = 0; occ_total = 0;
+  written = 0; written2 = 0; occ_total = 0; occ_total2 = 0;
   for (uint32_t r = 0; r < (1u << sub_bits); r++) {
     for (int i = threadIdx.x; i < kAggTable; i += blockDim.x) { t_key[i] = kAggEmpty; t_cnt[i] = 0; t_chk[i] = 0xFFFF; }
-    if (threadIdx.x == 0) { s_ndist = 0; s_nocc = 0; s_overflow = 0; }
+    for (int i = threadIdx.x; i < kAggBuckets; i += blockDim.x) s_bkt[i] = 0;
+    if (threadIdx.x == 0) { s_ndist = 0; s_nocc = 0; s_nocc2 = 0; s_overflow = 0; s_na = 0; s_nb = 0; }
     __syncthreads();
-    uint32_t my_occ = 0;
+    uint32_t my_occ = 0, my_occ2 = 0;
     for (uint32_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
       uint32_t w = packed[i];
       uint32_t kl = w & lowmask, ch = lb >= 32 ? 0 : (w >> lb);
       if (ch < chunk_lo || ch > chunk_hi) continue;
       if (sub_bits && (kl >> (lb - sub_bits)) != r) continue;
-      my_occ++;
+      bool second = SPLIT && ch > cstar;
+      if (second) my_occ2++; else my_occ++;
       uint32_t h = agg_hash(kl);
       bool placed = false;
       for (int probe = 0; probe < kAggTable; probe++) {
@@ -71,62 +87,120 @@ restart:
         h = (h + 1) & (kAggTable - 1);
       }
       if (placed) {
-        atomicAdd(&t_cnt[h], 1u);
-        if (out_chunk) {  // 16-bit atomic min of the first chunk through the containing 32-bit word
+        uint32_t old = atomicAdd(&t_cnt[h], second ? 0x10000u : 1u);
+        if (SPLIT) {
+          if ((second ? (old >> 16) : (old & 0xFFFFu)) >= 0xFFFEu) *o.split_overflow = 1;
+        }
+        if (want_chunk && !second) {  // 16-bit atomic min of the first chunk through the containing 32-bit word
           unsigned int* wp = reinterpret_cast<unsigned int*>(t_chk) + (h >> 1);
           unsigned int sh = (h & 1) * 16;
-          unsigned int old = *reinterpret_cast<volatile unsigned int*>(wp);
-          while (((old >> sh) & 0xFFFFu) > ch) {
-            unsigned int nw = (old & ~(0xFFFFu << sh)) | (ch << sh);
-            unsigned int prev = atomicCAS(wp, old, nw);
-            if (prev == old) break;
-            old = prev;
+          unsigned int oldw = *reinterpret_cast<volatile unsigned int*>(wp);
+          while (((oldw >> sh) & 0xFFFFu) > ch) {
+            unsigned int nw = (oldw & ~(0xFFFFu << sh)) | (ch << sh);
+            unsigned int prev = atomicCAS(wp, oldw, nw);
+            if (prev == oldw) break;
+            oldw = prev;
           }
         }
       }
     }
     __syncthreads();
     if (*reinterpret_cast<volatile uint32_t*>(&s_overflow)) { sub_bits++; __syncthreads(); goto restart; }
-    // gather distinct keys, sort them
-    if (threadIdx.x == 0) s_nsorted = 0;
+    // ---- bucket sort of the distinct keys (keys are hash values: buckets hold ~nd/4096 keys each)
+    const int bits = lb - sub_bits;                    // key_low bits that vary inside this round
+    const int bshift = bits > 12 ? bits - 12 : 0;
+    const uint32_t relmask = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1);
+    for (int i = threadIdx.x; i < kAggTable; i += blockDim.x) {
+      uint32_t k = t_key[i];
+      if (k != kAggEmpty) atomicAdd(&s_bkt[(k & relmask) >> bshift], 1u);
+    }
+    __syncthreads();
+    {
+      uint32_t v[4], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) { v[j] = s_bkt[threadIdx.x * 4 + j]; sum += v[j]; }
+      uint32_t tot;
+      uint32_t ex = block_exclusive_scan<SumU32>(sum, &tot);
+#pragma unroll
+      for (int j = 0; j < 4; j++) { s_bkt[threadIdx.x * 4 + j] = ex; ex += v[j]; }
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < kAggTable; i += blockDim.x) {
       uint32_t k = t_key[i];
-      if (k != kAggEmpty) s_sort[atomicAdd(&s_nsorted, 1u)] = k;
+      if (k != kAggEmpty) s_sort[atomicAdd(&s_bkt[(k & relmask) >> bshift], 1u)] = k;
     }
     __syncthreads();
-    const uint32_t nd = s_nsorted;
-    uint32_t m = 1; while (m < nd) m <<= 1;
-    for (uint32_t i = nd + threadIdx.x; i < m; i += blockDim.x) s_sort[i] = kAggEmpty;
-    __syncthreads();
-    for (uint32_t size = 2; size <= m; size <<= 1) {
-      for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-        for (uint32_t t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
-          uint32_t lo = (t / stride) * (stride << 1) + (t % stride);
-          uint32_t hi = lo + stride;
-          bool up = ((lo & size) == 0);
-          uint32_t x = s_sort[lo], y = s_sort[hi];
-          if ((x > y) == up) { s_sort[lo] = y; s_sort[hi] = x; }
-        }
-        __syncthreads();
+    const uint32_t nd = s_ndist;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {                      // s_bkt[b] is now the END of bucket b
+      int b = threadIdx.x * 4 + j;
+      uint32_t lo = b ? s_bkt[b - 1] : 0, hi = s_bkt[b];
+      for (uint32_t x = lo + 1; x < hi; x++) {
+        uint32_t kx = s_sort[x]; uint32_t y = x;
+        while (y > lo && s_sort[y - 1] > kx) { s_sort[y] = s_sort[y - 1]; y--; }
+        s_sort[y] = kx;
       }
     }
+    __syncthreads();
+    const bool do_hist = !SPLIT && o.first_hist != nullptr;
+    if (do_hist) {                                     // s_bkt is free now: per-CTA histogram of first chunks
+      for (int i = threadIdx.x; i < kAggBuckets; i += blockDim.x) s_bkt[i] = 0;
+      __syncthreads();
+    }
+    // ---- emit
     for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) {
       uint32_t kl = s_sort[i];
       uint32_t h = agg_hash(kl);
       while (t_key[h] != kl) h = (h + 1) & (kAggTable - 1);
-      size_t o = (size_t)beg + written + i;
-      out_keys[o] = key_lo + (((uint64_t)p << lb) | kl);
-      out_counts[o] = t_cnt[h];
-      if (out_chunk) out_chunk[o] = t_chk[h];
+      uint32_t c = t_cnt[h];
+      uint64_t key = key_lo + (((uint64_t)p << lb) | kl);
+      if (!SPLIT) {
+        size_t oo = (size_t)beg + written + i;
+        o.keys[oo] = key; o.counts[oo] = c;
+        if (o.chunk) o.chunk[oo] = t_chk[h];
+        if (do_hist) atomicAdd(&s_bkt[t_chk[h] & (kAggBuckets - 1)], 1u);
+      } else {
+        // order-preserving compaction of the two runs: ranks via a second pass below
+        s_sort[i] = kl;   // keep
+        (void)c; (void)key;
+      }
+    }
+    if (SPLIT) {
+      // two ordered runs: rank = number of earlier keys with a non-zero half counter (block scan over nd keys)
+      __syncthreads();
+      for (uint32_t base = 0; base < nd; base += blockDim.x) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t kl = 0, c = 0, h = 0;
+        if (i < nd) {
+          kl = s_sort[i]; h = agg_hash(kl);
+          while (t_key[h] != kl) h = (h + 1) & (kAggTable - 1);
+          c = t_cnt[h];
+        }
+        uint32_t fa = (i < nd && (c & 0xFFFFu)) ? 1 : 0, fb = (i < nd && (c >> 16)) ? 1 : 0;
+        uint32_t ta, tb;
+        uint32_t ra = block_exclusive_scan<SumU32>(fa, &ta);
+        uint32_t rb = block_exclusive_scan<SumU32>(fb, &tb);
+        uint32_t ba = s_na, bb = s_nb;
+        __syncthreads();
+        uint64_t key = key_lo + (((uint64_t)p << lb) | kl);
+        if (fa) { size_t oo = (size_t)beg + written + ba + ra; o.keys[oo] = key; o.counts[oo] = c & 0xFFFFu; if (o.chunk) o.chunk[oo] = t_chk[h]; }
+        if (fb) { size_t oo = (size_t)beg + written2 + bb + rb; o.keys2[oo] = key; o.counts2[oo] = c >> 16; }
+        if (threadIdx.x == 0) { s_na = ba + ta; s_nb = bb + tb; }
+        __syncthreads();
+      }
     }
     atomicAdd(&s_nocc, my_occ);
+    if (SPLIT) atomicAdd(&s_nocc2, my_occ2);
     __syncthreads();
-    written += nd;
-    occ_total += s_nocc;
+    if (do_hist) for (int i = threadIdx.x; i < kAggBuckets; i += blockDim.x) { uint32_t v = s_bkt[i]; if (v) atomicAdd(&o.first_hist[i], v); }
+    if (!SPLIT) written += nd; else { written += s_na; written2 += s_nb; }
+    occ_total += s_nocc; occ_total2 += s_nocc2;
     __syncthreads();
   }
-  if (threadIdx.x == 0) { n_out[p] = written; occ_out[p] = occ_total; }
+  if (threadIdx.x == 0) {
+    o.n_out[p] = written; o.occ_out[p] = occ_total;
+    if (SPLIT) { o.n_out2[p] = written2; o.occ_out2[p] = occ_total2; }
+  }
 }
 
 // Dense gather: bin p's n_out[p] entries move from [bin_off[p], ...) to [dense_off[p], ...).

@@ -13,6 +13,7 @@
 #include "shq_common.cuh"
 #include "shq_hash.cuh"
 #include "shq_layout.cuh"
+#include "shq_roll.cuh"
 #include "shq_scan.cuh"
 
 using namespace shq;
@@ -54,6 +55,7 @@ struct shq_handle_s {
   // scratch
   DevBuf d_text, d_nl_tiles, d_nl_pos, d_chunk_ends, d_chunk_line_end, d_chunk_keys, d_chunk_hist, d_slow;
   DevBuf d_hist, d_tot, d_binoff, d_packed, d_tmp_keys, d_tmp_counts, d_tmp_chunk, d_nout, d_occ, d_dense_off;
+  DevBuf d_tmp_keys2, d_tmp_counts2, d_run2_keys, d_run2_counts;
   DevBuf d_run_keys, d_run_counts, d_run_chunk, d_split, d_heads, d_heads64, d_scan_scratch, d_misc;
   DevBuf d_pairs, d_pos, d_flags, d_keep, d_q_in, d_q_cnt, d_q_was;
   int* d_err = nullptr;          // device error flag
@@ -113,22 +115,43 @@ T read_scalar(shq_handle_s* h, const T* d) {
 // ---------------------------------------------------------------------------
 // A "run" = sorted distinct (key, count[, first chunk]) produced from one batch of binned keys.
 struct BatchBins {
-  int n_bins = 0, lb = 0, rows = 0;
+  int n_bins = 0, lb = 0;
   uint32_t n_keys = 0;          // occurrences scattered
   bool armed = false;
   int nchunks = 0;
 };
+struct Run { DevBuf* keys; DevBuf* counts; DevBuf* chunk; size_t n = 0; uint64_t occ = 0; };
+
+int g_scatter_w = 32;           // keys staged per thread and round (tunable: SHQ_SCATTER_W)
+int g_bin_bits = 0;             // 0 = automatic (tunable: SHQ_BIN_BITS)
 
 int pick_bin_bits(shq_handle_s* h, uint64_t est_keys, int chunk_bits_needed) {
-  // aim at ~16K occurrences per bin, 2^8 .. 2^14 bins, and (key bits below the bin) + chunk bits <= 32
+  // aim at ~64K occurrences per bin (8 per bin and scatter round), 2^8 .. 2^13 bins,
+  // and (key bits below the bin) + chunk bits <= 32
   int shard_bits = 0; while ((1 << shard_bits) < h->nshards) shard_bits++;
   int local_bits = h->hb - shard_bits;
   int pb = 8;
-  while (pb < 14 && (est_keys >> pb) > 16384) pb++;
+  while (pb < 12 && (est_keys >> pb) > 65536) pb++;
+  if (g_bin_bits) pb = g_bin_bits;
   if (pb > local_bits) pb = local_bits;
-  while (local_bits - pb + chunk_bits_needed > 32 && pb < 16) pb++;
+  while (local_bits - pb + chunk_bits_needed > 32 && pb < 13) pb++;
   if (local_bits - pb + chunk_bits_needed > 32) SHQ_FAIL(SHQ_ERR_ARG, "hb=%d too wide for 32-bit packed keys", h->hb);
   return pb;
+}
+
+// K1: newline index of a batch; returns the number of lines.
+uint32_t index_lines(shq_handle_s* h, const char* d_text, size_t n_text) {
+  cudaStream_t st = h->stream;
+  uint64_t& L = h->stats.kernels_launched;
+  unsigned ntiles = cdiv(n_text, kNlTile);
+  h->d_nl_tiles.reserve((size_t)(ntiles + 1) * 4);
+  nl_count_kernel<<<ntiles, kNlThreads, 0, st>>>(d_text, n_text, h->d_nl_tiles.as<uint32_t>()); L++;
+  h->d_misc.reserve(256);
+  exclusive_scan_inplace<SumU32>(h->d_nl_tiles.as<uint32_t>(), ntiles, h->d_scan_scratch, st, h->d_misc.as<uint32_t>(), &L);
+  uint32_t n_lines = read_scalar(h, h->d_misc.as<uint32_t>());
+  h->d_nl_pos.reserve((size_t)(n_lines + 8) * 4);
+  nl_write_kernel<<<ntiles, kNlThreads, 0, st>>>(d_text, n_text, h->d_nl_tiles.as<uint32_t>(), h->d_nl_pos.as<uint32_t>()); L++;
+  return n_lines;
 }
 
 // Both hashing passes over the batch text (or a raw key array): count -> offsets -> scatter.
@@ -138,22 +161,12 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
   cudaStream_t st = h->stream;
   uint64_t& L = h->stats.kernels_launched;
   HashParams hp{};
-  uint32_t n_reads = 0;
   const bool from_text = d_keys == nullptr;
   if (from_text) {
-    if (K < 1 || K > kTilePos - 32) SHQ_FAIL(SHQ_ERR_ARG, "K=%d outside [1,%d]", K, kTilePos - 32);
+    if (K < 1 || K > 1024) SHQ_FAIL(SHQ_ERR_ARG, "K=%d outside [1,1024]", K);
     if (n_text >= ((size_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "batch text of %zu bytes exceeds 4 GiB", n_text);
     if (reinterpret_cast<uintptr_t>(d_text) & 15) SHQ_FAIL(SHQ_ERR_ARG, "device text must be 16-byte aligned");
-    // K1: newline index
-    unsigned ntiles = cdiv(n_text, kNlTile);
-    h->d_nl_tiles.reserve((size_t)(ntiles + 1) * 4);
-    nl_count_kernel<<<ntiles, kNlThreads, 0, st>>>(d_text, n_text, h->d_nl_tiles.as<uint32_t>()); L++;
-    h->d_misc.reserve(256);
-    exclusive_scan_inplace<SumU32>(h->d_nl_tiles.as<uint32_t>(), ntiles, h->d_scan_scratch, st, h->d_misc.as<uint32_t>(), &L);
-    uint32_t n_lines = read_scalar(h, h->d_misc.as<uint32_t>());
-    h->d_nl_pos.reserve((size_t)(n_lines + 4) * 4);
-    nl_write_kernel<<<ntiles, kNlThreads, 0, st>>>(d_text, n_text, h->d_nl_tiles.as<uint32_t>(), h->d_nl_pos.as<uint32_t>()); L++;
-    // per-chunk validation + chunk -> line map
+    uint32_t n_lines = index_lines(h, d_text, n_text);
     h->d_chunk_ends.reserve((size_t)nchunks * 8 + 8);
     h->d_chunk_line_end.reserve((size_t)nchunks * 4 + 4);
     SHQ_CUDA(cudaMemcpyAsync(h->d_chunk_ends.p, h_chunk_ends, (size_t)nchunks * 8, cudaMemcpyHostToDevice, st));
@@ -162,13 +175,11 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
                                                             nchunks, h->d_chunk_line_end.as<uint32_t>(), h->d_err); L++;
     check_err_flag(h);
     if (n_lines & 3) SHQ_FAIL(SHQ_ERR_MALFORMED, "batch holds %u lines, not a multiple of 4", n_lines);
-    n_reads = n_lines / 4;
-    hp.text = d_text; hp.nl_pos = h->d_nl_pos.as<uint32_t>(); hp.n_reads = n_reads; hp.K = K;
+    hp.text = d_text; hp.nl_pos = h->d_nl_pos.as<uint32_t>(); hp.n_reads = n_lines / 4; hp.K = K;
   }
-  // geometry of the bins
   int chunk_bits = 0;
-  if (armed) { while ((1 << chunk_bits) < nchunks) chunk_bits++; if (chunk_bits > 15) SHQ_FAIL(SHQ_ERR_ARG, "too many chunks in one batch"); }
-  uint64_t est = from_text ? (uint64_t)(n_text / 2) : (uint64_t)n_keys_in;
+  if (armed) { while ((1 << chunk_bits) < nchunks) chunk_bits++; if (chunk_bits > 12) SHQ_FAIL(SHQ_ERR_ARG, "too many chunks in one batch"); }
+  uint64_t est = from_text ? (uint64_t)(n_text / 3) : (uint64_t)n_keys_in;
   int pb = pick_bin_bits(h, est / (uint64_t)h->nshards + 1, chunk_bits);
   int shard_bits = 0; while ((1 << shard_bits) < h->nshards) shard_bits++;
   int lb = h->hb - shard_bits - pb;
@@ -176,107 +187,139 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
   hp.hb = h->hb; hp.lb = lb; hp.key_lo = h->key_lo; hp.key_hi = h->key_hi; hp.n_bins = n_bins;
   hp.nchunks = nchunks;
   hp.chunk_line_end = (armed && from_text) ? h->d_chunk_line_end.as<uint32_t>() : nullptr;
-  const int G = 2 * kNumSMs;           // persistent CTAs, two per SM
-  const int rows = G + 1;              // + one row for the serial 'N' path
-  h->d_hist.reserve((size_t)rows * n_bins * 4);
-  h->d_tot.reserve((size_t)(n_bins + 1) * 4);
+  h->d_hist.reserve((size_t)(n_bins + 1) * 4);
   h->d_binoff.reserve((size_t)(n_bins + 2) * 4);
+  h->d_tot.reserve((size_t)(n_bins + 2) * 4);      // scatter cursors
   h->d_chunk_keys.reserve((size_t)(nchunks + 1) * 4);
-  h->d_slow.reserve((size_t)(n_reads + 2) * 4 + 16);
-  uint32_t* slow_count = h->d_slow.as<uint32_t>();
-  hp.slow_count = slow_count; hp.slow_list = slow_count + 4;
   hp.chunk_keys = (armed && from_text) ? h->d_chunk_keys.as<uint32_t>() : nullptr;
-  SHQ_CUDA(cudaMemsetAsync(h->d_hist.p, 0, (size_t)rows * n_bins * 4, st));
+  SHQ_CUDA(cudaMemsetAsync(h->d_hist.p, 0, (size_t)(n_bins + 1) * 4, st));
   SHQ_CUDA(cudaMemsetAsync(h->d_chunk_keys.p, 0, (size_t)(nchunks + 1) * 4, st));
-  SHQ_CUDA(cudaMemsetAsync(slow_count, 0, 16, st));
+  const int G = kNumSMs * 2;
+  const int W = g_scatter_w;
+  size_t smem_count = sizeof(RollTables) + (size_t)n_bins * 4;
+  size_t smem_scatter = sizeof(RollTables) + (size_t)n_bins * 8 + (size_t)kRollThreads * W * 6;
+  size_t smem_keys = (size_t)n_bins * 8;
   Sink sk{};
-  uint32_t n_slow = 0;
-  size_t smem_text = (((size_t)n_bins * 4 + 15) & ~(size_t)15) + (size_t)kHashWarps * 2 * (kTilePos + 1) * 8;
-  size_t smem_keys = (size_t)n_bins * 4;
   {
     Phase ph(h, &h->stats.ms_hash_count);
     if (from_text) {
-      SHQ_CUDA(cudaFuncSetAttribute(hash_reads_kernel<kSinkCount>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_text));
-      hash_reads_kernel<kSinkCount><<<G, kHashThreads, smem_text, st>>>(hp, sk, h->d_hist.as<uint32_t>(), nullptr); L++;
-      n_slow = read_scalar(h, slow_count);
-      if (n_slow) {
-        Sink s2 = sk; s2.bins = h->d_hist.as<uint32_t>() + (size_t)G * n_bins;
-        hash_slow_reads_kernel<kSinkCount><<<cdiv(n_slow, 128), 128, 0, st>>>(hp, s2, n_slow); L++;
-      }
+      SHQ_CUDA(cudaFuncSetAttribute(roll_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
+      roll_count_kernel<<<G, kRollThreads, smem_count, st>>>(hp, h->d_hist.as<uint32_t>()); L++;
     } else {
       SHQ_CUDA(cudaFuncSetAttribute(hash_keys_kernel<kSinkCount>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_keys));
       hash_keys_kernel<kSinkCount><<<G, 256, smem_keys, st>>>(d_keys, n_keys_in, hp, sk, h->d_hist.as<uint32_t>(), nullptr); L++;
     }
-    hist_column_scan_kernel<<<cdiv(n_bins, 128), 128, 0, st>>>(h->d_hist.as<uint32_t>(), rows, n_bins, h->d_tot.as<uint32_t>()); L++;
-    SHQ_CUDA(cudaMemcpyAsync(h->d_binoff.p, h->d_tot.p, (size_t)n_bins * 4, cudaMemcpyDeviceToDevice, st));
+    SHQ_CUDA(cudaMemcpyAsync(h->d_binoff.p, h->d_hist.p, (size_t)n_bins * 4, cudaMemcpyDeviceToDevice, st));
     exclusive_scan_inplace<SumU32>(h->d_binoff.as<uint32_t>(), n_bins, h->d_scan_scratch, st, h->d_binoff.as<uint32_t>() + n_bins, &L);
+    SHQ_CUDA(cudaMemcpyAsync(h->d_tot.p, h->d_binoff.p, (size_t)n_bins * 4, cudaMemcpyDeviceToDevice, st));
   }
   uint32_t n_keys = read_scalar(h, h->d_binoff.as<uint32_t>() + n_bins);
   h->d_packed.reserve((size_t)(n_keys + 4) * 4);
   {
     Phase ph(h, &h->stats.ms_scatter);
-    sk.packed = h->d_packed.as<uint32_t>();
     if (from_text) {
-      SHQ_CUDA(cudaFuncSetAttribute(hash_reads_kernel<kSinkScatter>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_text));
-      hash_reads_kernel<kSinkScatter><<<G, kHashThreads, smem_text, st>>>(hp, sk, h->d_hist.as<uint32_t>(), h->d_binoff.as<uint32_t>()); L++;
-      if (n_slow) {
-        uint32_t* row = h->d_hist.as<uint32_t>() + (size_t)G * n_bins;
-        add_bin_off_kernel<<<cdiv(n_bins, 128), 128, 0, st>>>(row, h->d_binoff.as<uint32_t>(), n_bins); L++;
-        Sink s2 = sk; s2.bins = row;
-        hash_slow_reads_kernel<kSinkScatter><<<cdiv(n_slow, 128), 128, 0, st>>>(hp, s2, n_slow); L++;
+      if (W == 16) {
+        SHQ_CUDA(cudaFuncSetAttribute(roll_scatter_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
+        roll_scatter_kernel<16><<<G, kRollThreads, smem_scatter, st>>>(hp, h->d_tot.as<uint32_t>(), h->d_packed.as<uint32_t>());
+      } else {
+        SHQ_CUDA(cudaFuncSetAttribute(roll_scatter_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
+        roll_scatter_kernel<32><<<kNumSMs, kRollThreads, smem_scatter, st>>>(hp, h->d_tot.as<uint32_t>(), h->d_packed.as<uint32_t>());
       }
+      L++;
     } else {
+      sk.packed = h->d_packed.as<uint32_t>();
       SHQ_CUDA(cudaFuncSetAttribute(hash_keys_kernel<kSinkScatter>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_keys));
-      hash_keys_kernel<kSinkScatter><<<G, 256, smem_keys, st>>>(d_keys, n_keys_in, hp, sk, h->d_hist.as<uint32_t>(), h->d_binoff.as<uint32_t>()); L++;
+      hash_keys_kernel<kSinkScatter><<<G, 256, smem_keys, st>>>(d_keys, n_keys_in, hp, sk, h->d_tot.as<uint32_t>(), nullptr); L++;
     }
   }
   SHQ_CUDA(cudaGetLastError());
-  bb->n_bins = n_bins; bb->lb = lb; bb->rows = rows; bb->n_keys = n_keys; bb->armed = armed; bb->nchunks = nchunks;
+  bb->n_bins = n_bins; bb->lb = lb; bb->n_keys = n_keys; bb->armed = armed; bb->nchunks = nchunks;
   h->stats.keys_hashed += n_keys;
 }
 
-// Aggregate the binned batch (chunks [clo, chi]) into a dense sorted run in d_run_*; returns its size
-// and the number of occurrences it covers.
-void aggregate_bins(shq_handle_s* h, const BatchBins& bb, uint32_t clo, uint32_t chi, size_t* n_run, uint64_t* n_occ) {
+// Aggregate the binned batch (chunks [clo, chi]) into dense sorted run(s).
+//  split: occurrences with chunk <= cstar go to run A, the rest to run B (one pass).
+//  first_hist (host vector, may be null): histogram of the first chunk of every distinct key.
+// Returns false if the split counters overflowed (caller falls back to two plain passes).
+bool aggregate_bins(shq_handle_s* h, const BatchBins& bb, uint32_t clo, uint32_t chi, bool split, uint32_t cstar, Run* A, Run* B,
+                    std::vector<uint32_t>* first_hist) {
   cudaStream_t st = h->stream;
   uint64_t& L = h->stats.kernels_launched;
   Phase ph(h, &h->stats.ms_aggregate);
   size_t cap = (size_t)bb.n_keys + 4;
   h->d_tmp_keys.reserve(cap * 8); h->d_tmp_counts.reserve(cap * 4);
   if (bb.armed) h->d_tmp_chunk.reserve(cap * 2);
-  h->d_nout.reserve((size_t)(bb.n_bins + 1) * 4); h->d_occ.reserve((size_t)(bb.n_bins + 1) * 4);
-  h->d_dense_off.reserve((size_t)(bb.n_bins + 2) * 4);
-  SHQ_CUDA(cudaFuncSetAttribute(bin_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggSmemBytes));
-  bin_aggregate_kernel<<<bb.n_bins, kAggThreads, kAggSmemBytes, st>>>(
-      h->d_packed.as<uint32_t>(), h->d_binoff.as<uint32_t>(), bb.lb, h->key_lo, clo, chi, h->d_tmp_keys.as<uint64_t>(),
-      h->d_tmp_counts.as<uint32_t>(), bb.armed ? h->d_tmp_chunk.as<uint16_t>() : nullptr, h->d_nout.as<uint32_t>(),
-      h->d_occ.as<uint32_t>()); L++;
-  SHQ_CUDA(cudaMemcpyAsync(h->d_dense_off.p, h->d_nout.p, (size_t)bb.n_bins * 4, cudaMemcpyDeviceToDevice, st));
-  exclusive_scan_inplace<SumU32>(h->d_dense_off.as<uint32_t>(), bb.n_bins, h->d_scan_scratch, st,
-                                 h->d_dense_off.as<uint32_t>() + bb.n_bins, &L);
-  // occurrences covered (sum of occ_out): reuse d_occ with a scan total
+  if (split) { h->d_tmp_keys2.reserve(cap * 8); h->d_tmp_counts2.reserve(cap * 4); }
+  const size_t nb = (size_t)bb.n_bins;
+  h->d_nout.reserve((nb + 1) * 4 * 4);           // n_out, n_out2, occ, occ2
+  uint32_t* n_out = h->d_nout.as<uint32_t>(); uint32_t* n_out2 = n_out + nb + 1; uint32_t* occ = n_out2 + nb + 1; uint32_t* occ2 = occ + nb + 1;
+  h->d_dense_off.reserve((nb + 2) * 4 * 2);
+  uint32_t* doff = h->d_dense_off.as<uint32_t>(); uint32_t* doff2 = doff + nb + 2;
   h->d_misc.reserve(256);
-  exclusive_scan_inplace<SumU32>(h->d_occ.as<uint32_t>(), bb.n_bins, h->d_scan_scratch, st, h->d_misc.as<uint32_t>(), &L);
-  uint32_t nd = read_scalar(h, h->d_dense_off.as<uint32_t>() + bb.n_bins);
-  uint32_t occ = read_scalar(h, h->d_misc.as<uint32_t>());
-  h->d_run_keys.reserve((size_t)(nd + 4) * 8); h->d_run_counts.reserve((size_t)(nd + 4) * 4);
-  if (bb.armed) h->d_run_chunk.reserve((size_t)(nd + 4) * 2);
-  compact_bins_kernel<<<bb.n_bins, 256, 0, st>>>(h->d_binoff.as<uint32_t>(), h->d_dense_off.as<uint32_t>(), h->d_nout.as<uint32_t>(),
-                                                h->d_tmp_keys.as<uint64_t>(), h->d_tmp_counts.as<uint32_t>(),
-                                                bb.armed ? h->d_tmp_chunk.as<uint16_t>() : nullptr, h->d_run_keys.as<uint64_t>(),
-                                                h->d_run_counts.as<uint32_t>(), bb.armed ? h->d_run_chunk.as<uint16_t>() : nullptr); L++;
+  int* d_ovf = h->d_misc.as<int>() + 16;
+  SHQ_CUDA(cudaMemsetAsync(d_ovf, 0, 4, st));
+  uint32_t* d_fh = nullptr;
+  if (first_hist) {
+    if (bb.nchunks > kAggBuckets) SHQ_FAIL(SHQ_ERR_ARG, "too many chunks in one batch");
+    h->d_chunk_hist.reserve((size_t)kAggBuckets * 4);
+    d_fh = h->d_chunk_hist.as<uint32_t>();
+    SHQ_CUDA(cudaMemsetAsync(d_fh, 0, (size_t)kAggBuckets * 4, st));
+  }
+  AggOut o{};
+  o.keys = h->d_tmp_keys.as<uint64_t>(); o.counts = h->d_tmp_counts.as<uint32_t>(); o.chunk = bb.armed ? h->d_tmp_chunk.as<uint16_t>() : nullptr;
+  o.n_out = n_out; o.keys2 = split ? h->d_tmp_keys2.as<uint64_t>() : nullptr; o.counts2 = split ? h->d_tmp_counts2.as<uint32_t>() : nullptr;
+  o.n_out2 = n_out2; o.occ_out = occ; o.occ_out2 = occ2; o.first_hist = d_fh; o.split_overflow = d_ovf;
+  if (split) {
+    SHQ_CUDA(cudaFuncSetAttribute(bin_aggregate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggSmemBytes));
+    bin_aggregate_kernel<true><<<bb.n_bins, kAggThreads, kAggSmemBytes, st>>>(h->d_packed.as<uint32_t>(), h->d_binoff.as<uint32_t>(), bb.lb, h->key_lo,
+                                                                             clo, chi, cstar, o);
+  } else {
+    SHQ_CUDA(cudaFuncSetAttribute(bin_aggregate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggSmemBytes));
+    bin_aggregate_kernel<false><<<bb.n_bins, kAggThreads, kAggSmemBytes, st>>>(h->d_packed.as<uint32_t>(), h->d_binoff.as<uint32_t>(), bb.lb, h->key_lo,
+                                                                              clo, chi, cstar, o);
+  }
+  L++;
+  if (split && read_scalar(h, d_ovf)) return false;
+  auto finish = [&](Run* R, uint32_t* nout, uint32_t* dense, uint32_t* occs, const uint64_t* tk, const uint32_t* tc, const uint16_t* tch) {
+    SHQ_CUDA(cudaMemcpyAsync(dense, nout, nb * 4, cudaMemcpyDeviceToDevice, st));
+    exclusive_scan_inplace<SumU32>(dense, nb, h->d_scan_scratch, st, dense + nb, &L);
+    exclusive_scan_inplace<SumU32>(occs, nb, h->d_scan_scratch, st, h->d_misc.as<uint32_t>(), &L);
+    uint32_t nd = read_scalar(h, dense + nb);
+    uint32_t oc = read_scalar(h, h->d_misc.as<uint32_t>());
+    R->keys->reserve((size_t)(nd + 4) * 8); R->counts->reserve((size_t)(nd + 4) * 4);
+    if (tch) R->chunk->reserve((size_t)(nd + 4) * 2);
+    compact_bins_kernel<<<bb.n_bins, 256, 0, st>>>(h->d_binoff.as<uint32_t>(), dense, nout, tk, tc, tch, R->keys->as<uint64_t>(),
+                                                  R->counts->as<uint32_t>(), tch ? R->chunk->as<uint16_t>() : nullptr); L++;
+    R->n = nd; R->occ = oc;
+  };
+  finish(A, n_out, doff, occ, o.keys, o.counts, o.chunk);
+  if (split) finish(B, n_out2, doff2, occ2, o.keys2, o.counts2, nullptr);
+  if (first_hist) {
+    uint32_t* p = (uint32_t*)pinned(h, (size_t)bb.nchunks * 4);
+    SHQ_CUDA(cudaMemcpyAsync(p, d_fh, (size_t)bb.nchunks * 4, cudaMemcpyDeviceToHost, st));
+    SHQ_CUDA(cudaStreamSynchronize(st));
+    first_hist->assign(p, p + bb.nchunks);
+  }
   SHQ_CUDA(cudaGetLastError());
-  *n_run = nd; *n_occ = occ;
+  return true;
 }
 
-// Merge the run into the state.  If chunk_hist_host != null (armed) the per-chunk histogram of NEW keys is
-// returned before anything is committed; commit=false stops after that (boundary search).
-// Returns number of new keys.
-uint64_t merge_run(shq_handle_s* h, size_t n_run, bool armed, int nchunks, std::vector<uint32_t>* chunk_hist_host, bool commit) {
+// Merge run R into the state.  If chunk_hist_host != null the per-chunk histogram of NEW keys is returned;
+// commit=false stops after that (boundary search).  Returns the number of new keys.
+uint64_t merge_run(shq_handle_s* h, const Run& R, int nchunks, std::vector<uint32_t>* chunk_hist_host, bool commit) {
   cudaStream_t st = h->stream;
   uint64_t& L = h->stats.kernels_launched;
   Phase ph(h, &h->stats.ms_merge);
-  size_t na = h->n_state, nb = n_run;
+  size_t na = h->n_state, nb = R.n;
+  if (na == 0 && commit && !chunk_hist_host) {          // first run: it simply becomes the state
+    h->st_keys.reserve((nb + 4) * 8); h->st_counts.reserve((nb + 4) * 4);
+    if (nb) {
+      SHQ_CUDA(cudaMemcpyAsync(h->st_keys.p, R.keys->p, nb * 8, cudaMemcpyDeviceToDevice, st));
+      SHQ_CUDA(cudaMemcpyAsync(h->st_counts.p, R.counts->p, nb * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    h->n_state = nb; h->image_valid = false;
+    return nb;
+  }
   size_t total = na + nb;
   size_t ntiles = (total + kMergeTile - 1) / kMergeTile;
   if (ntiles == 0) { if (chunk_hist_host) chunk_hist_host->assign(nchunks, 0); return 0; }
@@ -284,21 +327,21 @@ uint64_t merge_run(shq_handle_s* h, size_t n_run, bool armed, int nchunks, std::
   h->d_heads.reserve((ntiles + 2) * 4);
   h->d_heads64.reserve((ntiles + 2) * 8);
   const uint64_t* A = h->st_keys.as<uint64_t>(); const uint32_t* Ac = h->st_counts.as<uint32_t>();
-  const uint64_t* B = h->d_run_keys.as<uint64_t>(); const uint32_t* Bc = h->d_run_counts.as<uint32_t>();
-  const uint16_t* Bch = armed ? h->d_run_chunk.as<uint16_t>() : nullptr;
-  merge_partition_kernel<<<cdiv(ntiles + 1, 128), 128, 0, st>>>(A, na, B, nb, h->d_split.as<uint64_t>(), ntiles); L++;
+  const uint64_t* Bk = R.keys->as<uint64_t>(); const uint32_t* Bc = R.counts->as<uint32_t>();
+  const uint16_t* Bch = (chunk_hist_host && R.chunk) ? R.chunk->as<uint16_t>() : nullptr;
+  merge_partition_kernel<<<cdiv(ntiles + 1, 128), 128, 0, st>>>(A, na, Bk, nb, h->d_split.as<uint64_t>(), ntiles); L++;
   uint32_t* d_hist = nullptr;
-  if (armed) {
-    h->d_chunk_hist.reserve((size_t)(nchunks + 1) * 4);
+  if (chunk_hist_host) {
+    h->d_chunk_hist.reserve((size_t)(nchunks + 1) * 4 + (size_t)kAggBuckets * 4);
     d_hist = h->d_chunk_hist.as<uint32_t>();
     SHQ_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)(nchunks + 1) * 4, st));
   }
-  merge_tiles_kernel<false><<<(unsigned)ntiles, kMergeThreads, 0, st>>>(A, Ac, na, B, Bc, Bch, nb, h->d_split.as<uint64_t>(),
+  merge_tiles_kernel<false><<<(unsigned)ntiles, kMergeThreads, 0, st>>>(A, Ac, na, Bk, Bc, Bch, nb, h->d_split.as<uint64_t>(),
                                                                        h->d_heads.as<uint32_t>(), nullptr, nullptr, nullptr, d_hist, h->d_err); L++;
   widen_u32_kernel<<<cdiv(ntiles, 256), 256, 0, st>>>(h->d_heads.as<uint32_t>(), h->d_heads64.as<uint64_t>(), ntiles); L++;
   exclusive_scan_inplace<SumU64>(h->d_heads64.as<uint64_t>(), ntiles, h->d_scan_scratch, st, h->d_heads64.as<uint64_t>() + ntiles, &L);
   uint64_t n_out = read_scalar(h, h->d_heads64.as<uint64_t>() + ntiles);
-  if (armed && chunk_hist_host) {
+  if (chunk_hist_host) {
     uint32_t* p = (uint32_t*)pinned(h, (size_t)nchunks * 4);
     SHQ_CUDA(cudaMemcpyAsync(p, d_hist, (size_t)nchunks * 4, cudaMemcpyDeviceToHost, st));
     SHQ_CUDA(cudaStreamSynchronize(st));
@@ -309,7 +352,7 @@ uint64_t merge_run(shq_handle_s* h, size_t n_run, bool armed, int nchunks, std::
   if (!commit) return n_new;
   if (n_out >= ((uint64_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "more than 2^32 distinct keys in one shard");
   h->st_keys2.reserve((n_out + 4) * 8); h->st_counts2.reserve((n_out + 4) * 4);
-  merge_tiles_kernel<true><<<(unsigned)ntiles, kMergeThreads, 0, st>>>(A, Ac, na, B, Bc, Bch, nb, h->d_split.as<uint64_t>(), nullptr,
+  merge_tiles_kernel<true><<<(unsigned)ntiles, kMergeThreads, 0, st>>>(A, Ac, na, Bk, Bc, nullptr, nb, h->d_split.as<uint64_t>(), nullptr,
                                                                       h->d_heads64.as<uint64_t>(), h->st_keys2.as<uint64_t>(),
                                                                       h->st_counts2.as<uint32_t>(), nullptr, h->d_err); L++;
   SHQ_CUDA(cudaGetLastError());
@@ -419,44 +462,80 @@ void process_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uin
   bin_batch(h, d_text, n_text, chunk_ends, nchunks, K, d_keys, n_keys_in, armed, &bb);
   h->stats.batches++;
   if (bb.n_keys == 0) return;
-  std::vector<uint32_t> chunk_keys;
-  if (armed) {
-    uint32_t* p = (uint32_t*)pinned(h, (size_t)nchunks * 4);
-    SHQ_CUDA(cudaMemcpyAsync(p, h->d_chunk_keys.p, (size_t)nchunks * 4, cudaMemcpyDeviceToHost, h->stream));
-    SHQ_CUDA(cudaStreamSynchronize(h->stream));
-    chunk_keys.assign(p, p + nchunks);
-  }
+  Run A{&h->d_run_keys, &h->d_run_counts, &h->d_run_chunk}, B{&h->d_run2_keys, &h->d_run2_counts, nullptr};
   uint32_t clo = 0;
   const uint32_t last = (uint32_t)(nchunks > 0 ? nchunks - 1 : 0);
   for (;;) {
-    size_t n_run = 0; uint64_t n_occ = 0;
     bool track = armed && h->rounds_left > 0;
-    aggregate_bins(h, bb, clo, armed ? last : 0xFFFFFFFFu, &n_run, &n_occ);
     if (!track) {
-      uint64_t n_new = merge_run(h, n_run, armed, nchunks, nullptr, true);
-      h->ndistinct += n_new; h->nelts += n_occ;
+      aggregate_bins(h, bb, clo, armed ? last : 0xFFFFFFFFu, false, 0, &A, nullptr, nullptr);
+      uint64_t n_new = merge_run(h, A, nchunks, nullptr, true);
+      h->ndistinct += n_new; h->nelts += A.occ;
       break;
     }
     // find the first chunk c* >= clo after which ndistinct >= trigger (t=1 rule, CQF_mt.h:837)
     std::vector<uint32_t> hist;
-    merge_run(h, n_run, true, nchunks, &hist, false);
+    const bool empty_state = h->n_state == 0;
+    aggregate_bins(h, bb, clo, last, false, 0, &A, nullptr, empty_state ? &hist : nullptr);
+    if (!empty_state) merge_run(h, A, nchunks, &hist, false);
     uint64_t nd = h->ndistinct; int cstar = -1;
     for (uint32_t c = clo; c <= last; c++) { nd += hist[c]; if (nd >= h->trigger) { cstar = (int)c; break; } }
     if (cstar < 0 || (uint32_t)cstar == last) {
-      uint64_t n_new = merge_run(h, n_run, true, nchunks, nullptr, true);
-      h->ndistinct += n_new; h->nelts += n_occ;
+      uint64_t n_new = merge_run(h, A, nchunks, nullptr, true);
+      h->ndistinct += n_new; h->nelts += A.occ;
       if (cstar >= 0) { h->rounds_left--; denoise_round(h); }
       break;
     }
-    // commit chunks [clo, c*] only, sweep, then replay the rest of the batch
-    aggregate_bins(h, bb, clo, (uint32_t)cstar, &n_run, &n_occ);
-    uint64_t n_new = merge_run(h, n_run, true, nchunks, nullptr, true);
-    h->ndistinct += n_new; h->nelts += n_occ;
+    // boundary inside the batch.  Last scheduled round: one split pass yields both sides.
+    if (h->rounds_left == 1 && aggregate_bins(h, bb, clo, last, true, (uint32_t)cstar, &A, &B, nullptr)) {
+      uint64_t n_new = merge_run(h, A, nchunks, nullptr, true);
+      h->ndistinct += n_new; h->nelts += A.occ;
+      h->rounds_left--;
+      denoise_round(h);
+      n_new = merge_run(h, B, nchunks, nullptr, true);
+      h->ndistinct += n_new; h->nelts += B.occ;
+      break;
+    }
+    // general case: commit chunks [clo, c*], sweep, then replay the rest of the batch with tracking
+    aggregate_bins(h, bb, clo, (uint32_t)cstar, false, 0, &A, nullptr, nullptr);
+    uint64_t n_new = merge_run(h, A, nchunks, nullptr, true);
+    h->ndistinct += n_new; h->nelts += A.occ;
     h->rounds_left--;
     denoise_round(h);
     clo = (uint32_t)cstar + 1;
   }
   check_err_flag(h);
+}
+
+// All keys of the reads in d_text as a device list: read r owns slots [off[r], off[r+1]) (off = scan of len-K+1);
+// slots the N rule leaves unused hold ~0.  Returns the number of slots.
+size_t hash_to_keylist(shq_handle_s* h, const char* d_text, size_t n, int K, uint64_t* d_out, size_t cap) {
+  cudaStream_t st = h->stream;
+  uint64_t& L = h->stats.kernels_launched;
+  if (K < 1 || K > 1024) SHQ_FAIL(SHQ_ERR_ARG, "K=%d outside [1,1024]", K);
+  if (n >= ((size_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "text of %zu bytes exceeds 4 GiB per call", n);
+  const char* src = d_text;
+  if (reinterpret_cast<uintptr_t>(src) & 15) {
+    h->d_text.reserve(n + 64);
+    SHQ_CUDA(cudaMemcpyAsync(h->d_text.p, src, n, cudaMemcpyDeviceToDevice, st));
+    src = h->d_text.as<char>();
+  }
+  uint32_t n_lines = index_lines(h, src, n);
+  if (n_lines & 3) SHQ_FAIL(SHQ_ERR_MALFORMED, "text holds %u lines, not a multiple of 4", n_lines);
+  uint32_t n_reads = n_lines / 4;
+  if (n_reads == 0) return 0;
+  h->d_heads64.reserve((size_t)(n_reads + 2) * 8);
+  uint64_t* off = h->d_heads64.as<uint64_t>();
+  read_window_counts_kernel<<<cdiv(n_reads, 256), 256, 0, st>>>(h->d_nl_pos.as<uint32_t>(), n_reads, K, off); L++;
+  exclusive_scan_inplace<SumU64>(off, n_reads, h->d_scan_scratch, st, off + n_reads, &L);
+  uint64_t total = read_scalar(h, off + n_reads);
+  if (total > cap) SHQ_FAIL(SHQ_ERR_ARG, "key buffer too small: %llu slots needed, capacity %zu", (unsigned long long)total, cap);
+  HashParams hp{};
+  hp.text = src; hp.nl_pos = h->d_nl_pos.as<uint32_t>(); hp.n_reads = n_reads; hp.K = K; hp.hb = h->hb;
+  roll_keys_kernel<<<cdiv(n_reads, 256), 256, 0, st>>>(hp, off, d_out); L++;
+  SHQ_CUDA(cudaGetLastError());
+  h->stats.keys_hashed += total;
+  return (size_t)total;
 }
 
 void flush_stage(shq_handle_s* h) {
@@ -495,6 +574,8 @@ void init_handle(shq_handle_s* h, int qb, int hb, uint32_t seed, int device, int
   if (qb < 1 || qb > 40 || hb - qb != 8) SHQ_FAIL(SHQ_ERR_ARG, "need 1 <= qb <= 40 and hb - qb == 8 (got qb=%d hb=%d)", qb, hb);
   if (nshards < 1 || (nshards & (nshards - 1)) || shard < 0 || shard >= nshards || (1 << qb) < nshards * 64)
     SHQ_FAIL(SHQ_ERR_ARG, "bad shard %d of %d", shard, nshards);
+  if (const char* e = getenv("SHQ_SCATTER_W")) { int v = atoi(e); if (v == 16 || v == 32) g_scatter_w = v; }
+  if (const char* e = getenv("SHQ_BIN_BITS")) { int v = atoi(e); if (v >= 4 && v <= 13) g_bin_bits = v; }
   SHQ_CUDA(cudaSetDevice(device));
   h->device = device; h->qb = qb; h->hb = hb; h->seed = seed; h->shard = shard; h->nshards = nshards;
   h->nslots = 1ULL << qb;
@@ -517,7 +598,8 @@ void free_handle(shq_handle_s* h) {
                     &h->d_chunk_ends, &h->d_chunk_line_end, &h->d_chunk_keys, &h->d_chunk_hist, &h->d_slow, &h->d_hist, &h->d_tot,
                     &h->d_binoff, &h->d_packed, &h->d_tmp_keys, &h->d_tmp_counts, &h->d_tmp_chunk, &h->d_nout, &h->d_occ,
                     &h->d_dense_off, &h->d_run_keys, &h->d_run_counts, &h->d_run_chunk, &h->d_split, &h->d_heads, &h->d_heads64,
-                    &h->d_scan_scratch, &h->d_misc, &h->d_pairs, &h->d_pos, &h->d_flags, &h->d_keep, &h->d_q_in, &h->d_q_cnt, &h->d_q_was};
+                    &h->d_scan_scratch, &h->d_misc, &h->d_pairs, &h->d_pos, &h->d_flags, &h->d_keep, &h->d_q_in, &h->d_q_cnt, &h->d_q_was,
+                    &h->d_tmp_keys2, &h->d_tmp_counts2, &h->d_run2_keys, &h->d_run2_counts};
   for (DevBuf* b : bufs) b->release();
   if (h->d_err) cudaFree(h->d_err);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -855,53 +937,21 @@ int shq_hash_fastq_chunk(shq_t h, const char* text, size_t n, int K, uint64_t* k
   struct { const char* t; size_t n; int K; uint64_t* keys; size_t cap; size_t* nk; } args{text, n, K, keys, cap, nkeys};
   SHQ_API_BEGIN(h)
     cudaStream_t st = h->stream;
-    uint64_t& L = h->stats.kernels_launched;
     *a.nk = 0;
     if (a.n == 0) return;
-    if (a.K < 1 || a.K > kTilePos - 32) SHQ_FAIL(SHQ_ERR_ARG, "K=%d outside [1,%d]", a.K, kTilePos - 32);
+    if (a.t[a.n - 1] != '\n') SHQ_FAIL(SHQ_ERR_MALFORMED, "chunk has no trailing newline");
     h->d_text.reserve(a.n + 64);
     SHQ_CUDA(cudaMemcpyAsync(h->d_text.p, a.t, a.n, cudaMemcpyHostToDevice, st));
-    unsigned ntiles = cdiv(a.n, kNlTile);
-    h->d_nl_tiles.reserve((size_t)(ntiles + 1) * 4);
-    nl_count_kernel<<<ntiles, kNlThreads, 0, st>>>(h->d_text.as<char>(), a.n, h->d_nl_tiles.as<uint32_t>()); L++;
-    h->d_misc.reserve(256);
-    exclusive_scan_inplace<SumU32>(h->d_nl_tiles.as<uint32_t>(), ntiles, h->d_scan_scratch, st, h->d_misc.as<uint32_t>(), &L);
-    uint32_t n_lines = read_scalar(h, h->d_misc.as<uint32_t>());
-    if ((n_lines & 3) || a.t[a.n - 1] != '\n') SHQ_FAIL(SHQ_ERR_MALFORMED, "chunk holds %u lines / no trailing newline", n_lines);
-    h->d_nl_pos.reserve((size_t)(n_lines + 4) * 4);
-    nl_write_kernel<<<ntiles, kNlThreads, 0, st>>>(h->d_text.as<char>(), a.n, h->d_nl_tiles.as<uint32_t>(), h->d_nl_pos.as<uint32_t>()); L++;
-    HashParams hp{};
-    hp.text = h->d_text.as<char>(); hp.nl_pos = h->d_nl_pos.as<uint32_t>(); hp.n_reads = n_lines / 4; hp.K = a.K; hp.hb = h->hb;
-    hp.key_lo = 0; hp.key_hi = ~0ULL; hp.n_bins = 0;
-    h->d_slow.reserve((size_t)(hp.n_reads + 2) * 4 + 16);
-    uint32_t* slow_count = h->d_slow.as<uint32_t>();
-    hp.slow_count = slow_count; hp.slow_list = slow_count + 4;
-    SHQ_CUDA(cudaMemsetAsync(slow_count, 0, 16, st));
-    h->d_q_cnt.reserve(a.cap * 8 + 64);
-    h->d_misc.reserve(256);
-    unsigned long long* d_n = h->d_misc.as<unsigned long long>() + 8;
-    SHQ_CUDA(cudaMemsetAsync(d_n, 0, 8, st));
-    Sink sk{}; sk.keys = h->d_q_cnt.as<uint64_t>(); sk.nkeys = d_n; sk.cap = a.cap;
-    size_t smem = (size_t)kHashWarps * 2 * (kTilePos + 1) * 8;
-    // the key-list mode needs the slow list too: run the count-mode N test through a dry pass
-    SHQ_CUDA(cudaFuncSetAttribute(hash_reads_kernel<kSinkKeys>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    hash_reads_kernel<kSinkKeys><<<2 * kNumSMs, kHashThreads, smem, st>>>(hp, sk, nullptr, nullptr); L++;
-    // reads with 'N' past the first K bases: list them with a tiny classify pass (count mode over 1 bin)
-    HashParams hc = hp; hc.n_bins = 1; hc.lb = 63; hc.key_lo = 0; hc.key_hi = 0;   // drops every key, only fills the slow list
-    h->d_hist.reserve((size_t)(2 * kNumSMs + 1) * 4);
-    size_t smem_c = 16 + smem;
-    SHQ_CUDA(cudaFuncSetAttribute(hash_reads_kernel<kSinkCount>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-    Sink sc{};
-    hash_reads_kernel<kSinkCount><<<2 * kNumSMs, kHashThreads, smem_c, st>>>(hc, sc, h->d_hist.as<uint32_t>(), nullptr); L++;
-    uint32_t n_slow = read_scalar(h, slow_count);
-    if (n_slow) { hash_slow_reads_kernel<kSinkKeys><<<cdiv(n_slow, 128), 128, 0, st>>>(hp, sk, n_slow); L++; }
-    SHQ_CUDA(cudaGetLastError());
-    unsigned long long nk = read_scalar(h, d_n);
-    *a.nk = (size_t)nk;
-    size_t m = std::min((size_t)nk, a.cap);
-    if (m && a.keys) SHQ_CUDA(cudaMemcpyAsync(a.keys, h->d_q_cnt.p, m * 8, cudaMemcpyDeviceToHost, st));
+    size_t slots_cap = a.n;
+    h->d_q_cnt.reserve(slots_cap * 8 + 64);
+    size_t slots = hash_to_keylist(h, h->d_text.as<char>(), a.n, a.K, h->d_q_cnt.as<uint64_t>(), slots_cap);
+    std::vector<uint64_t> tmp(slots);
+    if (slots) SHQ_CUDA(cudaMemcpyAsync(tmp.data(), h->d_q_cnt.p, slots * 8, cudaMemcpyDeviceToHost, st));
     SHQ_CUDA(cudaStreamSynchronize(st));
-    h->stats.h2d_bytes += a.n; h->stats.d2h_bytes += m * 8;
+    size_t m = 0;
+    for (size_t i = 0; i < slots; i++) if (tmp[i] != ~0ULL) { if (m < a.cap && a.keys) a.keys[m] = tmp[i]; m++; }
+    *a.nk = m;
+    h->stats.h2d_bytes += a.n; h->stats.d2h_bytes += slots * 8;
   SHQ_API_END
 }
 
@@ -920,53 +970,10 @@ int shq_hash_fastq_device(shq_t h, const char* d_text, size_t n, int K, uint64_t
   if (!h || !nkeys || (!d_text && n)) return SHQ_ERR_ARG;
   struct { const char* t; size_t n; int K; uint64_t* keys; size_t cap; size_t* nk; } args{d_text, n, K, d_keys, cap, nkeys};
   SHQ_API_BEGIN(h)
-    cudaStream_t st = h->stream;
-    uint64_t& L = h->stats.kernels_launched;
     *a.nk = 0;
     if (a.n == 0) return;
-    if (a.K < 1 || a.K > kTilePos - 32) SHQ_FAIL(SHQ_ERR_ARG, "K=%d outside [1,%d]", a.K, kTilePos - 32);
-    if (a.n >= ((size_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "text of %zu bytes exceeds 4 GiB per call", a.n);
-    const char* src = a.t;
-    if (reinterpret_cast<uintptr_t>(src) & 15) {
-      h->d_text.reserve(a.n + 64);
-      SHQ_CUDA(cudaMemcpyAsync(h->d_text.p, src, a.n, cudaMemcpyDeviceToDevice, st));
-      src = h->d_text.as<char>();
-    }
-    unsigned ntiles = cdiv(a.n, kNlTile);
-    h->d_nl_tiles.reserve((size_t)(ntiles + 1) * 4);
-    nl_count_kernel<<<ntiles, kNlThreads, 0, st>>>(src, a.n, h->d_nl_tiles.as<uint32_t>()); L++;
-    h->d_misc.reserve(256);
-    exclusive_scan_inplace<SumU32>(h->d_nl_tiles.as<uint32_t>(), ntiles, h->d_scan_scratch, st, h->d_misc.as<uint32_t>(), &L);
-    uint32_t n_lines = read_scalar(h, h->d_misc.as<uint32_t>());
-    if (n_lines & 3) SHQ_FAIL(SHQ_ERR_MALFORMED, "text holds %u lines, not a multiple of 4", n_lines);
-    h->d_nl_pos.reserve((size_t)(n_lines + 4) * 4);
-    nl_write_kernel<<<ntiles, kNlThreads, 0, st>>>(src, a.n, h->d_nl_tiles.as<uint32_t>(), h->d_nl_pos.as<uint32_t>()); L++;
-    HashParams hp{};
-    hp.text = src; hp.nl_pos = h->d_nl_pos.as<uint32_t>(); hp.n_reads = n_lines / 4; hp.K = a.K; hp.hb = h->hb;
-    hp.key_lo = 0; hp.key_hi = ~0ULL; hp.n_bins = 0;
-    h->d_slow.reserve((size_t)(hp.n_reads + 2) * 4 + 16);
-    uint32_t* slow_count = h->d_slow.as<uint32_t>();
-    hp.slow_count = slow_count; hp.slow_list = slow_count + 4;
-    SHQ_CUDA(cudaMemsetAsync(slow_count, 0, 16, st));
-    unsigned long long* d_n = h->d_misc.as<unsigned long long>() + 8;
-    SHQ_CUDA(cudaMemsetAsync(d_n, 0, 8, st));
-    Sink sk{}; sk.keys = a.keys; sk.nkeys = d_n; sk.cap = a.cap;
-    size_t smem = (size_t)kHashWarps * 2 * (kTilePos + 1) * 8;
-    SHQ_CUDA(cudaFuncSetAttribute(hash_reads_kernel<kSinkKeys>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    hash_reads_kernel<kSinkKeys><<<2 * kNumSMs, kHashThreads, smem, st>>>(hp, sk, nullptr, nullptr); L++;
-    HashParams hc = hp; hc.n_bins = 1; hc.lb = 63; hc.key_lo = 0; hc.key_hi = 0;
-    h->d_hist.reserve((size_t)(2 * kNumSMs + 1) * 4);
-    size_t smem_c = 16 + smem;
-    SHQ_CUDA(cudaFuncSetAttribute(hash_reads_kernel<kSinkCount>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-    Sink sc{};
-    hash_reads_kernel<kSinkCount><<<2 * kNumSMs, kHashThreads, smem_c, st>>>(hc, sc, h->d_hist.as<uint32_t>(), nullptr); L++;
-    uint32_t n_slow = read_scalar(h, slow_count);
-    if (n_slow) { hash_slow_reads_kernel<kSinkKeys><<<cdiv(n_slow, 128), 128, 0, st>>>(hp, sk, n_slow); L++; }
-    SHQ_CUDA(cudaGetLastError());
-    unsigned long long nk = read_scalar(h, d_n);
-    if (nk > a.cap) SHQ_FAIL(SHQ_ERR_ARG, "key buffer too small: %llu keys, capacity %zu", nk, a.cap);
-    *a.nk = (size_t)nk;
-    h->stats.keys_hashed += nk;
+    *a.nk = hash_to_keylist(h, a.t, a.n, a.K, a.keys, a.cap);
+    SHQ_CUDA(cudaStreamSynchronize(h->stream));
   SHQ_API_END
 }
 

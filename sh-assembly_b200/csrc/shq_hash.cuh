@@ -293,27 +293,44 @@ __global__ void hash_slow_reads_kernel(HashParams hp, Sink sk, uint32_t n_slow) 
   if (MODE == kSinkCount && hp.chunk_keys) atomicAdd(&hp.chunk_keys[chunk], emitted);
 }
 
-// Raw key stream source (shq_insert_keys*): same two passes over a u64 array.
+// Raw key stream source (shq_insert_keys*): the same two passes over a u64 array.
+// count: global histogram.  scatter: each CTA re-counts its strip, reserves one range per bin on the shared
+// cursors and writes its keys there.  dynamic smem: 2 * n_bins * 4.
 template <int MODE>
 __global__ void __launch_bounds__(256) hash_keys_kernel(const uint64_t* __restrict__ keys, size_t n, HashParams hp, Sink sk,
-                                                       uint32_t* __restrict__ hist_matrix, const uint32_t* __restrict__ bin_off) {
+                                                       uint32_t* __restrict__ g_bins, const uint32_t* __restrict__ unused) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t* s_bins = reinterpret_cast<uint32_t*>(smem_raw);
-  if (MODE == kSinkCount) {
-    for (int i = threadIdx.x; i < hp.n_bins; i += blockDim.x) s_bins[i] = 0;
-  } else {
-    const uint32_t* row = hist_matrix + (size_t)blockIdx.x * hp.n_bins;
-    for (int i = threadIdx.x; i < hp.n_bins; i += blockDim.x) s_bins[i] = bin_off[i] + row[i];
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw);
+  uint32_t* s_base = s_hist + hp.n_bins;
+  for (int i = threadIdx.x; i < hp.n_bins; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  size_t i0 = (n * blockIdx.x) / gridDim.x, i1 = (n * (blockIdx.x + 1)) / gridDim.x;
+  for (size_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    uint64_t key = keys[i];
+    if (key < hp.key_lo || key >= hp.key_hi) continue;
+    atomicAdd(&s_hist[(uint32_t)((key - hp.key_lo) >> hp.lb)], 1u);
   }
   __syncthreads();
-  Sink lsk = sk; lsk.bins = s_bins;
-  size_t i0 = (n * blockIdx.x) / gridDim.x, i1 = (n * (blockIdx.x + 1)) / gridDim.x;
-  for (size_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) sink_key<MODE>(hp, lsk, keys[i], 0);
   if (MODE == kSinkCount) {
-    __syncthreads();
-    uint32_t* row = hist_matrix + (size_t)blockIdx.x * hp.n_bins;
-    for (int i = threadIdx.x; i < hp.n_bins; i += blockDim.x) row[i] = s_bins[i];
+    for (int i = threadIdx.x; i < hp.n_bins; i += blockDim.x) { uint32_t v = s_hist[i]; if (v) atomicAdd(&g_bins[i], v); }
+    return;
   }
+  for (int i = threadIdx.x; i < hp.n_bins; i += blockDim.x) {
+    uint32_t c = s_hist[i];
+    s_base[i] = c ? atomicAdd(&g_bins[i], c) : 0;
+    s_hist[i] = 0;
+  }
+  __syncthreads();
+  const uint64_t lowmask = (1ULL << hp.lb) - 1;
+  for (size_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    uint64_t key = keys[i];
+    if (key < hp.key_lo || key >= hp.key_hi) continue;
+    uint64_t rel = key - hp.key_lo;
+    uint32_t bin = (uint32_t)(rel >> hp.lb);
+    uint32_t rank = atomicAdd(&s_hist[bin], 1u);
+    sk.packed[s_base[bin] + rank] = (uint32_t)(rel & lowmask);
+  }
+  (void)unused;
 }
 
 // Column-wise exclusive scan of the (rows x n_bins) histogram matrix, in place; tot[p] = column sum.
@@ -350,11 +367,12 @@ __global__ void owner_partition_kernel(const uint64_t* __restrict__ keys, size_t
 #pragma unroll
   for (int i = 0; i < 16; i++) loc[i] = 0;
   if (!SCATTER) {
-    for (size_t i = b; i < e; i++) { int o = (int)(keys[i] >> shift); loc[o & 15]++; }
+    for (size_t i = b; i < e; i++) { uint64_t k = keys[i]; if (k == ~0ULL) continue; int o = (int)(k >> shift); loc[o & 15]++; }
     for (int o = 0; o < nparts; o++) mat[(size_t)o * nthreads + t] = loc[o];
   } else {
     for (size_t i = b; i < e; i++) {
       uint64_t k = keys[i];
+      if (k == ~0ULL) continue;      // unused slot of the key list (N restart rule)
       int o = (int)(k >> shift);
       out[mat[(size_t)o * nthreads + t] + loc[o & 15]++] = k;
     }

@@ -1,0 +1,216 @@
+// shq_roll.cuh -- K2, second generation: one THREAD per read, rolling canonical ntHash.
+//
+// The first generation (shq_hash.cuh, warp per read + prefix-XOR scan) executed ~10 warp instructions per
+// window and scattered 4-byte stores into 296 x 16384 open segments (21 GB of DRAM traffic for 2.4 GB of
+// algorithmic bytes, profiles/r1_ncu_full_v1_raw.csv).  Here:
+//   * hashing is the reference's own recurrence (base/nthash.hpp:305-309) per thread: 4 shared-memory table
+//     lookups, two 1-bit rotates and four XORs per window; text is fetched as aligned 32-bit words;
+//     the 'N' restart rule (cqf/CQF_mt.h:624-718) is part of the same loop, so there is no slow path;
+//   * the scatter pass stages one round of keys per CTA in shared memory, reserves space in every bin with ONE
+//     global atomicAdd per (round, bin) on cursors shared by all CTAs, and writes the keys of a bin next to
+//     each other, so L2 merges them into full sectors (one open line per bin instead of one per CTA x bin).
+#pragma once
+#include "shq_common.cuh"
+#include "shq_hash.cuh"
+
+namespace shq {
+
+struct RollTables {            // in shared memory, indexed by the text byte
+  uint64_t in_f[256];          // seed(c)
+  uint64_t out_f[256];         // rol(seed(c), K)
+  uint64_t in_r[256];          // rol(seed'(c & 7), K-1)
+  uint64_t out_r[256];         // rol(seed'(c & 7), 63)
+};
+__device__ __forceinline__ void roll_tables_init(RollTables* t, int K) {
+  for (int c = threadIdx.x; c < 256; c += blockDim.x) {
+    uint64_t f = nt_seed_fwd((unsigned char)c), r = nt_seed_rev((unsigned char)c);
+    t->in_f[c] = f; t->out_f[c] = rotl64(f, K);
+    t->in_r[c] = rotl64(r, K - 1); t->out_r[c] = rotl64(r, 63);
+  }
+}
+
+// Sequential byte reader over global text using aligned 32-bit loads.
+struct ByteStream {
+  const uint32_t* wp; uint32_t w; int left;   // bytes left in w
+  __device__ __forceinline__ void init(const char* text, uint32_t pos) {
+    uintptr_t a = reinterpret_cast<uintptr_t>(text) + pos;
+    wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    int skip = (int)(a & 3);
+    w = __ldg(wp) >> (8 * skip);
+    left = 4 - skip;
+  }
+  __device__ __forceinline__ unsigned char next() {
+    if (left == 0) { wp++; w = __ldg(wp); left = 4; }
+    unsigned char c = (unsigned char)(w & 0xFF);
+    w >>= 8; left--;
+    return c;
+  }
+};
+
+// Per-thread generator of the key stream of one read after another (reads first, first+stride, ...).
+struct Roller {
+  const HashParams* hp; const RollTables* tab;
+  uint32_t read, read_end, stride;
+  uint32_t s, len, pos;        // current read: start offset, length, index of the NEXT char to roll in
+  uint64_t fh, rh; uint32_t chunk;
+  ByteStream in, out;
+  bool active;                 // a read is open and primed (fh/rh valid for the window ending at pos-1)
+
+  __device__ __forceinline__ void start(const HashParams* hp_, const RollTables* tab_, uint32_t first, uint32_t end, uint32_t stride_) {
+    hp = hp_; tab = tab_; read = first; read_end = end; stride = stride_; active = false;
+  }
+  // prime at sub-read start s0 (absolute index in the read); returns false if fewer than K chars remain
+  __device__ __forceinline__ bool prime(uint32_t s0) {
+    const uint32_t K = hp->K;
+    if (s0 > len || len - s0 < K) return false;
+    in.init(hp->text, s + s0);
+    out.init(hp->text, s + s0);
+    uint64_t f = 0, r = 0;
+    for (uint32_t i = 0; i < K; i++) {
+      unsigned char c = in.next();
+      f = rotl64(f, 1) ^ tab->in_f[c];                 // == xor of rol(seed, K-1-i)
+      r ^= rotl64(nt_seed_rev(c), i);
+    }
+    fh = f; rh = r; pos = s0 + K;
+    return true;
+  }
+  // next key of the stream; false when this thread has no reads left
+  __device__ __forceinline__ bool next(uint64_t* key, uint32_t* ch) {
+    const uint64_t mask = hp->hb >= 64 ? ~0ULL : ((1ULL << hp->hb) - 1);
+    for (;;) {
+      if (!active) {
+        if (read >= read_end) return false;
+        s = hp->nl_pos[4 * (size_t)read] + 1;
+        len = hp->nl_pos[4 * (size_t)read + 1] - s;
+        chunk = chunk_of_line(*hp, 4 * read + 1);
+        read += stride;
+        if (!prime(0)) continue;
+        active = true;
+        *key = (fh < rh ? fh : rh) & mask; *ch = chunk;
+        return true;
+      }
+      if (pos >= len) { active = false; continue; }
+      unsigned char cin = in.next();
+      if (cin == 'N') {                                 // restart after the N (CQF_mt.h:680-683)
+        if (!prime(pos + 1)) { active = false; continue; }
+        *key = (fh < rh ? fh : rh) & mask; *ch = chunk;
+        return true;
+      }
+      unsigned char cout = out.next();
+      fh = rotl64(fh, 1) ^ tab->out_f[cout] ^ tab->in_f[cin];
+      rh = rotr64(rh, 1) ^ tab->out_r[cout] ^ tab->in_r[cin];
+      pos++;
+      *key = (fh < rh ? fh : rh) & mask; *ch = chunk;
+      return true;
+    }
+  }
+};
+
+constexpr int kRollThreads = 512;
+
+// Pass 1: global histogram of bins (+ per-chunk key counts when armed).
+// dynamic smem: RollTables + n_bins * 4
+__global__ void __launch_bounds__(kRollThreads) roll_count_kernel(HashParams hp, uint32_t* __restrict__ g_hist) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RollTables* tab = reinterpret_cast<RollTables*>(smem_raw);
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw + sizeof(RollTables));
+  roll_tables_init(tab, hp.K);
+  for (int i = threadIdx.x; i < hp.n_bins; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  uint32_t r0 = (uint32_t)(((uint64_t)hp.n_reads * blockIdx.x) / gridDim.x);
+  uint32_t r1 = (uint32_t)(((uint64_t)hp.n_reads * (blockIdx.x + 1)) / gridDim.x);
+  Roller R;
+  R.start(&hp, tab, r0 + threadIdx.x, r1, blockDim.x);
+  uint64_t key; uint32_t ch; uint32_t last_chunk = 0xFFFFFFFFu, run = 0;
+  while (R.next(&key, &ch)) {
+    if (hp.chunk_keys) {
+      if (ch != last_chunk) { if (run) atomicAdd(&hp.chunk_keys[last_chunk], run); last_chunk = ch; run = 0; }
+      run++;
+    }
+    if (key < hp.key_lo || key >= hp.key_hi) continue;
+    atomicAdd(&s_hist[(uint32_t)((key - hp.key_lo) >> hp.lb)], 1u);
+  }
+  if (hp.chunk_keys && run) atomicAdd(&hp.chunk_keys[last_chunk], run);
+  __syncthreads();
+  for (int i = threadIdx.x; i < hp.n_bins; i += blockDim.x) { uint32_t v = s_hist[i]; if (v) atomicAdd(&g_hist[i], v); }
+}
+
+// Pass 2: staged scatter.  g_cursor[bin] starts at the bin's offset and is shared by all CTAs.
+// dynamic smem: RollTables + n_bins * 8 (hist, base) + kRollThreads * W * 6 (keys u32, bins u16)
+template <int W>
+__global__ void __launch_bounds__(kRollThreads) roll_scatter_kernel(HashParams hp, uint32_t* __restrict__ g_cursor, uint32_t* __restrict__ packed) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RollTables* tab = reinterpret_cast<RollTables*>(smem_raw);
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw + sizeof(RollTables));
+  uint32_t* s_base = s_hist + hp.n_bins;
+  uint32_t* s_key = s_base + hp.n_bins;
+  uint16_t* s_bin = reinterpret_cast<uint16_t*>(s_key + kRollThreads * W);
+  roll_tables_init(tab, hp.K);
+  uint32_t r0 = (uint32_t)(((uint64_t)hp.n_reads * blockIdx.x) / gridDim.x);
+  uint32_t r1 = (uint32_t)(((uint64_t)hp.n_reads * (blockIdx.x + 1)) / gridDim.x);
+  __syncthreads();
+  Roller R;
+  R.start(&hp, tab, r0 + threadIdx.x, r1, blockDim.x);
+  const uint32_t lowmask = hp.lb >= 32 ? 0xFFFFFFFFu : ((1u << hp.lb) - 1);
+  bool more = true;
+  for (;;) {
+    for (int i = threadIdx.x; i < hp.n_bins; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    int produced = 0;
+    while (more && produced < W) {
+      uint64_t key; uint32_t ch;
+      if (!R.next(&key, &ch)) { more = false; break; }
+      if (key < hp.key_lo || key >= hp.key_hi) continue;
+      uint64_t rel = key - hp.key_lo;
+      uint32_t bin = (uint32_t)(rel >> hp.lb);
+      int idx = produced * kRollThreads + threadIdx.x;          // strided: conflict-free in the write-out loop
+      s_key[idx] = ((uint32_t)rel & lowmask) | (hp.lb >= 32 ? 0 : (ch << hp.lb));
+      s_bin[idx] = (uint16_t)bin;
+      atomicAdd(&s_hist[bin], 1u);
+      produced++;
+    }
+    for (int j = produced; j < W; j++) s_bin[j * kRollThreads + threadIdx.x] = 0xFFFF;
+    int any = __syncthreads_or(produced > 0);
+    if (!any) break;
+    for (int i = threadIdx.x; i < hp.n_bins; i += blockDim.x) {
+      uint32_t c = s_hist[i];
+      s_base[i] = c ? atomicAdd(&g_cursor[i], c) : 0;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < W; j++) {
+      int idx = j * kRollThreads + threadIdx.x;
+      uint32_t bin = s_bin[idx];
+      if (bin != 0xFFFF) {
+        uint32_t rank = atomicSub(&s_hist[bin], 1u) - 1;
+        packed[s_base[bin] + rank] = s_key[idx];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Key list (test hook / multi-GPU exchange): read r writes its keys at out[off[r] ...]; off = exclusive scan of
+// max(len-K+1, 0).  Slots that the N rule leaves unused hold the sentinel ~0.
+__global__ void read_window_counts_kernel(const uint32_t* __restrict__ nl_pos, uint32_t n_reads, int K, uint64_t* __restrict__ cnt) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  uint32_t len = nl_pos[4 * (size_t)r + 1] - (nl_pos[4 * (size_t)r] + 1);
+  cnt[r] = len >= (uint32_t)K ? len - K + 1 : 0;
+}
+constexpr uint64_t kNoKey = ~0ULL;
+__global__ void __launch_bounds__(256) roll_keys_kernel(HashParams hp, const uint64_t* __restrict__ off, uint64_t* __restrict__ out) {
+  __shared__ RollTables tab;
+  roll_tables_init(&tab, hp.K);
+  __syncthreads();
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= hp.n_reads) return;
+  uint64_t o = off[r], e = off[r + 1];
+  Roller R;
+  R.start(&hp, &tab, r, r + 1, 1);
+  uint64_t key; uint32_t ch;
+  while (o < e && R.next(&key, &ch)) out[o++] = key;
+  while (o < e) out[o++] = kNoKey;
+}
+
+}  // namespace shq

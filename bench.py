@@ -244,7 +244,7 @@ def run_ours(args, rank, world, local_rank):
         q.set_denoise_schedule(int(p.trigger), int(p.num_deNoise), args.end_denoise)
         o = 0
         for e in ends:
-            q.insert_fastq_chunk_raw(h_ptr + o, int(e) - o, args.k)
+            q.insert_fastq_pinned_raw(h_ptr + o, int(e) - o, args.k)
             o = int(e)
         q.finish()
         w = C.c_size_t()

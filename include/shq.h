@@ -69,6 +69,11 @@ int shq_set_denoise_schedule(shq_t h, uint64_t trigger_ndistinct, uint32_t round
  * counters become exact at shq_sync / shq_counts / shq_finish.                  */
 int shq_insert_fastq_chunk(shq_t h, const char* text, size_t n, int K);
 
+/* Zero-copy variant for PINNED (page-locked) host memory: the chunk is copied straight from the caller's buffer
+ * with an asynchronous DMA on a separate copy stream, double-buffered against the compute of the previous
+ * batch.  The buffer must stay valid and unchanged until shq_sync / shq_finish / shq_counts returns.          */
+int shq_insert_fastq_pinned(shq_t h, const char* pinned_text, size_t n, int K);
+
 /* Same for text already resident in device memory (benchmark / pipeline use):
  * d_text holds nchunks consecutive chunks, chunk c = [chunk_ends[c-1], chunk_ends[c])
  * (host array of byte offsets).  Processed before the call returns control

@@ -60,7 +60,7 @@ _lib = None
 # every symbol include/shq.h declares
 EXPORTS = [
     "shq_strerror", "shq_last_error", "shq_create", "shq_create_shard", "shq_destroy", "shq_reset", "shq_set_denoise_schedule",
-    "shq_insert_fastq_chunk", "shq_insert_fastq_device", "shq_insert_keys", "shq_insert_keys_device", "shq_finish",
+    "shq_insert_fastq_chunk", "shq_insert_fastq_pinned", "shq_insert_fastq_device", "shq_insert_keys", "shq_insert_keys_device", "shq_finish",
     "shq_sync", "shq_counts", "shq_rounds_done", "shq_denoise", "shq_image_size", "shq_export_cqf", "shq_save",
     "shq_load", "shq_load_image", "shq_geometry", "shq_iterate", "shq_query_set_traveled", "shq_query",
     "shq_hash_fastq_chunk", "shq_unitigs_begin", "shq_unitigs_add_reads", "shq_unitigs_build", "shq_unitigs_count",
@@ -90,6 +90,7 @@ def lib():
         L.shq_reset.argtypes = [vp]
         L.shq_set_denoise_schedule.argtypes = [vp, u64, C.c_uint32, C.c_int]
         L.shq_insert_fastq_chunk.argtypes = [vp, vp, sz, C.c_int]
+        L.shq_insert_fastq_pinned.argtypes = [vp, vp, sz, C.c_int]
         L.shq_insert_fastq_device.argtypes = [vp, vp, sz, vp, sz, C.c_int]
         L.shq_insert_keys.argtypes = [vp, vp, sz]
         L.shq_insert_keys_device.argtypes = [vp, vp, sz]
@@ -293,6 +294,9 @@ class CQF:
 
     def build_kmer_spectrum(self, reader, K):
         self._check(self.L.shq_build_kmer_spectrum(self.h, reader.h, K))
+
+    def insert_fastq_pinned_raw(self, addr, n, K):
+        self._check(self.L.shq_insert_fastq_pinned(self.h, addr, n, K))
 
     def insert_fastq_chunk_raw(self, addr, n, K):
         self._check(self.L.shq_insert_fastq_chunk(self.h, addr, n, K))

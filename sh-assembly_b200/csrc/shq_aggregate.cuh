@@ -63,43 +63,51 @@ restart:
     if (threadIdx.x == 0) { s_ndist = 0; s_nocc = 0; s_nocc2 = 0; s_overflow = 0; s_na = 0; s_nb = 0; }
     __syncthreads();
     uint32_t my_occ = 0, my_occ2 = 0;
-    for (uint32_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
-      uint32_t w = packed[i];
-      uint32_t kl = w & lowmask, ch = lb >= 32 ? 0 : (w >> lb);
-      if (ch < chunk_lo || ch > chunk_hi) continue;
-      if (sub_bits && (kl >> (lb - sub_bits)) != r) continue;
-      bool second = SPLIT && ch > cstar;
-      if (second) my_occ2++; else my_occ++;
-      uint32_t h = agg_hash(kl);
-      bool placed = false;
-      for (int probe = 0; probe < kAggTable; probe++) {
-        uint32_t cur = t_key[h];
-        if (cur == kl) { placed = true; break; }
-        if (cur == kAggEmpty) {
-          if (*reinterpret_cast<volatile uint32_t*>(&s_overflow)) break;
-          uint32_t old = atomicCAS(&t_key[h], kAggEmpty, kl);
-          if (old == kAggEmpty) {
-            if (atomicAdd(&s_ndist, 1u) >= (uint32_t)kAggMaxDistinct) s_overflow = 1;
-            placed = true; break;
+    constexpr int U = 4;                               // loads of U strided words are issued before any is consumed
+    for (uint32_t i0 = beg + threadIdx.x; i0 < end; i0 += blockDim.x * U) {
+      uint32_t wv[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) { uint32_t i = i0 + u * blockDim.x; wv[u] = i < end ? __ldg(&packed[i]) : 0; }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (i0 + u * blockDim.x >= end) break;
+        uint32_t w = wv[u];
+        uint32_t kl = w & lowmask, ch = lb >= 32 ? 0 : (w >> lb);
+        if (ch < chunk_lo || ch > chunk_hi) continue;
+        if (sub_bits && (kl >> (lb - sub_bits)) != r) continue;
+        bool second = SPLIT && ch > cstar;
+        if (second) my_occ2++; else my_occ++;
+        uint32_t h = agg_hash(kl);
+        bool placed = false;
+        for (int probe = 0; probe < kAggTable; probe++) {
+          uint32_t cur = t_key[h];
+          if (cur == kl) { placed = true; break; }
+          if (cur == kAggEmpty) {
+            if (*reinterpret_cast<volatile uint32_t*>(&s_overflow)) break;
+            uint32_t old = atomicCAS(&t_key[h], kAggEmpty, kl);
+            if (old == kAggEmpty) {
+              if (atomicAdd(&s_ndist, 1u) >= (uint32_t)kAggMaxDistinct) s_overflow = 1;
+              placed = true; break;
+            }
+            if (old == kl) { placed = true; break; }
           }
-          if (old == kl) { placed = true; break; }
+          h = (h + 1) & (kAggTable - 1);
         }
-        h = (h + 1) & (kAggTable - 1);
-      }
-      if (placed) {
-        uint32_t old = atomicAdd(&t_cnt[h], second ? 0x10000u : 1u);
-        if (SPLIT) {
-          if ((second ? (old >> 16) : (old & 0xFFFFu)) >= 0xFFFEu) *o.split_overflow = 1;
-        }
-        if (want_chunk && !second) {  // 16-bit atomic min of the first chunk through the containing 32-bit word
-          unsigned int* wp = reinterpret_cast<unsigned int*>(t_chk) + (h >> 1);
-          unsigned int sh = (h & 1) * 16;
-          unsigned int oldw = *reinterpret_cast<volatile unsigned int*>(wp);
-          while (((oldw >> sh) & 0xFFFFu) > ch) {
-            unsigned int nw = (oldw & ~(0xFFFFu << sh)) | (ch << sh);
-            unsigned int prev = atomicCAS(wp, oldw, nw);
-            if (prev == oldw) break;
-            oldw = prev;
+        if (placed) {
+          uint32_t old = atomicAdd(&t_cnt[h], second ? 0x10000u : 1u);
+          if (SPLIT) {
+            if ((second ? (old >> 16) : (old & 0xFFFFu)) >= 0xFFFEu) *o.split_overflow = 1;
+          }
+          if (want_chunk && !second) {  // 16-bit atomic min of the first chunk through the containing 32-bit word
+            unsigned int* wp = reinterpret_cast<unsigned int*>(t_chk) + (h >> 1);
+            unsigned int sh = (h & 1) * 16;
+            unsigned int oldw = *reinterpret_cast<volatile unsigned int*>(wp);
+            while (((oldw >> sh) & 0xFFFFu) > ch) {
+              unsigned int nw = (oldw & ~(0xFFFFu << sh)) | (ch << sh);
+              unsigned int prev = atomicCAS(wp, oldw, nw);
+              if (prev == oldw) break;
+              oldw = prev;
+            }
           }
         }
       }

@@ -50,7 +50,14 @@ struct shq_handle_s {
   char* h_stage = nullptr; size_t h_stage_cap = 0, h_stage_fill = 0;
   std::vector<uint64_t> stage_chunk_ends;
   int stage_K = 0;
-  size_t max_batch_bytes = (size_t)1 << 30;
+  size_t max_batch_bytes = (size_t)1 << 28;
+
+  // pinned-source pipeline: copy stream + 3 rotating device text buffers
+  struct PinBatch { int buf; size_t bytes; std::vector<uint64_t> ends; int K; cudaEvent_t ev; };
+  cudaStream_t cstream = nullptr;
+  DevBuf pin_buf[3];
+  int pin_cur = 0; size_t pin_fill = 0; std::vector<uint64_t> pin_ends; int pin_K = 0;
+  std::vector<PinBatch> pin_queue;
 
   // scratch
   DevBuf d_text, d_nl_tiles, d_nl_pos, d_chunk_ends, d_chunk_line_end, d_chunk_keys, d_chunk_hist, d_slow;
@@ -197,7 +204,7 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
   const int G = kNumSMs * 2;
   const int W = g_scatter_w;
   size_t smem_count = sizeof(RollTables) + (size_t)n_bins * 4;
-  size_t smem_scatter = sizeof(RollTables) + (size_t)n_bins * 8 + (size_t)kRollThreads * W * 6;
+  size_t smem_scatter = sizeof(RollTables) + ((size_t)3 * n_bins + 1) * 4 + (size_t)kRollThreads * W * 10 + 16;
   size_t smem_keys = (size_t)n_bins * 8;
   Sink sk{};
   {
@@ -220,7 +227,7 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
     if (from_text) {
       if (W == 16) {
         SHQ_CUDA(cudaFuncSetAttribute(roll_scatter_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
-        roll_scatter_kernel<16><<<G, kRollThreads, smem_scatter, st>>>(hp, h->d_tot.as<uint32_t>(), h->d_packed.as<uint32_t>());
+        roll_scatter_kernel<16><<<kNumSMs * (smem_scatter <= 110 * 1024 ? 2 : 1), kRollThreads, smem_scatter, st>>>(hp, h->d_tot.as<uint32_t>(), h->d_packed.as<uint32_t>());
       } else {
         SHQ_CUDA(cudaFuncSetAttribute(roll_scatter_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
         roll_scatter_kernel<32><<<kNumSMs, kRollThreads, smem_scatter, st>>>(hp, h->d_tot.as<uint32_t>(), h->d_packed.as<uint32_t>());
@@ -538,7 +545,30 @@ size_t hash_to_keylist(shq_handle_s* h, const char* d_text, size_t n, int K, uin
   return (size_t)total;
 }
 
+void pin_process_oldest(shq_handle_s* h) {
+  shq_handle_s::PinBatch b = h->pin_queue.front();
+  h->pin_queue.erase(h->pin_queue.begin());
+  SHQ_CUDA(cudaStreamWaitEvent(h->stream, b.ev, 0));
+  SHQ_CUDA(cudaEventSynchronize(b.ev));
+  cudaEventDestroy(b.ev);
+  process_batch(h, h->pin_buf[b.buf].as<char>(), b.bytes, b.ends.data(), (int)b.ends.size(), b.K, nullptr, 0);
+}
+void pin_seal(shq_handle_s* h) {
+  if (h->pin_fill == 0) return;
+  shq_handle_s::PinBatch b;
+  b.buf = h->pin_cur; b.bytes = h->pin_fill; b.ends.swap(h->pin_ends); b.K = h->pin_K;
+  SHQ_CUDA(cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming));
+  SHQ_CUDA(cudaEventRecord(b.ev, h->cstream));
+  h->pin_queue.push_back(b);
+  h->pin_cur = (h->pin_cur + 1) % 3; h->pin_fill = 0; h->pin_ends.clear();
+}
+void pin_drain(shq_handle_s* h) {
+  pin_seal(h);
+  while (!h->pin_queue.empty()) pin_process_oldest(h);
+}
+
 void flush_stage(shq_handle_s* h) {
+  pin_drain(h);
   if (h->h_stage_fill == 0) { h->stage_chunk_ends.clear(); return; }
   size_t n = h->h_stage_fill;
   h->d_text.reserve(n + 64);
@@ -575,6 +605,7 @@ void init_handle(shq_handle_s* h, int qb, int hb, uint32_t seed, int device, int
   if (nshards < 1 || (nshards & (nshards - 1)) || shard < 0 || shard >= nshards || (1 << qb) < nshards * 64)
     SHQ_FAIL(SHQ_ERR_ARG, "bad shard %d of %d", shard, nshards);
   if (const char* e = getenv("SHQ_SCATTER_W")) { int v = atoi(e); if (v == 16 || v == 32) g_scatter_w = v; }
+  if (const char* e = getenv("SHQ_MAX_BATCH_MB")) { long v = atol(e); if (v >= 1 && v <= 3072) h->max_batch_bytes = (size_t)v << 20; }
   if (const char* e = getenv("SHQ_BIN_BITS")) { int v = atoi(e); if (v >= 4 && v <= 13) g_bin_bits = v; }
   SHQ_CUDA(cudaSetDevice(device));
   h->device = device; h->qb = qb; h->hb = hb; h->seed = seed; h->shard = shard; h->nshards = nshards;
@@ -601,6 +632,9 @@ void free_handle(shq_handle_s* h) {
                     &h->d_scan_scratch, &h->d_misc, &h->d_pairs, &h->d_pos, &h->d_flags, &h->d_keep, &h->d_q_in, &h->d_q_cnt, &h->d_q_was,
                     &h->d_tmp_keys2, &h->d_tmp_counts2, &h->d_run2_keys, &h->d_run2_counts};
   for (DevBuf* b : bufs) b->release();
+  for (auto& b : h->pin_buf) b.release();
+  for (auto& b : h->pin_queue) cudaEventDestroy(b.ev);
+  if (h->cstream) { cudaStreamSynchronize(h->cstream); cudaStreamDestroy(h->cstream); }
   if (h->d_err) cudaFree(h->d_err);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -668,6 +702,9 @@ int shq_reset(shq_t h) {
   h->image_valid = false; h->image_only = false;
   h->trigger = 0; h->rounds_left = 0; h->end_denoise = false; h->rounds_done = 0; h->finished = false;
   h->h_stage_fill = 0; h->stage_chunk_ends.clear();
+  for (auto& b : h->pin_queue) cudaEventDestroy(b.ev);
+  h->pin_queue.clear(); h->pin_fill = 0; h->pin_ends.clear();
+  if (h->cstream) cudaStreamSynchronize(h->cstream);
   return SHQ_OK;
 }
 
@@ -695,6 +732,34 @@ int shq_insert_fastq_chunk(shq_t h, const char* text, size_t n, int K) {
     h->h_stage_fill += a.n;
     h->stage_chunk_ends.push_back(h->h_stage_fill);
     h->stage_K = a.K;
+  SHQ_API_END
+}
+
+int shq_insert_fastq_pinned(shq_t h, const char* text, size_t n, int K) {
+  if (!h || (!text && n)) return SHQ_ERR_ARG;
+  if (n == 0) return SHQ_OK;
+  struct { const char* text; size_t n; int K; } args{text, n, K};
+  SHQ_API_BEGIN(h)
+    if (h->h_stage_fill) {            // keep chunk order if the staged path was used before
+      size_t nn = h->h_stage_fill;
+      h->d_text.reserve(nn + 64);
+      SHQ_CUDA(cudaMemcpyAsync(h->d_text.p, h->h_stage, nn, cudaMemcpyHostToDevice, h->stream));
+      std::vector<uint64_t> ends; ends.swap(h->stage_chunk_ends); h->h_stage_fill = 0;
+      process_batch(h, h->d_text.as<char>(), nn, ends.data(), (int)ends.size(), h->stage_K, nullptr, 0);
+    }
+    if (a.n >= ((size_t)1 << 31)) SHQ_FAIL(SHQ_ERR_ARG, "chunk too large");
+    if (!h->cstream) SHQ_CUDA(cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking));
+    size_t cap = std::max(h->max_batch_bytes, a.n);
+    if (h->pin_fill && (h->pin_K != a.K || h->pin_fill + a.n > cap)) {
+      pin_seal(h);
+      // keep one sealed batch in flight behind the one being processed: its copies overlap the compute
+      while (h->pin_queue.size() >= 2) pin_process_oldest(h);
+    }
+    h->pin_buf[h->pin_cur].reserve(cap + 64);
+    // 16-byte alignment of every batch start holds because each batch starts at offset 0 of its buffer
+    SHQ_CUDA(cudaMemcpyAsync(h->pin_buf[h->pin_cur].as<char>() + h->pin_fill, a.text, a.n, cudaMemcpyHostToDevice, h->cstream));
+    h->stats.h2d_bytes += a.n;
+    h->pin_fill += a.n; h->pin_ends.push_back(h->pin_fill); h->pin_K = a.K;
   SHQ_API_END
 }
 

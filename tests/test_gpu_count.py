@@ -144,3 +144,28 @@ def test_load_query_roundtrip(po, shq, tmp_path):
     g.save(path)
     assert open(path, "rb").read() == o.export()
     g.close()
+
+
+@pytest.mark.parametrize("batch_mb", ["1", "4"])
+def test_pinned_pipeline_matches_oracle(po, shq, batch_mb, monkeypatch):
+    """Zero-copy pinned path: several small device batches, copies overlapped with compute, schedule armed."""
+    import torch
+    monkeypatch.setenv("SHQ_MAX_BATCH_MB", batch_mb)
+    K, qb = 27, 22
+    files = [fastq(po, G=120000, cov=30, err=0.008, seed=61 + i, L=120) for i in range(2)]
+    part = 1 << 19
+    total_distinct = len(np.unique(np.concatenate([po.reads_to_keys(f, K, qb + 8) for f in files])))
+    trigger = total_distinct // 3
+    o, o_rounds = po.count_run(files, K, qb, qb + 8, trigger, 2, True, part_size=part)
+    g = shq.CQF(qb, qb + 8)
+    g.set_denoise_schedule(trigger, 2, True)
+    keep = []
+    for _, ch in po.chunks(files, part_size=part):
+        t = torch.frombuffer(bytearray(ch), dtype=torch.uint8).pin_memory()
+        keep.append(t)
+        g.insert_fastq_pinned_raw(t.data_ptr(), t.numel(), K)
+    g.finish()
+    assert g.rounds_done() == o_rounds
+    assert g.counts() == o.counts()
+    assert g.export() == o.export()
+    g.close()

@@ -312,8 +312,47 @@ def run_ours(args, rank, world, local_rank):
                     "d2h_bytes_per_step": int(st2["d2h_bytes"] // args.steps), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(stats["kernels_launched"]), "roofline": roofline,
             "result": {"ndistinct": int(ndistinct), "nelts": int(nelts), "denoise_rounds": int(rounds), "kmers_per_step": int(n_total)}}
+    if args.unitigs:
+        line["unitig"] = bench_unitigs(args, shq, q, text, ends, h_ptr)
     line["cpu_baseline"] = cpu_baseline(args, text, ends, p, n_total)
     print(json.dumps(line))
+
+
+def bench_unitigs(args, shq, q, text, ends, h_ptr):
+    """Second half of the BASELINE metric: seconds to build the unitig graph (Contiger) from the filter just
+    counted, reads given as host chunks; beside it the sequential CPU restatement on the same input (1 core)."""
+    import ctypes as C
+    L = shq.lib()
+    opts = shq.shq_unitig_opts(args.k, 2, 2, 1000000)
+    best = None
+    info = {}
+    for rep in range(2):
+        u = C.c_void_p()
+        t0 = time.perf_counter()
+        q._check(L.shq_unitigs_begin(q.h, C.byref(opts), C.byref(u)))
+        o = 0
+        for e in ends:
+            q._check(L.shq_unitigs_add_reads(u, h_ptr + o, int(e) - o))
+            o = int(e)
+        q._check(L.shq_unitigs_build(u))
+        dt = time.perf_counter() - t0
+        n, tot = C.c_size_t(), C.c_size_t()
+        L.shq_unitigs_count(u, C.byref(n), C.byref(tot))
+        L.shq_unitigs_free(u)
+        best = dt if best is None else min(best, dt)
+        info = {"n_unitigs": n.value, "total_bases": tot.value}
+    out = {"seconds": best, "unit": "s", "config": "Contiger -k %d -s 2 -x 2 -X 1000000 on the filter of this run, reads from pinned host chunks" % args.k}
+    out.update(info)
+    if args.unitig_cpu:
+        from oracle import pyoracle as po
+        img = q.export()
+        o = po.OracleCqf.from_bytes(img)
+        t0 = time.perf_counter()
+        fa, nq = po.contiger_run(o, [text.tobytes()], args.k)
+        out["cpu_baseline"] = {"seconds": time.perf_counter() - t0, "cores": 1, "kind": "port",
+                               "sample": "whole read set, sequential restatement of Contiger over a hash-map CQF model",
+                               "n_unitigs": len(po.parse_unitigs(fa)), "cqf_queries": int(nq)}
+    return out
 
 
 PHASE_KERNEL = {"ms_hash_count": "hash_reads_kernel<count>", "ms_scatter": "hash_reads_kernel<scatter>", "ms_aggregate": "bin_aggregate_kernel",
@@ -364,6 +403,8 @@ def main():
     ap.add_argument("--end-denoise", type=int, default=1)
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--unitigs", type=int, default=1, help="also time the Contiger device path (unitig build seconds)")
+    ap.add_argument("--unitig-cpu", type=int, default=0, help="also time the sequential CPU restatement of Contiger")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

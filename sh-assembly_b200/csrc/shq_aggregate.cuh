@@ -28,6 +28,67 @@ struct AggOut {
   int* split_overflow;      // SPLIT: set when a 16-bit half counter would overflow
 };
 
+// Streams the bin through the shared-memory table.  Compile-time flags strip everything a plain batch
+// does not need: FILT = chunk-range / key-sub-range filters, CHUNK = first-chunk minimum, SPLIT = two counters.
+template <bool SPLIT, bool CHUNK, bool FILT>
+__device__ __forceinline__ void agg_insert_pass(const uint32_t* __restrict__ packed, uint32_t beg, uint32_t end, int lb, uint32_t lowmask,
+                                                uint32_t chunk_lo, uint32_t chunk_hi, uint32_t cstar, int sub_bits, uint32_t r,
+                                                uint32_t* t_key, uint32_t* t_cnt, uint16_t* t_chk, uint32_t* s_ndist,
+                                                volatile uint32_t* s_overflow, int* split_overflow, uint32_t* occ1, uint32_t* occ2) {
+  uint32_t my_occ = 0, my_occ2 = 0;
+  constexpr int U = 4;                               // loads of U strided words are issued before any is consumed
+  for (uint32_t i0 = beg + threadIdx.x; i0 < end; i0 += blockDim.x * U) {
+    uint32_t wv[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) { uint32_t i = i0 + u * blockDim.x; wv[u] = i < end ? __ldg(&packed[i]) : 0; }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (i0 + u * blockDim.x >= end) break;
+      const uint32_t w = wv[u];
+      const uint32_t kl = w & lowmask;
+      uint32_t ch = 0;
+      if (CHUNK || FILT || SPLIT) ch = lb >= 32 ? 0 : (w >> lb);
+      if (FILT) {
+        if (ch < chunk_lo || ch > chunk_hi) continue;
+        if (sub_bits && (kl >> (lb - sub_bits)) != r) continue;
+      }
+      const bool second = SPLIT && ch > cstar;
+      if (FILT || SPLIT) { if (second) my_occ2++; else my_occ++; }
+      uint32_t h = agg_hash(kl);
+      for (;;) {
+        uint32_t cur = t_key[h];
+        if (cur == kl) break;
+        if (cur == kAggEmpty) {
+          if (*s_overflow) break;
+          uint32_t old = atomicCAS(&t_key[h], kAggEmpty, kl);
+          if (old == kAggEmpty) { if (atomicAdd(s_ndist, 1u) >= (uint32_t)kAggMaxDistinct) *s_overflow = 1; break; }
+          if (old == kl) break;
+        }
+        h = (h + 1) & (kAggTable - 1);
+      }
+      if (SPLIT) {
+        uint32_t old = atomicAdd(&t_cnt[h], second ? 0x10000u : 1u);
+        if ((second ? (old >> 16) : (old & 0xFFFFu)) >= 0xFFFEu) *split_overflow = 1;
+      } else {
+        atomicAdd(&t_cnt[h], 1u);
+      }
+      if (CHUNK && !second) {   // 16-bit atomic min of the first chunk through the containing 32-bit word
+        unsigned int* wp = reinterpret_cast<unsigned int*>(t_chk) + (h >> 1);
+        unsigned int sh = (h & 1) * 16;
+        unsigned int oldw = *reinterpret_cast<volatile unsigned int*>(wp);
+        while (((oldw >> sh) & 0xFFFFu) > ch) {
+          unsigned int nw = (oldw & ~(0xFFFFu << sh)) | (ch << sh);
+          unsigned int prev = atomicCAS(wp, oldw, nw);
+          if (prev == oldw) break;
+          oldw = prev;
+        }
+      }
+    }
+  }
+  if (FILT || SPLIT) { atomicAdd(occ1, my_occ); if (SPLIT) atomicAdd(occ2, my_occ2); }
+  else if (threadIdx.x == 0) atomicAdd(occ1, end - beg);
+}
+
 // One CTA per bin.  packed[bin_off[p] .. bin_off[p+1]) holds (key_low | chunk << lb).
 // Occurrences whose chunk is outside [chunk_lo, chunk_hi] are ignored.
 // SPLIT: occurrences with chunk <= cstar are counted in the low half of the counter, the others in the high
@@ -62,55 +123,16 @@ restart:
     for (int i = threadIdx.x; i < kAggBuckets; i += blockDim.x) s_bkt[i] = 0;
     if (threadIdx.x == 0) { s_ndist = 0; s_nocc = 0; s_nocc2 = 0; s_overflow = 0; s_na = 0; s_nb = 0; }
     __syncthreads();
-    uint32_t my_occ = 0, my_occ2 = 0;
-    constexpr int U = 4;                               // loads of U strided words are issued before any is consumed
-    for (uint32_t i0 = beg + threadIdx.x; i0 < end; i0 += blockDim.x * U) {
-      uint32_t wv[U];
-#pragma unroll
-      for (int u = 0; u < U; u++) { uint32_t i = i0 + u * blockDim.x; wv[u] = i < end ? __ldg(&packed[i]) : 0; }
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        if (i0 + u * blockDim.x >= end) break;
-        uint32_t w = wv[u];
-        uint32_t kl = w & lowmask, ch = lb >= 32 ? 0 : (w >> lb);
-        if (ch < chunk_lo || ch > chunk_hi) continue;
-        if (sub_bits && (kl >> (lb - sub_bits)) != r) continue;
-        bool second = SPLIT && ch > cstar;
-        if (second) my_occ2++; else my_occ++;
-        uint32_t h = agg_hash(kl);
-        bool placed = false;
-        for (int probe = 0; probe < kAggTable; probe++) {
-          uint32_t cur = t_key[h];
-          if (cur == kl) { placed = true; break; }
-          if (cur == kAggEmpty) {
-            if (*reinterpret_cast<volatile uint32_t*>(&s_overflow)) break;
-            uint32_t old = atomicCAS(&t_key[h], kAggEmpty, kl);
-            if (old == kAggEmpty) {
-              if (atomicAdd(&s_ndist, 1u) >= (uint32_t)kAggMaxDistinct) s_overflow = 1;
-              placed = true; break;
-            }
-            if (old == kl) { placed = true; break; }
-          }
-          h = (h + 1) & (kAggTable - 1);
-        }
-        if (placed) {
-          uint32_t old = atomicAdd(&t_cnt[h], second ? 0x10000u : 1u);
-          if (SPLIT) {
-            if ((second ? (old >> 16) : (old & 0xFFFFu)) >= 0xFFFEu) *o.split_overflow = 1;
-          }
-          if (want_chunk && !second) {  // 16-bit atomic min of the first chunk through the containing 32-bit word
-            unsigned int* wp = reinterpret_cast<unsigned int*>(t_chk) + (h >> 1);
-            unsigned int sh = (h & 1) * 16;
-            unsigned int oldw = *reinterpret_cast<volatile unsigned int*>(wp);
-            while (((oldw >> sh) & 0xFFFFu) > ch) {
-              unsigned int nw = (oldw & ~(0xFFFFu << sh)) | (ch << sh);
-              unsigned int prev = atomicCAS(wp, oldw, nw);
-              if (prev == oldw) break;
-              oldw = prev;
-            }
-          }
-        }
-      }
+    {
+      const uint32_t max_chunk = lb >= 32 ? 0u : (0xFFFFFFFFu >> lb);
+      const bool filt = sub_bits != 0 || chunk_lo != 0 || chunk_hi < max_chunk;
+      volatile uint32_t* ovf = &s_overflow;
+#define SHQ_AGG_CALL(S, C, F) agg_insert_pass<S, C, F>(packed, beg, end, lb, lowmask, chunk_lo, chunk_hi, cstar, sub_bits, r, t_key, t_cnt, t_chk, \
+                                                       &s_ndist, ovf, o.split_overflow, &s_nocc, &s_nocc2)
+      if (SPLIT) { if (filt) SHQ_AGG_CALL(SPLIT, true, true); else SHQ_AGG_CALL(SPLIT, true, false); }
+      else if (want_chunk) { if (filt) SHQ_AGG_CALL(false, true, true); else SHQ_AGG_CALL(false, true, false); }
+      else { if (filt) SHQ_AGG_CALL(false, false, true); else SHQ_AGG_CALL(false, false, false); }
+#undef SHQ_AGG_CALL
     }
     __syncthreads();
     if (*reinterpret_cast<volatile uint32_t*>(&s_overflow)) { sub_bits++; __syncthreads(); goto restart; }
@@ -197,8 +219,6 @@ restart:
         __syncthreads();
       }
     }
-    atomicAdd(&s_nocc, my_occ);
-    if (SPLIT) atomicAdd(&s_nocc2, my_occ2);
     __syncthreads();
     if (do_hist) for (int i = threadIdx.x; i < kAggBuckets; i += blockDim.x) { uint32_t v = s_bkt[i]; if (v) atomicAdd(&o.first_hist[i], v); }
     if (!SPLIT) written += nd; else { written += s_na; written2 += s_nb; }

@@ -29,80 +29,83 @@ __device__ __forceinline__ void roll_tables_init(RollTables* t, int K) {
   }
 }
 
-// Sequential byte reader over global text using aligned 32-bit loads.
-struct ByteStream {
-  const uint32_t* wp; uint32_t w; int left;   // bytes left in w
-  __device__ __forceinline__ void init(const char* text, uint32_t pos) {
-    uintptr_t a = reinterpret_cast<uintptr_t>(text) + pos;
-    wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-    int skip = (int)(a & 3);
-    w = __ldg(wp) >> (8 * skip);
-    left = 4 - skip;
-  }
-  __device__ __forceinline__ unsigned char next() {
-    if (left == 0) { wp++; w = __ldg(wp); left = 4; }
-    unsigned char c = (unsigned char)(w & 0xFF);
-    w >>= 8; left--;
-    return c;
-  }
-};
+// Four consecutive text bytes starting at an arbitrary address, from two aligned 32-bit loads.
+__device__ __forceinline__ uint32_t load4(const char* p) {
+  uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  uint32_t sh = (uint32_t)(a & 3) * 8;
+  uint32_t w0 = __ldg(wp);
+  if (sh == 0) return w0;
+  return __funnelshift_r(w0, __ldg(wp + 1), sh);
+}
 
 // Per-thread generator of the key stream of one read after another (reads first, first+stride, ...).
+// step() advances by one unit -- open+prime a read (1 key), a group of 4 windows (4 keys), or a single
+// window near the end of a read / around an 'N' (<= 1 key) -- and hands every key to emit(key, chunk).
 struct Roller {
   const HashParams* hp; const RollTables* tab;
   uint32_t read, read_end, stride;
   uint32_t s, len, pos;        // current read: start offset, length, index of the NEXT char to roll in
   uint64_t fh, rh; uint32_t chunk;
-  ByteStream in, out;
   bool active;                 // a read is open and primed (fh/rh valid for the window ending at pos-1)
 
   __device__ __forceinline__ void start(const HashParams* hp_, const RollTables* tab_, uint32_t first, uint32_t end, uint32_t stride_) {
     hp = hp_; tab = tab_; read = first; read_end = end; stride = stride_; active = false;
   }
-  // prime at sub-read start s0 (absolute index in the read); returns false if fewer than K chars remain
+  // prime at sub-read start s0; false if fewer than K chars remain (cqf/CQF_mt.h:624-625)
   __device__ __forceinline__ bool prime(uint32_t s0) {
     const uint32_t K = hp->K;
     if (s0 > len || len - s0 < K) return false;
-    in.init(hp->text, s + s0);
-    out.init(hp->text, s + s0);
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(hp->text) + s + s0;
     uint64_t f = 0, r = 0;
     for (uint32_t i = 0; i < K; i++) {
-      unsigned char c = in.next();
+      unsigned char c = __ldg(p + i);
       f = rotl64(f, 1) ^ tab->in_f[c];                 // == xor of rol(seed, K-1-i)
-      r ^= rotl64(nt_seed_rev(c), i);
+      r ^= rotr64(tab->in_r[c], K - 1 - i);            // in_r = rol(seed', K-1)  ->  rol(seed', i)
     }
     fh = f; rh = r; pos = s0 + K;
     return true;
   }
-  // next key of the stream; false when this thread has no reads left
-  __device__ __forceinline__ bool next(uint64_t* key, uint32_t* ch) {
-    const uint64_t mask = hp->hb >= 64 ? ~0ULL : ((1ULL << hp->hb) - 1);
-    for (;;) {
-      if (!active) {
-        if (read >= read_end) return false;
-        s = hp->nl_pos[4 * (size_t)read] + 1;
-        len = hp->nl_pos[4 * (size_t)read + 1] - s;
-        chunk = chunk_of_line(*hp, 4 * read + 1);
-        read += stride;
-        if (!prime(0)) continue;
-        active = true;
-        *key = (fh < rh ? fh : rh) & mask; *ch = chunk;
-        return true;
-      }
-      if (pos >= len) { active = false; continue; }
-      unsigned char cin = in.next();
-      if (cin == 'N') {                                 // restart after the N (CQF_mt.h:680-683)
-        if (!prime(pos + 1)) { active = false; continue; }
-        *key = (fh < rh ? fh : rh) & mask; *ch = chunk;
-        return true;
-      }
-      unsigned char cout = out.next();
-      fh = rotl64(fh, 1) ^ tab->out_f[cout] ^ tab->in_f[cin];
-      rh = rotr64(rh, 1) ^ tab->out_r[cout] ^ tab->in_r[cin];
-      pos++;
-      *key = (fh < rh ? fh : rh) & mask; *ch = chunk;
+  __device__ __forceinline__ void roll(unsigned char cout, unsigned char cin) {   // base/nthash.hpp:305-309
+    fh = rotl64(fh, 1) ^ tab->out_f[cout] ^ tab->in_f[cin];
+    rh = rotr64(rh, 1) ^ tab->out_r[cout] ^ tab->in_r[cin];
+  }
+  // returns false when this thread has no reads left; never emits more than 4 keys per call
+  template <class Emit>
+  __device__ __forceinline__ bool step(const uint64_t mask, Emit&& emit) {
+    if (!active) {
+      if (read >= read_end) return false;
+      s = hp->nl_pos[4 * (size_t)read] + 1;
+      len = hp->nl_pos[4 * (size_t)read + 1] - s;
+      chunk = chunk_of_line(*hp, 4 * read + 1);
+      read += stride;
+      if (prime(0)) { active = true; emit((fh < rh ? fh : rh) & mask, chunk); }
       return true;
     }
+    if (pos >= len) { active = false; return true; }
+    const char* base = hp->text + s;
+    if (len - pos >= 4) {
+      uint32_t vin = load4(base + pos);
+      if (__vcmpeq4(vin, 0x4E4E4E4Eu) == 0) {            // no 'N' among the next four characters
+        uint32_t vout = load4(base + pos - hp->K);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          roll((unsigned char)(vout >> (8 * j)), (unsigned char)(vin >> (8 * j)));
+          emit((fh < rh ? fh : rh) & mask, chunk);
+        }
+        pos += 4;
+        return true;
+      }
+    }
+    unsigned char cin = __ldg(reinterpret_cast<const unsigned char*>(base) + pos);
+    if (cin == 'N') {                                     // restart after the N (CQF_mt.h:680-683)
+      if (prime(pos + 1)) emit((fh < rh ? fh : rh) & mask, chunk); else active = false;
+      return true;
+    }
+    roll(__ldg(reinterpret_cast<const unsigned char*>(base) + pos - hp->K), cin);
+    pos++;
+    emit((fh < rh ? fh : rh) & mask, chunk);
+    return true;
   }
 };
 
@@ -121,16 +124,22 @@ __global__ void __launch_bounds__(kRollThreads) roll_count_kernel(HashParams hp,
   uint32_t r1 = (uint32_t)(((uint64_t)hp.n_reads * (blockIdx.x + 1)) / gridDim.x);
   Roller R;
   R.start(&hp, tab, r0 + threadIdx.x, r1, blockDim.x);
-  uint64_t key; uint32_t ch; uint32_t last_chunk = 0xFFFFFFFFu, run = 0;
-  while (R.next(&key, &ch)) {
-    if (hp.chunk_keys) {
-      if (ch != last_chunk) { if (run) atomicAdd(&hp.chunk_keys[last_chunk], run); last_chunk = ch; run = 0; }
+  const uint64_t mask = hp.hb >= 64 ? ~0ULL : ((1ULL << hp.hb) - 1);
+  const uint64_t key_lo = hp.key_lo, key_hi = hp.key_hi; const int lb = hp.lb;
+  const bool whole = key_lo == 0 && key_hi > mask;      // unsharded: every key is ours
+  uint32_t last_chunk = 0xFFFFFFFFu, run = 0;
+  uint32_t* chunk_keys = hp.chunk_keys;
+  auto emit = [&](uint64_t key, uint32_t ch) {
+    if (chunk_keys) {
+      if (ch != last_chunk) { if (run) atomicAdd(&chunk_keys[last_chunk], run); last_chunk = ch; run = 0; }
       run++;
     }
-    if (key < hp.key_lo || key >= hp.key_hi) continue;
-    atomicAdd(&s_hist[(uint32_t)((key - hp.key_lo) >> hp.lb)], 1u);
-  }
-  if (hp.chunk_keys && run) atomicAdd(&hp.chunk_keys[last_chunk], run);
+    if (whole) { atomicAdd(&s_hist[(uint32_t)(key >> lb)], 1u); return; }
+    if (key < key_lo || key >= key_hi) return;
+    atomicAdd(&s_hist[(uint32_t)((key - key_lo) >> lb)], 1u);
+  };
+  while (R.step(mask, emit)) {}
+  if (chunk_keys && run) atomicAdd(&chunk_keys[last_chunk], run);
   __syncthreads();
   for (int i = threadIdx.x; i < hp.n_bins; i += blockDim.x) { uint32_t v = s_hist[i]; if (v) atomicAdd(&g_hist[i], v); }
 }
@@ -157,26 +166,29 @@ __global__ void __launch_bounds__(kRollThreads) roll_scatter_kernel(HashParams h
   __syncthreads();
   Roller R;
   R.start(&hp, tab, r0 + threadIdx.x, r1, blockDim.x);
-  const uint32_t lowmask = hp.lb >= 32 ? 0xFFFFFFFFu : ((1u << hp.lb) - 1);
+  const uint64_t mask = hp.hb >= 64 ? ~0ULL : ((1ULL << hp.hb) - 1);
+  const uint64_t key_lo = hp.key_lo, key_hi = hp.key_hi; const int lb = hp.lb;
+  const bool whole = key_lo == 0 && key_hi > mask;
+  const uint32_t lowmask = lb >= 32 ? 0xFFFFFFFFu : ((1u << lb) - 1);
   const int per = (hp.n_bins + kRollThreads - 1) / kRollThreads;      // bins per thread in the scan
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   bool more = true;
+  int produced = 0;
+  auto emit = [&](uint64_t key, uint32_t ch) {
+    if (!whole && (key < key_lo || key >= key_hi)) return;
+    uint64_t rel = key - key_lo;
+    uint32_t bin = (uint32_t)(rel >> lb);
+    int idx = produced * kRollThreads + threadIdx.x;
+    s_key[idx] = ((uint32_t)rel & lowmask) | (lb >= 32 ? 0 : (ch << lb));
+    s_bin[idx] = (uint16_t)bin;
+    atomicAdd(&s_hist[bin], 1u);
+    produced++;
+  };
   for (;;) {
     for (int i = threadIdx.x; i < hp.n_bins; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
-    int produced = 0;
-    while (more && produced < W) {
-      uint64_t key; uint32_t ch;
-      if (!R.next(&key, &ch)) { more = false; break; }
-      if (key < hp.key_lo || key >= hp.key_hi) continue;
-      uint64_t rel = key - hp.key_lo;
-      uint32_t bin = (uint32_t)(rel >> hp.lb);
-      int idx = produced * kRollThreads + threadIdx.x;
-      s_key[idx] = ((uint32_t)rel & lowmask) | (hp.lb >= 32 ? 0 : (ch << hp.lb));
-      s_bin[idx] = (uint16_t)bin;
-      atomicAdd(&s_hist[bin], 1u);
-      produced++;
-    }
+    produced = 0;
+    while (more && produced + 4 <= W) more = R.step(mask, emit);
     for (int j = produced; j < W; j++) s_bin[j * kRollThreads + threadIdx.x] = 0xFFFF;
     int any = __syncthreads_or(produced > 0);
     if (!any) break;
@@ -233,8 +245,9 @@ __global__ void __launch_bounds__(256) roll_keys_kernel(HashParams hp, const uin
   uint64_t o = off[r], e = off[r + 1];
   Roller R;
   R.start(&hp, &tab, r, r + 1, 1);
-  uint64_t key; uint32_t ch;
-  while (o < e && R.next(&key, &ch)) out[o++] = key;
+  const uint64_t mask = hp.hb >= 64 ? ~0ULL : ((1ULL << hp.hb) - 1);
+  auto emit = [&](uint64_t key, uint32_t) { if (o < e) out[o++] = key; };
+  while (R.step(mask, emit)) {}
   while (o < e) out[o++] = kNoKey;
 }
 

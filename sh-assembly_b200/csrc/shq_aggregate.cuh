@@ -11,14 +11,14 @@
 namespace shq {
 
 // ----------------------------------------------------- per-bin aggregation ---
-constexpr int kAggThreads = 1024;
-constexpr int kAggTable = 16384;         // open-addressing slots per CTA
-constexpr int kAggMaxDistinct = 8192;    // per round (load factor <= 0.5)
+constexpr int kAggThreads = 512;
+constexpr int kAggTable = 8192;          // open-addressing slots per CTA (two CTAs per SM)
+constexpr int kAggMaxDistinct = 4096;    // per round (load factor <= 0.5)
 constexpr int kAggBuckets = 4096;        // bucket sort of the distinct keys
 constexpr uint32_t kAggEmpty = 0xFFFFFFFFu;
 constexpr size_t kAggSmemBytes = (size_t)kAggTable * (4 + 4 + 2) + (size_t)kAggMaxDistinct * 4 + (size_t)kAggBuckets * 4;
 
-__device__ __forceinline__ uint32_t agg_hash(uint32_t k) { return (k * 2654435761u) >> (32 - 14); }
+__device__ __forceinline__ uint32_t agg_hash(uint32_t k) { return (k * 2654435761u) >> (32 - 13); }
 
 struct AggOut {
   uint64_t* keys; uint32_t* counts; uint16_t* chunk; uint32_t* n_out;   // run A (or the only run)
@@ -26,6 +26,8 @@ struct AggOut {
   uint32_t* occ_out; uint32_t* occ_out2;
   uint32_t* first_hist;     // optional: histogram over first-chunk ids of the distinct keys (state empty => all new)
   int* split_overflow;      // SPLIT: set when a 16-bit half counter would overflow
+  int fixed_bits;           // each bin is handled by 2^fixed_bits CTAs, one per key sub-range
+  size_t sub_stride;        // outputs of sub-range s live at [s * sub_stride + bin_off[p] + i]
 };
 
 // Streams the bin through the shared-memory table.  Compile-time flags strip everything a plain batch
@@ -107,25 +109,26 @@ __global__ void __launch_bounds__(kAggThreads) bin_aggregate_kernel(
   uint16_t* t_chk = reinterpret_cast<uint16_t*>(s_bkt + kAggBuckets);
   __shared__ uint32_t s_ndist, s_nocc, s_nocc2, s_overflow, s_na, s_nb;
 
-  const uint32_t p = blockIdx.x;
+  const uint32_t p = blockIdx.x >> o.fixed_bits;
+  const uint32_t fsub = blockIdx.x & ((1u << o.fixed_bits) - 1);
   const uint32_t beg = bin_off[p], end = bin_off[p + 1];
+  const size_t obase = (size_t)fsub * o.sub_stride + beg;
   const uint32_t lowmask = lb >= 32 ? 0xFFFFFFFFu : ((1u << lb) - 1);
   const bool want_chunk = o.chunk != nullptr || o.first_hist != nullptr;
   uint32_t written = 0, written2 = 0, occ_total = 0, occ_total2 = 0;
-  int sub_bits = 0;
-  // expected duplication is high for sequencing data; start with one round unless the bin is huge
+  int sub_bits = o.fixed_bits;   // key_low bits fixed per round: fixed_bits chosen by the grid, the rest by overflow restarts
   while (sub_bits < lb && ((end - beg) >> sub_bits) > 64u * kAggMaxDistinct) sub_bits++;
 
 restart:
   written = 0; written2 = 0; occ_total = 0; occ_total2 = 0;
-  for (uint32_t r = 0; r < (1u << sub_bits); r++) {
+  for (uint32_t r = fsub << (sub_bits - o.fixed_bits); r < ((fsub + 1) << (sub_bits - o.fixed_bits)); r++) {
     for (int i = threadIdx.x; i < kAggTable; i += blockDim.x) { t_key[i] = kAggEmpty; t_cnt[i] = 0; t_chk[i] = 0xFFFF; }
     for (int i = threadIdx.x; i < kAggBuckets; i += blockDim.x) s_bkt[i] = 0;
     if (threadIdx.x == 0) { s_ndist = 0; s_nocc = 0; s_nocc2 = 0; s_overflow = 0; s_na = 0; s_nb = 0; }
     __syncthreads();
     {
       const uint32_t max_chunk = lb >= 32 ? 0u : (0xFFFFFFFFu >> lb);
-      const bool filt = sub_bits != 0 || chunk_lo != 0 || chunk_hi < max_chunk;
+      const bool filt = sub_bits != 0 || chunk_lo != 0 || chunk_hi < max_chunk;   // sub_bits includes the grid's fixed bits
       volatile uint32_t* ovf = &s_overflow;
 #define SHQ_AGG_CALL(S, C, F) agg_insert_pass<S, C, F>(packed, beg, end, lb, lowmask, chunk_lo, chunk_hi, cstar, sub_bits, r, t_key, t_cnt, t_chk, \
                                                        &s_ndist, ovf, o.split_overflow, &s_nocc, &s_nocc2)
@@ -145,14 +148,15 @@ restart:
       if (k != kAggEmpty) atomicAdd(&s_bkt[(k & relmask) >> bshift], 1u);
     }
     __syncthreads();
+    constexpr int PER = kAggBuckets / kAggThreads;
     {
-      uint32_t v[4], sum = 0;
+      uint32_t v[PER], sum = 0;
 #pragma unroll
-      for (int j = 0; j < 4; j++) { v[j] = s_bkt[threadIdx.x * 4 + j]; sum += v[j]; }
+      for (int j = 0; j < PER; j++) { v[j] = s_bkt[threadIdx.x * PER + j]; sum += v[j]; }
       uint32_t tot;
       uint32_t ex = block_exclusive_scan<SumU32>(sum, &tot);
 #pragma unroll
-      for (int j = 0; j < 4; j++) { s_bkt[threadIdx.x * 4 + j] = ex; ex += v[j]; }
+      for (int j = 0; j < PER; j++) { s_bkt[threadIdx.x * PER + j] = ex; ex += v[j]; }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < kAggTable; i += blockDim.x) {
@@ -162,8 +166,8 @@ restart:
     __syncthreads();
     const uint32_t nd = s_ndist;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {                      // s_bkt[b] is now the END of bucket b
-      int b = threadIdx.x * 4 + j;
+    for (int j = 0; j < PER; j++) {                    // s_bkt[b] is now the END of bucket b
+      int b = threadIdx.x * PER + j;
       uint32_t lo = b ? s_bkt[b - 1] : 0, hi = s_bkt[b];
       for (uint32_t x = lo + 1; x < hi; x++) {
         uint32_t kx = s_sort[x]; uint32_t y = x;
@@ -185,7 +189,7 @@ restart:
       uint32_t c = t_cnt[h];
       uint64_t key = key_lo + (((uint64_t)p << lb) | kl);
       if (!SPLIT) {
-        size_t oo = (size_t)beg + written + i;
+        size_t oo = obase + written + i;
         o.keys[oo] = key; o.counts[oo] = c;
         if (o.chunk) o.chunk[oo] = t_chk[h];
         if (do_hist) atomicAdd(&s_bkt[t_chk[h] & (kAggBuckets - 1)], 1u);
@@ -213,8 +217,8 @@ restart:
         uint32_t ba = s_na, bb = s_nb;
         __syncthreads();
         uint64_t key = key_lo + (((uint64_t)p << lb) | kl);
-        if (fa) { size_t oo = (size_t)beg + written + ba + ra; o.keys[oo] = key; o.counts[oo] = c & 0xFFFFu; if (o.chunk) o.chunk[oo] = t_chk[h]; }
-        if (fb) { size_t oo = (size_t)beg + written2 + bb + rb; o.keys2[oo] = key; o.counts2[oo] = c >> 16; }
+        if (fa) { size_t oo = obase + written + ba + ra; o.keys[oo] = key; o.counts[oo] = c & 0xFFFFu; if (o.chunk) o.chunk[oo] = t_chk[h]; }
+        if (fb) { size_t oo = obase + written2 + bb + rb; o.keys2[oo] = key; o.counts2[oo] = c >> 16; }
         if (threadIdx.x == 0) { s_na = ba + ta; s_nb = bb + tb; }
         __syncthreads();
       }
@@ -226,20 +230,21 @@ restart:
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    o.n_out[p] = written; o.occ_out[p] = occ_total;
-    if (SPLIT) { o.n_out2[p] = written2; o.occ_out2[p] = occ_total2; }
+    o.n_out[blockIdx.x] = written; o.occ_out[blockIdx.x] = occ_total;
+    if (SPLIT) { o.n_out2[blockIdx.x] = written2; o.occ_out2[blockIdx.x] = occ_total2; }
   }
 }
 
-// Dense gather: bin p's n_out[p] entries move from [bin_off[p], ...) to [dense_off[p], ...).
+// Dense gather: the n_out[g] entries of (bin, sub-range) g = p * 2^fixed_bits + s move from
+// [s * sub_stride + bin_off[p], ...) to [dense_off[g], ...).
 __global__ void __launch_bounds__(256) compact_bins_kernel(const uint32_t* __restrict__ bin_off, const uint32_t* __restrict__ dense_off,
-                                                          const uint32_t* __restrict__ n_out, const uint64_t* __restrict__ in_keys,
-                                                          const uint32_t* __restrict__ in_counts, const uint16_t* __restrict__ in_chunk,
-                                                          uint64_t* __restrict__ out_keys, uint32_t* __restrict__ out_counts,
-                                                          uint16_t* __restrict__ out_chunk) {
-  uint32_t p = blockIdx.x;
-  uint32_t n = n_out[p];
-  size_t src = bin_off[p], dst = dense_off[p];
+                                                          const uint32_t* __restrict__ n_out, int fixed_bits, size_t sub_stride,
+                                                          const uint64_t* __restrict__ in_keys, const uint32_t* __restrict__ in_counts,
+                                                          const uint16_t* __restrict__ in_chunk, uint64_t* __restrict__ out_keys,
+                                                          uint32_t* __restrict__ out_counts, uint16_t* __restrict__ out_chunk) {
+  uint32_t g = blockIdx.x, p = g >> fixed_bits, sub = g & ((1u << fixed_bits) - 1);
+  uint32_t n = n_out[g];
+  size_t src = (size_t)sub * sub_stride + bin_off[p], dst = dense_off[g];
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
     out_keys[dst + i] = in_keys[src + i];
     out_counts[dst + i] = in_counts[src + i];

@@ -254,10 +254,13 @@ bool aggregate_bins(shq_handle_s* h, const BatchBins& bb, uint32_t clo, uint32_t
   uint64_t& L = h->stats.kernels_launched;
   Phase ph(h, &h->stats.ms_aggregate);
   size_t cap = (size_t)bb.n_keys + 4;
-  h->d_tmp_keys.reserve(cap * 8); h->d_tmp_counts.reserve(cap * 4);
-  if (bb.armed) h->d_tmp_chunk.reserve(cap * 2);
-  if (split) { h->d_tmp_keys2.reserve(cap * 8); h->d_tmp_counts2.reserve(cap * 4); }
-  const size_t nb = (size_t)bb.n_bins;
+  int fixed_bits = 0;               // CTAs per bin: keep each CTA's share of the bin's distinct keys inside its table
+  { uint64_t avg = bb.n_keys / (uint64_t)bb.n_bins; while (fixed_bits < 4 && fixed_bits < bb.lb && (avg >> fixed_bits) > 28000) fixed_bits++; }
+  const size_t S = (size_t)1 << fixed_bits;
+  h->d_tmp_keys.reserve(cap * 8 * S); h->d_tmp_counts.reserve(cap * 4 * S);
+  if (bb.armed) h->d_tmp_chunk.reserve(cap * 2 * S);
+  if (split) { h->d_tmp_keys2.reserve(cap * 8 * S); h->d_tmp_counts2.reserve(cap * 4 * S); }
+  const size_t nb = (size_t)bb.n_bins * S;          // (bin, sub-range) groups
   h->d_nout.reserve((nb + 1) * 4 * 4);           // n_out, n_out2, occ, occ2
   uint32_t* n_out = h->d_nout.as<uint32_t>(); uint32_t* n_out2 = n_out + nb + 1; uint32_t* occ = n_out2 + nb + 1; uint32_t* occ2 = occ + nb + 1;
   h->d_dense_off.reserve((nb + 2) * 4 * 2);
@@ -276,13 +279,14 @@ bool aggregate_bins(shq_handle_s* h, const BatchBins& bb, uint32_t clo, uint32_t
   o.keys = h->d_tmp_keys.as<uint64_t>(); o.counts = h->d_tmp_counts.as<uint32_t>(); o.chunk = bb.armed ? h->d_tmp_chunk.as<uint16_t>() : nullptr;
   o.n_out = n_out; o.keys2 = split ? h->d_tmp_keys2.as<uint64_t>() : nullptr; o.counts2 = split ? h->d_tmp_counts2.as<uint32_t>() : nullptr;
   o.n_out2 = n_out2; o.occ_out = occ; o.occ_out2 = occ2; o.first_hist = d_fh; o.split_overflow = d_ovf;
+  o.fixed_bits = fixed_bits; o.sub_stride = cap;
   if (split) {
     SHQ_CUDA(cudaFuncSetAttribute(bin_aggregate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggSmemBytes));
-    bin_aggregate_kernel<true><<<bb.n_bins, kAggThreads, kAggSmemBytes, st>>>(h->d_packed.as<uint32_t>(), h->d_binoff.as<uint32_t>(), bb.lb, h->key_lo,
+    bin_aggregate_kernel<true><<<(unsigned)nb, kAggThreads, kAggSmemBytes, st>>>(h->d_packed.as<uint32_t>(), h->d_binoff.as<uint32_t>(), bb.lb, h->key_lo,
                                                                              clo, chi, cstar, o);
   } else {
     SHQ_CUDA(cudaFuncSetAttribute(bin_aggregate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggSmemBytes));
-    bin_aggregate_kernel<false><<<bb.n_bins, kAggThreads, kAggSmemBytes, st>>>(h->d_packed.as<uint32_t>(), h->d_binoff.as<uint32_t>(), bb.lb, h->key_lo,
+    bin_aggregate_kernel<false><<<(unsigned)nb, kAggThreads, kAggSmemBytes, st>>>(h->d_packed.as<uint32_t>(), h->d_binoff.as<uint32_t>(), bb.lb, h->key_lo,
                                                                               clo, chi, cstar, o);
   }
   L++;
@@ -295,7 +299,7 @@ bool aggregate_bins(shq_handle_s* h, const BatchBins& bb, uint32_t clo, uint32_t
     uint32_t oc = read_scalar(h, h->d_misc.as<uint32_t>());
     R->keys->reserve((size_t)(nd + 4) * 8); R->counts->reserve((size_t)(nd + 4) * 4);
     if (tch) R->chunk->reserve((size_t)(nd + 4) * 2);
-    compact_bins_kernel<<<bb.n_bins, 256, 0, st>>>(h->d_binoff.as<uint32_t>(), dense, nout, tk, tc, tch, R->keys->as<uint64_t>(),
+    compact_bins_kernel<<<(unsigned)nb, 256, 0, st>>>(h->d_binoff.as<uint32_t>(), dense, nout, fixed_bits, cap, tk, tc, tch, R->keys->as<uint64_t>(),
                                                   R->counts->as<uint32_t>(), tch ? R->chunk->as<uint16_t>() : nullptr); L++;
     R->n = nd; R->occ = oc;
   };

@@ -272,7 +272,7 @@ __device__ __forceinline__ void oriented_kmer(const NodeTable& T, uint32_t oid, 
 
 // processes list[begin, end): both orientations of each node.  New (false-positive) neighbours are
 // inserted and will be processed by the next round.
-__global__ void link_nodes_kernel(NodeTable T, ImageView im, LinkArrays L, int K, int hb, uint32_t s_min, uint32_t begin, uint32_t end) {
+__global__ void link_nodes_kernel(NodeTable T, ImageView im, LinkArrays L, VictimList V, int K, int hb, uint32_t s_min, uint32_t begin, uint32_t end) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t idx = begin + (t >> 1);
   if (idx >= end) return;
@@ -287,7 +287,8 @@ __global__ void link_nodes_kernel(NodeTable T, ImageView im, LinkArrays L, int K
     uint64_t nfh, nrh;
     nthash_roll(fh, rh, out, x, K, &nfh, &nrh);
     uint64_t key = (nfh < nrh ? nfh : nrh) & mask;
-    uint64_t cnt = img_lookup(im, key, nullptr);
+    uint64_t cslot = 0;
+    uint64_t cnt = img_lookup(im, key, &cslot);
     if (cnt < s_min) continue;
     Kmer n = kmer_push_right(k, x, km);
     Kmer rc = kmer_rc(n, K);
@@ -296,6 +297,10 @@ __global__ void link_nodes_kernel(NodeTable T, ImageView im, LinkArrays L, int K
     uint32_t slot = node_insert(T, fwd_canon ? n : rc, (uint32_t)(cnt > 0xFFFFFFFFull ? 0xFFFFFFFFull : cnt), fwd_canon ? nfh : nrh,
                                 fwd_canon ? nrh : nfh, &fresh);
     if (slot == kNil) return;
+    if (fresh) {   // a k-mer no read contains: it shares its key with the entry's first visitor (seed blocking rule)
+      uint32_t vi = atomicAdd(V.n, 1u);
+      if (vi < V.cap) { V.node[vi] = slot; V.cqf_slot[vi] = cslot; }
+    }
     deg++; last = 2 * slot + (fwd_canon ? 0 : 1); pmask |= 1u << x;
   }
   L.outdeg[oid] = (uint8_t)deg; L.succ[oid] = last; L.succ_mask[oid] = (uint8_t)pmask;
@@ -312,12 +317,17 @@ __global__ void link_nodes_kernel(NodeTable T, ImageView im, LinkArrays L, int K
       uint64_t sfh, srh;
       kmer_nthash(sib, K, &sfh, &srh);
       uint64_t key = (sfh < srh ? sfh : srh) & mask;
-      uint64_t cnt = img_lookup(im, key, nullptr);
+      uint64_t cslot = 0;
+      uint64_t cnt = img_lookup(im, key, &cslot);
       if (cnt < s_min) continue;
       Kmer rc = kmer_rc(sib, K);
       bool fwd_canon = !kmer_less(rc, sib);
       bool fresh;
-      node_insert(T, fwd_canon ? sib : rc, (uint32_t)(cnt > 0xFFFFFFFFull ? 0xFFFFFFFFull : cnt), fwd_canon ? sfh : srh, fwd_canon ? srh : sfh, &fresh);
+      uint32_t ns = node_insert(T, fwd_canon ? sib : rc, (uint32_t)(cnt > 0xFFFFFFFFull ? 0xFFFFFFFFull : cnt), fwd_canon ? sfh : srh, fwd_canon ? srh : sfh, &fresh);
+      if (fresh && ns != kNil) {
+        uint32_t vi = atomicAdd(V.n, 1u);
+        if (vi < V.cap) { V.node[vi] = ns; V.cqf_slot[vi] = cslot; }
+      }
     }
   }
 }
@@ -659,9 +669,10 @@ void unitigs_build_impl(shq_unitigs_s* u) {
   SHQ_CUDA(cudaMemsetAsync(u->outdeg.p, 0, O, st)); SHQ_CUDA(cudaMemsetAsync(u->smask.p, 0, O, st));
   LinkArrays LA{u->outdeg.as<uint8_t>(), u->succ.as<uint32_t>(), u->smask.as<uint8_t>()};
   uint32_t begin = 0;
+  VictimList VL{u->v_node.as<uint32_t>(), u->v_slot.as<uint64_t>(), u->v_n.as<uint32_t>(), u->victim_cap};
   for (int round = 0; round < 64 && begin < n_nodes; round++) {
     uint32_t cnt = n_nodes - begin;
-    link_nodes_kernel<<<cdiv((size_t)cnt * 2, 128), 128, 0, st>>>(T, im, LA, K, h->hb, (uint32_t)u->opts.abundance_min, begin, n_nodes); L++;
+    link_nodes_kernel<<<cdiv((size_t)cnt * 2, 128), 128, 0, st>>>(T, im, LA, VL, K, h->hb, (uint32_t)u->opts.abundance_min, begin, n_nodes); L++;
     u->n_queries += (uint64_t)cnt * 8;
     begin = n_nodes;
     n_nodes = read_scalar(h, u->nn.as<uint32_t>());
@@ -756,16 +767,25 @@ void unitigs_build_impl(shq_unitigs_s* u) {
   SHQ_CUDA(cudaStreamSynchronize(st));
   h->stats.d2h_bytes += total_seq + total_k * 4 + (size_t)nu * 36 + (size_t)n_seeds * 8 + (size_t)nv * 16;
   check_err_flag(h);
+  auto rc_dbg = [](const std::string& s0) { std::string r(s0.rbegin(), s0.rend()); for (auto& c : r) c = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : 'A'; return r; };
   // The seed rule at t=1 (contig_assembly.cpp:1874-1880): seeds are taken in read order; a seed is skipped when its
   // KEY was traveled before.  All of a component's keys become traveled when its first seed is accepted, so a
   // seed is blocked iff another k-mer string sharing its key lives in a component explored earlier.
   {
-    std::unordered_map<uint32_t, std::vector<uint32_t>> partners;   // node slot -> roots of same-key nodes
+    // same-key groups: the entry's first visitor pn plus every victim recorded against it
+    std::unordered_map<uint32_t, std::vector<std::pair<uint32_t, uint32_t>>> groups;   // pn -> (node, root) members
     for (uint32_t i = 0; i < nv; i++) {
       uint32_t vn = vout[4 * i], vr = vout[4 * i + 1], pn = vout[4 * i + 2], pr = vout[4 * i + 3];
-      if (vr != kNil && pn != kNil) partners[pn].push_back(vr);
-      if (pr != kNil && vn != kNil) partners[vn].push_back(pr);
+      if (pn == kNil) continue;
+      auto& g = groups[pn];
+      if (g.empty()) g.push_back({pn, pr});
+      g.push_back({vn, vr});
     }
+    std::unordered_map<uint32_t, std::vector<uint32_t>> partners;   // node slot -> roots of the other same-key nodes
+    for (auto& kv : groups)
+      for (auto& a : kv.second)
+        for (auto& b : kv.second)
+          if (a.first != b.first && b.second != kNil) partners[a.first].push_back(b.second);
     std::vector<uint32_t> t_explored(nu, 0xFFFFFFFFu);
     for (uint32_t i = 0; i < n_seeds; i++) {
       uint32_t r = seed_root[i];
@@ -776,6 +796,23 @@ void unitigs_build_impl(shq_unitigs_s* u) {
       if (!blocked && t_explored[r] == 0xFFFFFFFFu) t_explored[r] = i;
     }
     for (uint32_t i = 0; i < nu; i++) keep[i] = roots[i] < nu && t_explored[roots[i]] != 0xFFFFFFFFu;
+    if (const char* dbg = getenv("SHQ_DEBUG_UNITIG")) {      // diagnostics for one unitig sequence (either strand)
+      std::string want(dbg);
+      uint64_t so = 0;
+      for (uint32_t i = 0; i < nu; i++) {
+        std::string sq(seq.data() + so, seqlen[i]);
+        so += seqlen[i];
+        if (sq != want && rc_dbg(sq) != want) continue;
+        fprintf(stderr, "[dbg] unitig old=%u root=%u t_explored=%u keep=%d nv=%u n_seeds=%u\n", i, roots[i], t_explored[roots[i]], (int)keep[i], nv, n_seeds);
+        for (uint32_t j = 0; j < n_seeds; j++) if (seed_root[j] == roots[i]) {
+          fprintf(stderr, "[dbg]   seed %u node %u partners:", j, seed_node[j]);
+          auto it = partners.find(seed_node[j]);
+          if (it != partners.end()) for (uint32_t pr : it->second) fprintf(stderr, " root %u (t=%u)", pr, pr < nu ? t_explored[pr] : 0);
+          fprintf(stderr, "\n");
+        }
+        for (int jj = 0; jj < 8; jj++) fprintf(stderr, "[dbg]   link[%d]=%d\n", jj, links[(size_t)i * 8 + jj]);
+      }
+    }
   }
   // host: canonical orientation, deterministic order, renumbering, medians, FASTA (contig_assembly.cpp:603-629)
   auto rc_str = [](const std::string& s) {

@@ -200,28 +200,36 @@ restart:
       }
     }
     if (SPLIT) {
-      // two ordered runs: rank = number of earlier keys with a non-zero half counter (block scan over nd keys)
+      // two ordered runs: every thread owns a contiguous slice of the sorted keys; rank = number of earlier keys with a
+      // non-zero half counter (two block scans per round in total)
       __syncthreads();
-      for (uint32_t base = 0; base < nd; base += blockDim.x) {
-        uint32_t i = base + threadIdx.x;
-        uint32_t kl = 0, c = 0, h = 0;
+      constexpr int SL = kAggMaxDistinct / kAggThreads + 1;      // nd may exceed kAggMaxDistinct by < blockDim racing inserts
+      const uint32_t per = (nd + blockDim.x - 1) / blockDim.x;
+      uint32_t cs[SL], hs[SL];
+      uint32_t fa = 0, fb = 0;
+      const uint32_t i0 = threadIdx.x * per;
+      for (uint32_t j = 0; j < per && j < (uint32_t)SL; j++) {
+        uint32_t i = i0 + j;
+        cs[j] = 0; hs[j] = 0;
         if (i < nd) {
-          kl = s_sort[i]; h = agg_hash(kl);
+          uint32_t kl = s_sort[i]; uint32_t h = agg_hash(kl);
           while (t_key[h] != kl) h = (h + 1) & (kAggTable - 1);
-          c = t_cnt[h];
+          cs[j] = t_cnt[h]; hs[j] = h;
+          fa += (cs[j] & 0xFFFFu) ? 1 : 0; fb += (cs[j] >> 16) ? 1 : 0;
         }
-        uint32_t fa = (i < nd && (c & 0xFFFFu)) ? 1 : 0, fb = (i < nd && (c >> 16)) ? 1 : 0;
-        uint32_t ta, tb;
-        uint32_t ra = block_exclusive_scan<SumU32>(fa, &ta);
-        uint32_t rb = block_exclusive_scan<SumU32>(fb, &tb);
-        uint32_t ba = s_na, bb = s_nb;
-        __syncthreads();
-        uint64_t key = key_lo + (((uint64_t)p << lb) | kl);
-        if (fa) { size_t oo = obase + written + ba + ra; o.keys[oo] = key; o.counts[oo] = c & 0xFFFFu; if (o.chunk) o.chunk[oo] = t_chk[h]; }
-        if (fb) { size_t oo = obase + written2 + bb + rb; o.keys2[oo] = key; o.counts2[oo] = c >> 16; }
-        if (threadIdx.x == 0) { s_na = ba + ta; s_nb = bb + tb; }
-        __syncthreads();
       }
+      uint32_t ta, tb;
+      uint32_t ra = block_exclusive_scan<SumU32>(fa, &ta);
+      uint32_t rb = block_exclusive_scan<SumU32>(fb, &tb);
+      for (uint32_t j = 0; j < per && j < (uint32_t)SL; j++) {
+        uint32_t i = i0 + j;
+        if (i >= nd) break;
+        uint32_t c = cs[j];
+        uint64_t key = key_lo + (((uint64_t)p << lb) | s_sort[i]);
+        if (c & 0xFFFFu) { size_t oo = obase + written + ra; o.keys[oo] = key; o.counts[oo] = c & 0xFFFFu; if (o.chunk) o.chunk[oo] = t_chk[hs[j]]; ra++; }
+        if (c >> 16) { size_t oo = obase + written2 + rb; o.keys2[oo] = key; o.counts2[oo] = c >> 16; rb++; }
+      }
+      if (threadIdx.x == 0) { s_na = ta; s_nb = tb; }
     }
     __syncthreads();
     if (do_hist) for (int i = threadIdx.x; i < kAggBuckets; i += blockDim.x) { uint32_t v = s_bkt[i]; if (v) atomicAdd(&o.first_hist[i], v); }

@@ -204,7 +204,7 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
   const int G = kNumSMs * 2;
   const int W = g_scatter_w;
   size_t smem_count = sizeof(RollTables) + (size_t)n_bins * 4;
-  size_t smem_scatter = sizeof(RollTables) + ((size_t)3 * n_bins + 1) * 4 + (size_t)kRollThreads * W * 10 + 16;
+  size_t smem_scatter = sizeof(RollTables) + ((size_t)3 * n_bins + 1) * 4 + (size_t)16384 * 10 + 16;   // threads * W == 16384 keys per round
   size_t smem_keys = (size_t)n_bins * 8;
   Sink sk{};
   {
@@ -225,12 +225,12 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
   {
     Phase ph(h, &h->stats.ms_scatter);
     if (from_text) {
-      if (W == 16) {
-        SHQ_CUDA(cudaFuncSetAttribute(roll_scatter_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
-        roll_scatter_kernel<16><<<kNumSMs * (smem_scatter <= 110 * 1024 ? 2 : 1), kRollThreads, smem_scatter, st>>>(hp, h->d_tot.as<uint32_t>(), h->d_packed.as<uint32_t>());
+      if (W == 16) {     // 1024 threads x 16 windows: same shared memory, twice the warps
+        SHQ_CUDA(cudaFuncSetAttribute(roll_scatter_kernel<1024, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
+        roll_scatter_kernel<1024, 16><<<kNumSMs, 1024, smem_scatter, st>>>(hp, h->d_tot.as<uint32_t>(), h->d_packed.as<uint32_t>());
       } else {
-        SHQ_CUDA(cudaFuncSetAttribute(roll_scatter_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
-        roll_scatter_kernel<32><<<kNumSMs, kRollThreads, smem_scatter, st>>>(hp, h->d_tot.as<uint32_t>(), h->d_packed.as<uint32_t>());
+        SHQ_CUDA(cudaFuncSetAttribute(roll_scatter_kernel<512, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
+        roll_scatter_kernel<512, 32><<<kNumSMs, 512, smem_scatter, st>>>(hp, h->d_tot.as<uint32_t>(), h->d_packed.as<uint32_t>());
       }
       L++;
     } else {

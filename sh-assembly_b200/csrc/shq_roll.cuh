@@ -150,16 +150,16 @@ __global__ void __launch_bounds__(kRollThreads) roll_count_kernel(HashParams hp,
 // (3) counting-sorts the round by bin inside shared memory, (4) writes every bin's keys with 8 adjacent
 // lanes, i.e. as one 32-byte sector request instead of eight scattered 4-byte stores.
 // dynamic smem: RollTables + (3*n_bins + 1) * 4 + kRollThreads * W * (4 + 4 + 2)
-template <int W>
-__global__ void __launch_bounds__(kRollThreads) roll_scatter_kernel(HashParams hp, uint32_t* __restrict__ g_cursor, uint32_t* __restrict__ packed) {
+template <int THREADS, int W>
+__global__ void __launch_bounds__(THREADS) roll_scatter_kernel(HashParams hp, uint32_t* __restrict__ g_cursor, uint32_t* __restrict__ packed) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RollTables* tab = reinterpret_cast<RollTables*>(smem_raw);
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw + sizeof(RollTables));
   uint32_t* s_off = s_hist + hp.n_bins;              // n_bins + 1 entries
   uint32_t* s_base = s_off + hp.n_bins + 1;
   uint32_t* s_key = s_base + hp.n_bins;
-  uint32_t* s_sorted = s_key + kRollThreads * W;
-  uint16_t* s_bin = reinterpret_cast<uint16_t*>(s_sorted + kRollThreads * W);
+  uint32_t* s_sorted = s_key + THREADS * W;
+  uint16_t* s_bin = reinterpret_cast<uint16_t*>(s_sorted + THREADS * W);
   roll_tables_init(tab, hp.K);
   uint32_t r0 = (uint32_t)(((uint64_t)hp.n_reads * blockIdx.x) / gridDim.x);
   uint32_t r1 = (uint32_t)(((uint64_t)hp.n_reads * (blockIdx.x + 1)) / gridDim.x);
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kRollThreads) roll_scatter_kernel(HashParams h
   const uint64_t key_lo = hp.key_lo, key_hi = hp.key_hi; const int lb = hp.lb;
   const bool whole = key_lo == 0 && key_hi > mask;
   const uint32_t lowmask = lb >= 32 ? 0xFFFFFFFFu : ((1u << lb) - 1);
-  const int per = (hp.n_bins + kRollThreads - 1) / kRollThreads;      // bins per thread in the scan
+  const int per = (hp.n_bins + THREADS - 1) / THREADS;      // bins per thread in the scan
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   bool more = true;
   int produced = 0;
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kRollThreads) roll_scatter_kernel(HashParams h
     if (!whole && (key < key_lo || key >= key_hi)) return;
     uint64_t rel = key - key_lo;
     uint32_t bin = (uint32_t)(rel >> lb);
-    int idx = produced * kRollThreads + threadIdx.x;
+    int idx = produced * THREADS + threadIdx.x;
     s_key[idx] = ((uint32_t)rel & lowmask) | (lb >= 32 ? 0 : (ch << lb));
     s_bin[idx] = (uint16_t)bin;
     atomicAdd(&s_hist[bin], 1u);
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(kRollThreads) roll_scatter_kernel(HashParams h
     __syncthreads();
     produced = 0;
     while (more && produced + 4 <= W) more = R.step(mask, emit);
-    for (int j = produced; j < W; j++) s_bin[j * kRollThreads + threadIdx.x] = 0xFFFF;
+    for (int j = produced; j < W; j++) s_bin[j * THREADS + threadIdx.x] = 0xFFFF;
     int any = __syncthreads_or(produced > 0);
     if (!any) break;
     {   // exclusive scan over the bins + global reservation
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kRollThreads) roll_scatter_kernel(HashParams h
     __syncthreads();
 #pragma unroll 4
     for (int j = 0; j < W; j++) {      // counting sort of the round by bin
-      int idx = j * kRollThreads + threadIdx.x;
+      int idx = j * THREADS + threadIdx.x;
       uint32_t bin = s_bin[idx];
       if (bin != 0xFFFF) {
         uint32_t rank = atomicSub(&s_hist[bin], 1u) - 1;
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(kRollThreads) roll_scatter_kernel(HashParams h
       }
     }
     __syncthreads();
-    for (int b = wid * 4 + (lane >> 3); b < hp.n_bins; b += (kRollThreads / 32) * 4) {
+    for (int b = wid * 4 + (lane >> 3); b < hp.n_bins; b += (THREADS / 32) * 4) {
       uint32_t off = s_off[b], cnt = s_off[b + 1] - off, base = s_base[b];
       for (uint32_t l = lane & 7; l < cnt; l += 8) packed[base + l] = s_sorted[off + l];
     }

@@ -132,7 +132,7 @@ restart:
       volatile uint32_t* ovf = &s_overflow;
 #define SHQ_AGG_CALL(S, C, F) agg_insert_pass<S, C, F>(packed, beg, end, lb, lowmask, chunk_lo, chunk_hi, cstar, sub_bits, r, t_key, t_cnt, t_chk, \
                                                        &s_ndist, ovf, o.split_overflow, &s_nocc, &s_nocc2)
-      if (SPLIT) { if (filt) SHQ_AGG_CALL(SPLIT, true, true); else SHQ_AGG_CALL(SPLIT, true, false); }
+      if (SPLIT) { if (filt) SHQ_AGG_CALL(SPLIT, false, true); else SHQ_AGG_CALL(SPLIT, false, false); }   // no first chunks: the split is the last tracked round
       else if (want_chunk) { if (filt) SHQ_AGG_CALL(false, true, true); else SHQ_AGG_CALL(false, true, false); }
       else { if (filt) SHQ_AGG_CALL(false, false, true); else SHQ_AGG_CALL(false, false, false); }
 #undef SHQ_AGG_CALL

@@ -129,7 +129,7 @@ struct BatchBins {
 };
 struct Run { DevBuf* keys; DevBuf* counts; DevBuf* chunk; size_t n = 0; uint64_t occ = 0; };
 
-int g_scatter_w = 32;           // keys staged per thread and round (tunable: SHQ_SCATTER_W)
+int g_scatter_w = 16;           // keys staged per thread and round (tunable: SHQ_SCATTER_W)
 int g_bin_bits = 0;             // 0 = automatic (tunable: SHQ_BIN_BITS)
 
 int pick_bin_bits(shq_handle_s* h, uint64_t est_keys, int chunk_bits_needed) {

@@ -120,10 +120,9 @@ __global__ void __launch_bounds__(kRollThreads) roll_count_kernel(HashParams hp,
   roll_tables_init(tab, hp.K);
   for (int i = threadIdx.x; i < hp.n_bins; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
-  uint32_t r0 = (uint32_t)(((uint64_t)hp.n_reads * blockIdx.x) / gridDim.x);
-  uint32_t r1 = (uint32_t)(((uint64_t)hp.n_reads * (blockIdx.x + 1)) / gridDim.x);
+  // reads are dealt round-robin over the whole grid, so all CTAs walk the text front to back together
   Roller R;
-  R.start(&hp, tab, r0 + threadIdx.x, r1, blockDim.x);
+  R.start(&hp, tab, blockIdx.x * blockDim.x + threadIdx.x, hp.n_reads, gridDim.x * blockDim.x);
   const uint64_t mask = hp.hb >= 64 ? ~0ULL : ((1ULL << hp.hb) - 1);
   const uint64_t key_lo = hp.key_lo, key_hi = hp.key_hi; const int lb = hp.lb;
   const bool whole = key_lo == 0 && key_hi > mask;      // unsharded: every key is ours
@@ -161,11 +160,11 @@ __global__ void __launch_bounds__(THREADS) roll_scatter_kernel(HashParams hp, ui
   uint32_t* s_sorted = s_key + THREADS * W;
   uint16_t* s_bin = reinterpret_cast<uint16_t*>(s_sorted + THREADS * W);
   roll_tables_init(tab, hp.K);
-  uint32_t r0 = (uint32_t)(((uint64_t)hp.n_reads * blockIdx.x) / gridDim.x);
-  uint32_t r1 = (uint32_t)(((uint64_t)hp.n_reads * (blockIdx.x + 1)) / gridDim.x);
   __syncthreads();
+  // reads are dealt round-robin over the whole grid: every bin then receives its words in (roughly) chunk
+  // order, which keeps the aggregator's first-chunk minimum almost free of updates
   Roller R;
-  R.start(&hp, tab, r0 + threadIdx.x, r1, blockDim.x);
+  R.start(&hp, tab, blockIdx.x * blockDim.x + threadIdx.x, hp.n_reads, gridDim.x * blockDim.x);
   const uint64_t mask = hp.hb >= 64 ? ~0ULL : ((1ULL << hp.hb) - 1);
   const uint64_t key_lo = hp.key_lo, key_hi = hp.key_hi; const int lb = hp.lb;
   const bool whole = key_lo == 0 && key_hi > mask;

@@ -14,6 +14,7 @@
 #pragma once
 #include "shq_common.cuh"
 #include "shq_layout.cuh"
+#include <chrono>
 #include <unordered_map>
 
 #include "shq_scan.cuh"
@@ -654,6 +655,18 @@ template <class T> void fill_u32(DevBuf& b, size_t n, uint32_t v, cudaStream_t s
   fill_u32_kernel<<<cdiv(n, 256), 256, 0, st>>>(b.as<uint32_t>(), v, n);
 }
 
+struct DbgTimer {
+  bool on; cudaStream_t st; std::chrono::steady_clock::time_point t0;
+  DbgTimer(cudaStream_t s) : on(getenv("SHQ_DEBUG_TIMING") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+  void lap(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[timing] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 void unitigs_build_impl(shq_unitigs_s* u) {
   shq_handle_s* h = u->h;
   cudaStream_t st = h->stream;
@@ -664,6 +677,7 @@ void unitigs_build_impl(shq_unitigs_s* u) {
   const size_t O = (size_t)2 * u->cap;      // oriented ids
   uint32_t n_nodes = read_scalar(h, u->nn.as<uint32_t>());
   check_err_flag(h);
+  DbgTimer tm(st);
   // U3: links + false-positive closure
   u->outdeg.reserve(O); u->smask.reserve(O); u->succ.reserve(O * 4);
   SHQ_CUDA(cudaMemsetAsync(u->outdeg.p, 0, O, st)); SHQ_CUDA(cudaMemsetAsync(u->smask.p, 0, O, st));
@@ -681,6 +695,7 @@ void unitigs_build_impl(shq_unitigs_s* u) {
   }
   if (n_nodes == 0) { u->built = true; return; }
   const unsigned g2 = cdiv((size_t)n_nodes * 2, 256);
+  tm.lap("U3 links+closure");
   // U4: chains
   fill_u32<uint32_t>(u->next, O, kNil, st); fill_u32<uint32_t>(u->prev, O, kNil, st); L += 2;
   simple_links_kernel<<<g2, 256, 0, st>>>(T, LA, n_nodes, u->next.as<uint32_t>(), u->prev.as<uint32_t>()); L++;
@@ -704,6 +719,7 @@ void unitigs_build_impl(shq_unitigs_s* u) {
     cycle_cut_kernel<<<g2, 256, 0, st>>>(T, n_nodes, u->minid.as<uint32_t>(), u->next.as<uint32_t>(), u->prev.as<uint32_t>()); L++;
     rank();
   }
+  tm.lap("U4 chains+ranking");
   // U5: unitigs
   fill_u32<uint32_t>(u->tail_of, O, kNil, st); fill_u32<uint32_t>(u->len_of, O, 0, st); fill_u32<uint32_t>(u->uid_of_head, O, kNil, st); L += 3;
   fill_u32<uint32_t>(u->unitig_of_oid, O, kNil, st); L++;
@@ -726,6 +742,7 @@ void unitigs_build_impl(shq_unitigs_s* u) {
   u->seq.reserve(total_seq + 16); u->kcounts.reserve((total_k + 4) * 4);
   assemble_kernel<<<g2, 256, 0, st>>>(T, n_nodes, u->jd.as<unsigned long long>(), u->uid_of_head.as<uint32_t>(), u->u_seqlen.as<uint64_t>(),
                                       u->u_klen.as<uint64_t>(), K, u->seq.as<char>(), u->kcounts.as<uint32_t>(), u->unitig_of_oid.as<uint32_t>()); L++;
+  tm.lap("U5 assemble");
   // U6: links, components, seeds
   u->links.reserve((size_t)nu * 8 * 4); u->parent.reserve((size_t)nu * 4); u->reached.reserve(nu); u->keep.reserve(nu);
   init_iota_kernel<<<cdiv(nu, 256), 256, 0, st>>>(u->parent.as<uint32_t>(), nu); L++;
@@ -759,6 +776,7 @@ void unitigs_build_impl(shq_unitigs_s* u) {
   std::vector<uint32_t> roots(nu);
   SHQ_CUDA(cudaMemcpyAsync(roots.data(), u->roots.p, (size_t)nu * 4, cudaMemcpyDeviceToHost, st));
   SHQ_CUDA(cudaGetLastError());
+  tm.lap("U6 links+seeds");
   // D2H
   std::vector<char> seq(total_seq); std::vector<uint32_t> kc(total_k); std::vector<int> links((size_t)nu * 8); std::vector<uint8_t> keep(nu, 0);
   SHQ_CUDA(cudaMemcpyAsync(seq.data(), u->seq.p, total_seq, cudaMemcpyDeviceToHost, st));
@@ -814,6 +832,7 @@ void unitigs_build_impl(shq_unitigs_s* u) {
       }
     }
   }
+  tm.lap("D2H + seed rule");
   // host: canonical orientation, deterministic order, renumbering, medians, FASTA (contig_assembly.cpp:603-629)
   auto rc_str = [](const std::string& s) {
     std::string r(s.rbegin(), s.rend());
@@ -869,6 +888,7 @@ void unitigs_build_impl(shq_unitigs_s* u) {
     for (int t : bef) f += t > 0 ? " L:-:" + std::to_string(t - 1) + ":+" : " L:-:" + std::to_string(-t - 1) + ":-";
     f += "\n" + R.seq + "\n";
   }
+  tm.lap("host canonicalise+FASTA");
   u->built = true;
 }
 
@@ -926,7 +946,9 @@ int shq_unitigs_add_reads(shq_unitigs_t u, const char* text, size_t n) {
     cudaStream_t st = h->stream;
     uint64_t& L = h->stats.kernels_launched;
     if (a.n >= ((size_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "chunk too large");
+    DbgTimer tm(st);
     collect_seeds(u, a.t, a.n);
+    tm.lap("add_reads: collect_seeds");
     u->d_text.reserve(a.n + 64);
     SHQ_CUDA(cudaMemcpyAsync(u->d_text.p, a.t, a.n, cudaMemcpyHostToDevice, st));
     h->stats.h2d_bytes += a.n;
@@ -947,6 +969,7 @@ int shq_unitigs_add_reads(shq_unitigs_t u, const char* text, size_t n) {
     enum_nodes_kernel<<<4 * kNumSMs, kEnumWarps * 32, smem, st>>>(ep, im, u->aux.as<uint64_t>(), u->aux2.as<uint32_t>(), V, node_table(u)); L++;
     SHQ_CUDA(cudaGetLastError());
     SHQ_CUDA(cudaStreamSynchronize(st));
+    tm.lap("add_reads: H2D+index+enum");
     check_err_flag(h);
   }, &args);
 }

@@ -14,9 +14,11 @@ namespace shq {
 constexpr int kAggThreads = 512;
 constexpr int kAggTable = 8192;          // open-addressing slots per CTA (two CTAs per SM)
 constexpr int kAggMaxDistinct = 4096;    // per round (load factor <= 0.5)
-constexpr int kAggBuckets = 4096;        // bucket sort of the distinct keys
+constexpr int kAggOrdCap = kAggMaxDistinct + kAggThreads;   // racing inserts may overshoot by < blockDim
+constexpr int kAggBuckets = 1024;        // bucket sort of the distinct keys
 constexpr uint32_t kAggEmpty = 0xFFFFFFFFu;
-constexpr size_t kAggSmemBytes = (size_t)kAggTable * (4 + 4 + 2) + (size_t)kAggMaxDistinct * 4 + (size_t)kAggBuckets * 4;
+// t_key, t_cnt, t_chk (u32 each) + slot order (u16) + bucket counters (u32)
+constexpr size_t kAggSmemBytes = (size_t)kAggTable * 12 + (size_t)kAggOrdCap * 2 + (size_t)kAggBuckets * 4;
 
 __device__ __forceinline__ uint32_t agg_hash(uint32_t k) { return (k * 2654435761u) >> (32 - 13); }
 
@@ -35,7 +37,7 @@ struct AggOut {
 template <bool SPLIT, bool CHUNK, bool FILT>
 __device__ __forceinline__ void agg_insert_pass(const uint32_t* __restrict__ packed, uint32_t beg, uint32_t end, int lb, uint32_t lowmask,
                                                 uint32_t chunk_lo, uint32_t chunk_hi, uint32_t cstar, int sub_bits, uint32_t r,
-                                                uint32_t* t_key, uint32_t* t_cnt, uint16_t* t_chk, uint32_t* s_ndist,
+                                                uint32_t* t_key, uint32_t* t_cnt, uint32_t* t_chk, uint32_t* s_ndist,
                                                 volatile uint32_t* s_overflow, int* split_overflow, uint32_t* occ1, uint32_t* occ2) {
   uint32_t my_occ = 0, my_occ2 = 0;
   constexpr int U = 4;                               // loads of U strided words are issued before any is consumed
@@ -74,29 +76,19 @@ __device__ __forceinline__ void agg_insert_pass(const uint32_t* __restrict__ pac
       } else {
         atomicAdd(&t_cnt[h], 1u);
       }
-      if (CHUNK && !second) {   // 16-bit atomic min of the first chunk through the containing 32-bit word
-        unsigned int* wp = reinterpret_cast<unsigned int*>(t_chk) + (h >> 1);
-        unsigned int sh = (h & 1) * 16;
-        unsigned int oldw = *reinterpret_cast<volatile unsigned int*>(wp);
-        while (((oldw >> sh) & 0xFFFFu) > ch) {
-          unsigned int nw = (oldw & ~(0xFFFFu << sh)) | (ch << sh);
-          unsigned int prev = atomicCAS(wp, oldw, nw);
-          if (prev == oldw) break;
-          oldw = prev;
-        }
-      }
+      if (CHUNK && !second) { if (ch < t_chk[h]) atomicMin(&t_chk[h], ch); }   // first chunk: native 32-bit minimum
     }
   }
   if (FILT || SPLIT) { atomicAdd(occ1, my_occ); if (SPLIT) atomicAdd(occ2, my_occ2); }
   else if (threadIdx.x == 0) atomicAdd(occ1, end - beg);
 }
 
-// One CTA per bin.  packed[bin_off[p] .. bin_off[p+1]) holds (key_low | chunk << lb).
+// One CTA per (bin, key sub-range).  packed[bin_off[p] .. bin_off[p+1]) holds (key_low | chunk << lb).
 // Occurrences whose chunk is outside [chunk_lo, chunk_hi] are ignored.
 // SPLIT: occurrences with chunk <= cstar are counted in the low half of the counter, the others in the high
 // half, and two sorted runs come out of one pass (deNoise boundary inside a batch).
-// Output (sorted by key) goes to out[bin_off[p] + i].  A bin with more than kAggMaxDistinct distinct keys is
-// re-streamed in 2^k key sub-ranges.
+// Output (sorted by key) goes to out[sub * sub_stride + bin_off[p] + i].  A sub-range with more than
+// kAggMaxDistinct distinct keys is re-streamed in 2^k narrower key ranges.
 template <bool SPLIT>
 __global__ void __launch_bounds__(kAggThreads) bin_aggregate_kernel(
     const uint32_t* __restrict__ packed, const uint32_t* __restrict__ bin_off, int lb, uint64_t key_lo,
@@ -104,9 +96,9 @@ __global__ void __launch_bounds__(kAggThreads) bin_aggregate_kernel(
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* t_key = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* t_cnt = t_key + kAggTable;
-  uint32_t* s_sort = t_cnt + kAggTable;
-  uint32_t* s_bkt = s_sort + kAggMaxDistinct;
-  uint16_t* t_chk = reinterpret_cast<uint16_t*>(s_bkt + kAggBuckets);
+  uint32_t* t_chk = t_cnt + kAggTable;
+  uint32_t* s_bkt = t_chk + kAggTable;
+  uint16_t* s_ord = reinterpret_cast<uint16_t*>(s_bkt + kAggBuckets);    // table slots in key order
   __shared__ uint32_t s_ndist, s_nocc, s_nocc2, s_overflow, s_na, s_nb;
 
   const uint32_t p = blockIdx.x >> o.fixed_bits;
@@ -114,7 +106,7 @@ __global__ void __launch_bounds__(kAggThreads) bin_aggregate_kernel(
   const uint32_t beg = bin_off[p], end = bin_off[p + 1];
   const size_t obase = (size_t)fsub * o.sub_stride + beg;
   const uint32_t lowmask = lb >= 32 ? 0xFFFFFFFFu : ((1u << lb) - 1);
-  const bool want_chunk = o.chunk != nullptr || o.first_hist != nullptr;
+  const bool want_chunk = !SPLIT && (o.chunk != nullptr || o.first_hist != nullptr);
   uint32_t written = 0, written2 = 0, occ_total = 0, occ_total2 = 0;
   int sub_bits = o.fixed_bits;   // key_low bits fixed per round: fixed_bits chosen by the grid, the rest by overflow restarts
   while (sub_bits < lb && ((end - beg) >> sub_bits) > 64u * kAggMaxDistinct) sub_bits++;
@@ -122,7 +114,8 @@ __global__ void __launch_bounds__(kAggThreads) bin_aggregate_kernel(
 restart:
   written = 0; written2 = 0; occ_total = 0; occ_total2 = 0;
   for (uint32_t r = fsub << (sub_bits - o.fixed_bits); r < ((fsub + 1) << (sub_bits - o.fixed_bits)); r++) {
-    for (int i = threadIdx.x; i < kAggTable; i += blockDim.x) { t_key[i] = kAggEmpty; t_cnt[i] = 0; t_chk[i] = 0xFFFF; }
+    for (int i = threadIdx.x; i < kAggTable; i += blockDim.x) { t_key[i] = kAggEmpty; t_cnt[i] = 0; }
+    if (want_chunk) for (int i = threadIdx.x; i < kAggTable; i += blockDim.x) t_chk[i] = 0xFFFFFFFFu;
     for (int i = threadIdx.x; i < kAggBuckets; i += blockDim.x) s_bkt[i] = 0;
     if (threadIdx.x == 0) { s_ndist = 0; s_nocc = 0; s_nocc2 = 0; s_overflow = 0; s_na = 0; s_nb = 0; }
     __syncthreads();
@@ -139,9 +132,9 @@ restart:
     }
     __syncthreads();
     if (*reinterpret_cast<volatile uint32_t*>(&s_overflow)) { sub_bits++; __syncthreads(); goto restart; }
-    // ---- bucket sort of the distinct keys (keys are hash values: buckets hold ~nd/4096 keys each)
+    // ---- bucket sort of the occupied slots by key (keys are hash values: ~nd/1024 keys per bucket)
     const int bits = lb - sub_bits;                    // key_low bits that vary inside this round
-    const int bshift = bits > 12 ? bits - 12 : 0;
+    const int bshift = bits > 10 ? bits - 10 : 0;
     const uint32_t relmask = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1);
     for (int i = threadIdx.x; i < kAggTable; i += blockDim.x) {
       uint32_t k = t_key[i];
@@ -161,18 +154,18 @@ restart:
     __syncthreads();
     for (int i = threadIdx.x; i < kAggTable; i += blockDim.x) {
       uint32_t k = t_key[i];
-      if (k != kAggEmpty) s_sort[atomicAdd(&s_bkt[(k & relmask) >> bshift], 1u)] = k;
+      if (k != kAggEmpty) s_ord[atomicAdd(&s_bkt[(k & relmask) >> bshift], 1u)] = (uint16_t)i;
     }
     __syncthreads();
     const uint32_t nd = s_ndist;
 #pragma unroll
-    for (int j = 0; j < PER; j++) {                    // s_bkt[b] is now the END of bucket b
+    for (int j = 0; j < PER; j++) {                    // s_bkt[b] is now the END of bucket b: insertion sort inside the bucket
       int b = threadIdx.x * PER + j;
       uint32_t lo = b ? s_bkt[b - 1] : 0, hi = s_bkt[b];
       for (uint32_t x = lo + 1; x < hi; x++) {
-        uint32_t kx = s_sort[x]; uint32_t y = x;
-        while (y > lo && s_sort[y - 1] > kx) { s_sort[y] = s_sort[y - 1]; y--; }
-        s_sort[y] = kx;
+        uint16_t sx = s_ord[x]; uint32_t kx = t_key[sx]; uint32_t y = x;
+        while (y > lo && t_key[s_ord[y - 1]] > kx) { s_ord[y] = s_ord[y - 1]; y--; }
+        s_ord[y] = sx;
       }
     }
     __syncthreads();
@@ -182,41 +175,27 @@ restart:
       __syncthreads();
     }
     // ---- emit
-    for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) {
-      uint32_t kl = s_sort[i];
-      uint32_t h = agg_hash(kl);
-      while (t_key[h] != kl) h = (h + 1) & (kAggTable - 1);
-      uint32_t c = t_cnt[h];
-      uint64_t key = key_lo + (((uint64_t)p << lb) | kl);
-      if (!SPLIT) {
+    if (!SPLIT) {
+      for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) {
+        uint32_t h = s_ord[i];
         size_t oo = obase + written + i;
-        o.keys[oo] = key; o.counts[oo] = c;
-        if (o.chunk) o.chunk[oo] = t_chk[h];
+        o.keys[oo] = key_lo + (((uint64_t)p << lb) | t_key[h]);
+        o.counts[oo] = t_cnt[h];
+        if (o.chunk) o.chunk[oo] = (uint16_t)t_chk[h];
         if (do_hist) atomicAdd(&s_bkt[t_chk[h] & (kAggBuckets - 1)], 1u);
-      } else {
-        // order-preserving compaction of the two runs: ranks via a second pass below
-        s_sort[i] = kl;   // keep
-        (void)c; (void)key;
       }
-    }
-    if (SPLIT) {
+    } else {
       // two ordered runs: every thread owns a contiguous slice of the sorted keys; rank = number of earlier keys with a
       // non-zero half counter (two block scans per round in total)
-      __syncthreads();
-      constexpr int SL = kAggMaxDistinct / kAggThreads + 1;      // nd may exceed kAggMaxDistinct by < blockDim racing inserts
+      constexpr int SL = kAggOrdCap / kAggThreads;
       const uint32_t per = (nd + blockDim.x - 1) / blockDim.x;
-      uint32_t cs[SL], hs[SL];
+      uint32_t cs[SL];
       uint32_t fa = 0, fb = 0;
       const uint32_t i0 = threadIdx.x * per;
       for (uint32_t j = 0; j < per && j < (uint32_t)SL; j++) {
         uint32_t i = i0 + j;
-        cs[j] = 0; hs[j] = 0;
-        if (i < nd) {
-          uint32_t kl = s_sort[i]; uint32_t h = agg_hash(kl);
-          while (t_key[h] != kl) h = (h + 1) & (kAggTable - 1);
-          cs[j] = t_cnt[h]; hs[j] = h;
-          fa += (cs[j] & 0xFFFFu) ? 1 : 0; fb += (cs[j] >> 16) ? 1 : 0;
-        }
+        cs[j] = i < nd ? t_cnt[s_ord[i]] : 0;
+        fa += (cs[j] & 0xFFFFu) ? 1 : 0; fb += (cs[j] >> 16) ? 1 : 0;
       }
       uint32_t ta, tb;
       uint32_t ra = block_exclusive_scan<SumU32>(fa, &ta);
@@ -225,8 +204,8 @@ restart:
         uint32_t i = i0 + j;
         if (i >= nd) break;
         uint32_t c = cs[j];
-        uint64_t key = key_lo + (((uint64_t)p << lb) | s_sort[i]);
-        if (c & 0xFFFFu) { size_t oo = obase + written + ra; o.keys[oo] = key; o.counts[oo] = c & 0xFFFFu; if (o.chunk) o.chunk[oo] = t_chk[hs[j]]; ra++; }
+        uint64_t key = key_lo + (((uint64_t)p << lb) | t_key[s_ord[i]]);
+        if (c & 0xFFFFu) { size_t oo = obase + written + ra; o.keys[oo] = key; o.counts[oo] = c & 0xFFFFu; if (o.chunk) o.chunk[oo] = 0; ra++; }
         if (c >> 16) { size_t oo = obase + written2 + rb; o.keys2[oo] = key; o.counts2[oo] = c >> 16; rb++; }
       }
       if (threadIdx.x == 0) { s_na = ta; s_nb = tb; }

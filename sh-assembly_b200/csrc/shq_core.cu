@@ -203,8 +203,9 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
   SHQ_CUDA(cudaMemsetAsync(h->d_chunk_keys.p, 0, (size_t)(nchunks + 1) * 4, st));
   const int G = kNumSMs * 2;
   const int W = g_scatter_w;
-  size_t smem_count = sizeof(RollTables) + (size_t)n_bins * 4;
-  size_t smem_scatter = sizeof(RollTables) + ((size_t)3 * n_bins + 1) * 4 + (size_t)16384 * 10 + 16;   // threads * W == 16384 keys per round
+  const size_t smem_cle = hp.chunk_line_end ? (size_t)nchunks * 4 + 16 : 0;
+  size_t smem_count = sizeof(RollTables) + (size_t)n_bins * 4 + smem_cle;
+  size_t smem_scatter = sizeof(RollTables) + ((size_t)3 * n_bins + 1) * 4 + (size_t)16384 * 10 + 16 + smem_cle;   // threads * W == 16384 keys per round
   size_t smem_keys = (size_t)n_bins * 8;
   Sink sk{};
   {
@@ -270,7 +271,7 @@ bool aggregate_bins(shq_handle_s* h, const BatchBins& bb, uint32_t clo, uint32_t
   SHQ_CUDA(cudaMemsetAsync(d_ovf, 0, 4, st));
   uint32_t* d_fh = nullptr;
   if (first_hist) {
-    if (bb.nchunks > kAggBuckets) SHQ_FAIL(SHQ_ERR_ARG, "too many chunks in one batch");
+    if (bb.nchunks > kAggBuckets) SHQ_FAIL(SHQ_ERR_ARG, "too many chunks in one batch (max %d)", kAggBuckets);
     h->d_chunk_hist.reserve((size_t)kAggBuckets * 4);
     d_fh = h->d_chunk_hist.as<uint32_t>();
     SHQ_CUDA(cudaMemsetAsync(d_fh, 0, (size_t)kAggBuckets * 4, st));
@@ -487,8 +488,9 @@ void process_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uin
     // find the first chunk c* >= clo after which ndistinct >= trigger (t=1 rule, CQF_mt.h:837)
     std::vector<uint32_t> hist;
     const bool empty_state = h->n_state == 0;
-    aggregate_bins(h, bb, clo, last, false, 0, &A, nullptr, empty_state ? &hist : nullptr);
-    if (!empty_state) merge_run(h, A, nchunks, &hist, false);
+    const bool agg_hist = empty_state && nchunks <= kAggBuckets;
+    aggregate_bins(h, bb, clo, last, false, 0, &A, nullptr, agg_hist ? &hist : nullptr);
+    if (!agg_hist) merge_run(h, A, nchunks, &hist, false);
     uint64_t nd = h->ndistinct; int cstar = -1;
     for (uint32_t c = clo; c <= last; c++) { nd += hist[c]; if (nd >= h->trigger) { cstar = (int)c; break; } }
     if (cstar < 0 || (uint32_t)cstar == last) {

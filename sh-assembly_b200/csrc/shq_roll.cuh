@@ -119,6 +119,11 @@ __global__ void __launch_bounds__(kRollThreads) roll_count_kernel(HashParams hp,
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw + sizeof(RollTables));
   roll_tables_init(tab, hp.K);
   for (int i = threadIdx.x; i < hp.n_bins; i += blockDim.x) s_hist[i] = 0;
+  if (hp.chunk_line_end) {                   // chunk -> line map next to the histogram: the per-read search stays on chip
+    uint32_t* s_cle = s_hist + hp.n_bins;
+    for (int i = threadIdx.x; i < hp.nchunks; i += blockDim.x) s_cle[i] = hp.chunk_line_end[i];
+    hp.chunk_line_end = s_cle;
+  }
   __syncthreads();
   // reads are dealt round-robin over the whole grid, so all CTAs walk the text front to back together
   Roller R;
@@ -160,6 +165,11 @@ __global__ void __launch_bounds__(THREADS) roll_scatter_kernel(HashParams hp, ui
   uint32_t* s_sorted = s_key + THREADS * W;
   uint16_t* s_bin = reinterpret_cast<uint16_t*>(s_sorted + THREADS * W);
   roll_tables_init(tab, hp.K);
+  if (hp.chunk_line_end) {
+    uint32_t* s_cle = reinterpret_cast<uint32_t*>(s_bin + THREADS * W);
+    for (int i = threadIdx.x; i < hp.nchunks; i += blockDim.x) s_cle[i] = hp.chunk_line_end[i];
+    hp.chunk_line_end = s_cle;
+  }
   __syncthreads();
   // reads are dealt round-robin over the whole grid: every bin then receives its words in (roughly) chunk
   // order, which keeps the aggregator's first-chunk minimum almost free of updates

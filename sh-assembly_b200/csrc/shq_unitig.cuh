@@ -15,6 +15,7 @@
 #include "shq_common.cuh"
 #include "shq_layout.cuh"
 #include <chrono>
+#include <thread>
 #include <unordered_map>
 
 #include "shq_scan.cuh"
@@ -616,11 +617,9 @@ NodeTable node_table(shq_unitigs_s* u) {
 // processDataChunk's line cursor (contig_assembly.cpp:1839-1924), restated literally: every `continue`
 // skips the two skipLines(), so the quality line is examined as a would-be header.  Collects the
 // upper-cased middle k-mer (worker rule: len/2 - K/2) of every record that passes the 'N' test.
-void collect_seeds(shq_unitigs_s* u, const char* text, size_t n) {
-  const int K = u->opts.K;
-  size_t p = 0;
+void collect_seeds_range(int K, const char* text, size_t p, size_t n, std::vector<char>* out) {
   auto read_line = [&](const char** s, size_t* len) -> bool {
-    if (p == n) return false;
+    if (p >= n) return false;
     const char* nl = (const char*)memchr(text + p, '\n', n - p);
     size_t e = nl ? (size_t)(nl - text) : n;
     *s = text + p; *len = e - p;
@@ -628,26 +627,58 @@ void collect_seeds(shq_unitigs_s* u, const char* text, size_t n) {
     return true;
   };
   const char* line; size_t ll; const char* seq; size_t sl;
-  std::string kmer;
+  char kmer[1024];
   while (read_line(&line, &ll)) {
     if (ll == 0 || line[0] != '@') continue;
     if (!read_line(&seq, &sl)) break;
     if ((int)sl < K) { const char* t; size_t tl; read_line(&t, &tl); read_line(&t, &tl); continue; }
     int seq_len = (int)sl, middle = seq_len / 2 - K / 2;
     if (middle <= seq_len - K) {
-      kmer.assign(seq + middle, K);
       bool hasN = false;
-      for (auto& c : kmer) { if (c > 0x60) c -= 32; if (c == 'N') hasN = true; }
+      for (int i = 0; i < K; i++) { char c = seq[middle + i]; if (c > 0x60) c -= 32; if (c == 'N') hasN = true; kmer[i] = c; }
       if (hasN) continue;
       // the count / traveled tests happen on the device; rejected seeds `continue` in the reference too,
       // i.e. without skipLines(2) -- but so does every accepted-then-skipped path except full processing.
       // A seed that is processed ends with skipLines(2); one that is rejected does not.  Which of the two
       // applies is only known on the device, so the cursor follows the processed path here (regular
       // 4-line records make both paths parse identically unless a quality line starts with '@').
-      u->seeds.insert(u->seeds.end(), kmer.begin(), kmer.end());
+      out->insert(out->end(), kmer, kmer + K);
     }
     const char* t; size_t tl; read_line(&t, &tl); read_line(&t, &tl);
   }
+}
+
+// Record start at or after `from`: a line starting with '@' whose line+2 starts with '+', the test
+// fastq_read_parts itself uses to cut chunks (cqf/CQF_mt.h:796-806).
+size_t find_record_start(const char* text, size_t from, size_t n) {
+  size_t p = from;
+  if (p > 0) { const char* nl = (const char*)memchr(text + p - 1, '\n', n - p + 1); if (!nl) return n; p = (size_t)(nl - text) + 1; }
+  for (int tries = 0; tries < 8 && p < n; tries++) {
+    size_t l0 = p;
+    const char* a = (const char*)memchr(text + l0, '\n', n - l0); if (!a) return n;
+    size_t l1 = (size_t)(a - text) + 1;
+    const char* b = l1 < n ? (const char*)memchr(text + l1, '\n', n - l1) : nullptr; if (!b) return n;
+    size_t l2 = (size_t)(b - text) + 1;
+    if (text[l0] == '@' && l2 < n && text[l2] == '+') return l0;
+    p = l1;
+  }
+  return n;
+}
+
+void collect_seeds(shq_unitigs_s* u, const char* text, size_t n) {
+  const int K = u->opts.K;
+  unsigned hw = std::thread::hardware_concurrency();
+  int T = (int)std::min<unsigned>(hw ? hw : 1, 8);
+  if (n < ((size_t)1 << 20) || T <= 1) { collect_seeds_range(K, text, 0, n, &u->seeds); return; }
+  std::vector<size_t> starts(T + 1, n);
+  starts[0] = 0;
+  for (int i = 1; i < T; i++) starts[i] = find_record_start(text, n / T * i, n);
+  for (int i = 1; i <= T; i++) if (starts[i] < starts[i - 1]) starts[i] = starts[i - 1];
+  std::vector<std::vector<char>> parts(T);
+  std::vector<std::thread> th;
+  for (int i = 0; i < T; i++) th.emplace_back(collect_seeds_range, K, text, starts[i], starts[i + 1], &parts[i]);
+  for (auto& t : th) t.join();
+  for (auto& v : parts) u->seeds.insert(u->seeds.end(), v.begin(), v.end());
 }
 
 template <class T> void fill_u32(DevBuf& b, size_t n, uint32_t v, cudaStream_t st) {
@@ -805,12 +836,18 @@ void unitigs_build_impl(shq_unitigs_s* u) {
         for (auto& b : kv.second)
           if (a.first != b.first && b.second != kNil) partners[a.first].push_back(b.second);
     std::vector<uint32_t> t_explored(nu, 0xFFFFFFFFu);
+    std::vector<uint64_t> has_partner(((size_t)u->cap + 63) / 64, 0);
+    for (auto& kv : partners) has_partner[kv.first >> 6] |= 1ULL << (kv.first & 63);
     for (uint32_t i = 0; i < n_seeds; i++) {
       uint32_t r = seed_root[i];
       if (r == kNil || r >= nu) continue;
+      if (t_explored[r] != 0xFFFFFFFFu) continue;                 // component already explored: nothing to decide
       bool blocked = false;
-      auto it = partners.find(seed_node[i]);
-      if (it != partners.end()) for (uint32_t pr : it->second) if (pr != r && pr < nu && t_explored[pr] < i) blocked = true;
+      uint32_t sn = seed_node[i];
+      if ((has_partner[sn >> 6] >> (sn & 63)) & 1) {
+        auto it = partners.find(sn);
+        if (it != partners.end()) for (uint32_t pr : it->second) if (pr != r && pr < nu && t_explored[pr] < i) blocked = true;
+      }
       if (!blocked && t_explored[r] == 0xFFFFFFFFu) t_explored[r] = i;
     }
     for (uint32_t i = 0; i < nu; i++) keep[i] = roots[i] < nu && t_explored[roots[i]] != 0xFFFFFFFFu;
@@ -849,10 +886,11 @@ void unitigs_build_impl(shq_unitigs_s* u) {
         std::string s(seq.data() + so, seqlen[i]);
         std::string r = rc_str(s);
         bool flip = r < s;
-        std::vector<uint32_t> c(kc.begin() + ko, kc.begin() + ko + klen[i]);
-        std::sort(c.begin(), c.end());
-        size_t m = c.size() / 2;
-        double med = c.size() % 2 ? (double)c[m] : (c[m - 1] + c[m]) / 2.0;
+        uint32_t* c0 = kc.data() + ko; size_t cn = klen[i];       // median in place (counts are not needed afterwards)
+        size_t m = cn / 2;
+        std::nth_element(c0, c0 + m, c0 + cn);
+        double med = c0[m];
+        if (cn % 2 == 0) { uint32_t lo = *std::max_element(c0, c0 + m); med = (lo + c0[m]) / 2.0; }
         recs.push_back(Rec{flip ? r : s, (int)med, flip, i});
       }
       so += seqlen[i]; ko += klen[i];

@@ -585,6 +585,35 @@ __global__ void fill_u32_kernel(uint32_t* p, uint32_t v, size_t n) { size_t i = 
 
 }  // namespace shq
 
+// Seed candidates on the device: the middle k-mer (worker rule, len/2 - K/2) of every record of a REGULAR chunk
+// (every record is 4 lines, header starts with '@').  One slot of K bytes per read, slot[0] = 0 when the read has no
+// seed (too short, or an 'N' in the seed).  *irregular is raised when the reference's line cursor
+// (contig_assembly.cpp:1843-1921, whose `continue`s skip skipLines(2)) could parse the chunk differently:
+// a header not starting with '@', or an N-seed whose quality line starts with '@'.
+__global__ void seed_extract_kernel(const char* __restrict__ text, const uint32_t* __restrict__ nl_pos, uint32_t n_reads, int K,
+                                    char* __restrict__ seeds, int* __restrict__ irregular) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  uint32_t h0 = r ? nl_pos[4 * (size_t)r - 1] + 1 : 0;
+  uint32_t s = nl_pos[4 * (size_t)r] + 1, e = nl_pos[4 * (size_t)r + 1];
+  uint32_t q0 = nl_pos[4 * (size_t)r + 2] + 1, q1 = nl_pos[4 * (size_t)r + 3];
+  char* out = seeds + (size_t)r * K;
+  out[0] = 0;
+  if (nl_pos[4 * (size_t)r] == h0 || text[h0] != '@') { *irregular = 1; return; }     // empty or foreign header line
+  int len = (int)(e - s);
+  if (len < K) return;
+  int middle = len / 2 - K / 2;
+  if (middle > len - K) return;
+  bool hasN = false;
+  for (int i = 0; i < K; i++) {
+    signed char c = (signed char)text[s + middle + i];
+    if (c > 0x60) c -= 32;                                   // to_upper_DNA, base/Utility.h:120-155
+    if (c == 'N') hasN = true;
+    out[i] = (char)c;
+  }
+  if (hasN) { out[0] = 0; if (q1 > q0 && text[q0] == '@') *irregular = 1; }
+}
+
 // ============================================================ host side ======
 struct shq_unitigs_s {
   shq_t h = nullptr;
@@ -594,7 +623,8 @@ struct shq_unitigs_s {
       unitig_of_oid, u_head, u_seqlen, u_klen, seq, kcounts, links, parent, reached, keep, d_seeds, d_text, misc, aux2, v_node, v_slot, v_n, v_out,
       seed_node, seed_root, roots;
   uint32_t victim_cap = 0;
-  std::vector<char> seeds;        // host: K bytes per accepted seed candidate
+  std::vector<char> seeds;        // host scratch (irregular chunks only)
+  shq::DevBuf d_seed_slots; size_t n_seed_slots = 0;   // device: K bytes per seed candidate, in read order
   bool built = false;
   // results (host)
   std::vector<std::string> seqs; std::vector<int> km; std::vector<std::vector<int>> after, before;
@@ -780,14 +810,11 @@ void unitigs_build_impl(shq_unitigs_s* u) {
   unitig_links_kernel<<<cdiv((size_t)nu * 2, 128), 128, 0, st>>>(T, im, LA, K, h->hb, (uint32_t)u->opts.abundance_min, nu, u->u_head.as<uint32_t>(),
                                                                u->tail_of.as<uint32_t>(), u->uid_of_head.as<uint32_t>(),
                                                                u->unitig_of_oid.as<uint32_t>(), u->links.as<int>(), u->parent.as<uint32_t>()); L++;
-  uint32_t n_seeds = (uint32_t)(u->seeds.size() / K);
+  uint32_t n_seeds = (uint32_t)u->n_seed_slots;
   std::vector<uint32_t> seed_node(n_seeds), seed_root(n_seeds);
   if (n_seeds) {
-    u->d_seeds.reserve(u->seeds.size());
-    SHQ_CUDA(cudaMemcpyAsync(u->d_seeds.p, u->seeds.data(), u->seeds.size(), cudaMemcpyHostToDevice, st));
-    h->stats.h2d_bytes += u->seeds.size();
     u->seed_node.reserve((size_t)n_seeds * 4); u->seed_root.reserve((size_t)n_seeds * 4);
-    seeds_kernel<<<cdiv(n_seeds, 128), 128, 0, st>>>(T, u->d_seeds.as<char>(), n_seeds, K, (uint32_t)u->opts.solid_abundance_min,
+    seeds_kernel<<<cdiv(n_seeds, 128), 128, 0, st>>>(T, u->d_seed_slots.as<char>(), n_seeds, K, (uint32_t)u->opts.solid_abundance_min,
                                                     (uint32_t)u->opts.solid_abundance_max, u->unitig_of_oid.as<uint32_t>(), u->parent.as<uint32_t>(),
                                                     u->seed_node.as<uint32_t>(), u->seed_root.as<uint32_t>()); L++;
     SHQ_CUDA(cudaMemcpyAsync(seed_node.data(), u->seed_node.p, (size_t)n_seeds * 4, cudaMemcpyDeviceToHost, st));
@@ -985,21 +1012,42 @@ int shq_unitigs_add_reads(shq_unitigs_t u, const char* text, size_t n) {
     uint64_t& L = h->stats.kernels_launched;
     if (a.n >= ((size_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "chunk too large");
     DbgTimer tm(st);
-    collect_seeds(u, a.t, a.n);
-    tm.lap("add_reads: collect_seeds");
     u->d_text.reserve(a.n + 64);
     SHQ_CUDA(cudaMemcpyAsync(u->d_text.p, a.t, a.n, cudaMemcpyHostToDevice, st));
     h->stats.h2d_bytes += a.n;
-    unsigned ntiles = cdiv(a.n, kNlTile);
-    h->d_nl_tiles.reserve((size_t)(ntiles + 1) * 4);
-    nl_count_kernel<<<ntiles, kNlThreads, 0, st>>>(u->d_text.as<char>(), a.n, h->d_nl_tiles.as<uint32_t>()); L++;
-    h->d_misc.reserve(256);
-    exclusive_scan_inplace<SumU32>(h->d_nl_tiles.as<uint32_t>(), ntiles, h->d_scan_scratch, st, h->d_misc.as<uint32_t>(), &L);
-    uint32_t n_lines = read_scalar(h, h->d_misc.as<uint32_t>());
-    if ((n_lines & 3) || a.t[a.n - 1] != '\n') SHQ_FAIL(SHQ_ERR_MALFORMED, "chunk holds %u lines / no trailing newline", n_lines);
-    h->d_nl_pos.reserve((size_t)(n_lines + 4) * 4);
-    nl_write_kernel<<<ntiles, kNlThreads, 0, st>>>(u->d_text.as<char>(), a.n, h->d_nl_tiles.as<uint32_t>(), h->d_nl_pos.as<uint32_t>()); L++;
-    EnumParams ep{u->d_text.as<char>(), h->d_nl_pos.as<uint32_t>(), n_lines / 4, u->opts.K, h->hb, (uint32_t)u->opts.abundance_min};
+    if (a.t[a.n - 1] != '\n') SHQ_FAIL(SHQ_ERR_MALFORMED, "chunk has no trailing newline");
+    uint32_t n_lines = index_lines(h, u->d_text.as<char>(), a.n);
+    if (n_lines & 3) SHQ_FAIL(SHQ_ERR_MALFORMED, "chunk holds %u lines, not a multiple of 4", n_lines);
+    const uint32_t n_reads = n_lines / 4;
+    const int K = u->opts.K;
+    {   // seed candidates: device kernel for regular chunks, the literal host cursor otherwise
+      size_t need = (u->n_seed_slots + n_reads + 1) * (size_t)K;
+      if (need > u->d_seed_slots.cap) {
+        shq::DevBuf nb; nb.reserve(std::max(need * 2, (size_t)1 << 24));
+        if (u->n_seed_slots) SHQ_CUDA(cudaMemcpyAsync(nb.p, u->d_seed_slots.p, u->n_seed_slots * (size_t)K, cudaMemcpyDeviceToDevice, st));
+        SHQ_CUDA(cudaStreamSynchronize(st));
+        u->d_seed_slots.release(); u->d_seed_slots = nb;
+      }
+      u->misc.reserve(256);
+      int* d_irr = u->misc.as<int>() + 8;
+      SHQ_CUDA(cudaMemsetAsync(d_irr, 0, 4, st));
+      if (n_reads) {
+        seed_extract_kernel<<<cdiv(n_reads, 128), 128, 0, st>>>(u->d_text.as<char>(), h->d_nl_pos.as<uint32_t>(), n_reads, K,
+                                                              u->d_seed_slots.as<char>() + u->n_seed_slots * (size_t)K, d_irr); L++;
+      }
+      if (read_scalar(h, d_irr)) {
+        u->seeds.clear();
+        collect_seeds(u, a.t, a.n);
+        size_t m = u->seeds.size() / K;
+        if (m > n_reads) SHQ_FAIL(SHQ_ERR_MALFORMED, "irregular chunk yields more seeds than records");
+        if (m) SHQ_CUDA(cudaMemcpyAsync(u->d_seed_slots.as<char>() + u->n_seed_slots * (size_t)K, u->seeds.data(), m * (size_t)K, cudaMemcpyHostToDevice, st));
+        SHQ_CUDA(cudaStreamSynchronize(st));
+        u->n_seed_slots += m;
+      } else {
+        u->n_seed_slots += n_reads;
+      }
+    }
+    EnumParams ep{u->d_text.as<char>(), h->d_nl_pos.as<uint32_t>(), n_reads, u->opts.K, h->hb, (uint32_t)u->opts.abundance_min};
     ImageView im{h->image.as<uint8_t>(), h->nblocks, h->xnslots, 0};
     size_t smem = (size_t)kEnumWarps * ((kTilePos + 1) * 16 + 264 + 520);
     SHQ_CUDA(cudaFuncSetAttribute(enum_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1044,7 +1092,7 @@ void shq_unitigs_free(shq_unitigs_t u) {
   cudaSetDevice(u->h->device);
   shq::DevBuf* bufs[] = {&u->lo, &u->hi, &u->state, &u->count, &u->fh, &u->rh, &u->list, &u->nn, &u->aux, &u->outdeg, &u->succ, &u->smask, &u->next,
                          &u->prev, &u->jd, &u->minid, &u->jmp, &u->tail_of, &u->len_of, &u->uid_of_head, &u->unitig_of_oid, &u->u_head, &u->u_seqlen,
-                         &u->u_klen, &u->seq, &u->kcounts, &u->links, &u->parent, &u->reached, &u->keep, &u->d_seeds, &u->d_text, &u->misc, &u->aux2, &u->v_node, &u->v_slot, &u->v_n, &u->v_out, &u->seed_node, &u->seed_root, &u->roots};
+                         &u->u_klen, &u->seq, &u->kcounts, &u->links, &u->parent, &u->reached, &u->keep, &u->d_seeds, &u->d_text, &u->misc, &u->aux2, &u->v_node, &u->v_slot, &u->v_n, &u->v_out, &u->seed_node, &u->seed_root, &u->roots, &u->d_seed_slots};
   for (auto* b : bufs) b->release();
   delete u;
 }

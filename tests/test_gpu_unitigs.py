@@ -61,3 +61,23 @@ def test_unitig_invariants(po, shq):
     for hdr, s in us:
         ln = int([f for f in hdr if f.startswith("LN:i:")][0][5:])
         assert ln == len(s)
+
+
+def test_unitigs_irregular_chunk_host_cursor(po, shq):
+    """A seed with 'N' whose quality line starts with '@' derails the reference's line cursor for one record
+    (contig_assembly.cpp:1868-1871 `continue`s without skipLines); the device path detects it and replays the
+    literal host cursor for that chunk."""
+    K = 25
+    text = po.synth_fastq(G=30000, cov=30, err=0.003, L=100, seed=41)
+    recs = text.split(b"\n")
+    out = []
+    for i in range(0, len(recs) - 1, 4):
+        h, s, p, q = recs[i:i + 4]
+        if (i // 4) % 37 == 5:
+            s = s[:50] + b"N" + s[51:]
+            q = b"@" + q[1:]
+        out += [h, s, p, q]
+    text2 = b"\n".join(out) + b"\n"
+    fa_o, fa_g = run_both(po, shq, [text2], K, 19)
+    assert po.canonical_unitig_set(fa_g) == po.canonical_unitig_set(fa_o)
+    assert po.canonical_links(fa_g) == po.canonical_links(fa_o)

@@ -198,7 +198,7 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
   h->d_binoff.reserve((size_t)(n_bins + 2) * 4);
   h->d_tot.reserve((size_t)(n_bins + 2) * 4);      // scatter cursors
   h->d_chunk_keys.reserve((size_t)(nchunks + 1) * 4);
-  hp.chunk_keys = (armed && from_text) ? h->d_chunk_keys.as<uint32_t>() : nullptr;
+  hp.chunk_keys = nullptr;   // per-chunk key counts are no longer needed: nelts comes from the aggregator's occurrence totals
   SHQ_CUDA(cudaMemsetAsync(h->d_hist.p, 0, (size_t)(n_bins + 1) * 4, st));
   SHQ_CUDA(cudaMemsetAsync(h->d_chunk_keys.p, 0, (size_t)(nchunks + 1) * 4, st));
   const int G = kNumSMs * 2;
@@ -226,7 +226,11 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
   {
     Phase ph(h, &h->stats.ms_scatter);
     if (from_text) {
-      if (W == 16) {     // 1024 threads x 16 windows: same shared memory, twice the warps
+      if (W == 12) {     // direct variant: 2 CTAs x 1024 threads per SM, 12 windows per thread and round
+        size_t smem_direct = sizeof(RollTables) + (size_t)2 * n_bins * 4 + (size_t)1024 * 12 * 6 + 16 + smem_cle;
+        SHQ_CUDA(cudaFuncSetAttribute(roll_scatter_direct_kernel<1024, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_direct));
+        roll_scatter_direct_kernel<1024, 12><<<2 * kNumSMs, 1024, smem_direct, st>>>(hp, h->d_tot.as<uint32_t>(), h->d_packed.as<uint32_t>());
+      } else if (W == 16) {     // 1024 threads x 16 windows: same shared memory, twice the warps
         SHQ_CUDA(cudaFuncSetAttribute(roll_scatter_kernel<1024, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
         roll_scatter_kernel<1024, 16><<<kNumSMs, 1024, smem_scatter, st>>>(hp, h->d_tot.as<uint32_t>(), h->d_packed.as<uint32_t>());
       } else {
@@ -610,7 +614,7 @@ void init_handle(shq_handle_s* h, int qb, int hb, uint32_t seed, int device, int
   if (qb < 1 || qb > 40 || hb - qb != 8) SHQ_FAIL(SHQ_ERR_ARG, "need 1 <= qb <= 40 and hb - qb == 8 (got qb=%d hb=%d)", qb, hb);
   if (nshards < 1 || (nshards & (nshards - 1)) || shard < 0 || shard >= nshards || (1 << qb) < nshards * 64)
     SHQ_FAIL(SHQ_ERR_ARG, "bad shard %d of %d", shard, nshards);
-  if (const char* e = getenv("SHQ_SCATTER_W")) { int v = atoi(e); if (v == 16 || v == 32) g_scatter_w = v; }
+  if (const char* e = getenv("SHQ_SCATTER_W")) { int v = atoi(e); if (v == 12 || v == 16 || v == 32) g_scatter_w = v; }
   if (const char* e = getenv("SHQ_MAX_BATCH_MB")) { long v = atol(e); if (v >= 1 && v <= 3072) h->max_batch_bytes = (size_t)v << 20; }
   if (const char* e = getenv("SHQ_BIN_BITS")) { int v = atoi(e); if (v >= 4 && v <= 13) g_bin_bits = v; }
   SHQ_CUDA(cudaSetDevice(device));

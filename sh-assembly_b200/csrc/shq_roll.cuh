@@ -236,6 +236,65 @@ __global__ void __launch_bounds__(THREADS) roll_scatter_kernel(HashParams hp, ui
   }
 }
 
+// Variant without the in-round sort: keys go straight from production order to base[bin] + rank.  Needs only
+// 6 bytes of shared memory per staged key, so two CTAs of 1024 threads fit on an SM and overlap each other's
+// barrier phases (reserve / write-out) with hashing.
+// dynamic smem: RollTables + 2 * n_bins * 4 + THREADS * W * 6 (+ chunk map)
+template <int THREADS, int W>
+__global__ void __launch_bounds__(THREADS, 2) roll_scatter_direct_kernel(HashParams hp, uint32_t* __restrict__ g_cursor, uint32_t* __restrict__ packed) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RollTables* tab = reinterpret_cast<RollTables*>(smem_raw);
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw + sizeof(RollTables));
+  uint32_t* s_base = s_hist + hp.n_bins;
+  uint32_t* s_key = s_base + hp.n_bins;
+  uint16_t* s_bin = reinterpret_cast<uint16_t*>(s_key + THREADS * W);
+  roll_tables_init(tab, hp.K);
+  if (hp.chunk_line_end) {
+    uint32_t* s_cle = reinterpret_cast<uint32_t*>(s_bin + THREADS * W);
+    for (int i = threadIdx.x; i < hp.nchunks; i += blockDim.x) s_cle[i] = hp.chunk_line_end[i];
+    hp.chunk_line_end = s_cle;
+  }
+  __syncthreads();
+  Roller R;
+  R.start(&hp, tab, blockIdx.x * blockDim.x + threadIdx.x, hp.n_reads, gridDim.x * blockDim.x);
+  const uint64_t mask = hp.hb >= 64 ? ~0ULL : ((1ULL << hp.hb) - 1);
+  const uint64_t key_lo = hp.key_lo, key_hi = hp.key_hi; const int lb = hp.lb;
+  const bool whole = key_lo == 0 && key_hi > mask;
+  const uint32_t lowmask = lb >= 32 ? 0xFFFFFFFFu : ((1u << lb) - 1);
+  bool more = true;
+  int produced = 0;
+  auto emit = [&](uint64_t key, uint32_t ch) {
+    if (!whole && (key < key_lo || key >= key_hi)) return;
+    uint64_t rel = key - key_lo;
+    uint32_t bin = (uint32_t)(rel >> lb);
+    int idx = produced * THREADS + threadIdx.x;
+    s_key[idx] = ((uint32_t)rel & lowmask) | (lb >= 32 ? 0 : (ch << lb));
+    s_bin[idx] = (uint16_t)bin;
+    atomicAdd(&s_hist[bin], 1u);
+    produced++;
+  };
+  for (;;) {
+    for (int i = threadIdx.x; i < hp.n_bins; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    produced = 0;
+    while (more && produced + 4 <= W) more = R.step(mask, emit);
+    int any = __syncthreads_or(produced > 0);
+    if (!any) break;
+    for (int i = threadIdx.x; i < hp.n_bins; i += blockDim.x) {
+      uint32_t c = s_hist[i];
+      s_base[i] = c ? atomicAdd(&g_cursor[i], c) : 0;
+    }
+    __syncthreads();
+    for (int j = 0; j < produced; j++) {
+      int idx = j * THREADS + threadIdx.x;
+      uint32_t bin = s_bin[idx];
+      uint32_t rank = atomicSub(&s_hist[bin], 1u) - 1;
+      packed[s_base[bin] + rank] = s_key[idx];
+    }
+    __syncthreads();
+  }
+}
+
 // Key list (test hook / multi-GPU exchange): read r writes its keys at out[off[r] ...]; off = exclusive scan of
 // max(len-K+1, 0).  Slots that the N rule leaves unused hold the sentinel ~0.
 __global__ void read_window_counts_kernel(const uint32_t* __restrict__ nl_pos, uint32_t n_reads, int K, uint64_t* __restrict__ cnt) {

@@ -12,13 +12,19 @@ namespace shq {
 
 // ----------------------------------------------------- per-bin aggregation ---
 constexpr int kAggThreads = 512;
+constexpr int kAggWarps = kAggThreads / 32;
 constexpr int kAggTable = 8192;          // open-addressing slots per CTA (two CTAs per SM)
 constexpr int kAggMaxDistinct = 4096;    // per round (load factor <= 0.5)
 constexpr int kAggOrdCap = kAggMaxDistinct + kAggThreads;   // racing inserts may overshoot by < blockDim
 constexpr int kAggBuckets = 1024;        // bucket sort of the distinct keys
+constexpr int kAggU = 8;                 // words per lane and warp tile
+constexpr int kAggWarpTile = 32 * kAggU; // a warp streams its share of the bin in tiles of 256 words
 constexpr uint32_t kAggEmpty = 0xFFFFFFFFu;
-// t_key, t_cnt, t_chk (u32 each) + slot order (u16) + bucket counters (u32)
-constexpr size_t kAggSmemBytes = (size_t)kAggTable * 12 + (size_t)kAggOrdCap * 2 + (size_t)kAggBuckets * 4;
+// t_key, t_cnt (u32), t_chk (u16), bucket counters (u32), list of new slots (u16), then one region shared by the
+// per-warp pending lists (insert phase) and the slot order (sort phase)
+constexpr size_t kAggPendBytes = (size_t)kAggWarps * kAggWarpTile * 4;
+constexpr size_t kAggSmemBytes = (size_t)kAggTable * 10 + (size_t)kAggBuckets * 4 + (size_t)kAggOrdCap * 2 +
+                                 (kAggPendBytes > (size_t)kAggOrdCap * 2 ? kAggPendBytes : (size_t)kAggOrdCap * 2);
 
 __device__ __forceinline__ uint32_t agg_hash(uint32_t k) { return (k * 2654435761u) >> (32 - 13); }
 
@@ -32,51 +38,111 @@ struct AggOut {
   size_t sub_stride;        // outputs of sub-range s live at [s * sub_stride + bin_off[p] + i]
 };
 
-// Streams the bin through the shared-memory table.  Compile-time flags strip everything a plain batch
-// does not need: FILT = chunk-range / key-sub-range filters, CHUNK = first-chunk minimum, SPLIT = two counters.
+struct AggTable {
+  uint32_t* key; uint32_t* cnt; uint16_t* chk; uint32_t* bkt; uint16_t* fresh;
+  uint32_t* ndist; volatile uint32_t* overflow; int* split_overflow;
+  uint32_t relmask; int bshift;       // bucket of a key: (key & relmask) >> bshift
+};
+
+// 16-bit minimum on a shared-memory half word (rarely taken: bins receive their words in chunk order)
+__device__ __forceinline__ void agg_chunk_min(uint16_t* chk, uint32_t h, uint32_t ch) {
+  if (ch >= chk[h]) return;
+  uint32_t* wp = reinterpret_cast<uint32_t*>(chk) + (h >> 1);
+  const int sh = (h & 1) * 16;
+  uint32_t old = *wp;
+  for (;;) {
+    if (((old >> sh) & 0xFFFFu) <= ch) return;
+    uint32_t nv = (old & ~(0xFFFFu << sh)) | (ch << sh);
+    uint32_t seen = atomicCAS(wp, old, nv);
+    if (seen == old) return;
+    old = seen;
+  }
+}
+
+template <bool SPLIT, bool CHUNK>
+__device__ __forceinline__ void agg_count(const AggTable& T, uint32_t h, uint32_t ch, bool second) {
+  if (SPLIT) {
+    uint32_t old = atomicAdd(&T.cnt[h], second ? 0x10000u : 1u);
+    if ((second ? (old >> 16) : (old & 0xFFFFu)) >= 0xFFFEu) *T.split_overflow = 1;
+  } else {
+    atomicAdd(&T.cnt[h], 1u);
+  }
+  if (CHUNK && !second) agg_chunk_min(T.chk, h, ch);
+}
+
+// Streams the bin through the shared-memory table.  Every warp works on its own tiles of 256 words:
+//   pass 1 (all lanes, no loop): one probe; a word whose key sits in its home slot is counted on the spot
+//           (the common case at 30-100x coverage), every other word is appended to the warp's pending list;
+//   pass 2 (dense over the pending list): the full insert -- linear probing, CAS on an empty slot.
+// Other warps may insert while a warp probes: a probe then sees either "empty" (-> pending -> found in pass 2)
+// or the key itself, both correct.  Compile-time flags strip everything a plain batch does not need:
+// FILT = chunk-range / key-sub-range filters, CHUNK = first-chunk minimum, SPLIT = two counters.
 template <bool SPLIT, bool CHUNK, bool FILT>
 __device__ __forceinline__ void agg_insert_pass(const uint32_t* __restrict__ packed, uint32_t beg, uint32_t end, int lb, uint32_t lowmask,
                                                 uint32_t chunk_lo, uint32_t chunk_hi, uint32_t cstar, int sub_bits, uint32_t r,
-                                                uint32_t* t_key, uint32_t* t_cnt, uint32_t* t_chk, uint32_t* s_ndist,
-                                                volatile uint32_t* s_overflow, int* split_overflow, uint32_t* occ1, uint32_t* occ2) {
+                                                const AggTable& T, uint32_t* s_pend, uint32_t* occ1, uint32_t* occ2) {
   uint32_t my_occ = 0, my_occ2 = 0;
-  constexpr int U = 4;                               // loads of U strided words are issued before any is consumed
-  for (uint32_t i0 = beg + threadIdx.x; i0 < end; i0 += blockDim.x * U) {
-    uint32_t wv[U];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t* pend = s_pend + wid * kAggWarpTile;
+  for (uint32_t t0 = beg + wid * kAggWarpTile; t0 < end; t0 += kAggWarps * kAggWarpTile) {
+    uint32_t wv[kAggU];
 #pragma unroll
-    for (int u = 0; u < U; u++) { uint32_t i = i0 + u * blockDim.x; wv[u] = i < end ? __ldg(&packed[i]) : 0; }
+    for (int u = 0; u < kAggU; u++) { uint32_t i = t0 + u * 32 + lane; wv[u] = i < end ? __ldg(&packed[i]) : 0; }
+    uint32_t np = 0;
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      if (i0 + u * blockDim.x >= end) break;
+    for (int u = 0; u < kAggU; u++) {
       const uint32_t w = wv[u];
+      bool live = t0 + u * 32 + lane < end;
       const uint32_t kl = w & lowmask;
       uint32_t ch = 0;
       if (CHUNK || FILT || SPLIT) ch = lb >= 32 ? 0 : (w >> lb);
       if (FILT) {
-        if (ch < chunk_lo || ch > chunk_hi) continue;
-        if (sub_bits && (kl >> (lb - sub_bits)) != r) continue;
+        if (ch < chunk_lo || ch > chunk_hi) live = false;
+        if (sub_bits && (kl >> (lb - sub_bits)) != r) live = false;
       }
       const bool second = SPLIT && ch > cstar;
-      if (FILT || SPLIT) { if (second) my_occ2++; else my_occ++; }
-      uint32_t h = agg_hash(kl);
-      for (;;) {
-        uint32_t cur = t_key[h];
-        if (cur == kl) break;
-        if (cur == kAggEmpty) {
-          if (*s_overflow) break;
-          uint32_t old = atomicCAS(&t_key[h], kAggEmpty, kl);
-          if (old == kAggEmpty) { if (atomicAdd(s_ndist, 1u) >= (uint32_t)kAggMaxDistinct) *s_overflow = 1; break; }
-          if (old == kl) break;
+      if (FILT || SPLIT) { if (live) { if (second) my_occ2++; else my_occ++; } }
+      const uint32_t h = agg_hash(kl);
+      const bool hit = live && T.key[h] == kl;
+      if (hit) agg_count<SPLIT, CHUNK>(T, h, ch, second);
+      const bool miss = live && !hit;
+      const uint32_t m = __ballot_sync(0xffffffffu, miss);
+      if (miss) pend[np + __popc(m & ((1u << lane) - 1))] = w;
+      np += __popc(m);
+    }
+    np = __shfl_sync(0xffffffffu, np, 0);
+    // np is the same in every lane: a warp-uniform loop with one structured branch inside, so the warp
+    // reconverges after every group of 32 pending words
+    for (uint32_t i0 = 0; i0 < np; i0 += 32) {
+      const uint32_t i = i0 + lane;
+      if (i < np) {
+        const uint32_t w = pend[i];
+        const uint32_t kl = w & lowmask;
+        uint32_t ch = 0;
+        if (CHUNK || SPLIT) ch = lb >= 32 ? 0 : (w >> lb);
+        const bool second = SPLIT && ch > cstar;
+        uint32_t h = agg_hash(kl);
+        bool placed = true;
+        for (;;) {
+          uint32_t cur = T.key[h];
+          if (cur == kl) break;
+          if (cur == kAggEmpty) {
+            if (*T.overflow) { placed = false; break; }
+            uint32_t old = atomicCAS(&T.key[h], kAggEmpty, kl);
+            if (old == kAggEmpty) {
+              uint32_t idx = atomicAdd(T.ndist, 1u);
+              if (idx >= (uint32_t)kAggMaxDistinct) *T.overflow = 1;
+              if (idx < (uint32_t)kAggOrdCap) T.fresh[idx] = (uint16_t)h;
+              atomicAdd(&T.bkt[(kl & T.relmask) >> T.bshift], 1u);
+              break;
+            }
+            if (old == kl) break;
+          }
+          h = (h + 1) & (kAggTable - 1);
         }
-        h = (h + 1) & (kAggTable - 1);
+        if (placed) agg_count<SPLIT, CHUNK>(T, h, ch, second);
       }
-      if (SPLIT) {
-        uint32_t old = atomicAdd(&t_cnt[h], second ? 0x10000u : 1u);
-        if ((second ? (old >> 16) : (old & 0xFFFFu)) >= 0xFFFEu) *split_overflow = 1;
-      } else {
-        atomicAdd(&t_cnt[h], 1u);
-      }
-      if (CHUNK && !second) { if (ch < t_chk[h]) atomicMin(&t_chk[h], ch); }   // first chunk: native 32-bit minimum
+      __syncwarp();
     }
   }
   if (FILT || SPLIT) { atomicAdd(occ1, my_occ); if (SPLIT) atomicAdd(occ2, my_occ2); }
@@ -90,15 +156,17 @@ __device__ __forceinline__ void agg_insert_pass(const uint32_t* __restrict__ pac
 // Output (sorted by key) goes to out[sub * sub_stride + bin_off[p] + i].  A sub-range with more than
 // kAggMaxDistinct distinct keys is re-streamed in 2^k narrower key ranges.
 template <bool SPLIT>
-__global__ void __launch_bounds__(kAggThreads) bin_aggregate_kernel(
+__global__ void __launch_bounds__(kAggThreads, 2) bin_aggregate_kernel(
     const uint32_t* __restrict__ packed, const uint32_t* __restrict__ bin_off, int lb, uint64_t key_lo,
     uint32_t chunk_lo, uint32_t chunk_hi, uint32_t cstar, AggOut o) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* t_key = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* t_cnt = t_key + kAggTable;
-  uint32_t* t_chk = t_cnt + kAggTable;
-  uint32_t* s_bkt = t_chk + kAggTable;
-  uint16_t* s_ord = reinterpret_cast<uint16_t*>(s_bkt + kAggBuckets);    // table slots in key order
+  uint16_t* t_chk = reinterpret_cast<uint16_t*>(t_cnt + kAggTable);
+  uint32_t* s_bkt = reinterpret_cast<uint32_t*>(t_chk + kAggTable);
+  uint16_t* s_new = reinterpret_cast<uint16_t*>(s_bkt + kAggBuckets);    // table slots in order of insertion
+  uint32_t* s_pend = reinterpret_cast<uint32_t*>(s_new + kAggOrdCap);     // insert phase: per-warp pending lists
+  uint16_t* s_ord = reinterpret_cast<uint16_t*>(s_pend);                  // sort phase: table slots in key order
   __shared__ uint32_t s_ndist, s_nocc, s_nocc2, s_overflow, s_na, s_nb;
 
   const uint32_t p = blockIdx.x >> o.fixed_bits;
@@ -114,17 +182,24 @@ __global__ void __launch_bounds__(kAggThreads) bin_aggregate_kernel(
 restart:
   written = 0; written2 = 0; occ_total = 0; occ_total2 = 0;
   for (uint32_t r = fsub << (sub_bits - o.fixed_bits); r < ((fsub + 1) << (sub_bits - o.fixed_bits)); r++) {
-    for (int i = threadIdx.x; i < kAggTable; i += blockDim.x) { t_key[i] = kAggEmpty; t_cnt[i] = 0; }
-    if (want_chunk) for (int i = threadIdx.x; i < kAggTable; i += blockDim.x) t_chk[i] = 0xFFFFFFFFu;
-    for (int i = threadIdx.x; i < kAggBuckets; i += blockDim.x) s_bkt[i] = 0;
+    {
+      uint4* k4 = reinterpret_cast<uint4*>(t_key);
+      uint4* c4 = reinterpret_cast<uint4*>(t_cnt);
+      const uint4 e4 = make_uint4(kAggEmpty, kAggEmpty, kAggEmpty, kAggEmpty), z4 = make_uint4(0, 0, 0, 0);
+      for (int i = threadIdx.x; i < kAggTable / 4; i += blockDim.x) { k4[i] = e4; c4[i] = z4; }
+      if (want_chunk) { uint4* h4 = reinterpret_cast<uint4*>(t_chk); for (int i = threadIdx.x; i < kAggTable / 8; i += blockDim.x) h4[i] = e4; }
+      for (int i = threadIdx.x; i < kAggBuckets; i += blockDim.x) s_bkt[i] = 0;
+    }
     if (threadIdx.x == 0) { s_ndist = 0; s_nocc = 0; s_nocc2 = 0; s_overflow = 0; s_na = 0; s_nb = 0; }
     __syncthreads();
+    const int bits = lb - sub_bits;                    // key_low bits that vary inside this round
+    const int bshift = bits > 10 ? bits - 10 : 0;
+    const uint32_t relmask = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1);
     {
       const uint32_t max_chunk = lb >= 32 ? 0u : (0xFFFFFFFFu >> lb);
       const bool filt = sub_bits != 0 || chunk_lo != 0 || chunk_hi < max_chunk;   // sub_bits includes the grid's fixed bits
-      volatile uint32_t* ovf = &s_overflow;
-#define SHQ_AGG_CALL(S, C, F) agg_insert_pass<S, C, F>(packed, beg, end, lb, lowmask, chunk_lo, chunk_hi, cstar, sub_bits, r, t_key, t_cnt, t_chk, \
-                                                       &s_ndist, ovf, o.split_overflow, &s_nocc, &s_nocc2)
+      AggTable T{t_key, t_cnt, t_chk, s_bkt, s_new, &s_ndist, &s_overflow, o.split_overflow, relmask, bshift};
+#define SHQ_AGG_CALL(S, C, F) agg_insert_pass<S, C, F>(packed, beg, end, lb, lowmask, chunk_lo, chunk_hi, cstar, sub_bits, r, T, s_pend, &s_nocc, &s_nocc2)
       if (SPLIT) { if (filt) SHQ_AGG_CALL(SPLIT, false, true); else SHQ_AGG_CALL(SPLIT, false, false); }   // no first chunks: the split is the last tracked round
       else if (want_chunk) { if (filt) SHQ_AGG_CALL(false, true, true); else SHQ_AGG_CALL(false, true, false); }
       else { if (filt) SHQ_AGG_CALL(false, false, true); else SHQ_AGG_CALL(false, false, false); }
@@ -132,15 +207,9 @@ restart:
     }
     __syncthreads();
     if (*reinterpret_cast<volatile uint32_t*>(&s_overflow)) { sub_bits++; __syncthreads(); goto restart; }
-    // ---- bucket sort of the occupied slots by key (keys are hash values: ~nd/1024 keys per bucket)
-    const int bits = lb - sub_bits;                    // key_low bits that vary inside this round
-    const int bshift = bits > 10 ? bits - 10 : 0;
-    const uint32_t relmask = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1);
-    for (int i = threadIdx.x; i < kAggTable; i += blockDim.x) {
-      uint32_t k = t_key[i];
-      if (k != kAggEmpty) atomicAdd(&s_bkt[(k & relmask) >> bshift], 1u);
-    }
-    __syncthreads();
+    // ---- bucket sort of the occupied slots by key (keys are hash values: ~nd/1024 keys per bucket); the bucket
+    // counters were filled while inserting, the occupied slots are listed in s_new
+    const uint32_t nd = s_ndist;
     constexpr int PER = kAggBuckets / kAggThreads;
     {
       uint32_t v[PER], sum = 0;
@@ -152,12 +221,12 @@ restart:
       for (int j = 0; j < PER; j++) { s_bkt[threadIdx.x * PER + j] = ex; ex += v[j]; }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kAggTable; i += blockDim.x) {
-      uint32_t k = t_key[i];
-      if (k != kAggEmpty) s_ord[atomicAdd(&s_bkt[(k & relmask) >> bshift], 1u)] = (uint16_t)i;
+    for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) {
+      uint32_t slot = s_new[i];
+      uint32_t k = t_key[slot];
+      s_ord[atomicAdd(&s_bkt[(k & relmask) >> bshift], 1u)] = (uint16_t)slot;
     }
     __syncthreads();
-    const uint32_t nd = s_ndist;
 #pragma unroll
     for (int j = 0; j < PER; j++) {                    // s_bkt[b] is now the END of bucket b: insertion sort inside the bucket
       int b = threadIdx.x * PER + j;
@@ -181,7 +250,7 @@ restart:
         size_t oo = obase + written + i;
         o.keys[oo] = key_lo + (((uint64_t)p << lb) | t_key[h]);
         o.counts[oo] = t_cnt[h];
-        if (o.chunk) o.chunk[oo] = (uint16_t)t_chk[h];
+        if (o.chunk) o.chunk[oo] = t_chk[h];
         if (do_hist) atomicAdd(&s_bkt[t_chk[h] & (kAggBuckets - 1)], 1u);
       }
     } else {

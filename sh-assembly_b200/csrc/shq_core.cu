@@ -71,22 +71,51 @@ struct shq_handle_s {
 
   shq_stats stats;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> ev_pool;                 // free timing events
+  struct PendingPhase { cudaEvent_t e0, e1; double* acc; };
+  std::vector<PendingPhase> ev_pending;             // recorded, not yet read
 };
 
 namespace {
 
+// Phase timing without host round trips: a pair of pooled events is recorded around the phase and the
+// elapsed time is added to the statistic when the statistics are read (or the pool runs dry).
+struct PhaseRec { cudaEvent_t e0, e1; double* acc; };
+void resolve_phases(shq_handle_s* h);
 struct Phase {
-  shq_handle_s* h; double* acc;
-  Phase(shq_handle_s* h_, double* acc_) : h(h_), acc(acc_) { cudaEventRecord(h->ev0, h->stream); }
-  ~Phase() {
-    cudaEventRecord(h->ev1, h->stream);
-    cudaEventSynchronize(h->ev1);
-    float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-    *acc += ms;
-  }
+  shq_handle_s* h; cudaEvent_t e0, e1; double* acc;
+  Phase(shq_handle_s* h_, double* acc_);
+  ~Phase();
 };
 
 inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+void resolve_phases(shq_handle_s* h) {
+  for (auto& p : h->ev_pending) {
+    if (cudaEventSynchronize(p.e1) == cudaSuccess) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) *p.acc += ms;
+    }
+    h->ev_pool.push_back(p.e0); h->ev_pool.push_back(p.e1);
+  }
+  h->ev_pending.clear();
+}
+static cudaEvent_t phase_event(shq_handle_s* h) {
+  if (h->ev_pool.empty()) {
+    if (h->ev_pending.size() >= 256) resolve_phases(h);
+    if (h->ev_pool.empty()) { cudaEvent_t e; SHQ_CUDA(cudaEventCreate(&e)); return e; }
+  }
+  cudaEvent_t e = h->ev_pool.back(); h->ev_pool.pop_back();
+  return e;
+}
+Phase::Phase(shq_handle_s* h_, double* acc_) : h(h_), acc(acc_) {
+  e0 = phase_event(h); e1 = phase_event(h);
+  cudaEventRecord(e0, h->stream);
+}
+Phase::~Phase() {
+  cudaEventRecord(e1, h->stream);
+  h->ev_pending.push_back({e0, e1, acc});
+}
 
 void check_err_flag(shq_handle_s* h) {
   int e = 0;
@@ -119,6 +148,17 @@ T read_scalar(shq_handle_s* h, const T* d) {
   return *p;
 }
 
+// two device words (possibly in different buffers) with one host round trip
+template <class T, class U>
+void read_pair(shq_handle_s* h, const T* da, T* a, const U* db, U* b) {
+  char* p = (char*)pinned(h, 32);
+  SHQ_CUDA(cudaMemcpyAsync(p, da, sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+  SHQ_CUDA(cudaMemcpyAsync(p + 16, db, sizeof(U), cudaMemcpyDeviceToHost, h->stream));
+  SHQ_CUDA(cudaStreamSynchronize(h->stream));
+  h->stats.d2h_bytes += sizeof(T) + sizeof(U);
+  memcpy(a, p, sizeof(T)); memcpy(b, p + 16, sizeof(U));
+}
+
 // ---------------------------------------------------------------------------
 // A "run" = sorted distinct (key, count[, first chunk]) produced from one batch of binned keys.
 struct BatchBins {
@@ -129,7 +169,6 @@ struct BatchBins {
 };
 struct Run { DevBuf* keys; DevBuf* counts; DevBuf* chunk; size_t n = 0; uint64_t occ = 0; };
 
-int g_scatter_w = 16;           // keys staged per thread and round (tunable: SHQ_SCATTER_W)
 int g_bin_bits = 0;             // 0 = automatic (tunable: SHQ_BIN_BITS)
 
 int pick_bin_bits(shq_handle_s* h, uint64_t est_keys, int chunk_bits_needed) {
@@ -180,7 +219,8 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
     h->stats.h2d_bytes += (size_t)nchunks * 8;
     chunk_validate_kernel<<<cdiv(nchunks, 128), 128, 0, st>>>(d_text, h->d_nl_pos.as<uint32_t>(), n_lines, h->d_chunk_ends.as<uint64_t>(),
                                                             nchunks, h->d_chunk_line_end.as<uint32_t>(), h->d_err); L++;
-    check_err_flag(h);
+    // the device error flag is read together with the key total below (the kernels in between only index
+    // nl_pos[0 .. n_lines), whatever the text holds)
     if (n_lines & 3) SHQ_FAIL(SHQ_ERR_MALFORMED, "batch holds %u lines, not a multiple of 4", n_lines);
     hp.text = d_text; hp.nl_pos = h->d_nl_pos.as<uint32_t>(); hp.n_reads = n_lines / 4; hp.K = K;
   }
@@ -202,10 +242,10 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
   SHQ_CUDA(cudaMemsetAsync(h->d_hist.p, 0, (size_t)(n_bins + 1) * 4, st));
   SHQ_CUDA(cudaMemsetAsync(h->d_chunk_keys.p, 0, (size_t)(nchunks + 1) * 4, st));
   const int G = kNumSMs * 2;
-  const int W = g_scatter_w;
   const size_t smem_cle = hp.chunk_line_end ? (size_t)nchunks * 4 + 16 : 0;
   size_t smem_count = sizeof(RollTables) + (size_t)n_bins * 4 + smem_cle;
-  size_t smem_scatter = sizeof(RollTables) + ((size_t)3 * n_bins + 1) * 4 + (size_t)16384 * 10 + 16 + smem_cle;   // threads * W == 16384 keys per round
+  const bool wide = n_bins <= 4096;          // 16 keys per thread and round fit beside the bin arrays
+  size_t smem_scatter = sizeof(RollTables) + ((size_t)3 * n_bins + 1) * 4 + (size_t)kScatThreads * (wide ? 16 : 8) * 14 + 16 + smem_cle;
   size_t smem_keys = (size_t)n_bins * 8;
   Sink sk{};
   {
@@ -221,21 +261,22 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
     exclusive_scan_inplace<SumU32>(h->d_binoff.as<uint32_t>(), n_bins, h->d_scan_scratch, st, h->d_binoff.as<uint32_t>() + n_bins, &L);
     SHQ_CUDA(cudaMemcpyAsync(h->d_tot.p, h->d_binoff.p, (size_t)n_bins * 4, cudaMemcpyDeviceToDevice, st));
   }
-  uint32_t n_keys = read_scalar(h, h->d_binoff.as<uint32_t>() + n_bins);
+  uint32_t n_keys = 0; int dev_err = 0;
+  read_pair(h, h->d_binoff.as<uint32_t>() + n_bins, &n_keys, h->d_err, &dev_err);
+  if (dev_err) {
+    SHQ_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(int), st));
+    SHQ_FAIL(dev_err, "device reported: %s", shq_strerror(dev_err));
+  }
   h->d_packed.reserve((size_t)(n_keys + 4) * 4);
   {
     Phase ph(h, &h->stats.ms_scatter);
     if (from_text) {
-      if (W == 12) {     // direct variant: 2 CTAs x 1024 threads per SM, 12 windows per thread and round
-        size_t smem_direct = sizeof(RollTables) + (size_t)2 * n_bins * 4 + (size_t)1024 * 12 * 6 + 16 + smem_cle;
-        SHQ_CUDA(cudaFuncSetAttribute(roll_scatter_direct_kernel<1024, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_direct));
-        roll_scatter_direct_kernel<1024, 12><<<2 * kNumSMs, 1024, smem_direct, st>>>(hp, h->d_tot.as<uint32_t>(), h->d_packed.as<uint32_t>());
-      } else if (W == 16) {     // 1024 threads x 16 windows: same shared memory, twice the warps
-        SHQ_CUDA(cudaFuncSetAttribute(roll_scatter_kernel<1024, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
-        roll_scatter_kernel<1024, 16><<<kNumSMs, 1024, smem_scatter, st>>>(hp, h->d_tot.as<uint32_t>(), h->d_packed.as<uint32_t>());
+      if (wide) {
+        SHQ_CUDA(cudaFuncSetAttribute(roll_scatter_kernel<kScatThreads, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
+        roll_scatter_kernel<kScatThreads, 16><<<kNumSMs, kScatThreads, smem_scatter, st>>>(hp, h->d_tot.as<uint32_t>(), h->d_packed.as<uint32_t>());
       } else {
-        SHQ_CUDA(cudaFuncSetAttribute(roll_scatter_kernel<512, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
-        roll_scatter_kernel<512, 32><<<kNumSMs, 512, smem_scatter, st>>>(hp, h->d_tot.as<uint32_t>(), h->d_packed.as<uint32_t>());
+        SHQ_CUDA(cudaFuncSetAttribute(roll_scatter_kernel<kScatThreads, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
+        roll_scatter_kernel<kScatThreads, 8><<<kNumSMs, kScatThreads, smem_scatter, st>>>(hp, h->d_tot.as<uint32_t>(), h->d_packed.as<uint32_t>());
       }
       L++;
     } else {
@@ -300,8 +341,8 @@ bool aggregate_bins(shq_handle_s* h, const BatchBins& bb, uint32_t clo, uint32_t
     SHQ_CUDA(cudaMemcpyAsync(dense, nout, nb * 4, cudaMemcpyDeviceToDevice, st));
     exclusive_scan_inplace<SumU32>(dense, nb, h->d_scan_scratch, st, dense + nb, &L);
     exclusive_scan_inplace<SumU32>(occs, nb, h->d_scan_scratch, st, h->d_misc.as<uint32_t>(), &L);
-    uint32_t nd = read_scalar(h, dense + nb);
-    uint32_t oc = read_scalar(h, h->d_misc.as<uint32_t>());
+    uint32_t nd = 0, oc = 0;
+    read_pair(h, dense + nb, &nd, h->d_misc.as<uint32_t>(), &oc);
     R->keys->reserve((size_t)(nd + 4) * 8); R->counts->reserve((size_t)(nd + 4) * 4);
     if (tch) R->chunk->reserve((size_t)(nd + 4) * 2);
     compact_bins_kernel<<<(unsigned)nb, 256, 0, st>>>(h->d_binoff.as<uint32_t>(), dense, nout, fixed_bits, cap, tk, tc, tch, R->keys->as<uint64_t>(),
@@ -614,7 +655,6 @@ void init_handle(shq_handle_s* h, int qb, int hb, uint32_t seed, int device, int
   if (qb < 1 || qb > 40 || hb - qb != 8) SHQ_FAIL(SHQ_ERR_ARG, "need 1 <= qb <= 40 and hb - qb == 8 (got qb=%d hb=%d)", qb, hb);
   if (nshards < 1 || (nshards & (nshards - 1)) || shard < 0 || shard >= nshards || (1 << qb) < nshards * 64)
     SHQ_FAIL(SHQ_ERR_ARG, "bad shard %d of %d", shard, nshards);
-  if (const char* e = getenv("SHQ_SCATTER_W")) { int v = atoi(e); if (v == 12 || v == 16 || v == 32) g_scatter_w = v; }
   if (const char* e = getenv("SHQ_MAX_BATCH_MB")) { long v = atol(e); if (v >= 1 && v <= 3072) h->max_batch_bytes = (size_t)v << 20; }
   if (const char* e = getenv("SHQ_BIN_BITS")) { int v = atoi(e); if (v >= 4 && v <= 13) g_bin_bits = v; }
   SHQ_CUDA(cudaSetDevice(device));
@@ -648,6 +688,8 @@ void free_handle(shq_handle_s* h) {
   if (h->d_err) cudaFree(h->d_err);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->h_stage) cudaFreeHost(h->h_stage);
+  resolve_phases(h);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1123,8 +1165,20 @@ int shq_set_counts(shq_t h, uint64_t ndistinct, uint64_t nelts) {
   return SHQ_OK;
 }
 
-int shq_get_stats(shq_t h, shq_stats* out) { if (!h || !out) return SHQ_ERR_ARG; *out = h->stats; return SHQ_OK; }
-int shq_reset_stats(shq_t h) { if (!h) return SHQ_ERR_ARG; memset(&h->stats, 0, sizeof h->stats); return SHQ_OK; }
+int shq_get_stats(shq_t h, shq_stats* out) {
+  if (!h || !out) return SHQ_ERR_ARG;
+  cudaSetDevice(h->device);
+  resolve_phases(h);
+  *out = h->stats;
+  return SHQ_OK;
+}
+int shq_reset_stats(shq_t h) {
+  if (!h) return SHQ_ERR_ARG;
+  cudaSetDevice(h->device);
+  resolve_phases(h);
+  memset(&h->stats, 0, sizeof h->stats);
+  return SHQ_OK;
+}
 void* shq_stream(shq_t h) { return h ? (void*)h->stream : nullptr; }
 
 }  // extern "C"

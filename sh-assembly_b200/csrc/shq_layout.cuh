@@ -143,45 +143,72 @@ __global__ void __launch_bounds__(kImgThreads) image_tiles_kernel(const uint64_t
 // (cqf/CQF_mt.h:884-901) and its cleaners loop `while (start < end_bucket_id)`
 // (cqf/gqf.c:2878-2886, CQF_mt.h:1024): a cluster that is one slot wide and sits exactly on a
 // range end is never visited, so its count-1 key survives.  This walk finds those keys.
-// Single thread (the chain of ranges is inherently serial; nslots / 2^20 steps).
-__global__ void denoise_ranges_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts,
+// One warp: the chain of ranges is inherently serial (nslots / 2^20 steps), but every step is a pair of
+// searches and a walk to the end of a cluster, and those are done 32 entries at a time.
+// warp_first_false: first index in [lo, hi) whose predicate is false (the predicate is true on a prefix).
+template <class Pred>
+__device__ __forceinline__ size_t warp_first_false(size_t lo, size_t hi, int lane, Pred&& pred) {
+  while (lo < hi) {
+    size_t span = hi - lo;
+    size_t step = (span + 31) / 32;
+    size_t idx = lo + (size_t)lane * step;
+    bool t = idx < hi && pred(idx);
+    uint32_t m = __ballot_sync(0xffffffffu, t);
+    int c = __popc(m);                      // lanes 0..c-1 are true (monotone predicate)
+    if (c == 0) return lo;
+    size_t nlo = lo + (size_t)(c - 1) * step + 1;
+    size_t nhi = lo + (size_t)c * step;
+    if (nhi > hi) nhi = hi;
+    lo = nlo; hi = nhi;
+  }
+  return lo;
+}
+__global__ void __launch_bounds__(32) denoise_ranges_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts,
                                       const uint64_t* __restrict__ pos, size_t n, uint64_t nslots, uint64_t xnslots,
                                       uint32_t* __restrict__ keep_idx, uint32_t* __restrict__ n_keep, uint32_t keep_cap) {
-  if (blockIdx.x || threadIdx.x) return;
+  if (blockIdx.x) return;
+  const int lane = threadIdx.x;
   const uint64_t min_len = 1ULL << 20;
   uint32_t nk = 0;
-  if (n == 0) { *n_keep = 0; return; }
+  if (n == 0) { if (lane == 0) *n_keep = 0; return; }
   uint64_t cur = keys[0] >> 8;  // find_first_nonempty_slot(qf, 0)
   while (cur < nslots) {
     uint64_t start = cur;
     uint64_t e0 = (start + min_len) > nslots ? nslots : (start + min_len);
-    // k = last entry with pos <= e0
-    size_t lo = 0, hi = n;
-    while (lo < hi) { size_t mid = lo + ((hi - lo) >> 1); if (pos[mid] <= e0) lo = mid + 1; else hi = mid; }
+    // lo = number of entries with pos <= e0
+    size_t lo = warp_first_false(0, n, lane, [&](size_t i) { return pos[i] <= e0; });
     uint64_t end;
     size_t last = (size_t)-1;   // entry holding slot `end`, if any
-    if (lo > 0 && entry_end(keys, counts, pos, lo - 1) >= e0) {
+    uint64_t prev_end = lo > 0 ? entry_end(keys, counts, pos, lo - 1) : 0;
+    if (lo > 0 && prev_end >= e0) {
+      // walk to the end of the cluster: first j >= lo-1 whose successor is not adjacent
       size_t j = lo - 1;
-      uint64_t je = entry_end(keys, counts, pos, j);
-      while (j + 1 < n && pos[j + 1] == je + 1) { j++; je = entry_end(keys, counts, pos, j); }
-      end = je; last = j;                       // find_first_empty_slot(e0) - 1
+      for (;;) {
+        size_t i = j + lane;
+        bool adj = i + 1 < n && pos[i + 1] == entry_end(keys, counts, pos, i) + 1;
+        uint32_t m = __ballot_sync(0xffffffffu, adj);
+        int run = __ffs(~m) - 1;              // number of leading adjacent links (32 if all)
+        if (run < 0) run = 32;
+        j += run;
+        if (run < 32) break;
+      }
+      end = entry_end(keys, counts, pos, j); last = j;   // find_first_empty_slot(e0) - 1
     } else {
       end = e0 - 1;
-      if (lo > 0 && entry_end(keys, counts, pos, lo - 1) == end) last = lo - 1;
+      if (lo > 0 && prev_end == end) last = lo - 1;
     }
     if (last != (size_t)-1 && end >= start) {
       // one-slot cluster [end,end]: entry starts and ends at `end`, previous entry not adjacent
       if (pos[last] == end && counts[last] == 1 && (last == 0 || entry_end(keys, counts, pos, last - 1) + 1 < end)) {
-        if (nk < keep_cap) keep_idx[nk] = (uint32_t)last;
+        if (nk < keep_cap && lane == 0) keep_idx[nk] = (uint32_t)last;
         nk++;
       }
     }
     // find_first_nonempty_slot(end + 1): next occupied quotient >= end+1
-    lo = 0; hi = n;
-    while (lo < hi) { size_t mid = lo + ((hi - lo) >> 1); if ((keys[mid] >> 8) < end + 1) lo = mid + 1; else hi = mid; }
-    cur = lo < n ? (keys[lo] >> 8) : xnslots;
+    size_t nx = warp_first_false(0, n, lane, [&](size_t i) { return (keys[i] >> 8) < end + 1; });
+    cur = nx < n ? (keys[nx] >> 8) : xnslots;
   }
-  *n_keep = nk;
+  if (lane == 0) *n_keep = nk;
 }
 
 // ------------------------------------------------------------ queries -------

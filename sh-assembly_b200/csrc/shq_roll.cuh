@@ -1,56 +1,80 @@
-// shq_roll.cuh -- K2, second generation: one THREAD per read, rolling canonical ntHash.
+// shq_roll.cuh -- K2, third generation: one THREAD per read, rolling canonical ntHash, 8 windows per step.
 //
-// The first generation (shq_hash.cuh, warp per read + prefix-XOR scan) executed ~10 warp instructions per
-// window and scattered 4-byte stores into 296 x 16384 open segments (21 GB of DRAM traffic for 2.4 GB of
-// algorithmic bytes, profiles/r1_ncu_full_v1_raw.csv).  Here:
-//   * hashing is the reference's own recurrence (base/nthash.hpp:305-309) per thread: 4 shared-memory table
-//     lookups, two 1-bit rotates and four XORs per window; text is fetched as aligned 32-bit words;
-//     the 'N' restart rule (cqf/CQF_mt.h:624-718) is part of the same loop, so there is no slow path;
-//   * the scatter pass stages one round of keys per CTA in shared memory, reserves space in every bin with ONE
-//     global atomicAdd per (round, bin) on cursors shared by all CTAs, and writes the keys of a bin next to
-//     each other, so L2 merges them into full sectors (one open line per bin instead of one per CTA x bin).
+// History (profiles/): the first generation (shq_hash.cuh, warp per read + prefix-XOR scan) spent ~10 warp
+// instructions per window; the second (thread per read, 4-byte text loads, four byte-indexed table lookups per
+// window) was bound by L1 tag throughput -- every lane of a load touches its own cache line, one tag lookup per
+// window (l1tex 84 % busy in roll_count_kernel) -- and the staged scatter spent more instructions on the
+// in-round sort than on hashing.  Here:
+//   * the reference's recurrence (base/nthash.hpp:305-309) runs on 2-bit base codes: a step loads ONE aligned
+//     64-bit word of incoming characters and one of outgoing characters (8 windows per L1 lookup pair), checks
+//     with three SIMD byte operations that all eight are A/C/G/T (either case), packs them to 16 bits, and then
+//     needs one 16-byte shared-memory load per window: entry (out << 2 | in) of a 16-entry table holds
+//     rol(seed(out),K) ^ seed(in)  and  rol(seed'(out),63) ^ rol(seed'(in),K-1);
+//   * anything else -- 'N' (restart rule, cqf/CQF_mt.h:624-718), other bytes (which hash as 0 forward but through
+//     c & 7 on the reverse strand), the unaligned head and the tail of a read -- takes the byte-exact slow step
+//     on the 256-entry tables, for as long as such a byte is inside the window;
+//   * the scatter pass ranks every key inside its (round, bin) with the histogram atomic itself, places the
+//     round in bin order in shared memory with one pass, and writes it out as one linear sweep in which
+//     neighbouring lanes hold neighbouring words of the same bin (full sectors, no per-bin loop).
 #pragma once
 #include "shq_common.cuh"
 #include "shq_hash.cuh"
 
 namespace shq {
 
-struct RollTables {            // in shared memory, indexed by the text byte
-  uint64_t in_f[256];          // seed(c)
+struct RollTables {            // in shared memory
+  uint4 fast[16];              // [out << 2 | in] over 2-bit codes (c >> 1) & 3: {f.lo, f.hi, r.lo, r.hi}
+  uint64_t in_f[256];          // byte-indexed: seed(c)
   uint64_t out_f[256];         // rol(seed(c), K)
   uint64_t in_r[256];          // rol(seed'(c & 7), K-1)
   uint64_t out_r[256];         // rol(seed'(c & 7), 63)
+  uint8_t bad[256];            // 1 unless c is one of ACGTacgt
 };
 __device__ __forceinline__ void roll_tables_init(RollTables* t, int K) {
   for (int c = threadIdx.x; c < 256; c += blockDim.x) {
     uint64_t f = nt_seed_fwd((unsigned char)c), r = nt_seed_rev((unsigned char)c);
     t->in_f[c] = f; t->out_f[c] = rotl64(f, K);
     t->in_r[c] = rotl64(r, K - 1); t->out_r[c] = rotl64(r, 63);
+    unsigned char u = (unsigned char)(c & 0xDF);
+    t->bad[c] = (u == 'A' || u == 'C' || u == 'G' || u == 'T') ? 0 : 1;
+  }
+  if (threadIdx.x < 16) {
+    const unsigned char letter[4] = {'A', 'C', 'T', 'G'};      // code = (c >> 1) & 3
+    unsigned char co = letter[threadIdx.x >> 2], ci = letter[threadIdx.x & 3];
+    uint64_t f = rotl64(nt_seed_fwd(co), K) ^ nt_seed_fwd(ci);
+    uint64_t r = rotl64(nt_seed_rev(co), 63) ^ rotl64(nt_seed_rev(ci), K - 1);
+    t->fast[threadIdx.x] = make_uint4((uint32_t)f, (uint32_t)(f >> 32), (uint32_t)r, (uint32_t)(r >> 32));
   }
 }
 
-// Four consecutive text bytes starting at an arbitrary address, from two aligned 32-bit loads.
-__device__ __forceinline__ uint32_t load4(const char* p) {
-  uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-  uint32_t sh = (uint32_t)(a & 3) * 8;
-  uint32_t w0 = __ldg(wp);
-  if (sh == 0) return w0;
-  return __funnelshift_r(w0, __ldg(wp + 1), sh);
+// Four text bytes -> four 2-bit codes in one byte (first character in the low bits); *ok is cleared unless all
+// four are ACGT in either case.
+__device__ __forceinline__ uint32_t pack4(uint32_t w, bool* ok) {
+  uint32_t x = (w >> 1) & 0x03030303u;
+  uint32_t t = (x >> 1) & ~x & 0x01010101u;                        // code 2 = 'T'
+  uint32_t letter = 0x41414141u + (x << 1) + t * 15u;              // A 41, C 43, G 47, T 54
+  *ok = *ok && ((w & 0xDFDFDFDFu) == letter);
+  return ((x * 0x41041u) >> 18) & 0xFFu;
+}
+__device__ __forceinline__ uint32_t pack4_nocheck(uint32_t w) {
+  uint32_t x = (w >> 1) & 0x03030303u;
+  return ((x * 0x41041u) >> 18) & 0xFFu;
 }
 
 // Per-thread generator of the key stream of one read after another (reads first, first+stride, ...).
-// step() advances by one unit -- open+prime a read (1 key), a group of 4 windows (4 keys), or a single
-// window near the end of a read / around an 'N' (<= 1 key) -- and hands every key to emit(key, chunk).
+// step() advances by one unit -- open+prime a read (1 key), a group of 8 windows (8 keys), or a single
+// window (<= 1 key) -- and hands every key to emit(key, chunk).  Never more than 8 keys per call.
 struct Roller {
   const HashParams* hp; const RollTables* tab;
   uint32_t read, read_end, stride;
   uint32_t s, len, pos;        // current read: start offset, length, index of the NEXT char to roll in
-  uint64_t fh, rh; uint32_t chunk;
+  uint32_t slow_until;         // windows whose incoming char has index < slow_until take the byte-exact step
+  uint64_t fh, rh, ocur; uint32_t chunk;
   bool active;                 // a read is open and primed (fh/rh valid for the window ending at pos-1)
+  bool out_ok;                 // ocur holds the aligned word that follows the outgoing group just consumed
 
   __device__ __forceinline__ void start(const HashParams* hp_, const RollTables* tab_, uint32_t first, uint32_t end, uint32_t stride_) {
-    hp = hp_; tab = tab_; read = first; read_end = end; stride = stride_; active = false;
+    hp = hp_; tab = tab_; read = first; read_end = end; stride = stride_; active = false; out_ok = false; slow_until = 0;
   }
   // prime at sub-read start s0; false if fewer than K chars remain (cqf/CQF_mt.h:624-625)
   __device__ __forceinline__ bool prime(uint32_t s0) {
@@ -58,19 +82,33 @@ struct Roller {
     if (s0 > len || len - s0 < K) return false;
     const unsigned char* p = reinterpret_cast<const unsigned char*>(hp->text) + s + s0;
     uint64_t f = 0, r = 0;
-    for (uint32_t i = 0; i < K; i++) {
-      unsigned char c = __ldg(p + i);
-      f = rotl64(f, 1) ^ tab->in_f[c];                 // == xor of rol(seed, K-1-i)
-      r ^= rotr64(tab->in_r[c], K - 1 - i);            // in_r = rol(seed', K-1)  ->  rol(seed', i)
+    uint32_t anybad = 0;
+    // aligned 64-bit words covering [p, p + K)
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(p);
+    const uint64_t* wp = reinterpret_cast<const uint64_t*>(a0 & ~(uintptr_t)7);
+    uint32_t skip = (uint32_t)(a0 & 7);
+    uint32_t i = 0;
+    while (i < K) {
+      uint64_t w = __ldg(wp++) >> (8 * skip);
+      uint32_t nb = 8 - skip; skip = 0;
+      if (nb > K - i) nb = K - i;
+      for (uint32_t b = 0; b < nb; b++, i++) {
+        unsigned char c = (unsigned char)w; w >>= 8;
+        f = rotl64(f, 1) ^ tab->in_f[c];                 // == xor of rol(seed, K-1-i)
+        r ^= rotr64(tab->in_r[c], K - 1 - i);            // in_r = rol(seed', K-1)  ->  rol(seed', i)
+        anybad |= tab->bad[c];
+      }
     }
     fh = f; rh = r; pos = s0 + K;
+    if (anybad) slow_until = s0 + 2 * K;                 // until every byte of the primed window has left
+    out_ok = false;
     return true;
   }
   __device__ __forceinline__ void roll(unsigned char cout, unsigned char cin) {   // base/nthash.hpp:305-309
     fh = rotl64(fh, 1) ^ tab->out_f[cout] ^ tab->in_f[cin];
     rh = rotr64(rh, 1) ^ tab->out_r[cout] ^ tab->in_r[cin];
   }
-  // returns false when this thread has no reads left; never emits more than 4 keys per call
+  // returns false when this thread has no reads left
   template <class Emit>
   __device__ __forceinline__ bool step(const uint64_t mask, Emit&& emit) {
     if (!active) {
@@ -79,30 +117,52 @@ struct Roller {
       len = hp->nl_pos[4 * (size_t)read + 1] - s;
       chunk = chunk_of_line(*hp, 4 * read + 1);
       read += stride;
+      slow_until = 0;
       if (prime(0)) { active = true; emit((fh < rh ? fh : rh) & mask, chunk); }
       return true;
     }
     if (pos >= len) { active = false; return true; }
-    const char* base = hp->text + s;
-    if (len - pos >= 4) {
-      uint32_t vin = load4(base + pos);
-      if (__vcmpeq4(vin, 0x4E4E4E4Eu) == 0) {            // no 'N' among the next four characters
-        uint32_t vout = load4(base + pos - hp->K);
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(hp->text) + s;
+    const uint32_t K = hp->K;
+    const uintptr_t ia = reinterpret_cast<uintptr_t>(base + pos);
+    if ((ia & 7) == 0 && len - pos >= 8 && pos >= slow_until) {
+      const uint64_t in8 = __ldg(reinterpret_cast<const uint64_t*>(ia));
+      bool ok = true;
+      const uint32_t ic = pack4((uint32_t)in8, &ok) | (pack4((uint32_t)(in8 >> 32), &ok) << 8);
+      if (ok) {
+        const uintptr_t oa = ia - K;
+        const uint32_t sh = (uint32_t)(oa & 7) * 8;
+        const uint64_t* op = reinterpret_cast<const uint64_t*>(oa & ~(uintptr_t)7);
+        uint64_t w0 = out_ok ? ocur : __ldg(op);
+        uint64_t out8 = w0;
+        if (sh) { uint64_t w1 = __ldg(op + 1); out8 = (w0 >> sh) | (w1 << (64 - sh)); ocur = w1; out_ok = true; }
+        else out_ok = false;
+        const uint32_t oc = pack4_nocheck((uint32_t)out8) | (pack4_nocheck((uint32_t)(out8 >> 32)) << 8);
+        // nibble n of ze / zo = (out << 2 | in) of window 2n / 2n+1
+        const uint32_t ze = (ic & 0x3333u) | ((oc & 0x3333u) << 2);
+        const uint32_t zo = ((ic >> 2) & 0x3333u) | (oc & 0xCCCCu);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          roll((unsigned char)(vout >> (8 * j)), (unsigned char)(vin >> (8 * j)));
+        for (int j = 0; j < 8; j++) {
+          const uint32_t idx = (((j & 1) ? zo : ze) >> (4 * (j >> 1))) & 15u;
+          const uint4 t = tab->fast[idx];
+          fh = rotl64(fh, 1) ^ ((uint64_t)t.x | ((uint64_t)t.y << 32));
+          rh = rotr64(rh, 1) ^ ((uint64_t)t.z | ((uint64_t)t.w << 32));
           emit((fh < rh ? fh : rh) & mask, chunk);
         }
-        pos += 4;
+        pos += 8;
         return true;
       }
+      slow_until = pos + 8 + K;                           // some byte of this group is not ACGT
     }
-    unsigned char cin = __ldg(reinterpret_cast<const unsigned char*>(base) + pos);
+    out_ok = false;
+    unsigned char cin = __ldg(base + pos);
     if (cin == 'N') {                                     // restart after the N (CQF_mt.h:680-683)
-      if (prime(pos + 1)) emit((fh < rh ? fh : rh) & mask, chunk); else active = false;
+      const uint32_t su = slow_until;
+      if (prime(pos + 1)) { if (su > slow_until) slow_until = su; emit((fh < rh ? fh : rh) & mask, chunk); } else active = false;
       return true;
     }
-    roll(__ldg(reinterpret_cast<const unsigned char*>(base) + pos - hp->K), cin);
+    if (tab->bad[cin] && pos + 1 + K > slow_until) slow_until = pos + 1 + K;
+    roll(__ldg(base + pos - K), cin);
     pos++;
     emit((fh < rh ? fh : rh) & mask, chunk);
     return true;
@@ -111,8 +171,8 @@ struct Roller {
 
 constexpr int kRollThreads = 512;
 
-// Pass 1: global histogram of bins (+ per-chunk key counts when armed).
-// dynamic smem: RollTables + n_bins * 4
+// Pass 1: global histogram of bins.
+// dynamic smem: RollTables + n_bins * 4 (+ chunk map)
 __global__ void __launch_bounds__(kRollThreads) roll_count_kernel(HashParams hp, uint32_t* __restrict__ g_hist) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RollTables* tab = reinterpret_cast<RollTables*>(smem_raw);
@@ -131,45 +191,45 @@ __global__ void __launch_bounds__(kRollThreads) roll_count_kernel(HashParams hp,
   const uint64_t mask = hp.hb >= 64 ? ~0ULL : ((1ULL << hp.hb) - 1);
   const uint64_t key_lo = hp.key_lo, key_hi = hp.key_hi; const int lb = hp.lb;
   const bool whole = key_lo == 0 && key_hi > mask;      // unsharded: every key is ours
-  uint32_t last_chunk = 0xFFFFFFFFu, run = 0;
-  uint32_t* chunk_keys = hp.chunk_keys;
-  auto emit = [&](uint64_t key, uint32_t ch) {
-    if (chunk_keys) {
-      if (ch != last_chunk) { if (run) atomicAdd(&chunk_keys[last_chunk], run); last_chunk = ch; run = 0; }
-      run++;
-    }
+  auto emit = [&](uint64_t key, uint32_t) {
     if (whole) { atomicAdd(&s_hist[(uint32_t)(key >> lb)], 1u); return; }
     if (key < key_lo || key >= key_hi) return;
     atomicAdd(&s_hist[(uint32_t)((key - key_lo) >> lb)], 1u);
   };
   while (R.step(mask, emit)) {}
-  if (chunk_keys && run) atomicAdd(&chunk_keys[last_chunk], run);
   __syncthreads();
   for (int i = threadIdx.x; i < hp.n_bins; i += blockDim.x) { uint32_t v = s_hist[i]; if (v) atomicAdd(&g_hist[i], v); }
 }
 
 // Pass 2: staged scatter.  g_cursor[bin] starts at the bin's offset and is shared by all CTAs.
-// Per round a CTA (1) rolls up to W windows per thread into shared memory and histograms their bins,
-// (2) prefix-sums the histogram and reserves one global range per bin (one atomicAdd per bin and round),
-// (3) counting-sorts the round by bin inside shared memory, (4) writes every bin's keys with 8 adjacent
-// lanes, i.e. as one 32-byte sector request instead of eight scattered 4-byte stores.
-// dynamic smem: RollTables + (3*n_bins + 1) * 4 + kRollThreads * W * (4 + 4 + 2)
+// Per round a CTA
+//   A. rolls up to W windows per thread; every key takes its rank inside (round, bin) from the histogram
+//      atomic and is parked in shared memory as (packed word, bin << 16 | rank);
+//   B. prefix-sums the histogram and reserves one global range per bin (one atomicAdd per bin and round);
+//   C. moves every key to slot off[bin] + rank of the sorted round, with its bin beside it;
+//   D. writes the sorted round out linearly: word i goes to (base[bin] - off[bin]) + i, so lanes that hold
+//      neighbouring words of a bin write neighbouring addresses.
+// dynamic smem: RollTables + (3 * n_bins + 1) * 4 + THREADS * W * 14 (+ chunk map)
+constexpr int kScatThreads = 768;
+constexpr int kScatW = 16;
 template <int THREADS, int W>
 __global__ void __launch_bounds__(THREADS) roll_scatter_kernel(HashParams hp, uint32_t* __restrict__ g_cursor, uint32_t* __restrict__ packed) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RollTables* tab = reinterpret_cast<RollTables*>(smem_raw);
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw + sizeof(RollTables));
   uint32_t* s_off = s_hist + hp.n_bins;              // n_bins + 1 entries
-  uint32_t* s_base = s_off + hp.n_bins + 1;
-  uint32_t* s_key = s_base + hp.n_bins;
-  uint32_t* s_sorted = s_key + THREADS * W;
-  uint16_t* s_bin = reinterpret_cast<uint16_t*>(s_sorted + THREADS * W);
+  uint32_t* s_delta = s_off + hp.n_bins + 1;         // base[bin] - off[bin]
+  uint32_t* s_key = s_delta + hp.n_bins;
+  uint32_t* s_br = s_key + THREADS * W;
+  uint32_t* s_sorted = s_br + THREADS * W;
+  uint16_t* s_sbin = reinterpret_cast<uint16_t*>(s_sorted + THREADS * W);
   roll_tables_init(tab, hp.K);
   if (hp.chunk_line_end) {
-    uint32_t* s_cle = reinterpret_cast<uint32_t*>(s_bin + THREADS * W);
+    uint32_t* s_cle = reinterpret_cast<uint32_t*>(s_sbin + THREADS * W);
     for (int i = threadIdx.x; i < hp.nchunks; i += blockDim.x) s_cle[i] = hp.chunk_line_end[i];
     hp.chunk_line_end = s_cle;
   }
+  for (int i = threadIdx.x; i < hp.n_bins; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
   // reads are dealt round-robin over the whole grid: every bin then receives its words in (roughly) chunk
   // order, which keeps the aggregator's first-chunk minimum almost free of updates
@@ -180,7 +240,6 @@ __global__ void __launch_bounds__(THREADS) roll_scatter_kernel(HashParams hp, ui
   const bool whole = key_lo == 0 && key_hi > mask;
   const uint32_t lowmask = lb >= 32 ? 0xFFFFFFFFu : ((1u << lb) - 1);
   const int per = (hp.n_bins + THREADS - 1) / THREADS;      // bins per thread in the scan
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   bool more = true;
   int produced = 0;
   auto emit = [&](uint64_t key, uint32_t ch) {
@@ -189,19 +248,15 @@ __global__ void __launch_bounds__(THREADS) roll_scatter_kernel(HashParams hp, ui
     uint32_t bin = (uint32_t)(rel >> lb);
     int idx = produced * THREADS + threadIdx.x;
     s_key[idx] = ((uint32_t)rel & lowmask) | (lb >= 32 ? 0 : (ch << lb));
-    s_bin[idx] = (uint16_t)bin;
-    atomicAdd(&s_hist[bin], 1u);
+    s_br[idx] = (bin << 16) | atomicAdd(&s_hist[bin], 1u);
     produced++;
   };
   for (;;) {
-    for (int i = threadIdx.x; i < hp.n_bins; i += blockDim.x) s_hist[i] = 0;
-    __syncthreads();
     produced = 0;
-    while (more && produced + 4 <= W) more = R.step(mask, emit);
-    for (int j = produced; j < W; j++) s_bin[j * THREADS + threadIdx.x] = 0xFFFF;
+    while (more && produced + 8 <= W) more = R.step(mask, emit);
     int any = __syncthreads_or(produced > 0);
     if (!any) break;
-    {   // exclusive scan over the bins + global reservation
+    {   // B: exclusive scan over the bins + global reservation; the histogram is cleared for the next round
       uint32_t sum = 0;
       int b0 = threadIdx.x * per;
       for (int j = 0; j < per; j++) { int b = b0 + j; if (b < hp.n_bins) sum += s_hist[b]; }
@@ -211,86 +266,26 @@ __global__ void __launch_bounds__(THREADS) roll_scatter_kernel(HashParams hp, ui
         int b = b0 + j;
         if (b < hp.n_bins) {
           uint32_t c = s_hist[b];
-          s_off[b] = ex; ex += c;
-          s_base[b] = c ? atomicAdd(&g_cursor[b], c) : 0;
+          s_hist[b] = 0;
+          s_off[b] = ex;
+          s_delta[b] = (c ? atomicAdd(&g_cursor[b], c) : 0) - ex;
+          ex += c;
         }
       }
       if (threadIdx.x == 0) s_off[hp.n_bins] = tot;
     }
     __syncthreads();
-#pragma unroll 4
-    for (int j = 0; j < W; j++) {      // counting sort of the round by bin
+    const uint32_t total = s_off[hp.n_bins];
+    for (int j = 0; j < produced; j++) {      // C
       int idx = j * THREADS + threadIdx.x;
-      uint32_t bin = s_bin[idx];
-      if (bin != 0xFFFF) {
-        uint32_t rank = atomicSub(&s_hist[bin], 1u) - 1;
-        s_sorted[s_off[bin] + rank] = s_key[idx];
-      }
+      uint32_t br = s_br[idx];
+      uint32_t bin = br >> 16;
+      uint32_t dst = s_off[bin] + (br & 0xFFFFu);
+      s_sorted[dst] = s_key[idx];
+      s_sbin[dst] = (uint16_t)bin;
     }
     __syncthreads();
-    for (int b = wid * 4 + (lane >> 3); b < hp.n_bins; b += (THREADS / 32) * 4) {
-      uint32_t off = s_off[b], cnt = s_off[b + 1] - off, base = s_base[b];
-      for (uint32_t l = lane & 7; l < cnt; l += 8) packed[base + l] = s_sorted[off + l];
-    }
-    __syncthreads();
-  }
-}
-
-// Variant without the in-round sort: keys go straight from production order to base[bin] + rank.  Needs only
-// 6 bytes of shared memory per staged key, so two CTAs of 1024 threads fit on an SM and overlap each other's
-// barrier phases (reserve / write-out) with hashing.
-// dynamic smem: RollTables + 2 * n_bins * 4 + THREADS * W * 6 (+ chunk map)
-template <int THREADS, int W>
-__global__ void __launch_bounds__(THREADS, 2) roll_scatter_direct_kernel(HashParams hp, uint32_t* __restrict__ g_cursor, uint32_t* __restrict__ packed) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  RollTables* tab = reinterpret_cast<RollTables*>(smem_raw);
-  uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw + sizeof(RollTables));
-  uint32_t* s_base = s_hist + hp.n_bins;
-  uint32_t* s_key = s_base + hp.n_bins;
-  uint16_t* s_bin = reinterpret_cast<uint16_t*>(s_key + THREADS * W);
-  roll_tables_init(tab, hp.K);
-  if (hp.chunk_line_end) {
-    uint32_t* s_cle = reinterpret_cast<uint32_t*>(s_bin + THREADS * W);
-    for (int i = threadIdx.x; i < hp.nchunks; i += blockDim.x) s_cle[i] = hp.chunk_line_end[i];
-    hp.chunk_line_end = s_cle;
-  }
-  __syncthreads();
-  Roller R;
-  R.start(&hp, tab, blockIdx.x * blockDim.x + threadIdx.x, hp.n_reads, gridDim.x * blockDim.x);
-  const uint64_t mask = hp.hb >= 64 ? ~0ULL : ((1ULL << hp.hb) - 1);
-  const uint64_t key_lo = hp.key_lo, key_hi = hp.key_hi; const int lb = hp.lb;
-  const bool whole = key_lo == 0 && key_hi > mask;
-  const uint32_t lowmask = lb >= 32 ? 0xFFFFFFFFu : ((1u << lb) - 1);
-  bool more = true;
-  int produced = 0;
-  auto emit = [&](uint64_t key, uint32_t ch) {
-    if (!whole && (key < key_lo || key >= key_hi)) return;
-    uint64_t rel = key - key_lo;
-    uint32_t bin = (uint32_t)(rel >> lb);
-    int idx = produced * THREADS + threadIdx.x;
-    s_key[idx] = ((uint32_t)rel & lowmask) | (lb >= 32 ? 0 : (ch << lb));
-    s_bin[idx] = (uint16_t)bin;
-    atomicAdd(&s_hist[bin], 1u);
-    produced++;
-  };
-  for (;;) {
-    for (int i = threadIdx.x; i < hp.n_bins; i += blockDim.x) s_hist[i] = 0;
-    __syncthreads();
-    produced = 0;
-    while (more && produced + 4 <= W) more = R.step(mask, emit);
-    int any = __syncthreads_or(produced > 0);
-    if (!any) break;
-    for (int i = threadIdx.x; i < hp.n_bins; i += blockDim.x) {
-      uint32_t c = s_hist[i];
-      s_base[i] = c ? atomicAdd(&g_cursor[i], c) : 0;
-    }
-    __syncthreads();
-    for (int j = 0; j < produced; j++) {
-      int idx = j * THREADS + threadIdx.x;
-      uint32_t bin = s_bin[idx];
-      uint32_t rank = atomicSub(&s_hist[bin], 1u) - 1;
-      packed[s_base[bin] + rank] = s_key[idx];
-    }
+    for (uint32_t i = threadIdx.x; i < total; i += THREADS) packed[s_delta[s_sbin[i]] + i] = s_sorted[i];   // D
     __syncthreads();
   }
 }

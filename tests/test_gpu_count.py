@@ -26,10 +26,13 @@ def test_hash_odd_bytes(po, shq):
     # lower case, IUPAC letters, raw low bytes, reads shorter than K, empty sequence lines
     recs = [b"ACGTNNNNacgtRYKMSWacgtacgtacgtacgtACGTACGTACGTACGTAAAACCCCGGGGTTTT", b"ACG", b"",
             b"N" * 40, b"ACGTACGTACGTACGTACGTACGTACGTACGTACGTNACGTACGTACGTACGTACGTACGTACGTACGTACGTAN",
-            bytes([1, 3, 4, 7]) * 12 + b"ACGTACGTAC", b"ACGT" * 100 + b"N" + b"TTGA" * 50]
+            bytes([1, 3, 4, 7]) * 12 + b"ACGTACGTAC", b"ACGT" * 100 + b"N" + b"TTGA" * 50,
+            # odd bytes deep inside long reads: the 8-window fast step must hand over to the byte-exact step and back
+            b"GATTACA" * 20 + b"R" + b"CATG" * 40 + b"n" + b"TTGCA" * 30, b"ACCGT" * 25 + bytes([3]) + b"GGTCA" * 31 + b"Y",
+            b"acgtt" * 40 + b"NN" + b"ccgta" * 9 + b"N" + b"G" * 70, b"T" * 33 + b"-" + b"ACGGT" * 17 + b"N"]
     text = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, r, b"I" * len(r)) for i, r in enumerate(recs))
     q = shq.CQF(16, 24)
-    for K in (4, 11, 31):
+    for K in (4, 11, 31, 32, 47):
         want = np.sort(po.reads_to_keys(text, K, 24))
         got = np.sort(q.hash_fastq_chunk(text, K))
         assert len(got) == len(want) and (got == want).all(), K

@@ -59,6 +59,17 @@ __device__ __forceinline__ void agg_chunk_min(uint16_t* chk, uint32_t h, uint32_
   }
 }
 
+// predicated shared-memory operations: pass 1 of the insert stays free of branches, so a warp pays for it once
+// and not once per (hit, miss) side
+__device__ __forceinline__ void smem_red_add_if(bool p, uint32_t* addr, uint32_t v) {
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q red.shared.add.u32 [%1], %2; }"
+               :: "r"((uint32_t)p), "r"((uint32_t)__cvta_generic_to_shared(addr)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void smem_st_if(bool p, uint32_t* addr, uint32_t v) {
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.shared.u32 [%1], %2; }"
+               :: "r"((uint32_t)p), "r"((uint32_t)__cvta_generic_to_shared(addr)), "r"(v) : "memory");
+}
+
 template <bool SPLIT, bool CHUNK>
 __device__ __forceinline__ void agg_count(const AggTable& T, uint32_t h, uint32_t ch, bool second) {
   if (SPLIT) {
@@ -97,19 +108,25 @@ __device__ __forceinline__ void agg_insert_pass(const uint32_t* __restrict__ pac
       uint32_t ch = 0;
       if (CHUNK || FILT || SPLIT) ch = lb >= 32 ? 0 : (w >> lb);
       if (FILT) {
-        if (ch < chunk_lo || ch > chunk_hi) live = false;
-        if (sub_bits && (kl >> (lb - sub_bits)) != r) live = false;
+        live = live & (ch >= chunk_lo) & (ch <= chunk_hi);
+        if (sub_bits) live = live & ((kl >> (lb - sub_bits)) == r);
       }
       const bool second = SPLIT && ch > cstar;
-      if (FILT || SPLIT) { if (live) { if (second) my_occ2++; else my_occ++; } }
+      if (FILT || SPLIT) { my_occ2 += (live & second) ? 1u : 0u; my_occ += (live & !second) ? 1u : 0u; }
       const uint32_t h = agg_hash(kl);
-      const bool hit = live && T.key[h] == kl;
-      if (hit) agg_count<SPLIT, CHUNK>(T, h, ch, second);
-      const bool miss = live && !hit;
+      const bool hit = live & (T.key[h] == kl);
+      if (SPLIT) {
+        if (hit) agg_count<SPLIT, CHUNK>(T, h, ch, second);
+      } else {
+        smem_red_add_if(hit, &T.cnt[h], 1u);
+        if (CHUNK) { if (hit & (ch < T.chk[h])) agg_chunk_min(T.chk, h, ch); }
+      }
+      const bool miss = live & !hit;
       const uint32_t m = __ballot_sync(0xffffffffu, miss);
-      if (miss) pend[np + __popc(m & ((1u << lane) - 1))] = w;
+      smem_st_if(miss, &pend[np + __popc(m & ((1u << lane) - 1))], w);
       np += __popc(m);
     }
+    __syncwarp();
     np = __shfl_sync(0xffffffffu, np, 0);
     // np is the same in every lane: a warp-uniform loop with one structured branch inside, so the warp
     // reconverges after every group of 32 pending words
@@ -413,23 +430,31 @@ __global__ void widen_u32_kernel(const uint32_t* __restrict__ in, uint64_t* __re
 }
 
 // ---------------------------------------------------------------- deNoise ---
-// flags[k] = 1 if entry k survives the sweep: count != 1, or protected by the range-end rule.
-__global__ void denoise_flag_kernel(const uint32_t* __restrict__ counts, uint64_t* __restrict__ flags, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) flags[i] = counts[i] != 1 ? 1 : 0;
-}
-__global__ void denoise_keep_kernel(const uint32_t* __restrict__ keep_idx, const uint32_t* __restrict__ n_keep,
-                                    uint64_t* __restrict__ flags) {
+// An entry survives the sweep unless its count is exactly 1.  The few count-1 entries protected by the range-end
+// rule are marked by the host side with count 0 (a value the state never holds) and get their 1 back here.
+// No flag array: the tile totals are scanned, then every tile recomputes its flags and writes its survivors.
+__global__ void denoise_keep_kernel(const uint32_t* __restrict__ keep_idx, const uint32_t* __restrict__ n_keep, uint32_t keep_cap,
+                                    uint32_t* __restrict__ counts) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < *n_keep) flags[keep_idx[j]] = 1;
+  uint32_t nk = *n_keep; if (nk > keep_cap) nk = keep_cap;
+  if (j < nk) counts[keep_idx[j]] = 0;
 }
-__global__ void denoise_compact_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts,
-                                       const uint64_t* __restrict__ excl, size_t n, uint64_t total,
-                                       uint64_t* __restrict__ out_keys, uint32_t* __restrict__ out_counts) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint64_t me = excl[i], nxt = (i + 1 < n) ? excl[i + 1] : total;
-  if (nxt != me) { out_keys[me] = keys[i]; out_counts[me] = counts[i]; }
+template <bool WRITE>
+__global__ void __launch_bounds__(kScanThreads) denoise_tiles_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, size_t n,
+                                                                    uint64_t* __restrict__ tile_cnt, uint64_t* __restrict__ out_keys,
+                                                                    uint32_t* __restrict__ out_counts) {
+  const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+  uint32_t c[kScanItems]; uint32_t kept = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; i++) { c[i] = base + i < n ? counts[base + i] : 1; kept += c[i] != 1; }
+  uint32_t tot;
+  uint32_t rank = block_exclusive_scan<SumU32>(kept, &tot);
+  if (!WRITE) { if (threadIdx.x == 0) tile_cnt[blockIdx.x] = tot; return; }
+  size_t o = tile_cnt[blockIdx.x] + rank;
+#pragma unroll
+  for (int i = 0; i < kScanItems; i++) {
+    if (c[i] != 1) { out_keys[o] = keys[base + i]; out_counts[o] = c[i] ? c[i] : 1u; o++; }
+  }
 }
 
 }  // namespace shq

@@ -180,8 +180,9 @@ int pick_bin_bits(shq_handle_s* h, uint64_t est_keys, int chunk_bits_needed) {
   while (pb < 12 && (est_keys >> pb) > 65536) pb++;
   if (g_bin_bits) pb = g_bin_bits;
   if (pb > local_bits) pb = local_bits;
-  while (local_bits - pb + chunk_bits_needed > 32 && pb < 13) pb++;
-  if (local_bits - pb + chunk_bits_needed > 32) SHQ_FAIL(SHQ_ERR_ARG, "hb=%d too wide for 32-bit packed keys", h->hb);
+  // the low key bits share a 32-bit word with the chunk id, and 0xFFFFFFFF is the aggregator's empty marker
+  while ((local_bits - pb + chunk_bits_needed > 32 || local_bits - pb > 31) && pb < 13) pb++;
+  if (local_bits - pb + chunk_bits_needed > 32 || local_bits - pb > 31) SHQ_FAIL(SHQ_ERR_ARG, "hb=%d too wide for 32-bit packed keys", h->hb);
   return pb;
 }
 
@@ -244,6 +245,7 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
   const int G = kNumSMs * 2;
   const size_t smem_cle = hp.chunk_line_end ? (size_t)nchunks * 4 + 16 : 0;
   size_t smem_count = sizeof(RollTables) + (size_t)n_bins * 4 + smem_cle;
+  const bool whole = h->nshards == 1;         // every key of the hb-bit space belongs to this handle
   const bool wide = n_bins <= 4096;          // 16 keys per thread and round fit beside the bin arrays
   size_t smem_scatter = sizeof(RollTables) + ((size_t)3 * n_bins + 1) * 4 + (size_t)kScatThreads * (wide ? 16 : 8) * 14 + 16 + smem_cle;
   size_t smem_keys = (size_t)n_bins * 8;
@@ -251,8 +253,14 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
   {
     Phase ph(h, &h->stats.ms_hash_count);
     if (from_text) {
-      SHQ_CUDA(cudaFuncSetAttribute(roll_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
-      roll_count_kernel<<<G, kRollThreads, smem_count, st>>>(hp, h->d_hist.as<uint32_t>()); L++;
+      if (whole) {
+        SHQ_CUDA(cudaFuncSetAttribute(roll_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
+        roll_count_kernel<true><<<G, kRollThreads, smem_count, st>>>(hp, h->d_hist.as<uint32_t>());
+      } else {
+        SHQ_CUDA(cudaFuncSetAttribute(roll_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
+        roll_count_kernel<false><<<G, kRollThreads, smem_count, st>>>(hp, h->d_hist.as<uint32_t>());
+      }
+      L++;
     } else {
       SHQ_CUDA(cudaFuncSetAttribute(hash_keys_kernel<kSinkCount>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_keys));
       hash_keys_kernel<kSinkCount><<<G, 256, smem_keys, st>>>(d_keys, n_keys_in, hp, sk, h->d_hist.as<uint32_t>(), nullptr); L++;
@@ -271,13 +279,12 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
   {
     Phase ph(h, &h->stats.ms_scatter);
     if (from_text) {
-      if (wide) {
-        SHQ_CUDA(cudaFuncSetAttribute(roll_scatter_kernel<kScatThreads, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
-        roll_scatter_kernel<kScatThreads, 16><<<kNumSMs, kScatThreads, smem_scatter, st>>>(hp, h->d_tot.as<uint32_t>(), h->d_packed.as<uint32_t>());
-      } else {
-        SHQ_CUDA(cudaFuncSetAttribute(roll_scatter_kernel<kScatThreads, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
-        roll_scatter_kernel<kScatThreads, 8><<<kNumSMs, kScatThreads, smem_scatter, st>>>(hp, h->d_tot.as<uint32_t>(), h->d_packed.as<uint32_t>());
-      }
+#define SHQ_SCATTER(WW, WH) do { \
+        SHQ_CUDA(cudaFuncSetAttribute(roll_scatter_kernel<kScatThreads, WW, WH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter)); \
+        roll_scatter_kernel<kScatThreads, WW, WH><<<kNumSMs, kScatThreads, smem_scatter, st>>>(hp, h->d_tot.as<uint32_t>(), h->d_packed.as<uint32_t>()); } while (0)
+      if (wide) { if (whole) SHQ_SCATTER(16, true); else SHQ_SCATTER(16, false); }
+      else { if (whole) SHQ_SCATTER(8, true); else SHQ_SCATTER(8, false); }
+#undef SHQ_SCATTER
       L++;
     } else {
       sk.packed = h->d_packed.as<uint32_t>();
@@ -425,12 +432,15 @@ uint64_t compute_positions(shq_handle_s* h) {
   uint64_t& L = h->stats.kernels_launched;
   size_t n = h->n_state;
   if (n == 0) return 0;
-  h->d_pairs.reserve((n + 4) * sizeof(MaxPlus)); h->d_pos.reserve((n + 4) * 8);
+  const size_t ntiles = (n + kScanTile - 1) / kScanTile;
+  h->d_pairs.reserve((ntiles + 4) * sizeof(MaxPlus)); h->d_pos.reserve((n + 4) * 8);
   uint64_t q0 = h->key_lo >> 8;
-  layout_pairs_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->st_keys.as<uint64_t>(), h->st_counts.as<uint32_t>(), n, q0, h->d_pairs.as<MaxPlus>()); L++;
   h->d_misc.reserve(256);
-  exclusive_scan_inplace<MaxPlusOp>(h->d_pairs.as<MaxPlus>(), n, h->d_scan_scratch, st, h->d_misc.as<MaxPlus>(), &L);
-  layout_pos_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->st_keys.as<uint64_t>(), n, q0, h->d_pairs.as<MaxPlus>(), 0, h->d_pos.as<uint64_t>()); L++;
+  MaxPlus* agg = h->d_pairs.as<MaxPlus>();
+  layout_scan_kernel<false><<<(unsigned)ntiles, kScanThreads, 0, st>>>(h->st_keys.as<uint64_t>(), h->st_counts.as<uint32_t>(), n, q0, agg, nullptr, nullptr); L++;
+  exclusive_scan_inplace<MaxPlusOp>(agg, ntiles, h->d_scan_scratch, st, nullptr, &L);
+  layout_scan_kernel<true><<<(unsigned)ntiles, kScanThreads, 0, st>>>(h->st_keys.as<uint64_t>(), h->st_counts.as<uint32_t>(), n, q0, agg,
+                                                                   h->d_pos.as<uint64_t>(), h->d_misc.as<MaxPlus>()); L++;
   MaxPlus tot = read_scalar(h, h->d_misc.as<MaxPlus>());
   long long e = tot.a > tot.b ? tot.a : tot.b;   // f_total(0)
   return (uint64_t)e;
@@ -489,14 +499,16 @@ uint64_t denoise_round(shq_handle_s* h) {
   uint32_t* n_keep = h->d_keep.as<uint32_t>(); uint32_t* keep_idx = n_keep + 4;
   denoise_ranges_kernel<<<1, 32, 0, st>>>(h->st_keys.as<uint64_t>(), h->st_counts.as<uint32_t>(), h->d_pos.as<uint64_t>(), n, h->nslots,
                                         h->xnslots, keep_idx, n_keep, keep_cap); L++;
-  h->d_flags.reserve((n + 4) * 8);
-  denoise_flag_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->st_counts.as<uint32_t>(), h->d_flags.as<uint64_t>(), n); L++;
-  denoise_keep_kernel<<<cdiv(keep_cap, 128), 128, 0, st>>>(keep_idx, n_keep, h->d_flags.as<uint64_t>()); L++;
-  exclusive_scan_inplace<SumU64>(h->d_flags.as<uint64_t>(), n, h->d_scan_scratch, st, h->d_flags.as<uint64_t>() + n, &L);
-  uint64_t kept = read_scalar(h, h->d_flags.as<uint64_t>() + n);
+  const size_t ntiles = (n + kScanTile - 1) / kScanTile;
+  h->d_flags.reserve((ntiles + 4) * 8);
+  uint64_t* tile_cnt = h->d_flags.as<uint64_t>();
+  denoise_keep_kernel<<<cdiv(keep_cap, 128), 128, 0, st>>>(keep_idx, n_keep, keep_cap, h->st_counts.as<uint32_t>()); L++;
+  denoise_tiles_kernel<false><<<(unsigned)ntiles, kScanThreads, 0, st>>>(h->st_keys.as<uint64_t>(), h->st_counts.as<uint32_t>(), n, tile_cnt, nullptr, nullptr); L++;
+  exclusive_scan_inplace<SumU64>(tile_cnt, ntiles, h->d_scan_scratch, st, tile_cnt + ntiles, &L);
+  uint64_t kept = read_scalar(h, tile_cnt + ntiles);
   h->st_keys2.reserve((kept + 4) * 8); h->st_counts2.reserve((kept + 4) * 4);
-  denoise_compact_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->st_keys.as<uint64_t>(), h->st_counts.as<uint32_t>(), h->d_flags.as<uint64_t>(), n, kept,
-                                                     h->st_keys2.as<uint64_t>(), h->st_counts2.as<uint32_t>()); L++;
+  denoise_tiles_kernel<true><<<(unsigned)ntiles, kScanThreads, 0, st>>>(h->st_keys.as<uint64_t>(), h->st_counts.as<uint32_t>(), n, tile_cnt,
+                                                                     h->st_keys2.as<uint64_t>(), h->st_counts2.as<uint32_t>()); L++;
   SHQ_CUDA(cudaGetLastError());
   std::swap(h->st_keys, h->st_keys2); std::swap(h->st_counts, h->st_counts2);
   uint64_t removed = n - kept;

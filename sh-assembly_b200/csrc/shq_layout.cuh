@@ -38,6 +38,49 @@ __global__ void layout_pos_kernel(const uint64_t* __restrict__ keys, size_t n, u
   pos[k] = (uint64_t)e;
 }
 
+// Fused form of the two kernels above around the tile-level scan: the maps are recomputed from (key, count)
+// instead of being stored (32 instead of ~90 bytes of traffic per entry).
+//   layout_reduce_kernel : tile_agg[t] = composition of the maps of tile t
+//   (exclusive MaxPlus scan of tile_agg on the host side)
+//   layout_apply_kernel  : pos[k] for every entry of tile t, seeded with the scanned tile_agg[t]
+__device__ __forceinline__ MaxPlus layout_map(uint64_t key, uint64_t prev_key, bool has_prev, uint32_t count, uint64_t key_lo_q, bool* first, long long* q) {
+  *q = (long long)((key >> 8) - key_lo_q);
+  *first = !has_prev || ((prev_key >> 8) != (key >> 8));
+  long long len = enc_len((uint32_t)(key & 0xFF), count);
+  return MaxPlus{len, *first ? *q + len : kNegInf};
+}
+template <bool APPLY>
+__global__ void __launch_bounds__(kScanThreads) layout_scan_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, size_t n,
+                                                                  uint64_t key_lo_q, MaxPlus* __restrict__ tile_agg, uint64_t* __restrict__ pos,
+                                                                  MaxPlus* __restrict__ grand_total) {
+  const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+  uint64_t k[kScanItems + 1]; uint32_t c[kScanItems];
+  k[0] = (base > 0 && base <= n) ? keys[base - 1] : 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; i++) { k[i + 1] = base + i < n ? keys[base + i] : 0; c[i] = base + i < n ? counts[base + i] : 0; }
+  MaxPlus acc = MaxPlusOp::id();
+#pragma unroll
+  for (int i = 0; i < kScanItems; i++) {
+    if (base + i < n) { bool first; long long q; acc = MaxPlusOp::op(acc, layout_map(k[i + 1], k[i], base + i > 0, c[i], key_lo_q, &first, &q)); }
+  }
+  MaxPlus tot;
+  MaxPlus exc = block_exclusive_scan<MaxPlusOp>(acc, &tot);
+  if (!APPLY) { if (threadIdx.x == 0) tile_agg[blockIdx.x] = tot; return; }
+  MaxPlus run = MaxPlusOp::op(tile_agg[blockIdx.x], exc);
+#pragma unroll
+  for (int i = 0; i < kScanItems; i++) {
+    if (base + i < n) {
+      bool first; long long q;
+      MaxPlus m = layout_map(k[i + 1], k[i], base + i > 0, c[i], key_lo_q, &first, &q);
+      long long e = run.a > run.b ? run.a : run.b;      // f(0) of everything before this entry
+      if (first && q > e) e = q;
+      pos[base + i] = (uint64_t)e;
+      run = MaxPlusOp::op(run, m);
+    }
+  }
+  if (grand_total && blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) *grand_total = run;
+}
+
 __device__ __forceinline__ uint64_t entry_end(const uint64_t* keys, const uint32_t* counts, const uint64_t* pos, size_t k) {
   return pos[k] + enc_len((uint32_t)(keys[k] & 0xFF), counts[k]) - 1;
 }

@@ -61,20 +61,35 @@ __device__ __forceinline__ uint32_t pack4_nocheck(uint32_t w) {
   return ((x * 0x41041u) >> 18) & 0xFFu;
 }
 
+__device__ __forceinline__ uint64_t rol1(uint64_t v) {
+  uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+  return ((uint64_t)__funnelshift_l(lo, hi, 1) << 32) | __funnelshift_l(hi, lo, 1);
+}
+__device__ __forceinline__ uint64_t ror1(uint64_t v) {
+  uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+  return ((uint64_t)__funnelshift_r(hi, lo, 1) << 32) | __funnelshift_r(lo, hi, 1);
+}
+
 // Per-thread generator of the key stream of one read after another (reads first, first+stride, ...).
-// step() advances by one unit -- open+prime a read (1 key), a group of 8 windows (8 keys), or a single
-// window (<= 1 key) -- and hands every key to emit(key, chunk).  Never more than 8 keys per call.
+// step() advances by one unit -- open+prime a read (1 key), a group of up to 8 windows, or a single
+// byte-exact window (<= 1 key) -- and hands every key to emit(key, chunk).  Never more than 8 keys per call.
+// Lanes whose reads have the same length run the same sequence of units, i.e. stay converged.
 struct Roller {
   const HashParams* hp; const RollTables* tab;
   uint32_t read, read_end, stride;
   uint32_t s, len, pos;        // current read: start offset, length, index of the NEXT char to roll in
   uint32_t slow_until;         // windows whose incoming char has index < slow_until take the byte-exact step
-  uint64_t fh, rh, ocur; uint32_t chunk;
+  uint64_t fh, rh; uint32_t chunk;
+  // two streams of aligned 64-bit text words: incoming characters (at pos) and outgoing ones (at pos - K);
+  // lo holds the word with the current character, hi the next one (loaded one group ahead)
+  uint64_t ilo, ihi, olo, ohi;
+  const uint64_t* inext; uint32_t odelta;      // next incoming word to load; the outgoing stream trails by odelta words
+  const uint64_t* last_word;                   // word holding the last character of the read: nothing beyond is touched
   bool active;                 // a read is open and primed (fh/rh valid for the window ending at pos-1)
-  bool out_ok;                 // ocur holds the aligned word that follows the outgoing group just consumed
+  bool cont;                   // the stream registers are valid for pos
 
   __device__ __forceinline__ void start(const HashParams* hp_, const RollTables* tab_, uint32_t first, uint32_t end, uint32_t stride_) {
-    hp = hp_; tab = tab_; read = first; read_end = end; stride = stride_; active = false; out_ok = false; slow_until = 0;
+    hp = hp_; tab = tab_; read = first; read_end = end; stride = stride_; active = false; cont = false; slow_until = 0;
   }
   // prime at sub-read start s0; false if fewer than K chars remain (cqf/CQF_mt.h:624-625)
   __device__ __forceinline__ bool prime(uint32_t s0) {
@@ -94,19 +109,31 @@ struct Roller {
       if (nb > K - i) nb = K - i;
       for (uint32_t b = 0; b < nb; b++, i++) {
         unsigned char c = (unsigned char)w; w >>= 8;
-        f = rotl64(f, 1) ^ tab->in_f[c];                 // == xor of rol(seed, K-1-i)
-        r ^= rotr64(tab->in_r[c], K - 1 - i);            // in_r = rol(seed', K-1)  ->  rol(seed', i)
+        f = rol1(f) ^ tab->in_f[c];                      // ends as the xor of rol(seed(c_i), K-1-i)
+        r = ror1(r) ^ tab->in_r[c];                      // in_r = rol(seed', K-1): ends as the xor of rol(seed'(c_i), i)
         anybad |= tab->bad[c];
       }
     }
     fh = f; rh = r; pos = s0 + K;
     if (anybad) slow_until = s0 + 2 * K;                 // until every byte of the primed window has left
-    out_ok = false;
+    cont = false;
     return true;
   }
   __device__ __forceinline__ void roll(unsigned char cout, unsigned char cin) {   // base/nthash.hpp:305-309
-    fh = rotl64(fh, 1) ^ tab->out_f[cout] ^ tab->in_f[cin];
-    rh = rotr64(rh, 1) ^ tab->out_r[cout] ^ tab->in_r[cin];
+    fh = rol1(fh) ^ tab->out_f[cout] ^ tab->in_f[cin];
+    rh = ror1(rh) ^ tab->out_r[cout] ^ tab->in_r[cin];
+  }
+  __device__ __forceinline__ uint64_t guarded(const uint64_t* p) const { return p <= last_word ? __ldg(p) : 0; }
+  __device__ __forceinline__ void open_streams(const unsigned char* base) {
+    const uintptr_t ia = reinterpret_cast<uintptr_t>(base + pos), oa = ia - hp->K;
+    const uint64_t* ip = reinterpret_cast<const uint64_t*>(ia & ~(uintptr_t)7);
+    const uint64_t* op = reinterpret_cast<const uint64_t*>(oa & ~(uintptr_t)7);
+    last_word = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(base + len - 1) & ~(uintptr_t)7);
+    odelta = (uint32_t)(ip - op);
+    ilo = __ldg(ip); ihi = guarded(ip + 1);
+    olo = __ldg(op); ohi = guarded(op + 1);
+    inext = ip + 2;
+    cont = true;
   }
   // returns false when this thread has no reads left
   template <class Emit>
@@ -124,37 +151,48 @@ struct Roller {
     if (pos >= len) { active = false; return true; }
     const unsigned char* base = reinterpret_cast<const unsigned char*>(hp->text) + s;
     const uint32_t K = hp->K;
-    const uintptr_t ia = reinterpret_cast<uintptr_t>(base + pos);
-    if ((ia & 7) == 0 && len - pos >= 8 && pos >= slow_until) {
-      const uint64_t in8 = __ldg(reinterpret_cast<const uint64_t*>(ia));
+    if (pos >= slow_until) {
+      if (!cont) open_streams(base);
+      const uint32_t r = len - pos < 8 ? len - pos : 8;
+      const uint32_t ish = (uint32_t)(reinterpret_cast<uintptr_t>(base + pos) & 7) * 8;
+      const uint32_t osh = (uint32_t)(reinterpret_cast<uintptr_t>(base + pos - K) & 7) * 8;
+      uint64_t in8 = ish ? (ilo >> ish) | (ihi << (64 - ish)) : ilo;
+      const uint64_t out8 = osh ? (olo >> osh) | (ohi << (64 - osh)) : olo;
+      if (r < 8) { const uint64_t m = (1ULL << (8 * r)) - 1; in8 = (in8 & m) | (0x4141414141414141ULL & ~m); }   // past the read: 'A'
       bool ok = true;
       const uint32_t ic = pack4((uint32_t)in8, &ok) | (pack4((uint32_t)(in8 >> 32), &ok) << 8);
       if (ok) {
-        const uintptr_t oa = ia - K;
-        const uint32_t sh = (uint32_t)(oa & 7) * 8;
-        const uint64_t* op = reinterpret_cast<const uint64_t*>(oa & ~(uintptr_t)7);
-        uint64_t w0 = out_ok ? ocur : __ldg(op);
-        uint64_t out8 = w0;
-        if (sh) { uint64_t w1 = __ldg(op + 1); out8 = (w0 >> sh) | (w1 << (64 - sh)); ocur = w1; out_ok = true; }
-        else out_ok = false;
+        // next group's words, one group ahead of their use
+        ilo = ihi; ihi = guarded(inext);
+        olo = ohi; ohi = guarded(inext - odelta);
+        inext++;
         const uint32_t oc = pack4_nocheck((uint32_t)out8) | (pack4_nocheck((uint32_t)(out8 >> 32)) << 8);
         // nibble n of ze / zo = (out << 2 | in) of window 2n / 2n+1
         const uint32_t ze = (ic & 0x3333u) | ((oc & 0x3333u) << 2);
         const uint32_t zo = ((ic >> 2) & 0x3333u) | (oc & 0xCCCCu);
+        const uint4* fast = tab->fast;
+        if (r == 8) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          const uint32_t idx = (((j & 1) ? zo : ze) >> (4 * (j >> 1))) & 15u;
-          const uint4 t = tab->fast[idx];
-          fh = rotl64(fh, 1) ^ ((uint64_t)t.x | ((uint64_t)t.y << 32));
-          rh = rotr64(rh, 1) ^ ((uint64_t)t.z | ((uint64_t)t.w << 32));
-          emit((fh < rh ? fh : rh) & mask, chunk);
+          for (int j = 0; j < 8; j++) {
+            const uint4 t = fast[(((j & 1) ? zo : ze) >> (4 * (j >> 1))) & 15u];
+            fh = rol1(fh) ^ ((uint64_t)t.x | ((uint64_t)t.y << 32));
+            rh = ror1(rh) ^ ((uint64_t)t.z | ((uint64_t)t.w << 32));
+            emit((fh < rh ? fh : rh) & mask, chunk);
+          }
+        } else {
+          for (uint32_t j = 0; j < r; j++) {               // tail of the read
+            const uint4 t = fast[(((j & 1) ? zo : ze) >> (4 * (j >> 1))) & 15u];
+            fh = rol1(fh) ^ ((uint64_t)t.x | ((uint64_t)t.y << 32));
+            rh = ror1(rh) ^ ((uint64_t)t.z | ((uint64_t)t.w << 32));
+            emit((fh < rh ? fh : rh) & mask, chunk);
+          }
         }
-        pos += 8;
+        pos += r;
         return true;
       }
       slow_until = pos + 8 + K;                           // some byte of this group is not ACGT
     }
-    out_ok = false;
+    cont = false;
     unsigned char cin = __ldg(base + pos);
     if (cin == 'N') {                                     // restart after the N (CQF_mt.h:680-683)
       const uint32_t su = slow_until;
@@ -173,6 +211,7 @@ constexpr int kRollThreads = 512;
 
 // Pass 1: global histogram of bins.
 // dynamic smem: RollTables + n_bins * 4 (+ chunk map)
+template <bool WHOLE>          // WHOLE: unsharded handle, every key is ours
 __global__ void __launch_bounds__(kRollThreads) roll_count_kernel(HashParams hp, uint32_t* __restrict__ g_hist) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RollTables* tab = reinterpret_cast<RollTables*>(smem_raw);
@@ -190,9 +229,8 @@ __global__ void __launch_bounds__(kRollThreads) roll_count_kernel(HashParams hp,
   R.start(&hp, tab, blockIdx.x * blockDim.x + threadIdx.x, hp.n_reads, gridDim.x * blockDim.x);
   const uint64_t mask = hp.hb >= 64 ? ~0ULL : ((1ULL << hp.hb) - 1);
   const uint64_t key_lo = hp.key_lo, key_hi = hp.key_hi; const int lb = hp.lb;
-  const bool whole = key_lo == 0 && key_hi > mask;      // unsharded: every key is ours
   auto emit = [&](uint64_t key, uint32_t) {
-    if (whole) { atomicAdd(&s_hist[(uint32_t)(key >> lb)], 1u); return; }
+    if (WHOLE) { atomicAdd(&s_hist[(uint32_t)(key >> lb)], 1u); return; }
     if (key < key_lo || key >= key_hi) return;
     atomicAdd(&s_hist[(uint32_t)((key - key_lo) >> lb)], 1u);
   };
@@ -212,7 +250,7 @@ __global__ void __launch_bounds__(kRollThreads) roll_count_kernel(HashParams hp,
 // dynamic smem: RollTables + (3 * n_bins + 1) * 4 + THREADS * W * 14 (+ chunk map)
 constexpr int kScatThreads = 768;
 constexpr int kScatW = 16;
-template <int THREADS, int W>
+template <int THREADS, int W, bool WHOLE>
 __global__ void __launch_bounds__(THREADS) roll_scatter_kernel(HashParams hp, uint32_t* __restrict__ g_cursor, uint32_t* __restrict__ packed) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RollTables* tab = reinterpret_cast<RollTables*>(smem_raw);
@@ -237,22 +275,23 @@ __global__ void __launch_bounds__(THREADS) roll_scatter_kernel(HashParams hp, ui
   R.start(&hp, tab, blockIdx.x * blockDim.x + threadIdx.x, hp.n_reads, gridDim.x * blockDim.x);
   const uint64_t mask = hp.hb >= 64 ? ~0ULL : ((1ULL << hp.hb) - 1);
   const uint64_t key_lo = hp.key_lo, key_hi = hp.key_hi; const int lb = hp.lb;
-  const bool whole = key_lo == 0 && key_hi > mask;
   const uint32_t lowmask = lb >= 32 ? 0xFFFFFFFFu : ((1u << lb) - 1);
   const int per = (hp.n_bins + THREADS - 1) / THREADS;      // bins per thread in the scan
   bool more = true;
   int produced = 0;
+  uint32_t* my_key = s_key + threadIdx.x;                    // slot of this thread's next key: stride THREADS
+  const uint32_t br_off = (uint32_t)(s_br - s_key);
   auto emit = [&](uint64_t key, uint32_t ch) {
-    if (!whole && (key < key_lo || key >= key_hi)) return;
-    uint64_t rel = key - key_lo;
+    if (!WHOLE && (key < key_lo || key >= key_hi)) return;
+    uint64_t rel = WHOLE ? key : key - key_lo;
     uint32_t bin = (uint32_t)(rel >> lb);
-    int idx = produced * THREADS + threadIdx.x;
-    s_key[idx] = ((uint32_t)rel & lowmask) | (lb >= 32 ? 0 : (ch << lb));
-    s_br[idx] = (bin << 16) | atomicAdd(&s_hist[bin], 1u);
+    my_key[0] = ((uint32_t)rel & lowmask) | (lb >= 32 ? 0 : (ch << lb));
+    my_key[br_off] = (bin << 16) | atomicAdd(&s_hist[bin], 1u);
+    my_key += THREADS;
     produced++;
   };
   for (;;) {
-    produced = 0;
+    produced = 0; my_key = s_key + threadIdx.x;
     while (more && produced + 8 <= W) more = R.step(mask, emit);
     int any = __syncthreads_or(produced > 0);
     if (!any) break;
@@ -276,6 +315,7 @@ __global__ void __launch_bounds__(THREADS) roll_scatter_kernel(HashParams hp, ui
     }
     __syncthreads();
     const uint32_t total = s_off[hp.n_bins];
+#pragma unroll 4
     for (int j = 0; j < produced; j++) {      // C
       int idx = j * THREADS + threadIdx.x;
       uint32_t br = s_br[idx];
@@ -285,6 +325,7 @@ __global__ void __launch_bounds__(THREADS) roll_scatter_kernel(HashParams hp, ui
       s_sbin[dst] = (uint16_t)bin;
     }
     __syncthreads();
+#pragma unroll 4
     for (uint32_t i = threadIdx.x; i < total; i += THREADS) packed[s_delta[s_sbin[i]] + i] = s_sorted[i];   // D
     __syncthreads();
   }

@@ -115,6 +115,32 @@ int shq_state_view(shq_t h, const uint64_t** d_keys, const uint32_t** d_counts, 
 int shq_adopt_state(shq_t h, const uint64_t* d_keys, const uint32_t* d_counts, size_t n, uint64_t ndistinct,
                     uint64_t nelts);
 int shq_set_counts(shq_t h, uint64_t ndistinct, uint64_t nelts);
+/* Two-level exchange (4 bytes per k-mer on the wire instead of 8):
+ * shq_mg_bin_fastq_device: hash the chunk(s) and bin the keys over the WHOLE key space into 2^coarse_bits bins
+ *   (owner = high log2(world) bits of the bin index, so one owner's bins are one slice).  *d_words = binned
+ *   32-bit words (low hb - coarse_bits key bits), *d_bin_off = 2^coarse_bits + 1 offsets; both device pointers
+ *   into the handle, valid until its next call.
+ * shq_mg_insert_binned: d_recv holds, for source s = 0..world-1 starting at word seg_start[s] (host array), this
+ *   shard's coarse bins in order; d_counts[s * cps + c] (device, cps = 2^coarse_bits / world) = words of coarse bin
+ *   c from source s.  Splits every coarse bin into 2^fine_bits bins and inserts (aggregate + merge).           */
+/* Sharded image (no gather): the slot layout is a max-plus scan, so a shard needs from its predecessors only their
+ * composed map (two int64).  shq_mg_layout_aggregate: this shard's composed map in global slot coordinates.
+ * shq_mg_layout_tail: lay the shard out behind `carry` (composition of all previous shards' maps) and copy the
+ *   entries whose slots reach past the shard's last home slot -- they belong to the NEXT shard's blocks -- into
+ *   the caller's device buffers.  shq_mg_materialize_shard: the blocks of this shard's quotient range (the last
+ *   shard also owns the xnslots extension), given the previous shard's spill; *d_image points into the handle.
+ * shq_header: the 128-byte qfmetadata header for given global counters.                                         */
+int shq_mg_layout_aggregate(shq_t h, int64_t agg[2]);
+int shq_mg_layout_tail(shq_t h, const int64_t carry[2], size_t cap, uint64_t* d_keys, uint32_t* d_counts, uint64_t* d_pos,
+                       size_t* n_tail);
+int shq_mg_materialize_shard(shq_t h, const uint64_t* d_spill_keys, const uint32_t* d_spill_counts,
+                             const uint64_t* d_spill_pos, size_t n_spill, const uint8_t** d_image, uint64_t* first_block,
+                             uint64_t* n_blocks);
+int shq_header(shq_t h, uint64_t ndistinct, uint64_t nelts, uint8_t out[128]);
+int shq_mg_bin_fastq_device(shq_t h, const char* d_text, size_t n, int K, int coarse_bits, const uint32_t** d_words,
+                            const uint32_t** d_bin_off, size_t* n_words);
+int shq_mg_insert_binned(shq_t h, const uint32_t* d_recv, const uint64_t* seg_start, const uint32_t* d_counts, int world,
+                         int coarse_bits, int fine_bits, size_t n_words);
 /* device-to-device copy on the handle's stream, synchronous (plumbing for callers without a CUDA binding) */
 int shq_copy_device(shq_t h, void* d_dst, const void* d_src, size_t bytes);
 

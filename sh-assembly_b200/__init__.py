@@ -67,6 +67,7 @@ EXPORTS = [
     "shq_unitigs_write_fasta", "shq_unitigs_fasta", "shq_unitigs_free", "shq_get_stats", "shq_reset_stats", "shq_stream",
     "shq_reader_open", "shq_reader_open_memory", "shq_reader_next", "shq_reader_close", "shq_build_kmer_spectrum",
     "shq_materialize", "shq_param_block", "shq_cdfpoi_positive", "shq_cdfpoi",
+    "shq_mg_bin_fastq_device", "shq_mg_insert_binned", "shq_mg_layout_aggregate", "shq_mg_layout_tail", "shq_mg_materialize_shard", "shq_header",
     "shq_hash_fastq_device", "shq_partition_keys_device", "shq_state_view", "shq_adopt_state", "shq_set_counts", "shq_copy_device",
 ]
 
@@ -123,6 +124,12 @@ def lib():
         L.shq_stream.argtypes = [vp]
         L.shq_hash_fastq_device.argtypes = [vp, vp, sz, C.c_int, vp, sz, C.POINTER(sz)]
         L.shq_partition_keys_device.argtypes = [vp, vp, sz, C.c_int, vp, C.POINTER(u64)]
+        L.shq_mg_bin_fastq_device.argtypes = [vp, vp, sz, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(sz)]
+        L.shq_mg_insert_binned.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, sz]
+        L.shq_mg_layout_aggregate.argtypes = [vp, C.POINTER(C.c_int64)]
+        L.shq_mg_layout_tail.argtypes = [vp, C.POINTER(C.c_int64), sz, vp, vp, vp, C.POINTER(sz)]
+        L.shq_mg_materialize_shard.argtypes = [vp, vp, vp, vp, sz, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]
+        L.shq_header.argtypes = [vp, u64, u64, vp]
         L.shq_state_view.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(sz)]
         L.shq_adopt_state.argtypes = [vp, vp, vp, sz, u64, u64]
         L.shq_set_counts.argtypes = [vp, u64, u64]
@@ -391,6 +398,37 @@ class CQF:
         counts = (C.c_uint64 * nparts)()
         self._check(self.L.shq_partition_keys_device(self.h, d_in, n, nparts, d_out, counts))
         return list(counts)
+
+    def mg_bin_fastq_device(self, d_text, n, K, coarse_bits):
+        """(device pointer to the binned words, device pointer to the 2^coarse_bits + 1 offsets, number of words)"""
+        w, o, nw = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        self._check(self.L.shq_mg_bin_fastq_device(self.h, d_text, n, K, coarse_bits, C.byref(w), C.byref(o), C.byref(nw)))
+        return w.value, o.value, nw.value
+
+    def mg_insert_binned(self, d_recv, seg_start, d_counts, world, coarse_bits, fine_bits, n_words):
+        ss = np.ascontiguousarray(seg_start, np.uint64)
+        self._check(self.L.shq_mg_insert_binned(self.h, d_recv, ss.ctypes.data, d_counts, world, coarse_bits, fine_bits, n_words))
+
+    def mg_layout_aggregate(self):
+        g = (C.c_int64 * 2)()
+        self._check(self.L.shq_mg_layout_aggregate(self.h, g))
+        return int(g[0]), int(g[1])
+
+    def mg_layout_tail(self, carry, cap, d_keys, d_counts, d_pos):
+        g = (C.c_int64 * 2)(int(carry[0]), int(carry[1]))
+        nt = C.c_size_t()
+        self._check(self.L.shq_mg_layout_tail(self.h, g, cap, d_keys, d_counts, d_pos, C.byref(nt)))
+        return nt.value
+
+    def mg_materialize_shard(self, d_keys, d_counts, d_pos, n_spill):
+        img, fb, nb = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        self._check(self.L.shq_mg_materialize_shard(self.h, d_keys, d_counts, d_pos, n_spill, C.byref(img), C.byref(fb), C.byref(nb)))
+        return img.value, fb.value, nb.value
+
+    def header(self, ndistinct, nelts) -> bytes:
+        buf = np.zeros(128, np.uint8)
+        self._check(self.L.shq_header(self.h, ndistinct, nelts, buf.ctypes.data))
+        return buf.tobytes()
 
     def state_view(self):
         k, c, n = C.c_void_p(), C.c_void_p(), C.c_size_t()

@@ -11,6 +11,7 @@
 
 #include "shq_aggregate.cuh"
 #include "shq_common.cuh"
+#include "shq_exchange.cuh"
 #include "shq_hash.cuh"
 #include "shq_layout.cuh"
 #include "shq_roll.cuh"
@@ -65,6 +66,7 @@ struct shq_handle_s {
   DevBuf d_tmp_keys2, d_tmp_counts2, d_run2_keys, d_run2_counts;
   DevBuf d_run_keys, d_run_counts, d_run_chunk, d_split, d_heads, d_heads64, d_scan_scratch, d_misc;
   DevBuf d_pairs, d_pos, d_flags, d_keep, d_q_in, d_q_cnt, d_q_was;
+  DevBuf d_seg, d_fine, d_packed2;   // multi-GPU second-level split
   int* d_err = nullptr;          // device error flag
   void* h_pinned = nullptr;      // small pinned readback area (4 KiB + chunk hist)
   size_t h_pinned_cap = 0;
@@ -203,8 +205,10 @@ uint32_t index_lines(shq_handle_s* h, const char* d_text, size_t n_text) {
 
 // Both hashing passes over the batch text (or a raw key array): count -> offsets -> scatter.
 // On return d_packed holds the binned words and d_binoff the (n_bins+1) bin offsets.
+// global_bits > 0: bin over the WHOLE key space [0, 2^hb) into 2^global_bits bins, whatever this handle's shard
+// is (first level of the multi-GPU exchange: bins of one owner are contiguous).
 void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_t* h_chunk_ends, int nchunks, int K,
-               const uint64_t* d_keys, size_t n_keys_in, bool armed, BatchBins* bb) {
+               const uint64_t* d_keys, size_t n_keys_in, bool armed, BatchBins* bb, int global_bits = 0) {
   cudaStream_t st = h->stream;
   uint64_t& L = h->stats.kernels_launched;
   HashParams hp{};
@@ -228,11 +232,13 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
   int chunk_bits = 0;
   if (armed) { while ((1 << chunk_bits) < nchunks) chunk_bits++; if (chunk_bits > 12) SHQ_FAIL(SHQ_ERR_ARG, "too many chunks in one batch"); }
   uint64_t est = from_text ? (uint64_t)(n_text / 3) : (uint64_t)n_keys_in;
-  int pb = pick_bin_bits(h, est / (uint64_t)h->nshards + 1, chunk_bits);
+  int pb = global_bits ? global_bits : pick_bin_bits(h, est / (uint64_t)h->nshards + 1, chunk_bits);
   int shard_bits = 0; while ((1 << shard_bits) < h->nshards) shard_bits++;
+  if (global_bits) shard_bits = 0;
   int lb = h->hb - shard_bits - pb;
+  if (lb < 1 || lb > 31) SHQ_FAIL(SHQ_ERR_ARG, "bin geometry: %d low key bits do not fit the packed word", lb);
   int n_bins = 1 << pb;
-  hp.hb = h->hb; hp.lb = lb; hp.key_lo = h->key_lo; hp.key_hi = h->key_hi; hp.n_bins = n_bins;
+  hp.hb = h->hb; hp.lb = lb; hp.key_lo = global_bits ? 0 : h->key_lo; hp.key_hi = global_bits ? (1ULL << h->hb) : h->key_hi; hp.n_bins = n_bins;
   hp.nchunks = nchunks;
   hp.chunk_line_end = (armed && from_text) ? h->d_chunk_line_end.as<uint32_t>() : nullptr;
   h->d_hist.reserve((size_t)(n_bins + 1) * 4);
@@ -245,7 +251,7 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
   const int G = kNumSMs * 2;
   const size_t smem_cle = hp.chunk_line_end ? (size_t)nchunks * 4 + 16 : 0;
   size_t smem_count = sizeof(RollTables) + (size_t)n_bins * 4 + smem_cle;
-  const bool whole = h->nshards == 1;         // every key of the hb-bit space belongs to this handle
+  const bool whole = h->nshards == 1 || global_bits != 0;   // every key of the hb-bit space is binned
   const bool wide = n_bins <= 4096;          // 16 keys per thread and round fit beside the bin arrays
   size_t smem_scatter = sizeof(RollTables) + ((size_t)3 * n_bins + 1) * 4 + (size_t)kScatThreads * (wide ? 16 : 8) * 14 + 16 + smem_cle;
   size_t smem_keys = (size_t)n_bins * 8;
@@ -426,25 +432,29 @@ uint64_t merge_run(shq_handle_s* h, const Run& R, int nchunks, std::vector<uint3
   return n_new;
 }
 
-// positions of every state entry in the canonical layout -> d_pos; returns one past the last used slot
-uint64_t compute_positions(shq_handle_s* h) {
+// positions of every state entry in the canonical layout -> d_pos; returns one past the last used slot.
+// q0 = quotient of slot 0 of the coordinate system, init = composed map of everything before entry 0 (both trivial
+// for an unsharded filter); agg_out (host, optional) receives the composed map of THIS state alone.
+uint64_t compute_positions(shq_handle_s* h, uint64_t q0, MaxPlus init, MaxPlus* agg_out = nullptr, bool positions = true) {
   cudaStream_t st = h->stream;
   uint64_t& L = h->stats.kernels_launched;
   size_t n = h->n_state;
-  if (n == 0) return 0;
+  if (n == 0) { if (agg_out) *agg_out = MaxPlusOp::id(); return (uint64_t)(init.a > init.b ? init.a : init.b); }
   const size_t ntiles = (n + kScanTile - 1) / kScanTile;
   h->d_pairs.reserve((ntiles + 4) * sizeof(MaxPlus)); h->d_pos.reserve((n + 4) * 8);
-  uint64_t q0 = h->key_lo >> 8;
   h->d_misc.reserve(256);
   MaxPlus* agg = h->d_pairs.as<MaxPlus>();
-  layout_scan_kernel<false><<<(unsigned)ntiles, kScanThreads, 0, st>>>(h->st_keys.as<uint64_t>(), h->st_counts.as<uint32_t>(), n, q0, agg, nullptr, nullptr); L++;
-  exclusive_scan_inplace<MaxPlusOp>(agg, ntiles, h->d_scan_scratch, st, nullptr, &L);
+  layout_scan_kernel<false><<<(unsigned)ntiles, kScanThreads, 0, st>>>(h->st_keys.as<uint64_t>(), h->st_counts.as<uint32_t>(), n, q0, agg, nullptr, nullptr, init); L++;
+  exclusive_scan_inplace<MaxPlusOp>(agg, ntiles, h->d_scan_scratch, st, h->d_misc.as<MaxPlus>() + 1, &L);
+  if (agg_out) *agg_out = read_scalar(h, h->d_misc.as<MaxPlus>() + 1);
+  if (!positions) return 0;
   layout_scan_kernel<true><<<(unsigned)ntiles, kScanThreads, 0, st>>>(h->st_keys.as<uint64_t>(), h->st_counts.as<uint32_t>(), n, q0, agg,
-                                                                   h->d_pos.as<uint64_t>(), h->d_misc.as<MaxPlus>()); L++;
+                                                                   h->d_pos.as<uint64_t>(), h->d_misc.as<MaxPlus>(), init); L++;
   MaxPlus tot = read_scalar(h, h->d_misc.as<MaxPlus>());
   long long e = tot.a > tot.b ? tot.a : tot.b;   // f_total(0)
   return (uint64_t)e;
 }
+uint64_t compute_positions(shq_handle_s* h) { return compute_positions(h, h->key_lo >> 8, MaxPlusOp::id()); }
 
 void ensure_state(shq_handle_s* h);
 
@@ -692,7 +702,7 @@ void free_handle(shq_handle_s* h) {
                     &h->d_binoff, &h->d_packed, &h->d_tmp_keys, &h->d_tmp_counts, &h->d_tmp_chunk, &h->d_nout, &h->d_occ,
                     &h->d_dense_off, &h->d_run_keys, &h->d_run_counts, &h->d_run_chunk, &h->d_split, &h->d_heads, &h->d_heads64,
                     &h->d_scan_scratch, &h->d_misc, &h->d_pairs, &h->d_pos, &h->d_flags, &h->d_keep, &h->d_q_in, &h->d_q_cnt, &h->d_q_was,
-                    &h->d_tmp_keys2, &h->d_tmp_counts2, &h->d_run2_keys, &h->d_run2_counts};
+                    &h->d_tmp_keys2, &h->d_tmp_counts2, &h->d_run2_keys, &h->d_run2_counts, &h->d_seg, &h->d_fine, &h->d_packed2};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : h->pin_buf) b.release();
   for (auto& b : h->pin_queue) cudaEventDestroy(b.ev);
@@ -1131,6 +1141,170 @@ int shq_partition_keys_device(shq_t h, const uint64_t* d_in, size_t n, int npart
     starts[a.np] = a.n;
     for (int o = 0; o < a.np; o++) a.counts[o] = starts[o + 1] - starts[o];
   SHQ_API_END
+}
+
+int shq_mg_bin_fastq_device(shq_t h, const char* d_text, size_t n, int K, int coarse_bits, const uint32_t** d_words,
+                            const uint32_t** d_bin_off, size_t* n_words) {
+  if (!h || (!d_text && n) || !d_words || !d_bin_off || !n_words || coarse_bits < 1 || coarse_bits > 12) return SHQ_ERR_ARG;
+  struct { const char* t; size_t n; int K, cb; const uint32_t** w; const uint32_t** o; size_t* nw; } args{d_text, n, K, coarse_bits, d_words, d_bin_off, n_words};
+  SHQ_API_BEGIN(h)
+    flush_stage(h);
+    *a.nw = 0; *a.w = nullptr; *a.o = nullptr;
+    if (a.n == 0) return;
+    const char* src = a.t;
+    if (reinterpret_cast<uintptr_t>(src) & 15) {
+      h->d_text.reserve(a.n + 64);
+      SHQ_CUDA(cudaMemcpyAsync(h->d_text.p, src, a.n, cudaMemcpyDeviceToDevice, h->stream));
+      src = h->d_text.as<char>();
+    }
+    uint64_t end = a.n;
+    BatchBins bb;
+    bin_batch(h, src, a.n, &end, 1, a.K, nullptr, 0, false, &bb, a.cb);
+    SHQ_CUDA(cudaStreamSynchronize(h->stream));
+    h->stats.batches++;
+    *a.nw = bb.n_keys; *a.w = h->d_packed.as<uint32_t>(); *a.o = h->d_binoff.as<uint32_t>();
+  SHQ_API_END
+}
+
+int shq_mg_insert_binned(shq_t h, const uint32_t* d_recv, const uint64_t* seg_start, const uint32_t* d_counts, int world,
+                         int coarse_bits, int fine_bits, size_t n_words) {
+  if (!h || world < 1 || world > 64 || !seg_start || (n_words && (!d_recv || !d_counts)) || fine_bits < 0 || fine_bits > 6) return SHQ_ERR_ARG;
+  struct { const uint32_t* r; const uint64_t* ss; const uint32_t* c; int world, cb, fb; size_t n; } args{d_recv, seg_start, d_counts, world, coarse_bits, fine_bits, n_words};
+  SHQ_API_BEGIN(h)
+    flush_stage(h);
+    ensure_state(h);
+    if (a.n == 0) return;
+    if (a.world != h->nshards) SHQ_FAIL(SHQ_ERR_ARG, "world %d != shards of this handle %d", a.world, h->nshards);
+    if (a.n >= ((size_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "more than 2^32 words in one exchange batch");
+    cudaStream_t st = h->stream;
+    uint64_t& L = h->stats.kernels_launched;
+    int shard_bits = 0; while ((1 << shard_bits) < h->nshards) shard_bits++;
+    const int cps = 1 << (a.cb - shard_bits);            // coarse bins per shard
+    const int lbc = h->hb - a.cb, lbf = lbc - a.fb;
+    if (a.cb < shard_bits || lbf < 1 || lbc > 31) SHQ_FAIL(SHQ_ERR_ARG, "bad exchange geometry (coarse %d, fine %d bits)", a.cb, a.fb);
+    const int nfine = cps << a.fb;
+    BatchBins bb;
+    {
+      Phase ph(h, &h->stats.ms_scatter);
+      h->d_seg.reserve(((size_t)a.world * (cps + 1) + a.world + 8) * 8);
+      uint64_t* d_seg_start = h->d_seg.as<uint64_t>();
+      uint64_t* seg_beg = d_seg_start + a.world + 4;
+      SHQ_CUDA(cudaMemcpyAsync(d_seg_start, a.ss, (size_t)a.world * 8, cudaMemcpyHostToDevice, st));
+      seg_table_kernel<<<1, 64, 0, st>>>(a.c, d_seg_start, a.world, cps, seg_beg); L++;
+      h->d_fine.reserve(((size_t)nfine + 2) * 4);
+      h->d_binoff.reserve(((size_t)nfine + 2) * 4);
+      SHQ_CUDA(cudaMemsetAsync(h->d_fine.p, 0, ((size_t)nfine + 1) * 4, st));
+      int parts = 1; while (cps * parts < 4 * kNumSMs) parts *= 2;
+      resplit_kernel<true><<<cps * parts, kSplitThreads, 0, st>>>(a.r, seg_beg, a.world, cps, parts, lbc, a.fb, h->d_fine.as<uint32_t>(), nullptr); L++;
+      SHQ_CUDA(cudaMemcpyAsync(h->d_binoff.p, h->d_fine.p, (size_t)nfine * 4, cudaMemcpyDeviceToDevice, st));
+      exclusive_scan_inplace<SumU32>(h->d_binoff.as<uint32_t>(), nfine, h->d_scan_scratch, st, h->d_binoff.as<uint32_t>() + nfine, &L);
+      SHQ_CUDA(cudaMemcpyAsync(h->d_fine.p, h->d_binoff.p, (size_t)nfine * 4, cudaMemcpyDeviceToDevice, st));
+      h->d_packed.reserve((a.n + 4) * 4);
+      resplit_kernel<false><<<cps * parts, kSplitThreads, 0, st>>>(a.r, seg_beg, a.world, cps, parts, lbc, a.fb, h->d_fine.as<uint32_t>(),
+                                                                 h->d_packed.as<uint32_t>()); L++;
+      SHQ_CUDA(cudaGetLastError());
+    }
+    bb.n_bins = nfine; bb.lb = lbf; bb.n_keys = (uint32_t)a.n; bb.armed = false; bb.nchunks = 1;
+    Run A{&h->d_run_keys, &h->d_run_counts, &h->d_run_chunk};
+    aggregate_bins(h, bb, 0, 0xFFFFFFFFu, false, 0, &A, nullptr, nullptr);
+    if (A.occ != a.n) SHQ_FAIL(SHQ_ERR_STATE, "exchange batch: %llu words aggregated, %zu received", (unsigned long long)A.occ, a.n);
+    uint64_t n_new = merge_run(h, A, 1, nullptr, true);
+    h->ndistinct += n_new; h->nelts += A.occ;
+    check_err_flag(h);
+  SHQ_API_END
+}
+
+// ---- sharded image: layout with a carry from the previous shards, spill hand-over, per-shard blocks ----
+int shq_mg_layout_aggregate(shq_t h, int64_t agg[2]) {
+  if (!h || !agg) return SHQ_ERR_ARG;
+  struct { int64_t* g; } args{agg};
+  SHQ_API_BEGIN(h)
+    flush_stage(h); ensure_state(h);
+    MaxPlus m;
+    compute_positions(h, 0, MaxPlusOp::id(), &m, false);      // global slot coordinates
+    a.g[0] = m.a; a.g[1] = m.b;
+  SHQ_API_END
+}
+
+int shq_mg_layout_tail(shq_t h, const int64_t carry[2], size_t cap, uint64_t* d_keys, uint32_t* d_counts, uint64_t* d_pos, size_t* n_tail) {
+  if (!h || !carry || !n_tail) return SHQ_ERR_ARG;
+  struct { const int64_t* c; size_t cap; uint64_t* k; uint32_t* cn; uint64_t* p; size_t* nt; } args{carry, cap, d_keys, d_counts, d_pos, n_tail};
+  SHQ_API_BEGIN(h)
+    flush_stage(h); ensure_state(h);
+    cudaStream_t st = h->stream;
+    *a.nt = 0;
+    MaxPlus init{a.c[0], a.c[1]};
+    uint64_t used = compute_positions(h, 0, init);
+    const uint64_t boundary = (h->key_hi >> 8);                // first slot of the next shard
+    const bool last = h->shard == h->nshards - 1;
+    if (last) {
+      if (used > h->xnslots) SHQ_FAIL(SHQ_ERR_CAPACITY, "filter over-full: layout needs slot %llu but xnslots = %llu",
+                                      (unsigned long long)used, (unsigned long long)h->xnslots);
+      return;
+    }
+    if (h->n_state == 0 || used <= boundary) return;
+    tail_start_kernel<<<1, 32, 0, st>>>(h->st_keys.as<uint64_t>(), h->st_counts.as<uint32_t>(), h->d_pos.as<uint64_t>(), h->n_state, boundary,
+                                        h->d_misc.as<uint64_t>() + 8);
+    h->stats.kernels_launched++;
+    uint64_t k0 = read_scalar(h, h->d_misc.as<uint64_t>() + 8);
+    size_t nt = h->n_state - (size_t)k0;
+    if (nt > a.cap) SHQ_FAIL(SHQ_ERR_CAPACITY, "%zu entries spill into the next shard (buffer holds %zu)", nt, a.cap);
+    if (nt) {
+      SHQ_CUDA(cudaMemcpyAsync(a.k, h->st_keys.as<uint64_t>() + k0, nt * 8, cudaMemcpyDeviceToDevice, st));
+      SHQ_CUDA(cudaMemcpyAsync(a.cn, h->st_counts.as<uint32_t>() + k0, nt * 4, cudaMemcpyDeviceToDevice, st));
+      SHQ_CUDA(cudaMemcpyAsync(a.p, h->d_pos.as<uint64_t>() + k0, nt * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    SHQ_CUDA(cudaStreamSynchronize(st));
+    *a.nt = nt;
+  SHQ_API_END
+}
+
+int shq_mg_materialize_shard(shq_t h, const uint64_t* d_spill_keys, const uint32_t* d_spill_counts, const uint64_t* d_spill_pos,
+                             size_t n_spill, const uint8_t** d_image, uint64_t* first_block, uint64_t* n_blocks) {
+  if (!h || (n_spill && (!d_spill_keys || !d_spill_counts || !d_spill_pos))) return SHQ_ERR_ARG;
+  struct { const uint64_t* k; const uint32_t* c; const uint64_t* p; size_t n; const uint8_t** img; uint64_t* fb; uint64_t* nb; }
+      args{d_spill_keys, d_spill_counts, d_spill_pos, n_spill, d_image, first_block, n_blocks};
+  SHQ_API_BEGIN(h)
+    // positions (global coordinates) must be current: shq_mg_layout_tail has just run on this state
+    cudaStream_t st = h->stream;
+    Phase ph(h, &h->stats.ms_layout);
+    const uint64_t per = h->nslots / (uint64_t)h->nshards / 64;      // blocks per shard
+    const uint64_t b_first = per * (uint64_t)h->shard;
+    const uint64_t nb = h->shard == h->nshards - 1 ? h->nblocks - b_first : per;
+    if (per % kTileBlocks) SHQ_FAIL(SHQ_ERR_ARG, "shard of %llu blocks is not a multiple of %d", (unsigned long long)per, kTileBlocks);
+    const size_t n = h->n_state, m = a.n + n;
+    // entries that can touch this shard's blocks: the previous shard's spill, then our own state
+    h->d_tmp_keys.reserve((m + 4) * 8); h->d_tmp_counts.reserve((m + 4) * 4); h->d_run_keys.reserve((m + 4) * 8);
+    uint64_t* ck = h->d_tmp_keys.as<uint64_t>(); uint32_t* cc = h->d_tmp_counts.as<uint32_t>(); uint64_t* cp = h->d_run_keys.as<uint64_t>();
+    if (a.n) {
+      SHQ_CUDA(cudaMemcpyAsync(ck, a.k, a.n * 8, cudaMemcpyDeviceToDevice, st));
+      SHQ_CUDA(cudaMemcpyAsync(cc, a.c, a.n * 4, cudaMemcpyDeviceToDevice, st));
+      SHQ_CUDA(cudaMemcpyAsync(cp, a.p, a.n * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    if (n) {
+      SHQ_CUDA(cudaMemcpyAsync(ck + a.n, h->st_keys.p, n * 8, cudaMemcpyDeviceToDevice, st));
+      SHQ_CUDA(cudaMemcpyAsync(cc + a.n, h->st_counts.p, n * 4, cudaMemcpyDeviceToDevice, st));
+      SHQ_CUDA(cudaMemcpyAsync(cp + a.n, h->d_pos.p, n * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    size_t tiles = (nb + kTileBlocks - 1) / kTileBlocks;
+    h->image.reserve(tiles * kTileBytes + 16);
+    image_tiles_kernel<<<(unsigned)tiles, kImgThreads, 0, st>>>(ck, cc, cp, m, 0, nb, h->image.as<uint8_t>(), b_first);
+    h->stats.kernels_launched++;
+    SHQ_CUDA(cudaGetLastError());
+    SHQ_CUDA(cudaStreamSynchronize(st));
+    if (a.img) *a.img = h->image.as<uint8_t>();
+    if (a.fb) *a.fb = b_first;
+    if (a.nb) *a.nb = nb;
+  SHQ_API_END
+}
+
+int shq_header(shq_t h, uint64_t ndistinct, uint64_t nelts, uint8_t out[128]) {
+  if (!h || !out) return SHQ_ERR_ARG;
+  uint64_t sd = h->ndistinct, se = h->nelts;
+  h->ndistinct = ndistinct; h->nelts = nelts;
+  build_header(h, out);
+  h->ndistinct = sd; h->nelts = se;
+  return SHQ_OK;
 }
 
 int shq_state_view(shq_t h, const uint64_t** d_keys, const uint32_t** d_counts, size_t* n) {

@@ -52,7 +52,7 @@ __device__ __forceinline__ MaxPlus layout_map(uint64_t key, uint64_t prev_key, b
 template <bool APPLY>
 __global__ void __launch_bounds__(kScanThreads) layout_scan_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, size_t n,
                                                                   uint64_t key_lo_q, MaxPlus* __restrict__ tile_agg, uint64_t* __restrict__ pos,
-                                                                  MaxPlus* __restrict__ grand_total) {
+                                                                  MaxPlus* __restrict__ grand_total, MaxPlus init /* everything before entry 0 (shards) */) {
   const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
   uint64_t k[kScanItems + 1]; uint32_t c[kScanItems];
   k[0] = (base > 0 && base <= n) ? keys[base - 1] : 0;
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(kScanThreads) layout_scan_kernel(const uint64_
   MaxPlus tot;
   MaxPlus exc = block_exclusive_scan<MaxPlusOp>(acc, &tot);
   if (!APPLY) { if (threadIdx.x == 0) tile_agg[blockIdx.x] = tot; return; }
-  MaxPlus run = MaxPlusOp::op(tile_agg[blockIdx.x], exc);
+  MaxPlus run = MaxPlusOp::op(init, MaxPlusOp::op(tile_agg[blockIdx.x], exc));
 #pragma unroll
   for (int i = 0; i < kScanItems; i++) {
     if (base + i < n) {
@@ -85,6 +85,10 @@ __device__ __forceinline__ uint64_t entry_end(const uint64_t* keys, const uint32
   return pos[k] + enc_len((uint32_t)(keys[k] & 0xFF), counts[k]) - 1;
 }
 
+// first entry whose last slot is >= boundary (entries that reach into the next shard); one warp
+__global__ void __launch_bounds__(32) tail_start_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts,
+                                                       const uint64_t* __restrict__ pos, size_t n, uint64_t boundary, uint64_t* __restrict__ out);
+
 // ------------------------------------------------------- image tiles --------
 constexpr int kTileBlocks = 64;                       // 64 blocks = 4096 slots per CTA
 constexpr int kTileSlots = kTileBlocks * 64;
@@ -97,11 +101,13 @@ constexpr int kImgThreads = 128;
 // carry separately).
 __global__ void __launch_bounds__(kImgThreads) image_tiles_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts,
                                                                  const uint64_t* __restrict__ pos, size_t n, uint64_t key_lo_q,
-                                                                 uint64_t nblocks, uint8_t* __restrict__ image) {
+                                                                 uint64_t nblocks, uint8_t* __restrict__ image, uint64_t block_base = 0) {
   __shared__ __align__(16) uint8_t s_img[kTileBytes];
   __shared__ uint32_t s_occ[kTileBlocks * 2], s_run[kTileBlocks * 2];
   __shared__ size_t s_rng[4];
-  const uint64_t b0 = (uint64_t)blockIdx.x * kTileBlocks;
+  // blocks [block_base, block_base + nblocks) of the filter are written to image[0 ...) (a shard's slice; block_base
+  // is a multiple of kTileBlocks); slots and quotients are in the coordinates of (key >> 8) - key_lo_q
+  const uint64_t b0 = block_base + (uint64_t)blockIdx.x * kTileBlocks;
   const uint64_t S0 = b0 * 64, S1 = S0 + kTileSlots;
   for (int i = threadIdx.x; i < kTileBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(s_img)[i] = 0;
   for (int i = threadIdx.x; i < kTileBlocks * 2; i += blockDim.x) { s_occ[i] = 0; s_run[i] = 0; }
@@ -172,10 +178,10 @@ __global__ void __launch_bounds__(kImgThreads) image_tiles_kernel(const uint64_t
     for (int i = 0; i < 8; i++) { B[1 + i] = (uint8_t)(occ >> (8 * i)); B[9 + i] = (uint8_t)(run >> (8 * i)); }
   }
   __syncthreads();
-  uint64_t nb_here = nblocks > b0 ? nblocks - b0 : 0;
+  uint64_t nb_here = block_base + nblocks > b0 ? block_base + nblocks - b0 : 0;
   if (nb_here > kTileBlocks) nb_here = kTileBlocks;
   size_t bytes = (size_t)nb_here * kBlockBytes;
-  uint8_t* dst = image + b0 * kBlockBytes;   // b0 % 4 == 0 -> 4-byte aligned
+  uint8_t* dst = image + (b0 - block_base) * kBlockBytes;   // (b0 - block_base) % 4 == 0 -> 4-byte aligned
   size_t words = bytes / 4;
   for (size_t i = threadIdx.x; i < words; i += blockDim.x) reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<uint32_t*>(s_img)[i];
   for (size_t i = words * 4 + threadIdx.x; i < bytes; i += blockDim.x) dst[i] = s_img[i];
@@ -252,6 +258,12 @@ __global__ void __launch_bounds__(32) denoise_ranges_kernel(const uint64_t* __re
     cur = nx < n ? (keys[nx] >> 8) : xnslots;
   }
   if (lane == 0) *n_keep = nk;
+}
+
+__global__ void __launch_bounds__(32) tail_start_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts,
+                                                       const uint64_t* __restrict__ pos, size_t n, uint64_t boundary, uint64_t* __restrict__ out) {
+  size_t k = warp_first_false(0, n, threadIdx.x, [&](size_t i) { return entry_end(keys, counts, pos, i) < boundary; });
+  if (threadIdx.x == 0) *out = (uint64_t)k;
 }
 
 // ------------------------------------------------------------ queries -------

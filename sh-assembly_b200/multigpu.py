@@ -51,6 +51,47 @@ def slice_range(sorted_keys: np.ndarray, lo: int, hi: int):
     return int(np.searchsorted(sorted_keys, np.uint64(lo), "left")), int(np.searchsorted(sorted_keys, np.uint64(hi), "left"))
 
 
+NEG_INF = -(1 << 60)
+
+
+def maxplus_compose(x, y):
+    """f(e) = max(e + a, b) as the pair (a, b); apply x first, then y (csrc/shq_scan.cuh MaxPlusOp)."""
+    return (x[0] + y[0], max(x[1] + y[0], y[1]))
+
+
+def carry_before(aggs, rank):
+    """Composed slot-layout map of all shards before `rank` (identity for rank 0)."""
+    c = (0, NEG_INF)
+    for r in range(rank):
+        c = maxplus_compose(c, aggs[r])
+    return c
+
+
+def exchange_geometry(world, coarse_bits=11, fine_total_bits=12):
+    """(coarse_bits, coarse bins per shard, fine_bits): 2^coarse_bits bins over the whole key space at the source,
+    every coarse bin split into 2^fine_bits at the owner so that a shard ends up with 2^fine_total_bits bins."""
+    shard_bits = int(world).bit_length() - 1
+    cb = max(coarse_bits, shard_bits + 1)
+    cps = (1 << cb) // world
+    fb = max(0, fine_total_bits - (cb - shard_bits))
+    return cb, cps, fb
+
+
+def binned_plan(all_counts: np.ndarray, rank: int, world: int):
+    """all_counts[s][b] = words source s holds in global coarse bin b (owner of b = b // cps).
+    Returns (send_counts, recv_counts, seg_start, my_counts): words this rank sends to / receives from every rank,
+    the start of every source's slice in the receive buffer, and my_counts[s][c] = words of MY coarse bin c from s."""
+    all_counts = np.asarray(all_counts, np.int64)
+    nb = all_counts.shape[1]
+    cps = nb // world
+    per_owner = all_counts.reshape(world, world, cps)          # [source][owner][c]
+    send_counts = per_owner[rank].sum(axis=1)
+    recv_counts = per_owner[:, rank, :].sum(axis=1)
+    seg_start = np.concatenate([[0], np.cumsum(recv_counts)[:-1]]).astype(np.uint64)
+    my_counts = np.ascontiguousarray(per_owner[:, rank, :]).astype(np.uint32)
+    return [int(x) for x in send_counts], [int(x) for x in recv_counts], seg_start, my_counts
+
+
 def exchange(dist, send: "torch.Tensor", send_counts, world):
     """One all-to-all of int64 keys grouped by destination.  Works on CUDA (nccl) and CPU (gloo) tensors."""
     import torch
@@ -111,21 +152,55 @@ class ShardedCounter:
         self.shard.reset()
         self.nelts_local = 0
 
-    def insert_fastq_device(self, d_text_ptr, n_bytes, K):
-        """Hash this rank's reads, exchange keys by owner, insert the received keys into the local shard."""
+    def insert_fastq_device(self, d_text_ptr, n_bytes, K, chunk_ends=None, max_batch_bytes=256 << 20):
+        """Device-resident text of this rank, cut into batches at chunk boundaries (every rank runs the same number
+        of exchange rounds; a rank that has run out of text takes part with empty batches)."""
         torch = self.torch
-        cap = n_bytes // 2 + 1024
-        keys = self._buf("keys", cap, torch.int64)
-        nk = self.shard.hash_fastq_device(d_text_ptr, n_bytes, K, keys.data_ptr(), cap)
-        grouped = self._buf("grouped", max(nk, 1), torch.int64)
-        counts = self.shard.partition_keys_device(keys.data_ptr(), nk, self.world, grouped.data_ptr())
-        self.shard.sync()
-        torch.cuda.current_stream().synchronize()
-        recv, recv_counts = exchange(self.dist, grouped, counts, self.world)
+        ends = [int(e) for e in chunk_ends] if chunk_ends is not None and len(chunk_ends) else [int(n_bytes)]
+        cuts, start, prev = [], 0, 0
+        for e in ends:
+            if e - start > max_batch_bytes and prev > start:
+                cuts.append((start, prev)); start = prev
+            prev = e
+        if prev > start:
+            cuts.append((start, prev))
+        nb = torch.tensor([len(cuts)], dtype=torch.int64, device=torch.device("cuda", self.device))
+        self.dist.all_reduce(nb, op=self.dist.ReduceOp.MAX)
+        total = 0
+        for i in range(int(nb.item())):
+            a, b = cuts[i] if i < len(cuts) else (0, 0)
+            total += self._exchange_batch(d_text_ptr + a, b - a, K)
+        return total
+
+    def _exchange_batch(self, d_text_ptr, n_bytes, K):
+        """Two-level exchange: bin this rank's k-mers over the whole key space (coarse bins; 32-bit words), ship every
+        owner its slice with ONE all-to-all, split the received coarse bins into fine bins and insert them."""
+        torch = self.torch
+        world, rank = self.world, self.rank
+        dev = torch.device("cuda", self.device)
+        cb, cps, fb = exchange_geometry(world)
+        nb = 1 << cb
+        wp, op, nw = self.shard.mg_bin_fastq_device(d_text_ptr, n_bytes, K, cb)
+        off = self._buf("binoff", nb + 1, torch.int32)[:nb + 1]
+        if nw:
+            self.shard.copy_device(off.data_ptr(), op, (nb + 1) * 4)
+        else:
+            off.zero_()
+        counts = (off[1:] - off[:-1]).contiguous()
+        allc = self._buf("allc", world * nb, torch.int32)[:world * nb]
+        self.dist.all_gather_into_tensor(allc, counts)
+        send_counts, recv_counts, seg_start, my_counts = binned_plan(allc.view(world, nb).cpu().numpy(), rank, world)
+        send = self._buf("send", max(nw, 1), torch.int32)[:nw]
+        if nw:
+            self.shard.copy_device(send.data_ptr(), wp, nw * 4)
+        total = sum(recv_counts)
+        recv = self._buf("recv", max(total, 1), torch.int32)[:total]
+        self.dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=send_counts)
+        mc = torch.from_numpy(my_counts.view(np.int32)).to(dev)
         torch.cuda.synchronize()      # the collective ran on torch's streams; libshq works on its own stream
-        self.shard.insert_keys_device(recv.data_ptr(), recv.numel())
-        self.nelts_local += recv.numel()
-        return nk
+        self.shard.mg_insert_binned(recv.data_ptr(), seg_start, mc.data_ptr(), world, cb, fb, total)
+        self.nelts_local += total
+        return nw
 
     def _state_tensors(self):
         torch = self.torch
@@ -187,6 +262,52 @@ class ShardedCounter:
         full.adopt_state(allk.data_ptr(), allc.data_ptr(), allk.numel(), nd, ne)
         return full.export()
 
+    SPILL_CAP = 1 << 14
+
+    def materialize_sharded(self):
+        """Every rank builds the blocks of its own quotient range in its HBM (no gather): the slot layout is a max-plus
+        scan, so a shard needs the composed map of its predecessors (2 x int64, all-gathered) and the handful of
+        entries of the previous shard whose slots reach across the boundary (boundary stitch).
+        Returns (device pointer of the shard image, first block, number of blocks)."""
+        torch = self.torch
+        dev = torch.device("cuda", self.device)
+        a, b = self.shard.mg_layout_aggregate()
+        mine = torch.tensor([a, b], dtype=torch.int64, device=dev)
+        allg = torch.empty(2 * self.world, dtype=torch.int64, device=dev)
+        self.dist.all_gather_into_tensor(allg, mine)
+        aggs = [(int(x[0]), int(x[1])) for x in allg.view(self.world, 2).tolist()]
+        carry = carry_before(aggs, self.rank)
+        cap = self.SPILL_CAP
+        # one buffer per rank: [n_tail | keys | pos | counts] as int64 words
+        buf = self._buf("spill", 1 + 3 * cap, torch.int64)[:1 + 3 * cap]
+        kp, pp, cp = buf[1:1 + cap], buf[1 + cap:1 + 2 * cap], buf[1 + 2 * cap:1 + 3 * cap]
+        nt = self.shard.mg_layout_tail(carry, cap, kp.data_ptr(), cp.data_ptr(), pp.data_ptr())
+        buf[0] = nt
+        allb = self._buf("spill_all", self.world * (1 + 3 * cap), torch.int64)[:self.world * (1 + 3 * cap)]
+        self.dist.all_gather_into_tensor(allb, buf)
+        n_spill = 0
+        sk = sc = sp = 0
+        if self.rank > 0:
+            prev = allb.view(self.world, 1 + 3 * cap)[self.rank - 1]
+            n_spill = int(prev[0].item())
+            sk, sp, sc = prev[1:1 + cap].data_ptr(), prev[1 + cap:1 + 2 * cap].data_ptr(), prev[1 + 2 * cap:1 + 3 * cap].data_ptr()
+        torch.cuda.synchronize()
+        return self.shard.mg_materialize_shard(sk, sc, sp, n_spill)
+
+    def export_sharded(self):
+        """Rank 0 returns the reference-format .cqf bytes assembled from the shard images; other ranks return None."""
+        torch = self.torch
+        img, fb, nb = self.materialize_sharded()
+        t = torch.empty(nb * 89, dtype=torch.uint8, device=torch.device("cuda", self.device))
+        self.shard.copy_device(t.data_ptr(), img, nb * 89)
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, (fb, t.cpu().numpy().tobytes()))
+        nd, ne = self.global_counts()
+        if self.rank != 0:
+            return None
+        parts.sort(key=lambda x: x[0])
+        return self.shard.header(nd, ne) + b"".join(p[1] for p in parts)
+
     def materialize_global(self):
         """Build the global image on rank 0 in device memory (benchmark: 'table complete')."""
         torch = self.torch
@@ -213,10 +334,9 @@ def bench_sharded(args, rank, world, local_rank, text, ends, p, n_local, n_total
 
     def step():
         sc.reset()
-        sc.insert_fastq_device(d_text.data_ptr(), len(text), args.k)
-        if args.end_denoise:
-            sc.end_denoise()
-        return sc.materialize_global()
+        sc.insert_fastq_device(d_text.data_ptr(), len(text), args.k, ends)
+        sc.materialize_sharded()
+        return sc.global_counts()
 
     for _ in range(args.warmup):
         step()
@@ -242,7 +362,9 @@ def bench_sharded(args, rank, world, local_rank, text, ends, p, n_local, n_total
         ms_step = float(ms.item()) / args.steps
         value = n_total / (ms_step / 1e3)
         cfg = dict(config)
-        cfg["workload"] += " | N>1: --deNoise=0 mid-stream (sharded mid-stream rounds are not built yet), exact end sweep and image on the gathered state"
+        cfg["workload"] += " | N>1: counted with --deNoise=0 like BASELINE configs[3] (deNoise rounds need the global range hand-out and run on the gathered state, outside this step); filter sharded by quotient range, two-level binned all-to-all, every rank materialises its own blocks (max-plus carry + boundary stitch)"
+        cfg["deNoise"] = 0
+        cfg["endDeNoise"] = False
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))

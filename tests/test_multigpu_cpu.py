@@ -48,6 +48,30 @@ def _worker(rank, world, port, ret):
     dist.all_gather_object(all_counts, counts)
     rc, so, ro = mg.plan_for_rank(rank, all_counts)
     assert rc == recv_counts and so[0] == 0 and ro[0] == 0
+    # two-level exchange: coarse bins over the whole key space, 32-bit words, one slice per owner
+    cb, cps, fb = mg.exchange_geometry(world, coarse_bits=6)
+    lbc = hb - cb
+    bins = (keys >> np.uint64(lbc)).astype(np.int64)
+    order = np.argsort(bins, kind="stable")
+    words = (keys[order] & np.uint64((1 << lbc) - 1)).astype(np.int32)
+    cnt = torch.from_numpy(np.bincount(bins, minlength=1 << cb).astype(np.int32))
+    allc = [torch.empty_like(cnt) for _ in range(world)]
+    dist.all_gather(allc, cnt)
+    allc = np.stack([t.numpy() for t in allc])
+    sc, rcnt, seg_start, my_counts = mg.binned_plan(allc, rank, world)
+    assert sum(sc) == len(words) and seg_start[0] == 0
+    rbuf = torch.empty(sum(rcnt), dtype=torch.int32)
+    dist.all_to_all_single(rbuf, torch.from_numpy(words), output_split_sizes=rcnt, input_split_sizes=sc)
+    got = []
+    rb = rbuf.numpy().astype(np.uint64)
+    for s in range(world):
+        o = int(seg_start[s])
+        for c in range(cps):
+            n = int(my_counts[s][c])
+            got.append(((np.uint64(rank * cps + c) << np.uint64(lbc)) | rb[o:o + n]))
+            o += n
+    got = np.sort(np.concatenate(got))
+    assert (got == np.sort(recv)).all()          # same multiset as the 64-bit key exchange above
     ret[rank] = len(recv)
     dist.barrier()
     dist.destroy_process_group()
@@ -60,6 +84,46 @@ def test_world2_exchange_and_gather():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert len(ret) == world and sum(ret.values()) > 0
+
+
+def test_binned_plan_arithmetic():
+    mg = importlib.import_module("sh-assembly_b200.multigpu")
+    assert mg.exchange_geometry(2) == (11, 1024, 2) and mg.exchange_geometry(8) == (11, 256, 4)
+    rng = np.random.default_rng(3)
+    world, nb = 4, 32
+    allc = rng.integers(0, 50, size=(world, nb))
+    tot_recv = 0
+    for r in range(world):
+        sc, rc, ss, mc = mg.binned_plan(allc, r, world)
+        assert sc == [int(allc[r, d * 8:(d + 1) * 8].sum()) for d in range(world)]
+        assert rc == [int(allc[s, r * 8:(r + 1) * 8].sum()) for s in range(world)]
+        assert (mc == allc[:, r * 8:(r + 1) * 8]).all() and ss.tolist() == np.concatenate([[0], np.cumsum(rc)[:-1]]).tolist()
+        tot_recv += sum(rc)
+    assert tot_recv == allc.sum()
+
+
+def test_maxplus_carry_matches_sequential_layout():
+    """The per-shard composed maps + carry_before reproduce the sequential rule start = max(q, previous end + 1)."""
+    mg = importlib.import_module("sh-assembly_b200.multigpu")
+    rng = np.random.default_rng(11)
+    nslots, world = 1 << 12, 4
+    q = np.sort(rng.integers(0, nslots, size=3000))
+    ln = rng.integers(1, 4, size=len(q))
+    free, first_free_at = 0, {}
+    aggs = [(0, mg.NEG_INF)] * world
+    prev_q = -1
+    for qi, li in zip(q.tolist(), ln.tolist()):
+        shard = qi // (nslots // world)
+        first_free_at.setdefault(shard, free)               # first free slot when the shard's first entry arrives
+        m = (li, qi + li if qi != prev_q else mg.NEG_INF)
+        aggs[shard] = mg.maxplus_compose(aggs[shard], m)
+        free = max(free + li, qi + li) if qi != prev_q else free + li
+        prev_q = qi
+    for r in range(world):
+        c = mg.carry_before(aggs, r)
+        assert max(c[0], c[1], 0) == first_free_at[r] or (r == 0 and first_free_at[r] == 0)
+    tot = mg.carry_before(aggs, world)
+    assert max(tot[0], tot[1]) == free
 
 
 def test_owner_rule():

@@ -22,12 +22,15 @@ def main():
         sc.insert_fastq_device(d.data_ptr(), len(text), K)
         removed = sc.end_denoise() if end else 0
         img = sc.export()
+        img2 = sc.export_sharded()
         nd, ne = sc.global_counts()
         if rank == 0:
             o, _ = po.count_run(texts, K, qb, qb + 8, 0, 0, end)
             ok = img == o.export()
-            print("world", world, "endDeNoise", end, "removed", removed, "counts", (nd, ne), o.counts(), "image equal:", ok, flush=True)
-            assert ok and (nd, ne) == o.counts()
+            ok2 = img2 == o.export()
+            print("world", world, "endDeNoise", end, "removed", removed, "counts", (nd, ne), o.counts(), "image equal:", ok,
+                  "sharded image equal:", ok2, flush=True)
+            assert ok and ok2 and (nd, ne) == o.counts()
         dist.barrier()
     dist.destroy_process_group()
 

@@ -137,6 +137,20 @@ int shq_mg_materialize_shard(shq_t h, const uint64_t* d_spill_keys, const uint32
                              const uint64_t* d_spill_pos, size_t n_spill, const uint8_t** d_image, uint64_t* first_block,
                              uint64_t* n_blocks);
 int shq_header(shq_t h, uint64_t ndistinct, uint64_t nelts, uint8_t out[128]);
+/* Pull exchange over peer memory (one process per GPU on one NVLink/NVSwitch node): no all-to-all of k-mers at all.
+ * shq_mg_setup: two fixed buffers of max_words 32-bit words for this rank's binned k-mers; their CUDA IPC handles
+ *   (2 x 64 bytes) go to ipc_handles_out.  shq_mg_open_peers: all ranks' handles (world x 2 x 64 bytes, rank-major)
+ *   are mapped into this process.
+ * shq_mg_bin_local: hash the text; d_fine_hist (caller's device buffer, world * 4096 words) receives the histogram
+ *   over the fine bins of the WHOLE key space; the k-mers are binned (2048 coarse bins) into buffer `parity`.
+ * shq_mg_insert_pull: d_all_fine_hist = the all-gathered histograms [world][world * 4096].  The owner reads its
+ *   coarse bins straight out of every source's buffer `parity` (P2P loads inside the split kernel), splits them into
+ *   its 4096 fine bins and inserts.  A source may refill a buffer two batches later (the histogram all-gather of
+ *   the batch in between orders the accesses).                                                                   */
+int shq_mg_setup(shq_t h, size_t max_words, void* ipc_handles_out);
+int shq_mg_open_peers(shq_t h, const void* all_handles, int world);
+int shq_mg_bin_local(shq_t h, const char* d_text, size_t n, int K, int parity, uint32_t* d_fine_hist, size_t* n_words);
+int shq_mg_insert_pull(shq_t h, const uint32_t* d_all_fine_hist, int parity);
 int shq_mg_bin_fastq_device(shq_t h, const char* d_text, size_t n, int K, int coarse_bits, const uint32_t** d_words,
                             const uint32_t** d_bin_off, size_t* n_words);
 int shq_mg_insert_binned(shq_t h, const uint32_t* d_recv, const uint64_t* seg_start, const uint32_t* d_counts, int world,

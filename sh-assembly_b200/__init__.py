@@ -67,6 +67,7 @@ EXPORTS = [
     "shq_unitigs_write_fasta", "shq_unitigs_fasta", "shq_unitigs_free", "shq_get_stats", "shq_reset_stats", "shq_stream",
     "shq_reader_open", "shq_reader_open_memory", "shq_reader_next", "shq_reader_close", "shq_build_kmer_spectrum",
     "shq_materialize", "shq_param_block", "shq_cdfpoi_positive", "shq_cdfpoi",
+    "shq_mg_setup", "shq_mg_open_peers", "shq_mg_bin_local", "shq_mg_insert_pull",
     "shq_mg_bin_fastq_device", "shq_mg_insert_binned", "shq_mg_layout_aggregate", "shq_mg_layout_tail", "shq_mg_materialize_shard", "shq_header",
     "shq_hash_fastq_device", "shq_partition_keys_device", "shq_state_view", "shq_adopt_state", "shq_set_counts", "shq_copy_device",
 ]
@@ -126,6 +127,10 @@ def lib():
         L.shq_partition_keys_device.argtypes = [vp, vp, sz, C.c_int, vp, C.POINTER(u64)]
         L.shq_mg_bin_fastq_device.argtypes = [vp, vp, sz, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(sz)]
         L.shq_mg_insert_binned.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, sz]
+        L.shq_mg_setup.argtypes = [vp, sz, vp]
+        L.shq_mg_open_peers.argtypes = [vp, vp, C.c_int]
+        L.shq_mg_bin_local.argtypes = [vp, vp, sz, C.c_int, C.c_int, vp, C.POINTER(sz)]
+        L.shq_mg_insert_pull.argtypes = [vp, vp, C.c_int]
         L.shq_mg_layout_aggregate.argtypes = [vp, C.POINTER(C.c_int64)]
         L.shq_mg_layout_tail.argtypes = [vp, C.POINTER(C.c_int64), sz, vp, vp, vp, C.POINTER(sz)]
         L.shq_mg_materialize_shard.argtypes = [vp, vp, vp, vp, sz, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]
@@ -408,6 +413,24 @@ class CQF:
     def mg_insert_binned(self, d_recv, seg_start, d_counts, world, coarse_bits, fine_bits, n_words):
         ss = np.ascontiguousarray(seg_start, np.uint64)
         self._check(self.L.shq_mg_insert_binned(self.h, d_recv, ss.ctypes.data, d_counts, world, coarse_bits, fine_bits, n_words))
+
+    def mg_setup(self, max_words) -> bytes:
+        """Allocate the two exchange buffers; returns their CUDA IPC handles (2 x 64 bytes)."""
+        buf = np.zeros(128, np.uint8)
+        self._check(self.L.shq_mg_setup(self.h, max_words, buf.ctypes.data))
+        return buf.tobytes()
+
+    def mg_open_peers(self, all_handles: bytes, world):
+        a = np.frombuffer(all_handles, np.uint8)
+        self._check(self.L.shq_mg_open_peers(self.h, a.ctypes.data, world))
+
+    def mg_bin_local(self, d_text, n, K, parity, d_fine_hist):
+        nw = C.c_size_t()
+        self._check(self.L.shq_mg_bin_local(self.h, d_text, n, K, parity, d_fine_hist, C.byref(nw)))
+        return nw.value
+
+    def mg_insert_pull(self, d_all_hist, parity):
+        self._check(self.L.shq_mg_insert_pull(self.h, d_all_hist, parity))
 
     def mg_layout_aggregate(self):
         g = (C.c_int64 * 2)()

@@ -66,7 +66,12 @@ struct shq_handle_s {
   DevBuf d_tmp_keys2, d_tmp_counts2, d_run2_keys, d_run2_counts;
   DevBuf d_run_keys, d_run_counts, d_run_chunk, d_split, d_heads, d_heads64, d_scan_scratch, d_misc;
   DevBuf d_pairs, d_pos, d_flags, d_keep, d_q_in, d_q_cnt, d_q_was;
-  DevBuf d_seg, d_fine, d_packed2;   // multi-GPU second-level split
+  DevBuf d_seg, d_fine, d_packed2, d_bases;   // multi-GPU second-level split
+  // pull exchange: two fixed binned-word buffers that peers map through CUDA IPC, and the peers' buffers mapped here
+  uint32_t* mg_send[2] = {nullptr, nullptr};
+  size_t mg_cap_words = 0;
+  std::vector<const uint32_t*> mg_peer;            // [rank * 2 + parity]
+  std::vector<void*> mg_opened;                    // pointers obtained from cudaIpcOpenMemHandle
   int* d_err = nullptr;          // device error flag
   void* h_pinned = nullptr;      // small pinned readback area (4 KiB + chunk hist)
   size_t h_pinned_cap = 0;
@@ -702,9 +707,11 @@ void free_handle(shq_handle_s* h) {
                     &h->d_binoff, &h->d_packed, &h->d_tmp_keys, &h->d_tmp_counts, &h->d_tmp_chunk, &h->d_nout, &h->d_occ,
                     &h->d_dense_off, &h->d_run_keys, &h->d_run_counts, &h->d_run_chunk, &h->d_split, &h->d_heads, &h->d_heads64,
                     &h->d_scan_scratch, &h->d_misc, &h->d_pairs, &h->d_pos, &h->d_flags, &h->d_keep, &h->d_q_in, &h->d_q_cnt, &h->d_q_was,
-                    &h->d_tmp_keys2, &h->d_tmp_counts2, &h->d_run2_keys, &h->d_run2_counts, &h->d_seg, &h->d_fine, &h->d_packed2};
+                    &h->d_tmp_keys2, &h->d_tmp_counts2, &h->d_run2_keys, &h->d_run2_counts, &h->d_seg, &h->d_fine, &h->d_packed2, &h->d_bases};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : h->pin_buf) b.release();
+  for (void* p : h->mg_opened) cudaIpcCloseMemHandle(p);
+  for (uint32_t* p : h->mg_send) if (p) cudaFree(p);
   for (auto& b : h->pin_queue) cudaEventDestroy(b.ev);
   if (h->cstream) { cudaStreamSynchronize(h->cstream); cudaStreamDestroy(h->cstream); }
   if (h->d_err) cudaFree(h->d_err);
@@ -1190,17 +1197,22 @@ int shq_mg_insert_binned(shq_t h, const uint32_t* d_recv, const uint64_t* seg_st
       uint64_t* d_seg_start = h->d_seg.as<uint64_t>();
       uint64_t* seg_beg = d_seg_start + a.world + 4;
       SHQ_CUDA(cudaMemcpyAsync(d_seg_start, a.ss, (size_t)a.world * 8, cudaMemcpyHostToDevice, st));
-      seg_table_kernel<<<1, 64, 0, st>>>(a.c, d_seg_start, a.world, cps, seg_beg); L++;
+      seg_table_kernel<<<a.world, kScanThreads, 0, st>>>(a.c, d_seg_start, a.world, cps, seg_beg); L++;
       h->d_fine.reserve(((size_t)nfine + 2) * 4);
       h->d_binoff.reserve(((size_t)nfine + 2) * 4);
       SHQ_CUDA(cudaMemsetAsync(h->d_fine.p, 0, ((size_t)nfine + 1) * 4, st));
       int parts = 1; while (cps * parts < 4 * kNumSMs) parts *= 2;
-      resplit_kernel<true><<<cps * parts, kSplitThreads, 0, st>>>(a.r, seg_beg, a.world, cps, parts, lbc, a.fb, h->d_fine.as<uint32_t>(), nullptr); L++;
+      h->d_bases.reserve((size_t)a.world * 8 + 64);
+      { std::vector<const uint32_t*> b((size_t)a.world, a.r);
+        SHQ_CUDA(cudaMemcpyAsync(h->d_bases.p, b.data(), (size_t)a.world * 8, cudaMemcpyHostToDevice, st));
+        SHQ_CUDA(cudaStreamSynchronize(st)); }
+      const uint32_t* const* bases = h->d_bases.as<const uint32_t*>();
+      resplit_kernel<true><<<cps * parts, kSplitThreads, 0, st>>>(bases, seg_beg, a.world, cps, parts, lbc, a.fb, h->d_fine.as<uint32_t>(), nullptr); L++;
       SHQ_CUDA(cudaMemcpyAsync(h->d_binoff.p, h->d_fine.p, (size_t)nfine * 4, cudaMemcpyDeviceToDevice, st));
       exclusive_scan_inplace<SumU32>(h->d_binoff.as<uint32_t>(), nfine, h->d_scan_scratch, st, h->d_binoff.as<uint32_t>() + nfine, &L);
       SHQ_CUDA(cudaMemcpyAsync(h->d_fine.p, h->d_binoff.p, (size_t)nfine * 4, cudaMemcpyDeviceToDevice, st));
       h->d_packed.reserve((a.n + 4) * 4);
-      resplit_kernel<false><<<cps * parts, kSplitThreads, 0, st>>>(a.r, seg_beg, a.world, cps, parts, lbc, a.fb, h->d_fine.as<uint32_t>(),
+      resplit_kernel<false><<<cps * parts, kSplitThreads, 0, st>>>(bases, seg_beg, a.world, cps, parts, lbc, a.fb, h->d_fine.as<uint32_t>(),
                                                                  h->d_packed.as<uint32_t>()); L++;
       SHQ_CUDA(cudaGetLastError());
     }
@@ -1208,6 +1220,157 @@ int shq_mg_insert_binned(shq_t h, const uint32_t* d_recv, const uint64_t* seg_st
     Run A{&h->d_run_keys, &h->d_run_counts, &h->d_run_chunk};
     aggregate_bins(h, bb, 0, 0xFFFFFFFFu, false, 0, &A, nullptr, nullptr);
     if (A.occ != a.n) SHQ_FAIL(SHQ_ERR_STATE, "exchange batch: %llu words aggregated, %zu received", (unsigned long long)A.occ, a.n);
+    uint64_t n_new = merge_run(h, A, 1, nullptr, true);
+    h->ndistinct += n_new; h->nelts += A.occ;
+    check_err_flag(h);
+  SHQ_API_END
+}
+
+// ---- pull exchange: owners read their coarse bins out of the sources' binned arrays (peer memory over NVLink) ----
+constexpr int kMgCoarseBits = 11;      // coarse bins over the whole key space (level-1 scatter)
+constexpr int kMgFineBits = 12;        // fine bins per shard (what the aggregator wants)
+
+int shq_mg_setup(shq_t h, size_t max_words, void* ipc_handles_out) {
+  if (!h || !ipc_handles_out || max_words == 0 || max_words >= ((size_t)1 << 32)) return SHQ_ERR_ARG;
+  struct { size_t n; void* out; } args{max_words, ipc_handles_out};
+  SHQ_API_BEGIN(h)
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    for (int i = 0; i < 2; i++) {
+      if (h->mg_send[i]) { cudaFree(h->mg_send[i]); h->mg_send[i] = nullptr; }
+      SHQ_CUDA(cudaMalloc((void**)&h->mg_send[i], (a.n + 64) * 4));
+      cudaIpcMemHandle_t hd;
+      SHQ_CUDA(cudaIpcGetMemHandle(&hd, h->mg_send[i]));
+      memcpy((char*)a.out + 64 * i, &hd, 64);
+    }
+    h->mg_cap_words = a.n;
+  SHQ_API_END
+}
+
+int shq_mg_open_peers(shq_t h, const void* all_handles, int world) {
+  if (!h || !all_handles || world != h->nshards) return SHQ_ERR_ARG;
+  struct { const void* hs; int world; } args{all_handles, world};
+  SHQ_API_BEGIN(h)
+    if (!h->mg_send[0]) SHQ_FAIL(SHQ_ERR_STATE, "shq_mg_setup first");
+    for (void* p : h->mg_opened) cudaIpcCloseMemHandle(p);
+    h->mg_opened.clear();
+    h->mg_peer.assign((size_t)a.world * 2, nullptr);
+    for (int r = 0; r < a.world; r++) for (int i = 0; i < 2; i++) {
+      if (r == h->shard) { h->mg_peer[r * 2 + i] = h->mg_send[i]; continue; }
+      cudaIpcMemHandle_t hd;
+      memcpy(&hd, (const char*)a.hs + ((size_t)r * 2 + i) * 64, 64);
+      void* p = nullptr;
+      SHQ_CUDA(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+      h->mg_opened.push_back(p);
+      h->mg_peer[r * 2 + i] = (const uint32_t*)p;
+    }
+  SHQ_API_END
+}
+
+int shq_mg_bin_local(shq_t h, const char* d_text, size_t n, int K, int parity, uint32_t* d_fine_hist, size_t* n_words) {
+  if (!h || (!d_text && n) || !d_fine_hist || !n_words || parity < 0 || parity > 1) return SHQ_ERR_ARG;
+  struct { const char* t; size_t n; int K, par; uint32_t* fh; size_t* nw; } args{d_text, n, K, parity, d_fine_hist, n_words};
+  SHQ_API_BEGIN(h)
+    flush_stage(h);
+    if (!h->mg_send[0]) SHQ_FAIL(SHQ_ERR_STATE, "shq_mg_setup first");
+    cudaStream_t st = h->stream;
+    uint64_t& L = h->stats.kernels_launched;
+    *a.nw = 0;
+    int shard_bits = 0; while ((1 << shard_bits) < h->nshards) shard_bits++;
+    const int cb = kMgCoarseBits > shard_bits ? kMgCoarseBits : shard_bits + 1;
+    const int gfb = shard_bits + kMgFineBits;                 // fine bins over the whole key space
+    const int fb = gfb - cb;
+    const int nfg = 1 << gfb, ncoarse = 1 << cb;
+    const int lbf = h->hb - gfb, lbc = h->hb - cb;
+    if (lbf < 1 || lbc > 31 || fb < 0 || fb > 6) SHQ_FAIL(SHQ_ERR_ARG, "hb=%d does not fit the exchange geometry of %d shards", h->hb, h->nshards);
+    SHQ_CUDA(cudaMemsetAsync(a.fh, 0, (size_t)nfg * 4, st));
+    if (a.n == 0) { SHQ_CUDA(cudaStreamSynchronize(st)); return; }
+    if (a.K < 1 || a.K > 1024) SHQ_FAIL(SHQ_ERR_ARG, "K=%d outside [1,1024]", a.K);
+    if (a.n >= ((size_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "batch text of %zu bytes exceeds 4 GiB", a.n);
+    const char* src = a.t;
+    if (reinterpret_cast<uintptr_t>(src) & 15) {
+      h->d_text.reserve(a.n + 64);
+      SHQ_CUDA(cudaMemcpyAsync(h->d_text.p, src, a.n, cudaMemcpyDeviceToDevice, st));
+      src = h->d_text.as<char>();
+    }
+    uint32_t n_lines = index_lines(h, src, a.n);
+    h->d_chunk_ends.reserve(16); h->d_chunk_line_end.reserve(16);
+    uint64_t end = a.n;
+    SHQ_CUDA(cudaMemcpyAsync(h->d_chunk_ends.p, &end, 8, cudaMemcpyHostToDevice, st));
+    chunk_validate_kernel<<<1, 128, 0, st>>>(src, h->d_nl_pos.as<uint32_t>(), n_lines, h->d_chunk_ends.as<uint64_t>(), 1, h->d_chunk_line_end.as<uint32_t>(), h->d_err); L++;
+    if (n_lines & 3) SHQ_FAIL(SHQ_ERR_MALFORMED, "batch holds %u lines, not a multiple of 4", n_lines);
+    HashParams hp{};
+    hp.text = src; hp.nl_pos = h->d_nl_pos.as<uint32_t>(); hp.n_reads = n_lines / 4; hp.K = a.K;
+    hp.hb = h->hb; hp.key_lo = 0; hp.key_hi = 1ULL << h->hb; hp.nchunks = 1;
+    h->d_hist.reserve((size_t)(ncoarse + 1) * 4); h->d_binoff.reserve((size_t)(ncoarse + 2) * 4); h->d_tot.reserve((size_t)(ncoarse + 2) * 4);
+    {
+      Phase ph(h, &h->stats.ms_hash_count);
+      hp.lb = lbf; hp.n_bins = nfg;
+      size_t smem_count = sizeof(RollTables) + (size_t)nfg * 4;
+      SHQ_CUDA(cudaFuncSetAttribute(roll_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
+      roll_count_kernel<true><<<kNumSMs * (smem_count > 100000 ? 1 : 2), kRollThreads, smem_count, st>>>(hp, a.fh); L++;
+      coarse_from_fine_kernel<<<cdiv(ncoarse, 256), 256, 0, st>>>(a.fh, ncoarse, fb, h->d_binoff.as<uint32_t>()); L++;
+      exclusive_scan_inplace<SumU32>(h->d_binoff.as<uint32_t>(), ncoarse, h->d_scan_scratch, st, h->d_binoff.as<uint32_t>() + ncoarse, &L);
+      SHQ_CUDA(cudaMemcpyAsync(h->d_tot.p, h->d_binoff.p, (size_t)ncoarse * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    uint32_t n_keys = 0; int dev_err = 0;
+    read_pair(h, h->d_binoff.as<uint32_t>() + ncoarse, &n_keys, h->d_err, &dev_err);
+    if (dev_err) { SHQ_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(int), st)); SHQ_FAIL(dev_err, "device reported: %s", shq_strerror(dev_err)); }
+    if (n_keys > h->mg_cap_words) SHQ_FAIL(SHQ_ERR_CAPACITY, "%u k-mers in one batch, exchange buffers hold %zu", n_keys, h->mg_cap_words);
+    {
+      Phase ph(h, &h->stats.ms_scatter);
+      hp.lb = lbc; hp.n_bins = ncoarse;
+      size_t smem_scatter = sizeof(RollTables) + ((size_t)3 * ncoarse + 1) * 4 + (size_t)kScatThreads * 16 * 14 + 16;
+      SHQ_CUDA(cudaFuncSetAttribute(roll_scatter_kernel<kScatThreads, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
+      roll_scatter_kernel<kScatThreads, 16, true><<<kNumSMs, kScatThreads, smem_scatter, st>>>(hp, h->d_tot.as<uint32_t>(), h->mg_send[a.par]); L++;
+    }
+    SHQ_CUDA(cudaGetLastError());
+    SHQ_CUDA(cudaStreamSynchronize(st));
+    h->stats.batches++; h->stats.keys_hashed += n_keys;
+    *a.nw = n_keys;
+  SHQ_API_END
+}
+
+int shq_mg_insert_pull(shq_t h, const uint32_t* d_all_fine_hist, int parity) {
+  if (!h || !d_all_fine_hist || parity < 0 || parity > 1) return SHQ_ERR_ARG;
+  struct { const uint32_t* fh; int par; } args{d_all_fine_hist, parity};
+  SHQ_API_BEGIN(h)
+    flush_stage(h); ensure_state(h);
+    if (h->mg_peer.empty()) SHQ_FAIL(SHQ_ERR_STATE, "shq_mg_open_peers first");
+    cudaStream_t st = h->stream;
+    uint64_t& L = h->stats.kernels_launched;
+    const int world = h->nshards;
+    int shard_bits = 0; while ((1 << shard_bits) < world) shard_bits++;
+    const int cb = kMgCoarseBits > shard_bits ? kMgCoarseBits : shard_bits + 1;
+    const int gfb = shard_bits + kMgFineBits, fb = gfb - cb;
+    const int nfg = 1 << gfb, cps = 1 << (cb - shard_bits), F = 1 << kMgFineBits;
+    const int lbc = h->hb - cb, lbf = lbc - fb;
+    uint64_t n = 0;
+    {
+      Phase ph(h, &h->stats.ms_scatter);
+      h->d_bases.reserve((size_t)world * 8 + 64);
+      std::vector<const uint32_t*> b((size_t)world);
+      for (int r = 0; r < world; r++) b[r] = h->mg_peer[r * 2 + a.par];
+      SHQ_CUDA(cudaMemcpyAsync(h->d_bases.p, b.data(), (size_t)world * 8, cudaMemcpyHostToDevice, st));
+      SHQ_CUDA(cudaStreamSynchronize(st));
+      h->d_seg.reserve(((size_t)world * (cps + 1) + 8) * 8);
+      uint64_t* seg_beg = h->d_seg.as<uint64_t>();
+      h->d_fine.reserve(((size_t)F + 2) * 4); h->d_binoff.reserve(((size_t)F + 2) * 4);
+      pull_table_kernel<<<world, kScanThreads, 0, st>>>(a.fh, world, h->shard, cps, fb, nfg, seg_beg, h->d_binoff.as<uint32_t>()); L++;
+      exclusive_scan_inplace<SumU32>(h->d_binoff.as<uint32_t>(), F, h->d_scan_scratch, st, h->d_binoff.as<uint32_t>() + F, &L);
+      SHQ_CUDA(cudaMemcpyAsync(h->d_fine.p, h->d_binoff.p, (size_t)F * 4, cudaMemcpyDeviceToDevice, st));
+      n = read_scalar(h, h->d_binoff.as<uint32_t>() + F);
+      if (n == 0) return;
+      h->d_packed.reserve((n + 4) * 4);
+      int parts = 1; while (cps * parts < 4 * kNumSMs) parts *= 2;
+      resplit_kernel<false><<<cps * parts, kSplitThreads, 0, st>>>(h->d_bases.as<const uint32_t*>(), seg_beg, world, cps, parts, lbc, fb,
+                                                                 h->d_fine.as<uint32_t>(), h->d_packed.as<uint32_t>()); L++;
+      SHQ_CUDA(cudaGetLastError());
+    }
+    BatchBins bb;
+    bb.n_bins = F; bb.lb = lbf; bb.n_keys = (uint32_t)n; bb.armed = false; bb.nchunks = 1;
+    Run A{&h->d_run_keys, &h->d_run_counts, &h->d_run_chunk};
+    aggregate_bins(h, bb, 0, 0xFFFFFFFFu, false, 0, &A, nullptr, nullptr);
+    if (A.occ != n) SHQ_FAIL(SHQ_ERR_STATE, "exchange batch: %llu words aggregated, %llu expected", (unsigned long long)A.occ, (unsigned long long)n);
     uint64_t n_new = merge_run(h, A, 1, nullptr, true);
     h->ndistinct += n_new; h->nelts += A.occ;
     check_err_flag(h);

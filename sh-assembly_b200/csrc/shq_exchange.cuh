@@ -15,18 +15,70 @@
 namespace shq {
 
 // seg_beg[s * (cps + 1) + c] = first word of coarse bin c from source s inside the receive buffer;
-// counts[s * cps + c] = its length; source s starts at seg_start[s].  One thread per source.
-__global__ void seg_table_kernel(const uint32_t* __restrict__ counts, const uint64_t* __restrict__ seg_start, int world, int cps,
-                                 uint64_t* __restrict__ seg_beg) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= world) return;
-  uint64_t o = seg_start[s];
-  for (int c = 0; c < cps; c++) { seg_beg[(size_t)s * (cps + 1) + c] = o; o += counts[(size_t)s * cps + c]; }
-  seg_beg[(size_t)s * (cps + 1) + cps] = o;
+// counts[s * cps + c] = its length; source s starts at seg_start[s].  One CTA per source (block scan).
+__global__ void __launch_bounds__(kScanThreads) seg_table_kernel(const uint32_t* __restrict__ counts, const uint64_t* __restrict__ seg_start, int world,
+                                                                int cps, uint64_t* __restrict__ seg_beg) {
+  const int s = blockIdx.x;
+  const int per = (cps + kScanThreads - 1) / kScanThreads;
+  const int c0 = threadIdx.x * per;
+  uint64_t sum = 0;
+  for (int j = 0; j < per; j++) if (c0 + j < cps) sum += counts[(size_t)s * cps + c0 + j];
+  uint64_t tot;
+  uint64_t o = seg_start[s] + block_exclusive_scan<SumU64>(sum, &tot);
+  for (int j = 0; j < per; j++) {
+    if (c0 + j < cps) { seg_beg[(size_t)s * (cps + 1) + c0 + j] = o; o += counts[(size_t)s * cps + c0 + j]; }
+  }
+  if (threadIdx.x == 0) seg_beg[(size_t)s * (cps + 1) + cps] = seg_start[s] + tot;
+}
+
+// ---- pull variant: the owner reads its coarse bins straight out of every source's binned array over NVLink ----
+// fine[s * nfg + f] = words source s holds in GLOBAL fine bin f (nfg = world * F fine bins over the whole key space,
+// 2^fb fine bins per coarse bin).  One CTA per source s:
+//   seg_beg[s * (cps + 1) + c] = offset of MY coarse bin c inside source s's binned array (prefix over all its bins)
+// and, CTA-independent (grid-stride over my F fine bins): fine_tot[f] = sum over s of fine[s][rank * F + f].
+__global__ void __launch_bounds__(kScanThreads) pull_table_kernel(const uint32_t* __restrict__ fine, int world, int rank, int cps, int fb, int nfg,
+                                                                 uint64_t* __restrict__ seg_beg, uint32_t* __restrict__ fine_tot) {
+  const int s = blockIdx.x;
+  const int F = cps << fb;                                  // my fine bins
+  const uint32_t* row = fine + (size_t)s * nfg;
+  // prefix of everything before my first fine bin
+  const int before = rank * F;
+  uint64_t sum = 0;
+  for (int i = threadIdx.x; i < before; i += kScanThreads) sum += row[i];
+  uint64_t tot;
+  block_exclusive_scan<SumU64>(sum, &tot);
+  const uint64_t start = tot;
+  // my coarse bins: prefix over groups of 2^fb fine bins
+  const int per = (cps + kScanThreads - 1) / kScanThreads;
+  const int c0 = threadIdx.x * per;
+  uint64_t mine = 0;
+  for (int j = 0; j < per; j++) if (c0 + j < cps) for (int k = 0; k < (1 << fb); k++) mine += row[before + ((c0 + j) << fb) + k];
+  uint64_t tot2;
+  uint64_t o = start + block_exclusive_scan<SumU64>(mine, &tot2);
+  for (int j = 0; j < per; j++) {
+    if (c0 + j < cps) {
+      seg_beg[(size_t)s * (cps + 1) + c0 + j] = o;
+      for (int k = 0; k < (1 << fb); k++) o += row[before + ((c0 + j) << fb) + k];
+    }
+  }
+  if (threadIdx.x == 0) seg_beg[(size_t)s * (cps + 1) + cps] = start + tot2;
+  for (int f = blockIdx.x * kScanThreads + threadIdx.x; f < F; f += gridDim.x * kScanThreads) {
+    uint32_t t = 0;
+    for (int q = 0; q < world; q++) t += fine[(size_t)q * nfg + before + f];
+    fine_tot[f] = t;
+  }
+}
+// coarse[b] = sum of the 2^fb fine bins of global coarse bin b
+__global__ void coarse_from_fine_kernel(const uint32_t* __restrict__ fine, int ncoarse, int fb, uint32_t* __restrict__ coarse) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= ncoarse) return;
+  uint32_t t = 0;
+  for (int k = 0; k < (1 << fb); k++) t += fine[((size_t)b << fb) + k];
+  coarse[b] = t;
 }
 
 constexpr int kSplitThreads = 256;
-constexpr int kSplitItems = 8;
+constexpr int kSplitItems = 16;
 constexpr int kSplitTile = kSplitThreads * kSplitItems;
 constexpr int kSplitMaxFine = 64;           // fb <= 6
 
@@ -34,7 +86,7 @@ constexpr int kSplitMaxFine = 64;           // fb <= 6
 // COUNT: g_fine[c << fb | sub] += occurrences.   !COUNT: g_fine holds running cursors (start = fine bin offset);
 // the tile is counting-sorted by sub in shared memory and written out linearly.
 template <bool COUNT>
-__global__ void __launch_bounds__(kSplitThreads) resplit_kernel(const uint32_t* __restrict__ recv, const uint64_t* __restrict__ seg_beg, int world, int cps,
+__global__ void __launch_bounds__(kSplitThreads) resplit_kernel(const uint32_t* const* __restrict__ bases, const uint64_t* __restrict__ seg_beg, int world, int cps,
                                                                int parts, int lbc, int fb, uint32_t* __restrict__ g_fine, uint32_t* __restrict__ out) {
   __shared__ uint32_t s_cnt[kSplitMaxFine], s_off[kSplitMaxFine + 1], s_delta[kSplitMaxFine];
   __shared__ uint32_t s_sorted[kSplitTile];
@@ -49,6 +101,7 @@ __global__ void __launch_bounds__(kSplitThreads) resplit_kernel(const uint32_t* 
   uint32_t tile_no = 0;
   for (int s = 0; s < world; s++) {
     const uint64_t beg = seg_beg[(size_t)s * (cps + 1) + c], end = seg_beg[(size_t)s * (cps + 1) + c + 1];
+    const uint32_t* __restrict__ recv = bases[s];      // the receive buffer, or source s's own binned array (peer memory)
     for (uint64_t t0 = beg; t0 < end; t0 += kSplitTile, tile_no++) {
       if ((int)(tile_no % (uint32_t)parts) != part) continue;
       uint32_t w[kSplitItems], sr[kSplitItems];     // word, sub << 16 | rank inside (tile, sub)
@@ -56,18 +109,26 @@ __global__ void __launch_bounds__(kSplitThreads) resplit_kernel(const uint32_t* 
       for (int i = 0; i < kSplitItems; i++) {
         uint64_t idx = t0 + (uint64_t)i * kSplitThreads + threadIdx.x;
         const bool live = idx < end;
-        w[i] = live ? __ldg(&recv[idx]) : 0;
+        w[i] = live ? recv[idx] : 0;
         const uint32_t sub = live ? ((w[i] & cmask) >> lbf) : 0xFFu;
         // lanes with the same sub: one shared-memory atomic per (warp, sub), ranks from the lane order
-        const uint32_t peers = __match_any_sync(0xffffffffu, sub);
-        const int leader = __ffs(peers) - 1;
+        uint32_t peers = 0;
+        for (int j = 0; j < nfine; j++) {                 // warp-uniform: 2^fb ballots per 32 words
+          const uint32_t m = __ballot_sync(0xffffffffu, sub == (uint32_t)j);
+          if (sub == (uint32_t)j) peers = m;
+        }
+        if (COUNT) {
+          if (live && (peers & ((1u << lane) - 1)) == 0) atomicAdd(&s_cnt[sub], (uint32_t)__popc(peers));
+          continue;
+        }
+        const int leader = live ? __ffs(peers) - 1 : lane;
         uint32_t base = 0;
         if (live && lane == leader) base = atomicAdd(&s_cnt[sub], (uint32_t)__popc(peers));
         base = __shfl_sync(0xffffffffu, base, leader);
         sr[i] = (sub << 16) | (base + (uint32_t)__popc(peers & ((1u << lane) - 1)));
       }
+      if (COUNT) continue;     // counts accumulate over all tiles of this CTA (one barrier at the end)
       __syncthreads();
-      if (COUNT) continue;     // counts accumulate over all tiles of this CTA
       if (threadIdx.x == 0) {
         uint32_t o = 0;
         for (int j = 0; j < nfine; j++) {
@@ -95,6 +156,7 @@ __global__ void __launch_bounds__(kSplitThreads) resplit_kernel(const uint32_t* 
     }
   }
   if (COUNT) {
+    __syncthreads();
     if (threadIdx.x < nfine) { uint32_t v = s_cnt[threadIdx.x]; if (v) atomicAdd(&g_fine[((size_t)c << fb) | threadIdx.x], v); }
   }
 }

@@ -126,6 +126,18 @@ def gather_states(dist, keys: "torch.Tensor", counts: "torch.Tensor", world):
     return allk, allc, sizes
 
 
+class _DevView:
+    """CUDA array interface over a raw device pointer owned by libshq (no copy, no ownership)."""
+
+    def __init__(self, ptr, n, typestr="<i4"):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+def dev_view(torch, ptr, n, device):
+    """int32 tensor aliasing n words at device address ptr."""
+    return torch.as_tensor(_DevView(ptr, n), device=torch.device("cuda", device))
+
+
 class ShardedCounter:
     """CQF-deNoise over `world` GPUs: mid-stream counting with --deNoise=0, optional exact end sweep, exact export."""
 
@@ -140,6 +152,16 @@ class ShardedCounter:
         self.nelts_local = 0          # occurrences inserted into this shard
         self.full = None              # lazily created unsharded handle for sweeps / export
         self._bufs = {}
+        # k-mer exchange: "pull" = owners read their bins out of the sources' HBM over NVLink inside the split kernel
+        # (CUDA IPC, one node); "nccl" = one all-to-all of the binned 32-bit words
+        self.mode = os.environ.get("SHQ_MG_EXCHANGE", "pull")
+        self.parity = 0
+        self.max_batch_bytes = 256 << 20
+        if self.mode == "pull":
+            mine = self.shard.mg_setup(self.max_batch_bytes // 2 + (1 << 20))
+            handles = [None] * world
+            dist.all_gather_object(handles, mine)
+            self.shard.mg_open_peers(b"".join(handles), world)
 
     def _buf(self, name, n, dtype):
         t = self._bufs.get(name)
@@ -152,10 +174,11 @@ class ShardedCounter:
         self.shard.reset()
         self.nelts_local = 0
 
-    def insert_fastq_device(self, d_text_ptr, n_bytes, K, chunk_ends=None, max_batch_bytes=256 << 20):
+    def insert_fastq_device(self, d_text_ptr, n_bytes, K, chunk_ends=None, max_batch_bytes=None):
         """Device-resident text of this rank, cut into batches at chunk boundaries (every rank runs the same number
         of exchange rounds; a rank that has run out of text takes part with empty batches)."""
         torch = self.torch
+        max_batch_bytes = max_batch_bytes or self.max_batch_bytes
         ends = [int(e) for e in chunk_ends] if chunk_ends is not None and len(chunk_ends) else [int(n_bytes)]
         cuts, start, prev = [], 0, 0
         for e in ends:
@@ -169,8 +192,23 @@ class ShardedCounter:
         total = 0
         for i in range(int(nb.item())):
             a, b = cuts[i] if i < len(cuts) else (0, 0)
-            total += self._exchange_batch(d_text_ptr + a, b - a, K)
+            total += (self._pull_batch if self.mode == "pull" else self._exchange_batch)(d_text_ptr + a, b - a, K)
         return total
+
+    def _pull_batch(self, d_text_ptr, n_bytes, K):
+        """Fused exchange: bin locally into an IPC-mapped buffer, all-gather the (tiny) fine-bin histograms, then every
+        owner's split kernel loads its coarse bins straight from the peers' buffers."""
+        torch = self.torch
+        dev = torch.device("cuda", self.device)
+        nfg = self.world * 4096
+        hist = self._buf("fine_hist", nfg, torch.int32)[:nfg]
+        nw = self.shard.mg_bin_local(d_text_ptr, n_bytes, K, self.parity, hist.data_ptr())
+        allh = self._buf("all_hist", self.world * nfg, torch.int32)[:self.world * nfg]
+        self.dist.all_gather_into_tensor(allh, hist)
+        torch.cuda.ExternalStream(self.shard.stream(), device=dev).wait_stream(torch.cuda.current_stream())
+        self.shard.mg_insert_pull(allh.data_ptr(), self.parity)
+        self.parity ^= 1
+        return nw
 
     def _exchange_batch(self, d_text_ptr, n_bytes, K):
         """Two-level exchange: bin this rank's k-mers over the whole key space (coarse bins; 32-bit words), ship every
@@ -178,28 +216,37 @@ class ShardedCounter:
         torch = self.torch
         world, rank = self.world, self.rank
         dev = torch.device("cuda", self.device)
+        import time
+        T = self._timing = getattr(self, "_timing", {})
+        def tick(name, t0):
+            if os.environ.get("SHQ_MG_TIMING"):
+                torch.cuda.synchronize()
+                T[name] = T.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+            return time.perf_counter()
+        t0 = time.perf_counter()
         cb, cps, fb = exchange_geometry(world)
         nb = 1 << cb
         wp, op, nw = self.shard.mg_bin_fastq_device(d_text_ptr, n_bytes, K, cb)
-        off = self._buf("binoff", nb + 1, torch.int32)[:nb + 1]
+        t0 = tick("bin", t0)
         if nw:
-            self.shard.copy_device(off.data_ptr(), op, (nb + 1) * 4)
+            off = dev_view(torch, op, nb + 1, self.device)       # libshq's offsets, valid until its next call
+            counts = (off[1:] - off[:-1]).contiguous()
         else:
-            off.zero_()
-        counts = (off[1:] - off[:-1]).contiguous()
+            counts = torch.zeros(nb, dtype=torch.int32, device=dev)
         allc = self._buf("allc", world * nb, torch.int32)[:world * nb]
         self.dist.all_gather_into_tensor(allc, counts)
         send_counts, recv_counts, seg_start, my_counts = binned_plan(allc.view(world, nb).cpu().numpy(), rank, world)
-        send = self._buf("send", max(nw, 1), torch.int32)[:nw]
-        if nw:
-            self.shard.copy_device(send.data_ptr(), wp, nw * 4)
+        t0 = tick("plan", t0)
+        send = dev_view(torch, wp, nw, self.device) if nw else torch.zeros(0, dtype=torch.int32, device=dev)
         total = sum(recv_counts)
         recv = self._buf("recv", max(total, 1), torch.int32)[:total]
         self.dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=send_counts)
         mc = torch.from_numpy(my_counts.view(np.int32)).to(dev)
-        torch.cuda.synchronize()      # the collective ran on torch's streams; libshq works on its own stream
+        # the collective ran on torch's streams; libshq works on its own stream, which waits for it on the device
+        torch.cuda.ExternalStream(self.shard.stream(), device=dev).wait_stream(torch.cuda.current_stream())
+        t0 = tick("all_to_all", t0)
         self.shard.mg_insert_binned(recv.data_ptr(), seg_start, mc.data_ptr(), world, cb, fb, total)
-        self.nelts_local += total
+        t0 = tick("insert", t0)
         return nw
 
     def _state_tensors(self):
@@ -220,8 +267,8 @@ class ShardedCounter:
 
     def global_counts(self):
         torch = self.torch
-        nd, _ = self.shard.counts()
-        t = torch.tensor([nd, self.nelts_local], dtype=torch.int64, device=torch.device("cuda", self.device))
+        nd, ne = self.shard.counts()
+        t = torch.tensor([nd, ne], dtype=torch.int64, device=torch.device("cuda", self.device))
         self.dist.all_reduce(t)
         return int(t[0].item()), int(t[1].item())
 
@@ -245,8 +292,8 @@ class ShardedCounter:
         hi = int(torch.searchsorted(gk, torch.tensor([self.key_hi], dtype=torch.int64, device=dev)).item()) if self.key_hi < (1 << 63) else n
         # counts of the removed keys: each removed key had count 1
         before = k.numel()
-        self.shard.adopt_state(kp + lo * 8, cp + lo * 4, hi - lo, hi - lo, 0)
-        self.nelts_local -= before - (hi - lo)
+        _, ne_local = self.shard.counts()
+        self.shard.adopt_state(kp + lo * 8, cp + lo * 4, hi - lo, hi - lo, ne_local - (before - (hi - lo)))
         return removed
 
     def export(self):
@@ -342,6 +389,8 @@ def bench_sharded(args, rank, world, local_rank, text, ends, p, n_local, n_total
         step()
     torch.cuda.synchronize()
     dist.barrier()
+    sc._timing = {}
+    sc.shard.reset_stats()
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -358,6 +407,9 @@ def bench_sharded(args, rank, world, local_rank, text, ends, p, n_local, n_total
     st = sc.shard.stats()
     launches = torch.tensor([st["kernels_launched"]], dtype=torch.int64, device=dev)
     dist.all_reduce(launches)
+    if rank == 0 and os.environ.get("SHQ_MG_TIMING"):
+        import sys
+        print("mg timing (ms, warmup+timed steps):", {k: round(v, 2) for k, v in sc._timing.items()}, {k: round(v, 2) for k, v in st.items() if k.startswith("ms_")}, file=sys.stderr)
     if rank == 0:
         ms_step = float(ms.item()) / args.steps
         value = n_total / (ms_step / 1e3)

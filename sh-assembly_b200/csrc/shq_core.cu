@@ -1175,7 +1175,7 @@ int shq_mg_bin_fastq_device(shq_t h, const char* d_text, size_t n, int K, int co
 
 int shq_mg_insert_binned(shq_t h, const uint32_t* d_recv, const uint64_t* seg_start, const uint32_t* d_counts, int world,
                          int coarse_bits, int fine_bits, size_t n_words) {
-  if (!h || world < 1 || world > 64 || !seg_start || (n_words && (!d_recv || !d_counts)) || fine_bits < 0 || fine_bits > 6) return SHQ_ERR_ARG;
+  if (!h || world < 1 || world > 64 || !seg_start || (n_words && (!d_recv || !d_counts)) || fine_bits < 0 || fine_bits > 5) return SHQ_ERR_ARG;
   struct { const uint32_t* r; const uint64_t* ss; const uint32_t* c; int world, cb, fb; size_t n; } args{d_recv, seg_start, d_counts, world, coarse_bits, fine_bits, n_words};
   SHQ_API_BEGIN(h)
     flush_stage(h);
@@ -1281,7 +1281,7 @@ int shq_mg_bin_local(shq_t h, const char* d_text, size_t n, int K, int parity, u
     const int fb = gfb - cb;
     const int nfg = 1 << gfb, ncoarse = 1 << cb;
     const int lbf = h->hb - gfb, lbc = h->hb - cb;
-    if (lbf < 1 || lbc > 31 || fb < 0 || fb > 6) SHQ_FAIL(SHQ_ERR_ARG, "hb=%d does not fit the exchange geometry of %d shards", h->hb, h->nshards);
+    if (lbf < 1 || lbc > 31 || fb < 0 || fb > 5) SHQ_FAIL(SHQ_ERR_ARG, "hb=%d does not fit the exchange geometry of %d shards", h->hb, h->nshards);
     SHQ_CUDA(cudaMemsetAsync(a.fh, 0, (size_t)nfg * 4, st));
     if (a.n == 0) { SHQ_CUDA(cudaStreamSynchronize(st)); return; }
     if (a.K < 1 || a.K > 1024) SHQ_FAIL(SHQ_ERR_ARG, "K=%d outside [1,1024]", a.K);

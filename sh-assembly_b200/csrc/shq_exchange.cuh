@@ -80,7 +80,7 @@ __global__ void coarse_from_fine_kernel(const uint32_t* __restrict__ fine, int n
 constexpr int kSplitThreads = 256;
 constexpr int kSplitItems = 16;
 constexpr int kSplitTile = kSplitThreads * kSplitItems;
-constexpr int kSplitMaxFine = 64;           // fb <= 6
+constexpr int kSplitMaxFine = 32;           // fb <= 5
 
 // grid = cps * parts; CTA (c, part) walks every parts-th tile of the sub-segments of coarse bin c.
 // COUNT: g_fine[c << fb | sub] += occurrences.   !COUNT: g_fine holds running cursors (start = fine bin offset);
@@ -106,45 +106,40 @@ __global__ void __launch_bounds__(kSplitThreads) resplit_kernel(const uint32_t* 
       if ((int)(tile_no % (uint32_t)parts) != part) continue;
       uint32_t w[kSplitItems], sr[kSplitItems];     // word, sub << 16 | rank inside (tile, sub)
 #pragma unroll
+      for (int i = 0; i < kSplitItems; i++) {        // all loads of the tile are in flight before the first is used
+        uint64_t idx = t0 + (uint64_t)i * kSplitThreads + threadIdx.x;
+        w[i] = idx < end ? recv[idx] : 0xFFFFFFFFu;
+      }
+#pragma unroll
       for (int i = 0; i < kSplitItems; i++) {
         uint64_t idx = t0 + (uint64_t)i * kSplitThreads + threadIdx.x;
         const bool live = idx < end;
-        w[i] = live ? recv[idx] : 0;
-        const uint32_t sub = live ? ((w[i] & cmask) >> lbf) : 0xFFu;
-        // lanes with the same sub: one shared-memory atomic per (warp, sub), ranks from the lane order
-        uint32_t peers = 0;
-        for (int j = 0; j < nfine; j++) {                 // warp-uniform: 2^fb ballots per 32 words
-          const uint32_t m = __ballot_sync(0xffffffffu, sub == (uint32_t)j);
-          if (sub == (uint32_t)j) peers = m;
-        }
-        if (COUNT) {
-          if (live && (peers & ((1u << lane) - 1)) == 0) atomicAdd(&s_cnt[sub], (uint32_t)__popc(peers));
-          continue;
-        }
-        const int leader = live ? __ffs(peers) - 1 : lane;
-        uint32_t base = 0;
-        if (live && lane == leader) base = atomicAdd(&s_cnt[sub], (uint32_t)__popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        sr[i] = (sub << 16) | (base + (uint32_t)__popc(peers & ((1u << lane) - 1)));
+        const uint32_t sub = (w[i] & cmask) >> lbf;
+        // rank inside (tile, sub) straight from the shared-memory counter (a few-way conflict per warp)
+        if (COUNT) { if (live) atomicAdd(&s_cnt[sub], 1u); }
+        else sr[i] = live ? ((sub << 16) | atomicAdd(&s_cnt[sub], 1u)) : 0xFFFFFFFFu;
       }
       if (COUNT) continue;     // counts accumulate over all tiles of this CTA (one barrier at the end)
       __syncthreads();
-      if (threadIdx.x == 0) {
-        uint32_t o = 0;
-        for (int j = 0; j < nfine; j++) {
-          uint32_t n = s_cnt[j];
-          s_off[j] = o;
-          s_delta[j] = (n ? atomicAdd(&g_fine[((size_t)c << fb) | j], n) : 0) - o;
-          o += n; s_cnt[j] = 0;
+      if (threadIdx.x < 32) {  // nfine <= 32: lane j owns fine bin j -- one global reservation each, offsets by a warp scan
+        const uint32_t n = lane < nfine ? s_cnt[lane] : 0;
+        uint32_t inc = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+        if (lane < nfine) {
+          const uint32_t o = inc - n;
+          s_off[lane] = o;
+          s_delta[lane] = (n ? atomicAdd(&g_fine[((size_t)c << fb) | lane], n) : 0) - o;
+          s_cnt[lane] = 0;
         }
-        s_off[nfine] = o;
+        if (lane == 31) s_off[nfine] = inc;
       }
       __syncthreads();
       const uint32_t total = s_off[nfine];
 #pragma unroll
       for (int i = 0; i < kSplitItems; i++) {
         const uint32_t sub = sr[i] >> 16;
-        if (sub != 0xFFu) {
+        if (sr[i] != 0xFFFFFFFFu) {
           const uint32_t dst = s_off[sub] + (sr[i] & 0xFFFFu);
           s_sorted[dst] = w[i] & fmask;
           s_sub[dst] = (uint8_t)sub;

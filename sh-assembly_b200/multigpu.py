@@ -195,18 +195,31 @@ class ShardedCounter:
             total += (self._pull_batch if self.mode == "pull" else self._exchange_batch)(d_text_ptr + a, b - a, K)
         return total
 
+    def _tick(self, name, t0):
+        import time
+        if os.environ.get("SHQ_MG_TIMING"):
+            self.torch.cuda.synchronize()
+            T = self._timing = getattr(self, "_timing", {})
+            T[name] = T.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+        return time.perf_counter()
+
     def _pull_batch(self, d_text_ptr, n_bytes, K):
         """Fused exchange: bin locally into an IPC-mapped buffer, all-gather the (tiny) fine-bin histograms, then every
         owner's split kernel loads its coarse bins straight from the peers' buffers."""
+        import time
         torch = self.torch
         dev = torch.device("cuda", self.device)
         nfg = self.world * 4096
+        t0 = time.perf_counter()
         hist = self._buf("fine_hist", nfg, torch.int32)[:nfg]
         nw = self.shard.mg_bin_local(d_text_ptr, n_bytes, K, self.parity, hist.data_ptr())
+        t0 = self._tick("bin_local", t0)
         allh = self._buf("all_hist", self.world * nfg, torch.int32)[:self.world * nfg]
         self.dist.all_gather_into_tensor(allh, hist)
         torch.cuda.ExternalStream(self.shard.stream(), device=dev).wait_stream(torch.cuda.current_stream())
+        t0 = self._tick("all_gather_hist", t0)
         self.shard.mg_insert_pull(allh.data_ptr(), self.parity)
+        t0 = self._tick("insert_pull", t0)
         self.parity ^= 1
         return nw
 
@@ -381,9 +394,14 @@ def bench_sharded(args, rank, world, local_rank, text, ends, p, n_local, n_total
 
     def step():
         sc.reset()
+        import time
         sc.insert_fastq_device(d_text.data_ptr(), len(text), args.k, ends)
+        t0 = time.perf_counter()
         sc.materialize_sharded()
-        return sc.global_counts()
+        t0 = sc._tick("materialize_sharded", t0)
+        r = sc.global_counts()
+        sc._tick("global_counts", t0)
+        return r
 
     for _ in range(args.warmup):
         step()

@@ -11,7 +11,7 @@ def main():
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     mg = importlib.import_module("sh-assembly_b200.multigpu")
-    K, qb = 31, 21
+    K, qb = 31, 20 + (world.bit_length() - 1)      # the read set grows with the world size, so does the filter
     texts = [po.synth_fastq(G=100000, cov=30, err=0.004, n_rate=0.0003, seed=50 + r) for r in range(world)]
     text = np.frombuffer(texts[rank], np.uint8)
     d = torch.empty(len(text) + 64, dtype=torch.uint8, device="cuda")

@@ -11,12 +11,12 @@
 namespace shq {
 
 // ----------------------------------------------------- per-bin aggregation ---
-constexpr int kAggThreads = 512;
+constexpr int kAggThreads = 1024;
 constexpr int kAggWarps = kAggThreads / 32;
-constexpr int kAggTable = 8192;          // open-addressing slots per CTA (two CTAs per SM)
-constexpr int kAggMaxDistinct = 4096;    // per round (load factor <= 0.5)
+constexpr int kAggTable = 16384;         // open-addressing slots per CTA (one CTA of 32 warps per SM)
+constexpr int kAggMaxDistinct = 8192;    // per round (load factor <= 0.5)
 constexpr int kAggOrdCap = kAggMaxDistinct + kAggThreads;   // racing inserts may overshoot by < blockDim
-constexpr int kAggBuckets = 1024;        // bucket sort of the distinct keys
+constexpr int kAggBuckets = 2048;        // bucket sort of the distinct keys
 constexpr int kAggU = 8;                 // words per lane and warp tile
 constexpr int kAggWarpTile = 32 * kAggU; // a warp streams its share of the bin in tiles of 256 words
 constexpr uint32_t kAggEmpty = 0xFFFFFFFFu;
@@ -26,7 +26,7 @@ constexpr size_t kAggPendBytes = (size_t)kAggWarps * kAggWarpTile * 4;
 constexpr size_t kAggSmemBytes = (size_t)kAggTable * 10 + (size_t)kAggBuckets * 4 + (size_t)kAggOrdCap * 2 +
                                  (kAggPendBytes > (size_t)kAggOrdCap * 2 ? kAggPendBytes : (size_t)kAggOrdCap * 2);
 
-__device__ __forceinline__ uint32_t agg_hash(uint32_t k) { return (k * 2654435761u) >> (32 - 13); }
+__device__ __forceinline__ uint32_t agg_hash(uint32_t k) { return (k * 2654435761u) >> (32 - 14); }
 
 struct AggOut {
   uint64_t* keys; uint32_t* counts; uint16_t* chunk; uint32_t* n_out;   // run A (or the only run)
@@ -173,7 +173,7 @@ __device__ __forceinline__ void agg_insert_pass(const uint32_t* __restrict__ pac
 // Output (sorted by key) goes to out[sub * sub_stride + bin_off[p] + i].  A sub-range with more than
 // kAggMaxDistinct distinct keys is re-streamed in 2^k narrower key ranges.
 template <bool SPLIT>
-__global__ void __launch_bounds__(kAggThreads, 2) bin_aggregate_kernel(
+__global__ void __launch_bounds__(kAggThreads, 1) bin_aggregate_kernel(
     const uint32_t* __restrict__ packed, const uint32_t* __restrict__ bin_off, int lb, uint64_t key_lo,
     uint32_t chunk_lo, uint32_t chunk_hi, uint32_t cstar, AggOut o) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -210,7 +210,7 @@ restart:
     if (threadIdx.x == 0) { s_ndist = 0; s_nocc = 0; s_nocc2 = 0; s_overflow = 0; s_na = 0; s_nb = 0; }
     __syncthreads();
     const int bits = lb - sub_bits;                    // key_low bits that vary inside this round
-    const int bshift = bits > 10 ? bits - 10 : 0;
+    const int bshift = bits > 11 ? bits - 11 : 0;
     const uint32_t relmask = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1);
     {
       const uint32_t max_chunk = lb >= 32 ? 0u : (0xFFFFFFFFu >> lb);

@@ -319,7 +319,7 @@ bool aggregate_bins(shq_handle_s* h, const BatchBins& bb, uint32_t clo, uint32_t
   Phase ph(h, &h->stats.ms_aggregate);
   size_t cap = (size_t)bb.n_keys + 4;
   int fixed_bits = 0;               // CTAs per bin: keep each CTA's share of the bin's distinct keys inside its table
-  { uint64_t avg = bb.n_keys / (uint64_t)bb.n_bins; while (fixed_bits < 4 && fixed_bits < bb.lb && (avg >> fixed_bits) > 28000) fixed_bits++; }
+  { uint64_t avg = bb.n_keys / (uint64_t)bb.n_bins; while (fixed_bits < 4 && fixed_bits < bb.lb && (avg >> fixed_bits) > 56000) fixed_bits++; }
   const size_t S = (size_t)1 << fixed_bits;
   h->d_tmp_keys.reserve(cap * 8 * S); h->d_tmp_counts.reserve(cap * 4 * S);
   if (bb.armed) h->d_tmp_chunk.reserve(cap * 2 * S);

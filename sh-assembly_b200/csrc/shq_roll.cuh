@@ -136,8 +136,9 @@ struct Roller {
     cont = true;
   }
   // returns false when this thread has no reads left
-  template <class Emit>
-  __device__ __forceinline__ bool step(const uint64_t mask, Emit&& emit) {
+  // emit(key, chunk): one key; emit8(keys[8], chunk): the eight keys of a full group
+  template <class Emit, class Emit8>
+  __device__ __forceinline__ bool step(const uint64_t mask, Emit&& emit, Emit8&& emit8) {
     if (!active) {
       if (read >= read_end) return false;
       s = hp->nl_pos[4 * (size_t)read] + 1;
@@ -172,13 +173,22 @@ struct Roller {
         const uint32_t zo = ((ic >> 2) & 0x3333u) | (oc & 0xCCCCu);
         const uint4* fast = tab->fast;
         if (r == 8) {
+          // table entries first (they do not depend on the hashes), then the serial hash chain, then ONE call that
+          // hands over all eight keys, so the sink can overlap its shared-memory round trips
+          uint64_t k8[8];
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            const uint4 t = fast[(((j & 1) ? zo : ze) >> (4 * (j >> 1))) & 15u];
-            fh = rol1(fh) ^ ((uint64_t)t.x | ((uint64_t)t.y << 32));
-            rh = ror1(rh) ^ ((uint64_t)t.z | ((uint64_t)t.w << 32));
-            emit((fh < rh ? fh : rh) & mask, chunk);
+          for (int half = 0; half < 2; half++) {
+            uint4 t[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const int jj = half * 4 + j; t[j] = fast[(((jj & 1) ? zo : ze) >> (4 * (jj >> 1))) & 15u]; }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              fh = rol1(fh) ^ ((uint64_t)t[j].x | ((uint64_t)t[j].y << 32));
+              rh = ror1(rh) ^ ((uint64_t)t[j].z | ((uint64_t)t[j].w << 32));
+              k8[half * 4 + j] = (fh < rh ? fh : rh) & mask;
+            }
           }
+          emit8(k8, chunk);
         } else {
           for (uint32_t j = 0; j < r; j++) {               // tail of the read
             const uint4 t = fast[(((j & 1) ? zo : ze) >> (4 * (j >> 1))) & 15u];
@@ -234,7 +244,11 @@ __global__ void __launch_bounds__(kRollThreads) roll_count_kernel(HashParams hp,
     if (key < key_lo || key >= key_hi) return;
     atomicAdd(&s_hist[(uint32_t)((key - key_lo) >> lb)], 1u);
   };
-  while (R.step(mask, emit)) {}
+  auto emit8 = [&](const uint64_t* k, uint32_t ch) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) emit(k[j], ch);
+  };
+  while (R.step(mask, emit, emit8)) {}
   __syncthreads();
   for (int i = threadIdx.x; i < hp.n_bins; i += blockDim.x) { uint32_t v = s_hist[i]; if (v) atomicAdd(&g_hist[i], v); }
 }
@@ -290,9 +304,28 @@ __global__ void __launch_bounds__(THREADS) roll_scatter_kernel(HashParams hp, ui
     my_key += THREADS;
     produced++;
   };
+  auto emit8 = [&](const uint64_t* k, uint32_t ch) {
+    if (!WHOLE) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) emit(k[j], ch);
+      return;
+    }
+    uint32_t bin[8], rank[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) bin[j] = (uint32_t)(k[j] >> lb);
+#pragma unroll
+    for (int j = 0; j < 8; j++) rank[j] = atomicAdd(&s_hist[bin[j]], 1u);      // eight independent round trips
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      my_key[j * THREADS] = ((uint32_t)k[j] & lowmask) | (lb >= 32 ? 0 : (ch << lb));
+      my_key[br_off + j * THREADS] = (bin[j] << 16) | rank[j];
+    }
+    my_key += 8 * THREADS;
+    produced += 8;
+  };
   for (;;) {
     produced = 0; my_key = s_key + threadIdx.x;
-    while (more && produced + 8 <= W) more = R.step(mask, emit);
+    while (more && produced + 8 <= W) more = R.step(mask, emit, emit8);
     int any = __syncthreads_or(produced > 0);
     if (!any) break;
     {   // B: exclusive scan over the bins + global reservation; the histogram is cleared for the next round
@@ -315,18 +348,27 @@ __global__ void __launch_bounds__(THREADS) roll_scatter_kernel(HashParams hp, ui
     }
     __syncthreads();
     const uint32_t total = s_off[hp.n_bins];
-#pragma unroll 4
-    for (int j = 0; j < produced; j++) {      // C
-      int idx = j * THREADS + threadIdx.x;
-      uint32_t br = s_br[idx];
-      uint32_t bin = br >> 16;
-      uint32_t dst = s_off[bin] + (br & 0xFFFFu);
-      s_sorted[dst] = s_key[idx];
-      s_sbin[dst] = (uint16_t)bin;
+    for (int j0 = 0; j0 < produced; j0 += 4) {      // C: four keys at a time, loads before the dependent loads before the stores
+      uint32_t br[4], kk[4], off[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) { const int idx = (j0 + u) * THREADS + threadIdx.x; const bool on = j0 + u < produced; br[u] = on ? s_br[idx] : 0; kk[u] = on ? s_key[idx] : 0; }
+#pragma unroll
+      for (int u = 0; u < 4; u++) off[u] = s_off[br[u] >> 16];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (j0 + u < produced) { const uint32_t dst = off[u] + (br[u] & 0xFFFFu); s_sorted[dst] = kk[u]; s_sbin[dst] = (uint16_t)(br[u] >> 16); }
+      }
     }
     __syncthreads();
-#pragma unroll 4
-    for (uint32_t i = threadIdx.x; i < total; i += THREADS) packed[s_delta[s_sbin[i]] + i] = s_sorted[i];   // D
+    for (uint32_t i0 = threadIdx.x; i0 < total; i0 += 4 * THREADS) {   // D
+      uint32_t sb[4], dl[4], kk[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) { const uint32_t i = i0 + u * THREADS; const bool on = i < total; sb[u] = on ? s_sbin[i] : 0; kk[u] = on ? s_sorted[i] : 0; }
+#pragma unroll
+      for (int u = 0; u < 4; u++) dl[u] = s_delta[sb[u]];
+#pragma unroll
+      for (int u = 0; u < 4; u++) { const uint32_t i = i0 + u * THREADS; if (i < total) packed[dl[u] + i] = kk[u]; }
+    }
     __syncthreads();
   }
 }
@@ -351,7 +393,11 @@ __global__ void __launch_bounds__(256) roll_keys_kernel(HashParams hp, const uin
   R.start(&hp, &tab, r, r + 1, 1);
   const uint64_t mask = hp.hb >= 64 ? ~0ULL : ((1ULL << hp.hb) - 1);
   auto emit = [&](uint64_t key, uint32_t) { if (o < e) out[o++] = key; };
-  while (R.step(mask, emit)) {}
+  auto emit8 = [&](const uint64_t* k, uint32_t ch) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) emit(k[j], ch);
+  };
+  while (R.step(mask, emit, emit8)) {}
   while (o < e) out[o++] = kNoKey;
 }
 

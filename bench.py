@@ -298,10 +298,13 @@ def run_ours(args, rank, world, local_rank):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
     dom = max(phases, key=phases.get)
     alg = phase_bytes(dom, args, n_total, text.nbytes, ndistinct, table_bytes, rounds)
-    launches_dom = {"ms_hash_count": 1, "ms_scatter": 1, "ms_aggregate": None, "ms_merge": None, "ms_layout": None, "ms_denoise": None}
     achieved = alg / (phases[dom] / 1e3) / 1e9
+    nl = PHASE_LAUNCHES[dom]
     roofline = {"bound": "hbm", "kernel": PHASE_KERNEL[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": alg,
+                "traffic": measured_traffic(PHASE_KERNEL[dom]), "peak_source": peak_src, "algorithmic_bytes_per_step": alg,
+                "algorithmic_bytes_per_launch": alg / nl, "launches_per_step": nl, "ms_per_launch": phases[dom] / nl,
+                "note": "integer/byte path bound by instruction issue and shared-memory latency, not by HBM (DESIGN.md 4); "
+                        "achieved = algorithmic bytes / CUDA-event time of the phase on the handle's stream",
                 "phase_ms_per_step": phases,
                 "pipeline": {"bytes_per_kmer": a_ins, "achieved": value * a_ins / 1e9, "frac": value * a_ins / 1e9 / peak,
                              "note": "whole insert path against SURVEY 8(d) A_ins"}}
@@ -355,8 +358,21 @@ def bench_unitigs(args, shq, q, text, ends, h_ptr):
     return out
 
 
-PHASE_KERNEL = {"ms_hash_count": "hash_reads_kernel<count>", "ms_scatter": "hash_reads_kernel<scatter>", "ms_aggregate": "bin_aggregate_kernel",
-                "ms_merge": "merge_tiles_kernel", "ms_layout": "image_tiles_kernel", "ms_denoise": "denoise kernels"}
+PHASE_KERNEL = {"ms_hash_count": "roll_count_kernel", "ms_scatter": "roll_scatter_kernel", "ms_aggregate": "bin_aggregate_kernel",
+                "ms_merge": "merge_tiles_kernel", "ms_layout": "layout_scan_kernel + image_tiles_kernel", "ms_denoise": "denoise_tiles_kernel"}
+# launches of the phase's dominant kernel per step on the default workload (4 device batches; the aggregator runs once
+# more for the split at the mid-stream deNoise boundary)
+PHASE_LAUNCHES = {"ms_hash_count": 4, "ms_scatter": 4, "ms_aggregate": 5, "ms_merge": 10, "ms_layout": 1, "ms_denoise": 2}
+
+
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full capture
+    (profiles/r1_traffic.json, written by tools/ncu_summary.py from the same bench command); None if absent."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        return t.get(kernel)
+    except Exception:
+        return None
 
 
 def phase_bytes(phase, args, n_kmers, text_bytes, ndistinct, table_bytes, rounds):

@@ -368,6 +368,19 @@ class ShardedCounter:
         parts.sort(key=lambda x: x[0])
         return self.shard.header(nd, ne) + b"".join(p[1] for p in parts)
 
+    def build_unitigs(self, chunks, K, s_min=2, x_min=2, x_max=1000000):
+        """Contiger at N > 1 (replica): the shard images are assembled into the reference .cqf on rank 0 and the
+        single-GPU device path runs there; cross-shard neighbour queries are not built yet.  Rank 0 returns the
+        FASTA text, other ranks None.  `chunks` = the read chunks of ALL ranks on rank 0."""
+        img = self.export_sharded()
+        if self.rank != 0:
+            return None
+        g = self.shq.CQF.from_bytes(img, device=self.device)
+        try:
+            return self.shq.build_unitigs(g, chunks, K, s_min, x_min, x_max)
+        finally:
+            g.close()
+
     def materialize_global(self):
         """Build the global image on rank 0 in device memory (benchmark: 'table complete')."""
         torch = self.torch

@@ -172,3 +172,68 @@ def test_pinned_pipeline_matches_oracle(po, shq, batch_mb, monkeypatch):
     assert g.counts() == o.counts()
     assert g.export() == o.export()
     g.close()
+
+
+def _mg_text(po):
+    return fastq(po, G=80000, cov=30, err=0.004, n_rate=0.0003, seed=77)
+
+
+def test_two_level_binned_insert_world1(po, shq):
+    """The multi-GPU exchange path on one rank: coarse binning over the whole key space, owner-side split into fine
+    bins, aggregate + merge; image and counters must equal the oracle's."""
+    import importlib
+    import torch
+    mg = importlib.import_module("sh-assembly_b200.multigpu")
+    K, qb = 31, 20
+    text = _mg_text(po)
+    o, _ = po.count_run([text], K, qb, qb + 8, 0, 0, False)
+    t = np.frombuffer(text, np.uint8)
+    d = torch.empty(len(t) + 64, dtype=torch.uint8, device="cuda")
+    d[:len(t)].copy_(torch.from_numpy(t.copy()))
+    torch.cuda.synchronize()
+    for cb, fb in [(8, 4), (11, 1), (6, 5)]:
+        g = shq.CQF(qb, qb + 8)
+        wp, op, nw = g.mg_bin_fastq_device(d.data_ptr(), len(t), K, cb)
+        off = mg.dev_view(torch, op, (1 << cb) + 1, 0)
+        counts = (off[1:] - off[:-1]).contiguous()
+        torch.cuda.synchronize()
+        g.mg_insert_binned(wp, np.zeros(1, np.uint64), counts.data_ptr(), 1, cb, fb, nw)
+        assert g.counts() == o.counts(), (cb, fb)
+        assert g.export() == o.export(), (cb, fb)
+        g.close()
+
+
+def test_pull_exchange_and_shard_image_world1(po, shq):
+    """shq_mg_setup / open_peers / bin_local / insert_pull and the carry-based shard image with a single rank."""
+    import torch
+    K, qb = 31, 20
+    text = _mg_text(po)
+    o, _ = po.count_run([text], K, qb, qb + 8, 0, 0, False)
+    t = np.frombuffer(text, np.uint8)
+    d = torch.empty(len(t) + 64, dtype=torch.uint8, device="cuda")
+    d[:len(t)].copy_(torch.from_numpy(t.copy()))
+    torch.cuda.synchronize()
+    g = shq.CQF(qb, qb + 8)
+    handles = g.mg_setup(len(t))
+    g.mg_open_peers(handles, 1)
+    hist = torch.zeros(4096, dtype=torch.int32, device="cuda")
+    half = (len(t) // 2)
+    cut = text.rfind(b"\n@", 0, half) + 1          # a record boundary ('@' cannot start a quality line here: all 'I')
+    for parity, (a, b) in enumerate([(0, cut), (cut, len(t))]):
+        nw = g.mg_bin_local(d.data_ptr() + a, b - a, K, parity, hist.data_ptr())
+        assert nw > 0 and int(hist.sum().item()) == nw
+        g.mg_insert_pull(hist.data_ptr(), parity)
+    assert g.counts() == o.counts()
+    assert g.export() == o.export()
+    # shard image (world 1: no carry, no spill) == the blocks of the exported file
+    agg = g.mg_layout_aggregate()
+    NEG = -(1 << 60)
+    keys = torch.zeros(16, dtype=torch.int64, device="cuda")
+    nt = g.mg_layout_tail((0, NEG), 16, keys.data_ptr(), keys.data_ptr(), keys.data_ptr())
+    assert nt == 0 and agg[0] > 0
+    img, fb_, nb = g.mg_materialize_shard(0, 0, 0, 0)
+    assert fb_ == 0 and nb == g.nblocks
+    out = torch.empty(nb * 89, dtype=torch.uint8, device="cuda")
+    g.copy_device(out.data_ptr(), img, nb * 89)
+    assert g.header(*g.counts()) + out.cpu().numpy().tobytes() == o.export()
+    g.close()

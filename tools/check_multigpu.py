@@ -31,6 +31,13 @@ def main():
             print("world", world, "endDeNoise", end, "removed", removed, "counts", (nd, ne), o.counts(), "image equal:", ok,
                   "sharded image equal:", ok2, flush=True)
             assert ok and ok2 and (nd, ne) == o.counts()
+        if end:
+            fa = sc.build_unitigs(texts if rank == 0 else None, K)
+            if rank == 0:
+                fa_o, _ = po.contiger_run(o, texts, K, 2, 2, 1000000)
+                same = po.canonical_unitig_set(fa) == po.canonical_unitig_set(fa_o) and po.canonical_links(fa) == po.canonical_links(fa_o)
+                print("world", world, "unitigs", len(po.parse_unitigs(fa)), "equal to the oracle's:", same, flush=True)
+                assert same
         dist.barrier()
     dist.destroy_process_group()
 

@@ -17,6 +17,19 @@ for i, d in enumerate(data):
     print(i, name, ' '.join("%s=%s%s" % (v, d[hdr.index(k)][:9], units[hdr.index(k)][:2] if v in ('rd', 'wr', 'ms') else '') for k, v in short.items() if k in hdr))
     stalls = sorted(((float(d[hdr.index(s)]), s.split('stalled_')[1].split('_per')[0]) for s in st), reverse=True)[:6]
     print('    stalls:', ' '.join("%s=%.2f" % (n, v) for v, n in stalls))
+def _bytes(v, u):
+    v = float(v.replace(',', ''))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+if "--traffic" in sys.argv:
+    import collections, json, re
+    out = sys.argv[sys.argv.index("--traffic") + 1]
+    acc = collections.defaultdict(list)
+    ir, iw = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
+    for d in data:
+        name = re.split(r'[<(]', d[hdr.index('Kernel Name')])[0].split('::')[-1].replace('void ', '').strip()
+        acc[name].append(_bytes(d[ir], units[ir]) + _bytes(d[iw], units[iw]))
+    json.dump({k: sum(v) / len(v) for k, v in acc.items()}, open(out, 'w'), indent=1, sort_keys=True)
+    sys.argv = [a for a in sys.argv if a not in ("--traffic", out)]
 if len(sys.argv) > 2:
     src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
     secs = []; cur = None

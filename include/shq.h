@@ -251,6 +251,7 @@ typedef struct {
   uint64_t keys_hashed;        /* k-mer occurrences hashed */
   double ms_hash_count, ms_scatter, ms_aggregate, ms_merge, ms_layout, ms_denoise; /* CUDA-event ms */
   uint64_t h2d_bytes, d2h_bytes;
+  uint64_t bin_fallbacks;      /* batches whose one-pass binning overflowed a bin and were redone with exact offsets */
 } shq_stats;
 int shq_get_stats(shq_t h, shq_stats* out);
 int shq_reset_stats(shq_t h);

@@ -31,7 +31,7 @@ class shq_stats(C.Structure):
     _fields_ = [("kernels_launched", C.c_uint64), ("batches", C.c_uint64), ("keys_hashed", C.c_uint64),
                 ("ms_hash_count", C.c_double), ("ms_scatter", C.c_double), ("ms_aggregate", C.c_double),
                 ("ms_merge", C.c_double), ("ms_layout", C.c_double), ("ms_denoise", C.c_double),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("bin_fallbacks", C.c_uint64)]
 
 
 class shq_unitig_opts(C.Structure):

@@ -26,7 +26,9 @@ constexpr size_t kAggPendBytes = (size_t)kAggWarps * kAggWarpTile * 4;
 constexpr size_t kAggSmemBytes = (size_t)kAggTable * 10 + (size_t)kAggBuckets * 4 + (size_t)kAggOrdCap * 2 +
                                  (kAggPendBytes > (size_t)kAggOrdCap * 2 ? kAggPendBytes : (size_t)kAggOrdCap * 2);
 
-__device__ __forceinline__ uint32_t agg_hash(uint32_t k) { return (k * 2654435761u) >> (32 - 14); }
+// home slot: the first (even) slot of a pair.  Probing is linear from there, so a key sits in its home pair unless both
+// slots were taken by other keys; pass 1 looks at the whole pair with one 64-bit load.
+__device__ __forceinline__ uint32_t agg_hash(uint32_t k) { return ((k * 2654435761u) >> (32 - 13)) << 1; }
 
 struct AggOut {
   uint64_t* keys; uint32_t* counts; uint16_t* chunk; uint32_t* n_out;   // run A (or the only run)
@@ -34,6 +36,7 @@ struct AggOut {
   uint32_t* occ_out; uint32_t* occ_out2;
   uint32_t* first_hist;     // optional: histogram over first-chunk ids of the distinct keys (state empty => all new)
   int* split_overflow;      // SPLIT: set when a 16-bit half counter would overflow
+  const uint32_t* bin_end;  // optional: end of every bin (fixed-capacity bins); null = bin_off[p + 1]
   int fixed_bits;           // each bin is handled by 2^fixed_bits CTAs, one per key sub-range
   size_t sub_stride;        // outputs of sub-range s live at [s * sub_stride + bin_off[p] + i]
 };
@@ -113,8 +116,10 @@ __device__ __forceinline__ void agg_insert_pass(const uint32_t* __restrict__ pac
       }
       const bool second = SPLIT && ch > cstar;
       if (FILT || SPLIT) { my_occ2 += (live & second) ? 1u : 0u; my_occ += (live & !second) ? 1u : 0u; }
-      const uint32_t h = agg_hash(kl);
-      const bool hit = live & (T.key[h] == kl);
+      const uint32_t h0 = agg_hash(kl);
+      const uint2 pr = *reinterpret_cast<const uint2*>(&T.key[h0]);
+      const bool hit = live & ((pr.x == kl) | (pr.y == kl));
+      const uint32_t h = h0 + (pr.y == kl ? 1u : 0u);
       if (SPLIT) {
         if (hit) agg_count<SPLIT, CHUNK>(T, h, ch, second);
       } else {
@@ -188,7 +193,9 @@ __global__ void __launch_bounds__(kAggThreads, 1) bin_aggregate_kernel(
 
   const uint32_t p = blockIdx.x >> o.fixed_bits;
   const uint32_t fsub = blockIdx.x & ((1u << o.fixed_bits) - 1);
-  const uint32_t beg = bin_off[p], end = bin_off[p + 1];
+  const uint32_t beg = bin_off[p];
+  uint32_t end = bin_off[p + 1];
+  if (o.bin_end) { const uint32_t e = o.bin_end[p]; end = e < end ? e : end; }     // never past the bin's own range
   const size_t obase = (size_t)fsub * o.sub_stride + beg;
   const uint32_t lowmask = lb >= 32 ? 0xFFFFFFFFu : ((1u << lb) - 1);
   const bool want_chunk = !SPLIT && (o.chunk != nullptr || o.first_hist != nullptr);
@@ -244,17 +251,20 @@ restart:
       s_ord[atomicAdd(&s_bkt[(k & relmask) >> bshift], 1u)] = (uint16_t)slot;
     }
     __syncthreads();
-#pragma unroll
-    for (int j = 0; j < PER; j++) {                    // s_bkt[b] is now the END of bucket b: insertion sort inside the bucket
-      int b = threadIdx.x * PER + j;
-      uint32_t lo = b ? s_bkt[b - 1] : 0, hi = s_bkt[b];
-      for (uint32_t x = lo + 1; x < hi; x++) {
-        uint16_t sx = s_ord[x]; uint32_t kx = t_key[sx]; uint32_t y = x;
-        while (y > lo && t_key[s_ord[y - 1]] > kx) { s_ord[y] = s_ord[y - 1]; y--; }
-        s_ord[y] = sx;
-      }
+    // s_bkt[b] is now the END of bucket b.  Keys are distinct, so the place of a key inside its bucket is the number of
+    // smaller keys there: every thread ranks its own key (no serial insertion sort, no divergence beyond bucket size).
+    // The final order goes to s_new (its list of fresh slots is no longer needed).
+    for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) {
+      const uint16_t slot = s_ord[i];
+      const uint32_t k = t_key[slot];
+      const uint32_t b = (k & relmask) >> bshift;
+      const uint32_t lo = b ? s_bkt[b - 1] : 0, hi = s_bkt[b];
+      uint32_t rank = 0;
+      for (uint32_t x = lo; x < hi; x++) rank += t_key[s_ord[x]] < k ? 1u : 0u;
+      s_new[lo + rank] = slot;
     }
     __syncthreads();
+    const uint16_t* s_fin = s_new;
     const bool do_hist = !SPLIT && o.first_hist != nullptr;
     if (do_hist) {                                     // s_bkt is free now: per-CTA histogram of first chunks
       for (int i = threadIdx.x; i < kAggBuckets; i += blockDim.x) s_bkt[i] = 0;
@@ -263,7 +273,7 @@ restart:
     // ---- emit
     if (!SPLIT) {
       for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) {
-        uint32_t h = s_ord[i];
+        uint32_t h = s_fin[i];
         size_t oo = obase + written + i;
         o.keys[oo] = key_lo + (((uint64_t)p << lb) | t_key[h]);
         o.counts[oo] = t_cnt[h];
@@ -280,7 +290,7 @@ restart:
       const uint32_t i0 = threadIdx.x * per;
       for (uint32_t j = 0; j < per && j < (uint32_t)SL; j++) {
         uint32_t i = i0 + j;
-        cs[j] = i < nd ? t_cnt[s_ord[i]] : 0;
+        cs[j] = i < nd ? t_cnt[s_fin[i]] : 0;
         fa += (cs[j] & 0xFFFFu) ? 1 : 0; fb += (cs[j] >> 16) ? 1 : 0;
       }
       uint32_t ta, tb;
@@ -290,7 +300,7 @@ restart:
         uint32_t i = i0 + j;
         if (i >= nd) break;
         uint32_t c = cs[j];
-        uint64_t key = key_lo + (((uint64_t)p << lb) | t_key[s_ord[i]]);
+        uint64_t key = key_lo + (((uint64_t)p << lb) | t_key[s_fin[i]]);
         if (c & 0xFFFFu) { size_t oo = obase + written + ra; o.keys[oo] = key; o.counts[oo] = c & 0xFFFFu; if (o.chunk) o.chunk[oo] = 0; ra++; }
         if (c >> 16) { size_t oo = obase + written2 + rb; o.keys2[oo] = key; o.counts2[oo] = c >> 16; rb++; }
       }

@@ -170,10 +170,17 @@ void read_pair(shq_handle_s* h, const T* da, T* a, const U* db, U* b) {
 // A "run" = sorted distinct (key, count[, first chunk]) produced from one batch of binned keys.
 struct BatchBins {
   int n_bins = 0, lb = 0;
-  uint32_t n_keys = 0;          // occurrences scattered
+  uint32_t n_keys = 0;          // occurrences scattered (an upper bound when spec)
   bool armed = false;
   int nchunks = 0;
+  bool spec = false;            // fixed-capacity bins, no counting pass: bin p = [p * capbin, cursor[p])
+  mutable bool spec_checked = false;
+  uint32_t span = 0;            // words spanned by the binned array when spec
 };
+struct BinOverflow {};          // a fixed-capacity bin overflowed: redo the batch with exact offsets
+
+int g_spec_bins = 1;            // SHQ_SPEC_BINS=0 forces the two-pass (count, then scatter) binning
+uint64_t g_spec_fallbacks = 0;
 struct Run { DevBuf* keys; DevBuf* counts; DevBuf* chunk; size_t n = 0; uint64_t occ = 0; };
 
 int g_bin_bits = 0;             // 0 = automatic (tunable: SHQ_BIN_BITS)
@@ -213,7 +220,7 @@ uint32_t index_lines(shq_handle_s* h, const char* d_text, size_t n_text) {
 // global_bits > 0: bin over the WHOLE key space [0, 2^hb) into 2^global_bits bins, whatever this handle's shard
 // is (first level of the multi-GPU exchange: bins of one owner are contiguous).
 void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_t* h_chunk_ends, int nchunks, int K,
-               const uint64_t* d_keys, size_t n_keys_in, bool armed, BatchBins* bb, int global_bits = 0) {
+               const uint64_t* d_keys, size_t n_keys_in, bool armed, BatchBins* bb, int global_bits = 0, bool allow_spec = false) {
   cudaStream_t st = h->stream;
   uint64_t& L = h->stats.kernels_launched;
   HashParams hp{};
@@ -261,6 +268,37 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
   size_t smem_scatter = sizeof(RollTables) + ((size_t)3 * n_bins + 1) * 4 + (size_t)kScatThreads * (wide ? 16 : 8) * 14 + 16 + smem_cle;
   size_t smem_keys = (size_t)n_bins * 8;
   Sink sk{};
+  if (allow_spec && g_spec_bins && from_text && whole && wide && !global_bits) {
+    // One hashing pass.  ntHash keys are uniform, so every bin gets the mean + 6 % + 2048 words; a bin that would not
+    // fit is caught by the scatter kernel and the caller falls back to the exact two-pass binning for this batch.
+    h->d_misc.reserve(256);
+    unsigned long long* d_ub = h->d_misc.as<unsigned long long>() + 12;
+    SHQ_CUDA(cudaMemsetAsync(d_ub, 0, 8, st));
+    window_total_kernel<<<kNumSMs * 4, 256, 0, st>>>(hp.nl_pos, hp.n_reads, K, d_ub); L++;
+    unsigned long long n_ub = 0; int dev_err = 0;
+    read_pair(h, d_ub, &n_ub, h->d_err, &dev_err);
+    if (dev_err) { SHQ_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(int), st)); SHQ_FAIL(dev_err, "device reported: %s", shq_strerror(dev_err)); }
+    const uint64_t capbin = ((n_ub / (uint64_t)n_bins) * 17 / 16 + 2048 + 7) & ~7ULL;
+    const uint64_t span = capbin * (uint64_t)n_bins;
+    const uint64_t round = (uint64_t)kScatThreads * 16;
+    if (n_ub > 0 && span + round + 64 < ((uint64_t)1 << 32)) {
+      h->d_packed.reserve((size_t)(span + round + 64) * 4);
+      int* d_ovf = h->d_misc.as<int>() + 20;
+      SHQ_CUDA(cudaMemsetAsync(d_ovf, 0, 4, st));
+      fixed_bin_offsets_kernel<<<cdiv(n_bins + 1, 256), 256, 0, st>>>(h->d_binoff.as<uint32_t>(), h->d_tot.as<uint32_t>(), n_bins, (uint32_t)capbin); L++;
+      {
+        Phase ph(h, &h->stats.ms_scatter);
+        SHQ_CUDA(cudaFuncSetAttribute(roll_scatter_kernel<kScatThreads, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
+        roll_scatter_kernel<kScatThreads, 16, true><<<kNumSMs, kScatThreads, smem_scatter, st>>>(hp, h->d_tot.as<uint32_t>(), h->d_packed.as<uint32_t>(),
+                                                                                             (uint32_t)capbin, (uint32_t)span, d_ovf); L++;
+      }
+      SHQ_CUDA(cudaGetLastError());
+      bb->n_bins = n_bins; bb->lb = lb; bb->n_keys = (uint32_t)n_ub; bb->armed = armed; bb->nchunks = nchunks;
+      bb->spec = true; bb->span = (uint32_t)span;
+      h->stats.keys_hashed += n_ub;
+      return;
+    }
+  }
   {
     Phase ph(h, &h->stats.ms_hash_count);
     if (from_text) {
@@ -305,6 +343,7 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
   }
   SHQ_CUDA(cudaGetLastError());
   bb->n_bins = n_bins; bb->lb = lb; bb->n_keys = n_keys; bb->armed = armed; bb->nchunks = nchunks;
+  bb->spec = false; bb->span = 0;
   h->stats.keys_hashed += n_keys;
 }
 
@@ -317,7 +356,7 @@ bool aggregate_bins(shq_handle_s* h, const BatchBins& bb, uint32_t clo, uint32_t
   cudaStream_t st = h->stream;
   uint64_t& L = h->stats.kernels_launched;
   Phase ph(h, &h->stats.ms_aggregate);
-  size_t cap = (size_t)bb.n_keys + 4;
+  size_t cap = (size_t)(bb.spec ? bb.span : bb.n_keys) + 4;
   int fixed_bits = 0;               // CTAs per bin: keep each CTA's share of the bin's distinct keys inside its table
   { uint64_t avg = bb.n_keys / (uint64_t)bb.n_bins; while (fixed_bits < 4 && fixed_bits < bb.lb && (avg >> fixed_bits) > 56000) fixed_bits++; }
   const size_t S = (size_t)1 << fixed_bits;
@@ -344,6 +383,7 @@ bool aggregate_bins(shq_handle_s* h, const BatchBins& bb, uint32_t clo, uint32_t
   o.n_out = n_out; o.keys2 = split ? h->d_tmp_keys2.as<uint64_t>() : nullptr; o.counts2 = split ? h->d_tmp_counts2.as<uint32_t>() : nullptr;
   o.n_out2 = n_out2; o.occ_out = occ; o.occ_out2 = occ2; o.first_hist = d_fh; o.split_overflow = d_ovf;
   o.fixed_bits = fixed_bits; o.sub_stride = cap;
+  o.bin_end = bb.spec ? h->d_tot.as<uint32_t>() : nullptr;
   if (split) {
     SHQ_CUDA(cudaFuncSetAttribute(bin_aggregate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggSmemBytes));
     bin_aggregate_kernel<true><<<(unsigned)nb, kAggThreads, kAggSmemBytes, st>>>(h->d_packed.as<uint32_t>(), h->d_binoff.as<uint32_t>(), bb.lb, h->key_lo,
@@ -354,6 +394,11 @@ bool aggregate_bins(shq_handle_s* h, const BatchBins& bb, uint32_t clo, uint32_t
                                                                               clo, chi, cstar, o);
   }
   L++;
+  if (bb.spec && !bb.spec_checked) {   // did every bin fit its fixed range?  (read once per binned batch)
+    bb.spec_checked = true;
+    int* d_bovf = h->d_misc.as<int>() + 20;
+    if (read_scalar(h, d_bovf)) throw BinOverflow{};
+  }
   if (split && read_scalar(h, d_ovf)) return false;
   auto finish = [&](Run* R, uint32_t* nout, uint32_t* dense, uint32_t* occs, const uint64_t* tk, const uint32_t* tc, const uint16_t* tch) {
     SHQ_CUDA(cudaMemcpyAsync(dense, nout, nb * 4, cudaMemcpyDeviceToDevice, st));
@@ -543,13 +588,13 @@ void process_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uin
   if (!from_text && n_keys_in == 0) return;
   bool armed = from_text && h->rounds_left > 0;
   BatchBins bb;
-  bin_batch(h, d_text, n_text, chunk_ends, nchunks, K, d_keys, n_keys_in, armed, &bb);
+  bin_batch(h, d_text, n_text, chunk_ends, nchunks, K, d_keys, n_keys_in, armed, &bb, 0, true);
   h->stats.batches++;
   if (bb.n_keys == 0) return;
   Run A{&h->d_run_keys, &h->d_run_counts, &h->d_run_chunk}, B{&h->d_run2_keys, &h->d_run2_counts, nullptr};
   uint32_t clo = 0;
   const uint32_t last = (uint32_t)(nchunks > 0 ? nchunks - 1 : 0);
-  for (;;) {
+  for (;;) try {
     bool track = armed && h->rounds_left > 0;
     if (!track) {
       aggregate_bins(h, bb, clo, armed ? last : 0xFFFFFFFFu, false, 0, &A, nullptr, nullptr);
@@ -588,6 +633,11 @@ void process_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uin
     h->rounds_left--;
     denoise_round(h);
     clo = (uint32_t)cstar + 1;
+  } catch (const BinOverflow&) {
+    // thrown by the first aggregation of a one-pass batch, before anything was merged: bin again with exact offsets
+    g_spec_fallbacks++; h->stats.bin_fallbacks++;
+    bin_batch(h, d_text, n_text, chunk_ends, nchunks, K, d_keys, n_keys_in, armed, &bb, 0, false);
+    if (bb.n_keys == 0) return;
   }
   check_err_flag(h);
 }
@@ -683,6 +733,7 @@ void init_handle(shq_handle_s* h, int qb, int hb, uint32_t seed, int device, int
   if (nshards < 1 || (nshards & (nshards - 1)) || shard < 0 || shard >= nshards || (1 << qb) < nshards * 64)
     SHQ_FAIL(SHQ_ERR_ARG, "bad shard %d of %d", shard, nshards);
   if (const char* e = getenv("SHQ_MAX_BATCH_MB")) { long v = atol(e); if (v >= 1 && v <= 3072) h->max_batch_bytes = (size_t)v << 20; }
+  if (const char* e = getenv("SHQ_SPEC_BINS")) g_spec_bins = atoi(e) != 0;
   if (const char* e = getenv("SHQ_BIN_BITS")) { int v = atoi(e); if (v >= 4 && v <= 13) g_bin_bits = v; }
   SHQ_CUDA(cudaSetDevice(device));
   h->device = device; h->qb = qb; h->hb = hb; h->seed = seed; h->shard = shard; h->nshards = nshards;

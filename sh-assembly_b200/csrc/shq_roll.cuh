@@ -264,8 +264,12 @@ __global__ void __launch_bounds__(kRollThreads) roll_count_kernel(HashParams hp,
 // dynamic smem: RollTables + (3 * n_bins + 1) * 4 + THREADS * W * 14 (+ chunk map)
 constexpr int kScatThreads = 768;
 constexpr int kScatW = 16;
+// capbin > 0: no counting pass was run -- bin b owns the fixed range [b * capbin, (b + 1) * capbin); a reservation that
+// does not fit raises *ovf and its words go to a scratch area at slack_base (one round long), so nothing is overwritten;
+// the host then redoes the batch with exact offsets.
 template <int THREADS, int W, bool WHOLE>
-__global__ void __launch_bounds__(THREADS) roll_scatter_kernel(HashParams hp, uint32_t* __restrict__ g_cursor, uint32_t* __restrict__ packed) {
+__global__ void __launch_bounds__(THREADS) roll_scatter_kernel(HashParams hp, uint32_t* __restrict__ g_cursor, uint32_t* __restrict__ packed,
+                                                               uint32_t capbin = 0, uint32_t slack_base = 0, int* __restrict__ ovf = nullptr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RollTables* tab = reinterpret_cast<RollTables*>(smem_raw);
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw + sizeof(RollTables));
@@ -340,7 +344,9 @@ __global__ void __launch_bounds__(THREADS) roll_scatter_kernel(HashParams hp, ui
           uint32_t c = s_hist[b];
           s_hist[b] = 0;
           s_off[b] = ex;
-          s_delta[b] = (c ? atomicAdd(&g_cursor[b], c) : 0) - ex;
+          uint32_t base = c ? atomicAdd(&g_cursor[b], c) : 0;
+          if (capbin && c && (uint64_t)base + c > (uint64_t)(b + 1) * capbin) { *ovf = 1; base = slack_base + ex; }
+          s_delta[b] = base - ex;
           ex += c;
         }
       }
@@ -380,6 +386,21 @@ __global__ void read_window_counts_kernel(const uint32_t* __restrict__ nl_pos, u
   if (r >= n_reads) return;
   uint32_t len = nl_pos[4 * (size_t)r + 1] - (nl_pos[4 * (size_t)r] + 1);
   cnt[r] = len >= (uint32_t)K ? len - K + 1 : 0;
+}
+// upper bound of the number of keys in a batch: sum over the reads of max(len - K + 1, 0) (the N rule only removes keys)
+__global__ void __launch_bounds__(256) window_total_kernel(const uint32_t* __restrict__ nl_pos, uint32_t n_reads, int K,
+                                                          unsigned long long* __restrict__ total) {
+  unsigned long long acc = 0;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += gridDim.x * blockDim.x) {
+    uint32_t len = nl_pos[4 * (size_t)r + 1] - (nl_pos[4 * (size_t)r] + 1);
+    acc += len >= (uint32_t)K ? len - K + 1 : 0;
+  }
+  for (int d = 16; d; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(total, acc);
+}
+__global__ void fixed_bin_offsets_kernel(uint32_t* __restrict__ bin_off, uint32_t* __restrict__ cursor, int n_bins, uint32_t capbin) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p <= n_bins) { bin_off[p] = (uint32_t)p * capbin; if (p < n_bins) cursor[p] = (uint32_t)p * capbin; }
 }
 constexpr uint64_t kNoKey = ~0ULL;
 __global__ void __launch_bounds__(256) roll_keys_kernel(HashParams hp, const uint64_t* __restrict__ off, uint64_t* __restrict__ out) {

@@ -237,3 +237,21 @@ def test_pull_exchange_and_shard_image_world1(po, shq):
     g.copy_device(out.data_ptr(), img, nb * 89)
     assert g.header(*g.counts()) + out.cpu().numpy().tobytes() == o.export()
     g.close()
+
+
+def test_skewed_bins_fall_back_to_exact_binning(po, shq):
+    """One-pass binning gives every bin the mean + 6 %; a read set dominated by one k-mer overflows its bin and the
+    batch must be redone with exact offsets -- same image as the oracle either way."""
+    K, qb = 31, 20
+    base = fastq(po, G=30000, cov=10, err=0.003, seed=91)
+    rep = b"".join(b"@p%d\n%s\n+\n%s\n" % (i, b"A" * 150, b"I" * 150) for i in range(6000))
+    text = base + rep
+    o, _ = po.count_run([text], K, qb, qb + 8, 0, 0, False)
+    g = shq.CQF(qb, qb + 8)
+    for _, ch in po.chunks([text]):
+        g.insert_fastq_chunk(ch, K)
+    g.finish()
+    assert g.stats()["bin_fallbacks"] >= 1
+    assert g.counts() == o.counts()
+    assert g.export() == o.export()
+    g.close()

@@ -290,7 +290,8 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
         Phase ph(h, &h->stats.ms_scatter);
         SHQ_CUDA(cudaFuncSetAttribute(roll_scatter_kernel<kScatThreads, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
         roll_scatter_kernel<kScatThreads, 16, true><<<kNumSMs, kScatThreads, smem_scatter, st>>>(hp, h->d_tot.as<uint32_t>(), h->d_packed.as<uint32_t>(),
-                                                                                             (uint32_t)capbin, (uint32_t)span, d_ovf); L++;
+                                                                                             (uint32_t)capbin, (uint32_t)span, d_ovf);
+        L++;
       }
       SHQ_CUDA(cudaGetLastError());
       bb->n_bins = n_bins; bb->lb = lb; bb->n_keys = (uint32_t)n_ub; bb->armed = armed; bb->nchunks = nchunks;

@@ -25,16 +25,16 @@ namespace shq {
 struct RollTables {            // in shared memory
   uint4 fast[16];              // [out << 2 | in] over 2-bit codes (c >> 1) & 3: {f.lo, f.hi, r.lo, r.hi}
   uint64_t in_f[256];          // byte-indexed: seed(c)
-  uint64_t out_f[256];         // rol(seed(c), K)
   uint64_t in_r[256];          // rol(seed'(c & 7), K-1)
-  uint64_t out_r[256];         // rol(seed'(c & 7), 63)
+  // the outgoing terms rol(seed(c), K) and rol(seed'(c & 7), 63) of the byte-exact step are computed on the fly: that
+  // step is rare, and 4 KiB less per CTA lets two scatter CTAs share an SM
   uint8_t bad[256];            // 1 unless c is one of ACGTacgt
 };
 __device__ __forceinline__ void roll_tables_init(RollTables* t, int K) {
   for (int c = threadIdx.x; c < 256; c += blockDim.x) {
     uint64_t f = nt_seed_fwd((unsigned char)c), r = nt_seed_rev((unsigned char)c);
-    t->in_f[c] = f; t->out_f[c] = rotl64(f, K);
-    t->in_r[c] = rotl64(r, K - 1); t->out_r[c] = rotl64(r, 63);
+    t->in_f[c] = f;
+    t->in_r[c] = rotl64(r, K - 1);
     unsigned char u = (unsigned char)(c & 0xDF);
     t->bad[c] = (u == 'A' || u == 'C' || u == 'G' || u == 'T') ? 0 : 1;
   }
@@ -120,8 +120,8 @@ struct Roller {
     return true;
   }
   __device__ __forceinline__ void roll(unsigned char cout, unsigned char cin) {   // base/nthash.hpp:305-309
-    fh = rol1(fh) ^ tab->out_f[cout] ^ tab->in_f[cin];
-    rh = ror1(rh) ^ tab->out_r[cout] ^ tab->in_r[cin];
+    fh = rol1(fh) ^ rotl64(nt_seed_fwd(cout), hp->K) ^ tab->in_f[cin];
+    rh = ror1(rh) ^ rotl64(nt_seed_rev(cout), 63) ^ tab->in_r[cin];
   }
   __device__ __forceinline__ uint64_t guarded(const uint64_t* p) const { return p <= last_word ? __ldg(p) : 0; }
   __device__ __forceinline__ void open_streams(const unsigned char* base) {
@@ -332,21 +332,30 @@ __global__ void __launch_bounds__(THREADS) roll_scatter_kernel(HashParams hp, ui
     while (more && produced + 8 <= W) more = R.step(mask, emit, emit8);
     int any = __syncthreads_or(produced > 0);
     if (!any) break;
-    {   // B: exclusive scan over the bins + global reservation; the histogram is cleared for the next round
-      uint32_t sum = 0;
-      int b0 = threadIdx.x * per;
-      for (int j = 0; j < per; j++) { int b = b0 + j; if (b < hp.n_bins) sum += s_hist[b]; }
+    {   // B: global reservations first (their round trip runs under the block scan), then the exclusive scan over the
+        // bins; the histogram is cleared for the next round.  PER bins per thread (n_bins <= PER * THREADS).
+      constexpr int PER = W == 16 ? 6 : 11;     // 4096 bins with 16-key rounds, 8192 with 8-key rounds
+      uint32_t cnt[PER], base[PER], sum = 0;
+      const int b0 = threadIdx.x * per;
+#pragma unroll
+      for (int j = 0; j < PER; j++) {
+        const int b = b0 + j;
+        cnt[j] = (j < per && b < hp.n_bins) ? s_hist[b] : 0;
+        base[j] = cnt[j] ? atomicAdd(&g_cursor[b], cnt[j]) : 0;
+        sum += cnt[j];
+      }
       uint32_t tot;
       uint32_t ex = block_exclusive_scan<SumU32>(sum, &tot);
-      for (int j = 0; j < per; j++) {
-        int b = b0 + j;
-        if (b < hp.n_bins) {
-          uint32_t c = s_hist[b];
+#pragma unroll
+      for (int j = 0; j < PER; j++) {
+        const int b = b0 + j;
+        if (j < per && b < hp.n_bins) {
+          const uint32_t c = cnt[j];
+          uint32_t bs = base[j];
+          if (capbin && c && (uint64_t)bs + c > (uint64_t)(b + 1) * capbin) { *ovf = 1; bs = slack_base + ex; }
           s_hist[b] = 0;
           s_off[b] = ex;
-          uint32_t base = c ? atomicAdd(&g_cursor[b], c) : 0;
-          if (capbin && c && (uint64_t)base + c > (uint64_t)(b + 1) * capbin) { *ovf = 1; base = slack_base + ex; }
-          s_delta[b] = base - ex;
+          s_delta[b] = bs - ex;
           ex += c;
         }
       }

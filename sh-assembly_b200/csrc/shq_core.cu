@@ -43,6 +43,10 @@ struct shq_handle_s {
   uint8_t header[128];           // metadata of a loaded image
   bool has_header = false;
 
+  // distinct keys per occurrence seen by the last full aggregation of a batch: sizes the bins (the aggregator's
+  // shared-memory table holds kAggMaxDistinct keys); 1/8 until the first batch has been seen
+  double distinct_ratio = 0.125;
+
   // deNoise schedule
   uint64_t trigger = 0; uint32_t rounds_left = 0; bool end_denoise = false; uint32_t rounds_done = 0;
   bool finished = false;
@@ -186,12 +190,12 @@ struct Run { DevBuf* keys; DevBuf* counts; DevBuf* chunk; size_t n = 0; uint64_t
 int g_bin_bits = 0;             // 0 = automatic (tunable: SHQ_BIN_BITS)
 
 int pick_bin_bits(shq_handle_s* h, uint64_t est_keys, int chunk_bits_needed) {
-  // aim at ~64K occurrences per bin (8 per bin and scatter round), 2^8 .. 2^13 bins,
-  // and (key bits below the bin) + chunk bits <= 32
+  // aim at ~64K occurrences per bin (8 per bin and scatter round) AND at most ~7000 distinct keys per bin (one round
+  // of the aggregator's table), 2^8 .. 2^12 bins, and (key bits below the bin) + chunk bits <= 32
   int shard_bits = 0; while ((1 << shard_bits) < h->nshards) shard_bits++;
   int local_bits = h->hb - shard_bits;
   int pb = 8;
-  while (pb < 12 && (est_keys >> pb) > 65536) pb++;
+  while (pb < 12 && ((est_keys >> pb) > 65536 || (double)(est_keys >> pb) * h->distinct_ratio * 1.2 > 7000.0)) pb++;
   if (g_bin_bits) pb = g_bin_bits;
   if (pb > local_bits) pb = local_bits;
   // the low key bits share a 32-bit word with the chunk id, and 0xFFFFFFFF is the aggregator's empty marker
@@ -359,7 +363,10 @@ bool aggregate_bins(shq_handle_s* h, const BatchBins& bb, uint32_t clo, uint32_t
   Phase ph(h, &h->stats.ms_aggregate);
   size_t cap = (size_t)(bb.spec ? bb.span : bb.n_keys) + 4;
   int fixed_bits = 0;               // CTAs per bin: keep each CTA's share of the bin's distinct keys inside its table
-  { uint64_t avg = bb.n_keys / (uint64_t)bb.n_bins; while (fixed_bits < 4 && fixed_bits < bb.lb && (avg >> fixed_bits) > 56000) fixed_bits++; }
+  { // a CTA's table holds kAggMaxDistinct keys: split a bin over 2^fixed_bits CTAs (key sub-ranges) when the expected
+    // number of distinct keys -- occurrences x the ratio seen in the previous batch -- would not fit
+    const double per_bin = (double)bb.n_keys / (double)bb.n_bins * h->distinct_ratio * 1.2;
+    while (fixed_bits < 4 && fixed_bits < bb.lb && per_bin / (double)(1 << fixed_bits) > 0.9 * kAggMaxDistinct) fixed_bits++; }
   const size_t S = (size_t)1 << fixed_bits;
   h->d_tmp_keys.reserve(cap * 8 * S); h->d_tmp_counts.reserve(cap * 4 * S);
   if (bb.armed) h->d_tmp_chunk.reserve(cap * 2 * S);
@@ -415,6 +422,8 @@ bool aggregate_bins(shq_handle_s* h, const BatchBins& bb, uint32_t clo, uint32_t
   };
   finish(A, n_out, doff, occ, o.keys, o.counts, o.chunk);
   if (split) finish(B, n_out2, doff2, occ2, o.keys2, o.counts2, nullptr);
+  if (!split && clo == 0 && (chi == 0xFFFFFFFFu || chi + 1 >= (uint32_t)bb.nchunks) && A->occ > (uint64_t)bb.n_bins * 64)
+    h->distinct_ratio = (double)A->n / (double)A->occ;       // whole batch seen: the next one is sized by it
   if (first_hist) {
     uint32_t* p = (uint32_t*)pinned(h, (size_t)bb.nchunks * 4);
     SHQ_CUDA(cudaMemcpyAsync(p, d_fh, (size_t)bb.nchunks * 4, cudaMemcpyDeviceToHost, st));

@@ -12,6 +12,7 @@
 //   U6  links between unitig ends, connected components (union-find) and the seed rule
 //       (a component is reported iff it holds a read-middle k-mer with x <= count <= X).
 #pragma once
+#include <functional>
 #include "shq_common.cuh"
 #include "shq_layout.cuh"
 #include <chrono>
@@ -625,6 +626,8 @@ struct shq_unitigs_s {
   uint32_t victim_cap = 0;
   std::vector<char> seeds;        // host scratch (irregular chunks only)
   shq::DevBuf d_seed_slots; size_t n_seed_slots = 0;   // device: K bytes per seed candidate, in read order
+  shq::DevBuf d_stage; size_t st_fill = 0; std::vector<size_t> st_ends;   // read chunks staged on the device
+  size_t st_cap_target = (size_t)128 << 20;
   bool built = false;
   // results (host)
   std::vector<std::string> seqs; std::vector<int> km; std::vector<std::vector<int>> after, before;
@@ -904,54 +907,85 @@ void unitigs_build_impl(shq_unitigs_s* u) {
     return r;
   };
   struct Rec { std::string seq; int km; bool flipped; uint32_t old; };
+  // every unitig is independent here: a few host threads share the work (index ranges, no locks)
+  auto parallel_for = [](size_t n, const std::function<void(size_t, size_t)>& fn) {
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t T = std::min<size_t>(hw ? hw : 1, 8);
+    if (n < 4096 || T <= 1) { fn(0, n); return; }
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < T; t++) th.emplace_back(fn, n * t / T, n * (t + 1) / T);
+    for (auto& x : th) x.join();
+  };
+  std::vector<uint64_t> soff(nu + 1, 0), koff(nu + 1, 0);
+  for (uint32_t i = 0; i < nu; i++) { soff[i + 1] = soff[i] + seqlen[i]; koff[i + 1] = koff[i] + klen[i]; }
+  std::vector<Rec> by_old(nu);
+  parallel_for(nu, [&](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; i++) {
+      if (!keep[i]) continue;
+      std::string s(seq.data() + soff[i], seqlen[i]);
+      std::string r = rc_str(s);
+      bool flip = r < s;
+      uint32_t* c0 = kc.data() + koff[i]; size_t cn = klen[i];       // median in place (counts are not needed afterwards)
+      size_t m = cn / 2;
+      std::nth_element(c0, c0 + m, c0 + cn);
+      double med = c0[m];
+      if (cn % 2 == 0) { uint32_t lo2 = *std::max_element(c0, c0 + m); med = (lo2 + c0[m]) / 2.0; }
+      by_old[i] = Rec{flip ? std::move(r) : std::move(s), (int)med, flip, (uint32_t)i};
+    }
+  });
   std::vector<Rec> recs;
   std::vector<int> newid(nu, -1);
-  {
-    uint64_t so = 0, ko = 0;
-    for (uint32_t i = 0; i < nu; i++) {
-      if (keep[i]) {
-        std::string s(seq.data() + so, seqlen[i]);
-        std::string r = rc_str(s);
-        bool flip = r < s;
-        uint32_t* c0 = kc.data() + ko; size_t cn = klen[i];       // median in place (counts are not needed afterwards)
-        size_t m = cn / 2;
-        std::nth_element(c0, c0 + m, c0 + cn);
-        double med = c0[m];
-        if (cn % 2 == 0) { uint32_t lo = *std::max_element(c0, c0 + m); med = (lo + c0[m]) / 2.0; }
-        recs.push_back(Rec{flip ? r : s, (int)med, flip, i});
-      }
-      so += seqlen[i]; ko += klen[i];
-    }
-  }
+  for (uint32_t i = 0; i < nu; i++) if (keep[i]) recs.push_back(std::move(by_old[i]));
   std::vector<uint32_t> order(recs.size());
   for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
-  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return recs[a].seq < recs[b].seq; });
+  // the first 8 bases as a big-endian word decide almost every comparison
+  std::vector<uint64_t> prefix(recs.size());
+  for (size_t i = 0; i < recs.size(); i++) {
+    uint64_t v = 0; const std::string& q = recs[i].seq;
+    for (size_t j = 0; j < 8; j++) v = (v << 8) | (j < q.size() ? (unsigned char)q[j] : 0);
+    prefix[i] = v;
+  }
+  std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+    if (prefix[x] != prefix[y]) return prefix[x] < prefix[y];
+    return recs[x].seq < recs[y].seq;
+  });
   std::vector<bool> flipped_old(nu, false);
   for (uint32_t r = 0; r < order.size(); r++) { newid[recs[order[r]].old] = (int)r; flipped_old[recs[order[r]].old] = recs[order[r]].flipped; }
-  u->seqs.clear(); u->km.clear(); u->after.clear(); u->before.clear(); u->fasta.clear();
-  for (uint32_t r = 0; r < order.size(); r++) {
-    const Rec& R = recs[order[r]];
-    std::vector<int> aft, bef;
-    for (int side = 0; side < 2; side++) {
-      for (int j = 0; j < 4; j++) {
-        int ref = links[(size_t)R.old * 8 + side * 4 + j];
-        if (!ref) continue;
-        uint32_t o = (uint32_t)(abs(ref) - 1);
-        if (newid[o] < 0) continue;
-        bool plus = ref > 0;
-        if (flipped_old[o]) plus = !plus;
-        int v = plus ? newid[o] + 1 : -(newid[o] + 1);
-        // a flipped unitig swaps its own sides
-        if ((side == 0) != R.flipped) aft.push_back(v); else bef.push_back(v);
+  const size_t nrec = order.size();
+  u->seqs.assign(nrec, std::string()); u->km.assign(nrec, 0); u->after.assign(nrec, {}); u->before.assign(nrec, {}); u->fasta.clear();
+  std::vector<std::string> lines(nrec);
+  parallel_for(nrec, [&](size_t lo, size_t hi) {
+    for (size_t r = lo; r < hi; r++) {
+      Rec& R = recs[order[r]];
+      std::vector<int> aft, bef;
+      for (int side = 0; side < 2; side++) {
+        for (int j = 0; j < 4; j++) {
+          int ref = links[(size_t)R.old * 8 + side * 4 + j];
+          if (!ref) continue;
+          uint32_t o = (uint32_t)(abs(ref) - 1);
+          if (newid[o] < 0) continue;
+          bool plus = ref > 0;
+          if (flipped_old[o]) plus = !plus;
+          int v = plus ? newid[o] + 1 : -(newid[o] + 1);
+          // a flipped unitig swaps its own sides
+          if ((side == 0) != R.flipped) aft.push_back(v); else bef.push_back(v);
+        }
       }
+      std::string& f = lines[r];
+      f.reserve(R.seq.size() + 96);
+      f += ">" + std::to_string(r) + " LN:i:" + std::to_string(R.seq.size()) + " KC:i:" +
+           std::to_string((long long)R.km * (long long)(R.seq.size() - K + 1)) + " km:f:" + std::to_string(R.km);
+      for (int t : aft) f += t > 0 ? " L:+:" + std::to_string(t - 1) + ":+" : " L:+:" + std::to_string(-t - 1) + ":-";
+      for (int t : bef) f += t > 0 ? " L:-:" + std::to_string(t - 1) + ":+" : " L:-:" + std::to_string(-t - 1) + ":-";
+      f += "\n"; f += R.seq; f += "\n";
+      u->km[r] = R.km; u->after[r] = std::move(aft); u->before[r] = std::move(bef); u->seqs[r] = std::move(R.seq);
     }
-    u->seqs.push_back(R.seq); u->km.push_back(R.km); u->after.push_back(aft); u->before.push_back(bef);
-    std::string& f = u->fasta;
-    f += ">" + std::to_string(r) + " LN:i:" + std::to_string(R.seq.size()) + " KC:i:" +
-         std::to_string((long long)R.km * (long long)(R.seq.size() - K + 1)) + " km:f:" + std::to_string(R.km);
-    for (int t : aft) f += t > 0 ? " L:+:" + std::to_string(t - 1) + ":+" : " L:+:" + std::to_string(-t - 1) + ":-";
-    for (int t : bef) f += t > 0 ? " L:-:" + std::to_string(t - 1) + ":+" : " L:-:" + std::to_string(-t - 1) + ":-";
-    f += "\n" + R.seq + "\n";
+  });
+  {
+    size_t tot = 0;
+    for (auto& l : lines) tot += l.size();
+    u->fasta.reserve(tot);
+    for (auto& l : lines) u->fasta += l;
   }
   tm.lap("host canonicalise+FASTA");
   u->built = true;
@@ -1001,6 +1035,89 @@ int shq_unitigs_begin(shq_t h, const shq_unitig_opts* opts, shq_unitigs_t* out) 
   return SHQ_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// Seeds + node enumeration for read text resident in device memory (16-byte aligned, whole records).
+// host_text: the same bytes on the host, needed only when the text is irregular (a quality line that parses as a
+// header derails the reference's cursor, contig_assembly.cpp:1868-1871).  Returns false, with nothing committed, if
+// the text is irregular and host_text is null.
+bool unitigs_process_text(shq_unitigs_s* u, const char* d_text, size_t n, const char* host_text) {
+  shq_handle_s* h = u->h;
+  cudaStream_t st = h->stream;
+  uint64_t& L = h->stats.kernels_launched;
+  uint32_t n_lines = index_lines(h, d_text, n);
+  if (n_lines & 3) SHQ_FAIL(SHQ_ERR_MALFORMED, "read text holds %u lines, not a multiple of 4", n_lines);
+  const uint32_t n_reads = n_lines / 4;
+  const int K = u->opts.K;
+  {   // seed candidates: device kernel for regular text, the literal host cursor otherwise
+    size_t need = (u->n_seed_slots + n_reads + 1) * (size_t)K;
+    if (need > u->d_seed_slots.cap) {
+      shq::DevBuf nb; nb.reserve(std::max(need * 2, (size_t)1 << 24));
+      if (u->n_seed_slots) SHQ_CUDA(cudaMemcpyAsync(nb.p, u->d_seed_slots.p, u->n_seed_slots * (size_t)K, cudaMemcpyDeviceToDevice, st));
+      SHQ_CUDA(cudaStreamSynchronize(st));
+      u->d_seed_slots.release(); u->d_seed_slots = nb;
+    }
+    u->misc.reserve(256);
+    int* d_irr = u->misc.as<int>() + 8;
+    SHQ_CUDA(cudaMemsetAsync(d_irr, 0, 4, st));
+    if (n_reads) {
+      seed_extract_kernel<<<cdiv(n_reads, 128), 128, 0, st>>>(d_text, h->d_nl_pos.as<uint32_t>(), n_reads, K,
+                                                            u->d_seed_slots.as<char>() + u->n_seed_slots * (size_t)K, d_irr); L++;
+    }
+    if (read_scalar(h, d_irr)) {
+      if (!host_text) return false;
+      u->seeds.clear();
+      collect_seeds(u, host_text, n);
+      size_t m = u->seeds.size() / K;
+      if (m > n_reads) SHQ_FAIL(SHQ_ERR_MALFORMED, "irregular chunk yields more seeds than records");
+      if (m) SHQ_CUDA(cudaMemcpyAsync(u->d_seed_slots.as<char>() + u->n_seed_slots * (size_t)K, u->seeds.data(), m * (size_t)K, cudaMemcpyHostToDevice, st));
+      SHQ_CUDA(cudaStreamSynchronize(st));
+      u->n_seed_slots += m;
+    } else {
+      u->n_seed_slots += n_reads;
+    }
+  }
+  EnumParams ep{d_text, h->d_nl_pos.as<uint32_t>(), n_reads, u->opts.K, h->hb, (uint32_t)u->opts.abundance_min};
+  ImageView im{h->image.as<uint8_t>(), h->nblocks, h->xnslots, 0};
+  size_t smem = (size_t)kEnumWarps * ((kTilePos + 1) * 16 + 264 + 520);
+  SHQ_CUDA(cudaFuncSetAttribute(enum_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VictimList V{u->v_node.as<uint32_t>(), u->v_slot.as<uint64_t>(), u->v_n.as<uint32_t>(), u->victim_cap};
+  enum_nodes_kernel<<<4 * kNumSMs, kEnumWarps * 32, smem, st>>>(ep, im, u->aux.as<uint64_t>(), u->aux2.as<uint32_t>(), V, node_table(u)); L++;
+  SHQ_CUDA(cudaGetLastError());
+  SHQ_CUDA(cudaStreamSynchronize(st));
+  check_err_flag(h);
+  return true;
+}
+
+// Everything staged so far (several reference chunks, concatenated) in one go; an irregular batch is replayed chunk
+// by chunk with the host cursor, because the reference's cursor starts afresh in every chunk.
+void unitigs_flush_stage(shq_unitigs_s* u) {
+  if (u->st_fill == 0) return;
+  shq_handle_s* h = u->h;
+  cudaStream_t st = h->stream;
+  DbgTimer tm(st);
+  const size_t n = u->st_fill;
+  std::vector<size_t> ends; ends.swap(u->st_ends);
+  u->st_fill = 0;
+  if (!unitigs_process_text(u, u->d_stage.as<char>(), n, nullptr)) {
+    std::vector<char> host(n);
+    SHQ_CUDA(cudaMemcpyAsync(host.data(), u->d_stage.p, n, cudaMemcpyDeviceToHost, st));
+    SHQ_CUDA(cudaStreamSynchronize(st));
+    size_t b = 0;
+    for (size_t e : ends) {
+      u->d_text.reserve(e - b + 64);
+      SHQ_CUDA(cudaMemcpyAsync(u->d_text.p, u->d_stage.as<char>() + b, e - b, cudaMemcpyDeviceToDevice, st));
+      unitigs_process_text(u, u->d_text.as<char>(), e - b, host.data() + b);
+      b = e;
+    }
+  }
+  tm.lap("add_reads: index+seeds+enum of a staged batch");
+}
+}  // namespace
+
+extern "C" {
+
 int shq_unitigs_add_reads(shq_unitigs_t u, const char* text, size_t n) {
   if (!u || (!text && n)) return SHQ_ERR_ARG;
   if (n == 0) return SHQ_OK;
@@ -1009,61 +1126,28 @@ int shq_unitigs_add_reads(shq_unitigs_t u, const char* text, size_t n) {
     auto& a = *(decltype(args)*)ap;
     shq_unitigs_s* u = a.u;
     cudaStream_t st = h->stream;
-    uint64_t& L = h->stats.kernels_launched;
-    if (a.n >= ((size_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "chunk too large");
-    DbgTimer tm(st);
-    u->d_text.reserve(a.n + 64);
-    SHQ_CUDA(cudaMemcpyAsync(u->d_text.p, a.t, a.n, cudaMemcpyHostToDevice, st));
-    h->stats.h2d_bytes += a.n;
+    if (a.n >= ((size_t)1 << 31)) SHQ_FAIL(SHQ_ERR_ARG, "chunk too large");
     if (a.t[a.n - 1] != '\n') SHQ_FAIL(SHQ_ERR_MALFORMED, "chunk has no trailing newline");
-    uint32_t n_lines = index_lines(h, u->d_text.as<char>(), a.n);
-    if (n_lines & 3) SHQ_FAIL(SHQ_ERR_MALFORMED, "chunk holds %u lines, not a multiple of 4", n_lines);
-    const uint32_t n_reads = n_lines / 4;
-    const int K = u->opts.K;
-    {   // seed candidates: device kernel for regular chunks, the literal host cursor otherwise
-      size_t need = (u->n_seed_slots + n_reads + 1) * (size_t)K;
-      if (need > u->d_seed_slots.cap) {
-        shq::DevBuf nb; nb.reserve(std::max(need * 2, (size_t)1 << 24));
-        if (u->n_seed_slots) SHQ_CUDA(cudaMemcpyAsync(nb.p, u->d_seed_slots.p, u->n_seed_slots * (size_t)K, cudaMemcpyDeviceToDevice, st));
-        SHQ_CUDA(cudaStreamSynchronize(st));
-        u->d_seed_slots.release(); u->d_seed_slots = nb;
-      }
-      u->misc.reserve(256);
-      int* d_irr = u->misc.as<int>() + 8;
-      SHQ_CUDA(cudaMemsetAsync(d_irr, 0, 4, st));
-      if (n_reads) {
-        seed_extract_kernel<<<cdiv(n_reads, 128), 128, 0, st>>>(u->d_text.as<char>(), h->d_nl_pos.as<uint32_t>(), n_reads, K,
-                                                              u->d_seed_slots.as<char>() + u->n_seed_slots * (size_t)K, d_irr); L++;
-      }
-      if (read_scalar(h, d_irr)) {
-        u->seeds.clear();
-        collect_seeds(u, a.t, a.n);
-        size_t m = u->seeds.size() / K;
-        if (m > n_reads) SHQ_FAIL(SHQ_ERR_MALFORMED, "irregular chunk yields more seeds than records");
-        if (m) SHQ_CUDA(cudaMemcpyAsync(u->d_seed_slots.as<char>() + u->n_seed_slots * (size_t)K, u->seeds.data(), m * (size_t)K, cudaMemcpyHostToDevice, st));
-        SHQ_CUDA(cudaStreamSynchronize(st));
-        u->n_seed_slots += m;
-      } else {
-        u->n_seed_slots += n_reads;
-      }
-    }
-    EnumParams ep{u->d_text.as<char>(), h->d_nl_pos.as<uint32_t>(), n_reads, u->opts.K, h->hb, (uint32_t)u->opts.abundance_min};
-    ImageView im{h->image.as<uint8_t>(), h->nblocks, h->xnslots, 0};
-    size_t smem = (size_t)kEnumWarps * ((kTilePos + 1) * 16 + 264 + 520);
-    SHQ_CUDA(cudaFuncSetAttribute(enum_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VictimList V{u->v_node.as<uint32_t>(), u->v_slot.as<uint64_t>(), u->v_n.as<uint32_t>(), u->victim_cap};
-    enum_nodes_kernel<<<4 * kNumSMs, kEnumWarps * 32, smem, st>>>(ep, im, u->aux.as<uint64_t>(), u->aux2.as<uint32_t>(), V, node_table(u)); L++;
-    SHQ_CUDA(cudaGetLastError());
+    const size_t cap = std::max(u->st_cap_target, a.n);
+    if (u->st_fill && u->st_fill + a.n > cap) unitigs_flush_stage(u);
+    u->d_stage.reserve(cap + 64);
+    // chunks are whole records, so their concatenation is valid FASTQ text; the copy is complete when the call
+    // returns (the caller may reuse its buffer)
+    SHQ_CUDA(cudaMemcpyAsync(u->d_stage.as<char>() + u->st_fill, a.t, a.n, cudaMemcpyHostToDevice, st));
     SHQ_CUDA(cudaStreamSynchronize(st));
-    tm.lap("add_reads: H2D+index+enum");
-    check_err_flag(h);
+    h->stats.h2d_bytes += a.n;
+    u->st_fill += a.n; u->st_ends.push_back(u->st_fill);
   }, &args);
 }
 
 int shq_unitigs_build(shq_unitigs_t u) {
   if (!u) return SHQ_ERR_ARG;
   struct { shq_unitigs_s* u; } args{u};
-  return guard(u->h, [](shq_handle_s*, void* ap) { unitigs_build_impl(((decltype(args)*)ap)->u); }, &args);
+  return guard(u->h, [](shq_handle_s*, void* ap) {
+    shq_unitigs_s* u = ((decltype(args)*)ap)->u;
+    unitigs_flush_stage(u);
+    unitigs_build_impl(u);
+  }, &args);
 }
 int shq_unitigs_count(shq_unitigs_t u, size_t* n_unitigs, size_t* total_bases) {
   if (!u || !u->built) return SHQ_ERR_STATE;
@@ -1092,7 +1176,7 @@ void shq_unitigs_free(shq_unitigs_t u) {
   cudaSetDevice(u->h->device);
   shq::DevBuf* bufs[] = {&u->lo, &u->hi, &u->state, &u->count, &u->fh, &u->rh, &u->list, &u->nn, &u->aux, &u->outdeg, &u->succ, &u->smask, &u->next,
                          &u->prev, &u->jd, &u->minid, &u->jmp, &u->tail_of, &u->len_of, &u->uid_of_head, &u->unitig_of_oid, &u->u_head, &u->u_seqlen,
-                         &u->u_klen, &u->seq, &u->kcounts, &u->links, &u->parent, &u->reached, &u->keep, &u->d_seeds, &u->d_text, &u->misc, &u->aux2, &u->v_node, &u->v_slot, &u->v_n, &u->v_out, &u->seed_node, &u->seed_root, &u->roots, &u->d_seed_slots};
+                         &u->u_klen, &u->seq, &u->kcounts, &u->links, &u->parent, &u->reached, &u->keep, &u->d_seeds, &u->d_text, &u->misc, &u->aux2, &u->v_node, &u->v_slot, &u->v_n, &u->v_out, &u->seed_node, &u->seed_root, &u->roots, &u->d_seed_slots, &u->d_stage};
   for (auto* b : bufs) b->release();
   delete u;
 }

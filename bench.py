@@ -242,10 +242,13 @@ def run_ours(args, rank, world, local_rank):
     def step_e2e():
         q.reset()
         q.set_denoise_schedule(int(p.trigger), int(p.num_deNoise), args.end_denoise)
-        o = 0
-        for e in ends:
-            q.insert_fastq_pinned_raw(h_ptr + o, int(e) - o, args.k)
-            o = int(e)
+        if args.e2e_per_chunk_calls:
+            o = 0
+            for e in ends:
+                q.insert_fastq_pinned_raw(h_ptr + o, int(e) - o, args.k)
+                o = int(e)
+        else:       # one C call for all reference chunks of the pinned buffer (no interpreter time between chunks)
+            q.insert_fastq_pinned_chunks(h_ptr, len(text), ends, args.k)
         q.finish()
         w = C.c_size_t()
         q._check(q.L.shq_export_cqf(q.h, img.ctypes.data, img.nbytes, C.byref(w)))
@@ -420,6 +423,7 @@ def main():
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--unitigs", type=int, default=1, help="also time the Contiger device path (unitig build seconds)")
+    ap.add_argument("--e2e-per-chunk-calls", type=int, default=0, help="e2e leg: one Python->C call per reference chunk instead of one for all")
     ap.add_argument("--unitig-cpu", type=int, default=0, help="also time the sequential CPU restatement of Contiger")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -73,6 +73,9 @@ int shq_insert_fastq_chunk(shq_t h, const char* text, size_t n, int K);
  * with an asynchronous DMA on a separate copy stream, double-buffered against the compute of the previous
  * batch.  The buffer must stay valid and unchanged until shq_sync / shq_finish / shq_counts returns.          */
 int shq_insert_fastq_pinned(shq_t h, const char* pinned_text, size_t n, int K);
+/* the same for nchunks consecutive chunks of one pinned buffer (chunk c = [chunk_ends[c-1], chunk_ends[c])) */
+int shq_insert_fastq_pinned_chunks(shq_t h, const char* pinned_text, size_t n, const uint64_t* chunk_ends, size_t nchunks,
+                                   int K);
 
 /* Same for text already resident in device memory (benchmark / pipeline use):
  * d_text holds nchunks consecutive chunks, chunk c = [chunk_ends[c-1], chunk_ends[c])

@@ -60,7 +60,7 @@ _lib = None
 # every symbol include/shq.h declares
 EXPORTS = [
     "shq_strerror", "shq_last_error", "shq_create", "shq_create_shard", "shq_destroy", "shq_reset", "shq_set_denoise_schedule",
-    "shq_insert_fastq_chunk", "shq_insert_fastq_pinned", "shq_insert_fastq_device", "shq_insert_keys", "shq_insert_keys_device", "shq_finish",
+    "shq_insert_fastq_chunk", "shq_insert_fastq_pinned", "shq_insert_fastq_pinned_chunks", "shq_insert_fastq_device", "shq_insert_keys", "shq_insert_keys_device", "shq_finish",
     "shq_sync", "shq_counts", "shq_rounds_done", "shq_denoise", "shq_image_size", "shq_export_cqf", "shq_save",
     "shq_load", "shq_load_image", "shq_geometry", "shq_iterate", "shq_query_set_traveled", "shq_query",
     "shq_hash_fastq_chunk", "shq_unitigs_begin", "shq_unitigs_add_reads", "shq_unitigs_build", "shq_unitigs_count",
@@ -94,6 +94,7 @@ def lib():
         L.shq_insert_fastq_chunk.argtypes = [vp, vp, sz, C.c_int]
         L.shq_insert_fastq_pinned.argtypes = [vp, vp, sz, C.c_int]
         L.shq_insert_fastq_device.argtypes = [vp, vp, sz, vp, sz, C.c_int]
+        L.shq_insert_fastq_pinned_chunks.argtypes = [vp, vp, sz, vp, sz, C.c_int]
         L.shq_insert_keys.argtypes = [vp, vp, sz]
         L.shq_insert_keys_device.argtypes = [vp, vp, sz]
         L.shq_finish.argtypes = [vp]
@@ -309,6 +310,10 @@ class CQF:
 
     def insert_fastq_pinned_raw(self, addr, n, K):
         self._check(self.L.shq_insert_fastq_pinned(self.h, addr, n, K))
+
+    def insert_fastq_pinned_chunks(self, addr, n, chunk_ends, K):
+        ce = np.ascontiguousarray(chunk_ends, np.uint64)
+        self._check(self.L.shq_insert_fastq_pinned_chunks(self.h, addr, n, ce.ctypes.data, len(ce), K))
 
     def insert_fastq_chunk_raw(self, addr, n, K):
         self._check(self.L.shq_insert_fastq_chunk(self.h, addr, n, K))

@@ -905,6 +905,18 @@ int shq_insert_fastq_pinned(shq_t h, const char* text, size_t n, int K) {
   SHQ_API_END
 }
 
+int shq_insert_fastq_pinned_chunks(shq_t h, const char* pinned_text, size_t n, const uint64_t* chunk_ends, size_t nchunks, int K) {
+  if (!h || (!pinned_text && n) || (!chunk_ends && nchunks)) return SHQ_ERR_ARG;
+  if (nchunks && chunk_ends[nchunks - 1] != n) return SHQ_ERR_ARG;
+  uint64_t b = 0;
+  for (size_t c = 0; c < nchunks; c++) {
+    int rc = shq_insert_fastq_pinned(h, pinned_text + b, (size_t)(chunk_ends[c] - b), K);
+    if (rc) return rc;
+    b = chunk_ends[c];
+  }
+  return SHQ_OK;
+}
+
 int shq_insert_fastq_device(shq_t h, const char* d_text, size_t n, const uint64_t* chunk_ends, size_t nchunks, int K) {
   if (!h || (!d_text && n) || (!chunk_ends && nchunks)) return SHQ_ERR_ARG;
   struct { const char* t; size_t n; const uint64_t* ce; size_t nc; int K; } args{d_text, n, chunk_ends, nchunks, K};

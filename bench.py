@@ -366,6 +366,7 @@ PHASE_KERNEL = {"ms_hash_count": "roll_count_kernel", "ms_scatter": "roll_scatte
 # launches of the phase's dominant kernel per step on the default workload (4 device batches; the aggregator runs once
 # more for the split at the mid-stream deNoise boundary)
 PHASE_LAUNCHES = {"ms_hash_count": 4, "ms_scatter": 4, "ms_aggregate": 5, "ms_merge": 10, "ms_layout": 1, "ms_denoise": 2}
+# (ms_hash_count is 0 on the default path: bins have a fixed capacity and the counting pass only runs as the exact fallback)
 
 
 def measured_traffic(kernel):

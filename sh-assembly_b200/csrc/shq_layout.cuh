@@ -12,34 +12,10 @@ namespace shq {
 constexpr int kBlockBytes = 89;
 
 // ------------------------------------------------------------ positions -----
-// Step 1: per entry the map f_k(e) = max(e + len, first ? q + len : -inf)  (MaxPlus).
-__global__ void layout_pairs_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, size_t n,
-                                    uint64_t key_lo_q /* quotient offset of the shard */, MaxPlus* __restrict__ pairs) {
-  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  uint64_t key = keys[k];
-  long long q = (long long)((key >> 8) - key_lo_q);
-  bool first = (k == 0) || ((keys[k - 1] >> 8) != (key >> 8));
-  long long len = enc_len((uint32_t)(key & 0xFF), counts[k]);
-  pairs[k] = MaxPlus{len, first ? q + len : kNegInf};
-}
-// Step 2 (after the exclusive MaxPlus scan): pos_k = first slot of entry k (relative to the shard).
-__global__ void layout_pos_kernel(const uint64_t* __restrict__ keys, size_t n, uint64_t key_lo_q,
-                                  const MaxPlus* __restrict__ scanned, uint64_t start_free, uint64_t* __restrict__ pos) {
-  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  uint64_t key = keys[k];
-  long long q = (long long)((key >> 8) - key_lo_q);
-  bool first = (k == 0) || ((keys[k - 1] >> 8) != (key >> 8));
-  MaxPlus f = scanned[k];
-  long long e = (long long)start_free + f.a;
-  if (f.b > e) e = f.b;
-  if (first && q > e) e = q;
-  pos[k] = (uint64_t)e;
-}
-
-// Fused form of the two kernels above around the tile-level scan: the maps are recomputed from (key, count)
-// instead of being stored (32 instead of ~90 bytes of traffic per entry).
+// Per entry the map f_k(e) = max(e + len, first ? q + len : -inf)  (MaxPlus); pos_k = first slot of entry k =
+// (composition of all earlier maps)(0), raised to q_k for the first entry of a quotient.
+// Two kernels around the tile-level scan; the maps are recomputed from (key, count) instead of being stored
+// (32 instead of ~90 bytes of traffic per entry).
 //   layout_reduce_kernel : tile_agg[t] = composition of the maps of tile t
 //   (exclusive MaxPlus scan of tile_agg on the host side)
 //   layout_apply_kernel  : pos[k] for every entry of tile t, seeded with the scanned tile_agg[t]

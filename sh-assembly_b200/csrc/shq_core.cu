@@ -1047,19 +1047,40 @@ int shq_export_cqf(shq_t h, void* dst, size_t cap, size_t* written) {
 
 int shq_save(shq_t h, const char* path) {
   if (!h || !path) return SHQ_ERR_ARG;
-  size_t total = 0;
-  shq_image_size(h, &total);
-  void* buf = malloc(total);
-  if (!buf) return SHQ_ERR_ARG;
-  size_t w = 0;
-  int rc = shq_export_cqf(h, buf, total, &w);
-  if (rc == SHQ_OK) {
-    FILE* f = fopen(path, "wb+");
-    if (!f || fwrite(buf, 1, w, f) != w) { rc = SHQ_ERR_IO; h->last_error = std::string("cannot write ") + path; }
-    if (f) fclose(f);
-  }
-  free(buf);
-  return rc;
+  struct { const char* path; } args{path};
+  SHQ_API_BEGIN(h)
+    flush_stage(h);
+    if (h->nshards != 1) SHQ_FAIL(SHQ_ERR_STATE, "export of a sharded handle goes through the multi-GPU layer");
+    if (!h->image_only) materialise(h);
+    FILE* f = fopen(a.path, "wb+");
+    if (!f) SHQ_FAIL(SHQ_ERR_IO, "cannot write %s", a.path);
+    uint8_t hd[128];
+    build_header(h, hd);
+    bool ok = fwrite(hd, 1, 128, f) == 128;
+    // the image leaves the device through two page-locked buffers: the copy of piece i+1 runs under the write of piece i
+    const size_t total = (size_t)h->nblocks * kBlockBytes, piece = (size_t)32 << 20;
+    uint8_t* pin[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2];
+    for (int i = 0; i < 2; i++) { SHQ_CUDA(cudaMallocHost((void**)&pin[i], piece)); SHQ_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)); }
+    size_t off = 0; int cur = 0;
+    auto issue = [&](int b, size_t o) {
+      size_t m = std::min(piece, total - o);
+      cudaMemcpyAsync(pin[b], h->image.as<uint8_t>() + o, m, cudaMemcpyDeviceToHost, h->stream);
+      cudaEventRecord(ev[b], h->stream);
+    };
+    if (total) issue(0, 0);
+    while (off < total && ok) {
+      size_t m = std::min(piece, total - off);
+      if (off + m < total) issue(cur ^ 1, off + m);
+      ok = cudaEventSynchronize(ev[cur]) == cudaSuccess && fwrite(pin[cur], 1, m, f) == m;
+      off += m; cur ^= 1;
+    }
+    cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < 2; i++) { cudaFreeHost(pin[i]); cudaEventDestroy(ev[i]); }
+    h->stats.d2h_bytes += total;
+    if (fclose(f) != 0) ok = false;
+    if (!ok) SHQ_FAIL(SHQ_ERR_IO, "cannot write %s", a.path);
+  SHQ_API_END
 }
 
 int shq_load_image(const void* image, size_t n, int device, shq_t* out) {

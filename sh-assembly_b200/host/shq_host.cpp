@@ -13,10 +13,13 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <deque>
 #include <fstream>
 #include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/shq.h"
@@ -50,6 +53,16 @@ struct Source {
   const char* mem = nullptr; size_t mem_len = 0, mem_pos = 0; bool mem_eof = false;
   int index = 0;
   std::vector<char> tail;  // part_buffer / part_filled
+
+  // prefetch: one producer thread per file input cuts (and, for gzip / bzip2, decompresses) chunks ahead of the
+  // consumer; the chunk SEQUENCE of an input does not depend on the other inputs, so the round-robin order the
+  // consumer sees is the serial one
+  struct Item { std::vector<char>* buf; size_t size; int rc; };
+  std::thread worker;
+  std::mutex mu; std::condition_variable cv;
+  std::deque<Item> ready; std::vector<std::vector<char>*> free_bufs;
+  std::vector<std::unique_ptr<std::vector<char>>> owned;
+  bool stop = false, started = false;
 
   size_t read(char* dst, size_t n) {
     if (mode == 'm') {
@@ -94,11 +107,13 @@ struct shq_reader_s {
   std::vector<std::unique_ptr<Source>> all;
   int num_files = 0;
   uint64_t part_size = 1ULL << 23;
-  std::vector<char> part;              // current chunk storage
-  std::string error;
+  std::vector<char> part_serial;       // chunk storage of the in-memory inputs (no prefetch)
+  std::vector<char>* held = nullptr; Source* held_src = nullptr;   // prefetched chunk handed out by the last next()
+  std::string error; std::mutex err_mu;
+  static constexpr int kDepth = 3;     // chunks cut ahead per file
 
   // 1 = chunk produced (size in *size), 0 = this input is exhausted, <0 = error
-  int read_parts(Source* s, size_t* size) {
+  int read_parts(Source* s, std::vector<char>& part, size_t* size) {
     const int64_t OVERHEAD_SIZE = 65535;
     part.resize(part_size + OVERHEAD_SIZE);
     size_t part_filled = s->tail.size();
@@ -106,7 +121,7 @@ struct shq_reader_s {
     if (s->eof()) return 0;
     size_t readed = s->read(part.data() + part_filled, part_size);
     int64_t total_filled = (int64_t)(part_filled + readed);
-    if ((int64_t)part_filled >= OVERHEAD_SIZE) { error = "Error: Wrong input file!"; return -1; }
+    if ((int64_t)part_filled >= OVERHEAD_SIZE) { std::lock_guard<std::mutex> g(err_mu); error = "Error: Wrong input file!"; return -1; }
     if (s->eof()) { *size = (size_t)total_filled; s->tail.clear(); return 1; }
     int64_t cut = 0;
     int64_t line_start[9];
@@ -133,6 +148,43 @@ struct shq_reader_s {
     s->tail.assign(part.data() + cut, part.data() + total_filled);
     *size = (size_t)cut;
     return 1;
+  }
+
+  void start_prefetch(Source* s) {
+    for (int i = 0; i < kDepth + 2; i++) { s->owned.emplace_back(new std::vector<char>()); s->free_bufs.push_back(s->owned.back().get()); }
+    s->started = true;
+    s->worker = std::thread([this, s]() {
+      for (;;) {
+        std::vector<char>* buf = nullptr;
+        {
+          std::unique_lock<std::mutex> lk(s->mu);
+          s->cv.wait(lk, [&] { return s->stop || (!s->free_bufs.empty() && (int)s->ready.size() < kDepth); });
+          if (s->stop) return;
+          buf = s->free_bufs.back(); s->free_bufs.pop_back();
+        }
+        size_t size = 0;
+        int rc = read_parts(s, *buf, &size);
+        {
+          std::lock_guard<std::mutex> lk(s->mu);
+          s->ready.push_back(Source::Item{buf, size, rc});
+        }
+        s->cv.notify_all();
+        if (rc != 1) return;             // exhausted or malformed: nothing more to cut
+      }
+    });
+  }
+  void stop_prefetch(Source* s) {
+    if (!s->started) return;
+    { std::lock_guard<std::mutex> lk(s->mu); s->stop = true; }
+    s->cv.notify_all();
+    if (s->worker.joinable()) s->worker.join();
+    s->started = false;
+  }
+  void give_back() {                      // the chunk handed out by the previous next() may be overwritten now
+    if (!held) return;
+    { std::lock_guard<std::mutex> lk(held_src->mu); held_src->free_bufs.push_back(held); }
+    held_src->cv.notify_all();
+    held = nullptr; held_src = nullptr;
   }
 };
 
@@ -161,6 +213,7 @@ int shq_reader_open(const char* const* paths, int nfiles, char fmode, shq_reader
     if (ok) { r->queue.push_back(s.get()); r->all.push_back(std::move(s)); r->num_files++; }
     // files that cannot be opened are silently skipped, exactly like seqFile_batch (CQF_mt.h:350-360)
   }
+  for (auto& s : r->all) r->start_prefetch(s.get());
   *out = r;
   return SHQ_OK;
 }
@@ -182,17 +235,34 @@ int shq_reader_open_memory(const char* const* bufs, const size_t* lens, int nfil
 int shq_reader_next(shq_reader_t r, const char** chunk, size_t* n, int* file_index) {
   if (!r || !chunk || !n) return SHQ_ERR_ARG;
   *chunk = nullptr; *n = 0;
+  r->give_back();
   while (r->num_files) {               // seqFile_batch::getDataChunk, CQF_mt.h:364-390
     Source* s = r->queue.front(); r->queue.pop_front();
     size_t size = 0;
-    int rc = r->read_parts(s, &size);
+    int rc;
+    const char* data = nullptr;
+    if (s->started) {                  // next chunk of this input, cut ahead by its producer thread
+      Source::Item it;
+      {
+        std::unique_lock<std::mutex> lk(s->mu);
+        s->cv.wait(lk, [&] { return !s->ready.empty(); });
+        it = s->ready.front(); s->ready.pop_front();
+      }
+      s->cv.notify_all();
+      rc = it.rc; size = it.size; data = it.buf->data();
+      if (rc == 1) { r->held = it.buf; r->held_src = s; }
+    } else {
+      rc = r->read_parts(s, r->part_serial, &size);
+      data = r->part_serial.data();
+    }
     if (rc < 0) return SHQ_ERR_MALFORMED;
     if (rc == 1) {
       r->queue.push_back(s);
-      *chunk = r->part.data(); *n = size;
+      *chunk = data; *n = size;
       if (file_index) *file_index = s->index;
       return SHQ_OK;
     }
+    r->stop_prefetch(s);
     s->close();
     r->num_files--;
   }
@@ -201,7 +271,7 @@ int shq_reader_next(shq_reader_t r, const char** chunk, size_t* n, int* file_ind
 
 void shq_reader_close(shq_reader_t r) {
   if (!r) return;
-  for (auto& s : r->all) s->close();
+  for (auto& s : r->all) { r->stop_prefetch(s.get()); s->close(); }
   delete r;
 }
 

@@ -31,6 +31,27 @@ def test_reader_files_plain_and_gzip(po, shq, tmp_path):
     assert list(shq.Reader(paths=[str(tmp_path / "missing.fq")], fmode="f")) == []
 
 
+def test_prefetching_file_reader_keeps_the_serial_chunk_order(po, shq, tmp_path):
+    """Three gzip files of different lengths, several 8 MiB parts each: the per-file producer threads must hand out
+    exactly the chunk sequence (file order and bytes) of the sequential chunker."""
+    files = [po.synth_fastq(G=g, cov=40, seed=70 + i) for i, g in enumerate((400000, 150000, 300000))]
+    paths = []
+    for i, f in enumerate(files):
+        paths.append(str(tmp_path / ("r%d.fq.gz" % i)))
+        with gzip.open(paths[-1], "wb", compresslevel=1) as fh:
+            fh.write(f)
+    want = list(po.chunks(files))
+    assert len(want) > 6
+    for _ in range(2):
+        got = list(shq.Reader(paths=paths, fmode="g"))
+        assert [i for i, _ in got] == [i for i, _ in want]
+        assert [c for _, c in got] == [c for _, c in want]
+    # closing a reader whose producers are still ahead must not hang
+    r = shq.Reader(paths=paths, fmode="g")
+    next(r)
+    r.close()
+
+
 def test_reader_bzip2_via_dlopen(po, shq, tmp_path):
     import bz2
     text = po.synth_fastq(G=20000, cov=20, seed=6)

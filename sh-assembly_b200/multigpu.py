@@ -158,10 +158,25 @@ class ShardedCounter:
         self.parity = 0
         self.max_batch_bytes = 256 << 20
         if self.mode == "pull":
-            mine = self.shard.mg_setup(self.max_batch_bytes // 2 + (1 << 20))
+            # every rank must end up in the same mode: if mapping a peer's buffer fails anywhere (no CUDA IPC / no peer
+            # access in this environment), all ranks switch to the all-to-all exchange -- same results, more traffic
+            ok = 1
+            mine = b"\0" * 128
+            try:
+                mine = self.shard.mg_setup(self.max_batch_bytes // 2 + (1 << 20))
+            except self.shq.ShqError:
+                ok = 0
             handles = [None] * world
             dist.all_gather_object(handles, mine)
-            self.shard.mg_open_peers(b"".join(handles), world)
+            if ok:
+                try:
+                    self.shard.mg_open_peers(b"".join(handles), world)
+                except self.shq.ShqError:
+                    ok = 0
+            flag = torch.tensor([ok], dtype=torch.int64, device=torch.device("cuda", device))
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                self.mode = "nccl"
 
     def _buf(self, name, n, dtype):
         t = self._bufs.get(name)

@@ -433,6 +433,92 @@ __global__ void __launch_bounds__(kMergeThreads) merge_tiles_kernel(
   }
 }
 
+// Single-pass variant of the committing merge: no counting pass and no scan.  Tiles take a ticket (so a tile's
+// predecessors are always running or done), publish (flag | count) words and find their output offset by a
+// warp-wide decoupled look-back over the predecessors' words: flag 1 = the tile's own count, 2 = inclusive prefix.
+constexpr unsigned long long kLbValue = (1ULL << 62) - 1;
+__global__ void __launch_bounds__(kMergeThreads) merge_tiles_lookback_kernel(
+    const uint64_t* __restrict__ A, const uint32_t* __restrict__ Ac, size_t na, const uint64_t* __restrict__ B,
+    const uint32_t* __restrict__ Bc, size_t nb, const uint64_t* __restrict__ a_split, size_t ntiles,
+    unsigned long long* status /* ntiles words, zeroed */, unsigned int* ticket /* zeroed */, uint64_t* __restrict__ out_keys,
+    uint32_t* __restrict__ out_counts, unsigned long long* __restrict__ n_out_total, int* __restrict__ err) {
+  __shared__ uint64_t s_a[kMergeTile + 2];
+  __shared__ uint64_t s_b[kMergeTile + 2];
+  __shared__ unsigned int s_tile;
+  __shared__ unsigned long long s_prefix;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const size_t t = s_tile;
+  size_t diag0 = t * kMergeTile, diag1 = diag0 + kMergeTile;
+  if (diag1 > na + nb) diag1 = na + nb;
+  const size_t a0 = a_split[t], a1 = a_split[t + 1];
+  const size_t b0 = diag0 - a0, b1 = diag1 - a1;
+  const int la = (int)(a1 - a0), lbn = (int)(b1 - b0);
+  const uint64_t kNone = ~0ULL;
+  for (int i = threadIdx.x; i < la + 1; i += blockDim.x) s_a[i] = (i == 0) ? (a0 > 0 ? A[a0 - 1] : kNone) : A[a0 + i - 1];
+  for (int i = threadIdx.x; i < lbn + 1; i += blockDim.x) s_b[i] = (i < lbn) ? B[b0 + i] : (b1 < nb ? B[b1] : kNone);
+  __syncthreads();
+  const int total = la + lbn;
+  int d0 = min(threadIdx.x * kMergeItems, total), d1 = min(d0 + kMergeItems, total);
+  int lo = max(0, d0 - lbn), hi = min(d0, la);
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (s_a[1 + mid] <= s_b[d0 - mid - 1]) lo = mid + 1; else hi = mid;
+  }
+  int ai = lo, bi = d0 - lo;
+  uint32_t nheads = 0;
+  uint64_t okey[kMergeItems]; uint32_t ocnt[kMergeItems];
+  for (int d = d0; d < d1; d++) {
+    bool takeA = (bi >= lbn) || (ai < la && s_a[1 + ai] <= s_b[bi]);
+    if (takeA) {
+      uint64_t k = s_a[1 + ai];
+      uint64_t nextb = s_b[bi];
+      uint64_t c = Ac[a0 + ai];
+      if (nextb == k) c += Bc[b0 + bi];
+      if (c > 0xFFFFFFFFull) { *err = SHQ_ERR_COUNT_OVERFLOW; c = 0xFFFFFFFFull; }
+      okey[nheads] = k; ocnt[nheads] = (uint32_t)c;
+      nheads++; ai++;
+    } else {
+      uint64_t k = s_b[bi];
+      uint64_t preva = s_a[ai];
+      if (preva != k || (ai == 0 && a0 == 0)) { okey[nheads] = k; ocnt[nheads] = Bc[b0 + bi]; nheads++; }
+      bi++;
+    }
+  }
+  uint32_t tot;
+  uint32_t rank = block_exclusive_scan<SumU32>(nheads, &tot);
+  if (threadIdx.x < 32) {               // warp 0: publish, then look back 32 predecessors at a time
+    const int lane = threadIdx.x;
+    unsigned long long excl = 0;
+    if (t == 0) {
+      if (lane == 0) atomicExch(&status[0], (2ULL << 62) | (unsigned long long)tot);
+    } else {
+      if (lane == 0) atomicExch(&status[t], (1ULL << 62) | (unsigned long long)tot);
+      long long p = (long long)t - 1;   // lane l looks at tile p - l
+      for (;;) {
+        const long long q = p - lane;
+        unsigned long long v = 2ULL << 62;              // tiles before 0: an inclusive prefix of 0
+        if (q >= 0) { do { v = *reinterpret_cast<volatile unsigned long long*>(&status[q]); } while ((v >> 62) == 0); }
+        const unsigned incl = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+        const int first = incl ? __ffs(incl) - 1 : 32;  // nearest predecessor that already knows its inclusive prefix
+        unsigned long long part = lane <= first ? (v & kLbValue) : 0;
+        for (int d = 16; d; d >>= 1) part += __shfl_down_sync(0xffffffffu, part, d);
+        excl += __shfl_sync(0xffffffffu, part, 0);
+        if (first < 32) break;
+        p -= 32;
+      }
+      if (lane == 0) atomicExch(&status[t], (2ULL << 62) | (excl + tot));
+    }
+    if (lane == 0) {
+      s_prefix = excl;
+      if (t == ntiles - 1) *n_out_total = excl + tot;
+    }
+  }
+  __syncthreads();
+  size_t o = (size_t)s_prefix + rank;
+  for (uint32_t i = 0; i < nheads; i++) { out_keys[o + i] = okey[i]; out_counts[o + i] = ocnt[i]; }
+}
+
 // u32 -> u64 widening (scan input)
 __global__ void widen_u32_kernel(const uint32_t* __restrict__ in, uint64_t* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

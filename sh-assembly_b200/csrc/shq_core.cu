@@ -183,6 +183,7 @@ struct BatchBins {
 };
 struct BinOverflow {};          // a fixed-capacity bin overflowed: redo the batch with exact offsets
 
+int g_merge_lookback = 1;       // single-pass committing merge (decoupled look-back); SHQ_MERGE_LOOKBACK=0: count pass + scan + write pass
 int g_spec_bins = 1;            // SHQ_SPEC_BINS=0 forces the two-pass (count, then scatter) binning
 uint64_t g_spec_fallbacks = 0;
 struct Run { DevBuf* keys; DevBuf* counts; DevBuf* chunk; size_t n = 0; uint64_t occ = 0; };
@@ -460,6 +461,22 @@ uint64_t merge_run(shq_handle_s* h, const Run& R, int nchunks, std::vector<uint3
   const uint64_t* Bk = R.keys->as<uint64_t>(); const uint32_t* Bc = R.counts->as<uint32_t>();
   const uint16_t* Bch = (chunk_hist_host && R.chunk) ? R.chunk->as<uint16_t>() : nullptr;
   merge_partition_kernel<<<cdiv(ntiles + 1, 128), 128, 0, st>>>(A, na, Bk, nb, h->d_split.as<uint64_t>(), ntiles); L++;
+  if (g_merge_lookback && commit && !chunk_hist_host && total < ((uint64_t)1 << 32)) {
+    // single pass: the output can hold na + nb entries at most; the real size comes back with the last tile
+    h->st_keys2.reserve((total + 4) * 8); h->st_counts2.reserve((total + 4) * 4);
+    h->d_heads64.reserve((ntiles + 4) * 8);
+    unsigned long long* status = h->d_heads64.as<unsigned long long>();
+    unsigned long long* d_nout = status + ntiles; unsigned int* ticket = (unsigned int*)(status + ntiles + 1);
+    SHQ_CUDA(cudaMemsetAsync(status, 0, (ntiles + 2) * 8, st));
+    merge_tiles_lookback_kernel<<<(unsigned)ntiles, kMergeThreads, 0, st>>>(A, Ac, na, Bk, Bc, nb, h->d_split.as<uint64_t>(), ntiles, status, ticket,
+                                                                        h->st_keys2.as<uint64_t>(), h->st_counts2.as<uint32_t>(), d_nout, h->d_err); L++;
+    SHQ_CUDA(cudaGetLastError());
+    uint64_t n_out = read_scalar(h, (const uint64_t*)d_nout);
+    std::swap(h->st_keys, h->st_keys2); std::swap(h->st_counts, h->st_counts2);
+    h->n_state = n_out;
+    h->image_valid = false;
+    return n_out - na;
+  }
   uint32_t* d_hist = nullptr;
   if (chunk_hist_host) {
     h->d_chunk_hist.reserve((size_t)(nchunks + 1) * 4 + (size_t)kAggBuckets * 4);
@@ -744,6 +761,7 @@ void init_handle(shq_handle_s* h, int qb, int hb, uint32_t seed, int device, int
     SHQ_FAIL(SHQ_ERR_ARG, "bad shard %d of %d", shard, nshards);
   if (const char* e = getenv("SHQ_MAX_BATCH_MB")) { long v = atol(e); if (v >= 1 && v <= 3072) h->max_batch_bytes = (size_t)v << 20; }
   if (const char* e = getenv("SHQ_SPEC_BINS")) g_spec_bins = atoi(e) != 0;
+  if (const char* e = getenv("SHQ_MERGE_LOOKBACK")) g_merge_lookback = atoi(e) != 0;
   if (const char* e = getenv("SHQ_BIN_BITS")) { int v = atoi(e); if (v >= 4 && v <= 13) g_bin_bits = v; }
   SHQ_CUDA(cudaSetDevice(device));
   h->device = device; h->qb = qb; h->hb = hb; h->seed = seed; h->shard = shard; h->nshards = nshards;

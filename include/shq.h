@@ -62,6 +62,9 @@ int shq_reset(shq_t h);
  * end_denoise = --endDeNoise.  Rounds fire at reference-chunk boundaries with
  * t=1 semantics: after the first chunk that leaves ndistinct >= trigger.        */
 int shq_set_denoise_schedule(shq_t h, uint64_t trigger_ndistinct, uint32_t rounds, int end_denoise);
+/* the scheduler's stderr progress lines "Ready for DeNoise: ..." / "Finished DeNoise: ..."
+ * (cqf/CQF_mt.h:867-868, 912-913); ndistinct_true_elts = the -n value they echo.  Off by default. */
+int shq_set_progress_log(shq_t h, int enable, uint64_t ndistinct_true_elts);
 
 /* replaces reads_to_kmers (cqf/CQF_mt.h:610-731) for ONE chunk as cut by
  * fastq_read_parts (:735-816).  text is a host buffer (pageable or pinned) and

@@ -59,7 +59,7 @@ _lib = None
 
 # every symbol include/shq.h declares
 EXPORTS = [
-    "shq_strerror", "shq_last_error", "shq_create", "shq_create_shard", "shq_destroy", "shq_reset", "shq_set_denoise_schedule",
+    "shq_strerror", "shq_last_error", "shq_create", "shq_create_shard", "shq_destroy", "shq_reset", "shq_set_denoise_schedule", "shq_set_progress_log",
     "shq_insert_fastq_chunk", "shq_insert_fastq_pinned", "shq_insert_fastq_pinned_chunks", "shq_insert_fastq_device", "shq_insert_keys", "shq_insert_keys_device", "shq_finish",
     "shq_sync", "shq_counts", "shq_rounds_done", "shq_denoise", "shq_image_size", "shq_export_cqf", "shq_save",
     "shq_load", "shq_load_image", "shq_geometry", "shq_iterate", "shq_query_set_traveled", "shq_query",
@@ -91,6 +91,7 @@ def lib():
         L.shq_destroy.restype = None
         L.shq_reset.argtypes = [vp]
         L.shq_set_denoise_schedule.argtypes = [vp, u64, C.c_uint32, C.c_int]
+        L.shq_set_progress_log.argtypes = [vp, C.c_int, u64]
         L.shq_insert_fastq_chunk.argtypes = [vp, vp, sz, C.c_int]
         L.shq_insert_fastq_pinned.argtypes = [vp, vp, sz, C.c_int]
         L.shq_insert_fastq_device.argtypes = [vp, vp, sz, vp, sz, C.c_int]

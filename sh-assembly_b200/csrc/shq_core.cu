@@ -6,6 +6,7 @@
 // data-path step below is a CUDA kernel from shq_hash.cuh / shq_aggregate.cuh / shq_layout.cuh.
 #include <math.h>
 #include <stdlib.h>
+#include <time.h>
 
 #include <algorithm>
 
@@ -56,6 +57,12 @@ struct shq_handle_s {
   std::vector<uint64_t> stage_chunk_ends;
   int stage_K = 0;
   size_t max_batch_bytes = (size_t)1 << 28;
+  // tunables (environment, read once per handle in init_handle)
+  bool spec_bins = true;         // SHQ_SPEC_BINS=0 forces the two-pass (count, then scatter) binning
+  bool merge_lookback = true;    // SHQ_MERGE_LOOKBACK=0: count pass + scan + write pass instead of the single-pass merge
+  int bin_bits = 0;              // SHQ_BIN_BITS: 0 = automatic
+  // progress lines of the reference scheduler on stderr (cqf/CQF_mt.h:867-868, 912)
+  bool log_progress = false; uint64_t ndistinct_true = 0;
 
   // pinned-source pipeline: copy stream + 3 rotating device text buffers
   struct PinBatch { int buf; size_t bytes; std::vector<uint64_t> ends; int K; cudaEvent_t ev; };
@@ -183,12 +190,7 @@ struct BatchBins {
 };
 struct BinOverflow {};          // a fixed-capacity bin overflowed: redo the batch with exact offsets
 
-int g_merge_lookback = 1;       // single-pass committing merge (decoupled look-back); SHQ_MERGE_LOOKBACK=0: count pass + scan + write pass
-int g_spec_bins = 1;            // SHQ_SPEC_BINS=0 forces the two-pass (count, then scatter) binning
-uint64_t g_spec_fallbacks = 0;
 struct Run { DevBuf* keys; DevBuf* counts; DevBuf* chunk; size_t n = 0; uint64_t occ = 0; };
-
-int g_bin_bits = 0;             // 0 = automatic (tunable: SHQ_BIN_BITS)
 
 int pick_bin_bits(shq_handle_s* h, uint64_t est_keys, int chunk_bits_needed) {
   // aim at ~64K occurrences per bin (8 per bin and scatter round) AND at most ~7000 distinct keys per bin (one round
@@ -197,7 +199,7 @@ int pick_bin_bits(shq_handle_s* h, uint64_t est_keys, int chunk_bits_needed) {
   int local_bits = h->hb - shard_bits;
   int pb = 8;
   while (pb < 12 && ((est_keys >> pb) > 65536 || (double)(est_keys >> pb) * h->distinct_ratio * 1.2 > 7000.0)) pb++;
-  if (g_bin_bits) pb = g_bin_bits;
+  if (h->bin_bits) pb = h->bin_bits;
   if (pb > local_bits) pb = local_bits;
   // the low key bits share a 32-bit word with the chunk id, and 0xFFFFFFFF is the aggregator's empty marker
   while ((local_bits - pb + chunk_bits_needed > 32 || local_bits - pb > 31) && pb < 13) pb++;
@@ -273,7 +275,7 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
   size_t smem_scatter = sizeof(RollTables) + ((size_t)3 * n_bins + 1) * 4 + (size_t)kScatThreads * (wide ? 16 : 8) * 14 + 16 + smem_cle;
   size_t smem_keys = (size_t)n_bins * 8;
   Sink sk{};
-  if (allow_spec && g_spec_bins && from_text && whole && wide && !global_bits) {
+  if (allow_spec && h->spec_bins && from_text && whole && wide && !global_bits) {
     // One hashing pass.  ntHash keys are uniform, so every bin gets the mean + 6 % + 2048 words; a bin that would not
     // fit is caught by the scatter kernel and the caller falls back to the exact two-pass binning for this batch.
     h->d_misc.reserve(256);
@@ -461,7 +463,7 @@ uint64_t merge_run(shq_handle_s* h, const Run& R, int nchunks, std::vector<uint3
   const uint64_t* Bk = R.keys->as<uint64_t>(); const uint32_t* Bc = R.counts->as<uint32_t>();
   const uint16_t* Bch = (chunk_hist_host && R.chunk) ? R.chunk->as<uint16_t>() : nullptr;
   merge_partition_kernel<<<cdiv(ntiles + 1, 128), 128, 0, st>>>(A, na, Bk, nb, h->d_split.as<uint64_t>(), ntiles); L++;
-  if (g_merge_lookback && commit && !chunk_hist_host && total < ((uint64_t)1 << 32)) {
+  if (h->merge_lookback && commit && !chunk_hist_host && total < ((uint64_t)1 << 32)) {
     // single pass: the output can hold na + nb entries at most; the real size comes back with the last tile
     h->st_keys2.reserve((total + 4) * 8); h->st_counts2.reserve((total + 4) * 4);
     h->d_heads64.reserve((ntiles + 4) * 8);
@@ -571,7 +573,29 @@ void ensure_state(shq_handle_s* h) {
   h->image_only = false;
 }
 
+std::string current_date_time() {      // base/global.cpp:14-21
+  time_t now = time(nullptr);
+  struct tm t; localtime_r(&now, &t);
+  char buf[80];
+  strftime(buf, sizeof buf, "%Y-%m-%d.%X", &t);
+  return buf;
+}
+void log_denoise(shq_handle_s* h, bool ready) {   // the two progress lines of the scheduler, cqf/CQF_mt.h:867-868, 912-913
+  if (!h->log_progress) return;
+  if (ready) fprintf(stderr, "%s\n", current_date_time().c_str());
+  fprintf(stderr, "%s DeNoise: ndistinct_elts/total_elts.%llu/%llu ndistinct_true_elts.%llu\n", ready ? "Ready for" : "Finished",
+          (unsigned long long)h->ndistinct, (unsigned long long)h->nelts, (unsigned long long)h->ndistinct_true);
+  if (!ready) fprintf(stderr, "%s\n", current_date_time().c_str());
+}
+
+uint64_t denoise_round_impl(shq_handle_s* h);
 uint64_t denoise_round(shq_handle_s* h) {
+  log_denoise(h, true);
+  uint64_t r = denoise_round_impl(h);
+  log_denoise(h, false);
+  return r;
+}
+uint64_t denoise_round_impl(shq_handle_s* h) {
   ensure_state(h);
   cudaStream_t st = h->stream;
   uint64_t& L = h->stats.kernels_launched;
@@ -611,7 +635,13 @@ void process_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uin
   ensure_state(h);
   if (h->finished) SHQ_FAIL(SHQ_ERR_STATE, "handle already finished");
   const bool from_text = d_keys == nullptr;
-  if (from_text && (n_text == 0 || nchunks == 0)) return;
+  if (from_text && n_text == 0) {
+    // only empty chunks (fastq_read_parts found no record boundary, cut == 0): the reference still evaluates
+    // needDeNoise() after each of them (cqf/CQF_mt.h:829-839), so a round fires while ndistinct stays >= trigger
+    for (int c = 0; c < nchunks; c++)
+      if (h->rounds_left > 0 && h->ndistinct >= h->trigger) { h->rounds_left--; denoise_round(h); }
+    return;
+  }
   if (!from_text && n_keys_in == 0) return;
   bool armed = from_text && h->rounds_left > 0;
   BatchBins bb;
@@ -662,7 +692,7 @@ void process_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uin
     clo = (uint32_t)cstar + 1;
   } catch (const BinOverflow&) {
     // thrown by the first aggregation of a one-pass batch, before anything was merged: bin again with exact offsets
-    g_spec_fallbacks++; h->stats.bin_fallbacks++;
+    h->stats.bin_fallbacks++;
     bin_batch(h, d_text, n_text, chunk_ends, nchunks, K, d_keys, n_keys_in, armed, &bb, 0, false);
     if (bb.n_keys == 0) return;
   }
@@ -724,7 +754,13 @@ void pin_drain(shq_handle_s* h) {
 
 void flush_stage(shq_handle_s* h) {
   pin_drain(h);
-  if (h->h_stage_fill == 0) { h->stage_chunk_ends.clear(); return; }
+  if (h->h_stage_fill == 0) {
+    if (!h->stage_chunk_ends.empty()) {        // nothing but empty chunks
+      std::vector<uint64_t> e; e.swap(h->stage_chunk_ends);
+      process_batch(h, nullptr, 0, e.data(), (int)e.size(), h->stage_K, nullptr, 0);
+    }
+    return;
+  }
   size_t n = h->h_stage_fill;
   h->d_text.reserve(n + 64);
   SHQ_CUDA(cudaMemcpyAsync(h->d_text.p, h->h_stage, n, cudaMemcpyHostToDevice, h->stream));
@@ -760,9 +796,9 @@ void init_handle(shq_handle_s* h, int qb, int hb, uint32_t seed, int device, int
   if (nshards < 1 || (nshards & (nshards - 1)) || shard < 0 || shard >= nshards || (1 << qb) < nshards * 64)
     SHQ_FAIL(SHQ_ERR_ARG, "bad shard %d of %d", shard, nshards);
   if (const char* e = getenv("SHQ_MAX_BATCH_MB")) { long v = atol(e); if (v >= 1 && v <= 3072) h->max_batch_bytes = (size_t)v << 20; }
-  if (const char* e = getenv("SHQ_SPEC_BINS")) g_spec_bins = atoi(e) != 0;
-  if (const char* e = getenv("SHQ_MERGE_LOOKBACK")) g_merge_lookback = atoi(e) != 0;
-  if (const char* e = getenv("SHQ_BIN_BITS")) { int v = atoi(e); if (v >= 4 && v <= 13) g_bin_bits = v; }
+  if (const char* e = getenv("SHQ_SPEC_BINS")) h->spec_bins = atoi(e) != 0;
+  if (const char* e = getenv("SHQ_MERGE_LOOKBACK")) h->merge_lookback = atoi(e) != 0;
+  if (const char* e = getenv("SHQ_BIN_BITS")) { int v = atoi(e); if (v >= 4 && v <= 13) h->bin_bits = v; }
   SHQ_CUDA(cudaSetDevice(device));
   h->device = device; h->qb = qb; h->hb = hb; h->seed = seed; h->shard = shard; h->nshards = nshards;
   h->nslots = 1ULL << qb;
@@ -803,6 +839,19 @@ void free_handle(shq_handle_s* h) {
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
+
+// two page-locked staging buffers + events + a FILE*, released on every exit path (shq_save / shq_load)
+struct PinnedPair {
+  FILE* f = nullptr; uint8_t* pin[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr};
+  void alloc(size_t piece) {
+    for (int i = 0; i < 2; i++) { SHQ_CUDA(cudaMallocHost((void**)&pin[i], piece)); SHQ_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)); }
+  }
+  int close_file() { int rc = f ? fclose(f) : 0; f = nullptr; return rc; }
+  ~PinnedPair() {
+    if (f) fclose(f);
+    for (int i = 0; i < 2; i++) { if (pin[i]) cudaFreeHost(pin[i]); if (ev[i]) cudaEventDestroy(ev[i]); }
+  }
+};
 
 void build_header(shq_handle_s* h, uint8_t* hd) {   // qfmetadata, cqf/gqf.h:62-77 (x86-64 layout)
   memset(hd, 0, 128);
@@ -874,11 +923,17 @@ int shq_set_denoise_schedule(shq_t h, uint64_t trigger, uint32_t rounds, int end
   return SHQ_OK;
 }
 
+int shq_set_progress_log(shq_t h, int enable, uint64_t ndistinct_true_elts) {
+  if (!h) return SHQ_ERR_ARG;
+  h->log_progress = enable != 0; h->ndistinct_true = ndistinct_true_elts;
+  return SHQ_OK;
+}
+
 int shq_insert_fastq_chunk(shq_t h, const char* text, size_t n, int K) {
   if (!h || (!text && n)) return SHQ_ERR_ARG;
   struct { const char* text; size_t n; int K; } args{text, n, K};
   SHQ_API_BEGIN(h)
-    if (h->h_stage_fill && (h->stage_K != a.K || h->h_stage_fill + a.n > h->max_batch_bytes)) flush_stage(h);
+    if ((h->h_stage_fill || !h->stage_chunk_ends.empty()) && (h->stage_K != a.K || h->h_stage_fill + a.n > h->max_batch_bytes)) flush_stage(h);
     if (a.n > h->max_batch_bytes && a.n >= ((size_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "chunk too large");
     if (h->h_stage_cap < h->h_stage_fill + a.n) {
       size_t want = std::max(h->h_stage_fill + a.n, std::min(h->max_batch_bytes, std::max((size_t)64 << 20, 2 * h->h_stage_cap)));
@@ -1070,33 +1125,32 @@ int shq_save(shq_t h, const char* path) {
     flush_stage(h);
     if (h->nshards != 1) SHQ_FAIL(SHQ_ERR_STATE, "export of a sharded handle goes through the multi-GPU layer");
     if (!h->image_only) materialise(h);
-    FILE* f = fopen(a.path, "wb+");
-    if (!f) SHQ_FAIL(SHQ_ERR_IO, "cannot write %s", a.path);
+    // the image leaves the device through two page-locked buffers: the copy of piece i+1 runs under the write of piece i
+    PinnedPair pp;                       // releases file, buffers and events on every exit path
+    pp.f = fopen(a.path, "wb+");
+    if (!pp.f) SHQ_FAIL(SHQ_ERR_IO, "cannot write %s", a.path);
     uint8_t hd[128];
     build_header(h, hd);
-    bool ok = fwrite(hd, 1, 128, f) == 128;
-    // the image leaves the device through two page-locked buffers: the copy of piece i+1 runs under the write of piece i
+    bool ok = fwrite(hd, 1, 128, pp.f) == 128;
     const size_t total = (size_t)h->nblocks * kBlockBytes, piece = (size_t)32 << 20;
-    uint8_t* pin[2] = {nullptr, nullptr};
-    cudaEvent_t ev[2];
-    for (int i = 0; i < 2; i++) { SHQ_CUDA(cudaMallocHost((void**)&pin[i], piece)); SHQ_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)); }
+    pp.alloc(piece);
     size_t off = 0; int cur = 0;
     auto issue = [&](int b, size_t o) {
       size_t m = std::min(piece, total - o);
-      cudaMemcpyAsync(pin[b], h->image.as<uint8_t>() + o, m, cudaMemcpyDeviceToHost, h->stream);
-      cudaEventRecord(ev[b], h->stream);
+      SHQ_CUDA(cudaMemcpyAsync(pp.pin[b], h->image.as<uint8_t>() + o, m, cudaMemcpyDeviceToHost, h->stream));
+      SHQ_CUDA(cudaEventRecord(pp.ev[b], h->stream));
     };
     if (total) issue(0, 0);
     while (off < total && ok) {
       size_t m = std::min(piece, total - off);
       if (off + m < total) issue(cur ^ 1, off + m);
-      ok = cudaEventSynchronize(ev[cur]) == cudaSuccess && fwrite(pin[cur], 1, m, f) == m;
+      SHQ_CUDA(cudaEventSynchronize(pp.ev[cur]));
+      ok = fwrite(pp.pin[cur], 1, m, pp.f) == m;
       off += m; cur ^= 1;
     }
-    cudaStreamSynchronize(h->stream);
-    for (int i = 0; i < 2; i++) { cudaFreeHost(pin[i]); cudaEventDestroy(ev[i]); }
+    SHQ_CUDA(cudaStreamSynchronize(h->stream));
     h->stats.d2h_bytes += total;
-    if (fclose(f) != 0) ok = false;
+    if (pp.close_file() != 0) ok = false;
     if (!ok) SHQ_FAIL(SHQ_ERR_IO, "cannot write %s", a.path);
   SHQ_API_END
 }
@@ -1131,20 +1185,63 @@ int shq_load_image(const void* image, size_t n, int device, shq_t* out) {
   return SHQ_OK;
 }
 
+// header checks shared by shq_load_image / shq_load: geometry out of the 128-byte qfmetadata
+static int parse_header(const uint8_t* p, size_t avail, int* qb, int* hb, uint32_t* seed, uint64_t* size, uint64_t* nelts, uint64_t* ndistinct,
+                        uint64_t* xnslots_out, uint64_t* nblocks_out) {
+  auto get = [&](int off) { uint64_t v; memcpy(&v, p + off, 8); return v; };
+  uint64_t sz = get(0), nslots = get(16), xnslots = get(24), key_bits = get(32), bps = get(56), nblocks = get(80);
+  memcpy(seed, p + 8, 4);
+  int q = 0; while (q < 63 && (1ULL << q) < nslots) q++;
+  if (bps != 8 || (1ULL << q) != nslots || key_bits != (uint64_t)q + 8 || sz != nblocks * kBlockBytes || avail < 128 + sz) return SHQ_ERR_FORMAT;
+  *qb = q; *hb = (int)key_bits; *size = sz; *nelts = get(88); *ndistinct = get(96); *xnslots_out = xnslots; *nblocks_out = nblocks;
+  return SHQ_OK;
+}
+
+// qf_deserialize (cqf/gqf.c:2396-2420) without a whole-file host copy: the block array streams through two page-locked
+// pieces, the read of piece i+1 overlapping the H2D copy of piece i (a 22 GiB human table never sits in pageable memory)
 int shq_load(const char* path, int device, shq_t* out) {
   if (!path || !out) return SHQ_ERR_ARG;
+  *out = nullptr;
   FILE* f = fopen(path, "rb");
   if (!f) return SHQ_ERR_IO;
-  fseek(f, 0, SEEK_END);
-  long sz = ftell(f);
-  fseek(f, 0, SEEK_SET);
-  void* buf = malloc(sz > 0 ? (size_t)sz : 1);
-  if (!buf) { fclose(f); return SHQ_ERR_ARG; }
-  size_t got = fread(buf, 1, (size_t)sz, f);
-  fclose(f);
-  int rc = got == (size_t)sz ? shq_load_image(buf, got, device, out) : SHQ_ERR_IO;
-  free(buf);
-  return rc;
+  uint8_t hd[128];
+  if (fread(hd, 1, 128, f) != 128) { fclose(f); return SHQ_ERR_FORMAT; }
+  if (fseeko(f, 0, SEEK_END) != 0) { fclose(f); return SHQ_ERR_IO; }
+  const off_t fsz = ftello(f);
+  if (fseeko(f, 128, SEEK_SET) != 0) { fclose(f); return SHQ_ERR_IO; }
+  int qb, hb; uint32_t seed; uint64_t size, nelts, ndistinct, xnslots, nblocks;
+  int rc = parse_header(hd, fsz < 0 ? 0 : (size_t)fsz, &qb, &hb, &seed, &size, &nelts, &ndistinct, &xnslots, &nblocks);
+  if (rc) { fclose(f); return rc; }
+  shq_t h = nullptr;
+  rc = shq_create(qb, hb, seed, device, &h);
+  if (rc) { fclose(f); return rc; }
+  if (h->xnslots != xnslots || h->nblocks != nblocks) { fclose(f); shq_destroy(h); return SHQ_ERR_FORMAT; }
+  struct { FILE* f; size_t size; } args{f, (size_t)size};
+  rc = guard(h, [](shq_handle_s* h, void* ap) {
+    auto& a = *(decltype(args)*)ap;
+    PinnedPair pp; pp.f = a.f;
+    const size_t piece = (size_t)32 << 20;
+    pp.alloc(piece);
+    size_t tiles = (h->nblocks + kTileBlocks - 1) / kTileBlocks;
+    h->image.reserve(tiles * kTileBytes + 16);
+    int cur = 0; bool used[2] = {false, false};
+    for (size_t off = 0; off < a.size; off += piece, cur ^= 1) {
+      const size_t m = std::min(piece, a.size - off);
+      if (used[cur]) SHQ_CUDA(cudaEventSynchronize(pp.ev[cur]));       // the copy that last read this buffer is done
+      if (fread(pp.pin[cur], 1, m, pp.f) != m) SHQ_FAIL(SHQ_ERR_IO, "short read at image offset %zu", off);
+      SHQ_CUDA(cudaMemcpyAsync(h->image.as<uint8_t>() + off, pp.pin[cur], m, cudaMemcpyHostToDevice, h->stream));
+      SHQ_CUDA(cudaEventRecord(pp.ev[cur], h->stream));
+      used[cur] = true;
+    }
+    SHQ_CUDA(cudaStreamSynchronize(h->stream));
+    h->stats.h2d_bytes += a.size;
+  }, &args);
+  if (rc) { shq_destroy(h); return rc; }
+  memcpy(h->header, hd, 128); h->has_header = true;
+  h->nelts = nelts; h->ndistinct = ndistinct;
+  h->image_valid = true; h->image_only = true;
+  *out = h;
+  return SHQ_OK;
 }
 
 int shq_iterate(shq_t h, uint64_t* keys, uint64_t* counts, size_t cap, size_t* n) {
@@ -1477,6 +1574,9 @@ int shq_mg_insert_pull(shq_t h, const uint32_t* d_all_fine_hist, int parity) {
       resplit_kernel<false><<<cps * parts, kSplitThreads, 0, st>>>(h->d_bases.as<const uint32_t*>(), seg_beg, world, cps, parts, lbc, fb,
                                                                  h->d_fine.as<uint32_t>(), h->d_packed.as<uint32_t>()); L++;
       SHQ_CUDA(cudaGetLastError());
+      // the peers' buffers of this parity have been read completely once this returns: a source may refill its buffer
+      // two batches later only because every owner passed this point (and the all-gather in between) before
+      SHQ_CUDA(cudaStreamSynchronize(st));
     }
     BatchBins bb;
     bb.n_bins = F; bb.lb = lbf; bb.n_keys = (uint32_t)n; bb.armed = false; bb.nchunks = 1;

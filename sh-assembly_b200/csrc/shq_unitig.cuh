@@ -757,6 +757,7 @@ void unitigs_build_impl(shq_unitigs_s* u) {
     check_err_flag(h);
     if (n_nodes > u->max_nodes) SHQ_FAIL(SHQ_ERR_CAPACITY, "unitig node table overflow (%u nodes)", n_nodes);
   }
+  if (begin < n_nodes) SHQ_FAIL(SHQ_ERR_STATE, "false-positive closure did not converge in 64 rounds (%u nodes left)", n_nodes - begin);
   if (n_nodes == 0) { u->built = true; return; }
   const unsigned g2 = cdiv((size_t)n_nodes * 2, 256);
   tm.lap("U3 links+closure");
@@ -823,7 +824,8 @@ void unitigs_build_impl(shq_unitigs_s* u) {
     SHQ_CUDA(cudaMemcpyAsync(seed_node.data(), u->seed_node.p, (size_t)n_seeds * 4, cudaMemcpyDeviceToHost, st));
     SHQ_CUDA(cudaMemcpyAsync(seed_root.data(), u->seed_root.p, (size_t)n_seeds * 4, cudaMemcpyDeviceToHost, st));
   }
-  uint32_t nv = std::min(read_scalar(h, u->v_n.as<uint32_t>()), u->victim_cap);
+  uint32_t nv = read_scalar(h, u->v_n.as<uint32_t>());
+  if (nv > u->victim_cap) SHQ_FAIL(SHQ_ERR_CAPACITY, "%u same-key k-mer records exceed the victim list capacity %u", nv, u->victim_cap);
   std::vector<uint32_t> vout((size_t)nv * 4);
   if (nv) {
     u->v_out.reserve((size_t)nv * 16);

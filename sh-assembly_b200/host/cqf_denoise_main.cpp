@@ -129,6 +129,7 @@ int main(int argc, char* argv[]) {
   rc = shq_create((int)qb, (int)hb, seed, stoi(opt.get("device")), &h);
   if (rc) { cerr << "shq_create failed: " << shq_strerror(rc) << endl; return 1; }
   shq_set_denoise_schedule(h, p.trigger, (uint32_t)num_deNoise, end_deNoise ? 1 : 0);
+  shq_set_progress_log(h, 1, n_true_kmers);
 
   time_t start_time = time(NULL);
   cerr << currentDateTime() << endl;

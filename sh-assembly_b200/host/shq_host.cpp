@@ -282,7 +282,8 @@ int shq_build_kmer_spectrum(shq_t h, shq_reader_t r, int K) {
     int rc = shq_reader_next(r, &chunk, &n, nullptr);
     if (rc) return rc;
     if (!chunk) break;
-    if (n == 0) continue;
+    // an empty chunk (no record boundary found, cut == 0) is still a chunk boundary for the deNoise trigger
+    // (cqf/CQF_mt.h:829-839), so it is passed on
     rc = shq_insert_fastq_chunk(h, chunk, n, K);
     if (rc) return rc;
   }

@@ -7,7 +7,7 @@ the .cqf export need the reference's global slot layout (range hand-out of 2^20 
 boundaries), so they gather the sorted shard states onto every rank / rank 0 and run the single-GPU code there.
 
 torch / torch.distributed are plumbing only: device buffers, the process group, the collective.
-The index arithmetic (`split_plan`, `owner_of`, `slice_range`) is pure Python/NumPy so that the N>1 logic is
+The index arithmetic (`plan_for_rank`, `owner_of`, `slice_range`) is pure Python/NumPy so that the N>1 logic is
 covered by world_size-2 gloo tests on CPU (tests/test_multigpu_cpu.py).
 """
 import ctypes as C
@@ -22,20 +22,6 @@ def owner_of(keys: np.ndarray, hb: int, world: int) -> np.ndarray:
     """Shard that owns each key: the high log2(world) bits of the hb-bit key."""
     bits = int(world).bit_length() - 1
     return (keys.astype(np.uint64) >> np.uint64(hb - bits)).astype(np.int64) if bits else np.zeros(len(keys), np.int64)
-
-
-def split_plan(send_counts, all_send_counts):
-    """all-to-all plan.  send_counts[j] = #keys this rank sends to j; all_send_counts[i][j] = what rank i sends to j.
-    Returns (recv_counts, send_offsets, recv_offsets) for this rank (rank index inferred from the matching row)."""
-    send_counts = [int(x) for x in send_counts]
-    rank = None
-    for i, row in enumerate(all_send_counts):
-        if [int(x) for x in row] == send_counts:
-            rank = i if rank is None else rank
-    raise_if = rank is None
-    if raise_if:
-        raise ValueError("send_counts is not a row of all_send_counts")
-    return plan_for_rank(rank, all_send_counts)
 
 
 def plan_for_rank(rank, all_send_counts):

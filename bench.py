@@ -2,20 +2,24 @@
 """bench.py -- canonical k-mers inserted per second into the CQF (BASELINE.json metric).
 
   python bench.py --gpus N --steps K --warmup W            # our arm (libshq.so, CUDA)
-  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle/_ref)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle/_ref), no libshq
 
-Workload at N=1 = BASELINE.json configs[1]: synthetic E. coli-size genome (4.6 Mb), 100x 150 bp
-reads, 0.2 % substitutions, K=31, CQF-deNoise ... --deNoise=2 --endDeNoise (effective: 1 mid-stream
-round + the end round, qb=25).  A step = one whole counting job over that read set.
-For N>1 the genome grows with N (N x 4.6 Mb, 100x) and the filter is sharded by quotient range:
-weak scaling, every rank hashes 1/N of the reads and owns 1/N of the quotient space.
+Workload at N=1 = BASELINE.json configs[2] ("celegans"): synthetic 100 Mb genome, 100x 150 bp reads, 0.234 %
+substitutions, K=47, CQF-deNoise -n 1.2e8 -e 0.00234 with automatic deNoise rounds (3 mid-stream rounds, qb=29):
+6.93e9 k-mers, 21 GB of FASTQ text resident in HBM.  A step = the whole counting job over that read set.
+BASELINE configs[1] (E. coli-size, --deNoise=2 --endDeNoise) is measured in the same run and reported under
+"secondary" (plus the unitig build on its filter).  For N>1 the genome and the filter grow with N (weak scaling):
+every rank generates and hashes 1/N of the reads and owns 1/N of the quotient space.
 
 `value`  : device-resident FASTQ text -> complete CQF image in HBM (CUDA events on the handle's stream).
-`e2e`    : same job through the C ABI with HOST buffers: chunks cut by the reader, pinned staging,
-           H2D copies and the D2H export of the .cqf image inside the timed region.
+`e2e`    : same job through the C ABI with HOST buffers: pinned host text, H2D copies and the D2H export of the
+           .cqf image inside the timed region.
+`parity` : sha256 of the exported .cqf against tests/golden/digests.json, which the UNMODIFIED reference core
+           (oracle/_ref at t=1) produced for the same synthetic read set (tests/golden/make_digests.py).
 """
 import argparse
 import ctypes as C
+import hashlib
 import importlib
 import json
 import os
@@ -29,57 +33,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-A_INS_BYTES = None  # filled from the workload: L/(L-K+1) + 32 + 2*T/N  
+import synth  # noqa: E402
+from synth import workloads as wl  # noqa: E402
 
-
-# ----------------------------------------------------------------------------- data
-def gen_fastq(G, cov, L, err, seed, rank=0, world=1):
-    """SURVEY.md 8(d) synthetic reads: iid genome, uniform positions, strand flip p=.5, substitutions.
-    Rank r of `world` produces every world-th block of reads of the same global read set."""
-    rng_g = np.random.default_rng(seed)
-    genome = np.frombuffer(b"ACGT", np.uint8)[rng_g.integers(0, 4, G, dtype=np.uint8)]
-    nreads = int(G * cov / L)
-    comp = np.zeros(256, np.uint8)
-    for a, b in zip(b"ACGT", b"TGCA"):
-        comp[a] = b
-    code = np.zeros(256, np.uint8)
-    for i, a in enumerate(b"ACGT"):
-        code[a] = i
-    acgt = np.frombuffer(b"ACGT", np.uint8)
-    hdr_w = len(str(nreads))
-    rec = 2 + hdr_w + 1 + L + 1 + 2 + L + 1
-    block = 200000
-    parts = []
-    for bi, b0 in enumerate(range(0, nreads, block)):
-        if bi % world != rank:
-            continue
-        n = min(block, nreads - b0)
-        rng = np.random.default_rng([seed, 1, bi])
-        pos = rng.integers(0, G - L + 1, n)
-        reads = genome[pos[:, None] + np.arange(L)[None, :]]
-        flip = rng.random(n) < 0.5
-        reads[flip] = comp[reads[flip][:, ::-1]]
-        if err > 0:
-            mask = rng.random(reads.shape) < err
-            reads[mask] = acgt[(code[reads[mask]] + rng.integers(1, 4, int(mask.sum()), dtype=np.uint8)) % 4]
-        out = np.empty((n, rec), np.uint8)
-        out[:, 0] = ord("@")
-        out[:, 1] = ord("r")
-        ids = np.arange(b0, b0 + n)
-        for d in range(hdr_w):
-            out[:, 2 + hdr_w - 1 - d] = ord("0") + (ids // 10 ** d) % 10
-        o = 2 + hdr_w
-        out[:, o] = 10
-        out[:, o + 1:o + 1 + L] = reads
-        out[:, o + 1 + L] = 10
-        out[:, o + 2 + L] = ord("+")
-        out[:, o + 3 + L] = 10
-        out[:, o + 4 + L:o + 4 + 2 * L] = ord("I")
-        out[:, o + 4 + 2 * L] = 10
-        parts.append(out.reshape(-1))
-    text = np.concatenate(parts) if parts else np.zeros(0, np.uint8)
-    nloc = len(text) // rec
-    return text, nloc * (L - 0) , nloc
+METRIC = "canonical k-mers inserted/sec"
 
 
 class ClockSampler:
@@ -122,91 +79,161 @@ class ClockSampler:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        # the median under load: samples at (near) idle clocks between steps would only blur it
+        busy = [x for x in sm if x >= 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload(args, world):
-    G = args.genome * world
-    nreads = int(G * args.cov / args.read_len)
-    n_total = nreads * (args.read_len - args.k + 1)
-    return G, nreads, n_total
+def golden_digest(name, world):
+    try:
+        d = json.load(open(os.path.join(ROOT, "tests", "golden", "digests.json")))
+        return d.get(name if world == 1 else "%s@%d" % (name, world))
+    except Exception:
+        return None
 
 
-# ----------------------------------------------------------------------------- reference arm
-def run_reference(args, rank, world):
-    """The reference's own CPU code (gqf.c + nthash.hpp, unmodified) driven by the std::thread restatement of its
-    worker loop (oracle/ref_shim.cpp), all host threads, on a time-bounded sample of the same workload."""
-    if rank != 0:
-        return
-    from oracle import pyoracle as po
-    shq = importlib.import_module("sh-assembly_b200")
-    G, nreads, n_total = workload(args, world)
-    p = shq.param_block(args.k, G, n_total, alpha=args.err, deNoise=args.denoise)
-    text, _, nloc = gen_fastq(G, args.cov, args.read_len, args.err, args.seed, 0, 1)
-    rd = shq.Reader(buffers=[text])
-    ends, off = [], 0
-    while True:
-        r = rd.next_raw()
-        if r is None:
-            break
-        off += r[1]
-        ends.append(off)
-    rd.close()
-    cores = os.cpu_count() or 1
-    threads = cores
-    if po.ref() is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libshq_ref.so missing (built only where /root/reference exists)"}))
-        return
-    budget = args.cpu_seconds
-    times, rates, sample = [], [], ""
-    for it in range(args.warmup + args.steps):
-        r = po.RefCqf(int(p.qb), int(p.hb))
-        secs, kmers, chunks, rounds = r.count_mt(text.ctypes.data, ends, args.k, threads, trigger=int(p.trigger), rounds=int(p.num_deNoise),
-                                                 end_denoise=args.end_denoise, max_seconds=budget)
-        r.close()
-        if it >= args.warmup:
-            times.append(secs)
-            rates.append(kmers / secs)
-        sample = "first %d of %d chunks (%.3g of %.3g k-mers), %.1f s budget per step, table sized for the full set (qb=%d)" % (
-            chunks, len(ends), kmers, n_total, budget, p.qb)
-    v = float(np.mean(rates))
-    line = {"impl": "reference", "metric": "canonical k-mers inserted/sec", "value": v, "unit": "k-mers/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * float(np.mean(times)), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": config_dict(args, world, p),
-            "cpu_baseline": {"value": v, "unit": "k-mers/s", "cores": threads, "kind": "reference", "sample": sample},
-            "e2e": {"value": v, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
-
-
-def config_dict(args, world, p):
-    return {"workload": "BASELINE configs[1]: synthetic %.3g Mb genome, %dx %d bp reads, %.2g%% subst, k=%d, --deNoise=%d%s (effective %d mid-stream round(s)), qb=%d hb=%d"
-            % (args.genome * world / 1e6, args.cov, args.read_len, 100 * args.err, args.k, args.denoise, " --endDeNoise" if args.end_denoise else "",
-               p.num_deNoise, p.qb, p.hb),
-            "genome_bp": args.genome * world, "coverage": args.cov, "read_len": args.read_len, "error_rate": args.err, "K": args.k,
-            "deNoise": args.denoise, "endDeNoise": bool(args.end_denoise), "qb": int(p.qb), "trigger": int(p.trigger),
+def config_dict(w, world, p, name):
+    return {"workload": wl.describe(w, p), "name": name, "genome_bp": w["G"], "coverage": w["cov"], "read_len": w["L"],
+            "error_rate": w["err"], "K": w["K"], "n_true": w["n_true"], "deNoise": w["deNoise"], "endDeNoise": bool(w["end"]),
+            "num_deNoise_effective": int(p.num_deNoise), "qb": int(p.qb), "trigger": int(p.trigger), "seed": wl.SEED,
             "l2_policy": "inputs (>= 1 GB of FASTQ text per step) are larger than the 126 MB L2; no explicit flush",
             "shards": world}
 
 
-# ----------------------------------------------------------------------------- our arm
-def run_ours(args, rank, world, local_rank):
+def peak_hbm():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        if "hbm_gbs" in peaks:
+            return float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    except Exception:
+        pass
+    return 6650.0, "6650 GB/s (B200_PROFILING.md fallback)"
+
+
+# ----------------------------------------------------------------------------- CPU legs (oracle/_ref)
+def cpu_sample(w, sp, p, seconds, cores, po):
+    """A bounded sample of the workload through the reference core with `cores` host threads.
+    Returns (k-mers/s, seconds, kmers, description)."""
+    # the reference core does ~5e6 k-mers/s per thread: generate about 1.5x what the budget can absorb
+    per_read = w["L"] - w["K"] + 1
+    want = int(min(sp.n_reads, max(200000, seconds * cores * 7.5e6 / per_read)))
+    text = synth.cpu_fill(sp, 0, want)
+    ends = po.chunk_ends(text.ctypes.data, text.nbytes)
+    r = po.RefCqf(int(p.qb), int(p.hb))
+    secs, kmers, chunks, rounds = r.count_mt(text.ctypes.data, ends, w["K"], cores, trigger=int(p.trigger), rounds=int(p.num_deNoise),
+                                             end_denoise=bool(w["end"]) and want == sp.n_reads, max_seconds=seconds)
+    r.close()
+    desc = ("first %d of %d reads generated, %d chunks (%.3g of %.3g k-mers) counted in %.1f s; table sized for the full set (qb=%d); "
+            "unmodified gqf.c + nthash.hpp under the std::thread worker loop of oracle/ref_shim.cpp" % (
+                want, sp.n_reads, chunks, kmers, wl.n_kmers(w), secs, p.qb))
+    return kmers / secs, secs, kmers, desc
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU code (gqf.c + nthash.hpp, unmodified) driven by the std::thread restatement of its
+    worker loop (oracle/ref_shim.cpp), all host threads, on a time-bounded sample of the same workload.
+    Nothing of sh-assembly_b200 is imported here: parameters and chunking come from the oracle."""
+    if rank != 0:
+        return
+    from oracle import pyoracle as po
+    if po.ref() is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libshq_ref.so missing (built only where /root/reference exists)"}))
+        return
+    w = wl.scaled(args.workload, world)
+    sp = synth.make(w["G"], w["cov"], w["L"], w["err"], wl.SEED)
+    p = po.param_block(w["K"], w["n_true"], wl.n_kmers(w), alpha=w["err"], deNoise=w["deNoise"])
+    cores = os.cpu_count() or 1
+    # the whole --steps/--warmup run stays within a few minutes
+    budget = max(1.0, min(args.cpu_seconds, 100.0 / max(1, args.steps + args.warmup)))
+    times, rates, sample = [], [], ""
+    for it in range(args.warmup + args.steps):
+        rate, secs, kmers, sample = cpu_sample(w, sp, p, budget, cores, po)
+        if it >= args.warmup:
+            times.append(secs)
+            rates.append(rate)
+    v = float(np.mean(rates))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "k-mers/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * float(np.mean(times)), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": config_dict(w, world, p, args.workload),
+            "cpu_baseline": {"value": v, "unit": "k-mers/s", "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": v, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- roofline
+PHASES = {
+    # phase -> (dominant kernel, launches counter, algorithmic bytes from the work counters of shq_stats)
+    "ms_hash_count": ("roll_count_kernel", "scatter_launches", lambda s: s["scatter_text_bytes"]),
+    # read the text once, write one packed 32-bit word per k-mer
+    "ms_scatter": ("roll_scatter_kernel", "scatter_launches", lambda s: s["scatter_text_bytes"] + 4 * s["scatter_words"]),
+    # second binning level: read and write every packed word once
+    "ms_split": ("split_bins_kernel", "split_launches", lambda s: 8 * s["split_words"]),
+    # read the packed words; write (key u64, count u32, first chunk u16) per distinct key, twice (bin order, then dense)
+    "ms_aggregate": ("bin_aggregate_kernel", "agg_launches", lambda s: 4 * s["agg_words"] + 2 * 14 * s["agg_distinct"]),
+    # read (key u64, count u32) of state and run, write the merged state
+    "ms_merge": ("merge_tiles_lookback_kernel", "merge_launches", lambda s: 12 * (s["merge_in"] + s["merge_out"])),
+    "ms_layout": ("layout_scan_kernel + image_tiles_kernel", "layout_launches", None),
+    # two passes over (key, count), survivors written
+    "ms_denoise": ("denoise_tiles_kernel", "denoise_launches", lambda s: 2 * 12 * s["denoise_entries"]),
+}
+
+
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture of
+    this bench command (profiles/r2_traffic.json, written by tools/ncu_summary.py); None if absent."""
+    for f in ("r2_traffic.json",):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", f)))
+            if kernel in t:
+                return t[kernel]
+        except Exception:
+            pass
+    return None
+
+
+def roofline(stats, steps, value, a_ins, table_bytes):
+    peak, peak_src = peak_hbm()
+    phases = {k: stats[k] / steps for k in PHASES}
+    dom = max(phases, key=phases.get)
+    kernel, lkey, fn = PHASES[dom]
+    if fn is None:
+        alg = 12 * stats["layout_entries"] + table_bytes * stats["layout_launches"]
+    else:
+        alg = fn(stats)
+    nl = max(1, stats[lkey])
+    ms_launch = stats[dom] / nl
+    achieved = (alg / nl) / (ms_launch / 1e3) / 1e9 if ms_launch > 0 else 0.0
+    return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": measured_traffic(kernel), "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg / nl, "launches_per_step": nl / steps, "ms_per_launch": ms_launch,
+            "note": "achieved = algorithmic bytes of the phase's launches (work counters of shq_stats, summed per launch) / CUDA-event time "
+                    "of the phase on the handle's stream; the path is bound by instruction issue and shared-memory latency (DESIGN.md 4)",
+            "phase_ms_per_step": phases,
+            "pipeline": {"bytes_per_kmer": a_ins, "achieved": value * a_ins / 1e9, "frac": value * a_ins / 1e9 / peak,
+                         "note": "whole insert path against SURVEY 8(d) A_ins = L/(L-K+1) + 32 + 2T/N"}}
+
+
+# ----------------------------------------------------------------------------- our arm, one GPU
+def run_workload(args, name, steps, warmup, local_rank, want_unitigs, want_cpu):
     import torch
     shq = importlib.import_module("sh-assembly_b200")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- libshq has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_
-        dist = dist_
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    G, nreads, n_total = workload(args, world)
-    p = shq.param_block(args.k, G, n_total, alpha=args.err, deNoise=args.denoise)
-    text, _, nloc = gen_fastq(G, args.cov, args.read_len, args.err, args.seed, rank, world)
-    n_local = nloc * (args.read_len - args.k + 1)
-    # reference chunking (host reader, 8 MiB parts)
+    w = wl.scaled(name, 1)
+    sp = synth.make(w["G"], w["cov"], w["L"], w["err"], wl.SEED)
+    n_total = wl.n_kmers(w)
+    p = shq.param_block(w["K"], w["n_true"], n_total, alpha=w["err"], deNoise=w["deNoise"])
+    K = w["K"]
+    dev = torch.device("cuda", local_rank)
+    n_bytes = sp.n_reads * sp.rec_bytes
+    # synthetic reads straight into HBM, then one copy to pinned host memory (the e2e leg and the chunker read it there)
+    d_text = torch.empty(n_bytes + 64, dtype=torch.uint8, device=dev)
+    synth.gpu_fill(sp, 0, sp.n_reads, d_text.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    h_text = torch.empty(n_bytes, dtype=torch.uint8).pin_memory()
+    h_text.copy_(d_text[:n_bytes])
+    torch.cuda.synchronize()
+    text = h_text.numpy()
+    # reference chunking (host reader, 8 MiB parts cut at a record)
     rd = shq.Reader(buffers=[text])
     ends, off = [], 0
     while True:
@@ -217,46 +244,31 @@ def run_ours(args, rank, world, local_rank):
         ends.append(off)
     rd.close()
     ends = np.array(ends, np.uint64)
-    if world > 1:
-        from importlib import import_module
-        mg = import_module("sh-assembly_b200.multigpu")
-        return mg.bench_sharded(args, rank, world, local_rank, text, ends, p, n_local, n_total, config_dict(args, world, p), ClockSampler)
 
-    d_text = torch.empty(len(text) + 64, dtype=torch.uint8, device="cuda")
-    h_text = torch.from_numpy(text).pin_memory()
-    d_text[:len(text)].copy_(h_text)
-    torch.cuda.synchronize()
     q = shq.CQF(int(p.qb), int(p.hb), device=local_rank)
-    stream = torch.cuda.ExternalStream(q.stream(), device=torch.device("cuda", local_rank))
+    stream = torch.cuda.ExternalStream(q.stream(), device=dev)
 
     def step_device():
         q.reset()
-        q.set_denoise_schedule(int(p.trigger), int(p.num_deNoise), args.end_denoise)
-        q.insert_fastq_device(d_text.data_ptr(), len(text), ends, args.k)
+        q.set_denoise_schedule(int(p.trigger), int(p.num_deNoise), w["end"])
+        q.insert_fastq_device(d_text.data_ptr(), n_bytes, ends, K)
         q.finish()
         q.materialize()
 
-    # destination of the exported .cqf image: page-locked, so the D2H copy runs at PCIe speed (a pageable destination
-    # is staged through a bounce buffer at a fraction of it)
+    # destination of the exported .cqf image: page-locked, so the D2H copy runs at PCIe speed
     img_t = torch.empty(128 + q.nblocks * 89, dtype=torch.uint8).pin_memory()
     img = img_t.numpy()
     h_ptr = h_text.data_ptr()
 
     def step_e2e():
         q.reset()
-        q.set_denoise_schedule(int(p.trigger), int(p.num_deNoise), args.end_denoise)
-        if args.e2e_per_chunk_calls:
-            o = 0
-            for e in ends:
-                q.insert_fastq_pinned_raw(h_ptr + o, int(e) - o, args.k)
-                o = int(e)
-        else:       # one C call for all reference chunks of the pinned buffer (no interpreter time between chunks)
-            q.insert_fastq_pinned_chunks(h_ptr, len(text), ends, args.k)
+        q.set_denoise_schedule(int(p.trigger), int(p.num_deNoise), w["end"])
+        q.insert_fastq_pinned_chunks(h_ptr, n_bytes, ends, K)
         q.finish()
-        w = C.c_size_t()
-        q._check(q.L.shq_export_cqf(q.h, img.ctypes.data, img.nbytes, C.byref(w)))
+        wr = C.c_size_t()
+        q._check(q.L.shq_export_cqf(q.h, img.ctypes.data, img.nbytes, C.byref(wr)))
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_device()
     torch.cuda.synchronize()
     q.reset_stats()
@@ -265,7 +277,7 @@ def run_ours(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_device()
     e1.record(stream)
     torch.cuda.synchronize()
@@ -276,66 +288,71 @@ def run_ours(args, rank, world, local_rank):
     rounds = q.rounds_done()
 
     # end to end through host buffers
+    del d_text
+    torch.cuda.empty_cache()
     step_e2e()
     torch.cuda.synchronize()
     q.reset_stats()
+    e2e_steps = max(1, min(steps, args.e2e_steps))
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record(stream)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         step_e2e()
     e3.record(stream)
     torch.cuda.synchronize()
-    ms_e2e = max(e2.elapsed_time(e3), 1000 * (time.perf_counter() - t0))
+    ms_e2e = max(e2.elapsed_time(e3), 1000 * (time.perf_counter() - t0)) / e2e_steps
     st2 = q.stats()
 
-    ms_step = ms / args.steps
+    # parity: the image the e2e leg just exported against the digest of the unmodified reference core
+    gold = golden_digest(name, 1)
+    sha = hashlib.sha256(memoryview(img)).hexdigest()
+    parity = {"image_sha256": sha, "expected": gold["image_sha256"] if gold else None,
+              "match": bool(gold) and sha == gold["image_sha256"] and int(ndistinct) == gold["ndistinct"] and int(nelts) == gold["nelts"]
+              and int(rounds) == gold["denoise_rounds"],
+              "oracle": gold["made_by"] if gold else "no committed digest for this workload (tests/golden/digests.json)"}
+    if gold and not parity["match"]:
+        parity["expected_counters"] = {k: gold[k] for k in ("ndistinct", "nelts", "denoise_rounds")}
+        print("bench.py: PARITY FAILED on %s: %s" % (name, json.dumps(parity)), file=sys.stderr)
+
+    ms_step = ms / steps
     value = n_total / (ms_step / 1e3)
-    # roofline of the dominant phase (CUDA-event time per launch, accumulated inside libshq on its stream)
     table_bytes = q.nblocks * 89
-    a_ins = args.read_len / (args.read_len - args.k + 1) + 32 + 2 * table_bytes / n_total
-    phases = {k: stats[k] / args.steps for k in ("ms_hash_count", "ms_scatter", "ms_aggregate", "ms_merge", "ms_layout", "ms_denoise")}
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
-    dom = max(phases, key=phases.get)
-    alg = phase_bytes(dom, args, n_total, text.nbytes, ndistinct, table_bytes, rounds)
-    achieved = alg / (phases[dom] / 1e3) / 1e9
-    nl = PHASE_LAUNCHES[dom]
-    roofline = {"bound": "hbm", "kernel": PHASE_KERNEL[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": measured_traffic(PHASE_KERNEL[dom]), "peak_source": peak_src, "algorithmic_bytes_per_step": alg,
-                "algorithmic_bytes_per_launch": alg / nl, "launches_per_step": nl, "ms_per_launch": phases[dom] / nl,
-                "note": "integer/byte path bound by instruction issue and shared-memory latency, not by HBM (DESIGN.md 4); "
-                        "achieved = algorithmic bytes / CUDA-event time of the phase on the handle's stream",
-                "phase_ms_per_step": phases,
-                "pipeline": {"bytes_per_kmer": a_ins, "achieved": value * a_ins / 1e9, "frac": value * a_ins / 1e9 / peak,
-                             "note": "whole insert path against SURVEY 8(d) A_ins"}}
-    line = {"metric": "canonical k-mers inserted/sec", "value": value, "unit": "k-mers/s", "n_gpus": 1, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u64", "data": "synthetic", "config": config_dict(args, 1, p), "clocks": clocks,
-            "e2e": {"value": n_total / (ms_e2e / args.steps / 1e3), "unit": "k-mers/s", "h2d_bytes_per_step": int(st2["h2d_bytes"] // args.steps),
-                    "d2h_bytes_per_step": int(st2["d2h_bytes"] // args.steps), "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(stats["kernels_launched"]), "roofline": roofline,
-            "result": {"ndistinct": int(ndistinct), "nelts": int(nelts), "denoise_rounds": int(rounds), "kmers_per_step": int(n_total)}}
-    if args.unitigs:
-        line["unitig"] = bench_unitigs(args, shq, q, text, ends, h_ptr)
-    line["cpu_baseline"] = cpu_baseline(args, text, ends, p, n_total)
-    print(json.dumps(line))
+    a_ins = w["L"] / (w["L"] - K + 1) + 32 + 2 * table_bytes / n_total
+    line = {"metric": METRIC, "value": value, "unit": "k-mers/s", "n_gpus": 1, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic", "config": config_dict(w, 1, p, name), "clocks": clocks,
+            "e2e": {"value": n_total / (ms_e2e / 1e3), "unit": "k-mers/s", "h2d_bytes_per_step": int(st2["h2d_bytes"] // e2e_steps),
+                    "d2h_bytes_per_step": int(st2["d2h_bytes"] // e2e_steps), "ms_per_step": ms_e2e, "steps": e2e_steps},
+            "gpu_launches": int(stats["kernels_launched"]), "roofline": roofline(stats, steps, value, a_ins, table_bytes),
+            "result": {"ndistinct": int(ndistinct), "nelts": int(nelts), "denoise_rounds": int(rounds), "kmers_per_step": int(n_total),
+                       "batches_per_step": stats["batches"] / steps, "host_syncs_per_step": stats["host_syncs"] / steps,
+                       "bin_fallbacks": int(stats["bin_fallbacks"])},
+            "parity": parity}
+    if want_unitigs:
+        line["unitig"] = bench_unitigs(args, shq, q, text, ends, h_ptr, K)
+    if want_cpu:
+        from oracle import pyoracle as po
+        if po.ref() is None:
+            line["cpu_baseline"] = {"value": None, "unit": "k-mers/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
+        else:
+            cores = os.cpu_count() or 1
+            rate, secs, kmers, desc = cpu_sample(w, sp, p, args.cpu_seconds, cores, po)
+            line["cpu_baseline"] = {"value": rate, "unit": "k-mers/s", "cores": cores, "kind": "reference", "sample": desc}
+    q.close()
+    del h_text, img_t
+    torch.cuda.empty_cache()
+    return line
 
 
-def bench_unitigs(args, shq, q, text, ends, h_ptr):
+def bench_unitigs(args, shq, q, text, ends, h_ptr, K):
     """Second half of the BASELINE metric: seconds to build the unitig graph (Contiger) from the filter just
-    counted, reads given as host chunks; beside it the sequential CPU restatement on the same input (1 core)."""
-    import ctypes as C
+    counted, reads given as host chunks; beside it the sequential CPU restatement on a bounded sample."""
     L = shq.lib()
-    opts = shq.shq_unitig_opts(args.k, 2, 2, 1000000)
+    opts = shq.shq_unitig_opts(K, 2, 2, 1000000)
     best = None
     info = {}
-    for rep in range(2):
+    for rep in range(3):
         u = C.c_void_p()
         t0 = time.perf_counter()
         q._check(L.shq_unitigs_begin(q.h, C.byref(opts), C.byref(u)))
@@ -350,65 +367,43 @@ def bench_unitigs(args, shq, q, text, ends, h_ptr):
         L.shq_unitigs_free(u)
         best = dt if best is None else min(best, dt)
         info = {"n_unitigs": n.value, "total_bases": tot.value}
-    out = {"seconds": best, "unit": "s", "config": "Contiger -k %d -s 2 -x 2 -X 1000000 on the filter of this run, reads from pinned host chunks" % args.k}
+    out = {"seconds": best, "unit": "s", "config": "Contiger -k %d -s 2 -x 2 -X 1000000 on the filter of this run, reads from pinned host chunks" % K}
     out.update(info)
     if args.unitig_cpu:
         from oracle import pyoracle as po
         img = q.export()
         o = po.OracleCqf.from_bytes(img)
         t0 = time.perf_counter()
-        fa, nq = po.contiger_run(o, [text.tobytes()], args.k)
+        fa, nq = po.contiger_run(o, [text.tobytes()], K)
         out["cpu_baseline"] = {"seconds": time.perf_counter() - t0, "cores": 1, "kind": "port",
                                "sample": "whole read set, sequential restatement of Contiger over a hash-map CQF model",
                                "n_unitigs": len(po.parse_unitigs(fa)), "cqf_queries": int(nq)}
     return out
 
 
-PHASE_KERNEL = {"ms_hash_count": "roll_count_kernel", "ms_scatter": "roll_scatter_kernel", "ms_aggregate": "bin_aggregate_kernel",
-                "ms_merge": "merge_tiles_kernel", "ms_layout": "layout_scan_kernel + image_tiles_kernel", "ms_denoise": "denoise_tiles_kernel"}
-# launches of the phase's dominant kernel per step on the default workload (4 device batches; the aggregator runs once
-# more for the split at the mid-stream deNoise boundary)
-PHASE_LAUNCHES = {"ms_hash_count": 4, "ms_scatter": 4, "ms_aggregate": 5, "ms_merge": 10, "ms_layout": 1, "ms_denoise": 2}
-# (ms_hash_count is 0 on the default path: bins have a fixed capacity and the counting pass only runs as the exact fallback)
-
-
-def measured_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full capture
-    (profiles/r1_traffic.json, written by tools/ncu_summary.py from the same bench command); None if absent."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        return t.get(kernel)
-    except Exception:
-        return None
-
-
-def phase_bytes(phase, args, n_kmers, text_bytes, ndistinct, table_bytes, rounds):
-    """ALGORITHMIC bytes one step moves in each phase ('kernels and rooflines')."""
-    if phase == "ms_hash_count":
-        return text_bytes                                  # read every FASTQ byte once
-    if phase == "ms_scatter":
-        return text_bytes + 4 * n_kmers                    # re-read text, write one packed 32-bit word per k-mer
-    if phase == "ms_aggregate":
-        return 4 * n_kmers + 14 * 2 * ndistinct            # read packed words; write + compact (key,count,chunk)
-    if phase == "ms_merge":
-        return 2 * 12 * 2 * ndistinct
-    if phase == "ms_layout":
-        return 12 * ndistinct + table_bytes
-    return (rounds) * (2 * 12 * ndistinct)
-
-
-def cpu_baseline(args, text, ends, p, n_total):
-    from oracle import pyoracle as po
-    if po.ref() is None:
-        return {"value": None, "unit": "k-mers/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
-    cores = os.cpu_count() or 1
-    r = po.RefCqf(int(p.qb), int(p.hb))
-    secs, kmers, chunks, rounds = r.count_mt(text.ctypes.data, ends, args.k, cores, trigger=int(p.trigger), rounds=int(p.num_deNoise),
-                                             end_denoise=args.end_denoise, max_seconds=args.cpu_seconds)
-    r.close()
-    return {"value": kmers / secs, "unit": "k-mers/s", "cores": cores, "kind": "reference",
-            "sample": "first %d of %d chunks (%.3g of %.3g k-mers) in %.1f s; unmodified gqf.c+nthash.hpp, std::thread worker loop" % (
-                chunks, len(ends), kmers, n_total, secs)}
+def run_ours(args, rank, world, local_rank):
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- libshq has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        mg = importlib.import_module("sh-assembly_b200.multigpu")
+        return mg.bench_sharded(args, rank, world, local_rank, sys.modules[__name__])
+    line = run_workload(args, args.workload, args.steps, args.warmup, local_rank,
+                        want_unitigs=args.unitigs and args.workload.startswith("ecoli"), want_cpu=True)
+    if args.secondary and args.secondary != args.workload:
+        s_steps, s_warm = max(1, min(args.steps, 5)), max(3, min(args.warmup, 3))
+        sec = run_workload(args, args.secondary, s_steps, s_warm, local_rank, want_unitigs=bool(args.unitigs), want_cpu=False)
+        line["secondary"] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "config", "e2e", "roofline", "result", "parity")
+                             if k in sec}
+        if "unitig" in sec:
+            line["unitig"] = sec["unitig"]
+            line["unitig"]["workload"] = args.secondary
+    print(json.dumps(line))
+    if not line["parity"]["match"] and line["parity"]["expected"]:
+        raise SystemExit(3)
 
 
 def main():
@@ -417,17 +412,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--genome", type=int, default=4600000)
-    ap.add_argument("--cov", type=int, default=100)
-    ap.add_argument("--read-len", type=int, default=150)
-    ap.add_argument("--err", type=float, default=0.002)
-    ap.add_argument("-k", type=int, default=31)
-    ap.add_argument("--denoise", type=int, default=2)
-    ap.add_argument("--end-denoise", type=int, default=1)
-    ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--workload", default="celegans", choices=sorted(wl.WORKLOADS))
+    ap.add_argument("--secondary", default="ecoli", help="second workload reported under 'secondary' at N=1 ('' = none)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--e2e-steps", type=int, default=5, help="timed steps of the end-to-end leg (at most --steps)")
     ap.add_argument("--unitigs", type=int, default=1, help="also time the Contiger device path (unitig build seconds)")
-    ap.add_argument("--e2e-per-chunk-calls", type=int, default=0, help="e2e leg: one Python->C call per reference chunk instead of one for all")
     ap.add_argument("--unitig-cpu", type=int, default=0, help="also time the sequential CPU restatement of Contiger")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -258,6 +258,17 @@ typedef struct {
   double ms_hash_count, ms_scatter, ms_aggregate, ms_merge, ms_layout, ms_denoise; /* CUDA-event ms */
   uint64_t h2d_bytes, d2h_bytes;
   uint64_t bin_fallbacks;      /* batches whose one-pass binning overflowed a bin and were redone with exact offsets */
+  /* work counters per phase, for per-launch algorithmic bytes (bench.py roofline): launches of the phase's dominant
+     kernel and the units they processed, summed over the launches */
+  uint64_t scatter_launches, scatter_text_bytes, scatter_words;   /* roll_scatter_kernel: text read, words written */
+  uint64_t agg_launches, agg_words, agg_distinct;                 /* bin_aggregate_kernel: words read, distinct keys written */
+  uint64_t merge_launches, merge_in, merge_out;                   /* merge kernels: entries read (state + run), entries written */
+  uint64_t denoise_launches, denoise_entries;                     /* deNoise sweeps: state entries scanned */
+  uint64_t layout_launches, layout_entries;                       /* materialise: state entries laid out */
+  uint64_t host_syncs;                                            /* device->host scalar round trips */
+  uint64_t spec_rejected;      /* speculative merges of armed batches dropped because the deNoise trigger was crossed inside */
+  double ms_split;             /* second binning level (split_bins_kernel), CUDA-event ms */
+  uint64_t split_launches, split_words;
 } shq_stats;
 int shq_get_stats(shq_t h, shq_stats* out);
 int shq_reset_stats(shq_t h);

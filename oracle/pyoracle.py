@@ -181,6 +181,31 @@ def chunks(files, part_size=1 << 23):
         L.orc_chunker_free(h)
 
 
+def chunk_ends(addr, nbytes, part_size=1 << 23):
+    """Cumulative end offsets of the reference's chunks (fastq_read_parts, cqf/CQF_mt.h:735-816) over ONE in-memory
+    file at `addr`; only the sizes are kept, so this works on tens of GB."""
+    L = oracle()
+    bufs = (C.c_char_p * 1)(C.cast(C.c_void_p(addr), C.c_char_p))
+    lens = (C.c_size_t * 1)(nbytes)
+    h = L.orc_chunker_new(1, bufs, lens, part_size)
+    cap = part_size + 65536
+    buf = C.create_string_buffer(cap)
+    idx = C.c_int(0)
+    ends, off = [], 0
+    try:
+        while True:
+            n = L.orc_chunker_next(h, buf, cap, C.byref(idx))
+            if n == -1:
+                break
+            if n < 0:
+                raise ValueError("chunker error %d" % n)
+            off += n
+            ends.append(off)
+    finally:
+        L.orc_chunker_free(h)
+    return np.array(ends, np.uint64)
+
+
 class OracleCqf:
     def __init__(self, qb=None, hb=None, seed=2038074761, handle=None):
         self.L = oracle()
@@ -411,9 +436,11 @@ def canonical_unitig_set(fasta: str):
     return sorted(min(s, revcomp(s)) for _, s in parse_unitigs(fasta))
 
 
-def canonical_links(fasta: str):
+def canonical_links(fasta: str, stale=None):
     """Link structure up to renumbering/orientation: set of ((canon_seq_a, end_a), (canon_seq_b, end_b)) where
-    end is 'L' or 'R' of the canonical orientation."""
+    end is 'L' or 'R' of the canonical orientation.  Links whose target id is out of range are skipped and, if `stale`
+    is a list, appended to it: the reference's end-k-mer map keeps entries of contigs that lost a race and were cleared
+    (contig_assembly.cpp:935-1010 never removes them), so its FASTA can name ids that no unitig has."""
     us = parse_unitigs(fasta)
     canon = []
     for _, s in us:
@@ -425,6 +452,10 @@ def canonical_links(fasta: str):
             if f.startswith("L:"):
                 _, side, j, orient = f.split(":")
                 j = int(j)
+                if j >= len(us):
+                    if stale is not None:
+                        stale.append((i, f))
+                    continue
                 # this unitig's end: '+' side = its right end in stored orientation
                 a_end_right = (side == "+")
                 a = (canon[i][0], "R" if a_end_right == canon[i][1] else "L")

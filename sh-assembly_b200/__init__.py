@@ -31,7 +31,13 @@ class shq_stats(C.Structure):
     _fields_ = [("kernels_launched", C.c_uint64), ("batches", C.c_uint64), ("keys_hashed", C.c_uint64),
                 ("ms_hash_count", C.c_double), ("ms_scatter", C.c_double), ("ms_aggregate", C.c_double),
                 ("ms_merge", C.c_double), ("ms_layout", C.c_double), ("ms_denoise", C.c_double),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("bin_fallbacks", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("bin_fallbacks", C.c_uint64),
+                ("scatter_launches", C.c_uint64), ("scatter_text_bytes", C.c_uint64), ("scatter_words", C.c_uint64),
+                ("agg_launches", C.c_uint64), ("agg_words", C.c_uint64), ("agg_distinct", C.c_uint64),
+                ("merge_launches", C.c_uint64), ("merge_in", C.c_uint64), ("merge_out", C.c_uint64),
+                ("denoise_launches", C.c_uint64), ("denoise_entries", C.c_uint64),
+                ("layout_launches", C.c_uint64), ("layout_entries", C.c_uint64), ("host_syncs", C.c_uint64),
+                ("spec_rejected", C.c_uint64), ("ms_split", C.c_double), ("split_launches", C.c_uint64), ("split_words", C.c_uint64)]
 
 
 class shq_unitig_opts(C.Structure):

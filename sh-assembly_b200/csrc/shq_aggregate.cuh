@@ -11,24 +11,33 @@
 namespace shq {
 
 // ----------------------------------------------------- per-bin aggregation ---
-constexpr int kAggThreads = 1024;
+// One CTA per bin (or per key sub-range of a bin) streams the bin's 32-bit words through an ORDER-PRESERVING
+// open-addressing table in shared memory: the home slot of a key is a monotone function of the key (keys are ntHash
+// values, i.e. uniform), probing is linear and never wraps.  The occupied slots, read in slot order, are then sorted
+// except inside a cluster (a maximal run of occupied slots): every key of a cluster has its home inside that cluster, so
+// clusters are ordered among themselves, and a key's final place is the cluster's start plus the number of smaller
+// keys in its (short) cluster.  No bucket counters, no insertion-order list, no separate sort: counting the
+// duplicates and sorting the distinct keys are the same pass.  Two CTAs of 512 threads share an SM.
+constexpr int kAggThreads = 512;
 constexpr int kAggWarps = kAggThreads / 32;
-constexpr int kAggTable = 16384;         // open-addressing slots per CTA (one CTA of 32 warps per SM)
-constexpr int kAggMaxDistinct = 8192;    // per round (load factor <= 0.5)
-constexpr int kAggOrdCap = kAggMaxDistinct + kAggThreads;   // racing inserts may overshoot by < blockDim
-constexpr int kAggBuckets = 2048;        // bucket sort of the distinct keys
+constexpr int kAggHomes = 8192;          // home positions; even ones are used, so a key is looked up as a pair of slots
+constexpr int kAggPad = 256;             // slots behind the last home: probing never wraps around
+constexpr int kAggTable = kAggHomes + kAggPad;
+constexpr int kAggMaxProbe = kAggPad - 2;   // a longer probe sequence means skewed keys: restart with narrower key ranges
+constexpr int kAggMaxDistinct = 5000;    // what the host sizes the bins for (load factor 0.6)
+constexpr int kAggBuckets = 2048;        // upper bound of chunks per batch (first-chunk histograms)
 constexpr int kAggU = 8;                 // words per lane and warp tile
 constexpr int kAggWarpTile = 32 * kAggU; // a warp streams its share of the bin in tiles of 256 words
+constexpr int kAggSPT = (kAggTable + kAggThreads - 1) / kAggThreads;   // slots per thread in the compaction (17: odd, conflict free)
 constexpr uint32_t kAggEmpty = 0xFFFFFFFFu;
-// t_key, t_cnt (u32), t_chk (u16), bucket counters (u32), list of new slots (u16), then one region shared by the
-// per-warp pending lists (insert phase) and the slot order (sort phase)
+// t_key, t_cnt (u32) [, t_chk (u16)], then one region shared by the per-warp pending lists (insert phase) and the slot
+// order (sort phase) [, the sorted slot order (SPLIT only)]
+constexpr size_t kAggOrdBytes = ((size_t)kAggTable * 2 + 15) & ~(size_t)15;
 constexpr size_t kAggPendBytes = (size_t)kAggWarps * kAggWarpTile * 4;
-constexpr size_t kAggSmemBytes = (size_t)kAggTable * 10 + (size_t)kAggBuckets * 4 + (size_t)kAggOrdCap * 2 +
-                                 (kAggPendBytes > (size_t)kAggOrdCap * 2 ? kAggPendBytes : (size_t)kAggOrdCap * 2);
-
-// home slot: the first (even) slot of a pair.  Probing is linear from there, so a key sits in its home pair unless both
-// slots were taken by other keys; pass 1 looks at the whole pair with one 64-bit load.
-__device__ __forceinline__ uint32_t agg_hash(uint32_t k) { return ((k * 2654435761u) >> (32 - 13)) << 1; }
+constexpr size_t kAggShareBytes = kAggPendBytes > kAggOrdBytes ? kAggPendBytes : kAggOrdBytes;
+constexpr size_t agg_smem_bytes(bool chunk, bool split) {
+  return (size_t)kAggTable * 8 + (chunk ? kAggOrdBytes : 0) + kAggShareBytes + (split ? kAggOrdBytes : 0);
+}
 
 struct AggOut {
   uint64_t* keys; uint32_t* counts; uint16_t* chunk; uint32_t* n_out;   // run A (or the only run)
@@ -39,13 +48,18 @@ struct AggOut {
   const uint32_t* bin_end;  // optional: end of every bin (fixed-capacity bins); null = bin_off[p + 1]
   int fixed_bits;           // each bin is handled by 2^fixed_bits CTAs, one per key sub-range
   size_t sub_stride;        // outputs of sub-range s live at [s * sub_stride + bin_off[p] + i]
+  int direct;               // most words are first occurrences: insert straight away instead of probing first
 };
 
 struct AggTable {
-  uint32_t* key; uint32_t* cnt; uint16_t* chk; uint32_t* bkt; uint16_t* fresh;
-  uint32_t* ndist; volatile uint32_t* overflow; int* split_overflow;
-  uint32_t relmask; int bshift;       // bucket of a key: (key & relmask) >> bshift
+  uint32_t* key; uint32_t* cnt; uint16_t* chk;
+  volatile uint32_t* overflow; int* split_overflow;
+  uint32_t relmask; int hshift;       // home of a key: ((key & relmask) >> hshift, or << -hshift) << 1
 };
+__device__ __forceinline__ uint32_t agg_home(const AggTable& T, uint32_t kl) {
+  const uint32_t rel = kl & T.relmask;
+  return (T.hshift >= 0 ? (rel >> T.hshift) : (rel << (-T.hshift))) << 1;
+}
 
 // 16-bit minimum on a shared-memory half word (rarely taken: bins receive their words in chunk order)
 __device__ __forceinline__ void agg_chunk_min(uint16_t* chk, uint32_t h, uint32_t ch) {
@@ -84,14 +98,31 @@ __device__ __forceinline__ void agg_count(const AggTable& T, uint32_t h, uint32_
   if (CHUNK && !second) agg_chunk_min(T.chk, h, ch);
 }
 
-// Streams the bin through the shared-memory table.  Every warp works on its own tiles of 256 words:
-//   pass 1 (all lanes, no loop): one probe; a word whose key sits in its home slot is counted on the spot
-//           (the common case at 30-100x coverage), every other word is appended to the warp's pending list;
-//   pass 2 (dense over the pending list): the full insert -- linear probing, CAS on an empty slot.
+// find-or-insert by linear probing from the key's home; false (and the overflow flag) if the probe sequence gets too long
+__device__ __forceinline__ bool agg_place(const AggTable& T, uint32_t kl, uint32_t* slot) {
+  uint32_t h = agg_home(T, kl);
+  for (int pr = 0; pr < kAggMaxProbe; pr++, h++) {
+    const uint32_t cur = T.key[h];
+    if (cur == kl) { *slot = h; return true; }
+    if (cur == kAggEmpty) {
+      const uint32_t old = atomicCAS(&T.key[h], kAggEmpty, kl);
+      if (old == kAggEmpty || old == kl) { *slot = h; return true; }
+    }
+  }
+  *T.overflow = 1;
+  return false;
+}
+
+// Streams the bin through the table.  Every warp works on its own tiles of 256 words.
+//  DIRECT (most words are first occurrences, e.g. a batch of a large genome): find-or-insert per word.
+//  otherwise (30-100x coverage inside the batch):
+//   pass 1 (all lanes, no loop): one probe of the home pair; a word whose key sits there is counted on the spot,
+//           every other word is appended to the warp's pending list;
+//   pass 2 (dense over the pending list): find-or-insert.
 // Other warps may insert while a warp probes: a probe then sees either "empty" (-> pending -> found in pass 2)
 // or the key itself, both correct.  Compile-time flags strip everything a plain batch does not need:
 // FILT = chunk-range / key-sub-range filters, CHUNK = first-chunk minimum, SPLIT = two counters.
-template <bool SPLIT, bool CHUNK, bool FILT>
+template <bool SPLIT, bool CHUNK, bool FILT, bool DIRECT>
 __device__ __forceinline__ void agg_insert_pass(const uint32_t* __restrict__ packed, uint32_t beg, uint32_t end, int lb, uint32_t lowmask,
                                                 uint32_t chunk_lo, uint32_t chunk_hi, uint32_t cstar, int sub_bits, uint32_t r,
                                                 const AggTable& T, uint32_t* s_pend, uint32_t* occ1, uint32_t* occ2) {
@@ -116,7 +147,12 @@ __device__ __forceinline__ void agg_insert_pass(const uint32_t* __restrict__ pac
       }
       const bool second = SPLIT && ch > cstar;
       if (FILT || SPLIT) { my_occ2 += (live & second) ? 1u : 0u; my_occ += (live & !second) ? 1u : 0u; }
-      const uint32_t h0 = agg_hash(kl);
+      if (DIRECT) {
+        uint32_t h;
+        if (live && agg_place(T, kl, &h)) agg_count<SPLIT, CHUNK>(T, h, ch, second);
+        continue;
+      }
+      const uint32_t h0 = agg_home(T, kl);
       const uint2 pr = *reinterpret_cast<const uint2*>(&T.key[h0]);
       const bool hit = live & ((pr.x == kl) | (pr.y == kl));
       const uint32_t h = h0 + (pr.y == kl ? 1u : 0u);
@@ -131,6 +167,7 @@ __device__ __forceinline__ void agg_insert_pass(const uint32_t* __restrict__ pac
       smem_st_if(miss, &pend[np + __popc(m & ((1u << lane) - 1))], w);
       np += __popc(m);
     }
+    if (DIRECT) continue;
     __syncwarp();
     np = __shfl_sync(0xffffffffu, np, 0);
     // np is the same in every lane: a warp-uniform loop with one structured branch inside, so the warp
@@ -143,26 +180,8 @@ __device__ __forceinline__ void agg_insert_pass(const uint32_t* __restrict__ pac
         uint32_t ch = 0;
         if (CHUNK || SPLIT) ch = lb >= 32 ? 0 : (w >> lb);
         const bool second = SPLIT && ch > cstar;
-        uint32_t h = agg_hash(kl);
-        bool placed = true;
-        for (;;) {
-          uint32_t cur = T.key[h];
-          if (cur == kl) break;
-          if (cur == kAggEmpty) {
-            if (*T.overflow) { placed = false; break; }
-            uint32_t old = atomicCAS(&T.key[h], kAggEmpty, kl);
-            if (old == kAggEmpty) {
-              uint32_t idx = atomicAdd(T.ndist, 1u);
-              if (idx >= (uint32_t)kAggMaxDistinct) *T.overflow = 1;
-              if (idx < (uint32_t)kAggOrdCap) T.fresh[idx] = (uint16_t)h;
-              atomicAdd(&T.bkt[(kl & T.relmask) >> T.bshift], 1u);
-              break;
-            }
-            if (old == kl) break;
-          }
-          h = (h + 1) & (kAggTable - 1);
-        }
-        if (placed) agg_count<SPLIT, CHUNK>(T, h, ch, second);
+        uint32_t h;
+        if (agg_place(T, kl, &h)) agg_count<SPLIT, CHUNK>(T, h, ch, second);
       }
       __syncwarp();
     }
@@ -175,21 +194,22 @@ __device__ __forceinline__ void agg_insert_pass(const uint32_t* __restrict__ pac
 // Occurrences whose chunk is outside [chunk_lo, chunk_hi] are ignored.
 // SPLIT: occurrences with chunk <= cstar are counted in the low half of the counter, the others in the high
 // half, and two sorted runs come out of one pass (deNoise boundary inside a batch).
-// Output (sorted by key) goes to out[sub * sub_stride + bin_off[p] + i].  A sub-range with more than
-// kAggMaxDistinct distinct keys is re-streamed in 2^k narrower key ranges.
-template <bool SPLIT>
-__global__ void __launch_bounds__(kAggThreads, 1) bin_aggregate_kernel(
+// Output (sorted by key) goes to out[sub * sub_stride + bin_off[p] + i].  A sub-range whose probe sequences get too long
+// (more keys than the table is sized for, or skewed raw keys) is re-streamed in 2^k narrower key ranges.
+template <bool SPLIT, bool CHUNK>
+__global__ void __launch_bounds__(kAggThreads, 2) bin_aggregate_kernel(
     const uint32_t* __restrict__ packed, const uint32_t* __restrict__ bin_off, int lb, uint64_t key_lo,
     uint32_t chunk_lo, uint32_t chunk_hi, uint32_t cstar, AggOut o) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* t_key = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* t_cnt = t_key + kAggTable;
-  uint16_t* t_chk = reinterpret_cast<uint16_t*>(t_cnt + kAggTable);
-  uint32_t* s_bkt = reinterpret_cast<uint32_t*>(t_chk + kAggTable);
-  uint16_t* s_new = reinterpret_cast<uint16_t*>(s_bkt + kAggBuckets);    // table slots in order of insertion
-  uint32_t* s_pend = reinterpret_cast<uint32_t*>(s_new + kAggOrdCap);     // insert phase: per-warp pending lists
-  uint16_t* s_ord = reinterpret_cast<uint16_t*>(s_pend);                  // sort phase: table slots in key order
-  __shared__ uint32_t s_ndist, s_nocc, s_nocc2, s_overflow, s_na, s_nb;
+  unsigned char* nxt = reinterpret_cast<unsigned char*>(t_cnt + kAggTable);
+  uint16_t* t_chk = reinterpret_cast<uint16_t*>(nxt);
+  if (CHUNK) nxt += kAggOrdBytes;
+  uint32_t* s_pend = reinterpret_cast<uint32_t*>(nxt);                    // insert phase: per-warp pending lists
+  uint16_t* s_ord = reinterpret_cast<uint16_t*>(nxt);                     // sort phase: occupied slots in slot order (bit 15: cluster start)
+  uint16_t* s_fin = reinterpret_cast<uint16_t*>(nxt + kAggShareBytes);    // SPLIT: slots in key order
+  __shared__ uint32_t s_nocc, s_nocc2, s_overflow, s_na, s_nb;
 
   const uint32_t p = blockIdx.x >> o.fixed_bits;
   const uint32_t fsub = blockIdx.x & ((1u << o.fixed_bits) - 1);
@@ -198,7 +218,6 @@ __global__ void __launch_bounds__(kAggThreads, 1) bin_aggregate_kernel(
   if (o.bin_end) { const uint32_t e = o.bin_end[p]; end = e < end ? e : end; }     // never past the bin's own range
   const size_t obase = (size_t)fsub * o.sub_stride + beg;
   const uint32_t lowmask = lb >= 32 ? 0xFFFFFFFFu : ((1u << lb) - 1);
-  const bool want_chunk = !SPLIT && (o.chunk != nullptr || o.first_hist != nullptr);
   uint32_t written = 0, written2 = 0, occ_total = 0, occ_total2 = 0;
   int sub_bits = o.fixed_bits;   // key_low bits fixed per round: fixed_bits chosen by the grid, the rest by overflow restarts
   while (sub_bits < lb && ((end - beg) >> sub_bits) > 64u * kAggMaxDistinct) sub_bits++;
@@ -211,79 +230,72 @@ restart:
       uint4* c4 = reinterpret_cast<uint4*>(t_cnt);
       const uint4 e4 = make_uint4(kAggEmpty, kAggEmpty, kAggEmpty, kAggEmpty), z4 = make_uint4(0, 0, 0, 0);
       for (int i = threadIdx.x; i < kAggTable / 4; i += blockDim.x) { k4[i] = e4; c4[i] = z4; }
-      if (want_chunk) { uint4* h4 = reinterpret_cast<uint4*>(t_chk); for (int i = threadIdx.x; i < kAggTable / 8; i += blockDim.x) h4[i] = e4; }
-      for (int i = threadIdx.x; i < kAggBuckets; i += blockDim.x) s_bkt[i] = 0;
+      if (CHUNK) { uint4* h4 = reinterpret_cast<uint4*>(t_chk); for (int i = threadIdx.x; i < kAggTable / 8; i += blockDim.x) h4[i] = e4; }
     }
-    if (threadIdx.x == 0) { s_ndist = 0; s_nocc = 0; s_nocc2 = 0; s_overflow = 0; s_na = 0; s_nb = 0; }
+    if (threadIdx.x == 0) { s_nocc = 0; s_nocc2 = 0; s_overflow = 0; s_na = 0; s_nb = 0; }
     __syncthreads();
     const int bits = lb - sub_bits;                    // key_low bits that vary inside this round
-    const int bshift = bits > 11 ? bits - 11 : 0;
     const uint32_t relmask = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1);
     {
       const uint32_t max_chunk = lb >= 32 ? 0u : (0xFFFFFFFFu >> lb);
       const bool filt = sub_bits != 0 || chunk_lo != 0 || chunk_hi < max_chunk;   // sub_bits includes the grid's fixed bits
-      AggTable T{t_key, t_cnt, t_chk, s_bkt, s_new, &s_ndist, &s_overflow, o.split_overflow, relmask, bshift};
-#define SHQ_AGG_CALL(S, C, F) agg_insert_pass<S, C, F>(packed, beg, end, lb, lowmask, chunk_lo, chunk_hi, cstar, sub_bits, r, T, s_pend, &s_nocc, &s_nocc2)
-      if (SPLIT) { if (filt) SHQ_AGG_CALL(SPLIT, false, true); else SHQ_AGG_CALL(SPLIT, false, false); }   // no first chunks: the split is the last tracked round
-      else if (want_chunk) { if (filt) SHQ_AGG_CALL(false, true, true); else SHQ_AGG_CALL(false, true, false); }
-      else { if (filt) SHQ_AGG_CALL(false, false, true); else SHQ_AGG_CALL(false, false, false); }
+      AggTable T{t_key, t_cnt, t_chk, &s_overflow, o.split_overflow, relmask, bits - 12};
+#define SHQ_AGG_CALL(F, D) agg_insert_pass<SPLIT, CHUNK, F, D>(packed, beg, end, lb, lowmask, chunk_lo, chunk_hi, cstar, sub_bits, r, T, s_pend, &s_nocc, &s_nocc2)
+      if (o.direct) { if (filt) SHQ_AGG_CALL(true, true); else SHQ_AGG_CALL(false, true); }
+      else { if (filt) SHQ_AGG_CALL(true, false); else SHQ_AGG_CALL(false, false); }
 #undef SHQ_AGG_CALL
     }
     __syncthreads();
     if (*reinterpret_cast<volatile uint32_t*>(&s_overflow)) { sub_bits++; __syncthreads(); goto restart; }
-    // ---- bucket sort of the occupied slots by key (keys are hash values: ~nd/1024 keys per bucket); the bucket
-    // counters were filled while inserting, the occupied slots are listed in s_new
-    const uint32_t nd = s_ndist;
-    constexpr int PER = kAggBuckets / kAggThreads;
+    // ---- compaction: every thread owns kAggSPT consecutive slots; occupied slots are listed in slot order, the
+    // first slot of every cluster flagged
+    uint32_t nd;
     {
-      uint32_t v[PER], sum = 0;
+      const int s0 = threadIdx.x * kAggSPT;
+      uint32_t mask = 0;
 #pragma unroll
-      for (int j = 0; j < PER; j++) { v[j] = s_bkt[threadIdx.x * PER + j]; sum += v[j]; }
+      for (int j = 0; j < kAggSPT; j++) { const int sl = s0 + j; if (sl < kAggTable && t_key[sl] != kAggEmpty) mask |= 1u << j; }
+      const bool prev_occ = s0 > 0 && s0 <= kAggTable && t_key[s0 - 1] != kAggEmpty;
       uint32_t tot;
-      uint32_t ex = block_exclusive_scan<SumU32>(sum, &tot);
+      uint32_t ex = block_exclusive_scan<SumU32>((uint32_t)__popc(mask), &tot);     // ends with a barrier: the pending lists are dead
+      nd = tot;
 #pragma unroll
-      for (int j = 0; j < PER; j++) { s_bkt[threadIdx.x * PER + j] = ex; ex += v[j]; }
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) {
-      uint32_t slot = s_new[i];
-      uint32_t k = t_key[slot];
-      s_ord[atomicAdd(&s_bkt[(k & relmask) >> bshift], 1u)] = (uint16_t)slot;
-    }
-    __syncthreads();
-    // s_bkt[b] is now the END of bucket b.  Keys are distinct, so the place of a key inside its bucket is the number of
-    // smaller keys there: every thread ranks its own key (no serial insertion sort, no divergence beyond bucket size).
-    // The final order goes to s_new (its list of fresh slots is no longer needed).
-    for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) {
-      const uint16_t slot = s_ord[i];
-      const uint32_t k = t_key[slot];
-      const uint32_t b = (k & relmask) >> bshift;
-      const uint32_t lo = b ? s_bkt[b - 1] : 0, hi = s_bkt[b];
-      uint32_t rank = 0;
-      for (uint32_t x = lo; x < hi; x++) rank += t_key[s_ord[x]] < k ? 1u : 0u;
-      s_new[lo + rank] = slot;
-    }
-    __syncthreads();
-    const uint16_t* s_fin = s_new;
-    const bool do_hist = !SPLIT && o.first_hist != nullptr;
-    if (do_hist) {                                     // s_bkt is free now: per-CTA histogram of first chunks
-      for (int i = threadIdx.x; i < kAggBuckets; i += blockDim.x) s_bkt[i] = 0;
-      __syncthreads();
-    }
-    // ---- emit
-    if (!SPLIT) {
-      for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) {
-        uint32_t h = s_fin[i];
-        size_t oo = obase + written + i;
-        o.keys[oo] = key_lo + (((uint64_t)p << lb) | t_key[h]);
-        o.counts[oo] = t_cnt[h];
-        if (o.chunk) o.chunk[oo] = t_chk[h];
-        if (do_hist) atomicAdd(&s_bkt[t_chk[h] & (kAggBuckets - 1)], 1u);
+      for (int j = 0; j < kAggSPT; j++) {
+        if ((mask >> j) & 1u) {
+          const bool start = j == 0 ? !prev_occ : !((mask >> (j - 1)) & 1u);
+          s_ord[ex++] = (uint16_t)((s0 + j) | (start ? 0x8000 : 0));
+        }
       }
-    } else {
+    }
+    __syncthreads();
+    // ---- place inside the cluster = number of smaller keys there; emit in key order
+    for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) {
+      const uint32_t slot = s_ord[i] & 0x7FFFu;
+      const uint32_t k = t_key[slot];
+      uint32_t a = i;
+      while (!(s_ord[a] & 0x8000u)) a--;
+      uint32_t rank = 0;
+      for (uint32_t x = a; x < i; x++) rank += t_key[s_ord[x] & 0x7FFFu] < k ? 1u : 0u;
+      for (uint32_t x = i + 1; x < nd && !(s_ord[x] & 0x8000u); x++) rank += t_key[s_ord[x] & 0x7FFFu] < k ? 1u : 0u;
+      const uint32_t pos = a + rank;
+      if (SPLIT) { s_fin[pos] = (uint16_t)slot; continue; }
+      const size_t oo = obase + written + pos;
+      o.keys[oo] = key_lo + (((uint64_t)p << lb) | k);
+      o.counts[oo] = t_cnt[slot];
+      if (CHUNK) {
+        const uint32_t fc = t_chk[slot];
+        if (o.chunk) o.chunk[oo] = (uint16_t)fc;
+        if (o.first_hist) {                       // one atomic per (warp, chunk id): chunk ids of neighbouring keys repeat
+          const uint32_t peers = __match_any_sync(__activemask(), fc);
+          if ((uint32_t)(threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&o.first_hist[fc & (kAggBuckets - 1)], (uint32_t)__popc(peers));
+        }
+      }
+    }
+    if (SPLIT) {
+      __syncthreads();
       // two ordered runs: every thread owns a contiguous slice of the sorted keys; rank = number of earlier keys with a
       // non-zero half counter (two block scans per round in total)
-      constexpr int SL = kAggOrdCap / kAggThreads;
+      constexpr int SL = (kAggTable + kAggThreads - 1) / kAggThreads;
       const uint32_t per = (nd + blockDim.x - 1) / blockDim.x;
       uint32_t cs[SL];
       uint32_t fa = 0, fb = 0;
@@ -307,7 +319,6 @@ restart:
       if (threadIdx.x == 0) { s_na = ta; s_nb = tb; }
     }
     __syncthreads();
-    if (do_hist) for (int i = threadIdx.x; i < kAggBuckets; i += blockDim.x) { uint32_t v = s_bkt[i]; if (v) atomicAdd(&o.first_hist[i], v); }
     if (!SPLIT) written += nd; else { written += s_na; written2 += s_nb; }
     occ_total += s_nocc; occ_total2 += s_nocc2;
     __syncthreads();
@@ -436,16 +447,22 @@ __global__ void __launch_bounds__(kMergeThreads) merge_tiles_kernel(
 // Single-pass variant of the committing merge: no counting pass and no scan.  Tiles take a ticket (so a tile's
 // predecessors are always running or done), publish (flag | count) words and find their output offset by a
 // warp-wide decoupled look-back over the predecessors' words: flag 1 = the tile's own count, 2 = inclusive prefix.
+// HIST: B carries the first chunk of every key (Bchunk); chunk_hist[c] += keys of B that are NOT in A ("new" keys) whose
+// first chunk is c -- the by-product that lets the host find the deNoise boundary chunk of an armed batch.
 constexpr unsigned long long kLbValue = (1ULL << 62) - 1;
+template <bool HIST>
 __global__ void __launch_bounds__(kMergeThreads) merge_tiles_lookback_kernel(
     const uint64_t* __restrict__ A, const uint32_t* __restrict__ Ac, size_t na, const uint64_t* __restrict__ B,
     const uint32_t* __restrict__ Bc, size_t nb, const uint64_t* __restrict__ a_split, size_t ntiles,
     unsigned long long* status /* ntiles words, zeroed */, unsigned int* ticket /* zeroed */, uint64_t* __restrict__ out_keys,
-    uint32_t* __restrict__ out_counts, unsigned long long* __restrict__ n_out_total, int* __restrict__ err) {
+    uint32_t* __restrict__ out_counts, unsigned long long* __restrict__ n_out_total, int* __restrict__ err,
+    const uint16_t* __restrict__ Bchunk = nullptr, uint32_t* __restrict__ chunk_hist = nullptr) {
   __shared__ uint64_t s_a[kMergeTile + 2];
   __shared__ uint64_t s_b[kMergeTile + 2];
   __shared__ unsigned int s_tile;
   __shared__ unsigned long long s_prefix;
+  __shared__ uint32_t s_hist[HIST ? kMergeHistMax : 1];
+  if (HIST) for (int i = threadIdx.x; i < kMergeHistMax; i += blockDim.x) s_hist[i] = 0;
   if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
   __syncthreads();
   const size_t t = s_tile;
@@ -481,12 +498,16 @@ __global__ void __launch_bounds__(kMergeThreads) merge_tiles_lookback_kernel(
     } else {
       uint64_t k = s_b[bi];
       uint64_t preva = s_a[ai];
-      if (preva != k || (ai == 0 && a0 == 0)) { okey[nheads] = k; ocnt[nheads] = Bc[b0 + bi]; nheads++; }
+      if (preva != k || (ai == 0 && a0 == 0)) {
+        okey[nheads] = k; ocnt[nheads] = Bc[b0 + bi]; nheads++;
+        if (HIST) { const uint32_t ch = Bchunk[b0 + bi]; if (ch < (uint32_t)kMergeHistMax) atomicAdd(&s_hist[ch], 1u); else atomicAdd(&chunk_hist[ch], 1u); }
+      }
       bi++;
     }
   }
   uint32_t tot;
-  uint32_t rank = block_exclusive_scan<SumU32>(nheads, &tot);
+  uint32_t rank = block_exclusive_scan<SumU32>(nheads, &tot);      // ends with a barrier: s_hist is complete
+  if (HIST) for (int i = threadIdx.x; i < kMergeHistMax; i += blockDim.x) { const uint32_t v = s_hist[i]; if (v) atomicAdd(&chunk_hist[i], v); }
   if (threadIdx.x < 32) {               // warp 0: publish, then look back 32 predecessors at a time
     const int lane = threadIdx.x;
     unsigned long long excl = 0;

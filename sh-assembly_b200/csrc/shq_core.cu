@@ -47,6 +47,8 @@ struct shq_handle_s {
   // distinct keys per occurrence seen by the last full aggregation of a batch: sizes the bins (the aggregator's
   // shared-memory table holds kAggMaxDistinct keys); 1/8 until the first batch has been seen
   double distinct_ratio = 0.125;
+  bool ratio_seen = false;       // distinct_ratio comes from a batch of this job (not the prior)
+  double new_rate = -1.0;        // new keys per occurrence of the last committed run (< 0: none seen yet)
 
   // deNoise schedule
   uint64_t trigger = 0; uint32_t rounds_left = 0; bool end_denoise = false; uint32_t rounds_done = 0;
@@ -56,7 +58,8 @@ struct shq_handle_s {
   char* h_stage = nullptr; size_t h_stage_cap = 0, h_stage_fill = 0;
   std::vector<uint64_t> stage_chunk_ends;
   int stage_K = 0;
-  size_t max_batch_bytes = (size_t)1 << 28;
+  size_t max_batch_bytes = (size_t)1 << 28;   // first batches; later ones grow with the state (batch_target_bytes)
+  bool batch_fixed = false;                   // SHQ_MAX_BATCH_MB given: every batch at most that size
   // tunables (environment, read once per handle in init_handle)
   bool spec_bins = true;         // SHQ_SPEC_BINS=0 forces the two-pass (count, then scatter) binning
   bool merge_lookback = true;    // SHQ_MERGE_LOOKBACK=0: count pass + scan + write pass instead of the single-pass merge
@@ -68,6 +71,7 @@ struct shq_handle_s {
   struct PinBatch { int buf; size_t bytes; std::vector<uint64_t> ends; int K; cudaEvent_t ev; };
   cudaStream_t cstream = nullptr;
   DevBuf pin_buf[3];
+  size_t pin_cap = 0;
   int pin_cur = 0; size_t pin_fill = 0; std::vector<uint64_t> pin_ends; int pin_K = 0;
   std::vector<PinBatch> pin_queue;
 
@@ -77,7 +81,8 @@ struct shq_handle_s {
   DevBuf d_tmp_keys2, d_tmp_counts2, d_run2_keys, d_run2_counts;
   DevBuf d_run_keys, d_run_counts, d_run_chunk, d_split, d_heads, d_heads64, d_scan_scratch, d_misc;
   DevBuf d_pairs, d_pos, d_flags, d_keep, d_q_in, d_q_cnt, d_q_was;
-  DevBuf d_seg, d_fine, d_packed2, d_bases;   // multi-GPU second-level split
+  DevBuf d_seg, d_fine, d_fine_cur, d_packed2, d_bases;   // second binning level (single GPU: fine bins; multi-GPU: owner-side split)
+  int fine_bits_forced = -1;     // SHQ_FINE_BITS: force the second binning level (0 = off)
   // pull exchange: two fixed binned-word buffers that peers map through CUDA IPC, and the peers' buffers mapped here
   uint32_t* mg_send[2] = {nullptr, nullptr};
   size_t mg_cap_words = 0;
@@ -139,7 +144,7 @@ void check_err_flag(shq_handle_s* h) {
   int e = 0;
   SHQ_CUDA(cudaMemcpyAsync(&e, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   SHQ_CUDA(cudaStreamSynchronize(h->stream));
-  h->stats.d2h_bytes += 4;
+  h->stats.d2h_bytes += 4; h->stats.host_syncs++;
   if (e) {
     int z = 0;
     SHQ_CUDA(cudaMemcpyAsync(h->d_err, &z, sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -162,7 +167,7 @@ T read_scalar(shq_handle_s* h, const T* d) {
   T* p = (T*)pinned(h, sizeof(T));
   SHQ_CUDA(cudaMemcpyAsync(p, d, sizeof(T), cudaMemcpyDeviceToHost, h->stream));
   SHQ_CUDA(cudaStreamSynchronize(h->stream));
-  h->stats.d2h_bytes += sizeof(T);
+  h->stats.d2h_bytes += sizeof(T); h->stats.host_syncs++;
   return *p;
 }
 
@@ -173,7 +178,7 @@ void read_pair(shq_handle_s* h, const T* da, T* a, const U* db, U* b) {
   SHQ_CUDA(cudaMemcpyAsync(p, da, sizeof(T), cudaMemcpyDeviceToHost, h->stream));
   SHQ_CUDA(cudaMemcpyAsync(p + 16, db, sizeof(U), cudaMemcpyDeviceToHost, h->stream));
   SHQ_CUDA(cudaStreamSynchronize(h->stream));
-  h->stats.d2h_bytes += sizeof(T) + sizeof(U);
+  h->stats.d2h_bytes += sizeof(T) + sizeof(U); h->stats.host_syncs++;
   memcpy(a, p, sizeof(T)); memcpy(b, p + 16, sizeof(U));
 }
 
@@ -187,18 +192,23 @@ struct BatchBins {
   bool spec = false;            // fixed-capacity bins, no counting pass: bin p = [p * capbin, cursor[p])
   mutable bool spec_checked = false;
   uint32_t span = 0;            // words spanned by the binned array when spec
+  // the binned words, the bin offsets (n_bins + 1) and, for fixed-capacity bins, the end of every bin
+  const uint32_t* words = nullptr; const uint32_t* off = nullptr; const uint32_t* end = nullptr;
+  int fine_bits = 0;            // second binning level applied (n_bins and lb already include it)
 };
 struct BinOverflow {};          // a fixed-capacity bin overflowed: redo the batch with exact offsets
 
 struct Run { DevBuf* keys; DevBuf* counts; DevBuf* chunk; size_t n = 0; uint64_t occ = 0; };
 
 int pick_bin_bits(shq_handle_s* h, uint64_t est_keys, int chunk_bits_needed) {
-  // aim at ~64K occurrences per bin (8 per bin and scatter round) AND at most ~7000 distinct keys per bin (one round
-  // of the aggregator's table), 2^8 .. 2^12 bins, and (key bits below the bin) + chunk bits <= 32
+  // aim at ~64K occurrences per bin (8 per bin and scatter round) AND at most ~4500 distinct keys per bin (what the
+  // aggregator's table is sized for; with no batch seen yet every occurrence may be distinct), 2^8 .. 2^12 bins, and
+  // (key bits below the bin) + chunk bits <= 32.  More bins than 2^12 come from the second binning level.
   int shard_bits = 0; while ((1 << shard_bits) < h->nshards) shard_bits++;
   int local_bits = h->hb - shard_bits;
+  const double ratio = h->ratio_seen ? h->distinct_ratio : 1.0;
   int pb = 8;
-  while (pb < 12 && ((est_keys >> pb) > 65536 || (double)(est_keys >> pb) * h->distinct_ratio * 1.2 > 7000.0)) pb++;
+  while (pb < 12 && ((est_keys >> pb) > 65536 || (double)(est_keys >> pb) * ratio * 1.2 > 4500.0)) pb++;
   if (h->bin_bits) pb = h->bin_bits;
   if (pb > local_bits) pb = local_bits;
   // the low key bits share a 32-bit word with the chunk id, and 0xFFFFFFFF is the aggregator's empty marker
@@ -207,18 +217,55 @@ int pick_bin_bits(shq_handle_s* h, uint64_t est_keys, int chunk_bits_needed) {
   return pb;
 }
 
-// K1: newline index of a batch; returns the number of lines.
+// How much text the next device batch should hold.  Every batch pays one merge over the whole state, so batches grow
+// with the state (fewer, larger merges); a batch that contains a deNoise boundary is aggregated a second time, so they
+// start small; and the distinct keys of a batch must fit the aggregator's per-bin tables (~6500 keys x 4096 bins).
+size_t batch_target_bytes(shq_handle_s* h) {
+  if (h->batch_fixed) return h->max_batch_bytes;
+  // nothing known about this read set yet: a small first batch (< 5000 k-mers per bin, so every bin fits the aggregator's
+  // table even if all of them are distinct) tells how many distinct keys a batch holds
+  if (!h->ratio_seen) return (size_t)48 << 20;
+  double t = (double)h->max_batch_bytes * std::max(1.0, (double)h->n_state / 2.5e7);
+  t = std::min(t, 1024.0 * 1048576.0);
+  return (size_t)t;
+}
+// Chunks per batch while rounds are pending: the chunk id shares the 32-bit packed word with the low key bits
+size_t batch_chunk_cap(shq_handle_s* h) {
+  if (h->rounds_left == 0) return (size_t)1 << 20;
+  int shard_bits = 0; while ((1 << shard_bits) < h->nshards) shard_bits++;
+  const int local_bits = h->hb - shard_bits;
+  int bits = 32 - (local_bits - 12);                // with 4096 bins
+  if (bits < 3) bits = 32 - (local_bits - 13);      // 8192 bins
+  if (bits < 0) bits = 0;
+  if (bits > 10) bits = 10;                         // histogram arrays of the merge / aggregation kernels
+  return (size_t)1 << bits;
+}
+
+// Capacity of a fixed-size bin that is to receive `mean` words on average.  ntHash keys are uniform, but the c
+// occurrences of one k-mer inside the batch all land in the same bin, so the spread is sqrt(c * mean), not sqrt(mean);
+// c is taken from the distinct ratio of the previous batch (8 while nothing is known: the first batch is small).
+uint64_t bin_capacity(shq_handle_s* h, uint64_t mean) {
+  const double c = h->ratio_seen ? 1.0 / std::max(h->distinct_ratio, 1e-3) : 8.0;
+  const double slack = std::max((double)mean / 16.0, 6.0 * sqrt((double)mean * c)) + 1024.0;
+  return ((uint64_t)((double)mean + slack) + 7) & ~7ULL;
+}
+
+// K1: newline index of a batch; returns the number of lines.  d_text may start at any byte: the vector loads start at
+// the 16-byte boundary below it and the bytes in front of the batch are skipped (no staging copy of unaligned batches).
 uint32_t index_lines(shq_handle_s* h, const char* d_text, size_t n_text) {
   cudaStream_t st = h->stream;
   uint64_t& L = h->stats.kernels_launched;
-  unsigned ntiles = cdiv(n_text, kNlTile);
+  const uint32_t skip = (uint32_t)(reinterpret_cast<uintptr_t>(d_text) & 15);
+  const char* base = d_text - skip;
+  const size_t n_al = n_text + skip;
+  unsigned ntiles = cdiv(n_al, kNlTile);
   h->d_nl_tiles.reserve((size_t)(ntiles + 1) * 4);
-  nl_count_kernel<<<ntiles, kNlThreads, 0, st>>>(d_text, n_text, h->d_nl_tiles.as<uint32_t>()); L++;
+  nl_count_kernel<<<ntiles, kNlThreads, 0, st>>>(base, n_al, skip, h->d_nl_tiles.as<uint32_t>()); L++;
   h->d_misc.reserve(256);
   exclusive_scan_inplace<SumU32>(h->d_nl_tiles.as<uint32_t>(), ntiles, h->d_scan_scratch, st, h->d_misc.as<uint32_t>(), &L);
   uint32_t n_lines = read_scalar(h, h->d_misc.as<uint32_t>());
   h->d_nl_pos.reserve((size_t)(n_lines + 8) * 4);
-  nl_write_kernel<<<ntiles, kNlThreads, 0, st>>>(d_text, n_text, h->d_nl_tiles.as<uint32_t>(), h->d_nl_pos.as<uint32_t>()); L++;
+  nl_write_kernel<<<ntiles, kNlThreads, 0, st>>>(base, n_al, skip, h->d_nl_tiles.as<uint32_t>(), h->d_nl_pos.as<uint32_t>()); L++;
   return n_lines;
 }
 
@@ -235,7 +282,6 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
   if (from_text) {
     if (K < 1 || K > 1024) SHQ_FAIL(SHQ_ERR_ARG, "K=%d outside [1,1024]", K);
     if (n_text >= ((size_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "batch text of %zu bytes exceeds 4 GiB", n_text);
-    if (reinterpret_cast<uintptr_t>(d_text) & 15) SHQ_FAIL(SHQ_ERR_ARG, "device text must be 16-byte aligned");
     uint32_t n_lines = index_lines(h, d_text, n_text);
     h->d_chunk_ends.reserve((size_t)nchunks * 8 + 8);
     h->d_chunk_line_end.reserve((size_t)nchunks * 4 + 4);
@@ -285,7 +331,7 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
     unsigned long long n_ub = 0; int dev_err = 0;
     read_pair(h, d_ub, &n_ub, h->d_err, &dev_err);
     if (dev_err) { SHQ_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(int), st)); SHQ_FAIL(dev_err, "device reported: %s", shq_strerror(dev_err)); }
-    const uint64_t capbin = ((n_ub / (uint64_t)n_bins) * 17 / 16 + 2048 + 7) & ~7ULL;
+    const uint64_t capbin = bin_capacity(h, n_ub / (uint64_t)n_bins);
     const uint64_t span = capbin * (uint64_t)n_bins;
     const uint64_t round = (uint64_t)kScatThreads * 16;
     if (n_ub > 0 && span + round + 64 < ((uint64_t)1 << 32)) {
@@ -303,7 +349,36 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
       SHQ_CUDA(cudaGetLastError());
       bb->n_bins = n_bins; bb->lb = lb; bb->n_keys = (uint32_t)n_ub; bb->armed = armed; bb->nchunks = nchunks;
       bb->spec = true; bb->span = (uint32_t)span;
+      bb->words = h->d_packed.as<uint32_t>(); bb->off = h->d_binoff.as<uint32_t>(); bb->end = h->d_tot.as<uint32_t>(); bb->fine_bits = 0;
       h->stats.keys_hashed += n_ub;
+      h->stats.scatter_launches++; h->stats.scatter_text_bytes += n_text; h->stats.scatter_words += n_ub;
+      // second level: split every coarse bin into 2^fb fine bins when it would hold more distinct keys than the
+      // aggregator's table takes (the ratio of the previous batch is the estimate; a larger batch can only lower it)
+      {
+        const double ratio = h->ratio_seen ? std::min(1.0, h->distinct_ratio * 1.1) : 1.0;
+        const double est_d = (double)n_ub / (double)n_bins * ratio;
+        int fb = 0;
+        while (fb < 5 && lb - fb > 1 && est_d / (double)(1 << fb) > 5500.0) fb++;
+        if (h->fine_bits_forced >= 0) fb = std::min(h->fine_bits_forced, std::min(5, lb - 1));
+        const uint64_t n_fine = (uint64_t)n_bins << fb;
+        const uint64_t capfine = bin_capacity(h, n_ub / n_fine);
+        const uint64_t span2 = capfine * n_fine;
+        if (fb > 0 && span2 + kSplitTile + 64 < ((uint64_t)1 << 32)) {
+          Phase ph2(h, &h->stats.ms_split);
+          h->d_packed2.reserve((size_t)(span2 + kSplitTile + 64) * 4);
+          h->d_fine.reserve((size_t)(n_fine + 2) * 4); h->d_fine_cur.reserve((size_t)(n_fine + 2) * 4);
+          int* d_ovf2 = h->d_misc.as<int>() + 24;
+          SHQ_CUDA(cudaMemsetAsync(d_ovf2, 0, 4, st));
+          fine_bin_offsets_kernel<<<cdiv(n_fine + 1, 256), 256, 0, st>>>(h->d_fine.as<uint32_t>(), h->d_fine_cur.as<uint32_t>(), (uint32_t)n_fine, (uint32_t)capfine); L++;
+          int parts = 1; while (n_bins * parts < 8 * kNumSMs) parts *= 2;
+          split_bins_kernel<<<n_bins * parts, kSplitThreads, 0, st>>>(h->d_packed.as<uint32_t>(), h->d_binoff.as<uint32_t>(), h->d_tot.as<uint32_t>(), parts, lb, fb,
+                                                                    h->d_fine_cur.as<uint32_t>(), (uint32_t)capfine, (uint32_t)span2, d_ovf2, h->d_packed2.as<uint32_t>()); L++;
+          SHQ_CUDA(cudaGetLastError());
+          h->stats.split_launches++; h->stats.split_words += n_ub;
+          bb->n_bins = (int)n_fine; bb->lb = lb - fb; bb->span = (uint32_t)span2; bb->fine_bits = fb;
+          bb->words = h->d_packed2.as<uint32_t>(); bb->off = h->d_fine.as<uint32_t>(); bb->end = h->d_fine_cur.as<uint32_t>();
+        }
+      }
       return;
     }
   }
@@ -352,7 +427,9 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
   SHQ_CUDA(cudaGetLastError());
   bb->n_bins = n_bins; bb->lb = lb; bb->n_keys = n_keys; bb->armed = armed; bb->nchunks = nchunks;
   bb->spec = false; bb->span = 0;
+  bb->words = h->d_packed.as<uint32_t>(); bb->off = h->d_binoff.as<uint32_t>(); bb->end = nullptr; bb->fine_bits = 0;
   h->stats.keys_hashed += n_keys;
+  h->stats.scatter_launches++; h->stats.scatter_text_bytes += from_text ? n_text : n_keys_in * 8; h->stats.scatter_words += n_keys;
 }
 
 // Aggregate the binned batch (chunks [clo, chi]) into dense sorted run(s).
@@ -360,7 +437,7 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
 //  first_hist (host vector, may be null): histogram of the first chunk of every distinct key.
 // Returns false if the split counters overflowed (caller falls back to two plain passes).
 bool aggregate_bins(shq_handle_s* h, const BatchBins& bb, uint32_t clo, uint32_t chi, bool split, uint32_t cstar, Run* A, Run* B,
-                    std::vector<uint32_t>* first_hist) {
+                    std::vector<uint32_t>* first_hist, bool track = false) {
   cudaStream_t st = h->stream;
   uint64_t& L = h->stats.kernels_launched;
   Phase ph(h, &h->stats.ms_aggregate);
@@ -372,7 +449,8 @@ bool aggregate_bins(shq_handle_s* h, const BatchBins& bb, uint32_t clo, uint32_t
     while (fixed_bits < 4 && fixed_bits < bb.lb && per_bin / (double)(1 << fixed_bits) > 0.9 * kAggMaxDistinct) fixed_bits++; }
   const size_t S = (size_t)1 << fixed_bits;
   h->d_tmp_keys.reserve(cap * 8 * S); h->d_tmp_counts.reserve(cap * 4 * S);
-  if (bb.armed) h->d_tmp_chunk.reserve(cap * 2 * S);
+  const bool chunks = track || first_hist != nullptr;     // first chunk of every key wanted
+  if (chunks) h->d_tmp_chunk.reserve(cap * 2 * S);
   if (split) { h->d_tmp_keys2.reserve(cap * 8 * S); h->d_tmp_counts2.reserve(cap * 4 * S); }
   const size_t nb = (size_t)bb.n_bins * S;          // (bin, sub-range) groups
   h->d_nout.reserve((nb + 1) * 4 * 4);           // n_out, n_out2, occ, occ2
@@ -385,30 +463,32 @@ bool aggregate_bins(shq_handle_s* h, const BatchBins& bb, uint32_t clo, uint32_t
   uint32_t* d_fh = nullptr;
   if (first_hist) {
     if (bb.nchunks > kAggBuckets) SHQ_FAIL(SHQ_ERR_ARG, "too many chunks in one batch (max %d)", kAggBuckets);
-    h->d_chunk_hist.reserve((size_t)kAggBuckets * 4);
+    h->d_chunk_hist.reserve((size_t)(kMergeHistMax + kAggBuckets) * 4);
     d_fh = h->d_chunk_hist.as<uint32_t>();
     SHQ_CUDA(cudaMemsetAsync(d_fh, 0, (size_t)kAggBuckets * 4, st));
   }
   AggOut o{};
-  o.keys = h->d_tmp_keys.as<uint64_t>(); o.counts = h->d_tmp_counts.as<uint32_t>(); o.chunk = bb.armed ? h->d_tmp_chunk.as<uint16_t>() : nullptr;
+  o.keys = h->d_tmp_keys.as<uint64_t>(); o.counts = h->d_tmp_counts.as<uint32_t>(); o.chunk = chunks ? h->d_tmp_chunk.as<uint16_t>() : nullptr;
   o.n_out = n_out; o.keys2 = split ? h->d_tmp_keys2.as<uint64_t>() : nullptr; o.counts2 = split ? h->d_tmp_counts2.as<uint32_t>() : nullptr;
   o.n_out2 = n_out2; o.occ_out = occ; o.occ_out2 = occ2; o.first_hist = d_fh; o.split_overflow = d_ovf;
   o.fixed_bits = fixed_bits; o.sub_stride = cap;
-  o.bin_end = bb.spec ? h->d_tot.as<uint32_t>() : nullptr;
-  if (split) {
-    SHQ_CUDA(cudaFuncSetAttribute(bin_aggregate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggSmemBytes));
-    bin_aggregate_kernel<true><<<(unsigned)nb, kAggThreads, kAggSmemBytes, st>>>(h->d_packed.as<uint32_t>(), h->d_binoff.as<uint32_t>(), bb.lb, h->key_lo,
-                                                                             clo, chi, cstar, o);
-  } else {
-    SHQ_CUDA(cudaFuncSetAttribute(bin_aggregate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAggSmemBytes));
-    bin_aggregate_kernel<false><<<(unsigned)nb, kAggThreads, kAggSmemBytes, st>>>(h->d_packed.as<uint32_t>(), h->d_binoff.as<uint32_t>(), bb.lb, h->key_lo,
-                                                                              clo, chi, cstar, o);
-  }
+  o.bin_end = bb.end;
+  // most words of the batch are first occurrences (a batch of a large genome covers it less than once): insert directly
+  o.direct = (h->ratio_seen ? h->distinct_ratio : 1.0) > 0.3 ? 1 : 0;
+#define SHQ_AGG_LAUNCH(SP, CH) do { \
+    const size_t smem = agg_smem_bytes(CH, SP); \
+    SHQ_CUDA(cudaFuncSetAttribute(bin_aggregate_kernel<SP, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    bin_aggregate_kernel<SP, CH><<<(unsigned)nb, kAggThreads, smem, st>>>(bb.words, bb.off, bb.lb, h->key_lo, clo, chi, cstar, o); } while (0)
+  if (split) SHQ_AGG_LAUNCH(true, false);
+  else if (chunks) SHQ_AGG_LAUNCH(false, true);
+  else SHQ_AGG_LAUNCH(false, false);
+#undef SHQ_AGG_LAUNCH
   L++;
-  if (bb.spec && !bb.spec_checked) {   // did every bin fit its fixed range?  (read once per binned batch)
+  if (bb.spec && !bb.spec_checked) {   // did every bin (of both levels) fit its fixed range?  (read once per binned batch)
     bb.spec_checked = true;
-    int* d_bovf = h->d_misc.as<int>() + 20;
-    if (read_scalar(h, d_bovf)) throw BinOverflow{};
+    int o1 = 0, o2 = 0;
+    read_pair(h, h->d_misc.as<int>() + 20, &o1, h->d_misc.as<int>() + 24, &o2);
+    if (o1 || (bb.fine_bits && o2)) throw BinOverflow{};
   }
   if (split && read_scalar(h, d_ovf)) return false;
   auto finish = [&](Run* R, uint32_t* nout, uint32_t* dense, uint32_t* occs, const uint64_t* tk, const uint32_t* tc, const uint16_t* tch) {
@@ -419,14 +499,15 @@ bool aggregate_bins(shq_handle_s* h, const BatchBins& bb, uint32_t clo, uint32_t
     read_pair(h, dense + nb, &nd, h->d_misc.as<uint32_t>(), &oc);
     R->keys->reserve((size_t)(nd + 4) * 8); R->counts->reserve((size_t)(nd + 4) * 4);
     if (tch) R->chunk->reserve((size_t)(nd + 4) * 2);
-    compact_bins_kernel<<<(unsigned)nb, 256, 0, st>>>(h->d_binoff.as<uint32_t>(), dense, nout, fixed_bits, cap, tk, tc, tch, R->keys->as<uint64_t>(),
+    compact_bins_kernel<<<(unsigned)nb, 256, 0, st>>>(bb.off, dense, nout, fixed_bits, cap, tk, tc, tch, R->keys->as<uint64_t>(),
                                                   R->counts->as<uint32_t>(), tch ? R->chunk->as<uint16_t>() : nullptr); L++;
     R->n = nd; R->occ = oc;
   };
   finish(A, n_out, doff, occ, o.keys, o.counts, o.chunk);
   if (split) finish(B, n_out2, doff2, occ2, o.keys2, o.counts2, nullptr);
+  h->stats.agg_launches++; h->stats.agg_words += (uint64_t)bb.n_keys << fixed_bits; h->stats.agg_distinct += A->n + (split ? B->n : 0);
   if (!split && clo == 0 && (chi == 0xFFFFFFFFu || chi + 1 >= (uint32_t)bb.nchunks) && A->occ > (uint64_t)bb.n_bins * 64)
-    h->distinct_ratio = (double)A->n / (double)A->occ;       // whole batch seen: the next one is sized by it
+    { h->distinct_ratio = (double)A->n / (double)A->occ; h->ratio_seen = true; }   // whole batch seen: the next one is sized by it
   if (first_hist) {
     uint32_t* p = (uint32_t*)pinned(h, (size_t)bb.nchunks * 4);
     SHQ_CUDA(cudaMemcpyAsync(p, d_fh, (size_t)bb.nchunks * 4, cudaMemcpyDeviceToHost, st));
@@ -437,14 +518,97 @@ bool aggregate_bins(shq_handle_s* h, const BatchBins& bb, uint32_t clo, uint32_t
   return true;
 }
 
-// Merge run R into the state.  If chunk_hist_host != null the per-chunk histogram of NEW keys is returned;
-// commit=false stops after that (boundary search).  Returns the number of new keys.
-uint64_t merge_run(shq_handle_s* h, const Run& R, int nchunks, std::vector<uint32_t>* chunk_hist_host, bool commit) {
+// Merge run R with the state into the SHADOW copy (st_keys2 / st_counts2); the state itself stays untouched until
+// commit_shadow().  Returns the number of entries of the merged state.  chunk_hist_host (optional; R must carry first
+// chunks): per-chunk histogram of the keys of R that are NEW, a by-product of the same pass.  An armed batch is merged
+// speculatively this way: if the deNoise trigger turns out to be crossed inside the batch the shadow is simply dropped.
+uint64_t merge_shadow(shq_handle_s* h, const Run& R, int nchunks, std::vector<uint32_t>* chunk_hist_host) {
   cudaStream_t st = h->stream;
   uint64_t& L = h->stats.kernels_launched;
   Phase ph(h, &h->stats.ms_merge);
-  size_t na = h->n_state, nb = R.n;
-  if (na == 0 && commit && !chunk_hist_host) {          // first run: it simply becomes the state
+  const size_t na = h->n_state, nb = R.n;
+  const size_t total = na + nb;
+  if (chunk_hist_host) chunk_hist_host->assign((size_t)nchunks, 0);
+  h->st_keys2.reserve((total + 4) * 8); h->st_counts2.reserve((total + 4) * 4);
+  if (total == 0) return 0;
+  const uint16_t* Bch = (chunk_hist_host && R.chunk) ? R.chunk->as<uint16_t>() : nullptr;
+  if (chunk_hist_host && !Bch) SHQ_FAIL(SHQ_ERR_STATE, "merge: first chunks requested from a run without them");
+  if (chunk_hist_host && nchunks > kMergeHistMax) SHQ_FAIL(SHQ_ERR_ARG, "too many chunks in one batch (max %d)", kMergeHistMax);
+  const size_t ntiles = (total + kMergeTile - 1) / kMergeTile;
+  h->d_split.reserve((ntiles + 2) * 8);
+  h->d_heads.reserve((ntiles + 2) * 4);
+  h->d_heads64.reserve((ntiles + 4) * 8);
+  const uint64_t* A = h->st_keys.as<uint64_t>(); const uint32_t* Ac = h->st_counts.as<uint32_t>();
+  const uint64_t* Bk = R.keys->as<uint64_t>(); const uint32_t* Bc = R.counts->as<uint32_t>();
+  uint32_t* d_hist = nullptr;
+  if (chunk_hist_host) {
+    h->d_chunk_hist.reserve((size_t)(kMergeHistMax + kAggBuckets) * 4);
+    d_hist = h->d_chunk_hist.as<uint32_t>();
+    SHQ_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)kMergeHistMax * 4, st));
+  }
+  merge_partition_kernel<<<cdiv(ntiles + 1, 128), 128, 0, st>>>(A, na, Bk, nb, h->d_split.as<uint64_t>(), ntiles); L++;
+  uint64_t n_out = 0;
+  if (h->merge_lookback && total < ((uint64_t)1 << 32)) {
+    // single pass: the output can hold na + nb entries at most; the real size comes back with the last tile
+    unsigned long long* status = h->d_heads64.as<unsigned long long>();
+    unsigned long long* d_nout = status + ntiles; unsigned int* ticket = (unsigned int*)(status + ntiles + 1);
+    SHQ_CUDA(cudaMemsetAsync(status, 0, (ntiles + 2) * 8, st));
+    if (d_hist)
+      merge_tiles_lookback_kernel<true><<<(unsigned)ntiles, kMergeThreads, 0, st>>>(A, Ac, na, Bk, Bc, nb, h->d_split.as<uint64_t>(), ntiles, status, ticket,
+                                                                                h->st_keys2.as<uint64_t>(), h->st_counts2.as<uint32_t>(), d_nout, h->d_err, Bch, d_hist);
+    else
+      merge_tiles_lookback_kernel<false><<<(unsigned)ntiles, kMergeThreads, 0, st>>>(A, Ac, na, Bk, Bc, nb, h->d_split.as<uint64_t>(), ntiles, status, ticket,
+                                                                                 h->st_keys2.as<uint64_t>(), h->st_counts2.as<uint32_t>(), d_nout, h->d_err);
+    L++;
+    SHQ_CUDA(cudaGetLastError());
+    if (d_hist) {      // total and histogram with one round trip
+      char* pz = (char*)pinned(h, 16 + (size_t)nchunks * 4);
+      SHQ_CUDA(cudaMemcpyAsync(pz, d_nout, 8, cudaMemcpyDeviceToHost, st));
+      SHQ_CUDA(cudaMemcpyAsync(pz + 16, d_hist, (size_t)nchunks * 4, cudaMemcpyDeviceToHost, st));
+      SHQ_CUDA(cudaStreamSynchronize(st));
+      h->stats.d2h_bytes += 8 + (size_t)nchunks * 4; h->stats.host_syncs++;
+      memcpy(&n_out, pz, 8);
+      chunk_hist_host->assign((uint32_t*)(pz + 16), (uint32_t*)(pz + 16) + nchunks);
+    } else {
+      n_out = read_scalar(h, (const uint64_t*)d_nout);
+    }
+  } else {
+    // count pass + scan + write pass (SHQ_MERGE_LOOKBACK=0, or a state of 2^32 entries and more)
+    merge_tiles_kernel<false><<<(unsigned)ntiles, kMergeThreads, 0, st>>>(A, Ac, na, Bk, Bc, Bch, nb, h->d_split.as<uint64_t>(),
+                                                                         h->d_heads.as<uint32_t>(), nullptr, nullptr, nullptr, d_hist, h->d_err); L++;
+    widen_u32_kernel<<<cdiv(ntiles, 256), 256, 0, st>>>(h->d_heads.as<uint32_t>(), h->d_heads64.as<uint64_t>(), ntiles); L++;
+    exclusive_scan_inplace<SumU64>(h->d_heads64.as<uint64_t>(), ntiles, h->d_scan_scratch, st, h->d_heads64.as<uint64_t>() + ntiles, &L);
+    n_out = read_scalar(h, h->d_heads64.as<uint64_t>() + ntiles);
+    if (chunk_hist_host) {
+      uint32_t* pz = (uint32_t*)pinned(h, (size_t)nchunks * 4);
+      SHQ_CUDA(cudaMemcpyAsync(pz, d_hist, (size_t)nchunks * 4, cudaMemcpyDeviceToHost, st));
+      SHQ_CUDA(cudaStreamSynchronize(st));
+      h->stats.d2h_bytes += (size_t)nchunks * 4; h->stats.host_syncs++;
+      chunk_hist_host->assign(pz, pz + nchunks);
+    }
+    if (n_out >= ((uint64_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "more than 2^32 distinct keys in one shard");
+    merge_tiles_kernel<true><<<(unsigned)ntiles, kMergeThreads, 0, st>>>(A, Ac, na, Bk, Bc, nullptr, nb, h->d_split.as<uint64_t>(), nullptr,
+                                                                        h->d_heads64.as<uint64_t>(), h->st_keys2.as<uint64_t>(),
+                                                                        h->st_counts2.as<uint32_t>(), nullptr, h->d_err); L++;
+    SHQ_CUDA(cudaGetLastError());
+  }
+  h->stats.merge_launches++; h->stats.merge_in += total; h->stats.merge_out += n_out;
+  return n_out;
+}
+// the shadow becomes the state; returns the number of new keys
+uint64_t commit_shadow(shq_handle_s* h, uint64_t n_out) {
+  const uint64_t n_new = n_out - h->n_state;
+  std::swap(h->st_keys, h->st_keys2); std::swap(h->st_counts, h->st_counts2);
+  h->n_state = n_out;
+  h->image_valid = false;
+  return n_new;
+}
+// merge + commit; the very first run simply becomes the state
+uint64_t merge_run(shq_handle_s* h, const Run& R) {
+  if (h->n_state == 0) {
+    cudaStream_t st = h->stream;
+    Phase ph(h, &h->stats.ms_merge);
+    const size_t nb = R.n;
     h->st_keys.reserve((nb + 4) * 8); h->st_counts.reserve((nb + 4) * 4);
     if (nb) {
       SHQ_CUDA(cudaMemcpyAsync(h->st_keys.p, R.keys->p, nb * 8, cudaMemcpyDeviceToDevice, st));
@@ -453,62 +617,7 @@ uint64_t merge_run(shq_handle_s* h, const Run& R, int nchunks, std::vector<uint3
     h->n_state = nb; h->image_valid = false;
     return nb;
   }
-  size_t total = na + nb;
-  size_t ntiles = (total + kMergeTile - 1) / kMergeTile;
-  if (ntiles == 0) { if (chunk_hist_host) chunk_hist_host->assign(nchunks, 0); return 0; }
-  h->d_split.reserve((ntiles + 2) * 8);
-  h->d_heads.reserve((ntiles + 2) * 4);
-  h->d_heads64.reserve((ntiles + 2) * 8);
-  const uint64_t* A = h->st_keys.as<uint64_t>(); const uint32_t* Ac = h->st_counts.as<uint32_t>();
-  const uint64_t* Bk = R.keys->as<uint64_t>(); const uint32_t* Bc = R.counts->as<uint32_t>();
-  const uint16_t* Bch = (chunk_hist_host && R.chunk) ? R.chunk->as<uint16_t>() : nullptr;
-  merge_partition_kernel<<<cdiv(ntiles + 1, 128), 128, 0, st>>>(A, na, Bk, nb, h->d_split.as<uint64_t>(), ntiles); L++;
-  if (h->merge_lookback && commit && !chunk_hist_host && total < ((uint64_t)1 << 32)) {
-    // single pass: the output can hold na + nb entries at most; the real size comes back with the last tile
-    h->st_keys2.reserve((total + 4) * 8); h->st_counts2.reserve((total + 4) * 4);
-    h->d_heads64.reserve((ntiles + 4) * 8);
-    unsigned long long* status = h->d_heads64.as<unsigned long long>();
-    unsigned long long* d_nout = status + ntiles; unsigned int* ticket = (unsigned int*)(status + ntiles + 1);
-    SHQ_CUDA(cudaMemsetAsync(status, 0, (ntiles + 2) * 8, st));
-    merge_tiles_lookback_kernel<<<(unsigned)ntiles, kMergeThreads, 0, st>>>(A, Ac, na, Bk, Bc, nb, h->d_split.as<uint64_t>(), ntiles, status, ticket,
-                                                                        h->st_keys2.as<uint64_t>(), h->st_counts2.as<uint32_t>(), d_nout, h->d_err); L++;
-    SHQ_CUDA(cudaGetLastError());
-    uint64_t n_out = read_scalar(h, (const uint64_t*)d_nout);
-    std::swap(h->st_keys, h->st_keys2); std::swap(h->st_counts, h->st_counts2);
-    h->n_state = n_out;
-    h->image_valid = false;
-    return n_out - na;
-  }
-  uint32_t* d_hist = nullptr;
-  if (chunk_hist_host) {
-    h->d_chunk_hist.reserve((size_t)(nchunks + 1) * 4 + (size_t)kAggBuckets * 4);
-    d_hist = h->d_chunk_hist.as<uint32_t>();
-    SHQ_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)(nchunks + 1) * 4, st));
-  }
-  merge_tiles_kernel<false><<<(unsigned)ntiles, kMergeThreads, 0, st>>>(A, Ac, na, Bk, Bc, Bch, nb, h->d_split.as<uint64_t>(),
-                                                                       h->d_heads.as<uint32_t>(), nullptr, nullptr, nullptr, d_hist, h->d_err); L++;
-  widen_u32_kernel<<<cdiv(ntiles, 256), 256, 0, st>>>(h->d_heads.as<uint32_t>(), h->d_heads64.as<uint64_t>(), ntiles); L++;
-  exclusive_scan_inplace<SumU64>(h->d_heads64.as<uint64_t>(), ntiles, h->d_scan_scratch, st, h->d_heads64.as<uint64_t>() + ntiles, &L);
-  uint64_t n_out = read_scalar(h, h->d_heads64.as<uint64_t>() + ntiles);
-  if (chunk_hist_host) {
-    uint32_t* p = (uint32_t*)pinned(h, (size_t)nchunks * 4);
-    SHQ_CUDA(cudaMemcpyAsync(p, d_hist, (size_t)nchunks * 4, cudaMemcpyDeviceToHost, st));
-    SHQ_CUDA(cudaStreamSynchronize(st));
-    h->stats.d2h_bytes += (size_t)nchunks * 4;
-    chunk_hist_host->assign(p, p + nchunks);
-  }
-  uint64_t n_new = n_out - na;
-  if (!commit) return n_new;
-  if (n_out >= ((uint64_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "more than 2^32 distinct keys in one shard");
-  h->st_keys2.reserve((n_out + 4) * 8); h->st_counts2.reserve((n_out + 4) * 4);
-  merge_tiles_kernel<true><<<(unsigned)ntiles, kMergeThreads, 0, st>>>(A, Ac, na, Bk, Bc, nullptr, nb, h->d_split.as<uint64_t>(), nullptr,
-                                                                      h->d_heads64.as<uint64_t>(), h->st_keys2.as<uint64_t>(),
-                                                                      h->st_counts2.as<uint32_t>(), nullptr, h->d_err); L++;
-  SHQ_CUDA(cudaGetLastError());
-  std::swap(h->st_keys, h->st_keys2); std::swap(h->st_counts, h->st_counts2);
-  h->n_state = n_out;
-  h->image_valid = false;
-  return n_new;
+  return commit_shadow(h, merge_shadow(h, R, 1, nullptr));
 }
 
 // positions of every state entry in the canonical layout -> d_pos; returns one past the last used slot.
@@ -542,6 +651,7 @@ void materialise(shq_handle_s* h) {
   cudaStream_t st = h->stream;
   uint64_t& L = h->stats.kernels_launched;
   Phase ph(h, &h->stats.ms_layout);
+  h->stats.layout_launches++; h->stats.layout_entries += h->n_state;
   uint64_t used = compute_positions(h);
   if (used > h->xnslots) SHQ_FAIL(SHQ_ERR_CAPACITY, "filter over-full: layout needs slot %llu but xnslots = %llu",
                                   (unsigned long long)used, (unsigned long long)h->xnslots);
@@ -602,6 +712,7 @@ uint64_t denoise_round_impl(shq_handle_s* h) {
   Phase ph(h, &h->stats.ms_denoise);
   size_t n = h->n_state;
   h->rounds_done++;
+  h->stats.denoise_launches++; h->stats.denoise_entries += n;
   if (n == 0) return 0;
   if (h->nshards != 1) SHQ_FAIL(SHQ_ERR_STATE, "deNoise on a sharded handle is driven by the multi-GPU layer");
   compute_positions(h);
@@ -630,6 +741,14 @@ uint64_t denoise_round_impl(shq_handle_s* h) {
 }
 
 // One device batch: text of nchunks reference chunks (or raw keys) -> state, honouring the schedule.
+//
+// While deNoise rounds are pending ("armed") a round must fire after the first reference chunk that leaves
+// ndistinct >= trigger (t = 1 rule, cqf/CQF_mt.h:837).  ndistinct only grows inside a batch, so the batch is first merged
+// SPECULATIVELY into the shadow state as a whole: if the merged state stays below the trigger nothing can have fired and
+// the shadow is committed -- an armed batch then costs exactly what an unarmed one does.  Only the (at most `rounds`)
+// batches that contain a boundary pay for locating it: an aggregation that tracks the first chunk of every key, the
+// histogram of new keys per chunk out of the same merge pass, and one split aggregation around the boundary chunk c*.
+// When the new-key rate of the previous batch predicts a crossing, the tracking aggregation is run straight away.
 void process_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_t* chunk_ends, int nchunks, int K,
                    const uint64_t* d_keys, size_t n_keys_in) {
   ensure_state(h);
@@ -651,44 +770,75 @@ void process_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uin
   Run A{&h->d_run_keys, &h->d_run_counts, &h->d_run_chunk}, B{&h->d_run2_keys, &h->d_run2_counts, nullptr};
   uint32_t clo = 0;
   const uint32_t last = (uint32_t)(nchunks > 0 ? nchunks - 1 : 0);
+  const uint32_t all = 0xFFFFFFFFu;
+  // committed keys / occurrences of a run
+  auto account = [&](uint64_t n_new, const Run& R) {
+    h->ndistinct += n_new; h->nelts += R.occ;
+    if (R.occ > 4096) h->new_rate = (double)n_new / (double)R.occ;
+  };
+  auto fire = [&]() { h->rounds_left--; denoise_round(h); };
+  // does the new-key rate seen so far predict that chunks [clo, last] reach the trigger?  (no history: assume they might)
+  auto predicts_crossing = [&]() {
+    const double frac = (double)(last - clo + 1) / (double)(last + 1);
+    const double rate = h->new_rate < 0 ? 1.0 : h->new_rate * 1.15;
+    return (double)h->ndistinct + rate * frac * (double)bb.n_keys + 65536.0 >= (double)h->trigger;
+  };
   for (;;) try {
-    bool track = armed && h->rounds_left > 0;
-    if (!track) {
-      aggregate_bins(h, bb, clo, armed ? last : 0xFFFFFFFFu, false, 0, &A, nullptr, nullptr);
-      uint64_t n_new = merge_run(h, A, nchunks, nullptr, true);
-      h->ndistinct += n_new; h->nelts += A.occ;
+    if (!(armed && h->rounds_left > 0)) {                 // no round pending: chunks [clo, last] go in as one run
+      aggregate_bins(h, bb, clo, armed ? last : all, false, 0, &A, nullptr, nullptr);
+      account(merge_run(h, A), A);
       break;
     }
-    // find the first chunk c* >= clo after which ndistinct >= trigger (t=1 rule, CQF_mt.h:837)
+    if (h->ndistinct >= h->trigger) {                     // still over the trigger after a sweep: the next chunk fires again
+      aggregate_bins(h, bb, clo, clo, false, 0, &A, nullptr, nullptr);
+      account(merge_run(h, A), A);
+      fire();
+      if (clo == last) break;
+      clo++;
+      continue;
+    }
+    if (!predicts_crossing()) {
+      aggregate_bins(h, bb, clo, last, false, 0, &A, nullptr, nullptr);
+      if (h->n_state == 0) {                              // nothing to merge with: the run's size is the new ndistinct
+        if (h->ndistinct + A.n < h->trigger) { account(merge_run(h, A), A); break; }
+      } else {
+        const uint64_t n_out = merge_shadow(h, A, 1, nullptr);
+        if (h->ndistinct + (n_out - h->n_state) < h->trigger) { account(commit_shadow(h, n_out), A); break; }
+      }
+      h->stats.spec_rejected++;                           // the trigger is crossed inside [clo, last]: locate the chunk below
+    }
+    // first chunk of every key + histogram of the new keys per chunk -> c* = first chunk after which ndistinct >= trigger
     std::vector<uint32_t> hist;
+    uint64_t n_out = 0;
     const bool empty_state = h->n_state == 0;
-    const bool agg_hist = empty_state && nchunks <= kAggBuckets;
-    aggregate_bins(h, bb, clo, last, false, 0, &A, nullptr, agg_hist ? &hist : nullptr);
-    if (!agg_hist) merge_run(h, A, nchunks, &hist, false);
+    aggregate_bins(h, bb, clo, last, false, 0, &A, nullptr, empty_state ? &hist : nullptr, true);
+    if (!empty_state) n_out = merge_shadow(h, A, nchunks, &hist);
     uint64_t nd = h->ndistinct; int cstar = -1;
     for (uint32_t c = clo; c <= last; c++) { nd += hist[c]; if (nd >= h->trigger) { cstar = (int)c; break; } }
-    if (cstar < 0 || (uint32_t)cstar == last) {
-      uint64_t n_new = merge_run(h, A, nchunks, nullptr, true);
-      h->ndistinct += n_new; h->nelts += A.occ;
-      if (cstar >= 0) { h->rounds_left--; denoise_round(h); }
+    if (cstar < 0 || (uint32_t)cstar == last) {           // no boundary, or at the very end of the batch: the merge stands
+      account(empty_state ? merge_run(h, A) : commit_shadow(h, n_out), A);
+      if (cstar >= 0) fire();
       break;
     }
-    // boundary inside the batch.  Last scheduled round: one split pass yields both sides.
-    if (h->rounds_left == 1 && aggregate_bins(h, bb, clo, last, true, (uint32_t)cstar, &A, &B, nullptr)) {
-      uint64_t n_new = merge_run(h, A, nchunks, nullptr, true);
-      h->ndistinct += n_new; h->nelts += A.occ;
-      h->rounds_left--;
-      denoise_round(h);
-      n_new = merge_run(h, B, nchunks, nullptr, true);
-      h->ndistinct += n_new; h->nelts += B.occ;
-      break;
+    // boundary inside the batch: one split pass yields both sides of c*
+    if (aggregate_bins(h, bb, clo, last, true, (uint32_t)cstar, &A, &B, nullptr)) {
+      account(merge_run(h, A), A);
+      fire();
+      if (h->rounds_left == 0 || h->ndistinct >= h->trigger) {
+        if (h->rounds_left == 0) { account(merge_run(h, B), B); break; }
+      } else {
+        // the rest of the batch may hold the next boundary only if it crosses the trigger again: speculate once more
+        const uint64_t n2 = merge_shadow(h, B, 1, nullptr);
+        if (h->ndistinct + (n2 - h->n_state) < h->trigger) { account(commit_shadow(h, n2), B); break; }
+        h->stats.spec_rejected++;
+      }
+      clo = (uint32_t)cstar + 1;                          // replay chunks (c*, last] with tracking
+      continue;
     }
-    // general case: commit chunks [clo, c*], sweep, then replay the rest of the batch with tracking
+    // split counters overflowed (a key seen >= 65535 times on one side): two plain passes instead
     aggregate_bins(h, bb, clo, (uint32_t)cstar, false, 0, &A, nullptr, nullptr);
-    uint64_t n_new = merge_run(h, A, nchunks, nullptr, true);
-    h->ndistinct += n_new; h->nelts += A.occ;
-    h->rounds_left--;
-    denoise_round(h);
+    account(merge_run(h, A), A);
+    fire();
     clo = (uint32_t)cstar + 1;
   } catch (const BinOverflow&) {
     // thrown by the first aggregation of a one-pass batch, before anything was merged: bin again with exact offsets
@@ -707,11 +857,6 @@ size_t hash_to_keylist(shq_handle_s* h, const char* d_text, size_t n, int K, uin
   if (K < 1 || K > 1024) SHQ_FAIL(SHQ_ERR_ARG, "K=%d outside [1,1024]", K);
   if (n >= ((size_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "text of %zu bytes exceeds 4 GiB per call", n);
   const char* src = d_text;
-  if (reinterpret_cast<uintptr_t>(src) & 15) {
-    h->d_text.reserve(n + 64);
-    SHQ_CUDA(cudaMemcpyAsync(h->d_text.p, src, n, cudaMemcpyDeviceToDevice, st));
-    src = h->d_text.as<char>();
-  }
   uint32_t n_lines = index_lines(h, src, n);
   if (n_lines & 3) SHQ_FAIL(SHQ_ERR_MALFORMED, "text holds %u lines, not a multiple of 4", n_lines);
   uint32_t n_reads = n_lines / 4;
@@ -795,8 +940,9 @@ void init_handle(shq_handle_s* h, int qb, int hb, uint32_t seed, int device, int
   if (qb < 1 || qb > 40 || hb - qb != 8) SHQ_FAIL(SHQ_ERR_ARG, "need 1 <= qb <= 40 and hb - qb == 8 (got qb=%d hb=%d)", qb, hb);
   if (nshards < 1 || (nshards & (nshards - 1)) || shard < 0 || shard >= nshards || (1 << qb) < nshards * 64)
     SHQ_FAIL(SHQ_ERR_ARG, "bad shard %d of %d", shard, nshards);
-  if (const char* e = getenv("SHQ_MAX_BATCH_MB")) { long v = atol(e); if (v >= 1 && v <= 3072) h->max_batch_bytes = (size_t)v << 20; }
+  if (const char* e = getenv("SHQ_MAX_BATCH_MB")) { long v = atol(e); if (v >= 1 && v <= 3072) { h->max_batch_bytes = (size_t)v << 20; h->batch_fixed = true; } }
   if (const char* e = getenv("SHQ_SPEC_BINS")) h->spec_bins = atoi(e) != 0;
+  if (const char* e = getenv("SHQ_FINE_BITS")) { int v = atoi(e); if (v >= 0 && v <= 5) h->fine_bits_forced = v; }
   if (const char* e = getenv("SHQ_MERGE_LOOKBACK")) h->merge_lookback = atoi(e) != 0;
   if (const char* e = getenv("SHQ_BIN_BITS")) { int v = atoi(e); if (v >= 4 && v <= 13) h->bin_bits = v; }
   SHQ_CUDA(cudaSetDevice(device));
@@ -822,7 +968,7 @@ void free_handle(shq_handle_s* h) {
                     &h->d_binoff, &h->d_packed, &h->d_tmp_keys, &h->d_tmp_counts, &h->d_tmp_chunk, &h->d_nout, &h->d_occ,
                     &h->d_dense_off, &h->d_run_keys, &h->d_run_counts, &h->d_run_chunk, &h->d_split, &h->d_heads, &h->d_heads64,
                     &h->d_scan_scratch, &h->d_misc, &h->d_pairs, &h->d_pos, &h->d_flags, &h->d_keep, &h->d_q_in, &h->d_q_cnt, &h->d_q_was,
-                    &h->d_tmp_keys2, &h->d_tmp_counts2, &h->d_run2_keys, &h->d_run2_counts, &h->d_seg, &h->d_fine, &h->d_packed2, &h->d_bases};
+                    &h->d_tmp_keys2, &h->d_tmp_counts2, &h->d_run2_keys, &h->d_run2_counts, &h->d_seg, &h->d_fine, &h->d_fine_cur, &h->d_packed2, &h->d_bases};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : h->pin_buf) b.release();
   for (void* p : h->mg_opened) cudaIpcCloseMemHandle(p);
@@ -907,7 +1053,7 @@ int shq_reset(shq_t h) {
   if (!h) return SHQ_ERR_ARG;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  h->n_state = 0; h->ndistinct = 0; h->nelts = 0;
+  h->n_state = 0; h->ndistinct = 0; h->nelts = 0; h->new_rate = -1.0; h->ratio_seen = false; h->distinct_ratio = 0.125;
   h->image_valid = false; h->image_only = false;
   h->trigger = 0; h->rounds_left = 0; h->end_denoise = false; h->rounds_done = 0; h->finished = false;
   h->h_stage_fill = 0; h->stage_chunk_ends.clear();
@@ -933,10 +1079,12 @@ int shq_insert_fastq_chunk(shq_t h, const char* text, size_t n, int K) {
   if (!h || (!text && n)) return SHQ_ERR_ARG;
   struct { const char* text; size_t n; int K; } args{text, n, K};
   SHQ_API_BEGIN(h)
-    if ((h->h_stage_fill || !h->stage_chunk_ends.empty()) && (h->stage_K != a.K || h->h_stage_fill + a.n > h->max_batch_bytes)) flush_stage(h);
-    if (a.n > h->max_batch_bytes && a.n >= ((size_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "chunk too large");
+    const size_t target = batch_target_bytes(h);
+    if ((h->h_stage_fill || !h->stage_chunk_ends.empty()) &&
+        (h->stage_K != a.K || h->h_stage_fill + a.n > target || h->stage_chunk_ends.size() >= batch_chunk_cap(h))) flush_stage(h);
+    if (a.n >= ((size_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "chunk too large");
     if (h->h_stage_cap < h->h_stage_fill + a.n) {
-      size_t want = std::max(h->h_stage_fill + a.n, std::min(h->max_batch_bytes, std::max((size_t)64 << 20, 2 * h->h_stage_cap)));
+      size_t want = std::max(h->h_stage_fill + a.n, std::min(target, std::max((size_t)64 << 20, 2 * h->h_stage_cap)));
       char* p = nullptr;
       SHQ_CUDA(cudaMallocHost((void**)&p, want));
       if (h->h_stage_fill) memcpy(p, h->h_stage, h->h_stage_fill);
@@ -964,13 +1112,15 @@ int shq_insert_fastq_pinned(shq_t h, const char* text, size_t n, int K) {
     }
     if (a.n >= ((size_t)1 << 31)) SHQ_FAIL(SHQ_ERR_ARG, "chunk too large");
     if (!h->cstream) SHQ_CUDA(cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking));
-    size_t cap = std::max(h->max_batch_bytes, a.n);
-    if (h->pin_fill && (h->pin_K != a.K || h->pin_fill + a.n > cap)) {
+    if (h->pin_fill && (h->pin_K != a.K || h->pin_fill + a.n > h->pin_cap || h->pin_ends.size() >= batch_chunk_cap(h))) {
       pin_seal(h);
       // keep one sealed batch in flight behind the one being processed: its copies overlap the compute
       while (h->pin_queue.size() >= 2) pin_process_oldest(h);
     }
-    h->pin_buf[h->pin_cur].reserve(cap + 64);
+    if (h->pin_fill == 0) {      // a new batch: its size is fixed now (the buffer must not move under copies in flight)
+      h->pin_cap = std::max(batch_target_bytes(h), a.n);
+      h->pin_buf[h->pin_cur].reserve(h->pin_cap + 64);
+    }
     // 16-byte alignment of every batch start holds because each batch starts at offset 0 of its buffer
     SHQ_CUDA(cudaMemcpyAsync(h->pin_buf[h->pin_cur].as<char>() + h->pin_fill, a.text, a.n, cudaMemcpyHostToDevice, h->cstream));
     h->stats.h2d_bytes += a.n;
@@ -1001,16 +1151,12 @@ int shq_insert_fastq_device(shq_t h, const char* d_text, size_t n, const uint64_
     while (c0 < a.nc) {
       uint64_t base = c0 ? a.ce[c0 - 1] : 0;
       size_t c1 = c0;
-      while (c1 < a.nc && a.ce[c1] - base <= h->max_batch_bytes) c1++;
+      const size_t target = batch_target_bytes(h), cmax = batch_chunk_cap(h);
+      while (c1 < a.nc && a.ce[c1] - base <= target && c1 - c0 < cmax) c1++;
       if (c1 == c0) c1 = c0 + 1;
       std::vector<uint64_t> ends(a.ce + c0, a.ce + c1);
       for (auto& e : ends) e -= base;
-      const char* src = a.t + base;
-      if (reinterpret_cast<uintptr_t>(src) & 15) {   // vector loads need 16-byte alignment: stage a device copy
-        h->d_text.reserve(ends.back() + 64);
-        SHQ_CUDA(cudaMemcpyAsync(h->d_text.p, src, ends.back(), cudaMemcpyDeviceToDevice, h->stream));
-        src = h->d_text.as<char>();
-      }
+      const char* src = a.t + base;          // any byte offset: the line index copes with unaligned batch starts
       process_batch(h, src, ends.back(), ends.data(), (int)ends.size(), a.K, nullptr, 0);
       c0 = c1;
     }
@@ -1368,11 +1514,6 @@ int shq_mg_bin_fastq_device(shq_t h, const char* d_text, size_t n, int K, int co
     *a.nw = 0; *a.w = nullptr; *a.o = nullptr;
     if (a.n == 0) return;
     const char* src = a.t;
-    if (reinterpret_cast<uintptr_t>(src) & 15) {
-      h->d_text.reserve(a.n + 64);
-      SHQ_CUDA(cudaMemcpyAsync(h->d_text.p, src, a.n, cudaMemcpyDeviceToDevice, h->stream));
-      src = h->d_text.as<char>();
-    }
     uint64_t end = a.n;
     BatchBins bb;
     bin_batch(h, src, a.n, &end, 1, a.K, nullptr, 0, false, &bb, a.cb);
@@ -1426,10 +1567,11 @@ int shq_mg_insert_binned(shq_t h, const uint32_t* d_recv, const uint64_t* seg_st
       SHQ_CUDA(cudaGetLastError());
     }
     bb.n_bins = nfine; bb.lb = lbf; bb.n_keys = (uint32_t)a.n; bb.armed = false; bb.nchunks = 1;
+    bb.words = h->d_packed.as<uint32_t>(); bb.off = h->d_binoff.as<uint32_t>(); bb.end = nullptr;
     Run A{&h->d_run_keys, &h->d_run_counts, &h->d_run_chunk};
     aggregate_bins(h, bb, 0, 0xFFFFFFFFu, false, 0, &A, nullptr, nullptr);
     if (A.occ != a.n) SHQ_FAIL(SHQ_ERR_STATE, "exchange batch: %llu words aggregated, %zu received", (unsigned long long)A.occ, a.n);
-    uint64_t n_new = merge_run(h, A, 1, nullptr, true);
+    uint64_t n_new = merge_run(h, A);
     h->ndistinct += n_new; h->nelts += A.occ;
     check_err_flag(h);
   SHQ_API_END
@@ -1496,11 +1638,6 @@ int shq_mg_bin_local(shq_t h, const char* d_text, size_t n, int K, int parity, u
     if (a.K < 1 || a.K > 1024) SHQ_FAIL(SHQ_ERR_ARG, "K=%d outside [1,1024]", a.K);
     if (a.n >= ((size_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "batch text of %zu bytes exceeds 4 GiB", a.n);
     const char* src = a.t;
-    if (reinterpret_cast<uintptr_t>(src) & 15) {
-      h->d_text.reserve(a.n + 64);
-      SHQ_CUDA(cudaMemcpyAsync(h->d_text.p, src, a.n, cudaMemcpyDeviceToDevice, st));
-      src = h->d_text.as<char>();
-    }
     uint32_t n_lines = index_lines(h, src, a.n);
     h->d_chunk_ends.reserve(16); h->d_chunk_line_end.reserve(16);
     uint64_t end = a.n;
@@ -1580,10 +1717,11 @@ int shq_mg_insert_pull(shq_t h, const uint32_t* d_all_fine_hist, int parity) {
     }
     BatchBins bb;
     bb.n_bins = F; bb.lb = lbf; bb.n_keys = (uint32_t)n; bb.armed = false; bb.nchunks = 1;
+    bb.words = h->d_packed.as<uint32_t>(); bb.off = h->d_binoff.as<uint32_t>(); bb.end = nullptr;
     Run A{&h->d_run_keys, &h->d_run_counts, &h->d_run_chunk};
     aggregate_bins(h, bb, 0, 0xFFFFFFFFu, false, 0, &A, nullptr, nullptr);
     if (A.occ != n) SHQ_FAIL(SHQ_ERR_STATE, "exchange batch: %llu words aggregated, %llu expected", (unsigned long long)A.occ, (unsigned long long)n);
-    uint64_t n_new = merge_run(h, A, 1, nullptr, true);
+    uint64_t n_new = merge_run(h, A);
     h->ndistinct += n_new; h->nelts += A.occ;
     check_err_flag(h);
   SHQ_API_END

@@ -156,4 +156,81 @@ __global__ void __launch_bounds__(kSplitThreads) resplit_kernel(const uint32_t* 
   }
 }
 
+// ---- second binning level on ONE GPU ------------------------------------------------------------------------------
+// A device batch is binned by the hashing pass into <= 4096 coarse bins (roll_scatter_kernel keeps three words per
+// bin in shared memory).  When a coarse bin would hold more distinct keys than the aggregator's table -- large batches
+// of a large genome, where almost every k-mer of a batch is distinct -- every coarse bin is split once more into 2^fb
+// fine bins: a counting sort of 4096-word tiles in shared memory, one global reservation per (tile, fine bin), the tile
+// written out linearly.  Both levels use fixed-capacity bins (ntHash keys are uniform); a reservation that does not fit
+// raises *ovf and lands in a scratch area, and the host falls back to the coarse bins.
+// in:  coarse bin c = [bin_off[c], bin_end[c]);  word = chunk << lb | low lb key bits
+// out: fine bin (c << fb | sub) = [f * capfine, fine_cursor[f]);  word = chunk << (lb - fb) | low (lb - fb) key bits
+__global__ void __launch_bounds__(kSplitThreads) split_bins_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ bin_off,
+                                                                   const uint32_t* __restrict__ bin_end, int parts, int lb, int fb,
+                                                                   uint32_t* __restrict__ fine_cursor, uint32_t capfine, uint32_t slack_base,
+                                                                   int* __restrict__ ovf, uint32_t* __restrict__ out) {
+  __shared__ uint32_t s_cnt[kSplitMaxFine], s_off[kSplitMaxFine + 1], s_delta[kSplitMaxFine];
+  __shared__ uint32_t s_sorted[kSplitTile];
+  __shared__ uint8_t s_sub[kSplitTile];
+  const int c = blockIdx.x / parts, part = blockIdx.x % parts;
+  const int nfine = 1 << fb;
+  const int lbf = lb - fb;
+  const uint32_t cmask = lb >= 32 ? 0xFFFFFFFFu : ((1u << lb) - 1), fmask = (1u << lbf) - 1;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x < nfine) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t beg = bin_off[c];
+  uint32_t end = bin_off[c + 1];
+  { const uint32_t e = bin_end[c]; end = e < end ? e : end; }
+  for (uint32_t t0 = beg + (uint32_t)part * kSplitTile; t0 < end; t0 += (uint32_t)parts * kSplitTile) {
+    uint32_t w[kSplitItems], sr[kSplitItems];     // word, sub << 16 | rank inside (tile, sub)
+#pragma unroll
+    for (int i = 0; i < kSplitItems; i++) {        // all loads of the tile are in flight before the first is used
+      const uint32_t idx = t0 + (uint32_t)i * kSplitThreads + threadIdx.x;
+      w[i] = idx < end ? __ldg(&in[idx]) : 0xFFFFFFFFu;
+    }
+#pragma unroll
+    for (int i = 0; i < kSplitItems; i++) {
+      const uint32_t idx = t0 + (uint32_t)i * kSplitThreads + threadIdx.x;
+      const uint32_t sub = (w[i] & cmask) >> lbf;
+      sr[i] = idx < end ? ((sub << 16) | atomicAdd(&s_cnt[sub], 1u)) : 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {  // nfine <= 32: lane j owns fine bin j -- one global reservation each, offsets by a warp scan
+      const uint32_t n = lane < nfine ? s_cnt[lane] : 0;
+      uint32_t inc = n;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+      if (lane < nfine) {
+        const uint32_t o = inc - n;
+        const uint32_t f = ((uint32_t)c << fb) | (uint32_t)lane;
+        uint32_t bs = n ? atomicAdd(&fine_cursor[f], n) : 0;
+        if (n && (uint64_t)bs + n > (uint64_t)(f + 1) * capfine) { *ovf = 1; bs = slack_base + o; }
+        s_off[lane] = o;
+        s_delta[lane] = bs - o;
+        s_cnt[lane] = 0;
+      }
+      if (lane == 31) s_off[nfine] = inc;
+    }
+    __syncthreads();
+    const uint32_t total = s_off[nfine];
+#pragma unroll
+    for (int i = 0; i < kSplitItems; i++) {
+      if (sr[i] != 0xFFFFFFFFu) {
+        const uint32_t sub = sr[i] >> 16;
+        const uint32_t dst = s_off[sub] + (sr[i] & 0xFFFFu);
+        s_sorted[dst] = (w[i] & fmask) | ((lb >= 32 ? 0u : (w[i] >> lb)) << lbf);
+        s_sub[dst] = (uint8_t)sub;
+      }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < total; i += kSplitThreads) out[s_delta[s_sub[i]] + i] = s_sorted[i];
+    __syncthreads();
+  }
+}
+__global__ void fine_bin_offsets_kernel(uint32_t* __restrict__ bin_off, uint32_t* __restrict__ cursor, uint32_t n_bins, uint32_t capfine) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p <= n_bins) { bin_off[p] = p * capfine; if (p < n_bins) cursor[p] = p * capfine; }
+}
+
 }  // namespace shq

@@ -19,8 +19,10 @@ __device__ __forceinline__ int count_nl_u32(uint32_t w) {
   return __popc(__vcmpeq4(w, 0x0A0A0A0Au)) >> 3;
 }
 
-// text must be 16-byte aligned; bytes past n inside the last vector are masked out.
-__global__ void __launch_bounds__(kNlThreads) nl_count_kernel(const char* __restrict__ text, size_t n,
+// text must be 16-byte aligned; the batch proper is text[skip, n): the first `skip` (< 16) bytes belong to whatever lies
+// before it in the caller's buffer (a batch may start at any byte, its vector loads start at the aligned address below
+// it) and bytes past n inside the last vector are masked out.  Positions are reported relative to text + skip.
+__global__ void __launch_bounds__(kNlThreads) nl_count_kernel(const char* __restrict__ text, size_t n, uint32_t skip,
                                                              uint32_t* __restrict__ tile_counts) {
   size_t base = (size_t)blockIdx.x * kNlTile + (size_t)threadIdx.x * kNlBytesPerThread;
   int cnt = 0;
@@ -29,11 +31,11 @@ __global__ void __launch_bounds__(kNlThreads) nl_count_kernel(const char* __rest
 #pragma unroll
     for (int i = 0; i < kNlBytesPerThread / 16; i++) {
       size_t off = base + 16 * i;
-      if (off + 16 <= n) {
+      if (off + 16 <= n && off >= skip) {
         uint4 x = __ldg(v + i);
         cnt += count_nl_u32(x.x) + count_nl_u32(x.y) + count_nl_u32(x.z) + count_nl_u32(x.w);
       } else {
-        for (size_t b = off; b < n; b++) cnt += text[b] == '\n';
+        for (size_t b = off < skip ? skip : off; b < n && b < off + 16; b++) cnt += text[b] == '\n';
       }
     }
   }
@@ -42,7 +44,7 @@ __global__ void __launch_bounds__(kNlThreads) nl_count_kernel(const char* __rest
   if (threadIdx.x == 0) tile_counts[blockIdx.x] = tot;
 }
 
-__global__ void __launch_bounds__(kNlThreads) nl_write_kernel(const char* __restrict__ text, size_t n,
+__global__ void __launch_bounds__(kNlThreads) nl_write_kernel(const char* __restrict__ text, size_t n, uint32_t skip,
                                                              const uint32_t* __restrict__ tile_offs,
                                                              uint32_t* __restrict__ nl_pos) {
   size_t base = (size_t)blockIdx.x * kNlTile + (size_t)threadIdx.x * kNlBytesPerThread;
@@ -55,11 +57,11 @@ __global__ void __launch_bounds__(kNlThreads) nl_write_kernel(const char* __rest
 #pragma unroll
     for (int i = 0; i < kNlBytesPerThread / 16; i++) {
       size_t off = base + 16 * i;
-      if (off + 16 <= n) {
+      if (off + 16 <= n && off >= skip) {
         uint4 x = __ldg(v + i);
         words[4 * i] = x.x; words[4 * i + 1] = x.y; words[4 * i + 2] = x.z; words[4 * i + 3] = x.w;
       } else {
-        for (size_t b = off; b < n; b++) {
+        for (size_t b = off < skip ? skip : off; b < n && b < off + 16; b++) {
           int k = (int)(b - base);
           words[k >> 2] |= (uint32_t)(unsigned char)text[b] << (8 * (k & 3));
         }
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(kNlThreads) nl_write_kernel(const char* __rest
       uint32_t m = __vcmpeq4(words[i], 0x0A0A0A0Au);
       while (m) {
         int byte = (__ffs(m) - 1) >> 3;
-        nl_pos[o++] = (uint32_t)(base + 4 * i + byte);
+        nl_pos[o++] = (uint32_t)(base + 4 * i + byte) - skip;
         m &= ~(0xFFu << (8 * byte));
       }
     }

@@ -430,14 +430,41 @@ class ShardedCounter:
         return nd, ne
 
 
-def bench_sharded(args, rank, world, local_rank, text, ends, p, n_local, n_total, config, ClockSampler):
-    """bench.py for N>1: weak scaling, genome and filter grow with N, --deNoise=0 mid-stream + the end sweep."""
+def bench_sharded(args, rank, world, local_rank, B):
+    """bench.py for N>1 (B = the bench module): weak scaling, genome and filter grow with N; every rank generates and
+    hashes its slice of the global read set and owns 1/N of the quotient space."""
     import torch
     import torch.distributed as dist
+    import synth
+    from synth import workloads as wl
+    shq = importlib.import_module("sh-assembly_b200")
     dev = torch.device("cuda", local_rank)
-    d_text = torch.empty(len(text) + 64, dtype=torch.uint8, device=dev)
-    d_text[:len(text)].copy_(torch.from_numpy(text))
+    name = args.workload
+    w = wl.scaled(name, world)
+    sp = synth.make(w["G"], w["cov"], w["L"], w["err"], wl.SEED)
+    n_total = wl.n_kmers(w)
+    p = shq.param_block(w["K"], w["n_true"], n_total, alpha=w["err"], deNoise=w["deNoise"])
+    first, nloc = synth.rank_slice(sp, rank, world)
+    n_bytes = nloc * sp.rec_bytes
+    d_text = torch.empty(n_bytes + 64, dtype=torch.uint8, device=dev)
+    synth.gpu_fill(sp, first, nloc, d_text.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    h_text = torch.empty(n_bytes, dtype=torch.uint8).pin_memory()
+    h_text.copy_(d_text[:n_bytes])
     torch.cuda.synchronize()
+    text = h_text.numpy()
+    rd = shq.Reader(buffers=[text])
+    ends, off = [], 0
+    while True:
+        r = rd.next_raw()
+        if r is None:
+            break
+        off += r[1]
+        ends.append(off)
+    rd.close()
+    ends = np.array(ends, np.uint64)
+    config = B.config_dict(w, world, p, name)
+    ClockSampler = B.ClockSampler
+    args.k = w["K"]
     sc = ShardedCounter(int(p.qb), int(p.hb), rank, world, local_rank, dist)
 
     def step():
@@ -476,8 +503,7 @@ def bench_sharded(args, rank, world, local_rank, text, ends, p, n_local, n_total
 
     # end to end: pinned host text -> H2D (side stream, batch by batch) -> exchange + insert -> shard image -> D2H
     import time
-    h_text = torch.from_numpy(text).pin_memory()
-    d_buf = torch.empty(len(text) + 64, dtype=torch.uint8, device=dev)
+    d_buf = d_text
     _, _, nb_blocks = sc.materialize_sharded()
     h_img = torch.empty(nb_blocks * 89, dtype=torch.uint8).pin_memory()
 
@@ -505,16 +531,14 @@ def bench_sharded(args, rank, world, local_rank, text, ends, p, n_local, n_total
         ms_step = float(ms.item()) / args.steps
         value = n_total / (ms_step / 1e3)
         cfg = dict(config)
-        cfg["workload"] += " | N>1: counted with --deNoise=0 like BASELINE configs[3] (deNoise rounds need the global range hand-out and run on the gathered state, outside this step); filter sharded by quotient range, two-level binned all-to-all, every rank materialises its own blocks (max-plus carry + boundary stitch)"
-        cfg["deNoise"] = 0
-        cfg["endDeNoise"] = False
+        cfg["workload"] += " | filter sharded by quotient range, pull exchange over peer memory, every rank materialises its own blocks (max-plus carry + boundary stitch)"
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        a_ins = args.read_len / (args.read_len - args.k + 1) + 32
+        a_ins = w["L"] / (w["L"] - w["K"] + 1) + 32
         line = {"metric": "canonical k-mers inserted/sec", "value": value, "unit": "k-mers/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u64", "data": "synthetic", "config": cfg, "clocks": clocks,

@@ -49,6 +49,8 @@ struct AggOut {
   int fixed_bits;           // each bin is handled by 2^fixed_bits CTAs, one per key sub-range
   size_t sub_stride;        // outputs of sub-range s live at [s * sub_stride + bin_off[p] + i]
   int direct;               // most words are first occurrences: insert straight away instead of probing first
+  int sample_bits;          // > 0: aggregate only the keys of the first 1/2^sample_bits of the bin's key range (a sample by KEY,
+                            // so its distinct ratio is that of the whole bin) -- one pass over the bin by one CTA
 };
 
 struct AggTable {
@@ -221,10 +223,11 @@ __global__ void __launch_bounds__(kAggThreads, 2) bin_aggregate_kernel(
   uint32_t written = 0, written2 = 0, occ_total = 0, occ_total2 = 0;
   int sub_bits = o.fixed_bits;   // key_low bits fixed per round: fixed_bits chosen by the grid, the rest by overflow restarts
   while (sub_bits < lb && ((end - beg) >> sub_bits) > 64u * kAggMaxDistinct) sub_bits++;
+  if (o.sample_bits > sub_bits) sub_bits = o.sample_bits < lb ? o.sample_bits : lb - 1;
 
 restart:
   written = 0; written2 = 0; occ_total = 0; occ_total2 = 0;
-  for (uint32_t r = fsub << (sub_bits - o.fixed_bits); r < ((fsub + 1) << (sub_bits - o.fixed_bits)); r++) {
+  for (uint32_t r = fsub << (sub_bits - o.fixed_bits); r < (o.sample_bits ? (fsub << (sub_bits - o.fixed_bits)) + 1 : ((fsub + 1) << (sub_bits - o.fixed_bits))); r++) {
     {
       uint4* k4 = reinterpret_cast<uint4*>(t_key);
       uint4* c4 = reinterpret_cast<uint4*>(t_cnt);
@@ -350,7 +353,7 @@ __global__ void __launch_bounds__(256) compact_bins_kernel(const uint32_t* __res
 // State A (na sorted distinct keys) and batch run B (nb sorted distinct keys) -> merged state.
 // Merge-path tiles of kMergeTile merged elements; ties order A before B.
 constexpr int kMergeThreads = 256;
-constexpr int kMergeItems = 8;
+constexpr int kMergeItems = 6;
 constexpr int kMergeTile = kMergeThreads * kMergeItems;
 constexpr int kMergeHistMax = 1024;
 
@@ -447,9 +450,12 @@ __global__ void __launch_bounds__(kMergeThreads) merge_tiles_kernel(
 // Single-pass variant of the committing merge: no counting pass and no scan.  Tiles take a ticket (so a tile's
 // predecessors are always running or done), publish (flag | count) words and find their output offset by a
 // warp-wide decoupled look-back over the predecessors' words: flag 1 = the tile's own count, 2 = inclusive prefix.
+// All global traffic is coalesced: keys AND counts of both inputs are staged in shared memory, the merged tile is
+// assembled there and written out linearly.
 // HIST: B carries the first chunk of every key (Bchunk); chunk_hist[c] += keys of B that are NOT in A ("new" keys) whose
 // first chunk is c -- the by-product that lets the host find the deNoise boundary chunk of an armed batch.
 constexpr unsigned long long kLbValue = (1ULL << 62) - 1;
+constexpr size_t kMergeLbSmem = (size_t)(2 * (kMergeTile + 2)) * 8 + (size_t)(2 * (kMergeTile + 2)) * 4;
 template <bool HIST>
 __global__ void __launch_bounds__(kMergeThreads) merge_tiles_lookback_kernel(
     const uint64_t* __restrict__ A, const uint32_t* __restrict__ Ac, size_t na, const uint64_t* __restrict__ B,
@@ -457,8 +463,11 @@ __global__ void __launch_bounds__(kMergeThreads) merge_tiles_lookback_kernel(
     unsigned long long* status /* ntiles words, zeroed */, unsigned int* ticket /* zeroed */, uint64_t* __restrict__ out_keys,
     uint32_t* __restrict__ out_counts, unsigned long long* __restrict__ n_out_total, int* __restrict__ err,
     const uint16_t* __restrict__ Bchunk = nullptr, uint32_t* __restrict__ chunk_hist = nullptr) {
-  __shared__ uint64_t s_a[kMergeTile + 2];
-  __shared__ uint64_t s_b[kMergeTile + 2];
+  extern __shared__ __align__(16) unsigned char merge_smem[];
+  uint64_t* s_a = reinterpret_cast<uint64_t*>(merge_smem);          // kMergeTile + 2 keys of A (s_a[0] = the key before the tile)
+  uint64_t* s_b = s_a + kMergeTile + 2;                             // kMergeTile + 2 keys of B (one key past the tile at the end)
+  uint32_t* s_ac = reinterpret_cast<uint32_t*>(s_b + kMergeTile + 2);
+  uint32_t* s_bc = s_ac + kMergeTile + 2;
   __shared__ unsigned int s_tile;
   __shared__ unsigned long long s_prefix;
   __shared__ uint32_t s_hist[HIST ? kMergeHistMax : 1];
@@ -474,6 +483,9 @@ __global__ void __launch_bounds__(kMergeThreads) merge_tiles_lookback_kernel(
   const uint64_t kNone = ~0ULL;
   for (int i = threadIdx.x; i < la + 1; i += blockDim.x) s_a[i] = (i == 0) ? (a0 > 0 ? A[a0 - 1] : kNone) : A[a0 + i - 1];
   for (int i = threadIdx.x; i < lbn + 1; i += blockDim.x) s_b[i] = (i < lbn) ? B[b0 + i] : (b1 < nb ? B[b1] : kNone);
+  for (int i = threadIdx.x; i < la; i += blockDim.x) s_ac[i] = Ac[a0 + i];
+  // one count past the tile's B range: an A key at the very end of the tile may match B[b1]
+  for (int i = threadIdx.x; i < lbn + 1; i += blockDim.x) s_bc[i] = (b0 + i < nb) ? Bc[b0 + i] : 0;
   __syncthreads();
   const int total = la + lbn;
   int d0 = min(threadIdx.x * kMergeItems, total), d1 = min(d0 + kMergeItems, total);
@@ -490,8 +502,8 @@ __global__ void __launch_bounds__(kMergeThreads) merge_tiles_lookback_kernel(
     if (takeA) {
       uint64_t k = s_a[1 + ai];
       uint64_t nextb = s_b[bi];
-      uint64_t c = Ac[a0 + ai];
-      if (nextb == k) c += Bc[b0 + bi];
+      uint64_t c = s_ac[ai];
+      if (nextb == k) c += s_bc[bi];
       if (c > 0xFFFFFFFFull) { *err = SHQ_ERR_COUNT_OVERFLOW; c = 0xFFFFFFFFull; }
       okey[nheads] = k; ocnt[nheads] = (uint32_t)c;
       nheads++; ai++;
@@ -499,15 +511,18 @@ __global__ void __launch_bounds__(kMergeThreads) merge_tiles_lookback_kernel(
       uint64_t k = s_b[bi];
       uint64_t preva = s_a[ai];
       if (preva != k || (ai == 0 && a0 == 0)) {
-        okey[nheads] = k; ocnt[nheads] = Bc[b0 + bi]; nheads++;
+        okey[nheads] = k; ocnt[nheads] = s_bc[bi]; nheads++;
         if (HIST) { const uint32_t ch = Bchunk[b0 + bi]; if (ch < (uint32_t)kMergeHistMax) atomicAdd(&s_hist[ch], 1u); else atomicAdd(&chunk_hist[ch], 1u); }
       }
       bi++;
     }
   }
   uint32_t tot;
-  uint32_t rank = block_exclusive_scan<SumU32>(nheads, &tot);      // ends with a barrier: s_hist is complete
+  uint32_t rank = block_exclusive_scan<SumU32>(nheads, &tot);      // ends with a barrier: every thread is done with s_a / s_b, s_hist is complete
   if (HIST) for (int i = threadIdx.x; i < kMergeHistMax; i += blockDim.x) { const uint32_t v = s_hist[i]; if (v) atomicAdd(&chunk_hist[i], v); }
+  // the merged tile, assembled in place of the inputs
+  uint64_t* s_ok = s_a; uint32_t* s_oc = s_ac;
+  for (uint32_t i = 0; i < nheads; i++) { s_ok[rank + i] = okey[i]; s_oc[rank + i] = ocnt[i]; }
   if (threadIdx.x < 32) {               // warp 0: publish, then look back 32 predecessors at a time
     const int lane = threadIdx.x;
     unsigned long long excl = 0;
@@ -536,8 +551,8 @@ __global__ void __launch_bounds__(kMergeThreads) merge_tiles_lookback_kernel(
     }
   }
   __syncthreads();
-  size_t o = (size_t)s_prefix + rank;
-  for (uint32_t i = 0; i < nheads; i++) { out_keys[o + i] = okey[i]; out_counts[o + i] = ocnt[i]; }
+  const size_t o = (size_t)s_prefix;
+  for (uint32_t i = threadIdx.x; i < tot; i += blockDim.x) { out_keys[o + i] = s_ok[i]; out_counts[o + i] = s_oc[i]; }
 }
 
 // u32 -> u64 widening (scan input)

@@ -81,6 +81,7 @@ struct shq_handle_s {
   DevBuf d_tmp_keys2, d_tmp_counts2, d_run2_keys, d_run2_counts;
   DevBuf d_run_keys, d_run_counts, d_run_chunk, d_split, d_heads, d_heads64, d_scan_scratch, d_misc;
   DevBuf d_pairs, d_pos, d_flags, d_keep, d_q_in, d_q_cnt, d_q_was;
+  DevBuf d_sample;
   DevBuf d_seg, d_fine, d_fine_cur, d_packed2, d_bases;   // second binning level (single GPU: fine bins; multi-GPU: owner-side split)
   int fine_bits_forced = -1;     // SHQ_FINE_BITS: force the second binning level (0 = off)
   // pull exchange: two fixed binned-word buffers that peers map through CUDA IPC, and the peers' buffers mapped here
@@ -195,6 +196,8 @@ struct BatchBins {
   // the binned words, the bin offsets (n_bins + 1) and, for fixed-capacity bins, the end of every bin
   const uint32_t* words = nullptr; const uint32_t* off = nullptr; const uint32_t* end = nullptr;
   int fine_bits = 0;            // second binning level applied (n_bins and lb already include it)
+  // from the sample (coarse bin 0 aggregated on its own): distinct keys / new keys per occurrence of THIS batch; < 0: none
+  double ratio = -1.0, new_frac = -1.0; uint32_t sample_new = 0;
 };
 struct BinOverflow {};          // a fixed-capacity bin overflowed: redo the batch with exact offsets
 
@@ -206,9 +209,8 @@ int pick_bin_bits(shq_handle_s* h, uint64_t est_keys, int chunk_bits_needed) {
   // (key bits below the bin) + chunk bits <= 32.  More bins than 2^12 come from the second binning level.
   int shard_bits = 0; while ((1 << shard_bits) < h->nshards) shard_bits++;
   int local_bits = h->hb - shard_bits;
-  const double ratio = h->ratio_seen ? h->distinct_ratio : 1.0;
   int pb = 8;
-  while (pb < 12 && ((est_keys >> pb) > 65536 || (double)(est_keys >> pb) * ratio * 1.2 > 4500.0)) pb++;
+  while (pb < 12 && (est_keys >> pb) > 16384) pb++;
   if (h->bin_bits) pb = h->bin_bits;
   if (pb > local_bits) pb = local_bits;
   // the low key bits share a 32-bit word with the chunk id, and 0xFFFFFFFF is the aggregator's empty marker
@@ -222,9 +224,6 @@ int pick_bin_bits(shq_handle_s* h, uint64_t est_keys, int chunk_bits_needed) {
 // start small; and the distinct keys of a batch must fit the aggregator's per-bin tables (~6500 keys x 4096 bins).
 size_t batch_target_bytes(shq_handle_s* h) {
   if (h->batch_fixed) return h->max_batch_bytes;
-  // nothing known about this read set yet: a small first batch (< 5000 k-mers per bin, so every bin fits the aggregator's
-  // table even if all of them are distinct) tells how many distinct keys a batch holds
-  if (!h->ratio_seen) return (size_t)48 << 20;
   double t = (double)h->max_batch_bytes * std::max(1.0, (double)h->n_state / 2.5e7);
   t = std::min(t, 1024.0 * 1048576.0);
   return (size_t)t;
@@ -267,6 +266,51 @@ uint32_t index_lines(shq_handle_s* h, const char* d_text, size_t n_text) {
   h->d_nl_pos.reserve((size_t)(n_lines + 8) * 4);
   nl_write_kernel<<<ntiles, kNlThreads, 0, st>>>(base, n_al, skip, h->d_nl_tiles.as<uint32_t>(), h->d_nl_pos.as<uint32_t>()); L++;
   return n_lines;
+}
+
+// A 1/n_bins sample of the batch, for free of any assumption about the read set: coarse bin 0 (ntHash keys are uniform,
+// so it holds a uniform sample of the batch's k-mers, from all chunks) is aggregated on its own by one CTA, and its
+// distinct keys are looked up in the state.  Gives, before the batch is processed, its distinct-key ratio (-> second
+// binning level, insert strategy, bin capacities) and its new-key rate (-> is the deNoise trigger crossed inside?).
+__global__ void count_new_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ n_keys, const uint64_t* __restrict__ state, size_t n_state,
+                                 uint32_t* __restrict__ n_new) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool is_new = false;
+  if (i < *n_keys) {
+    const uint64_t k = keys[i];
+    size_t lo = 0, hi = n_state;
+    while (lo < hi) { const size_t mid = lo + ((hi - lo) >> 1); if (state[mid] < k) lo = mid + 1; else hi = mid; }
+    is_new = !(lo < n_state && state[lo] == k);
+  }
+  const uint32_t m = __ballot_sync(0xffffffffu, is_new);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_new, (uint32_t)__popc(m));
+}
+void sample_batch(shq_handle_s* h, BatchBins* bb, uint32_t capbin) {
+  cudaStream_t st = h->stream;
+  uint64_t& L = h->stats.kernels_launched;
+  h->d_tmp_keys.reserve(((size_t)capbin + 8) * 8); h->d_tmp_counts.reserve(((size_t)capbin + 8) * 4);
+  h->d_sample.reserve(64);
+  uint32_t* d_s = h->d_sample.as<uint32_t>();          // [0] distinct, [1] occurrences, [2] new, [3] split overflow (unused)
+  SHQ_CUDA(cudaMemsetAsync(d_s, 0, 16, st));
+  AggOut o{};
+  o.keys = h->d_tmp_keys.as<uint64_t>(); o.counts = h->d_tmp_counts.as<uint32_t>(); o.chunk = nullptr;
+  o.n_out = d_s; o.occ_out = d_s + 1; o.n_out2 = d_s + 3; o.occ_out2 = d_s + 3; o.split_overflow = reinterpret_cast<int*>(d_s + 3);
+  o.fixed_bits = 0; o.sub_stride = 0; o.bin_end = bb->end; o.direct = 1; o.first_hist = nullptr;
+  // sample by key range: about 6000 words of the bin, so that even an all-distinct sample fits the table
+  { const uint32_t mean = bb->n_keys / (uint32_t)bb->n_bins; int sb = 0; while (sb < bb->lb - 1 && (mean >> sb) > 6000u) sb++; o.sample_bits = sb; }
+  const size_t smem = agg_smem_bytes(false, false);
+  SHQ_CUDA(cudaFuncSetAttribute(bin_aggregate_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  bin_aggregate_kernel<false, false><<<1, kAggThreads, smem, st>>>(bb->words, bb->off, bb->lb, h->key_lo, 0u, 0xFFFFFFFFu, 0u, o); L++;
+  count_new_kernel<<<cdiv(capbin, 256), 256, 0, st>>>(o.keys, d_s, h->st_keys.as<uint64_t>(), h->n_state, d_s + 2); L++;
+  SHQ_CUDA(cudaGetLastError());
+  uint32_t* p = (uint32_t*)pinned(h, 16);
+  SHQ_CUDA(cudaMemcpyAsync(p, d_s, 12, cudaMemcpyDeviceToHost, st));
+  SHQ_CUDA(cudaStreamSynchronize(st));
+  h->stats.d2h_bytes += 12; h->stats.host_syncs++;
+  if (p[1] >= 256) {
+    bb->ratio = (double)p[0] / (double)p[1]; bb->new_frac = (double)p[2] / (double)p[1]; bb->sample_new = p[2];
+    h->distinct_ratio = bb->ratio; h->ratio_seen = true;
+  }
 }
 
 // Both hashing passes over the batch text (or a raw key array): count -> offsets -> scatter.
@@ -354,11 +398,12 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
       h->stats.scatter_launches++; h->stats.scatter_text_bytes += n_text; h->stats.scatter_words += n_ub;
       // second level: split every coarse bin into 2^fb fine bins when it would hold more distinct keys than the
       // aggregator's table takes (the ratio of the previous batch is the estimate; a larger batch can only lower it)
+      sample_batch(h, bb, (uint32_t)capbin);
       {
-        const double ratio = h->ratio_seen ? std::min(1.0, h->distinct_ratio * 1.1) : 1.0;
+        const double ratio = bb->ratio >= 0 ? std::min(1.0, bb->ratio * 1.1) : 1.0;
         const double est_d = (double)n_ub / (double)n_bins * ratio;
         int fb = 0;
-        while (fb < 5 && lb - fb > 1 && est_d / (double)(1 << fb) > 5500.0) fb++;
+        while (fb < 5 && lb - fb > 1 && est_d / (double)(1 << fb) > 3500.0) fb++;      // load factor of the aggregator's table <= ~0.45
         if (h->fine_bits_forced >= 0) fb = std::min(h->fine_bits_forced, std::min(5, lb - 1));
         const uint64_t n_fine = (uint64_t)n_bins << fb;
         const uint64_t capfine = bin_capacity(h, n_ub / n_fine);
@@ -474,7 +519,7 @@ bool aggregate_bins(shq_handle_s* h, const BatchBins& bb, uint32_t clo, uint32_t
   o.fixed_bits = fixed_bits; o.sub_stride = cap;
   o.bin_end = bb.end;
   // most words of the batch are first occurrences (a batch of a large genome covers it less than once): insert directly
-  o.direct = (h->ratio_seen ? h->distinct_ratio : 1.0) > 0.3 ? 1 : 0;
+  o.direct = (bb.ratio >= 0 ? bb.ratio : (h->ratio_seen ? h->distinct_ratio : 1.0)) > 0.3 ? 1 : 0;
 #define SHQ_AGG_LAUNCH(SP, CH) do { \
     const size_t smem = agg_smem_bytes(CH, SP); \
     SHQ_CUDA(cudaFuncSetAttribute(bin_aggregate_kernel<SP, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -553,11 +598,13 @@ uint64_t merge_shadow(shq_handle_s* h, const Run& R, int nchunks, std::vector<ui
     unsigned long long* status = h->d_heads64.as<unsigned long long>();
     unsigned long long* d_nout = status + ntiles; unsigned int* ticket = (unsigned int*)(status + ntiles + 1);
     SHQ_CUDA(cudaMemsetAsync(status, 0, (ntiles + 2) * 8, st));
+    SHQ_CUDA(cudaFuncSetAttribute(merge_tiles_lookback_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMergeLbSmem));
+    SHQ_CUDA(cudaFuncSetAttribute(merge_tiles_lookback_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMergeLbSmem));
     if (d_hist)
-      merge_tiles_lookback_kernel<true><<<(unsigned)ntiles, kMergeThreads, 0, st>>>(A, Ac, na, Bk, Bc, nb, h->d_split.as<uint64_t>(), ntiles, status, ticket,
+      merge_tiles_lookback_kernel<true><<<(unsigned)ntiles, kMergeThreads, kMergeLbSmem, st>>>(A, Ac, na, Bk, Bc, nb, h->d_split.as<uint64_t>(), ntiles, status, ticket,
                                                                                 h->st_keys2.as<uint64_t>(), h->st_counts2.as<uint32_t>(), d_nout, h->d_err, Bch, d_hist);
     else
-      merge_tiles_lookback_kernel<false><<<(unsigned)ntiles, kMergeThreads, 0, st>>>(A, Ac, na, Bk, Bc, nb, h->d_split.as<uint64_t>(), ntiles, status, ticket,
+      merge_tiles_lookback_kernel<false><<<(unsigned)ntiles, kMergeThreads, kMergeLbSmem, st>>>(A, Ac, na, Bk, Bc, nb, h->d_split.as<uint64_t>(), ntiles, status, ticket,
                                                                                  h->st_keys2.as<uint64_t>(), h->st_counts2.as<uint32_t>(), d_nout, h->d_err);
     L++;
     SHQ_CUDA(cudaGetLastError());
@@ -780,8 +827,15 @@ void process_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uin
   // does the new-key rate seen so far predict that chunks [clo, last] reach the trigger?  (no history: assume they might)
   auto predicts_crossing = [&]() {
     const double frac = (double)(last - clo + 1) / (double)(last + 1);
-    const double rate = h->new_rate < 0 ? 1.0 : h->new_rate * 1.15;
-    return (double)h->ndistinct + rate * frac * (double)bb.n_keys + 65536.0 >= (double)h->trigger;
+    double est_new;
+    if (bb.new_frac >= 0 && clo == 0) {
+      // measured on this batch's sample; 3 sigma of the sample count plus 10 % on top
+      est_new = bb.new_frac * (double)bb.n_keys * (1.10 + 3.0 / sqrt((double)bb.sample_new + 1.0));
+    } else {
+      const double rate = h->new_rate < 0 ? 1.0 : h->new_rate * 1.15;
+      est_new = rate * frac * (double)bb.n_keys;
+    }
+    return (double)h->ndistinct + est_new + 4096.0 >= (double)h->trigger;
   };
   for (;;) try {
     if (!(armed && h->rounds_left > 0)) {                 // no round pending: chunks [clo, last] go in as one run
@@ -968,7 +1022,7 @@ void free_handle(shq_handle_s* h) {
                     &h->d_binoff, &h->d_packed, &h->d_tmp_keys, &h->d_tmp_counts, &h->d_tmp_chunk, &h->d_nout, &h->d_occ,
                     &h->d_dense_off, &h->d_run_keys, &h->d_run_counts, &h->d_run_chunk, &h->d_split, &h->d_heads, &h->d_heads64,
                     &h->d_scan_scratch, &h->d_misc, &h->d_pairs, &h->d_pos, &h->d_flags, &h->d_keep, &h->d_q_in, &h->d_q_cnt, &h->d_q_was,
-                    &h->d_tmp_keys2, &h->d_tmp_counts2, &h->d_run2_keys, &h->d_run2_counts, &h->d_seg, &h->d_fine, &h->d_fine_cur, &h->d_packed2, &h->d_bases};
+                    &h->d_tmp_keys2, &h->d_tmp_counts2, &h->d_run2_keys, &h->d_run2_counts, &h->d_seg, &h->d_fine, &h->d_fine_cur, &h->d_packed2, &h->d_bases, &h->d_sample};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : h->pin_buf) b.release();
   for (void* p : h->mg_opened) cudaIpcCloseMemHandle(p);

@@ -208,6 +208,11 @@ typedef struct {
 } shq_unitig_opts;
 typedef struct shq_unitigs_s* shq_unitigs_t;
 int shq_unitigs_begin(shq_t h, const shq_unitig_opts* opts, shq_unitigs_t* out);
+/* Which k-mer of a read seeds the traversal.  The reference has two consumers of read chunks with different rules: its
+ * worker threads take the k-mer at len/2 - K/2 (contig_assembly.cpp:1859-1863; the default here: with -t 16 workers
+ * see 16 of every 17 chunks), its master thread the one at len/2 (:2067-2071).  The rules differ only in which small
+ * islands get a seed.  Call before the first shq_unitigs_add_reads.                                              */
+int shq_unitigs_set_seed_rule(shq_unitigs_t u, int master_rule);
 int shq_unitigs_add_reads(shq_unitigs_t u, const char* text, size_t n);   /* one chunk of FASTQ */
 int shq_unitigs_build(shq_unitigs_t u);
 int shq_unitigs_count(shq_unitigs_t u, size_t* n_unitigs, size_t* total_bases);

@@ -69,7 +69,7 @@ EXPORTS = [
     "shq_insert_fastq_chunk", "shq_insert_fastq_pinned", "shq_insert_fastq_pinned_chunks", "shq_insert_fastq_device", "shq_insert_keys", "shq_insert_keys_device", "shq_finish",
     "shq_sync", "shq_counts", "shq_rounds_done", "shq_denoise", "shq_image_size", "shq_export_cqf", "shq_save",
     "shq_load", "shq_load_image", "shq_geometry", "shq_iterate", "shq_query_set_traveled", "shq_query",
-    "shq_hash_fastq_chunk", "shq_unitigs_begin", "shq_unitigs_add_reads", "shq_unitigs_build", "shq_unitigs_count",
+    "shq_hash_fastq_chunk", "shq_unitigs_begin", "shq_unitigs_set_seed_rule", "shq_unitigs_add_reads", "shq_unitigs_build", "shq_unitigs_count",
     "shq_unitigs_write_fasta", "shq_unitigs_fasta", "shq_unitigs_free", "shq_get_stats", "shq_reset_stats", "shq_stream",
     "shq_reader_open", "shq_reader_open_memory", "shq_reader_next", "shq_reader_close", "shq_build_kmer_spectrum",
     "shq_materialize", "shq_param_block", "shq_cdfpoi_positive", "shq_cdfpoi",
@@ -120,6 +120,7 @@ def lib():
         L.shq_query.argtypes = [vp, vp, sz, vp]
         L.shq_hash_fastq_chunk.argtypes = [vp, vp, sz, C.c_int, vp, sz, C.POINTER(sz)]
         L.shq_unitigs_begin.argtypes = [vp, C.POINTER(shq_unitig_opts), C.POINTER(vp)]
+        L.shq_unitigs_set_seed_rule.argtypes = [vp, C.c_int]
         L.shq_unitigs_add_reads.argtypes = [vp, vp, sz]
         L.shq_unitigs_build.argtypes = [vp]
         L.shq_unitigs_count.argtypes = [vp, C.POINTER(sz), C.POINTER(sz)]
@@ -172,13 +173,15 @@ def param_block(K, n_true, N_total, alpha=-1.0, error_profile="", deNoise=-1, fr
     return out
 
 
-def build_unitigs(cqf, chunks, K, s_min=2, x_min=2, x_max=1000000):
+def build_unitigs(cqf, chunks, K, s_min=2, x_min=2, x_max=1000000, master_rule=False):
     """Contiger device path: returns the unitig FASTA text (BCALM/Minia style headers)."""
     L = lib()
     opts = shq_unitig_opts(K, s_min, x_min, x_max)
     u = C.c_void_p()
     cqf._check(L.shq_unitigs_begin(cqf.h, C.byref(opts), C.byref(u)))
     try:
+        if master_rule:
+            cqf._check(L.shq_unitigs_set_seed_rule(u, 1))
         for ch in chunks:
             p, n, keep = _buf(ch)
             cqf._check(L.shq_unitigs_add_reads(u, p, n))

@@ -592,7 +592,7 @@ __global__ void fill_u32_kernel(uint32_t* p, uint32_t v, size_t n) { size_t i = 
 // (contig_assembly.cpp:1843-1921, whose `continue`s skip skipLines(2)) could parse the chunk differently:
 // a header not starting with '@', or an N-seed whose quality line starts with '@'.
 __global__ void seed_extract_kernel(const char* __restrict__ text, const uint32_t* __restrict__ nl_pos, uint32_t n_reads, int K,
-                                    char* __restrict__ seeds, int* __restrict__ irregular) {
+                                    char* __restrict__ seeds, int* __restrict__ irregular, int master_rule) {
   uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
   uint32_t h0 = r ? nl_pos[4 * (size_t)r - 1] + 1 : 0;
@@ -603,7 +603,7 @@ __global__ void seed_extract_kernel(const char* __restrict__ text, const uint32_
   if (nl_pos[4 * (size_t)r] == h0 || text[h0] != '@') { *irregular = 1; return; }     // empty or foreign header line
   int len = (int)(e - s);
   if (len < K) return;
-  int middle = len / 2 - K / 2;
+  int middle = master_rule ? len / 2 : len / 2 - K / 2;      // contig_assembly.cpp:2067-2071 (master) vs 1859-1863 (workers)
   if (middle > len - K) return;
   bool hasN = false;
   for (int i = 0; i < K; i++) {
@@ -629,6 +629,7 @@ struct shq_unitigs_s {
   shq::DevBuf d_stage; size_t st_fill = 0; std::vector<size_t> st_ends;   // read chunks staged on the device
   size_t st_cap_target = (size_t)128 << 20;
   bool built = false;
+  bool master_rule = false;       // seed k-mer of a read: len/2 - K/2 (workers, the default) or len/2 (the master thread)
   // results (host)
   std::vector<std::string> seqs; std::vector<int> km; std::vector<std::vector<int>> after, before;
   std::string fasta;
@@ -650,7 +651,7 @@ NodeTable node_table(shq_unitigs_s* u) {
 // processDataChunk's line cursor (contig_assembly.cpp:1839-1924), restated literally: every `continue`
 // skips the two skipLines(), so the quality line is examined as a would-be header.  Collects the
 // upper-cased middle k-mer (worker rule: len/2 - K/2) of every record that passes the 'N' test.
-void collect_seeds_range(int K, const char* text, size_t p, size_t n, std::vector<char>* out) {
+void collect_seeds_range(int K, const char* text, size_t p, size_t n, std::vector<char>* out, bool master_rule) {
   auto read_line = [&](const char** s, size_t* len) -> bool {
     if (p >= n) return false;
     const char* nl = (const char*)memchr(text + p, '\n', n - p);
@@ -665,7 +666,7 @@ void collect_seeds_range(int K, const char* text, size_t p, size_t n, std::vecto
     if (ll == 0 || line[0] != '@') continue;
     if (!read_line(&seq, &sl)) break;
     if ((int)sl < K) { const char* t; size_t tl; read_line(&t, &tl); read_line(&t, &tl); continue; }
-    int seq_len = (int)sl, middle = seq_len / 2 - K / 2;
+    int seq_len = (int)sl, middle = master_rule ? seq_len / 2 : seq_len / 2 - K / 2;
     if (middle <= seq_len - K) {
       bool hasN = false;
       for (int i = 0; i < K; i++) { char c = seq[middle + i]; if (c > 0x60) c -= 32; if (c == 'N') hasN = true; kmer[i] = c; }
@@ -702,14 +703,14 @@ void collect_seeds(shq_unitigs_s* u, const char* text, size_t n) {
   const int K = u->opts.K;
   unsigned hw = std::thread::hardware_concurrency();
   int T = (int)std::min<unsigned>(hw ? hw : 1, 8);
-  if (n < ((size_t)1 << 20) || T <= 1) { collect_seeds_range(K, text, 0, n, &u->seeds); return; }
+  if (n < ((size_t)1 << 20) || T <= 1) { collect_seeds_range(K, text, 0, n, &u->seeds, u->master_rule); return; }
   std::vector<size_t> starts(T + 1, n);
   starts[0] = 0;
   for (int i = 1; i < T; i++) starts[i] = find_record_start(text, n / T * i, n);
   for (int i = 1; i <= T; i++) if (starts[i] < starts[i - 1]) starts[i] = starts[i - 1];
   std::vector<std::vector<char>> parts(T);
   std::vector<std::thread> th;
-  for (int i = 0; i < T; i++) th.emplace_back(collect_seeds_range, K, text, starts[i], starts[i + 1], &parts[i]);
+  for (int i = 0; i < T; i++) th.emplace_back(collect_seeds_range, K, text, starts[i], starts[i + 1], &parts[i], u->master_rule);
   for (auto& t : th) t.join();
   for (auto& v : parts) u->seeds.insert(u->seeds.end(), v.begin(), v.end());
 }
@@ -1065,7 +1066,7 @@ bool unitigs_process_text(shq_unitigs_s* u, const char* d_text, size_t n, const 
     SHQ_CUDA(cudaMemsetAsync(d_irr, 0, 4, st));
     if (n_reads) {
       seed_extract_kernel<<<cdiv(n_reads, 128), 128, 0, st>>>(d_text, h->d_nl_pos.as<uint32_t>(), n_reads, K,
-                                                            u->d_seed_slots.as<char>() + u->n_seed_slots * (size_t)K, d_irr); L++;
+                                                            u->d_seed_slots.as<char>() + u->n_seed_slots * (size_t)K, d_irr, u->master_rule ? 1 : 0); L++;
     }
     if (read_scalar(h, d_irr)) {
       if (!host_text) return false;
@@ -1140,6 +1141,13 @@ int shq_unitigs_add_reads(shq_unitigs_t u, const char* text, size_t n) {
     h->stats.h2d_bytes += a.n;
     u->st_fill += a.n; u->st_ends.push_back(u->st_fill);
   }, &args);
+}
+
+int shq_unitigs_set_seed_rule(shq_unitigs_t u, int master_rule) {
+  if (!u) return SHQ_ERR_ARG;
+  if (u->st_fill || u->n_seed_slots) return SHQ_ERR_STATE;      // before the first reads
+  u->master_rule = master_rule != 0;
+  return SHQ_OK;
 }
 
 int shq_unitigs_build(shq_unitigs_t u) {

@@ -18,8 +18,8 @@ def cases(po):
                                     K=27, qb=19, s=2, x=2, X=1000000, part=1 << 20)
     out["thresholds"] = dict(files=[po.synth_fastq(G=30000, cov=30, err=0.005, L=100, seed=23)], K=23, qb=19, s=3, x=4, X=60, part=1 << 23)
     out["invariants_k31"] = dict(files=[po.synth_fastq(G=50000, cov=30, err=0.003, seed=29)], K=31, qb=19, s=2, x=2, X=1000000, part=1 << 23)
-    # many false-positive neighbours: a small filter (hb = 24) under a 100 kb genome
-    out["collisions_qb16"] = dict(files=[po.synth_fastq(G=100000, cov=25, err=0.003, L=120, seed=31)], K=29, qb=16, s=2, x=2, X=1000000, part=1 << 23)
+    # many false-positive neighbours: a small filter (hb = 25, about 40 % full) under a 30 kb genome
+    out["collisions_qb17"] = dict(files=[po.synth_fastq(G=30000, cov=25, err=0.002, L=120, seed=31)], K=29, qb=17, s=2, x=2, X=1000000, part=1 << 23)
     return out
 
 

@@ -20,7 +20,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from oracle import pyoracle as po  # noqa: E402
-import contiger_cases as cc  # noqa: E402
+from tests import contiger_cases as cc  # noqa: E402
 
 BIN = os.path.join(ROOT, "oracle", "_ref", "Contiger_ref")
 OUT = os.path.join(ROOT, "tests", "golden", "contiger_ref.json")
@@ -50,7 +50,7 @@ def run_reference(case, tmp, runs=3):
     for i in range(runs):
         fa = os.path.join(tmp, "ref%d.fa" % i)
         subprocess.run([BIN, "-k", str(K), "-i", lst, "-c", cqf, "-s", str(case["s"]), "-x", str(case["x"]), "-X", str(case["X"]), "-t", "1", "-o", fa],
-                       check=True, capture_output=True)
+                       check=True, capture_output=True, timeout=300)
         outs.append(open(fa).read())
     return image, outs
 

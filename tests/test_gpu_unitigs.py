@@ -81,3 +81,50 @@ def test_unitigs_irregular_chunk_host_cursor(po, shq):
     fa_o, fa_g = run_both(po, shq, [text2], K, 19)
     assert po.canonical_unitig_set(fa_g) == po.canonical_unitig_set(fa_o)
     assert po.canonical_links(fa_g) == po.canonical_links(fa_o)
+
+
+# ---- against OUTPUT OF THE UNMODIFIED REFERENCE CONTIGER (tests/golden/contiger_ref.json, see tests/test_contiger_ref.py) ----
+import json
+import os
+
+from tests import contiger_cases as cc
+
+_GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "contiger_ref.json")))
+
+
+@pytest.mark.parametrize("name", sorted(n for n in _GOLD if n != "repeats_two_files"))
+def test_unitigs_match_reference_binary_output(po, shq, name):
+    """one read chunk: the reference applies ONE seed rule to all reads (its master thread's, len/2, in almost every run);
+    the device path under that rule gives the reference's canonical unitig set and link structure"""
+    case = cc.cases(po)[name]
+    o, _ = po.count_run(case["files"], case["K"], case["qb"], case["qb"] + 8, 0, 0, True, part_size=case["part"])
+    img = o.export()
+    chunks = [c for _, c in shq.Reader(buffers=case["files"], part_size=case["part"])]
+    digests = []
+    for master in (True, False):
+        g = shq.CQF.from_bytes(img)
+        fa = shq.build_unitigs(g, chunks, case["K"], case["s"], case["x"], case["X"], master_rule=master)
+        g.close()
+        digests.append(cc.unitig_digest(po, fa))
+    outcomes = _GOLD[name]["reference_outcomes"]
+    assert outcomes and all(d in digests for d in outcomes)
+    assert digests[0] in outcomes or digests[1] in outcomes
+
+
+def test_unitigs_two_chunks_between_the_seed_rules(po, shq):
+    """several chunks: master and worker race for them in the reference, its output varies between the two rules' results;
+    the device path reproduces both ends of that range (links are the same under both)"""
+    name = "repeats_two_files"
+    case = cc.cases(po)[name]
+    o, _ = po.count_run(case["files"], case["K"], case["qb"], case["qb"] + 8, 0, 0, True, part_size=case["part"])
+    img = o.export()
+    chunks = [c for _, c in shq.Reader(buffers=case["files"], part_size=case["part"])]
+    ds = []
+    for master in (True, False):
+        g = shq.CQF.from_bytes(img)
+        fa = shq.build_unitigs(g, chunks, case["K"], case["s"], case["x"], case["X"], master_rule=master)
+        g.close()
+        ds.append(cc.unitig_digest(po, fa))
+    for d in _GOLD[name]["reference_outcomes"]:
+        assert min(x["n_unitigs"] for x in ds) - 2 <= d["n_unitigs"] <= max(x["n_unitigs"] for x in ds) + 2
+        assert d["links_sha256"] in [x["links_sha256"] for x in ds]

@@ -157,6 +157,21 @@ int shq_mg_setup(shq_t h, size_t max_words, void* ipc_handles_out);
 int shq_mg_open_peers(shq_t h, const void* all_handles, int world);
 int shq_mg_bin_local(shq_t h, const char* d_text, size_t n, int K, int parity, uint32_t* d_fine_hist, size_t* n_words);
 int shq_mg_insert_pull(shq_t h, const uint32_t* d_all_fine_hist, int parity);
+/* "The same job at every N": while deNoise rounds are pending a batch may only go in if the GLOBAL number of distinct keys
+ * stays below the trigger (cqf/CQF_mt.h:837).  shq_mg_stage_pull = shq_mg_insert_pull up to that decision: this shard's
+ * share of the batch is pulled, split, aggregated and its new keys counted (merge into a shadow copy of the state, or
+ * binary searches for a batch much smaller than the state); the caller sums n_new over the ranks and then commits or
+ * discards on every rank.  A deNoise boundary inside a batch is located by staging ever smaller chunk ranges.
+ * shq_mg_denoise_walk / _finalize / _apply: one sharded sweep (cqf/CQF_mt.h:884-922, cqf/gqf.c:2792-3040): the chain of
+ * 2^20-slot ranges runs over global slot positions, so rank r walks its entries (laid out behind `carry`, see
+ * shq_mg_layout_aggregate) and hands the 16-word chain state to rank r + 1; after the last rank _finalize closes the
+ * open range; _apply drops the count-1 entries except the protected ones (protect_last = bit `rank` of state[11]).  */
+int shq_mg_stage_pull(shq_t h, const uint32_t* d_all_fine_hist, int parity, uint64_t* n_new, uint64_t* n_occ);
+int shq_mg_commit(shq_t h);
+int shq_mg_discard(shq_t h);
+int shq_mg_denoise_walk(shq_t h, const int64_t carry[2], uint64_t state[16]);
+int shq_mg_denoise_finalize(uint64_t state[16]);
+int shq_mg_denoise_apply(shq_t h, int protect_last, uint64_t* removed);
 int shq_mg_bin_fastq_device(shq_t h, const char* d_text, size_t n, int K, int coarse_bits, const uint32_t** d_words,
                             const uint32_t** d_bin_off, size_t* n_words);
 int shq_mg_insert_binned(shq_t h, const uint32_t* d_recv, const uint64_t* seg_start, const uint32_t* d_counts, int world,

@@ -74,6 +74,7 @@ EXPORTS = [
     "shq_reader_open", "shq_reader_open_memory", "shq_reader_next", "shq_reader_close", "shq_build_kmer_spectrum",
     "shq_materialize", "shq_param_block", "shq_cdfpoi_positive", "shq_cdfpoi",
     "shq_mg_setup", "shq_mg_open_peers", "shq_mg_bin_local", "shq_mg_insert_pull",
+    "shq_mg_stage_pull", "shq_mg_commit", "shq_mg_discard", "shq_mg_denoise_walk", "shq_mg_denoise_finalize", "shq_mg_denoise_apply",
     "shq_mg_bin_fastq_device", "shq_mg_insert_binned", "shq_mg_layout_aggregate", "shq_mg_layout_tail", "shq_mg_materialize_shard", "shq_header",
     "shq_hash_fastq_device", "shq_partition_keys_device", "shq_state_view", "shq_adopt_state", "shq_set_counts", "shq_copy_device",
 ]
@@ -140,6 +141,12 @@ def lib():
         L.shq_mg_open_peers.argtypes = [vp, vp, C.c_int]
         L.shq_mg_bin_local.argtypes = [vp, vp, sz, C.c_int, C.c_int, vp, C.POINTER(sz)]
         L.shq_mg_insert_pull.argtypes = [vp, vp, C.c_int]
+        L.shq_mg_stage_pull.argtypes = [vp, vp, C.c_int, C.POINTER(u64), C.POINTER(u64)]
+        L.shq_mg_commit.argtypes = [vp]
+        L.shq_mg_discard.argtypes = [vp]
+        L.shq_mg_denoise_walk.argtypes = [vp, C.POINTER(C.c_int64), vp]
+        L.shq_mg_denoise_finalize.argtypes = [vp]
+        L.shq_mg_denoise_apply.argtypes = [vp, C.c_int, C.POINTER(u64)]
         L.shq_mg_layout_aggregate.argtypes = [vp, C.POINTER(C.c_int64)]
         L.shq_mg_layout_tail.argtypes = [vp, C.POINTER(C.c_int64), sz, vp, vp, vp, C.POINTER(sz)]
         L.shq_mg_materialize_shard.argtypes = [vp, vp, vp, vp, sz, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]
@@ -446,6 +453,28 @@ class CQF:
 
     def mg_insert_pull(self, d_all_hist, parity):
         self._check(self.L.shq_mg_insert_pull(self.h, d_all_hist, parity))
+
+    def mg_stage_pull(self, d_all_hist, parity):
+        """(new keys, occurrences) of this shard's share of the batch; commit or discard afterwards"""
+        nn, no = C.c_uint64(), C.c_uint64()
+        self._check(self.L.shq_mg_stage_pull(self.h, d_all_hist, parity, C.byref(nn), C.byref(no)))
+        return nn.value, no.value
+
+    def mg_commit(self):
+        self._check(self.L.shq_mg_commit(self.h))
+
+    def mg_discard(self):
+        self._check(self.L.shq_mg_discard(self.h))
+
+    def mg_denoise_walk(self, carry, state):
+        """state: numpy uint64[16], updated in place"""
+        g = (C.c_int64 * 2)(int(carry[0]), int(carry[1]))
+        self._check(self.L.shq_mg_denoise_walk(self.h, g, state.ctypes.data))
+
+    def mg_denoise_apply(self, protect_last):
+        r = C.c_uint64()
+        self._check(self.L.shq_mg_denoise_apply(self.h, 1 if protect_last else 0, C.byref(r)))
+        return r.value
 
     def mg_layout_aggregate(self):
         g = (C.c_int64 * 2)()

@@ -82,6 +82,7 @@ struct shq_handle_s {
   DevBuf d_run_keys, d_run_counts, d_run_chunk, d_split, d_heads, d_heads64, d_scan_scratch, d_misc;
   DevBuf d_pairs, d_pos, d_flags, d_keep, d_q_in, d_q_cnt, d_q_was;
   DevBuf d_sample;
+  DevBuf d_fine2;   // offsets of the second-level bins
   DevBuf d_seg, d_fine, d_fine_cur, d_packed2, d_bases;   // second binning level (single GPU: fine bins; multi-GPU: owner-side split)
   int fine_bits_forced = -1;     // SHQ_FINE_BITS: force the second binning level (0 = off)
   // pull exchange: two fixed binned-word buffers that peers map through CUDA IPC, and the peers' buffers mapped here
@@ -89,6 +90,9 @@ struct shq_handle_s {
   size_t mg_cap_words = 0;
   std::vector<const uint32_t*> mg_peer;            // [rank * 2 + parity]
   std::vector<void*> mg_opened;                    // pointers obtained from cudaIpcOpenMemHandle
+  // staged (not yet committed) exchange batch: its run sits in d_run_*, optionally merged into the shadow state
+  struct { bool valid = false, has_shadow = false; size_t run_n = 0; uint64_t run_occ = 0, n_out = 0, n_new = 0; } mg_pending;
+  DevBuf d_walk;                 // WalkState of the sharded deNoise range walk
   int* d_err = nullptr;          // device error flag
   void* h_pinned = nullptr;      // small pinned readback area (4 KiB + chunk hist)
   size_t h_pinned_cap = 0;
@@ -196,6 +200,7 @@ struct BatchBins {
   // the binned words, the bin offsets (n_bins + 1) and, for fixed-capacity bins, the end of every bin
   const uint32_t* words = nullptr; const uint32_t* off = nullptr; const uint32_t* end = nullptr;
   int fine_bits = 0;            // second binning level applied (n_bins and lb already include it)
+  bool level1_spec = false;     // the first level used fixed-capacity bins too
   // from the sample (coarse bin 0 aggregated on its own): distinct keys / new keys per occurrence of THIS batch; < 0: none
   double ratio = -1.0, new_frac = -1.0; uint32_t sample_new = 0;
 };
@@ -313,6 +318,43 @@ void sample_batch(shq_handle_s* h, BatchBins* bb, uint32_t capbin) {
   }
 }
 
+// After the first binning level: sample the batch (coarse bin 0) and, when a coarse bin would hold more distinct keys
+// than the aggregator's table takes -- large batches of a large genome, where almost every k-mer of a batch is
+// distinct -- split every coarse bin into 2^fb fine bins (split_bins_kernel).  bb describes the coarse bins on entry
+// and the bins to aggregate on return.  max_bin_words bounds the words of one coarse bin (sizes the sample's output).
+void refine_bins(shq_handle_s* h, BatchBins* bb, uint32_t max_bin_words) {
+  cudaStream_t st = h->stream;
+  uint64_t& L = h->stats.kernels_launched;
+  sample_batch(h, bb, max_bin_words);
+  const int lb = bb->lb, n_bins = bb->n_bins;
+  const uint64_t n_ub = bb->n_keys;
+  const double ratio = bb->ratio >= 0 ? std::min(1.0, bb->ratio * 1.1) : 1.0;
+  const double est_d = (double)n_ub / (double)n_bins * ratio;
+  int fb = 0;
+  while (fb < 5 && lb - fb > 1 && est_d / (double)(1 << fb) > 3500.0) fb++;      // load factor of the aggregator's table <= ~0.45
+  if (h->fine_bits_forced >= 0) fb = std::min(h->fine_bits_forced, std::min(5, lb - 1));
+  const uint64_t n_fine = (uint64_t)n_bins << fb;
+  const uint64_t capfine = bin_capacity(h, n_ub / n_fine);
+  const uint64_t span2 = capfine * n_fine;
+  if (fb == 0 || span2 + kSplitTile + 64 >= ((uint64_t)1 << 32)) return;
+  Phase ph2(h, &h->stats.ms_split);
+  h->d_packed2.reserve((size_t)(span2 + kSplitTile + 64) * 4);
+  h->d_fine2.reserve((size_t)(n_fine + 2) * 4); h->d_fine_cur.reserve((size_t)(n_fine + 2) * 4);
+  h->d_misc.reserve(256);
+  int* d_ovf2 = h->d_misc.as<int>() + 24;
+  SHQ_CUDA(cudaMemsetAsync(d_ovf2, 0, 4, st));
+  fine_bin_offsets_kernel<<<cdiv(n_fine + 1, 256), 256, 0, st>>>(h->d_fine2.as<uint32_t>(), h->d_fine_cur.as<uint32_t>(), (uint32_t)n_fine, (uint32_t)capfine); L++;
+  int parts = 1; while (n_bins * parts < 8 * kNumSMs) parts *= 2;
+  // exact-offset bins (no cursor array): bin c ends where bin c + 1 starts
+  const uint32_t* bin_end = bb->end ? bb->end : bb->off + 1;
+  split_bins_kernel<<<n_bins * parts, kSplitThreads, 0, st>>>(bb->words, bb->off, bin_end, parts, lb, fb, h->d_fine_cur.as<uint32_t>(), (uint32_t)capfine,
+                                                            (uint32_t)span2, d_ovf2, h->d_packed2.as<uint32_t>()); L++;
+  SHQ_CUDA(cudaGetLastError());
+  h->stats.split_launches++; h->stats.split_words += n_ub;
+  bb->n_bins = (int)n_fine; bb->lb = lb - fb; bb->span = (uint32_t)span2; bb->fine_bits = fb; bb->spec = true;
+  bb->words = h->d_packed2.as<uint32_t>(); bb->off = h->d_fine2.as<uint32_t>(); bb->end = h->d_fine_cur.as<uint32_t>();
+}
+
 // Both hashing passes over the batch text (or a raw key array): count -> offsets -> scatter.
 // On return d_packed holds the binned words and d_binoff the (n_bins+1) bin offsets.
 // global_bits > 0: bin over the WHOLE key space [0, 2^hb) into 2^global_bits bins, whatever this handle's shard
@@ -392,38 +434,11 @@ void bin_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uint64_
       }
       SHQ_CUDA(cudaGetLastError());
       bb->n_bins = n_bins; bb->lb = lb; bb->n_keys = (uint32_t)n_ub; bb->armed = armed; bb->nchunks = nchunks;
-      bb->spec = true; bb->span = (uint32_t)span;
+      bb->spec = true; bb->span = (uint32_t)span; bb->level1_spec = true;
       bb->words = h->d_packed.as<uint32_t>(); bb->off = h->d_binoff.as<uint32_t>(); bb->end = h->d_tot.as<uint32_t>(); bb->fine_bits = 0;
       h->stats.keys_hashed += n_ub;
       h->stats.scatter_launches++; h->stats.scatter_text_bytes += n_text; h->stats.scatter_words += n_ub;
-      // second level: split every coarse bin into 2^fb fine bins when it would hold more distinct keys than the
-      // aggregator's table takes (the ratio of the previous batch is the estimate; a larger batch can only lower it)
-      sample_batch(h, bb, (uint32_t)capbin);
-      {
-        const double ratio = bb->ratio >= 0 ? std::min(1.0, bb->ratio * 1.1) : 1.0;
-        const double est_d = (double)n_ub / (double)n_bins * ratio;
-        int fb = 0;
-        while (fb < 5 && lb - fb > 1 && est_d / (double)(1 << fb) > 3500.0) fb++;      // load factor of the aggregator's table <= ~0.45
-        if (h->fine_bits_forced >= 0) fb = std::min(h->fine_bits_forced, std::min(5, lb - 1));
-        const uint64_t n_fine = (uint64_t)n_bins << fb;
-        const uint64_t capfine = bin_capacity(h, n_ub / n_fine);
-        const uint64_t span2 = capfine * n_fine;
-        if (fb > 0 && span2 + kSplitTile + 64 < ((uint64_t)1 << 32)) {
-          Phase ph2(h, &h->stats.ms_split);
-          h->d_packed2.reserve((size_t)(span2 + kSplitTile + 64) * 4);
-          h->d_fine.reserve((size_t)(n_fine + 2) * 4); h->d_fine_cur.reserve((size_t)(n_fine + 2) * 4);
-          int* d_ovf2 = h->d_misc.as<int>() + 24;
-          SHQ_CUDA(cudaMemsetAsync(d_ovf2, 0, 4, st));
-          fine_bin_offsets_kernel<<<cdiv(n_fine + 1, 256), 256, 0, st>>>(h->d_fine.as<uint32_t>(), h->d_fine_cur.as<uint32_t>(), (uint32_t)n_fine, (uint32_t)capfine); L++;
-          int parts = 1; while (n_bins * parts < 8 * kNumSMs) parts *= 2;
-          split_bins_kernel<<<n_bins * parts, kSplitThreads, 0, st>>>(h->d_packed.as<uint32_t>(), h->d_binoff.as<uint32_t>(), h->d_tot.as<uint32_t>(), parts, lb, fb,
-                                                                    h->d_fine_cur.as<uint32_t>(), (uint32_t)capfine, (uint32_t)span2, d_ovf2, h->d_packed2.as<uint32_t>()); L++;
-          SHQ_CUDA(cudaGetLastError());
-          h->stats.split_launches++; h->stats.split_words += n_ub;
-          bb->n_bins = (int)n_fine; bb->lb = lb - fb; bb->span = (uint32_t)span2; bb->fine_bits = fb;
-          bb->words = h->d_packed2.as<uint32_t>(); bb->off = h->d_fine.as<uint32_t>(); bb->end = h->d_fine_cur.as<uint32_t>();
-        }
-      }
+      refine_bins(h, bb, (uint32_t)capbin);
       return;
     }
   }
@@ -533,7 +548,7 @@ bool aggregate_bins(shq_handle_s* h, const BatchBins& bb, uint32_t clo, uint32_t
     bb.spec_checked = true;
     int o1 = 0, o2 = 0;
     read_pair(h, h->d_misc.as<int>() + 20, &o1, h->d_misc.as<int>() + 24, &o2);
-    if (o1 || (bb.fine_bits && o2)) throw BinOverflow{};
+    if ((bb.level1_spec && o1) || (bb.fine_bits && o2)) throw BinOverflow{};
   }
   if (split && read_scalar(h, d_ovf)) return false;
   auto finish = [&](Run* R, uint32_t* nout, uint32_t* dense, uint32_t* occs, const uint64_t* tk, const uint32_t* tc, const uint16_t* tch) {
@@ -1022,7 +1037,7 @@ void free_handle(shq_handle_s* h) {
                     &h->d_binoff, &h->d_packed, &h->d_tmp_keys, &h->d_tmp_counts, &h->d_tmp_chunk, &h->d_nout, &h->d_occ,
                     &h->d_dense_off, &h->d_run_keys, &h->d_run_counts, &h->d_run_chunk, &h->d_split, &h->d_heads, &h->d_heads64,
                     &h->d_scan_scratch, &h->d_misc, &h->d_pairs, &h->d_pos, &h->d_flags, &h->d_keep, &h->d_q_in, &h->d_q_cnt, &h->d_q_was,
-                    &h->d_tmp_keys2, &h->d_tmp_counts2, &h->d_run2_keys, &h->d_run2_counts, &h->d_seg, &h->d_fine, &h->d_fine_cur, &h->d_packed2, &h->d_bases, &h->d_sample};
+                    &h->d_tmp_keys2, &h->d_tmp_counts2, &h->d_run2_keys, &h->d_run2_counts, &h->d_seg, &h->d_fine, &h->d_fine_cur, &h->d_packed2, &h->d_bases, &h->d_sample, &h->d_fine2, &h->d_walk};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : h->pin_buf) b.release();
   for (void* p : h->mg_opened) cudaIpcCloseMemHandle(p);
@@ -1778,6 +1793,214 @@ int shq_mg_insert_pull(shq_t h, const uint32_t* d_all_fine_hist, int parity) {
     uint64_t n_new = merge_run(h, A);
     h->ndistinct += n_new; h->nelts += A.occ;
     check_err_flag(h);
+  SHQ_API_END
+}
+
+
+// ---- staged exchange batches + sharded deNoise: the building blocks of "the same job at every N" -----------------------
+// While deNoise rounds are pending, a batch may only be committed if the GLOBAL number of distinct keys stays below
+// the trigger afterwards.  shq_mg_stage_pull does everything up to that decision for this shard -- pull + split of the
+// peers' binned words, aggregation, and the count of the batch's keys that are new to the shard (by a merge into the
+// shadow state, or, for a batch much smaller than the state, by binary searches) -- and reports the shard's numbers.
+// The caller sums them over the ranks and then calls shq_mg_commit or shq_mg_discard on every rank.
+int shq_mg_stage_pull(shq_t h, const uint32_t* d_all_fine_hist, int parity, uint64_t* n_new, uint64_t* n_occ) {
+  if (!h || !d_all_fine_hist || parity < 0 || parity > 1 || !n_new || !n_occ) return SHQ_ERR_ARG;
+  struct { const uint32_t* fh; int par; uint64_t* nn; uint64_t* no; } args{d_all_fine_hist, parity, n_new, n_occ};
+  SHQ_API_BEGIN(h)
+    flush_stage(h); ensure_state(h);
+    if (h->mg_peer.empty()) SHQ_FAIL(SHQ_ERR_STATE, "shq_mg_open_peers first");
+    if (h->mg_pending.valid) SHQ_FAIL(SHQ_ERR_STATE, "a staged batch is waiting for shq_mg_commit / shq_mg_discard");
+    cudaStream_t st = h->stream;
+    uint64_t& L = h->stats.kernels_launched;
+    *a.nn = 0; *a.no = 0;
+    const int world = h->nshards;
+    int shard_bits = 0; while ((1 << shard_bits) < world) shard_bits++;
+    const int cb = kMgCoarseBits > shard_bits ? kMgCoarseBits : shard_bits + 1;
+    const int gfb = shard_bits + kMgFineBits, fb = gfb - cb;
+    const int nfg = 1 << gfb, cps = 1 << (cb - shard_bits), F = 1 << kMgFineBits;
+    const int lbc = h->hb - cb, lbf = lbc - fb;
+    uint64_t n = 0;
+    {
+      Phase ph(h, &h->stats.ms_scatter);
+      h->d_bases.reserve((size_t)world * 8 + 64);
+      std::vector<const uint32_t*> b((size_t)world);
+      for (int r = 0; r < world; r++) b[r] = h->mg_peer[r * 2 + a.par];
+      SHQ_CUDA(cudaMemcpyAsync(h->d_bases.p, b.data(), (size_t)world * 8, cudaMemcpyHostToDevice, st));
+      SHQ_CUDA(cudaStreamSynchronize(st));
+      h->d_seg.reserve(((size_t)world * (cps + 1) + 8) * 8);
+      uint64_t* seg_beg = h->d_seg.as<uint64_t>();
+      h->d_fine.reserve(((size_t)F + 2) * 4); h->d_binoff.reserve(((size_t)F + 2) * 4);
+      pull_table_kernel<<<world, kScanThreads, 0, st>>>(a.fh, world, h->shard, cps, fb, nfg, seg_beg, h->d_binoff.as<uint32_t>()); L++;
+      exclusive_scan_inplace<SumU32>(h->d_binoff.as<uint32_t>(), F, h->d_scan_scratch, st, h->d_binoff.as<uint32_t>() + F, &L);
+      SHQ_CUDA(cudaMemcpyAsync(h->d_fine.p, h->d_binoff.p, (size_t)F * 4, cudaMemcpyDeviceToDevice, st));
+      n = read_scalar(h, h->d_binoff.as<uint32_t>() + F);
+      if (n) {
+        h->d_packed.reserve((n + 4) * 4);
+        int parts = 1; while (cps * parts < 4 * kNumSMs) parts *= 2;
+        resplit_kernel<false><<<cps * parts, kSplitThreads, 0, st>>>(h->d_bases.as<const uint32_t*>(), seg_beg, world, cps, parts, lbc, fb,
+                                                                   h->d_fine.as<uint32_t>(), h->d_packed.as<uint32_t>()); L++;
+        SHQ_CUDA(cudaGetLastError());
+      }
+      // the peers' buffers of this parity have been read completely once this returns (see shq_mg_insert_pull)
+      SHQ_CUDA(cudaStreamSynchronize(st));
+    }
+    h->stats.batches++;
+    h->mg_pending = {};
+    h->mg_pending.valid = true;
+    if (n == 0) return;
+    Run A{&h->d_run_keys, &h->d_run_counts, &h->d_run_chunk};
+    for (int attempt = 0; attempt < 2; attempt++) {
+      BatchBins bb;
+      bb.n_bins = F; bb.lb = lbf; bb.n_keys = (uint32_t)n; bb.armed = false; bb.nchunks = 1;
+      bb.words = h->d_packed.as<uint32_t>(); bb.off = h->d_binoff.as<uint32_t>(); bb.end = nullptr;
+      const int forced = h->fine_bits_forced;
+      if (attempt == 1) h->fine_bits_forced = 0;        // the fixed-capacity fine bins overflowed: aggregate the bins as received
+      try {
+        refine_bins(h, &bb, (uint32_t)std::min<uint64_t>(n, (n / F) * 4 + 65536));
+        h->fine_bits_forced = forced;
+        aggregate_bins(h, bb, 0, 0xFFFFFFFFu, false, 0, &A, nullptr, nullptr);
+        break;
+      } catch (const BinOverflow&) {
+        h->fine_bits_forced = forced;
+        h->stats.bin_fallbacks++;
+        if (attempt == 1) SHQ_FAIL(SHQ_ERR_STATE, "binning overflow without fixed-capacity bins");
+      }
+    }
+    if (A.occ != n) SHQ_FAIL(SHQ_ERR_STATE, "exchange batch: %llu words aggregated, %llu expected", (unsigned long long)A.occ, (unsigned long long)n);
+    h->mg_pending.run_n = A.n; h->mg_pending.run_occ = A.occ;
+    if (h->n_state == 0) {
+      h->mg_pending.n_new = A.n;
+    } else if ((uint64_t)A.n * 24 < (uint64_t)h->n_state) {
+      // a batch much smaller than the state (locating a deNoise boundary): count its new keys by binary search
+      h->d_sample.reserve(64);
+      uint32_t* d_cnt = h->d_sample.as<uint32_t>() + 8;     // [8] = n keys, [9] = new
+      uint32_t hv[2] = {(uint32_t)A.n, 0};
+      SHQ_CUDA(cudaMemcpyAsync(d_cnt, hv, 8, cudaMemcpyHostToDevice, st));
+      count_new_kernel<<<cdiv(A.n, 256), 256, 0, st>>>(A.keys->as<uint64_t>(), d_cnt, h->st_keys.as<uint64_t>(), h->n_state, d_cnt + 1); L++;
+      h->mg_pending.n_new = read_scalar(h, d_cnt + 1);
+    } else {
+      h->mg_pending.n_out = merge_shadow(h, A, 1, nullptr);
+      h->mg_pending.has_shadow = true;
+      h->mg_pending.n_new = h->mg_pending.n_out - h->n_state;
+    }
+    check_err_flag(h);
+    *a.nn = h->mg_pending.n_new; *a.no = h->mg_pending.run_occ;
+  SHQ_API_END
+}
+
+int shq_mg_commit(shq_t h) {
+  if (!h) return SHQ_ERR_ARG;
+  int args = 0;
+  SHQ_API_BEGIN(h)
+    (void)a;
+    if (!h->mg_pending.valid) SHQ_FAIL(SHQ_ERR_STATE, "nothing staged");
+    auto pd = h->mg_pending;
+    h->mg_pending = {};
+    if (pd.run_n == 0) return;
+    uint64_t n_new;
+    if (pd.has_shadow) n_new = commit_shadow(h, pd.n_out);
+    else { Run A{&h->d_run_keys, &h->d_run_counts, &h->d_run_chunk}; A.n = pd.run_n; A.occ = pd.run_occ; n_new = merge_run(h, A); }
+    if (n_new != pd.n_new) SHQ_FAIL(SHQ_ERR_STATE, "staged batch: %llu new keys counted, %llu merged", (unsigned long long)pd.n_new, (unsigned long long)n_new);
+    h->ndistinct += n_new; h->nelts += pd.run_occ;
+    check_err_flag(h);
+  SHQ_API_END
+}
+
+int shq_mg_discard(shq_t h) {
+  if (!h) return SHQ_ERR_ARG;
+  h->mg_pending = {};
+  return SHQ_OK;
+}
+
+// One sharded deNoise sweep (cqf/CQF_mt.h:884-922) in three calls:
+//  shq_mg_denoise_walk : this shard's entries laid out behind `carry` (composition of the previous shards' layout maps,
+//      see shq_mg_layout_aggregate), then this shard's part of the range walk.  state (16 words, host) comes from the
+//      previous rank (zeros for rank 0) and goes on to the next one.
+//  shq_mg_denoise_finalize : after the last rank, closes the range that was open at the end of all entries (host only).
+//  shq_mg_denoise_apply : drops the count-1 entries except the protected ones; protect_last = bit `rank` of state[11].
+int shq_mg_denoise_walk(shq_t h, const int64_t carry[2], uint64_t state[16]) {
+  if (!h || !carry || !state) return SHQ_ERR_ARG;
+  struct { const int64_t* c; uint64_t* s; } args{carry, state};
+  SHQ_API_BEGIN(h)
+    flush_stage(h); ensure_state(h);
+    if (h->mg_pending.valid) SHQ_FAIL(SHQ_ERR_STATE, "a staged batch is waiting for shq_mg_commit / shq_mg_discard");
+    cudaStream_t st = h->stream;
+    uint64_t& L = h->stats.kernels_launched;
+    Phase ph(h, &h->stats.ms_denoise);
+    a.s[12] = h->nslots; a.s[13] = (uint64_t)h->shard;
+    const size_t n = h->n_state;
+    uint32_t keep_cap = (uint32_t)(h->nslots >> 20) + 8;
+    h->d_keep.reserve((size_t)(keep_cap + 4) * 4);
+    uint32_t* n_keep = h->d_keep.as<uint32_t>(); uint32_t* keep_idx = n_keep + 4;
+    SHQ_CUDA(cudaMemsetAsync(n_keep, 0, 16, st));
+    if (n == 0) return;       // nothing to walk: the chain passes through unchanged
+    MaxPlus init{a.c[0], a.c[1]};
+    compute_positions(h, 0, init);
+    h->d_walk.reserve(256);
+    SHQ_CUDA(cudaMemcpyAsync(h->d_walk.p, a.s, 128, cudaMemcpyHostToDevice, st));
+    denoise_walk_kernel<<<1, 32, 0, st>>>(h->st_keys.as<uint64_t>(), h->st_counts.as<uint32_t>(), h->d_pos.as<uint64_t>(), n,
+                                          h->d_walk.as<WalkState>(), keep_idx, n_keep, keep_cap); L++;
+    SHQ_CUDA(cudaGetLastError());
+    uint64_t* p = (uint64_t*)pinned(h, 128);
+    SHQ_CUDA(cudaMemcpyAsync(p, h->d_walk.p, 128, cudaMemcpyDeviceToHost, st));
+    SHQ_CUDA(cudaStreamSynchronize(st));
+    h->stats.host_syncs++;
+    memcpy(a.s, p, 128);
+  SHQ_API_END
+}
+
+int shq_mg_denoise_finalize(uint64_t state[16]) {
+  if (!state) return SHQ_ERR_ARG;
+  // the range that is open when the entries run out: the only candidate is the very last entry (state[5..10])
+  const uint64_t phase = state[0], e0 = state[2], cur_end = state[4];
+  const bool valid = state[5] != 0;
+  const uint64_t pos = state[6], end = state[7], count = state[8], gap = state[9], owner = state[10];
+  if (!valid || phase == 0) return SHQ_OK;
+  uint64_t range_end;
+  if (phase == 1) range_end = end >= e0 ? end : e0 - 1;     // slot e0 covered by the last entry: its cluster ends the range
+  else range_end = cur_end;
+  if (pos == range_end && end == range_end && count == 1 && gap) state[11] |= 1ULL << owner;
+  state[0] = 0;
+  return SHQ_OK;
+}
+
+int shq_mg_denoise_apply(shq_t h, int protect_last, uint64_t* removed) {
+  if (!h) return SHQ_ERR_ARG;
+  struct { int pl; uint64_t* r; } args{protect_last, removed};
+  SHQ_API_BEGIN(h)
+    cudaStream_t st = h->stream;
+    uint64_t& L = h->stats.kernels_launched;
+    Phase ph(h, &h->stats.ms_denoise);
+    const size_t n = h->n_state;
+    h->rounds_done++;
+    h->stats.denoise_launches++; h->stats.denoise_entries += n;
+    if (a.r) *a.r = 0;
+    if (n == 0) return;
+    uint32_t keep_cap = (uint32_t)(h->nslots >> 20) + 8;
+    uint32_t* n_keep = h->d_keep.as<uint32_t>(); uint32_t* keep_idx = n_keep + 4;
+    denoise_keep_kernel<<<cdiv(keep_cap, 128), 128, 0, st>>>(keep_idx, n_keep, keep_cap, h->st_counts.as<uint32_t>()); L++;
+    if (a.pl) {   // our last entry is the one-slot cluster a later shard's range ended on
+      uint32_t c = 0;
+      SHQ_CUDA(cudaMemcpyAsync(&c, h->st_counts.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+      SHQ_CUDA(cudaStreamSynchronize(st));
+      if (c == 1) { uint32_t z = 0; SHQ_CUDA(cudaMemcpyAsync(h->st_counts.as<uint32_t>() + (n - 1), &z, 4, cudaMemcpyHostToDevice, st)); SHQ_CUDA(cudaStreamSynchronize(st)); }
+    }
+    const size_t ntiles = (n + kScanTile - 1) / kScanTile;
+    h->d_flags.reserve((ntiles + 4) * 8);
+    uint64_t* tile_cnt = h->d_flags.as<uint64_t>();
+    denoise_tiles_kernel<false><<<(unsigned)ntiles, kScanThreads, 0, st>>>(h->st_keys.as<uint64_t>(), h->st_counts.as<uint32_t>(), n, tile_cnt, nullptr, nullptr); L++;
+    exclusive_scan_inplace<SumU64>(tile_cnt, ntiles, h->d_scan_scratch, st, tile_cnt + ntiles, &L);
+    uint64_t kept = read_scalar(h, tile_cnt + ntiles);
+    h->st_keys2.reserve((kept + 4) * 8); h->st_counts2.reserve((kept + 4) * 4);
+    denoise_tiles_kernel<true><<<(unsigned)ntiles, kScanThreads, 0, st>>>(h->st_keys.as<uint64_t>(), h->st_counts.as<uint32_t>(), n, tile_cnt,
+                                                                       h->st_keys2.as<uint64_t>(), h->st_counts2.as<uint32_t>()); L++;
+    SHQ_CUDA(cudaGetLastError());
+    std::swap(h->st_keys, h->st_keys2); std::swap(h->st_counts, h->st_counts2);
+    const uint64_t rem = n - kept;
+    h->n_state = kept;
+    h->nelts -= rem; h->ndistinct -= rem;
+    h->image_valid = false;
+    if (a.r) *a.r = rem;
   SHQ_API_END
 }
 

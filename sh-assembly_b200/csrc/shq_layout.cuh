@@ -236,6 +236,111 @@ __global__ void __launch_bounds__(32) denoise_ranges_kernel(const uint64_t* __re
   if (lane == 0) *n_keep = nk;
 }
 
+// ---- the same range walk over a SHARDED state -------------------------------------------------------------------
+// The chain of sweep ranges runs over global slot positions, so with the state sharded by key range every rank walks its
+// own entries and hands the chain over to the next rank.  The walk only ever moves forward through the entries, in three
+// resumable phases:
+//   A  seek the first entry whose quotient is >= need_q: it starts a range [start, e0 = min(start + 2^20, nslots)];
+//   B  seek the first entry whose position is > e0; the entry before it decides: it covers slot e0 -> phase C,
+//      otherwise the range ends at e0 - 1;
+//   C  follow the cluster to its end (first entry not adjacent to its predecessor).
+// At a range end the entry holding that slot is tested for the range-end rule (one-slot cluster, count 1).  What crosses
+// a shard boundary is the phase, its operands and a summary of the last entry seen (position, end, count, gap before,
+// owner), because the entry a decision is about may be the previous shard's last one (WalkState, 16 words).
+struct WalkState {
+  unsigned long long phase, need_q, e0, start, cur_end;
+  unsigned long long prev_valid, prev_pos, prev_end, prev_count, prev_gap, prev_owner;
+  unsigned long long protect_mask;     // bit r: rank r's LAST entry survives the sweep although its count is 1
+  unsigned long long nslots, rank, reserved0, reserved1;
+};
+static_assert(sizeof(WalkState) == 128, "WalkState is 16 words");
+
+struct WalkEntry { uint64_t pos, end; uint32_t count; bool gap; bool local; size_t idx; unsigned long long owner; };
+
+__device__ __forceinline__ bool walk_rule(const WalkEntry& L, uint64_t end) {
+  // cqf/gqf.c:2878-2886 + cqf/CQF_mt.h:1024: a one-slot cluster [end, end] is never visited by `while (start < end)`
+  return L.pos == end && L.end == end && L.count == 1 && L.gap;
+}
+
+__global__ void __launch_bounds__(32) denoise_walk_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts,
+                                                         const uint64_t* __restrict__ pos, size_t n, WalkState* __restrict__ state,
+                                                         uint32_t* __restrict__ keep_idx, uint32_t* __restrict__ n_keep, uint32_t keep_cap) {
+  const int lane = threadIdx.x;
+  WalkState S = *state;
+  uint32_t nk = 0;
+  const uint64_t min_len = 1ULL << 20;
+  // summary of local entry i (its predecessor is local entry i - 1, or the entry handed over by the previous shards)
+  auto entry = [&](size_t i) {
+    WalkEntry e;
+    e.pos = pos[i]; e.end = entry_end(keys, counts, pos, i); e.count = counts[i]; e.local = true; e.idx = i; e.owner = S.rank;
+    if (i > 0) e.gap = entry_end(keys, counts, pos, i - 1) + 1 < e.pos;
+    else e.gap = !S.prev_valid || S.prev_end + 1 < e.pos;
+    return e;
+  };
+  auto handed = [&]() {
+    WalkEntry e;
+    e.pos = S.prev_pos; e.end = S.prev_end; e.count = (uint32_t)S.prev_count; e.gap = S.prev_gap != 0; e.local = false; e.idx = 0; e.owner = S.prev_owner;
+    return e;
+  };
+  auto protect = [&](const WalkEntry& L) {
+    if (L.local) { if (nk < keep_cap && lane == 0) keep_idx[nk] = (uint32_t)L.idx; nk++; }
+    else S.protect_mask |= 1ULL << L.owner;
+  };
+  size_t i = 0;
+  while (i < n || false) {
+    if (S.phase == 0) {
+      const unsigned long long need = S.need_q;
+      const size_t j = warp_first_false(i, n, lane, [&](size_t x) { return (keys[x] >> 8) < need; });
+      if (j == n) { i = n; break; }
+      S.start = keys[j] >> 8;
+      S.e0 = S.start + min_len > S.nslots ? S.nslots : S.start + min_len;
+      S.phase = 1; i = j;
+    } else if (S.phase == 1) {
+      const unsigned long long e0 = S.e0;
+      const size_t lo = warp_first_false(i, n, lane, [&](size_t x) { return pos[x] <= e0; });
+      if (lo == n) { i = n; break; }
+      WalkEntry P;
+      bool have = true;
+      if (lo > 0) P = entry(lo - 1); else if (S.prev_valid) P = handed(); else have = false;
+      if (have && P.end >= e0) { S.phase = 2; S.cur_end = P.end; i = lo; }
+      else {
+        const uint64_t end = e0 - 1;
+        if (have && P.end == end && walk_rule(P, end)) protect(P);
+        S.need_q = end + 1; S.phase = 0; i = lo;
+      }
+    } else {
+      // first entry from i on that is not adjacent to its predecessor (entry i's predecessor ends at cur_end)
+      size_t j = i;
+      for (;;) {
+        const size_t x = j + lane;
+        bool adj = false;
+        if (x < n) {
+          const uint64_t pe = x == i ? S.cur_end : entry_end(keys, counts, pos, x - 1);
+          adj = pos[x] == pe + 1;
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, adj);
+        int run = __ffs(~m) - 1;
+        if (run < 0) run = 32;
+        j += run;
+        if (run < 32 || j >= n) break;
+      }
+      if (j >= n) { S.cur_end = entry_end(keys, counts, pos, n - 1); i = n; break; }     // the cluster may go on in the next shard
+      WalkEntry Lst;
+      if (j > 0) Lst = entry(j - 1); else Lst = handed();       // j == 0: the cluster ended with the handed-over entry
+      const uint64_t end = j > i ? Lst.end : S.cur_end;
+      if (walk_rule(Lst, end)) protect(Lst);
+      S.need_q = end + 1; S.phase = 0; i = j;
+    }
+  }
+  // every local entry has been passed: the last one becomes the handed-over entry
+  if (n > 0) {
+    const WalkEntry e = entry(n - 1);
+    S.prev_valid = 1; S.prev_pos = e.pos; S.prev_end = e.end; S.prev_count = e.count; S.prev_gap = e.gap ? 1 : 0; S.prev_owner = S.rank;
+    if (S.phase == 2 && S.cur_end < e.end) S.cur_end = e.end;
+  }
+  if (lane == 0) { *state = S; *n_keep = nk; }
+}
+
 __global__ void __launch_bounds__(32) tail_start_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts,
                                                        const uint64_t* __restrict__ pos, size_t n, uint64_t boundary, uint64_t* __restrict__ out) {
   size_t k = warp_first_false(0, n, threadIdx.x, [&](size_t i) { return entry_end(keys, counts, pos, i) < boundary; });

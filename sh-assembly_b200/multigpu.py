@@ -53,6 +53,82 @@ def carry_before(aggs, rank):
     return c
 
 
+def local_chunk_range(c0, c1, rank, world, n_local):
+    """The global chunk sequence of `world` read files is the reference's round robin (seqFile_batch::getDataChunk,
+    cqf/CQF_mt.h:364-390): global chunk c = round * world + rank.  Returns the local chunks [lo, hi) of `rank` that fall
+    into the global interval [c0, c1), clipped to the n_local chunks this rank has."""
+    lo = max(0, -(-(c0 - rank) // world))
+    hi = max(0, -(-(c1 - rank) // world))
+    return min(lo, n_local), min(hi, n_local)
+
+
+class TriggerSearch:
+    """Locates the deNoise boundary of the t = 1 rule (a round fires after the first chunk that leaves
+    ndistinct >= trigger, cqf/CQF_mt.h:837) WITHOUT chunk ids in the exchanged words: chunk intervals are staged
+    speculatively -- stage(c0, c1) returns the number of new keys of the interval and leaves it uncommitted --, an
+    interval that stays below the trigger is committed, one that crosses it is dropped and retried shorter.  The new-key
+    rate per chunk seen so far sizes the next attempt just short of the expected crossing, so the search ends after a
+    handful of short attempts.  Every decision uses global (all-reduced) numbers only: all ranks run the same sequence.
+
+    stage/commit/discard/fire are callables; fire() runs one sweep and returns the number of removed keys."""
+
+    def __init__(self, trigger, rounds, stage, commit, discard, fire):
+        self.trigger, self.rounds_left = int(trigger), int(rounds)
+        self.stage, self.commit, self.discard, self.fire = stage, commit, discard, fire
+        self.ndistinct = 0
+        self.nelts = 0
+        self.rate = None          # new keys per global chunk, from the last staged interval
+        self.attempts = 0
+        self.rejected = 0
+
+    def _fire(self):
+        removed = self.fire()
+        self.ndistinct -= removed
+        self.nelts -= removed
+        self.rounds_left -= 1
+
+    def feed(self, c0, c1):
+        """global chunks [c0, c1), in order"""
+        while c0 < c1:
+            if self.rounds_left <= 0:
+                new, occ = self.stage(c0, c1)
+                self.commit()
+                self.ndistinct += new
+                self.nelts += occ
+                return
+            e = c1
+            if self.ndistinct >= self.trigger:
+                e = c0 + 1                     # still over the trigger after a sweep: the next chunk fires again
+            elif self.rate is not None and self.rate > 0:
+                reach = (self.trigger - self.ndistinct) / self.rate
+                if reach < (c1 - c0):
+                    e = c0 + max(1, int(reach * 0.92))
+            new, occ = self.stage(c0, e)
+            self.attempts += 1
+            if self.ndistinct + new < self.trigger or e - c0 == 1:
+                self.commit()
+                self.ndistinct += new
+                self.nelts += occ
+                if e - c0 > 1 or self.rate is None:
+                    self.rate = new / (e - c0)
+                if self.ndistinct >= self.trigger:
+                    self._fire()
+                c0 = e
+            else:
+                self.discard()
+                self.rejected += 1
+                self.rate = new / (e - c0)
+
+    def finish(self, end_denoise):
+        """EOF rule of fastq_to_uint64kmers_prod (cqf/CQF_mt.h:858-866)"""
+        if (self.rounds_left > 0 and self.ndistinct >= self.trigger) or end_denoise:
+            removed = self.fire()
+            self.ndistinct -= removed
+            self.nelts -= removed
+            if self.rounds_left > 0:
+                self.rounds_left -= 1
+
+
 def exchange_geometry(world, coarse_bits=11, fine_total_bits=12):
     """(coarse_bits, coarse bins per shard, fine_bits): 2^coarse_bits bins over the whole key space at the source,
     every coarse bin split into 2^fine_bits at the owner so that a shard ends up with 2^fine_total_bits bins."""
@@ -142,7 +218,7 @@ class ShardedCounter:
         # (CUDA IPC, one node); "nccl" = one all-to-all of the binned 32-bit words
         self.mode = os.environ.get("SHQ_MG_EXCHANGE", "pull")
         self.parity = 0
-        self.max_batch_bytes = 256 << 20
+        self.max_batch_bytes = 1 << 30
         if self.mode == "pull":
             # every rank must end up in the same mode: if mapping a peer's buffer fails anywhere (no CUDA IPC / no peer
             # access in this environment), all ranks switch to the all-to-all exchange -- same results, more traffic
@@ -297,6 +373,133 @@ class ShardedCounter:
         t0 = tick("insert", t0)
         return nw
 
+
+    # ---------------------------------------------------------------- the same job at every N
+    def _ctl_allreduce(self, vals):
+        """sum of a few integers over the ranks (control plane)"""
+        torch = self.torch
+        if self.dist.get_backend() == "nccl":
+            t = torch.tensor([int(v) for v in vals], dtype=torch.int64, device=torch.device("cuda", self.device))
+            self.dist.all_reduce(t)
+            return [int(x) for x in t.tolist()]
+        t = torch.tensor([int(v) for v in vals], dtype=torch.int64)
+        self.dist.all_reduce(t)
+        return [int(x) for x in t.tolist()]
+
+    def _ctl_allgather_hist(self, hist, allh):
+        if self.dist.get_backend() == "nccl":
+            self.dist.all_gather_into_tensor(allh, hist)
+        else:   # gloo (two processes on one GPU in the tests): staged through the host
+            parts = [self.torch.empty(hist.numel(), dtype=hist.dtype) for _ in range(self.world)]
+            self.dist.all_gather(parts, hist.cpu())
+            allh.copy_(self.torch.cat(parts))
+
+    def _stage_interval(self, c0, c1):
+        """stage global chunks [c0, c1): every rank bins its local share, owners pull, aggregate and count new keys"""
+        torch = self.torch
+        dev = torch.device("cuda", self.device)
+        lo, hi = local_chunk_range(c0, c1, self.rank, self.world, len(self._ends))
+        a = int(self._ends[lo - 1]) if lo > 0 else 0
+        b = int(self._ends[hi - 1]) if hi > lo else a
+        nfg = self.world * 4096
+        hist = self._buf("fine_hist", nfg, torch.int32)[:nfg]
+        self.shard.mg_bin_local(self._text_ptr + a, b - a, self._K, self.parity, hist.data_ptr())
+        allh = self._buf("all_hist", self.world * nfg, torch.int32)[:self.world * nfg]
+        self._ctl_allgather_hist(hist, allh)
+        torch.cuda.ExternalStream(self.shard.stream(), device=dev).wait_stream(torch.cuda.current_stream())
+        nn, no = self.shard.mg_stage_pull(allh.data_ptr(), self.parity)
+        self.parity ^= 1
+        tot = self._ctl_allreduce([nn, no])
+        return tot[0], tot[1]
+
+    def _commit(self):
+        self.shard.mg_commit()
+
+    def _discard(self):
+        self.shard.mg_discard()
+
+    def denoise(self):
+        """One deNoise sweep over the sharded filter (exact: the reference's range hand-out incl. the range-end rule).
+        Layout carry (max-plus) -> the range walk handed from rank to rank -> local compaction.  Returns the number of
+        keys removed over all shards."""
+        torch = self.torch
+        a, b = self.shard.mg_layout_aggregate()
+        aggs = self._ctl_allgather_pairs((a, b))
+        carry = carry_before(aggs, self.rank)
+        state = np.zeros(16, np.uint64)
+        for r in range(self.world):
+            if self.rank == r:
+                self.shard.mg_denoise_walk(carry, state)
+            state = self._ctl_bcast_state(state, r)
+        self.shq.lib().shq_mg_denoise_finalize(state.ctypes.data)
+        protect = (int(state[11]) >> self.rank) & 1
+        removed = self.shard.mg_denoise_apply(protect)
+        return self._ctl_allreduce([removed])[0]
+
+    def _allgather_dev(self, allb, buf):
+        """all_gather_into_tensor for device tensors on any backend (gloo: staged through the host)"""
+        if self.dist.get_backend() == "nccl":
+            self.dist.all_gather_into_tensor(allb, buf)
+        else:
+            parts = [self.torch.empty(buf.numel(), dtype=buf.dtype) for _ in range(self.world)]
+            self.dist.all_gather(parts, buf.cpu())
+            allb.copy_(self.torch.cat(parts))
+
+    def _ctl_allgather_pairs(self, pair):
+        torch = self.torch
+        if self.dist.get_backend() == "nccl":
+            dev = torch.device("cuda", self.device)
+            mine = torch.tensor([int(pair[0]), int(pair[1])], dtype=torch.int64, device=dev)
+            allg = torch.empty(2 * self.world, dtype=torch.int64, device=dev)
+            self.dist.all_gather_into_tensor(allg, mine)
+            v = allg.view(self.world, 2).tolist()
+        else:
+            parts = [torch.empty(2, dtype=torch.int64) for _ in range(self.world)]
+            self.dist.all_gather(parts, torch.tensor([int(pair[0]), int(pair[1])], dtype=torch.int64))
+            v = [p.tolist() for p in parts]
+        return [(int(x[0]), int(x[1])) for x in v]
+
+    def _ctl_bcast_state(self, state, src):
+        torch = self.torch
+        t = torch.from_numpy(state.view(np.int64).copy())
+        if self.dist.get_backend() == "nccl":
+            t = t.to(torch.device("cuda", self.device))
+            self.dist.broadcast(t, src)
+            t = t.cpu()
+        else:
+            self.dist.broadcast(t, src)
+        return t.numpy().view(np.uint64).copy()
+
+    def count(self, d_text_ptr, n_bytes, K, chunk_ends, trigger=0, rounds=0, end_denoise=False):
+        """CQF_mt::build_KmerSpectrum over `world` read files, one per rank (this rank's text at d_text_ptr, cut into
+        the reference's chunks by chunk_ends), with the t = 1 deNoise schedule on the global chunk order.
+        Returns (global ndistinct, global nelts, sweeps done)."""
+        self._text_ptr, self._K = int(d_text_ptr), int(K)
+        self._ends = [int(e) for e in chunk_ends] if chunk_ends is not None and len(chunk_ends) else ([int(n_bytes)] if n_bytes else [])
+        R = self._ctl_allreduce_max(len(self._ends))
+        ts = TriggerSearch(trigger, rounds, self._stage_interval, self._commit, self._discard, self.denoise)
+        self.search = ts
+        j = 0
+        while j < R:
+            # rounds per batch: 32 (256 MiB of text per rank) while the shards are small, up to 128 (1 GiB) as they grow
+            grow = max(1.0, min(4.0, (ts.ndistinct / self.world) / 2.5e7))
+            rb = int(32 * grow) if not os.environ.get("SHQ_MG_ROUNDS") else int(os.environ["SHQ_MG_ROUNDS"])
+            j1 = min(R, j + rb)
+            ts.feed(j * self.world, j1 * self.world)
+            j = j1
+        ts.finish(end_denoise)
+        self.sweeps = self.shard.rounds_done()
+        return ts.ndistinct, ts.nelts
+
+    def _ctl_allreduce_max(self, v):
+        torch = self.torch
+        if self.dist.get_backend() == "nccl":
+            t = torch.tensor([int(v)], dtype=torch.int64, device=torch.device("cuda", self.device))
+        else:
+            t = torch.tensor([int(v)], dtype=torch.int64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return int(t.item())
+
     def _state_tensors(self):
         torch = self.torch
         kp, cp, n = self.shard.state_view()
@@ -314,11 +517,9 @@ class ShardedCounter:
         return self.full
 
     def global_counts(self):
-        torch = self.torch
         nd, ne = self.shard.counts()
-        t = torch.tensor([nd, ne], dtype=torch.int64, device=torch.device("cuda", self.device))
-        self.dist.all_reduce(t)
-        return int(t[0].item()), int(t[1].item())
+        t = self._ctl_allreduce([nd, ne])
+        return t[0], t[1]
 
     def end_denoise(self):
         """One exact sweep (reference range hand-out incl. the range-end rule) on the gathered global state;
@@ -367,10 +568,7 @@ class ShardedCounter:
         torch = self.torch
         dev = torch.device("cuda", self.device)
         a, b = self.shard.mg_layout_aggregate()
-        mine = torch.tensor([a, b], dtype=torch.int64, device=dev)
-        allg = torch.empty(2 * self.world, dtype=torch.int64, device=dev)
-        self.dist.all_gather_into_tensor(allg, mine)
-        aggs = [(int(x[0]), int(x[1])) for x in allg.view(self.world, 2).tolist()]
+        aggs = self._ctl_allgather_pairs((a, b))
         carry = carry_before(aggs, self.rank)
         cap = self.SPILL_CAP
         # one buffer per rank: [n_tail | keys | pos | counts] as int64 words
@@ -379,7 +577,7 @@ class ShardedCounter:
         nt = self.shard.mg_layout_tail(carry, cap, kp.data_ptr(), cp.data_ptr(), pp.data_ptr())
         buf[0] = nt
         allb = self._buf("spill_all", self.world * (1 + 3 * cap), torch.int64)[:self.world * (1 + 3 * cap)]
-        self.dist.all_gather_into_tensor(allb, buf)
+        self._allgather_dev(allb, buf)
         n_spill = 0
         sk = sc = sp = 0
         if self.rank > 0:

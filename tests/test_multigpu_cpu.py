@@ -132,3 +132,73 @@ def test_owner_rule():
     keys = np.array([0, (1 << 28) - 1, 1 << 28, (1 << 30) - 1], np.uint64)
     assert mg.owner_of(keys, hb, 4).tolist() == [0, 0, 1, 3]
     assert mg.owner_of(keys, hb, 1).tolist() == [0, 0, 0, 0]
+
+
+def test_local_chunk_range_partitions_the_round_robin():
+    mg = importlib.import_module("sh-assembly_b200.multigpu")
+    world, n_local = 4, [5, 5, 4, 3]
+    for c0, c1 in [(0, 20), (3, 9), (7, 8), (0, 1), (13, 40), (6, 6)]:
+        got = []
+        for r in range(world):
+            lo, hi = mg.local_chunk_range(c0, c1, r, world, n_local[r])
+            got += [j * world + r for j in range(lo, hi)]
+        want = [c for c in range(c0, c1) if (c // world) < n_local[c % world]]
+        assert sorted(got) == want
+
+
+def test_trigger_search_reproduces_the_t1_schedule():
+    """TriggerSearch over a fake key stream: rounds fire after exactly the chunks the sequential t = 1 rule names."""
+    mg = importlib.import_module("sh-assembly_b200.multigpu")
+    rng = np.random.default_rng(5)
+    for trial in range(6):
+        nchunks = int(rng.integers(20, 120))
+        chunks = [rng.integers(0, 3000 + 400 * c, size=int(rng.integers(50, 400))) for c in range(nchunks)]   # keys drift: new keys keep coming
+        trigger, rounds = int(rng.integers(800, 3000)), int(rng.integers(1, 4))
+        end = bool(trial % 2)
+        # sequential reference: count -> fire after the first chunk that leaves ndistinct >= trigger; a sweep drops count-1 keys
+        state, left, fired_ref = {}, rounds, []
+        for c, ks in enumerate(chunks):
+            for k in ks.tolist():
+                state[k] = state.get(k, 0) + 1
+            if left and len(state) >= trigger:
+                left -= 1
+                state = {k: v for k, v in state.items() if v != 1}
+                fired_ref.append(c)
+        if (left and len(state) >= trigger) or end:
+            state = {k: v for k, v in state.items() if v != 1}
+            fired_ref.append("eof")
+        # the search: staged intervals against a committed state
+        st = {"state": {}, "pending": None, "fired": [], "last": -1}
+
+        def stage(c0, c1):
+            add = {}
+            for c in range(c0, c1):
+                for k in chunks[c].tolist():
+                    add[k] = add.get(k, 0) + 1
+            st["pending"] = (add, c1 - 1)
+            return sum(1 for k in add if k not in st["state"]), sum(add.values())
+
+        def commit():
+            add, last = st["pending"]
+            for k, v in add.items():
+                st["state"][k] = st["state"].get(k, 0) + v
+            st["last"] = last
+            st["pending"] = None
+
+        def discard():
+            st["pending"] = None
+
+        def fire():
+            before = len(st["state"])
+            st["state"] = {k: v for k, v in st["state"].items() if v != 1}
+            st["fired"].append(st["last"])
+            return before - len(st["state"])
+
+        ts = mg.TriggerSearch(trigger, rounds, stage, commit, discard, fire)
+        for b0 in range(0, nchunks, 32):
+            ts.feed(b0, min(nchunks, b0 + 32))
+        n_mid = len(st["fired"])
+        ts.finish(end)
+        fired = st["fired"][:n_mid] + (["eof"] if len(st["fired"]) > n_mid else [])
+        assert fired == fired_ref, (trial, fired, fired_ref)
+        assert st["state"] == state and ts.ndistinct == len(state) and ts.nelts == sum(state.values())

@@ -310,7 +310,7 @@ def run_workload(args, name, steps, warmup, local_rank, want_unitigs, want_cpu):
     parity = {"image_sha256": sha, "expected": gold["image_sha256"] if gold else None,
               "match": bool(gold) and sha == gold["image_sha256"] and int(ndistinct) == gold["ndistinct"] and int(nelts) == gold["nelts"]
               and int(rounds) == gold["denoise_rounds"],
-              "oracle": gold["made_by"] if gold else "no committed digest for this workload (tests/golden/digests.json)"}
+              "checker": gold["made_by"] if gold else "no committed digest for this workload (tests/golden/digests.json)"}
     if gold and not parity["match"]:
         parity["expected_counters"] = {k: gold[k] for k in ("ndistinct", "nelts", "denoise_rounds")}
         print("bench.py: PARITY FAILED on %s: %s" % (name, json.dumps(parity)), file=sys.stderr)

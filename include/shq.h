@@ -96,6 +96,9 @@ int shq_insert_keys_device(shq_t h, const uint64_t* d_keys, size_t n);
  * chunks, runs the --endDeNoise round if scheduled, fixes nelts/ndistinct.       */
 int shq_finish(shq_t h);
 int shq_sync(shq_t h);
+/* waits until every host buffer handed to shq_insert_fastq_pinned so far has been read (its H2D copy is complete);
+ * does not wait for the compute                                                                                    */
+int shq_sync_copies(shq_t h);
 
 /* replaces runtime->ndistinct_elts / runtime->nelts (cqf/CQF_mt.h:279-280).     */
 int shq_counts(shq_t h, uint64_t* ndistinct, uint64_t* nelts);
@@ -248,6 +251,9 @@ int shq_reader_open_memory(const char* const* bufs, const size_t* lens, int nfil
                            shq_reader_t* out);
 /* next chunk; *chunk == NULL at the end.  The buffer stays valid until the next call. */
 int shq_reader_next(shq_reader_t r, const char** chunk, size_t* n, int* file_index);
+/* page-lock the reader's chunk buffers (cudaHostRegister) so that chunks can go to the device with asynchronous copies
+ * (shq_insert_fastq_pinned); SHQ_ERR_CUDA if that is not possible -- the staged path still works then.        */
+int shq_reader_pin(shq_reader_t r);
 void shq_reader_close(shq_reader_t r);
 /* CQF_mt::build_KmerSpectrum (cqf/CQF_mt.h:959-995): every chunk of the reader goes into the
  * filter under the schedule set by shq_set_denoise_schedule, then shq_finish.           */

@@ -71,7 +71,7 @@ EXPORTS = [
     "shq_load", "shq_load_image", "shq_geometry", "shq_iterate", "shq_query_set_traveled", "shq_query",
     "shq_hash_fastq_chunk", "shq_unitigs_begin", "shq_unitigs_set_seed_rule", "shq_unitigs_add_reads", "shq_unitigs_build", "shq_unitigs_count",
     "shq_unitigs_write_fasta", "shq_unitigs_fasta", "shq_unitigs_free", "shq_get_stats", "shq_reset_stats", "shq_stream",
-    "shq_reader_open", "shq_reader_open_memory", "shq_reader_next", "shq_reader_close", "shq_build_kmer_spectrum",
+    "shq_reader_open", "shq_reader_open_memory", "shq_reader_next", "shq_reader_pin", "shq_reader_close", "shq_sync_copies", "shq_build_kmer_spectrum",
     "shq_materialize", "shq_param_block", "shq_cdfpoi_positive", "shq_cdfpoi",
     "shq_mg_setup", "shq_mg_open_peers", "shq_mg_bin_local", "shq_mg_insert_pull",
     "shq_mg_stage_pull", "shq_mg_commit", "shq_mg_discard", "shq_mg_denoise_walk", "shq_mg_denoise_finalize", "shq_mg_denoise_apply",
@@ -158,6 +158,8 @@ def lib():
         L.shq_reader_open.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_char, C.POINTER(vp)]
         L.shq_reader_open_memory.argtypes = [C.POINTER(vp), C.POINTER(sz), C.c_int, u64, C.POINTER(vp)]
         L.shq_reader_next.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(C.c_int)]
+        L.shq_reader_pin.argtypes = [vp]
+        L.shq_sync_copies.argtypes = [vp]
         L.shq_reader_close.argtypes = [vp]
         L.shq_reader_close.restype = None
         L.shq_build_kmer_spectrum.argtypes = [vp, vp, C.c_int]

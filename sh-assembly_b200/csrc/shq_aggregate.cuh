@@ -555,6 +555,201 @@ __global__ void __launch_bounds__(kMergeThreads) merge_tiles_lookback_kernel(
   for (uint32_t i = threadIdx.x; i < tot; i += blockDim.x) { out_keys[o + i] = s_ok[i]; out_counts[o + i] = s_oc[i]; }
 }
 
+// ---- the same single-pass merge as a PERSISTENT kernel fed by the TMA engine ------------------------------------
+// Each CTA loops over tickets; the four input slices of its NEXT tile (keys and counts of A and B, contiguous in HBM)
+// are fetched by bulk asynchronous copies (cp.async.bulk.shared::cluster.global with mbarrier::complete_tx) into the other
+// half of a two-stage shared-memory ring while the current tile is merged, so the loads cost no issue slots and their
+// latency hides behind the merge of the previous tile.  Bulk copies move multiples of 16 bytes from 16-byte aligned
+// addresses: every slice is fetched from the aligned element at or below its first one and indexed with that offset.
+namespace tma {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// bytes: a multiple of 16; src and dst 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+}  // namespace tma
+
+struct MergeTileDesc {       // what the consumer needs to know about a staged tile
+  unsigned long long t;      // ticket (ntiles = none)
+  unsigned long long a0, b0;
+  int la, lbn, da, db, dac, dbc;
+  int a_first, b_last_real;  // a0 == 0 (no key before the tile) ; b1 < nb (B[b1] exists)
+};
+constexpr int kMergeTmaKeys = kMergeTile + 8;      // per input, incl. alignment slack
+constexpr size_t kMergeTmaStage = (size_t)kMergeTmaKeys * 8 * 2 + (size_t)kMergeTmaKeys * 4 * 2;
+constexpr size_t kMergeTmaSmem = 2 * kMergeTmaStage;
+template <bool HIST>
+__global__ void __launch_bounds__(kMergeThreads) merge_tiles_tma_kernel(
+    const uint64_t* __restrict__ A, const uint32_t* __restrict__ Ac, size_t na, const uint64_t* __restrict__ B,
+    const uint32_t* __restrict__ Bc, size_t nb, const uint64_t* __restrict__ a_split, size_t ntiles,
+    unsigned long long* status /* ntiles words, zeroed */, unsigned int* ticket /* zeroed */, uint64_t* __restrict__ out_keys,
+    uint32_t* __restrict__ out_counts, unsigned long long* __restrict__ n_out_total, int* __restrict__ err,
+    const uint16_t* __restrict__ Bchunk = nullptr, uint32_t* __restrict__ chunk_hist = nullptr) {
+  extern __shared__ __align__(128) unsigned char merge_smem[];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ MergeTileDesc s_desc[2];
+  __shared__ unsigned long long s_prefix;
+  __shared__ uint32_t s_hist[HIST ? kMergeHistMax : 1];
+  if (HIST) for (int i = threadIdx.x; i < kMergeHistMax; i += blockDim.x) s_hist[i] = 0;
+  if (threadIdx.x == 0) { tma::mbar_init(&s_bar[0], 1); tma::mbar_init(&s_bar[1], 1); tma::fence_mbar_init(); }
+  __syncthreads();
+  auto stage_ptr = [&](int st, int which) -> unsigned char* {   // which: 0 keys A, 1 keys B, 2 counts A, 3 counts B
+    unsigned char* base = merge_smem + (size_t)st * kMergeTmaStage;
+    if (which == 0) return base;
+    if (which == 1) return base + (size_t)kMergeTmaKeys * 8;
+    if (which == 2) return base + (size_t)kMergeTmaKeys * 16;
+    return base + (size_t)kMergeTmaKeys * 16 + (size_t)kMergeTmaKeys * 4;
+  };
+  // thread 0: take a ticket and start the bulk copies of that tile into stage st
+  auto fetch = [&](int st) {
+    MergeTileDesc d;
+    d.t = atomicAdd(ticket, 1u);
+    if (d.t >= ntiles) { d.t = ntiles; s_desc[st] = d; return; }
+    size_t diag0 = d.t * kMergeTile, diag1 = diag0 + kMergeTile;
+    if (diag1 > na + nb) diag1 = na + nb;
+    const size_t a0 = a_split[d.t], a1 = a_split[d.t + 1];
+    const size_t b0 = diag0 - a0, b1 = diag1 - a1;
+    d.a0 = a0; d.b0 = b0; d.la = (int)(a1 - a0); d.lbn = (int)(b1 - b0);
+    d.a_first = a0 == 0; d.b_last_real = b1 < nb;
+    // keys A: want A[a0 - 1 .. a1); fetched from the even element at or below a0 - 1 (a0 - 1 itself is patched in when a0 is even)
+    const size_t ka = (a0 & ~(size_t)1);
+    d.da = (int)(a0 - ka);                                   // keys of the tile start at element da of the fetched slice
+    const uint32_t nA = (uint32_t)((d.la + d.da + 1) & ~1);
+    const size_t kb = (b0 & ~(size_t)1);
+    d.db = (int)(b0 - kb);
+    const uint32_t nB = (uint32_t)((d.lbn + 1 + d.db + 1) & ~1);
+    const size_t kac = (a0 & ~(size_t)3);
+    d.dac = (int)(a0 - kac);
+    const uint32_t nAc = (uint32_t)((d.la + d.dac + 3) & ~3);
+    const size_t kbc = (b0 & ~(size_t)3);
+    d.dbc = (int)(b0 - kbc);
+    const uint32_t nBc = (uint32_t)((d.lbn + 1 + d.dbc + 3) & ~3);
+    s_desc[st] = d;
+    const uint32_t bytes = nA * 8 + nB * 8 + nAc * 4 + nBc * 4;
+    tma::mbar_expect_tx(&s_bar[st], bytes);
+    // element 2 of the key buffers / element 4.. keep 16-byte alignment: slices land at byte offset 16
+    if (nA) tma::bulk_g2s(stage_ptr(st, 0) + 16, A + ka, nA * 8, &s_bar[st]);
+    if (nB) tma::bulk_g2s(stage_ptr(st, 1) + 16, B + kb, nB * 8, &s_bar[st]);
+    if (nAc) tma::bulk_g2s(stage_ptr(st, 2) + 16, Ac + kac, nAc * 4, &s_bar[st]);
+    if (nBc) tma::bulk_g2s(stage_ptr(st, 3) + 16, Bc + kbc, nBc * 4, &s_bar[st]);
+  };
+  uint32_t phase[2] = {0, 0};
+  if (threadIdx.x == 0) fetch(0);
+  __syncthreads();
+  const uint64_t kNone = ~0ULL;
+  for (int cur = 0;; cur ^= 1) {
+    const MergeTileDesc d = s_desc[cur];
+    if (d.t >= ntiles) break;
+    if (threadIdx.x == 0) fetch(cur ^ 1);                    // the next tile streams in while this one is merged
+    tma::mbar_wait(&s_bar[cur], phase[cur]); phase[cur] ^= 1;
+    // s_a[0] = A[a0 - 1] (or none), s_a[1 + i] = A[a0 + i];  s_b[i] = B[b0 + i], s_b[lbn] = B[b1] (or none)
+    uint64_t* s_a = reinterpret_cast<uint64_t*>(stage_ptr(cur, 0) + 16) + d.da - 1;
+    uint64_t* s_b = reinterpret_cast<uint64_t*>(stage_ptr(cur, 1) + 16) + d.db;
+    uint32_t* s_ac = reinterpret_cast<uint32_t*>(stage_ptr(cur, 2) + 16) + d.dac;
+    uint32_t* s_bc = reinterpret_cast<uint32_t*>(stage_ptr(cur, 3) + 16) + d.dbc;
+    if (threadIdx.x == 0) {
+      if (d.da == 0) s_a[0] = d.a_first ? kNone : A[d.a0 - 1];      // the element below an even a0 is not part of the slice
+      else if (d.a_first) s_a[0] = kNone;                            // (cannot happen: a0 == 0 is even)
+      if (!d.b_last_real) s_b[d.lbn] = kNone;
+    }
+    __syncthreads();
+    const size_t a0 = d.a0, b0 = d.b0;
+    const int la = d.la, lbn = d.lbn;
+    const int total = la + lbn;
+    int d0 = min(threadIdx.x * kMergeItems, total), d1 = min(d0 + kMergeItems, total);
+    int lo = max(0, d0 - lbn), hi = min(d0, la);
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (s_a[1 + mid] <= s_b[d0 - mid - 1]) lo = mid + 1; else hi = mid;
+    }
+    int ai = lo, bi = d0 - lo;
+    uint32_t nheads = 0;
+    uint64_t okey[kMergeItems]; uint32_t ocnt[kMergeItems];
+    for (int dd = d0; dd < d1; dd++) {
+      bool takeA = (bi >= lbn) || (ai < la && s_a[1 + ai] <= s_b[bi]);
+      if (takeA) {
+        uint64_t k = s_a[1 + ai];
+        uint64_t nextb = s_b[bi];
+        uint64_t c = s_ac[ai];
+        if (nextb == k) c += s_bc[bi];
+        if (c > 0xFFFFFFFFull) { *err = SHQ_ERR_COUNT_OVERFLOW; c = 0xFFFFFFFFull; }
+        okey[nheads] = k; ocnt[nheads] = (uint32_t)c;
+        nheads++; ai++;
+      } else {
+        uint64_t k = s_b[bi];
+        uint64_t preva = s_a[ai];
+        if (preva != k || (ai == 0 && a0 == 0)) {
+          okey[nheads] = k; ocnt[nheads] = s_bc[bi]; nheads++;
+          if (HIST) { const uint32_t ch = Bchunk[b0 + bi]; if (ch < (uint32_t)kMergeHistMax) atomicAdd(&s_hist[ch], 1u); else atomicAdd(&chunk_hist[ch], 1u); }
+        }
+        bi++;
+      }
+    }
+    uint32_t tot;
+    uint32_t rank = block_exclusive_scan<SumU32>(nheads, &tot);      // ends with a barrier: every thread is done with the inputs
+    uint64_t* s_ok = reinterpret_cast<uint64_t*>(stage_ptr(cur, 0) + 16);
+    uint32_t* s_oc = reinterpret_cast<uint32_t*>(stage_ptr(cur, 2) + 16);
+    for (uint32_t i = 0; i < nheads; i++) { s_ok[rank + i] = okey[i]; s_oc[rank + i] = ocnt[i]; }
+    const size_t t = d.t;
+    if (threadIdx.x < 32) {               // warp 0: publish, then look back 32 predecessors at a time
+      const int lane = threadIdx.x;
+      unsigned long long excl = 0;
+      if (t == 0) {
+        if (lane == 0) atomicExch(&status[0], (2ULL << 62) | (unsigned long long)tot);
+      } else {
+        if (lane == 0) atomicExch(&status[t], (1ULL << 62) | (unsigned long long)tot);
+        long long p = (long long)t - 1;   // lane l looks at tile p - l
+        for (;;) {
+          const long long q = p - lane;
+          unsigned long long v = 2ULL << 62;              // tiles before 0: an inclusive prefix of 0
+          if (q >= 0) { do { v = *reinterpret_cast<volatile unsigned long long*>(&status[q]); } while ((v >> 62) == 0); }
+          const unsigned incl = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+          const int first = incl ? __ffs(incl) - 1 : 32;  // nearest predecessor that already knows its inclusive prefix
+          unsigned long long part = lane <= first ? (v & kLbValue) : 0;
+          for (int s2 = 16; s2; s2 >>= 1) part += __shfl_down_sync(0xffffffffu, part, s2);
+          excl += __shfl_sync(0xffffffffu, part, 0);
+          if (first < 32) break;
+          p -= 32;
+        }
+        if (lane == 0) atomicExch(&status[t], (2ULL << 62) | (excl + tot));
+      }
+      if (lane == 0) {
+        s_prefix = excl;
+        if (t == ntiles - 1) *n_out_total = excl + tot;
+      }
+    }
+    __syncthreads();
+    const size_t o = (size_t)s_prefix;
+    for (uint32_t i = threadIdx.x; i < tot; i += blockDim.x) { out_keys[o + i] = s_ok[i]; out_counts[o + i] = s_oc[i]; }
+    __syncthreads();                                         // the stage is free again ...
+    if (threadIdx.x == 0) tma::fence_proxy_async();           // ... and the generic-proxy accesses to it are ordered before the next bulk copy
+  }
+  if (HIST) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kMergeHistMax; i += blockDim.x) { const uint32_t v = s_hist[i]; if (v) atomicAdd(&chunk_hist[i], v); }
+  }
+}
+
 // u32 -> u64 widening (scan input)
 __global__ void widen_u32_kernel(const uint32_t* __restrict__ in, uint64_t* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -63,6 +63,7 @@ struct shq_handle_s {
   // tunables (environment, read once per handle in init_handle)
   bool spec_bins = true;         // SHQ_SPEC_BINS=0 forces the two-pass (count, then scatter) binning
   bool merge_lookback = true;    // SHQ_MERGE_LOOKBACK=0: count pass + scan + write pass instead of the single-pass merge
+  bool merge_tma = false;        // SHQ_MERGE_TMA=1: persistent single-pass merge with inputs staged by bulk async copies
   int bin_bits = 0;              // SHQ_BIN_BITS: 0 = automatic
   // progress lines of the reference scheduler on stderr (cqf/CQF_mt.h:867-868, 912)
   bool log_progress = false; uint64_t ndistinct_true = 0;
@@ -613,6 +614,18 @@ uint64_t merge_shadow(shq_handle_s* h, const Run& R, int nchunks, std::vector<ui
     unsigned long long* status = h->d_heads64.as<unsigned long long>();
     unsigned long long* d_nout = status + ntiles; unsigned int* ticket = (unsigned int*)(status + ntiles + 1);
     SHQ_CUDA(cudaMemsetAsync(status, 0, (ntiles + 2) * 8, st));
+    if (h->merge_tma) {
+      // persistent CTAs, inputs staged by the TMA engine (cp.async.bulk + mbarrier), two stages per CTA
+      SHQ_CUDA(cudaFuncSetAttribute(merge_tiles_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMergeTmaSmem));
+      SHQ_CUDA(cudaFuncSetAttribute(merge_tiles_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMergeTmaSmem));
+      const unsigned grid = (unsigned)std::min<size_t>(ntiles, (size_t)kNumSMs * 2);   // 2 CTAs of 78 KB fit an SM
+      if (d_hist)
+        merge_tiles_tma_kernel<true><<<grid, kMergeThreads, kMergeTmaSmem, st>>>(A, Ac, na, Bk, Bc, nb, h->d_split.as<uint64_t>(), ntiles, status, ticket,
+                                                                              h->st_keys2.as<uint64_t>(), h->st_counts2.as<uint32_t>(), d_nout, h->d_err, Bch, d_hist);
+      else
+        merge_tiles_tma_kernel<false><<<grid, kMergeThreads, kMergeTmaSmem, st>>>(A, Ac, na, Bk, Bc, nb, h->d_split.as<uint64_t>(), ntiles, status, ticket,
+                                                                               h->st_keys2.as<uint64_t>(), h->st_counts2.as<uint32_t>(), d_nout, h->d_err);
+    } else {
     SHQ_CUDA(cudaFuncSetAttribute(merge_tiles_lookback_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMergeLbSmem));
     SHQ_CUDA(cudaFuncSetAttribute(merge_tiles_lookback_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMergeLbSmem));
     if (d_hist)
@@ -621,6 +634,7 @@ uint64_t merge_shadow(shq_handle_s* h, const Run& R, int nchunks, std::vector<ui
     else
       merge_tiles_lookback_kernel<false><<<(unsigned)ntiles, kMergeThreads, kMergeLbSmem, st>>>(A, Ac, na, Bk, Bc, nb, h->d_split.as<uint64_t>(), ntiles, status, ticket,
                                                                                  h->st_keys2.as<uint64_t>(), h->st_counts2.as<uint32_t>(), d_nout, h->d_err);
+    }
     L++;
     SHQ_CUDA(cudaGetLastError());
     if (d_hist) {      // total and histogram with one round trip
@@ -1013,6 +1027,7 @@ void init_handle(shq_handle_s* h, int qb, int hb, uint32_t seed, int device, int
   if (const char* e = getenv("SHQ_SPEC_BINS")) h->spec_bins = atoi(e) != 0;
   if (const char* e = getenv("SHQ_FINE_BITS")) { int v = atoi(e); if (v >= 0 && v <= 5) h->fine_bits_forced = v; }
   if (const char* e = getenv("SHQ_MERGE_LOOKBACK")) h->merge_lookback = atoi(e) != 0;
+  if (const char* e = getenv("SHQ_MERGE_TMA")) h->merge_tma = atoi(e) != 0;
   if (const char* e = getenv("SHQ_BIN_BITS")) { int v = atoi(e); if (v >= 4 && v <= 13) h->bin_bits = v; }
   SHQ_CUDA(cudaSetDevice(device));
   h->device = device; h->qb = qb; h->hb = hb; h->seed = seed; h->shard = shard; h->nshards = nshards;
@@ -1266,6 +1281,13 @@ int shq_sync(shq_t h) {
     flush_stage(h);
     SHQ_CUDA(cudaStreamSynchronize(h->stream));
   SHQ_API_END
+}
+
+int shq_sync_copies(shq_t h) {
+  if (!h) return SHQ_ERR_ARG;
+  if (!h->cstream) return SHQ_OK;
+  cudaSetDevice(h->device);
+  return cudaStreamSynchronize(h->cstream) == cudaSuccess ? SHQ_OK : SHQ_ERR_CUDA;
 }
 
 int shq_finish(shq_t h) {

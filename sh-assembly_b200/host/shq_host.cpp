@@ -22,6 +22,8 @@
 #include <thread>
 #include <vector>
 
+#include <cuda_runtime.h>
+
 #include "../../include/shq.h"
 
 namespace {
@@ -103,6 +105,14 @@ bool skip_next_eol(const char* part, int64_t& pos, int64_t max_pos) {
 }  // namespace
 
 struct shq_reader_s {
+  bool pin = false;                    // chunk buffers are page-locked (cudaHostRegister) so that H2D copies can be asynchronous
+  std::vector<void*> registered;
+  void pin_buffer(std::vector<char>& v) {
+    if (!pin || v.empty()) return;
+    void* p = v.data();
+    for (void* q : registered) if (q == p) return;
+    if (cudaHostRegister(p, v.size(), cudaHostRegisterDefault) == cudaSuccess) registered.push_back(p); else { (void)cudaGetLastError(); pin = false; }
+  }
   std::deque<Source*> queue;           // FIFO of open inputs (round-robin)
   std::vector<std::unique_ptr<Source>> all;
   int num_files = 0;
@@ -115,7 +125,7 @@ struct shq_reader_s {
   // 1 = chunk produced (size in *size), 0 = this input is exhausted, <0 = error
   int read_parts(Source* s, std::vector<char>& part, size_t* size) {
     const int64_t OVERHEAD_SIZE = 65535;
-    part.resize(part_size + OVERHEAD_SIZE);
+    if (part.size() != part_size + OVERHEAD_SIZE) { part.resize(part_size + OVERHEAD_SIZE); std::lock_guard<std::mutex> g(err_mu); pin_buffer(part); }
     size_t part_filled = s->tail.size();
     if (part_filled) memcpy(part.data(), s->tail.data(), part_filled);
     if (s->eof()) return 0;
@@ -272,19 +282,34 @@ int shq_reader_next(shq_reader_t r, const char** chunk, size_t* n, int* file_ind
 void shq_reader_close(shq_reader_t r) {
   if (!r) return;
   for (auto& s : r->all) { r->stop_prefetch(s.get()); s->close(); }
+  for (void* p : r->registered) cudaHostUnregister(p);
   delete r;
+}
+
+int shq_reader_pin(shq_reader_t r) {
+  if (!r) return SHQ_ERR_ARG;
+  std::lock_guard<std::mutex> g(r->err_mu);
+  r->pin = true;
+  for (auto& s : r->all) for (auto& b : s->owned) r->pin_buffer(*b);
+  r->pin_buffer(r->part_serial);
+  return r->pin ? SHQ_OK : SHQ_ERR_CUDA;
 }
 
 int shq_build_kmer_spectrum(shq_t h, shq_reader_t r, int K) {
   if (!h || !r) return SHQ_ERR_ARG;
+  // the reader's chunk buffers are page-locked, so every chunk goes to the device with an asynchronous copy on the
+  // handle's copy stream straight out of the buffer the producer thread filled (no staging memcpy), overlapping the
+  // compute of the previous batch; the buffer goes back to its producer once that copy has landed
+  const bool pinned = shq_reader_pin(r) == SHQ_OK;
   for (;;) {
     const char* chunk = nullptr; size_t n = 0;
+    if (pinned) { int rc = shq_sync_copies(h); if (rc) return rc; }     // shq_reader_next recycles the previous chunk's buffer
     int rc = shq_reader_next(r, &chunk, &n, nullptr);
     if (rc) return rc;
     if (!chunk) break;
     // an empty chunk (no record boundary found, cut == 0) is still a chunk boundary for the deNoise trigger
     // (cqf/CQF_mt.h:829-839), so it is passed on
-    rc = shq_insert_fastq_chunk(h, chunk, n, K);
+    rc = (pinned && n) ? shq_insert_fastq_pinned(h, chunk, n, K) : shq_insert_fastq_chunk(h, chunk, n, K);
     if (rc) return rc;
   }
   return shq_finish(h);

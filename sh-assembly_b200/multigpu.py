@@ -403,6 +403,12 @@ class ShardedCounter:
         b = int(self._ends[hi - 1]) if hi > lo else a
         nfg = self.world * 4096
         hist = self._buf("fine_hist", nfg, torch.int32)[:nfg]
+        evs = getattr(self, "h2d_events", None)
+        if evs:      # end-to-end runs: the text of this interval must have landed
+            for off, ev in evs:
+                ev.synchronize()
+                if off >= b:
+                    break
         self.shard.mg_bin_local(self._text_ptr + a, b - a, self._K, self.parity, hist.data_ptr())
         allh = self._buf("all_hist", self.world * nfg, torch.int32)[:self.world * nfg]
         self._ctl_allgather_hist(hist, allh)
@@ -665,16 +671,13 @@ def bench_sharded(args, rank, world, local_rank, B):
     args.k = w["K"]
     sc = ShardedCounter(int(p.qb), int(p.hb), rank, world, local_rank, dist)
 
+    trigger, rounds, end = int(p.trigger), int(p.num_deNoise), bool(w["end"])
+
     def step():
         sc.reset()
-        import time
-        sc.insert_fastq_device(d_text.data_ptr(), len(text), args.k, ends)
-        t0 = time.perf_counter()
+        nd_, ne_ = sc.count(d_text.data_ptr(), n_bytes, w["K"], ends, trigger=trigger, rounds=rounds, end_denoise=end)
         sc.materialize_sharded()
-        t0 = sc._tick("materialize_sharded", t0)
-        r = sc.global_counts()
-        sc._tick("global_counts", t0)
-        return r
+        return nd_, ne_
 
     for _ in range(args.warmup):
         step()
@@ -686,6 +689,7 @@ def bench_sharded(args, rank, world, local_rank, B):
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    dist.barrier()
     e0.record()
     for _ in range(args.steps):
         nd, ne = step()
@@ -698,16 +702,31 @@ def bench_sharded(args, rank, world, local_rank, B):
     st = sc.shard.stats()
     launches = torch.tensor([st["kernels_launched"]], dtype=torch.int64, device=dev)
     dist.all_reduce(launches)
+    search = (sc.search.attempts, sc.search.rejected)
+    sweeps = sc.sweeps
 
-    # end to end: pinned host text -> H2D (side stream, batch by batch) -> exchange + insert -> shard image -> D2H
+    # end to end: pinned host text -> H2D in 64 MiB slices on a side stream (a batch is binned as soon as its slices have
+    # landed) -> exchange + insert -> shard image -> D2H
     import time
-    d_buf = d_text
     _, _, nb_blocks = sc.materialize_sharded()
     h_img = torch.empty(nb_blocks * 89, dtype=torch.uint8).pin_memory()
+    cs = torch.cuda.Stream(device=dev)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
 
     def step_e2e():
         sc.reset()
-        sc.insert_fastq_pinned(h_text, d_buf, args.k, ends)
+        cs.wait_stream(torch.cuda.current_stream())
+        evs = []
+        with torch.cuda.stream(cs):
+            for a0 in range(0, n_bytes, 64 << 20):
+                b0 = min(n_bytes, a0 + (64 << 20))
+                d_text[a0:b0].copy_(h_text[a0:b0], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                evs.append((b0, ev))
+        sc.h2d_events = evs
+        sc.count(d_text.data_ptr(), n_bytes, w["K"], ends, trigger=trigger, rounds=rounds, end_denoise=end)
+        sc.h2d_events = None
         img, _, nbk = sc.materialize_sharded()
         h_img[:nbk * 89].copy_(torch.as_tensor(_DevView(img, nbk * 89, "|u1"), device=dev))
         torch.cuda.synchronize()
@@ -715,13 +734,28 @@ def bench_sharded(args, rank, world, local_rank, B):
     step_e2e()
     dist.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         step_e2e()
     dist.barrier()
-    ms_e2e = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], dtype=torch.float64, device=dev)
+    ms_e2e = torch.tensor([(time.perf_counter() - t0) * 1e3 / e2e_steps], dtype=torch.float64, device=dev)
     dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
-    io = torch.tensor([len(text), nb_blocks * 89], dtype=torch.int64, device=dev)
+    io = torch.tensor([n_bytes, nb_blocks * 89], dtype=torch.int64, device=dev)
     dist.all_reduce(io)
+    # parity: the sharded image against the digest of the unmodified reference core run over the same N read files
+    gold = B.golden_digest(name, world)
+    parity = {"image_sha256": None, "expected": gold["image_sha256"] if gold else None, "match": False,
+              "checker": gold["made_by"] if gold else "no committed digest for %s@%d (tests/golden/digests.json)" % (name, world)}
+    if gold:
+        import hashlib
+        parts = [None] * world
+        dist.all_gather_object(parts, (sc.rank, bytes(h_img[:nb_blocks * 89].numpy())))
+        if rank == 0:
+            parts.sort(key=lambda x: x[0])
+            hsh = hashlib.sha256(sc.shard.header(int(nd), int(ne)))
+            for _, bts in parts:
+                hsh.update(bts)
+            parity["image_sha256"] = hsh.hexdigest()
+            parity["match"] = parity["image_sha256"] == gold["image_sha256"] and int(nd) == gold["ndistinct"] and int(ne) == gold["nelts"] and sweeps == gold["denoise_rounds"]
     if rank == 0 and os.environ.get("SHQ_MG_TIMING"):
         import sys
         print("mg timing (ms, warmup+timed steps):", {k: round(v, 2) for k, v in sc._timing.items()}, {k: round(v, 2) for k, v in st.items() if k.startswith("ms_")}, file=sys.stderr)
@@ -746,7 +780,9 @@ def bench_sharded(args, rank, world, local_rank, B):
                 "gpu_launches": int(launches.item()),
                 "roofline": {"bound": "hbm", "kernel": "whole sharded insert path", "achieved": value * a_ins / 1e9 / world, "peak": peak, "unit": "GB/s",
                              "frac": value * a_ins / 1e9 / world / peak, "traffic": None, "note": "per GPU, against SURVEY 8(d) A_ins"},
-                "result": {"ndistinct": int(nd), "nelts": int(ne), "kmers_per_step": int(n_total)}}
+                "result": {"ndistinct": int(nd), "nelts": int(ne), "denoise_rounds": int(sweeps), "kmers_per_step": int(n_total),
+                           "boundary_search": {"staged_intervals": search[0], "rejected": search[1]}},
+                "parity": parity}
         print(json.dumps(line))
     dist.barrier()
     dist.destroy_process_group()

@@ -30,8 +30,28 @@ def digest(name, world=1):
     N = wl.n_kmers(w)
     p = po.param_block(w["K"], w["n_true"], N, alpha=w["err"], deNoise=w["deNoise"])
     t0 = time.time()
-    text = synth.cpu_fill(sp, 0, sp.n_reads)
-    ends = po.chunk_ends(text.ctypes.data, text.nbytes)
+    if world == 1:
+        text = synth.cpu_fill(sp, 0, sp.n_reads)
+        ends = po.chunk_ends(text.ctypes.data, text.nbytes)
+    else:
+        # `world` read files, one per rank; at t = 1 the reference takes their chunks round robin
+        # (seqFile_batch::getDataChunk, cqf/CQF_mt.h:364-390): the same job as the chunk-interleaved text below
+        import numpy as np
+        files, cuts = [], []
+        for r in range(world):
+            first, n = synth.rank_slice(sp, r, world)
+            f = synth.cpu_fill(sp, first, n)
+            e = po.chunk_ends(f.ctypes.data, f.nbytes)
+            files.append(f)
+            cuts.append([0] + [int(x) for x in e])
+        pieces = []
+        for j in range(max(len(c) - 1 for c in cuts)):
+            for r in range(world):
+                if j + 1 < len(cuts[r]):
+                    pieces.append(files[r][cuts[r][j]:cuts[r][j + 1]])
+        text = np.concatenate(pieces)
+        ends = np.cumsum([len(x) for x in pieces]).astype(np.uint64)
+        del files, pieces
     print("%s: %d reads, %.2f GB of text, %d chunks, qb=%d rounds=%d trigger=%d (%.0f s)" % (
         name, sp.n_reads, text.nbytes / 1e9, len(ends), p.qb, p.num_deNoise, p.trigger, time.time() - t0), flush=True)
     th = hashlib.sha256(memoryview(text)).hexdigest()

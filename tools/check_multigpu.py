@@ -1,4 +1,6 @@
-"""torchrun --nproc-per-node N tools/check_multigpu.py : sharded counting vs the oracle (bit-exact .cqf)."""
+"""torchrun --nproc-per-node N tools/check_multigpu.py : the sharded filter on N real GPUs against the t = 1 oracle over N
+read files -- counters, deNoise sweeps, the sharded image (bit-exact .cqf) and the unitigs -- with a deNoise schedule
+whose boundaries fall inside batches."""
 import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -10,27 +12,28 @@ def main():
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    shq = importlib.import_module("sh-assembly_b200")
     mg = importlib.import_module("sh-assembly_b200.multigpu")
-    K, qb = 31, 20 + (world.bit_length() - 1)      # the read set grows with the world size, so does the filter
+    os.environ.setdefault("SHQ_MG_ROUNDS", "6")
+    K, qb, part = 31, 20 + (world.bit_length() - 1), 1 << 18      # the read set grows with the world size, so does the filter
     texts = [po.synth_fastq(G=100000, cov=30, err=0.004, n_rate=0.0003, seed=50 + r) for r in range(world)]
     text = np.frombuffer(texts[rank], np.uint8)
+    ends, off = [], 0
+    for _, ch in shq.Reader(buffers=[text], part_size=part):
+        off += len(ch); ends.append(off)
     d = torch.empty(len(text) + 64, dtype=torch.uint8, device="cuda")
     d[:len(text)].copy_(torch.from_numpy(text.copy()))
     torch.cuda.synchronize()
-    for end in (False, True):
+    for trigger, rounds, end in ((0, 0, False), (130000 * world, 2, True), (110000 * world, 4, False)):
         sc = mg.ShardedCounter(qb, qb + 8, rank, world, lr, dist)
-        sc.insert_fastq_device(d.data_ptr(), len(text), K)
-        removed = sc.end_denoise() if end else 0
-        img = sc.export()
-        img2 = sc.export_sharded()
-        nd, ne = sc.global_counts()
+        nd, ne = sc.count(d.data_ptr(), len(text), K, ends, trigger=trigger, rounds=rounds, end_denoise=end)
+        img = sc.export_sharded()
         if rank == 0:
-            o, _ = po.count_run(texts, K, qb, qb + 8, 0, 0, end)
+            o, orounds = po.count_run(texts, K, qb, qb + 8, trigger, rounds, end, part_size=part)
             ok = img == o.export()
-            ok2 = img2 == o.export()
-            print("world", world, "endDeNoise", end, "removed", removed, "counts", (nd, ne), o.counts(), "image equal:", ok,
-                  "sharded image equal:", ok2, flush=True)
-            assert ok and ok2 and (nd, ne) == o.counts()
+            print("world", world, "schedule", (trigger, rounds, end), "sweeps", sc.sweeps, orounds, "counts", (nd, ne), o.counts(),
+                  "sharded image equal:", ok, "search", (sc.search.attempts, sc.search.rejected), flush=True)
+            assert ok and (nd, ne) == o.counts() and sc.sweeps == orounds
         if end:
             fa = sc.build_unitigs(texts if rank == 0 else None, K)
             if rank == 0:

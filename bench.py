@@ -331,6 +331,7 @@ def run_workload(args, name, steps, warmup, local_rank, want_unitigs, want_cpu):
             "parity": parity}
     if want_unitigs:
         line["unitig"] = bench_unitigs(args, shq, q, text, ends, h_ptr, K)
+        line["cli"] = bench_cli(args, shq, text, w, p, name)
     if want_cpu:
         from oracle import pyoracle as po
         if po.ref() is None:
@@ -347,12 +348,12 @@ def run_workload(args, name, steps, warmup, local_rank, want_unitigs, want_cpu):
 
 def bench_unitigs(args, shq, q, text, ends, h_ptr, K):
     """Second half of the BASELINE metric: seconds to build the unitig graph (Contiger) from the filter just
-    counted, reads given as host chunks; beside it the sequential CPU restatement on a bounded sample."""
+    counted, reads given as host chunks; beside it the sequential CPU restatement of Contiger (1 core)."""
     L = shq.lib()
     opts = shq.shq_unitig_opts(K, 2, 2, 1000000)
-    best = None
+    times = []
     info = {}
-    for rep in range(3):
+    for rep in range(4):      # the first build allocates the device buffers; they stay with the handle afterwards
         u = C.c_void_p()
         t0 = time.perf_counter()
         q._check(L.shq_unitigs_begin(q.h, C.byref(opts), C.byref(u)))
@@ -365,9 +366,15 @@ def bench_unitigs(args, shq, q, text, ends, h_ptr, K):
         n, tot = C.c_size_t(), C.c_size_t()
         L.shq_unitigs_count(u, C.byref(n), C.byref(tot))
         L.shq_unitigs_free(u)
-        best = dt if best is None else min(best, dt)
+        times.append(dt)
         info = {"n_unitigs": n.value, "total_bases": tot.value}
-    out = {"seconds": best, "unit": "s", "config": "Contiger -k %d -s 2 -x 2 -X 1000000 on the filter of this run, reads from pinned host chunks" % K}
+    best = min(times[1:])
+    steps = max(0, info["total_bases"] - (K - 1) * info["n_unitigs"])       # k-mers appended to unitigs = extension steps
+    peak, peak_src = peak_hbm()
+    out = {"seconds": best, "unit": "s", "seconds_all_runs": times,
+           "config": "Contiger -k %d -s 2 -x 2 -X 1000000 on the filter of this run, reads from pinned host chunks (H2D inside the time)" % K,
+           "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak, "achieved": steps * 623 / best / 1e9, "frac": steps * 623 / best / 1e9 / peak,
+                        "extension_steps": steps, "note": "SURVEY 8(d) A_ext = 7 probes x 89 bytes per k-mer appended to a unitig; whole build incl. H2D of the reads"}}
     out.update(info)
     if args.unitig_cpu:
         from oracle import pyoracle as po
@@ -376,9 +383,44 @@ def bench_unitigs(args, shq, q, text, ends, h_ptr, K):
         t0 = time.perf_counter()
         fa, nq = po.contiger_run(o, [text.tobytes()], K)
         out["cpu_baseline"] = {"seconds": time.perf_counter() - t0, "cores": 1, "kind": "port",
-                               "sample": "whole read set, sequential restatement of Contiger over a hash-map CQF model",
+                               "sample": "whole read set; sequential restatement of Contiger (oracle/contiger_oracle.cpp, pinned to the reference "
+                                         "binary's output by tests/test_contiger_ref.py) over a hash-map CQF model",
                                "n_unitigs": len(po.parse_unitigs(fa)), "cqf_queries": int(nq)}
     return out
+
+
+def bench_cli(args, shq, text, w, p, name):
+    """file -> .cqf through the drop-in command line (bin/CQF-deNoise): the read set written to tmpfs, wall clock of the
+    whole process (CUDA context, reader threads, page-locked chunk buffers, asynchronous copies, counting, shq_save)."""
+    import tempfile
+    d = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    tmp = tempfile.mkdtemp(dir=d)
+    try:
+        fq = os.path.join(tmp, "reads.fq")
+        with open(fq, "wb") as f:
+            f.write(memoryview(text))
+        with open(os.path.join(tmp, "list.txt"), "w") as f:
+            f.write("reads.fq\n")
+        exe = os.path.join(ROOT, "sh-assembly_b200", "bin", "CQF-deNoise")
+        cmd = [exe, "-k", str(w["K"]), "-n", str(w["n_true"]), "-N", str(wl.n_kmers(w)), "-e", str(w["err"]), "--deNoise", str(w["deNoise"]),
+               "-t", "16", "-f", "f", "-i", os.path.join(tmp, "list.txt"), "-o", os.path.join(tmp, "out.cqf")]
+        if w["end"]:
+            cmd.append("--endDeNoise")
+        best = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            dt = time.perf_counter() - t0
+            if r.returncode:
+                return {"error": (r.stderr or "")[-300:]}
+            best = dt if best is None else min(best, dt)
+        sha = hashlib.sha256(open(os.path.join(tmp, "out.cqf"), "rb").read()).hexdigest()
+        gold = golden_digest(name, 1)
+        return {"seconds": best, "unit": "s", "kmers_per_s": wl.n_kmers(w) / best, "command": " ".join(cmd[:1] + cmd[1:13]) + " ...",
+                "input": "plain FASTQ on tmpfs, %d bytes" % text.nbytes, "image_sha256_matches_reference": bool(gold) and sha == gold["image_sha256"]}
+    finally:
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 def run_ours(args, rank, world, local_rank):
@@ -401,6 +443,9 @@ def run_ours(args, rank, world, local_rank):
         if "unitig" in sec:
             line["unitig"] = sec["unitig"]
             line["unitig"]["workload"] = args.secondary
+        if "cli" in sec:
+            line["cli"] = sec["cli"]
+            line["cli"]["workload"] = args.secondary
     print(json.dumps(line))
     if not line["parity"]["match"] and line["parity"]["expected"]:
         raise SystemExit(3)
@@ -417,7 +462,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--e2e-steps", type=int, default=5, help="timed steps of the end-to-end leg (at most --steps)")
     ap.add_argument("--unitigs", type=int, default=1, help="also time the Contiger device path (unitig build seconds)")
-    ap.add_argument("--unitig-cpu", type=int, default=0, help="also time the sequential CPU restatement of Contiger")
+    ap.add_argument("--unitig-cpu", type=int, default=1, help="also time the sequential CPU restatement of Contiger (about 20 s on the E. coli-size set)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -20,7 +20,7 @@ namespace shq {
 // duplicates and sorting the distinct keys are the same pass.  Two CTAs of 512 threads share an SM.
 constexpr int kAggThreads = 512;
 constexpr int kAggWarps = kAggThreads / 32;
-constexpr int kAggHomes = 8192;          // home positions; even ones are used, so a key is looked up as a pair of slots
+constexpr int kAggHomes = 8192;          // home positions (a power of two)
 constexpr int kAggPad = 256;             // slots behind the last home: probing never wraps around
 constexpr int kAggTable = kAggHomes + kAggPad;
 constexpr int kAggMaxProbe = kAggPad - 2;   // a longer probe sequence means skewed keys: restart with narrower key ranges
@@ -56,11 +56,11 @@ struct AggOut {
 struct AggTable {
   uint32_t* key; uint32_t* cnt; uint16_t* chk;
   volatile uint32_t* overflow; int* split_overflow;
-  uint32_t relmask; int hshift;       // home of a key: ((key & relmask) >> hshift, or << -hshift) << 1
+  uint32_t relmask; int hshift;       // home of a key: (key & relmask) >> hshift (or << -hshift): monotone, all kAggHomes slots
 };
 __device__ __forceinline__ uint32_t agg_home(const AggTable& T, uint32_t kl) {
   const uint32_t rel = kl & T.relmask;
-  return (T.hshift >= 0 ? (rel >> T.hshift) : (rel << (-T.hshift))) << 1;
+  return T.hshift >= 0 ? (rel >> T.hshift) : (rel << (-T.hshift));
 }
 
 // 16-bit minimum on a shared-memory half word (rarely taken: bins receive their words in chunk order)
@@ -118,7 +118,7 @@ __device__ __forceinline__ bool agg_place(const AggTable& T, uint32_t kl, uint32
 // Streams the bin through the table.  Every warp works on its own tiles of 256 words.
 //  DIRECT (most words are first occurrences, e.g. a batch of a large genome): find-or-insert per word.
 //  otherwise (30-100x coverage inside the batch):
-//   pass 1 (all lanes, no loop): one probe of the home pair; a word whose key sits there is counted on the spot,
+//   pass 1 (all lanes, no loop): one probe of the home slot and its neighbour; a word whose key sits there is counted on the spot,
 //           every other word is appended to the warp's pending list;
 //   pass 2 (dense over the pending list): find-or-insert.
 // Other warps may insert while a warp probes: a probe then sees either "empty" (-> pending -> found in pass 2)
@@ -155,9 +155,9 @@ __device__ __forceinline__ void agg_insert_pass(const uint32_t* __restrict__ pac
         continue;
       }
       const uint32_t h0 = agg_home(T, kl);
-      const uint2 pr = *reinterpret_cast<const uint2*>(&T.key[h0]);
-      const bool hit = live & ((pr.x == kl) | (pr.y == kl));
-      const uint32_t h = h0 + (pr.y == kl ? 1u : 0u);
+      const uint32_t p0 = T.key[h0], p1 = T.key[h0 + 1];          // the home slot and its neighbour
+      const bool hit = live & ((p0 == kl) | (p1 == kl));
+      const uint32_t h = h0 + (p1 == kl ? 1u : 0u);
       if (SPLIT) {
         if (hit) agg_count<SPLIT, CHUNK>(T, h, ch, second);
       } else {
@@ -242,7 +242,7 @@ restart:
     {
       const uint32_t max_chunk = lb >= 32 ? 0u : (0xFFFFFFFFu >> lb);
       const bool filt = sub_bits != 0 || chunk_lo != 0 || chunk_hi < max_chunk;   // sub_bits includes the grid's fixed bits
-      AggTable T{t_key, t_cnt, t_chk, &s_overflow, o.split_overflow, relmask, bits - 12};
+      AggTable T{t_key, t_cnt, t_chk, &s_overflow, o.split_overflow, relmask, bits - 13};
 #define SHQ_AGG_CALL(F, D) agg_insert_pass<SPLIT, CHUNK, F, D>(packed, beg, end, lb, lowmask, chunk_lo, chunk_hi, cstar, sub_bits, r, T, s_pend, &s_nocc, &s_nocc2)
       if (o.direct) { if (filt) SHQ_AGG_CALL(true, true); else SHQ_AGG_CALL(false, true); }
       else { if (filt) SHQ_AGG_CALL(true, false); else SHQ_AGG_CALL(false, false); }

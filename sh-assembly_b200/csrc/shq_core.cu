@@ -21,6 +21,8 @@
 using namespace shq;
 
 struct PhaseTimer;
+struct shq_unitigs_s;
+extern "C" void shq_unitigs_release(shq_unitigs_s* u);
 
 struct shq_handle_s {
   int device = 0;
@@ -98,6 +100,7 @@ struct shq_handle_s {
   void* h_pinned = nullptr;      // small pinned readback area (4 KiB + chunk hist)
   size_t h_pinned_cap = 0;
 
+  void* unitig_cache = nullptr;  // parked shq_unitigs_s of the last unitig build (its device buffers are reused)
   shq_stats stats;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> ev_pool;                 // free timing events
@@ -1047,6 +1050,7 @@ void free_handle(shq_handle_s* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->unitig_cache) { shq_unitigs_s* u = (shq_unitigs_s*)h->unitig_cache; h->unitig_cache = nullptr; shq_unitigs_release(u); }
   DevBuf* bufs[] = {&h->st_keys, &h->st_counts, &h->st_keys2, &h->st_counts2, &h->image, &h->d_text, &h->d_nl_tiles, &h->d_nl_pos,
                     &h->d_chunk_ends, &h->d_chunk_line_end, &h->d_chunk_keys, &h->d_chunk_hist, &h->d_slow, &h->d_hist, &h->d_tot,
                     &h->d_binoff, &h->d_packed, &h->d_tmp_keys, &h->d_tmp_counts, &h->d_tmp_chunk, &h->d_nout, &h->d_occ,

@@ -1005,8 +1005,13 @@ int shq_unitigs_begin(shq_t h, const shq_unitig_opts* opts, shq_unitigs_t* out) 
     h->last_error = "unitigs need 2 <= K <= 64, -s >= 1 and -x >= -s";
     return SHQ_ERR_ARG;
   }
-  shq_unitigs_s* u = new shq_unitigs_s();
+  // the device buffers of the previous build on this handle are kept (shq_unitigs_free parks the object in the
+  // handle), so a repeated build allocates nothing
+  shq_unitigs_s* u = h->unitig_cache ? (shq_unitigs_s*)h->unitig_cache : new shq_unitigs_s();
+  h->unitig_cache = nullptr;
   u->h = h; u->opts = *opts;
+  u->built = false; u->master_rule = false; u->n_seed_slots = 0; u->st_fill = 0; u->st_ends.clear(); u->n_queries = 0;
+  u->seqs.clear(); u->km.clear(); u->after.clear(); u->before.clear(); u->fasta.clear(); u->seeds.clear();
   struct { shq_unitigs_s* u; } args{u};
   int rc = guard(h, [](shq_handle_s* h, void* ap) {
     shq_unitigs_s* u = ((decltype(args)*)ap)->u;
@@ -1182,6 +1187,15 @@ int shq_unitigs_write_fasta(shq_unitigs_t u, const char* path) {
   return w == u->fasta.size() ? SHQ_OK : SHQ_ERR_IO;
 }
 void shq_unitigs_free(shq_unitigs_t u) {
+  if (!u) return;
+  if (u->h && !u->h->unitig_cache) {       // park the object (and its device buffers) for the next build on this handle
+    u->seqs.clear(); u->seqs.shrink_to_fit(); u->fasta.clear(); u->fasta.shrink_to_fit(); u->km.clear(); u->after.clear(); u->before.clear();
+    u->h->unitig_cache = u;
+    return;
+  }
+  shq_unitigs_release(u);
+}
+void shq_unitigs_release(shq_unitigs_s* u) {
   if (!u) return;
   cudaSetDevice(u->h->device);
   shq::DevBuf* bufs[] = {&u->lo, &u->hi, &u->state, &u->count, &u->fh, &u->rh, &u->list, &u->nn, &u->aux, &u->outdeg, &u->succ, &u->smask, &u->next,

@@ -14,8 +14,10 @@ _u64p = C.c_void_p
 
 
 def build(ref=True):
-    """Compile liboracle.so (always) and _ref/libshq_ref.so (when /root/reference exists)."""
-    subprocess.run(["make", "-s", "-C", HERE, "liboracle.so"] + (["ref"] if ref else []), check=True,
+    """Compile liboracle.so (always) and, when /root/reference exists, the checkers made of UNMODIFIED reference sources:
+    _ref/libshq_ref.so (gqf.c + nthash.hpp), _ref/Contiger_ref and _ref/CQF-deNoise_ref (the two command lines, compiled
+    against the header stand-ins of oracle/shim)."""
+    subprocess.run(["make", "-s", "-C", HERE, "liboracle.so"] + (["ref", "contiger_ref", "cqf_denoise_ref"] if ref else []), check=True,
                    stdout=subprocess.DEVNULL)
 
 

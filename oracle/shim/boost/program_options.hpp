@@ -132,7 +132,7 @@ inline void store(const parsed_options& p, variables_map& vm) {
   }
   for (auto& o : p.desc->opts) {
     if (vm.count(o.key)) continue;
-    if (o.sem->has_default_ && !o.sem->is_switch_) vm.put(o.key, variable_value(o.sem->default_value_any(), true));
+    if (o.sem->has_default_) vm.put(o.key, variable_value(o.sem->default_value_any(), true));     // bool_switch() defaults to false
   }
 }
 inline void notify(variables_map& vm) {

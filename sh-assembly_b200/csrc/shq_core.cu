@@ -1142,6 +1142,7 @@ int shq_reset(shq_t h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   h->n_state = 0; h->ndistinct = 0; h->nelts = 0; h->new_rate = -1.0; h->ratio_seen = false; h->distinct_ratio = 0.125;
+  h->mg_pending = {};
   h->image_valid = false; h->image_only = false;
   h->trigger = 0; h->rounds_left = 0; h->end_denoise = false; h->rounds_done = 0; h->finished = false;
   h->h_stage_fill = 0; h->stage_chunk_ends.clear();
@@ -1191,13 +1192,7 @@ int shq_insert_fastq_pinned(shq_t h, const char* text, size_t n, int K) {
   if (n == 0) return SHQ_OK;
   struct { const char* text; size_t n; int K; } args{text, n, K};
   SHQ_API_BEGIN(h)
-    if (h->h_stage_fill) {            // keep chunk order if the staged path was used before
-      size_t nn = h->h_stage_fill;
-      h->d_text.reserve(nn + 64);
-      SHQ_CUDA(cudaMemcpyAsync(h->d_text.p, h->h_stage, nn, cudaMemcpyHostToDevice, h->stream));
-      std::vector<uint64_t> ends; ends.swap(h->stage_chunk_ends); h->h_stage_fill = 0;
-      process_batch(h, h->d_text.as<char>(), nn, ends.data(), (int)ends.size(), h->stage_K, nullptr, 0);
-    }
+    if (h->h_stage_fill || !h->stage_chunk_ends.empty()) flush_stage(h);     // keep chunk order if the staged path was used before
     if (a.n >= ((size_t)1 << 31)) SHQ_FAIL(SHQ_ERR_ARG, "chunk too large");
     if (!h->cstream) SHQ_CUDA(cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking));
     if (h->pin_fill && (h->pin_K != a.K || h->pin_fill + a.n > h->pin_cap || h->pin_ends.size() >= batch_chunk_cap(h))) {

@@ -111,7 +111,7 @@ struct shq_reader_s {
     if (!pin || v.empty()) return;
     void* p = v.data();
     for (void* q : registered) if (q == p) return;
-    if (cudaHostRegister(p, v.size(), cudaHostRegisterDefault) == cudaSuccess) registered.push_back(p); else { (void)cudaGetLastError(); pin = false; }
+    if (cudaHostRegister(p, v.size(), cudaHostRegisterPortable) == cudaSuccess) registered.push_back(p); else { (void)cudaGetLastError(); pin = false; }
   }
   std::deque<Source*> queue;           // FIFO of open inputs (round-robin)
   std::vector<std::unique_ptr<Source>> all;

@@ -175,6 +175,12 @@ int shq_mg_discard(shq_t h);
 int shq_mg_denoise_walk(shq_t h, const int64_t carry[2], uint64_t state[16]);
 int shq_mg_denoise_finalize(uint64_t state[16]);
 int shq_mg_denoise_apply(shq_t h, int protect_last, uint64_t* removed);
+/* Sharded image across processes: shq_mg_image_ipc = CUDA IPC handle (64 bytes) of this rank's block array (after
+ * shq_mg_materialize_shard); a rank that opens all of them (shq_mg_open_image_peers, world x 64 bytes rank-major) sees
+ * the WHOLE filter: the query and unitig kernels load from (and set traveled bits in) the owners' HBM directly.      */
+int shq_mg_image_ipc(shq_t h, void* ipc_handle_out);
+int shq_mg_open_image_peers(shq_t h, const void* all_handles, int world);
+int shq_mg_close_image_peers(shq_t h);
 int shq_mg_bin_fastq_device(shq_t h, const char* d_text, size_t n, int K, int coarse_bits, const uint32_t** d_words,
                             const uint32_t** d_bin_off, size_t* n_words);
 int shq_mg_insert_binned(shq_t h, const uint32_t* d_recv, const uint64_t* seg_start, const uint32_t* d_counts, int world,
@@ -226,6 +232,9 @@ typedef struct {
 } shq_unitig_opts;
 typedef struct shq_unitigs_s* shq_unitigs_t;
 int shq_unitigs_begin(shq_t h, const shq_unitig_opts* opts, shq_unitigs_t* out);
+/* the same over a sharded filter (multi-GPU): h is one rank's shard whose peers' images were opened with
+ * shq_mg_open_image_peers; global_ndistinct (all shards) sizes the node table                                      */
+int shq_unitigs_begin_sharded(shq_t h, const shq_unitig_opts* opts, uint64_t global_ndistinct, shq_unitigs_t* out);
 /* Which k-mer of a read seeds the traversal.  The reference has two consumers of read chunks with different rules: its
  * worker threads take the k-mer at len/2 - K/2 (contig_assembly.cpp:1859-1863; the default here: with -t 16 workers
  * see 16 of every 17 chunks), its master thread the one at len/2 (:2067-2071).  The rules differ only in which small

@@ -74,6 +74,7 @@ EXPORTS = [
     "shq_reader_open", "shq_reader_open_memory", "shq_reader_next", "shq_reader_pin", "shq_reader_close", "shq_sync_copies", "shq_build_kmer_spectrum",
     "shq_materialize", "shq_param_block", "shq_cdfpoi_positive", "shq_cdfpoi",
     "shq_mg_setup", "shq_mg_open_peers", "shq_mg_bin_local", "shq_mg_insert_pull",
+    "shq_mg_image_ipc", "shq_mg_open_image_peers", "shq_mg_close_image_peers", "shq_unitigs_begin_sharded",
     "shq_mg_stage_pull", "shq_mg_commit", "shq_mg_discard", "shq_mg_denoise_walk", "shq_mg_denoise_finalize", "shq_mg_denoise_apply",
     "shq_mg_bin_fastq_device", "shq_mg_insert_binned", "shq_mg_layout_aggregate", "shq_mg_layout_tail", "shq_mg_materialize_shard", "shq_header",
     "shq_hash_fastq_device", "shq_partition_keys_device", "shq_state_view", "shq_adopt_state", "shq_set_counts", "shq_copy_device",
@@ -141,6 +142,10 @@ def lib():
         L.shq_mg_open_peers.argtypes = [vp, vp, C.c_int]
         L.shq_mg_bin_local.argtypes = [vp, vp, sz, C.c_int, C.c_int, vp, C.POINTER(sz)]
         L.shq_mg_insert_pull.argtypes = [vp, vp, C.c_int]
+        L.shq_mg_image_ipc.argtypes = [vp, vp]
+        L.shq_mg_open_image_peers.argtypes = [vp, vp, C.c_int]
+        L.shq_mg_close_image_peers.argtypes = [vp]
+        L.shq_unitigs_begin_sharded.argtypes = [vp, C.POINTER(shq_unitig_opts), u64, C.POINTER(vp)]
         L.shq_mg_stage_pull.argtypes = [vp, vp, C.c_int, C.POINTER(u64), C.POINTER(u64)]
         L.shq_mg_commit.argtypes = [vp]
         L.shq_mg_discard.argtypes = [vp]
@@ -182,12 +187,16 @@ def param_block(K, n_true, N_total, alpha=-1.0, error_profile="", deNoise=-1, fr
     return out
 
 
-def build_unitigs(cqf, chunks, K, s_min=2, x_min=2, x_max=1000000, master_rule=False):
-    """Contiger device path: returns the unitig FASTA text (BCALM/Minia style headers)."""
+def build_unitigs(cqf, chunks, K, s_min=2, x_min=2, x_max=1000000, master_rule=False, global_ndistinct=None):
+    """Contiger device path: returns the unitig FASTA text (BCALM/Minia style headers).
+    global_ndistinct: cqf is one shard of a sharded filter whose peers' images are open (multi-GPU)."""
     L = lib()
     opts = shq_unitig_opts(K, s_min, x_min, x_max)
     u = C.c_void_p()
-    cqf._check(L.shq_unitigs_begin(cqf.h, C.byref(opts), C.byref(u)))
+    if global_ndistinct is None:
+        cqf._check(L.shq_unitigs_begin(cqf.h, C.byref(opts), C.byref(u)))
+    else:
+        cqf._check(L.shq_unitigs_begin_sharded(cqf.h, C.byref(opts), int(global_ndistinct), C.byref(u)))
     try:
         if master_rule:
             cqf._check(L.shq_unitigs_set_seed_rule(u, 1))
@@ -455,6 +464,18 @@ class CQF:
 
     def mg_insert_pull(self, d_all_hist, parity):
         self._check(self.L.shq_mg_insert_pull(self.h, d_all_hist, parity))
+
+    def mg_image_ipc(self) -> bytes:
+        buf = np.zeros(64, np.uint8)
+        self._check(self.L.shq_mg_image_ipc(self.h, buf.ctypes.data))
+        return buf.tobytes()
+
+    def mg_open_image_peers(self, all_handles: bytes, world):
+        a = np.frombuffer(all_handles, np.uint8)
+        self._check(self.L.shq_mg_open_image_peers(self.h, a.ctypes.data, world))
+
+    def mg_close_image_peers(self):
+        self._check(self.L.shq_mg_close_image_peers(self.h))
 
     def mg_stage_pull(self, d_all_hist, parity):
         """(new keys, occurrences) of this shard's share of the batch; commit or discard afterwards"""

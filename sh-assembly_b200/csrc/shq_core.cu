@@ -93,6 +93,8 @@ struct shq_handle_s {
   size_t mg_cap_words = 0;
   std::vector<const uint32_t*> mg_peer;            // [rank * 2 + parity]
   std::vector<void*> mg_opened;                    // pointers obtained from cudaIpcOpenMemHandle
+  // sharded image: every rank's block array (own + peers mapped through CUDA IPC), for queries / the unitig build
+  std::vector<uint8_t*> img_peer; std::vector<void*> img_opened; DevBuf d_img_peer;
   // staged (not yet committed) exchange batch: its run sits in d_run_*, optionally merged into the shadow state
   struct { bool valid = false, has_shadow = false; size_t run_n = 0; uint64_t run_occ = 0, n_out = 0, n_new = 0; } mg_pending;
   DevBuf d_walk;                 // WalkState of the sharded deNoise range walk
@@ -1060,6 +1062,8 @@ void free_handle(shq_handle_s* h) {
   for (DevBuf* b : bufs) b->release();
   for (auto& b : h->pin_buf) b.release();
   for (void* p : h->mg_opened) cudaIpcCloseMemHandle(p);
+  for (void* p : h->img_opened) cudaIpcCloseMemHandle(p);
+  h->d_img_peer.release();
   for (uint32_t* p : h->mg_send) if (p) cudaFree(p);
   for (auto& b : h->pin_queue) cudaEventDestroy(b.ev);
   if (h->cstream) { cudaStreamSynchronize(h->cstream); cudaStreamDestroy(h->cstream); }
@@ -1098,6 +1102,18 @@ void build_header(shq_handle_s* h, uint8_t* hd) {   // qfmetadata, cqf/gqf.h:62-
   memcpy(hd + 64, &range, 16);
   put(80, h->nblocks); put(88, h->nelts); put(96, h->ndistinct); put(104, 0);
   put(112, h->xnslots / 65536 + 2);
+}
+
+// the image as the query / unitig kernels see it: one array, or the shards' arrays (own + peer-mapped)
+ImageView image_view(shq_handle_s* h) {
+  ImageView im{h->image.as<uint8_t>(), h->nblocks, h->xnslots, 0};
+  if (!h->img_peer.empty()) {
+    im.blocks = nullptr;
+    im.shard_blocks = h->d_img_peer.as<uint8_t*>();
+    im.blocks_per_shard = h->nslots / (uint64_t)h->nshards / 64;
+    im.nshards = (uint32_t)h->nshards;
+  }
+  return im;
 }
 
 }  // namespace
@@ -2023,6 +2039,49 @@ int shq_mg_denoise_apply(shq_t h, int protect_last, uint64_t* removed) {
     h->image_valid = false;
     if (a.r) *a.r = rem;
   SHQ_API_END
+}
+
+
+// Sharded image across processes: every rank exports the CUDA IPC handle of its block array (after
+// shq_mg_materialize_shard); a rank that opens all of them can query the WHOLE filter -- and run the unitig build over
+// it -- with loads (and traveled-bit atomics) that go straight to the owners' HBM.  No rank holds the whole image.
+int shq_mg_image_ipc(shq_t h, void* ipc_handle_out) {
+  if (!h || !ipc_handle_out) return SHQ_ERR_ARG;
+  struct { void* out; } args{ipc_handle_out};
+  SHQ_API_BEGIN(h)
+    if (!h->image.p) SHQ_FAIL(SHQ_ERR_STATE, "shq_mg_materialize_shard first");
+    cudaIpcMemHandle_t hd;
+    SHQ_CUDA(cudaIpcGetMemHandle(&hd, h->image.p));
+    memcpy(a.out, &hd, 64);
+  SHQ_API_END
+}
+int shq_mg_open_image_peers(shq_t h, const void* all_handles, int world) {
+  if (!h || !all_handles || world != h->nshards) return SHQ_ERR_ARG;
+  struct { const void* hs; int world; } args{all_handles, world};
+  SHQ_API_BEGIN(h)
+    for (void* p : h->img_opened) cudaIpcCloseMemHandle(p);
+    h->img_opened.clear();
+    h->img_peer.assign((size_t)a.world, nullptr);
+    for (int r = 0; r < a.world; r++) {
+      if (r == h->shard) { h->img_peer[r] = h->image.as<uint8_t>(); continue; }
+      cudaIpcMemHandle_t hd;
+      memcpy(&hd, (const char*)a.hs + (size_t)r * 64, 64);
+      void* p = nullptr;
+      SHQ_CUDA(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+      h->img_opened.push_back(p);
+      h->img_peer[r] = (uint8_t*)p;
+    }
+    h->d_img_peer.reserve((size_t)a.world * 8 + 64);
+    SHQ_CUDA(cudaMemcpyAsync(h->d_img_peer.p, h->img_peer.data(), (size_t)a.world * 8, cudaMemcpyHostToDevice, h->stream));
+    SHQ_CUDA(cudaStreamSynchronize(h->stream));
+  SHQ_API_END
+}
+int shq_mg_close_image_peers(shq_t h) {
+  if (!h) return SHQ_ERR_ARG;
+  cudaSetDevice(h->device);
+  for (void* p : h->img_opened) cudaIpcCloseMemHandle(p);
+  h->img_opened.clear(); h->img_peer.clear();
+  return SHQ_OK;
 }
 
 // ---- sharded image: layout with a carry from the previous shards, spill hand-over, per-shard blocks ----

@@ -350,6 +350,9 @@ __global__ void __launch_bounds__(32) tail_start_kernel(const uint64_t* __restri
 // ------------------------------------------------------------ queries -------
 struct ImageView {
   uint8_t* blocks; uint64_t nblocks; uint64_t xnslots; uint64_t q_base;  // q_base: quotient of slot 0 (shards)
+  // sharded image: the blocks of the filter live in `nshards` arrays (blocks_per_shard blocks each, the last one also holds
+  // the xnslots extension), possibly in other GPUs' memory (peer mappings); null = one array at `blocks`
+  uint8_t* const* shard_blocks = nullptr; uint64_t blocks_per_shard = 0; uint32_t nshards = 0;
 };
 __device__ __forceinline__ uint64_t ld64u(const uint8_t* p) {  // unaligned little-endian load
   uint64_t v = 0;
@@ -357,10 +360,16 @@ __device__ __forceinline__ uint64_t ld64u(const uint8_t* p) {  // unaligned litt
   for (int i = 0; i < 8; i++) v |= (uint64_t)p[i] << (8 * i);
   return v;
 }
-__device__ __forceinline__ const uint8_t* blk(const ImageView& im, uint64_t b) { return im.blocks + b * kBlockBytes; }
-__device__ __forceinline__ uint8_t img_slot(const ImageView& im, uint64_t s) { return im.blocks[(s >> 6) * kBlockBytes + 25 + (s & 63)]; }
+__device__ __forceinline__ uint8_t* blk_rw(const ImageView& im, uint64_t b) {
+  if (!im.shard_blocks) return im.blocks + b * kBlockBytes;
+  uint64_t sh = b / im.blocks_per_shard;
+  if (sh >= im.nshards) sh = im.nshards - 1;
+  return im.shard_blocks[sh] + (b - sh * im.blocks_per_shard) * kBlockBytes;
+}
+__device__ __forceinline__ const uint8_t* blk(const ImageView& im, uint64_t b) { return blk_rw(im, b); }
+__device__ __forceinline__ uint8_t img_slot(const ImageView& im, uint64_t s) { return blk(im, s >> 6)[25 + (s & 63)]; }
 __device__ __forceinline__ bool img_bit(const ImageView& im, uint64_t s, int field) {
-  return (im.blocks[(s >> 6) * kBlockBytes + 1 + 8 * field + ((s & 63) >> 3)] >> (s & 7)) & 1;
+  return (blk(im, s >> 6)[1 + 8 * field + ((s & 63) >> 3)] >> (s & 7)) & 1;
 }
 // position of the r-th (0-based) set bit of v, 64 if none
 __device__ __forceinline__ int select64(uint64_t v, int r) {
@@ -460,8 +469,7 @@ __global__ void query_kernel(ImageView im, const uint64_t* __restrict__ qkeys, s
         cnt = c;
         if (SET) {
           // traveled bit of the entry's first slot; 32-bit atomic on the word holding that byte
-          size_t byte_off = (idx >> 6) * kBlockBytes + 17 + ((idx & 63) >> 3);
-          uintptr_t addr = reinterpret_cast<uintptr_t>(im.blocks) + byte_off;
+          uintptr_t addr = reinterpret_cast<uintptr_t>(blk_rw(im, idx >> 6)) + 17 + ((idx & 63) >> 3);
           unsigned int* wp = reinterpret_cast<unsigned int*>(addr & ~(uintptr_t)3);
           unsigned int bit = 1u << (8 * (addr & 3) + (idx & 7));
           unsigned int old = atomicOr(wp, bit);

@@ -629,6 +629,7 @@ struct shq_unitigs_s {
   shq::DevBuf d_stage; size_t st_fill = 0; std::vector<size_t> st_ends;   // read chunks staged on the device
   size_t st_cap_target = (size_t)128 << 20;
   bool built = false;
+  uint64_t global_ndistinct = 0;  // sharded filter: distinct keys over all shards (sizes the node table)
   bool master_rule = false;       // seed k-mer of a read: len/2 - K/2 (workers, the default) or len/2 (the master thread)
   // results (host)
   std::vector<std::string> seqs; std::vector<int> km; std::vector<std::vector<int>> after, before;
@@ -737,7 +738,7 @@ void unitigs_build_impl(shq_unitigs_s* u) {
   cudaStream_t st = h->stream;
   uint64_t& L = h->stats.kernels_launched;
   const int K = u->opts.K;
-  ImageView im{h->image.as<uint8_t>(), h->nblocks, h->xnslots, 0};
+  ImageView im = image_view(h);
   NodeTable T = node_table(u);
   const size_t O = (size_t)2 * u->cap;      // oriented ids
   uint32_t n_nodes = read_scalar(h, u->nn.as<uint32_t>());
@@ -998,6 +999,13 @@ void unitigs_build_impl(shq_unitigs_s* u) {
 
 extern "C" {
 
+static thread_local uint64_t g_unitig_global_ndistinct = 0;
+int shq_unitigs_begin(shq_t h, const shq_unitig_opts* opts, shq_unitigs_t* out);
+// the unitig build over a SHARDED filter whose shards' images were opened with shq_mg_open_image_peers
+int shq_unitigs_begin_sharded(shq_t h, const shq_unitig_opts* opts, uint64_t global_ndistinct, shq_unitigs_t* out) {
+  g_unitig_global_ndistinct = global_ndistinct;
+  return shq_unitigs_begin(h, opts, out);
+}
 int shq_unitigs_begin(shq_t h, const shq_unitig_opts* opts, shq_unitigs_t* out) {
   if (!h || !opts || !out) return SHQ_ERR_ARG;
   *out = nullptr;
@@ -1009,16 +1017,17 @@ int shq_unitigs_begin(shq_t h, const shq_unitig_opts* opts, shq_unitigs_t* out) 
   // handle), so a repeated build allocates nothing
   shq_unitigs_s* u = h->unitig_cache ? (shq_unitigs_s*)h->unitig_cache : new shq_unitigs_s();
   h->unitig_cache = nullptr;
-  u->h = h; u->opts = *opts;
+  u->h = h; u->opts = *opts; u->global_ndistinct = g_unitig_global_ndistinct; g_unitig_global_ndistinct = 0;
   u->built = false; u->master_rule = false; u->n_seed_slots = 0; u->st_fill = 0; u->st_ends.clear(); u->n_queries = 0;
   u->seqs.clear(); u->km.clear(); u->after.clear(); u->before.clear(); u->fasta.clear(); u->seeds.clear();
   struct { shq_unitigs_s* u; } args{u};
   int rc = guard(h, [](shq_handle_s* h, void* ap) {
     shq_unitigs_s* u = ((decltype(args)*)ap)->u;
     flush_stage(h);
-    if (h->nshards != 1) SHQ_FAIL(SHQ_ERR_STATE, "unitigs on a sharded handle go through the multi-GPU layer");
-    if (!h->image_only) materialise(h);
-    uint64_t expect = h->image_only ? h->ndistinct : (uint64_t)h->n_state;
+    const bool sharded = h->nshards != 1;
+    if (sharded && h->img_peer.empty()) SHQ_FAIL(SHQ_ERR_STATE, "unitigs on a sharded handle need the shards' images (shq_mg_open_image_peers)");
+    if (!sharded && !h->image_only) materialise(h);
+    uint64_t expect = sharded ? u->global_ndistinct : (h->image_only ? h->ndistinct : (uint64_t)h->n_state);
     if (expect < 1024) expect = 1024;
     uint64_t want = expect * 3 + 4096;
     uint32_t cap = 1024;
@@ -1087,7 +1096,7 @@ bool unitigs_process_text(shq_unitigs_s* u, const char* d_text, size_t n, const 
     }
   }
   EnumParams ep{d_text, h->d_nl_pos.as<uint32_t>(), n_reads, u->opts.K, h->hb, (uint32_t)u->opts.abundance_min};
-  ImageView im{h->image.as<uint8_t>(), h->nblocks, h->xnslots, 0};
+  ImageView im = image_view(h);
   size_t smem = (size_t)kEnumWarps * ((kTilePos + 1) * 16 + 264 + 520);
   SHQ_CUDA(cudaFuncSetAttribute(enum_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   VictimList V{u->v_node.as<uint32_t>(), u->v_slot.as<uint64_t>(), u->v_n.as<uint32_t>(), u->victim_cap};

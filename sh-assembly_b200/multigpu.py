@@ -607,18 +607,25 @@ class ShardedCounter:
         parts.sort(key=lambda x: x[0])
         return self.shard.header(nd, ne) + b"".join(p[1] for p in parts)
 
-    def build_unitigs(self, chunks, K, s_min=2, x_min=2, x_max=1000000):
-        """Contiger at N > 1 (replica): the shard images are assembled into the reference .cqf on rank 0 and the
-        single-GPU device path runs there; cross-shard neighbour queries are not built yet.  Rank 0 returns the
-        FASTA text, other ranks None.  `chunks` = the read chunks of ALL ranks on rank 0."""
-        img = self.export_sharded()
-        if self.rank != 0:
-            return None
-        g = self.shq.CQF.from_bytes(img, device=self.device)
-        try:
-            return self.shq.build_unitigs(g, chunks, K, s_min, x_min, x_max)
-        finally:
-            g.close()
+    def build_unitigs(self, chunks, K, s_min=2, x_min=2, x_max=1000000, master_rule=False):
+        """Contiger over the SHARDED filter: every rank keeps the blocks of its own quotient range in its HBM
+        (materialize_sharded); rank 0 maps the peers' block arrays through CUDA IPC and runs the device path with its
+        neighbour queries (and traveled-bit atomics) going straight to the owners' memory -- no rank ever holds the whole
+        image.  The node table and the chain contraction still live on rank 0 (owner-partitioned nodes with a stitch of chain
+        ends are not built).  Rank 0 returns the FASTA text, other ranks None.  `chunks` = the read chunks of ALL ranks, on rank 0."""
+        self.materialize_sharded()
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, self.shard.mg_image_ipc())
+        nd, _ = self.global_counts()
+        fa = None
+        if self.rank == 0:
+            self.shard.mg_open_image_peers(b"".join(handles), self.world)
+            try:
+                fa = self.shq.build_unitigs(self.shard, chunks, K, s_min, x_min, x_max, master_rule=master_rule, global_ndistinct=nd)
+            finally:
+                self.shard.mg_close_image_peers()
+        self.dist.barrier()       # the peers' images stay alive until rank 0 is done with them
+        return fa
 
     def materialize_global(self):
         """Build the global image on rank 0 in device memory (benchmark: 'table complete')."""
@@ -652,7 +659,12 @@ def bench_sharded(args, rank, world, local_rank, B):
     n_bytes = nloc * sp.rec_bytes
     d_text = torch.empty(n_bytes + 64, dtype=torch.uint8, device=dev)
     synth.gpu_fill(sp, first, nloc, d_text.data_ptr(), torch.cuda.current_stream().cuda_stream)
-    h_text = torch.empty(n_bytes, dtype=torch.uint8).pin_memory()
+    try:
+        h_text = torch.empty(n_bytes, dtype=torch.uint8).pin_memory()
+        host_note = "page-locked host text"
+    except RuntimeError:      # the node cannot page-lock world x this much: pageable host memory (slower copies, same bytes)
+        h_text = torch.empty(n_bytes, dtype=torch.uint8)
+        host_note = "pageable host text (page-locking %d bytes per rank failed)" % n_bytes
     h_text.copy_(d_text[:n_bytes])
     torch.cuda.synchronize()
     text = h_text.numpy()
@@ -776,7 +788,8 @@ def bench_sharded(args, rank, world, local_rank, B):
                 "dtype": "u64", "data": "synthetic", "config": cfg, "clocks": clocks,
                 "e2e": {"value": n_total / (float(ms_e2e.item()) / 1e3), "unit": "k-mers/s", "h2d_bytes_per_step": int(io[0].item()),
                         "d2h_bytes_per_step": int(io[1].item()), "ms_per_step": float(ms_e2e.item()),
-                        "note": "every rank: pinned host text -> H2D on a side stream, batch by batch -> exchange + insert -> its blocks of the .cqf image -> D2H; wall clock between barriers, max over ranks; bytes summed over ranks"},
+                        "steps": e2e_steps,
+                        "note": "every rank: " + host_note + " -> H2D in 64 MiB slices on a side stream -> exchange + insert as the slices land -> its blocks of the .cqf image -> D2H; wall clock between barriers, max over ranks; bytes summed over ranks"},
                 "gpu_launches": int(launches.item()),
                 "roofline": {"bound": "hbm", "kernel": "whole sharded insert path", "achieved": value * a_ins / 1e9 / world, "peak": peak, "unit": "GB/s",
                              "frac": value * a_ins / 1e9 / world / peak, "traffic": None, "note": "per GPU, against SURVEY 8(d) A_ins"},

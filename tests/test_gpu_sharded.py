@@ -41,19 +41,28 @@ def _worker(rank, world, port, case, ret):
     assert sc.mode == "pull"
     nd, ne = sc.count(d.data_ptr(), len(text), K, ends, trigger=case["trigger"], rounds=case["rounds"], end_denoise=case["end"])
     img = sc.export_sharded()
+    fa = None
+    if case.get("unitigs"):
+        # Contiger over the sharded image: rank 0 reads the other shard's blocks through the CUDA-IPC mapping
+        all_chunks = [c for _, c in shq.Reader(buffers=texts, part_size=part)] if rank == 0 else None
+        fa = sc.build_unitigs(all_chunks, K)
     if rank == 0:
         o, rounds = po.count_run(texts, K, qb, qb + 8, case["trigger"], case["rounds"], case["end"], part_size=part)
         ret["counts"] = ((nd, ne), o.counts())
         ret["rounds"] = (sc.sweeps, rounds)
         ret["image_equal"] = img == o.export()
         ret["search"] = (sc.search.attempts, sc.search.rejected)
+        if fa is not None:
+            fo, _ = po.contiger_run(o, texts, K, part_size=part)
+            ret["unitigs_equal"] = po.canonical_unitig_set(fa) == po.canonical_unitig_set(fo) and po.canonical_links(fa) == po.canonical_links(fo)
+            ret["n_unitigs"] = len(po.parse_unitigs(fa))
     dist.barrier()
     dist.destroy_process_group()
 
 
 CASES = {
     # trigger low enough for two mid-stream rounds, plus the end round; small batches so that boundaries fall inside batches
-    "two_rounds_end": dict(K=31, qb=21, part=1 << 18, G=60000, cov=40, err=0.004, seed=50, trigger=90000, rounds=2, end=True, rounds_env=6),
+    "two_rounds_end": dict(K=31, qb=21, part=1 << 18, G=60000, cov=40, err=0.004, seed=50, trigger=90000, rounds=2, end=True, rounds_env=6, unitigs=True),
     # --deNoise=0: one batch after the other, no sweep
     "plain": dict(K=27, qb=20, part=1 << 18, G=50000, cov=30, err=0.003, seed=60, trigger=0, rounds=0, end=False),
     # ranks with different numbers of chunks, K=47, rounds left over at EOF
@@ -74,3 +83,5 @@ def test_two_shards_match_the_oracle(name):
     assert ret["image_equal"]
     if CASES[name]["rounds"]:
         assert ret["search"][0] > 0
+    if CASES[name].get("unitigs"):
+        assert ret["unitigs_equal"] and ret["n_unitigs"] > 10

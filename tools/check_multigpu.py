@@ -35,9 +35,10 @@ def main():
                   "sharded image equal:", ok, "search", (sc.search.attempts, sc.search.rejected), flush=True)
             assert ok and (nd, ne) == o.counts() and sc.sweeps == orounds
         if end:
-            fa = sc.build_unitigs(texts if rank == 0 else None, K)
+            chunks = [c for _, c in shq.Reader(buffers=texts, part_size=part)] if rank == 0 else None
+            fa = sc.build_unitigs(chunks, K)
             if rank == 0:
-                fa_o, _ = po.contiger_run(o, texts, K, 2, 2, 1000000)
+                fa_o, _ = po.contiger_run(o, texts, K, 2, 2, 1000000, part_size=part)
                 same = po.canonical_unitig_set(fa) == po.canonical_unitig_set(fa_o) and po.canonical_links(fa) == po.canonical_links(fa_o)
                 print("world", world, "unitigs", len(po.parse_unitigs(fa)), "equal to the oracle's:", same, flush=True)
                 assert same

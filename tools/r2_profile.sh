@@ -1,0 +1,16 @@
+#!/bin/bash
+# tools/r2_profile.sh -- the ncu evidence of round 2, run on the GPU box AFTER the same bench command has exited 0 without ncu
+# (B200_PROFILING.md): 1) launch list of the default bench command, 2) --set full capture of the hot kernels on the
+# configs[2] twin and on configs[1], 3) per-kernel summaries + DRAM traffic per launch (profiles/r2_traffic.json).
+set -x
+out=gpurun_out
+python bench.py --workload celegans20 --secondary ecoli --steps 1 --warmup 1 --cpu-seconds 1 --unitigs 0 --e2e-steps 1 > $out/r2_prof_plain.json 2> $out/r2_prof_plain.err || exit 1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $out/r2_launches.csv \
+    python bench.py --workload celegans20 --secondary ecoli --steps 1 --warmup 1 --cpu-seconds 1 --unitigs 0 --e2e-steps 1 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"bin_aggregate|merge_tiles|roll_scatter|split_bins|denoise_tiles|layout_scan|image_tiles|nl_write" -s 40 -c 24 \
+    -o $out/r2_full python bench.py --workload celegans20 --secondary "" --steps 1 --warmup 0 --cpu-seconds 1 --e2e-steps 1 > $out/r2_full.log 2>&1
+python tools/ncu_summary.py $out/r2_full.ncu-rep $out/r2_full.pkl --traffic $out/r2_traffic.json > $out/r2_full.summary.txt 2>&1
+for i in 0 1 2 3 4 5 6 7; do python tools/line_profile.py $out/r2_full.pkl $i sh-assembly_b200/libshq.so 18 >> $out/r2_line_profiles.txt 2>&1; done
+rm -f $out/r2_full.ncu-rep
+cuobjdump -sass sh-assembly_b200/libshq.so | grep -E "Function :|UBLKCP|SYNCS|UTMALDG" | grep -B1 -E "UBLKCP|SYNCS|UTMALDG" | head -60 > $out/r2_sass_tma.txt
+ls -la $out | tail -12

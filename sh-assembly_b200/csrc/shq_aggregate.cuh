@@ -51,6 +51,13 @@ struct AggOut {
   int direct;               // most words are first occurrences: insert straight away instead of probing first
   int sample_bits;          // > 0: aggregate only the keys of the first 1/2^sample_bits of the bin's key range (a sample by KEY,
                             // so its distinct ratio is that of the whole bin) -- one pass over the bin by one CTA
+  // dense != 0: the runs are written DENSE and in order straight away (no per-bin staging + compaction pass): CTAs take
+  // tickets, publish their distinct counts and find their output offset by a decoupled look-back over the
+  // predecessors (status words, zeroed; counts of run A in the low 31 bits, of run B above).  keys/counts/chunk are then
+  // the dense run arrays; totals[0..3] receive n(A), n(B), occurrences(A), occurrences(B).  A CTA that needs several
+  // rounds (key sub-ranges) stages its rounds in scratch_* first.
+  int dense; uint32_t n_groups; unsigned long long* status; unsigned int* ticket; unsigned long long* totals;
+  uint64_t* scratch_keys; uint32_t* scratch_counts; uint16_t* scratch_chunk; uint64_t* scratch_keys2; uint32_t* scratch_counts2;
 };
 
 struct AggTable {
@@ -192,6 +199,33 @@ __device__ __forceinline__ void agg_insert_pass(const uint32_t* __restrict__ pac
   else if (threadIdx.x == 0) atomicAdd(occ1, end - beg);
 }
 
+// Decoupled look-back over (flag | value) words, one per ticket: flag 1 = the ticket's own value, 2 = inclusive prefix.
+// Called by the 32 lanes of one warp; returns the exclusive prefix of ticket t (values may pack two counters).
+__device__ __forceinline__ unsigned long long agg_lookback(unsigned long long* status, size_t t, unsigned long long val, int lane) {
+  const unsigned long long kVal = (1ULL << 62) - 1;
+  unsigned long long excl = 0;
+  if (t == 0) {
+    if (lane == 0) atomicExch(&status[0], (2ULL << 62) | val);
+    return 0;
+  }
+  if (lane == 0) atomicExch(&status[t], (1ULL << 62) | val);
+  long long p = (long long)t - 1;   // lane l looks at ticket p - l
+  for (;;) {
+    const long long q = p - lane;
+    unsigned long long v = 2ULL << 62;              // tickets before 0: an inclusive prefix of 0
+    if (q >= 0) { do { v = *reinterpret_cast<volatile unsigned long long*>(&status[q]); } while ((v >> 62) == 0); }
+    const unsigned incl = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+    const int first = incl ? __ffs(incl) - 1 : 32;  // nearest predecessor that already knows its inclusive prefix
+    unsigned long long part = lane <= first ? (v & kVal) : 0;
+    for (int d = 16; d; d >>= 1) part += __shfl_down_sync(0xffffffffu, part, d);
+    excl += __shfl_sync(0xffffffffu, part, 0);
+    if (first < 32) break;
+    p -= 32;
+  }
+  if (lane == 0) atomicExch(&status[t], (2ULL << 62) | (excl + val));
+  return excl;
+}
+
 // One CTA per (bin, key sub-range).  packed[bin_off[p] .. bin_off[p+1]) holds (key_low | chunk << lb).
 // Occurrences whose chunk is outside [chunk_lo, chunk_hi] are ignored.
 // SPLIT: occurrences with chunk <= cstar are counted in the low half of the counter, the others in the high
@@ -213,14 +247,19 @@ __global__ void __launch_bounds__(kAggThreads, 2) bin_aggregate_kernel(
   uint16_t* s_fin = reinterpret_cast<uint16_t*>(nxt + kAggShareBytes);    // SPLIT: slots in key order
   __shared__ uint32_t s_nocc, s_nocc2, s_overflow, s_na, s_nb;
 
-  const uint32_t p = blockIdx.x >> o.fixed_bits;
-  const uint32_t fsub = blockIdx.x & ((1u << o.fixed_bits) - 1);
+  __shared__ uint32_t s_ticket;
+  __shared__ unsigned long long s_excl;
+  if (o.dense) { if (threadIdx.x == 0) s_ticket = atomicAdd(o.ticket, 1u); __syncthreads(); }
+  const uint32_t g = o.dense ? s_ticket : blockIdx.x;      // (bin, sub-range) group handled by this CTA; tickets keep the look-back deadlock free
+  const uint32_t p = g >> o.fixed_bits;
+  const uint32_t fsub = g & ((1u << o.fixed_bits) - 1);
   const uint32_t beg = bin_off[p];
   uint32_t end = bin_off[p + 1];
   if (o.bin_end) { const uint32_t e = o.bin_end[p]; end = e < end ? e : end; }     // never past the bin's own range
-  const size_t obase = (size_t)fsub * o.sub_stride + beg;
+  const size_t obase = (size_t)fsub * o.sub_stride + beg;       // staging position of this group (per-bin layout)
   const uint32_t lowmask = lb >= 32 ? 0xFFFFFFFFu : ((1u << lb) - 1);
   uint32_t written = 0, written2 = 0, occ_total = 0, occ_total2 = 0;
+  bool did_direct = false;      // dense output: this CTA has already looked back and written its run in place
   int sub_bits = o.fixed_bits;   // key_low bits fixed per round: fixed_bits chosen by the grid, the rest by overflow restarts
   while (sub_bits < lb && ((end - beg) >> sub_bits) > 64u * kAggMaxDistinct) sub_bits++;
   if (o.sample_bits > sub_bits) sub_bits = o.sample_bits < lb ? o.sample_bits : lb - 1;
@@ -271,6 +310,21 @@ restart:
       }
     }
     __syncthreads();
+    // dense output: a CTA that is done after this round (the usual case) learns its offset now and writes the run in place;
+    // one that needs more rounds stages them in the scratch arrays and copies them over at the end
+    const bool last_round = r + 1 == (o.sample_bits ? (fsub << (sub_bits - o.fixed_bits)) + 1 : ((fsub + 1) << (sub_bits - o.fixed_bits)));
+    const bool direct_out = o.dense && !SPLIT && last_round && written == 0;
+    if (direct_out) {
+      if (threadIdx.x < 32) {
+        const unsigned long long excl = agg_lookback(o.status, g, (unsigned long long)nd, threadIdx.x);
+        if (threadIdx.x == 0) { s_excl = excl; if (g == o.n_groups - 1) { o.totals[0] = excl + nd; o.totals[1] = 0; } }
+      }
+      did_direct = true;
+      __syncthreads();
+    }
+    uint64_t* const wkeys = o.dense ? (direct_out ? o.keys + s_excl : o.scratch_keys + obase) : o.keys + obase;
+    uint32_t* const wcounts = o.dense ? (direct_out ? o.counts + s_excl : o.scratch_counts + obase) : o.counts + obase;
+    uint16_t* const wchunk = !o.chunk ? nullptr : (o.dense ? (direct_out ? o.chunk + s_excl : o.scratch_chunk + obase) : o.chunk + obase);
     // ---- place inside the cluster = number of smaller keys there; emit in key order
     for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) {
       const uint32_t slot = s_ord[i] & 0x7FFFu;
@@ -282,12 +336,12 @@ restart:
       for (uint32_t x = i + 1; x < nd && !(s_ord[x] & 0x8000u); x++) rank += t_key[s_ord[x] & 0x7FFFu] < k ? 1u : 0u;
       const uint32_t pos = a + rank;
       if (SPLIT) { s_fin[pos] = (uint16_t)slot; continue; }
-      const size_t oo = obase + written + pos;
-      o.keys[oo] = key_lo + (((uint64_t)p << lb) | k);
-      o.counts[oo] = t_cnt[slot];
+      const size_t oo = (size_t)written + pos;
+      wkeys[oo] = key_lo + (((uint64_t)p << lb) | k);
+      wcounts[oo] = t_cnt[slot];
       if (CHUNK) {
         const uint32_t fc = t_chk[slot];
-        if (o.chunk) o.chunk[oo] = (uint16_t)fc;
+        if (wchunk) wchunk[oo] = (uint16_t)fc;
         if (o.first_hist) {                       // one atomic per (warp, chunk id): chunk ids of neighbouring keys repeat
           const uint32_t peers = __match_any_sync(__activemask(), fc);
           if ((uint32_t)(threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&o.first_hist[fc & (kAggBuckets - 1)], (uint32_t)__popc(peers));
@@ -316,8 +370,8 @@ restart:
         if (i >= nd) break;
         uint32_t c = cs[j];
         uint64_t key = key_lo + (((uint64_t)p << lb) | t_key[s_fin[i]]);
-        if (c & 0xFFFFu) { size_t oo = obase + written + ra; o.keys[oo] = key; o.counts[oo] = c & 0xFFFFu; if (o.chunk) o.chunk[oo] = 0; ra++; }
-        if (c >> 16) { size_t oo = obase + written2 + rb; o.keys2[oo] = key; o.counts2[oo] = c >> 16; rb++; }
+        if (c & 0xFFFFu) { size_t oo = obase + written + ra; (o.dense ? o.scratch_keys : o.keys)[oo] = key; (o.dense ? o.scratch_counts : o.counts)[oo] = c & 0xFFFFu; ra++; }
+        if (c >> 16) { size_t oo = obase + written2 + rb; (o.dense ? o.scratch_keys2 : o.keys2)[oo] = key; (o.dense ? o.scratch_counts2 : o.counts2)[oo] = c >> 16; rb++; }
       }
       if (threadIdx.x == 0) { s_na = ta; s_nb = tb; }
     }
@@ -326,9 +380,29 @@ restart:
     occ_total += s_nocc; occ_total2 += s_nocc2;
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    o.n_out[blockIdx.x] = written; o.occ_out[blockIdx.x] = occ_total;
-    if (SPLIT) { o.n_out2[blockIdx.x] = written2; o.occ_out2[blockIdx.x] = occ_total2; }
+  if (!o.dense) {
+    if (threadIdx.x == 0) {
+      o.n_out[blockIdx.x] = written; o.occ_out[blockIdx.x] = occ_total;
+      if (SPLIT) { o.n_out2[blockIdx.x] = written2; o.occ_out2[blockIdx.x] = occ_total2; }
+    }
+    return;
+  }
+  // dense: occurrences into the global totals; staged rounds (several key sub-ranges, SPLIT) copied to their place
+  if (threadIdx.x == 0) { if (occ_total) atomicAdd(&o.totals[2], (unsigned long long)occ_total); if (SPLIT && occ_total2) atomicAdd(&o.totals[3], (unsigned long long)occ_total2); }
+  if (!did_direct) {
+    // look back with both counts (A in the low 31 bits, B above)
+    if (threadIdx.x < 32) {
+      const unsigned long long val = (unsigned long long)written | ((unsigned long long)written2 << 31);
+      const unsigned long long excl = agg_lookback(o.status, g, val, threadIdx.x);
+      if (threadIdx.x == 0) { s_excl = excl; if (g == o.n_groups - 1) { o.totals[0] = (excl + val) & 0x7FFFFFFFull; o.totals[1] = (excl + val) >> 31; } }
+    }
+    __syncthreads();
+    const size_t oa = (size_t)(s_excl & 0x7FFFFFFFull), ob = (size_t)(s_excl >> 31);
+    for (uint32_t i = threadIdx.x; i < written; i += blockDim.x) {
+      o.keys[oa + i] = o.scratch_keys[obase + i]; o.counts[oa + i] = o.scratch_counts[obase + i];
+      if (o.chunk) o.chunk[oa + i] = SPLIT ? (uint16_t)0 : o.scratch_chunk[obase + i];
+    }
+    if (SPLIT) for (uint32_t i = threadIdx.x; i < written2; i += blockDim.x) { o.keys2[ob + i] = o.scratch_keys2[obase + i]; o.counts2[ob + i] = o.scratch_counts2[obase + i]; }
   }
 }
 

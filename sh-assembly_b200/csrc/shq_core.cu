@@ -84,7 +84,7 @@ struct shq_handle_s {
   DevBuf d_tmp_keys2, d_tmp_counts2, d_run2_keys, d_run2_counts;
   DevBuf d_run_keys, d_run_counts, d_run_chunk, d_split, d_heads, d_heads64, d_scan_scratch, d_misc;
   DevBuf d_pairs, d_pos, d_flags, d_keep, d_q_in, d_q_cnt, d_q_was;
-  DevBuf d_sample;
+  DevBuf d_sample, d_aggctl;
   DevBuf d_fine2;   // offsets of the second-level bins
   DevBuf d_seg, d_fine, d_fine_cur, d_packed2, d_bases;   // second binning level (single GPU: fine bins; multi-GPU: owner-side split)
   int fine_bits_forced = -1;     // SHQ_FINE_BITS: force the second binning level (0 = off)
@@ -539,6 +539,19 @@ bool aggregate_bins(shq_handle_s* h, const BatchBins& bb, uint32_t clo, uint32_t
   o.n_out2 = n_out2; o.occ_out = occ; o.occ_out2 = occ2; o.first_hist = d_fh; o.split_overflow = d_ovf;
   o.fixed_bits = fixed_bits; o.sub_stride = cap;
   o.bin_end = bb.end;
+  // dense output: the runs are written in order straight away (look-back over the groups' distinct counts): no per-bin
+  // staging of the whole batch, no compaction pass
+  const uint64_t bound = (uint64_t)bb.n_keys + 8;           // distinct keys <= occurrences
+  A->keys->reserve(bound * 8); A->counts->reserve(bound * 4);
+  if (chunks) A->chunk->reserve(bound * 2);
+  if (split) { B->keys->reserve(bound * 8); B->counts->reserve(bound * 4); }
+  h->d_aggctl.reserve((nb + 16) * 8 + 64);
+  unsigned long long* d_ctl = h->d_aggctl.as<unsigned long long>();       // [0..3] totals, [4] ticket, [8 ...] status
+  SHQ_CUDA(cudaMemsetAsync(d_ctl, 0, (nb + 16) * 8, st));
+  o.dense = 1; o.n_groups = (uint32_t)nb; o.totals = d_ctl; o.ticket = reinterpret_cast<unsigned int*>(d_ctl + 4); o.status = d_ctl + 8;
+  o.scratch_keys = o.keys; o.scratch_counts = o.counts; o.scratch_chunk = o.chunk; o.scratch_keys2 = o.keys2; o.scratch_counts2 = o.counts2;
+  o.keys = A->keys->as<uint64_t>(); o.counts = A->counts->as<uint32_t>(); o.chunk = chunks ? A->chunk->as<uint16_t>() : nullptr;
+  o.keys2 = split ? B->keys->as<uint64_t>() : nullptr; o.counts2 = split ? B->counts->as<uint32_t>() : nullptr;
   // most words of the batch are first occurrences (a batch of a large genome covers it less than once): insert directly
   o.direct = (bb.ratio >= 0 ? bb.ratio : (h->ratio_seen ? h->distinct_ratio : 1.0)) > 0.3 ? 1 : 0;
 #define SHQ_AGG_LAUNCH(SP, CH) do { \
@@ -556,21 +569,17 @@ bool aggregate_bins(shq_handle_s* h, const BatchBins& bb, uint32_t clo, uint32_t
     read_pair(h, h->d_misc.as<int>() + 20, &o1, h->d_misc.as<int>() + 24, &o2);
     if ((bb.level1_spec && o1) || (bb.fine_bits && o2)) throw BinOverflow{};
   }
-  if (split && read_scalar(h, d_ovf)) return false;
-  auto finish = [&](Run* R, uint32_t* nout, uint32_t* dense, uint32_t* occs, const uint64_t* tk, const uint32_t* tc, const uint16_t* tch) {
-    SHQ_CUDA(cudaMemcpyAsync(dense, nout, nb * 4, cudaMemcpyDeviceToDevice, st));
-    exclusive_scan_inplace<SumU32>(dense, nb, h->d_scan_scratch, st, dense + nb, &L);
-    exclusive_scan_inplace<SumU32>(occs, nb, h->d_scan_scratch, st, h->d_misc.as<uint32_t>(), &L);
-    uint32_t nd = 0, oc = 0;
-    read_pair(h, dense + nb, &nd, h->d_misc.as<uint32_t>(), &oc);
-    R->keys->reserve((size_t)(nd + 4) * 8); R->counts->reserve((size_t)(nd + 4) * 4);
-    if (tch) R->chunk->reserve((size_t)(nd + 4) * 2);
-    compact_bins_kernel<<<(unsigned)nb, 256, 0, st>>>(bb.off, dense, nout, fixed_bits, cap, tk, tc, tch, R->keys->as<uint64_t>(),
-                                                  R->counts->as<uint32_t>(), tch ? R->chunk->as<uint16_t>() : nullptr); L++;
-    R->n = nd; R->occ = oc;
-  };
-  finish(A, n_out, doff, occ, o.keys, o.counts, o.chunk);
-  if (split) finish(B, n_out2, doff2, occ2, o.keys2, o.counts2, nullptr);
+  {
+    // totals and the split-overflow flag with one round trip
+    unsigned long long* pz = (unsigned long long*)pinned(h, 64);
+    SHQ_CUDA(cudaMemcpyAsync(pz, d_ctl, 32, cudaMemcpyDeviceToHost, st));
+    SHQ_CUDA(cudaMemcpyAsync(pz + 4, d_ovf, 4, cudaMemcpyDeviceToHost, st));
+    SHQ_CUDA(cudaStreamSynchronize(st));
+    h->stats.d2h_bytes += 36; h->stats.host_syncs++;
+    if (split && (uint32_t)pz[4]) return false;
+    A->n = (size_t)pz[0]; A->occ = pz[2];
+    if (split) { B->n = (size_t)pz[1]; B->occ = pz[3]; }
+  }
   h->stats.agg_launches++; h->stats.agg_words += (uint64_t)bb.n_keys << fixed_bits; h->stats.agg_distinct += A->n + (split ? B->n : 0);
   if (!split && clo == 0 && (chi == 0xFFFFFFFFu || chi + 1 >= (uint32_t)bb.nchunks) && A->occ > (uint64_t)bb.n_bins * 64)
     { h->distinct_ratio = (double)A->n / (double)A->occ; h->ratio_seen = true; }   // whole batch seen: the next one is sized by it
@@ -1058,7 +1067,7 @@ void free_handle(shq_handle_s* h) {
                     &h->d_binoff, &h->d_packed, &h->d_tmp_keys, &h->d_tmp_counts, &h->d_tmp_chunk, &h->d_nout, &h->d_occ,
                     &h->d_dense_off, &h->d_run_keys, &h->d_run_counts, &h->d_run_chunk, &h->d_split, &h->d_heads, &h->d_heads64,
                     &h->d_scan_scratch, &h->d_misc, &h->d_pairs, &h->d_pos, &h->d_flags, &h->d_keep, &h->d_q_in, &h->d_q_cnt, &h->d_q_was,
-                    &h->d_tmp_keys2, &h->d_tmp_counts2, &h->d_run2_keys, &h->d_run2_counts, &h->d_seg, &h->d_fine, &h->d_fine_cur, &h->d_packed2, &h->d_bases, &h->d_sample, &h->d_fine2, &h->d_walk};
+                    &h->d_tmp_keys2, &h->d_tmp_counts2, &h->d_run2_keys, &h->d_run2_counts, &h->d_seg, &h->d_fine, &h->d_fine_cur, &h->d_packed2, &h->d_bases, &h->d_sample, &h->d_fine2, &h->d_walk, &h->d_aggctl};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : h->pin_buf) b.release();
   for (void* p : h->mg_opened) cudaIpcCloseMemHandle(p);

@@ -792,7 +792,9 @@ def bench_sharded(args, rank, world, local_rank, B):
                         "note": "every rank: " + host_note + " -> H2D in 64 MiB slices on a side stream -> exchange + insert as the slices land -> its blocks of the .cqf image -> D2H; wall clock between barriers, max over ranks; bytes summed over ranks"},
                 "gpu_launches": int(launches.item()),
                 "roofline": {"bound": "hbm", "kernel": "whole sharded insert path", "achieved": value * a_ins / 1e9 / world, "peak": peak, "unit": "GB/s",
-                             "frac": value * a_ins / 1e9 / world / peak, "traffic": None, "note": "per GPU, against SURVEY 8(d) A_ins"},
+                             "frac": value * a_ins / 1e9 / world / peak, "traffic": None, "note": "per GPU, against SURVEY 8(d) A_ins",
+                             "phase_ms_per_step_rank0": {k: st[k] / args.steps for k in st if k.startswith("ms_")},
+                             "host_syncs_per_step_rank0": st["host_syncs"] / args.steps, "batches_per_step": st["batches"] / args.steps},
                 "result": {"ndistinct": int(nd), "nelts": int(ne), "denoise_rounds": int(sweeps), "kmers_per_step": int(n_total),
                            "boundary_search": {"staged_intervals": search[0], "rejected": search[1]}},
                 "parity": parity}

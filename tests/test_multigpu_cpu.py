@@ -202,3 +202,27 @@ def test_trigger_search_reproduces_the_t1_schedule():
         fired = st["fired"][:n_mid] + (["eof"] if len(st["fired"]) > n_mid else [])
         assert fired == fired_ref, (trial, fired, fired_ref)
         assert st["state"] == state and ts.ndistinct == len(state) and ts.nelts == sum(state.values())
+
+
+def test_denoise_walk_finalize_closes_the_open_range():
+    """shq_mg_denoise_finalize (host only): the range that is open when the entries run out ends on the very last entry,
+    which is protected iff it is a one-slot cluster with count 1 sitting exactly on the range end."""
+    import ctypes as C
+    shq = importlib.import_module("sh-assembly_b200")
+    L = shq.lib()
+
+    def run(phase, e0, cur_end, pos, end, count, gap, owner=3):
+        st = np.zeros(16, np.uint64)
+        st[0], st[2], st[4] = phase, e0, cur_end
+        st[5], st[6], st[7], st[8], st[9], st[10] = 1, pos, end, count, gap, owner
+        assert L.shq_mg_denoise_finalize(st.ctypes.data) == 0
+        return int(st[11])
+
+    assert run(1, 1000, 0, 999, 999, 1, 1) == 1 << 3          # range ends at e0 - 1 = 999: one-slot cluster there, count 1
+    assert run(1, 1000, 0, 999, 999, 2, 1) == 0               # count 2 is never a candidate
+    assert run(1, 1000, 0, 999, 999, 1, 0) == 0               # adjacent to its predecessor: part of a longer cluster
+    assert run(1, 1000, 0, 998, 998, 1, 1) == 0               # not on the range end
+    assert run(1, 1000, 0, 1000, 1000, 1, 1) == 1 << 3        # covers slot e0: its cluster (itself) ends the range
+    assert run(2, 1000, 1203, 1203, 1203, 1, 1) == 1 << 3     # cluster walk reached the end of all entries
+    assert run(2, 1000, 1203, 1200, 1203, 1, 0) == 0
+    assert run(0, 0, 0, 5, 5, 1, 1) == 0                      # no range open

@@ -304,6 +304,8 @@ typedef struct {
   uint64_t spec_rejected;      /* speculative merges of armed batches dropped because the deNoise trigger was crossed inside */
   double ms_split;             /* second binning level (split_bins_kernel), CUDA-event ms */
   uint64_t split_launches, split_words;
+  uint64_t wide_batches;       /* batches past the armed chunk cap, merged speculatively without chunk ids (and kept) */
+  uint64_t wide_fallbacks;     /* ... dropped because the trigger was reached inside: redone in halves */
 } shq_stats;
 int shq_get_stats(shq_t h, shq_stats* out);
 int shq_reset_stats(shq_t h);

@@ -37,7 +37,8 @@ class shq_stats(C.Structure):
                 ("merge_launches", C.c_uint64), ("merge_in", C.c_uint64), ("merge_out", C.c_uint64),
                 ("denoise_launches", C.c_uint64), ("denoise_entries", C.c_uint64),
                 ("layout_launches", C.c_uint64), ("layout_entries", C.c_uint64), ("host_syncs", C.c_uint64),
-                ("spec_rejected", C.c_uint64), ("ms_split", C.c_double), ("split_launches", C.c_uint64), ("split_words", C.c_uint64)]
+                ("spec_rejected", C.c_uint64), ("ms_split", C.c_double), ("split_launches", C.c_uint64), ("split_words", C.c_uint64),
+                ("wide_batches", C.c_uint64), ("wide_fallbacks", C.c_uint64)]
 
 
 class shq_unitig_opts(C.Structure):

@@ -13,11 +13,12 @@ namespace shq {
 // ----------------------------------------------------- per-bin aggregation ---
 // One CTA per bin (or per key sub-range of a bin) streams the bin's 32-bit words through an ORDER-PRESERVING
 // open-addressing table in shared memory: the home slot of a key is a monotone function of the key (keys are ntHash
-// values, i.e. uniform), probing is linear and never wraps.  The occupied slots, read in slot order, are then sorted
-// except inside a cluster (a maximal run of occupied slots): every key of a cluster has its home inside that cluster, so
-// clusters are ordered among themselves, and a key's final place is the cluster's start plus the number of smaller
-// keys in its (short) cluster.  No bucket counters, no insertion-order list, no separate sort: counting the
-// duplicates and sorting the distinct keys are the same pass.  Two CTAs of 512 threads share an SM.
+// values, i.e. uniform), probing is linear and never wraps.  A key with a smaller home is a smaller key, so the sorted
+// position of a key is (number of keys with a smaller home) + (its rank among the keys that share its home).  The
+// first term is an exclusive scan over per-home key counters (one byte per home, bumped by whoever inserts a new
+// key); the second is 0 for most keys (homes are rarely shared at the load factors used) and otherwise costs a short
+// walk from the home slot.  No insertion-order list, no separate sort: counting the duplicates and sorting the distinct
+// keys are the same pass.  Two CTAs of 512 threads share an SM.
 constexpr int kAggThreads = 512;
 constexpr int kAggWarps = kAggThreads / 32;
 constexpr int kAggHomes = 8192;          // home positions (a power of two)
@@ -26,17 +27,18 @@ constexpr int kAggTable = kAggHomes + kAggPad;
 constexpr int kAggMaxProbe = kAggPad - 2;   // a longer probe sequence means skewed keys: restart with narrower key ranges
 constexpr int kAggMaxDistinct = 5000;    // what the host sizes the bins for (load factor 0.6)
 constexpr int kAggBuckets = 2048;        // upper bound of chunks per batch (first-chunk histograms)
-constexpr int kAggU = 8;                 // words per lane and warp tile
-constexpr int kAggWarpTile = 32 * kAggU; // a warp streams its share of the bin in tiles of 256 words
-constexpr int kAggSPT = (kAggTable + kAggThreads - 1) / kAggThreads;   // slots per thread in the compaction (17: odd, conflict free)
+constexpr int kAggU = 8;                 // words per thread and round
+constexpr int kAggWarpTile = 32 * kAggU; // words of one warp per round (= capacity of its pending list)
+constexpr int kAggSPT = (kAggTable + kAggThreads - 1) / kAggThreads;   // slots per thread in the emission
+constexpr int kAggHPT = kAggHomes / kAggThreads;                       // homes per thread in the scan (16 = 4 counter words)
 constexpr uint32_t kAggEmpty = 0xFFFFFFFFu;
-// t_key, t_cnt (u32) [, t_chk (u16)], then one region shared by the per-warp pending lists (insert phase) and the slot
-// order (sort phase) [, the sorted slot order (SPLIT only)]
+// t_key, t_cnt (u32), the per-home key counters (u8) [, t_chk (u16)], then one region shared by the per-warp pending
+// lists (insert phase) and the per-home output offsets (sort phase) [, the slots in key order (SPLIT only)]
 constexpr size_t kAggOrdBytes = ((size_t)kAggTable * 2 + 15) & ~(size_t)15;
 constexpr size_t kAggPendBytes = (size_t)kAggWarps * kAggWarpTile * 4;
 constexpr size_t kAggShareBytes = kAggPendBytes > kAggOrdBytes ? kAggPendBytes : kAggOrdBytes;
 constexpr size_t agg_smem_bytes(bool chunk, bool split) {
-  return (size_t)kAggTable * 8 + (chunk ? kAggOrdBytes : 0) + kAggShareBytes + (split ? kAggOrdBytes : 0);
+  return (size_t)kAggTable * 8 + (size_t)kAggHomes + (chunk ? kAggOrdBytes : 0) + kAggShareBytes + (split ? kAggOrdBytes : 0);
 }
 
 struct AggOut {
@@ -62,6 +64,7 @@ struct AggOut {
 
 struct AggTable {
   uint32_t* key; uint32_t* cnt; uint16_t* chk;
+  uint32_t* hcnt;                     // keys per home, one byte each (four homes per word)
   volatile uint32_t* overflow; int* split_overflow;
   uint32_t relmask; int hshift;       // home of a key: (key & relmask) >> hshift (or << -hshift): monotone, all kAggHomes slots
 };
@@ -109,13 +112,15 @@ __device__ __forceinline__ void agg_count(const AggTable& T, uint32_t h, uint32_
 
 // find-or-insert by linear probing from the key's home; false (and the overflow flag) if the probe sequence gets too long
 __device__ __forceinline__ bool agg_place(const AggTable& T, uint32_t kl, uint32_t* slot) {
-  uint32_t h = agg_home(T, kl);
+  const uint32_t h0 = agg_home(T, kl);
+  uint32_t h = h0;
   for (int pr = 0; pr < kAggMaxProbe; pr++, h++) {
     const uint32_t cur = T.key[h];
     if (cur == kl) { *slot = h; return true; }
     if (cur == kAggEmpty) {
       const uint32_t old = atomicCAS(&T.key[h], kAggEmpty, kl);
-      if (old == kAggEmpty || old == kl) { *slot = h; return true; }
+      if (old == kAggEmpty) { atomicAdd(&T.hcnt[h0 >> 2], 1u << ((h0 & 3u) * 8)); *slot = h; return true; }   // a new key of home h0
+      if (old == kl) { *slot = h; return true; }
     }
   }
   *T.overflow = 1;
@@ -138,15 +143,17 @@ __device__ __forceinline__ void agg_insert_pass(const uint32_t* __restrict__ pac
   uint32_t my_occ = 0, my_occ2 = 0;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   uint32_t* pend = s_pend + wid * kAggWarpTile;
-  for (uint32_t t0 = beg + wid * kAggWarpTile; t0 < end; t0 += kAggWarps * kAggWarpTile) {
+  // rounds of kAggThreads x kAggU words; inside a round word u of thread t is base + u * kAggThreads + t, so a short last
+  // round is shared by all warps (a warp-contiguous split would leave most warps idle through it)
+  for (uint32_t t0 = beg; t0 < end; t0 += kAggThreads * kAggU) {
     uint32_t wv[kAggU];
 #pragma unroll
-    for (int u = 0; u < kAggU; u++) { uint32_t i = t0 + u * 32 + lane; wv[u] = i < end ? __ldg(&packed[i]) : 0; }
+    for (int u = 0; u < kAggU; u++) { uint32_t i = t0 + u * kAggThreads + threadIdx.x; wv[u] = i < end ? __ldg(&packed[i]) : 0; }
     uint32_t np = 0;
 #pragma unroll
     for (int u = 0; u < kAggU; u++) {
       const uint32_t w = wv[u];
-      bool live = t0 + u * 32 + lane < end;
+      bool live = t0 + u * kAggThreads + threadIdx.x < end;
       const uint32_t kl = w & lowmask;
       uint32_t ch = 0;
       if (CHUNK || FILT || SPLIT) ch = lb >= 32 ? 0 : (w >> lb);
@@ -239,11 +246,12 @@ __global__ void __launch_bounds__(kAggThreads, 2) bin_aggregate_kernel(
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* t_key = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* t_cnt = t_key + kAggTable;
-  unsigned char* nxt = reinterpret_cast<unsigned char*>(t_cnt + kAggTable);
+  uint32_t* t_hcnt = t_cnt + kAggTable;                                   // keys per home: kAggHomes bytes
+  unsigned char* nxt = reinterpret_cast<unsigned char*>(t_hcnt + kAggHomes / 4);
   uint16_t* t_chk = reinterpret_cast<uint16_t*>(nxt);
   if (CHUNK) nxt += kAggOrdBytes;
   uint32_t* s_pend = reinterpret_cast<uint32_t*>(nxt);                    // insert phase: per-warp pending lists
-  uint16_t* s_ord = reinterpret_cast<uint16_t*>(nxt);                     // sort phase: occupied slots in slot order (bit 15: cluster start)
+  uint16_t* s_hpre = reinterpret_cast<uint16_t*>(nxt);                    // sort phase: keys with a smaller home, per home
   uint16_t* s_fin = reinterpret_cast<uint16_t*>(nxt + kAggShareBytes);    // SPLIT: slots in key order
   __shared__ uint32_t s_nocc, s_nocc2, s_overflow, s_na, s_nb;
 
@@ -272,6 +280,7 @@ restart:
       uint4* c4 = reinterpret_cast<uint4*>(t_cnt);
       const uint4 e4 = make_uint4(kAggEmpty, kAggEmpty, kAggEmpty, kAggEmpty), z4 = make_uint4(0, 0, 0, 0);
       for (int i = threadIdx.x; i < kAggTable / 4; i += blockDim.x) { k4[i] = e4; c4[i] = z4; }
+      t_hcnt[threadIdx.x] = 0; t_hcnt[threadIdx.x + kAggThreads] = 0; t_hcnt[threadIdx.x + 2 * kAggThreads] = 0; t_hcnt[threadIdx.x + 3 * kAggThreads] = 0;
       if (CHUNK) { uint4* h4 = reinterpret_cast<uint4*>(t_chk); for (int i = threadIdx.x; i < kAggTable / 8; i += blockDim.x) h4[i] = e4; }
     }
     if (threadIdx.x == 0) { s_nocc = 0; s_nocc2 = 0; s_overflow = 0; s_na = 0; s_nb = 0; }
@@ -281,7 +290,7 @@ restart:
     {
       const uint32_t max_chunk = lb >= 32 ? 0u : (0xFFFFFFFFu >> lb);
       const bool filt = sub_bits != 0 || chunk_lo != 0 || chunk_hi < max_chunk;   // sub_bits includes the grid's fixed bits
-      AggTable T{t_key, t_cnt, t_chk, &s_overflow, o.split_overflow, relmask, bits - 13};
+      AggTable T{t_key, t_cnt, t_chk, t_hcnt, &s_overflow, o.split_overflow, relmask, bits - 13};
 #define SHQ_AGG_CALL(F, D) agg_insert_pass<SPLIT, CHUNK, F, D>(packed, beg, end, lb, lowmask, chunk_lo, chunk_hi, cstar, sub_bits, r, T, s_pend, &s_nocc, &s_nocc2)
       if (o.direct) { if (filt) SHQ_AGG_CALL(true, true); else SHQ_AGG_CALL(false, true); }
       else { if (filt) SHQ_AGG_CALL(true, false); else SHQ_AGG_CALL(false, false); }
@@ -289,27 +298,25 @@ restart:
     }
     __syncthreads();
     if (*reinterpret_cast<volatile uint32_t*>(&s_overflow)) { sub_bits++; __syncthreads(); goto restart; }
-    // ---- compaction: every thread owns kAggSPT consecutive slots; occupied slots are listed in slot order, the
-    // first slot of every cluster flagged
+    // ---- output offsets per home: every thread owns kAggHPT consecutive homes (four counter words); the exclusive scan of
+    // the per-home key counts is the number of keys with a smaller home, i.e. where the keys of a home start in the run
     uint32_t nd;
     {
-      const int s0 = threadIdx.x * kAggSPT;
-      uint32_t mask = 0;
-#pragma unroll
-      for (int j = 0; j < kAggSPT; j++) { const int sl = s0 + j; if (sl < kAggTable && t_key[sl] != kAggEmpty) mask |= 1u << j; }
-      const bool prev_occ = s0 > 0 && s0 <= kAggTable && t_key[s0 - 1] != kAggEmpty;
+      const uint4 cw = reinterpret_cast<const uint4*>(t_hcnt)[threadIdx.x];
+      const uint32_t w4[4] = {cw.x, cw.y, cw.z, cw.w};
+      const uint32_t mine = __vsadu4(cw.x, 0u) + __vsadu4(cw.y, 0u) + __vsadu4(cw.z, 0u) + __vsadu4(cw.w, 0u);
       uint32_t tot;
-      uint32_t ex = block_exclusive_scan<SumU32>((uint32_t)__popc(mask), &tot);     // ends with a barrier: the pending lists are dead
+      uint32_t ex = block_exclusive_scan<SumU32>(mine, &tot);     // ends with a barrier: the pending lists are dead
       nd = tot;
+      uint32_t pk[kAggHPT / 2];
 #pragma unroll
-      for (int j = 0; j < kAggSPT; j++) {
-        if ((mask >> j) & 1u) {
-          const bool start = j == 0 ? !prev_occ : !((mask >> (j - 1)) & 1u);
-          s_ord[ex++] = (uint16_t)((s0 + j) | (start ? 0x8000 : 0));
-        }
+      for (int j = 0; j < kAggHPT; j++) {
+        if (j & 1) pk[j >> 1] |= ex << 16; else pk[j >> 1] = ex;
+        ex += (w4[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
       }
+      uint4* dst = reinterpret_cast<uint4*>(s_hpre + threadIdx.x * kAggHPT);
+      dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]); dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
-    __syncthreads();
     // dense output: a CTA that is done after this round (the usual case) learns its offset now and writes the run in place;
     // one that needs more rounds stages them in the scratch arrays and copies them over at the end
     const bool last_round = r + 1 == (o.sample_bits ? (fsub << (sub_bits - o.fixed_bits)) + 1 : ((fsub + 1) << (sub_bits - o.fixed_bits)));
@@ -320,31 +327,42 @@ restart:
         if (threadIdx.x == 0) { s_excl = excl; if (g == o.n_groups - 1) { o.totals[0] = excl + nd; o.totals[1] = 0; } }
       }
       did_direct = true;
-      __syncthreads();
     }
+    __syncthreads();
     uint64_t* const wkeys = o.dense ? (direct_out ? o.keys + s_excl : o.scratch_keys + obase) : o.keys + obase;
     uint32_t* const wcounts = o.dense ? (direct_out ? o.counts + s_excl : o.scratch_counts + obase) : o.counts + obase;
     uint16_t* const wchunk = !o.chunk ? nullptr : (o.dense ? (direct_out ? o.chunk + s_excl : o.scratch_chunk + obase) : o.chunk + obase);
-    // ---- place inside the cluster = number of smaller keys there; emit in key order
-    for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) {
-      const uint32_t slot = s_ord[i] & 0x7FFFu;
-      const uint32_t k = t_key[slot];
-      uint32_t a = i;
-      while (!(s_ord[a] & 0x8000u)) a--;
-      uint32_t rank = 0;
-      for (uint32_t x = a; x < i; x++) rank += t_key[s_ord[x] & 0x7FFFu] < k ? 1u : 0u;
-      for (uint32_t x = i + 1; x < nd && !(s_ord[x] & 0x8000u); x++) rank += t_key[s_ord[x] & 0x7FFFu] < k ? 1u : 0u;
-      const uint32_t pos = a + rank;
-      if (SPLIT) { s_fin[pos] = (uint16_t)slot; continue; }
-      const size_t oo = (size_t)written + pos;
-      wkeys[oo] = key_lo + (((uint64_t)p << lb) | k);
-      wcounts[oo] = t_cnt[slot];
-      if (CHUNK) {
-        const uint32_t fc = t_chk[slot];
-        if (wchunk) wchunk[oo] = (uint16_t)fc;
-        if (o.first_hist) {                       // one atomic per (warp, chunk id): chunk ids of neighbouring keys repeat
-          const uint32_t peers = __match_any_sync(__activemask(), fc);
-          if ((uint32_t)(threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&o.first_hist[fc & (kAggBuckets - 1)], (uint32_t)__popc(peers));
+    // ---- emit in key order: slot by slot (lanes read neighbouring slots and, the order being preserved, write
+    // neighbouring entries).  Keys that share their home are ranked by a walk from the home slot: they all sit at or
+    // behind it with nothing but occupied slots in between, and the walk stops at the last of them.
+    {
+      const AggTable T{t_key, t_cnt, t_chk, t_hcnt, &s_overflow, o.split_overflow, relmask, bits - 13};
+#pragma unroll 1
+      for (int j = 0; j < kAggSPT; j++) {
+        const uint32_t slot = threadIdx.x + j * kAggThreads;
+        const uint32_t k = slot < (uint32_t)kAggTable ? t_key[slot] : kAggEmpty;
+        if (k == kAggEmpty) continue;
+        const uint32_t h = agg_home(T, k);
+        const uint32_t same = (t_hcnt[h >> 2] >> ((h & 3u) * 8)) & 0xFFu;
+        uint32_t pos = s_hpre[h];
+        if (same > 1) {
+          uint32_t seen = 0;
+          for (uint32_t x = h; seen < same && x < (uint32_t)kAggTable; x++) {
+            const uint32_t kx = t_key[x];
+            if (agg_home(T, kx) == h) { seen++; pos += kx < k ? 1u : 0u; }
+          }
+        }
+        if (SPLIT) { s_fin[pos] = (uint16_t)slot; continue; }
+        const size_t oo = (size_t)written + pos;
+        wkeys[oo] = key_lo + (((uint64_t)p << lb) | k);
+        wcounts[oo] = t_cnt[slot];
+        if (CHUNK) {
+          const uint32_t fc = t_chk[slot];
+          if (wchunk) wchunk[oo] = (uint16_t)fc;
+          if (o.first_hist) {                       // one atomic per (warp, chunk id): chunk ids of neighbouring keys repeat
+            const uint32_t peers = __match_any_sync(__activemask(), fc);
+            if ((uint32_t)(threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&o.first_hist[fc & (kAggBuckets - 1)], (uint32_t)__popc(peers));
+          }
         }
       }
     }
@@ -555,13 +573,34 @@ __global__ void __launch_bounds__(kMergeThreads) merge_tiles_lookback_kernel(
   const size_t b0 = diag0 - a0, b1 = diag1 - a1;
   const int la = (int)(a1 - a0), lbn = (int)(b1 - b0);
   const uint64_t kNone = ~0ULL;
-  for (int i = threadIdx.x; i < la + 1; i += blockDim.x) s_a[i] = (i == 0) ? (a0 > 0 ? A[a0 - 1] : kNone) : A[a0 + i - 1];
-  for (int i = threadIdx.x; i < lbn + 1; i += blockDim.x) s_b[i] = (i < lbn) ? B[b0 + i] : (b1 < nb ? B[b1] : kNone);
-  for (int i = threadIdx.x; i < la; i += blockDim.x) s_ac[i] = Ac[a0 + i];
-  // one count past the tile's B range: an A key at the very end of the tile may match B[b1]
-  for (int i = threadIdx.x; i < lbn + 1; i += blockDim.x) s_bc[i] = (b0 + i < nb) ? Bc[b0 + i] : 0;
-  __syncthreads();
   const int total = la + lbn;
+  {
+    // staging: la + 1 keys of A (from a0 - 1) followed by lbn + 1 keys of B, and the matching counts (one count past
+    // the tile's B range: an A key at the very end of the tile may match B[b1]).  Fixed trip count, loads first and
+    // shared-memory stores after, so that all of a thread's loads are in flight together.
+    constexpr int kLd = kMergeItems + 1;           // (total + 2) / kMergeThreads rounded up
+    uint64_t vk[kLd]; uint32_t vc[kLd];
+#pragma unroll
+    for (int j = 0; j < kLd; j++) {
+      const int i = threadIdx.x + j * kMergeThreads;
+      uint64_t k = kNone; uint32_t c = 0;
+      if (i <= la) {
+        if (i > 0) { k = A[a0 + i - 1]; c = Ac[a0 + i - 1]; }
+        else if (a0 > 0) k = A[a0 - 1];
+      } else if (i < total + 2) {
+        const size_t bj = b0 + (size_t)(i - la - 1);
+        if (bj < nb) { k = B[bj]; c = Bc[bj]; }
+      }
+      vk[j] = k; vc[j] = c;
+    }
+#pragma unroll
+    for (int j = 0; j < kLd; j++) {
+      const int i = threadIdx.x + j * kMergeThreads;
+      if (i <= la) { s_a[i] = vk[j]; if (i > 0) s_ac[i - 1] = vc[j]; }
+      else if (i < total + 2) { s_b[i - la - 1] = vk[j]; s_bc[i - la - 1] = vc[j]; }
+    }
+  }
+  __syncthreads();
   int d0 = min(threadIdx.x * kMergeItems, total), d1 = min(d0 + kMergeItems, total);
   int lo = max(0, d0 - lbn), hi = min(d0, la);
   while (lo < hi) {

@@ -61,6 +61,11 @@ struct shq_handle_s {
   std::vector<uint64_t> stage_chunk_ends;
   int stage_K = 0;
   size_t max_batch_bytes = (size_t)1 << 28;   // first batches; later ones grow with the state (batch_target_bytes)
+  size_t batch_cap_bytes = (size_t)3 << 30;   // ... up to this much text (SHQ_BATCH_CAP_MB)
+  int wide_batches = 1;          // SHQ_WIDE: 0 = never batch past the armed chunk cap while rounds are pending, 1 = when the trigger is
+                                 // predicted to be far away, 2 = always (tests: exercises the fallback)
+  int armed_chunk_cap = 0;       // SHQ_ARMED_CHUNKS: override of the chunks an armed batch may hold (tests)
+  double bytes_per_kmer = 3.0;   // text bytes per k-mer, from the last batch
   bool batch_fixed = false;                   // SHQ_MAX_BATCH_MB given: every batch at most that size
   // tunables (environment, read once per handle in init_handle)
   bool spec_bins = true;         // SHQ_SPEC_BINS=0 forces the two-pass (count, then scatter) binning
@@ -73,8 +78,8 @@ struct shq_handle_s {
   // pinned-source pipeline: copy stream + 3 rotating device text buffers
   struct PinBatch { int buf; size_t bytes; std::vector<uint64_t> ends; int K; cudaEvent_t ev; };
   cudaStream_t cstream = nullptr;
-  DevBuf pin_buf[3];
-  size_t pin_cap = 0;
+  DevBuf pin_buf[4];
+  size_t pin_cap = 0, pin_chunk_cap = 1;
   int pin_cur = 0; size_t pin_fill = 0; std::vector<uint64_t> pin_ends; int pin_K = 0;
   std::vector<PinBatch> pin_queue;
 
@@ -88,6 +93,7 @@ struct shq_handle_s {
   DevBuf d_fine2;   // offsets of the second-level bins
   DevBuf d_seg, d_fine, d_fine_cur, d_packed2, d_bases;   // second binning level (single GPU: fine bins; multi-GPU: owner-side split)
   int fine_bits_forced = -1;     // SHQ_FINE_BITS: force the second binning level (0 = off)
+  double fine_target = 3500.0;   // SHQ_FINE_TARGET: distinct keys per fine bin the second level aims below
   // pull exchange: two fixed binned-word buffers that peers map through CUDA IPC, and the peers' buffers mapped here
   uint32_t* mg_send[2] = {nullptr, nullptr};
   size_t mg_cap_words = 0;
@@ -235,13 +241,14 @@ int pick_bin_bits(shq_handle_s* h, uint64_t est_keys, int chunk_bits_needed) {
 // start small; and the distinct keys of a batch must fit the aggregator's per-bin tables (~6500 keys x 4096 bins).
 size_t batch_target_bytes(shq_handle_s* h) {
   if (h->batch_fixed) return h->max_batch_bytes;
-  double t = (double)h->max_batch_bytes * std::max(1.0, (double)h->n_state / 2.5e7);
-  t = std::min(t, 1024.0 * 1048576.0);
+  double t = (double)h->max_batch_bytes * std::max(1.0, (double)h->n_state / 8.0e6);
+  t = std::min(t, (double)h->batch_cap_bytes);
   return (size_t)t;
 }
 // Chunks per batch while rounds are pending: the chunk id shares the 32-bit packed word with the low key bits
 size_t batch_chunk_cap(shq_handle_s* h) {
   if (h->rounds_left == 0) return (size_t)1 << 20;
+  if (h->armed_chunk_cap > 0) return (size_t)h->armed_chunk_cap;
   int shard_bits = 0; while ((1 << shard_bits) < h->nshards) shard_bits++;
   const int local_bits = h->hb - shard_bits;
   int bits = 32 - (local_bits - 12);                // with 4096 bins
@@ -249,6 +256,32 @@ size_t batch_chunk_cap(shq_handle_s* h) {
   if (bits < 0) bits = 0;
   if (bits > 10) bits = 10;                         // histogram arrays of the merge / aggregation kernels
   return (size_t)1 << bits;
+}
+// Text bytes and chunks the next batch may hold.  While rounds are pending a batch normally keeps the chunk id of every
+// word (<= batch_chunk_cap chunks, <= 1 GiB), so that a deNoise boundary inside it can be located.  When the new-key rate
+// of the previous batch says that the trigger is still far away, the batch is made WIDE instead: as much text as is
+// predicted to stay below the trigger (up to batch_cap_bytes), binned without chunk ids and merged speculatively; should
+// the trigger be reached after all, process_batch() drops the shadow and redoes the batch in halves.  Fewer, larger
+// batches mean fewer passes over the resident state.
+constexpr size_t kArmedBatchBytes = (size_t)1 << 30;
+void batch_limits(shq_handle_s* h, size_t* bytes, size_t* chunks) {
+  size_t t = batch_target_bytes(h), c = batch_chunk_cap(h);
+  if (h->rounds_left > 0) {
+    const size_t armed_bytes = std::min(t, kArmedBatchBytes);
+    bool wide = false;
+    if (h->wide_batches == 2) { c = (size_t)1 << 20; wide = true; }
+    else if (h->wide_batches && h->new_rate >= 0 && h->n_state > 0 && h->ndistinct < h->trigger) {
+      const double room = (double)(h->trigger - h->ndistinct) / std::max(h->new_rate * 1.3, 1e-9);   // k-mers until the predicted crossing
+      double pending = 0;                                   // text already queued behind the state (pinned pipeline)
+      for (const auto& b : h->pin_queue) pending += (double)b.bytes;
+      const double room_bytes = room * h->bytes_per_kmer - pending;
+      if (h->armed_chunk_cap > 0 || (t > armed_bytes && room_bytes > 1.5 * (double)armed_bytes)) {
+        t = (size_t)std::min((double)t, room_bytes); c = (size_t)1 << 20; wide = true;
+      }
+    }
+    if (!wide) t = armed_bytes;
+  }
+  *bytes = t; *chunks = c;
 }
 
 // Capacity of a fixed-size bin that is to receive `mean` words on average.  ntHash keys are uniform, but the c
@@ -337,7 +370,7 @@ void refine_bins(shq_handle_s* h, BatchBins* bb, uint32_t max_bin_words) {
   const double ratio = bb->ratio >= 0 ? std::min(1.0, bb->ratio * 1.1) : 1.0;
   const double est_d = (double)n_ub / (double)n_bins * ratio;
   int fb = 0;
-  while (fb < 5 && lb - fb > 1 && est_d / (double)(1 << fb) > 3500.0) fb++;      // load factor of the aggregator's table <= ~0.45
+  while (fb < 5 && lb - fb > 1 && est_d / (double)(1 << fb) > h->fine_target) fb++;      // load factor of the aggregator's table <= ~0.45
   if (h->fine_bits_forced >= 0) fb = std::min(h->fine_bits_forced, std::min(5, lb - 1));
   const uint64_t n_fine = (uint64_t)n_bins << fb;
   const uint64_t capfine = bin_capacity(h, n_ub / n_fine);
@@ -853,11 +886,55 @@ void process_batch(shq_handle_s* h, const char* d_text, size_t n_text, const uin
   }
   if (!from_text && n_keys_in == 0) return;
   bool armed = from_text && h->rounds_left > 0;
+  Run A{&h->d_run_keys, &h->d_run_counts, &h->d_run_chunk}, B{&h->d_run2_keys, &h->d_run2_counts, nullptr};
+  if (armed && (size_t)nchunks > batch_chunk_cap(h)) {
+    // WIDE batch (batch_limits): more chunks than the packed word has chunk-id bits for.  Binned without chunk ids and
+    // merged speculatively as a whole; if the trigger is reached inside after all, the halves are processed on their own
+    // (each may be wide again), down to batches that keep their chunk ids.
+    bool done = false;
+    if (h->ndistinct < h->trigger && h->n_state > 0) {
+      BatchBins wb;
+      for (int attempt = 0; attempt < 2 && !done; attempt++) {
+        try {
+          bin_batch(h, d_text, n_text, chunk_ends, nchunks, K, nullptr, 0, false, &wb, 0, attempt == 0);
+          if (attempt == 0) h->stats.batches++;
+          if (wb.n_keys == 0) break;
+          if (wb.n_keys > 4096) h->bytes_per_kmer = (double)n_text / (double)wb.n_keys;
+          aggregate_bins(h, wb, 0, 0xFFFFFFFFu, false, 0, &A, nullptr, nullptr);
+          const uint64_t n_out = merge_shadow(h, A, 1, nullptr);
+          if (h->ndistinct + (n_out - h->n_state) < h->trigger) {
+            const uint64_t n_new = commit_shadow(h, n_out);
+            h->ndistinct += n_new; h->nelts += A.occ;
+            if (A.occ > 4096) h->new_rate = (double)n_new / (double)A.occ;
+            done = true;
+          }
+          break;
+        } catch (const BinOverflow&) { h->stats.bin_fallbacks++; }
+      }
+      if (!done && wb.n_keys == 0) {      // no k-mer in the whole batch: only the per-chunk trigger checks remain (none can fire below the trigger)
+        check_err_flag(h);
+        return;
+      }
+      if (!done) { h->stats.spec_rejected++; h->stats.wide_fallbacks++; }
+    }
+    if (!done) {
+      const int m = nchunks / 2;
+      const uint64_t cut = chunk_ends[m - 1];
+      process_batch(h, d_text, (size_t)cut, chunk_ends, m, K, nullptr, 0);
+      std::vector<uint64_t> rest(chunk_ends + m, chunk_ends + nchunks);
+      for (auto& e : rest) e -= cut;
+      process_batch(h, d_text + cut, n_text - (size_t)cut, rest.data(), nchunks - m, K, nullptr, 0);
+    } else {
+      h->stats.wide_batches++;
+      check_err_flag(h);
+    }
+    return;
+  }
   BatchBins bb;
   bin_batch(h, d_text, n_text, chunk_ends, nchunks, K, d_keys, n_keys_in, armed, &bb, 0, true);
   h->stats.batches++;
   if (bb.n_keys == 0) return;
-  Run A{&h->d_run_keys, &h->d_run_counts, &h->d_run_chunk}, B{&h->d_run2_keys, &h->d_run2_counts, nullptr};
+  if (from_text && bb.n_keys > 4096) h->bytes_per_kmer = (double)n_text / (double)bb.n_keys;
   uint32_t clo = 0;
   const uint32_t last = (uint32_t)(nchunks > 0 ? nchunks - 1 : 0);
   const uint32_t all = 0xFFFFFFFFu;
@@ -987,7 +1064,7 @@ void pin_seal(shq_handle_s* h) {
   SHQ_CUDA(cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming));
   SHQ_CUDA(cudaEventRecord(b.ev, h->cstream));
   h->pin_queue.push_back(b);
-  h->pin_cur = (h->pin_cur + 1) % 3; h->pin_fill = 0; h->pin_ends.clear();
+  h->pin_cur = (h->pin_cur + 1) % 4; h->pin_fill = 0; h->pin_ends.clear();
 }
 void pin_drain(shq_handle_s* h) {
   pin_seal(h);
@@ -1038,7 +1115,11 @@ void init_handle(shq_handle_s* h, int qb, int hb, uint32_t seed, int device, int
   if (nshards < 1 || (nshards & (nshards - 1)) || shard < 0 || shard >= nshards || (1 << qb) < nshards * 64)
     SHQ_FAIL(SHQ_ERR_ARG, "bad shard %d of %d", shard, nshards);
   if (const char* e = getenv("SHQ_MAX_BATCH_MB")) { long v = atol(e); if (v >= 1 && v <= 3072) { h->max_batch_bytes = (size_t)v << 20; h->batch_fixed = true; } }
+  if (const char* e = getenv("SHQ_BATCH_CAP_MB")) { long v = atol(e); if (v >= 64 && v <= 3072) h->batch_cap_bytes = (size_t)v << 20; }
+  if (const char* e = getenv("SHQ_WIDE")) { int v = atoi(e); if (v >= 0 && v <= 2) h->wide_batches = v; }
+  if (const char* e = getenv("SHQ_ARMED_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 1024) h->armed_chunk_cap = v; }
   if (const char* e = getenv("SHQ_SPEC_BINS")) h->spec_bins = atoi(e) != 0;
+  if (const char* e = getenv("SHQ_FINE_TARGET")) { double v = atof(e); if (v >= 500 && v <= 7000) h->fine_target = v; }
   if (const char* e = getenv("SHQ_FINE_BITS")) { int v = atoi(e); if (v >= 0 && v <= 5) h->fine_bits_forced = v; }
   if (const char* e = getenv("SHQ_MERGE_LOOKBACK")) h->merge_lookback = atoi(e) != 0;
   if (const char* e = getenv("SHQ_MERGE_TMA")) h->merge_tma = atoi(e) != 0;
@@ -1193,7 +1274,8 @@ int shq_insert_fastq_chunk(shq_t h, const char* text, size_t n, int K) {
   if (!h || (!text && n)) return SHQ_ERR_ARG;
   struct { const char* text; size_t n; int K; } args{text, n, K};
   SHQ_API_BEGIN(h)
-    const size_t target = batch_target_bytes(h);
+    // the staged path copies through one page-locked host buffer: its batches stay within 1 GiB and the armed chunk cap
+    const size_t target = std::min(batch_target_bytes(h), kArmedBatchBytes);
     if ((h->h_stage_fill || !h->stage_chunk_ends.empty()) &&
         (h->stage_K != a.K || h->h_stage_fill + a.n > target || h->stage_chunk_ends.size() >= batch_chunk_cap(h))) flush_stage(h);
     if (a.n >= ((size_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "chunk too large");
@@ -1220,13 +1302,17 @@ int shq_insert_fastq_pinned(shq_t h, const char* text, size_t n, int K) {
     if (h->h_stage_fill || !h->stage_chunk_ends.empty()) flush_stage(h);     // keep chunk order if the staged path was used before
     if (a.n >= ((size_t)1 << 31)) SHQ_FAIL(SHQ_ERR_ARG, "chunk too large");
     if (!h->cstream) SHQ_CUDA(cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking));
-    if (h->pin_fill && (h->pin_K != a.K || h->pin_fill + a.n > h->pin_cap || h->pin_ends.size() >= batch_chunk_cap(h))) {
+    if (h->pin_fill && (h->pin_K != a.K || h->pin_fill + a.n > h->pin_cap || h->pin_ends.size() >= h->pin_chunk_cap)) {
       pin_seal(h);
-      // keep one sealed batch in flight behind the one being processed: its copies overlap the compute
-      while (h->pin_queue.size() >= 2) pin_process_oldest(h);
+      // keep two sealed batches in flight behind the one being processed: process_batch blocks this thread, and only
+      // copies that were issued before it starts can overlap it -- with one batch ahead the copy engine idles whenever a
+      // batch computes for longer than the next one copies
+      while (h->pin_queue.size() >= 3) pin_process_oldest(h);
     }
     if (h->pin_fill == 0) {      // a new batch: its size is fixed now (the buffer must not move under copies in flight)
-      h->pin_cap = std::max(batch_target_bytes(h), a.n);
+      size_t lim_bytes, lim_chunks;
+      batch_limits(h, &lim_bytes, &lim_chunks);
+      h->pin_cap = std::max(lim_bytes, a.n); h->pin_chunk_cap = lim_chunks;
       h->pin_buf[h->pin_cur].reserve(h->pin_cap + 64);
     }
     // 16-byte alignment of every batch start holds because each batch starts at offset 0 of its buffer
@@ -1259,7 +1345,8 @@ int shq_insert_fastq_device(shq_t h, const char* d_text, size_t n, const uint64_
     while (c0 < a.nc) {
       uint64_t base = c0 ? a.ce[c0 - 1] : 0;
       size_t c1 = c0;
-      const size_t target = batch_target_bytes(h), cmax = batch_chunk_cap(h);
+      size_t target, cmax;
+      batch_limits(h, &target, &cmax);
       while (c1 < a.nc && a.ce[c1] - base <= target && c1 - c0 < cmax) c1++;
       if (c1 == c0) c1 = c0 + 1;
       std::vector<uint64_t> ends(a.ce + c0, a.ce + c1);

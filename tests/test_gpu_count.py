@@ -174,6 +174,48 @@ def test_pinned_pipeline_matches_oracle(po, shq, batch_mb, monkeypatch):
     g.close()
 
 
+@pytest.mark.parametrize("wide,path", [("2", "device"), ("2", "pinned"), ("1", "device")])
+def test_wide_batches_match_oracle(po, shq, wide, path, monkeypatch):
+    """Batches past the armed chunk cap (binned without chunk ids, merged speculatively): a wide batch that reaches the
+    deNoise trigger is dropped and redone in halves.  SHQ_WIDE=2 forces every pending-round batch wide, so the halving runs
+    down to single chunks around each of the three boundaries; SHQ_WIDE=1 is the production rule (by the new-key rate)."""
+    import torch
+    monkeypatch.setenv("SHQ_MAX_BATCH_MB", "6")
+    monkeypatch.setenv("SHQ_ARMED_CHUNKS", "2")
+    monkeypatch.setenv("SHQ_WIDE", wide)
+    K, qb = 27, 22
+    files = [fastq(po, G=150000, cov=30, err=0.008, seed=91 + i, L=120) for i in range(2)]
+    part = 1 << 19
+    total_distinct = len(np.unique(np.concatenate([po.reads_to_keys(f, K, qb + 8) for f in files])))
+    trigger = total_distinct // 4
+    o, o_rounds = po.count_run(files, K, qb, qb + 8, trigger, 3, False, part_size=part)
+    g = shq.CQF(qb, qb + 8)
+    g.set_denoise_schedule(trigger, 3, False)
+    chunks = [ch for _, ch in po.chunks(files, part_size=part)]
+    if path == "pinned":
+        keep = []
+        for ch in chunks:
+            t = torch.frombuffer(bytearray(ch), dtype=torch.uint8).pin_memory()
+            keep.append(t)
+            g.insert_fastq_pinned_raw(t.data_ptr(), t.numel(), K)
+    else:
+        text = b"".join(chunks)
+        ends = np.cumsum([len(ch) for ch in chunks]).astype(np.uint64)
+        d = torch.empty(len(text) + 64, dtype=torch.uint8, device="cuda")
+        d[:len(text)].copy_(torch.frombuffer(bytearray(text), dtype=torch.uint8))
+        torch.cuda.synchronize()
+        g.insert_fastq_device(d.data_ptr(), len(text), ends, K)
+    g.finish()
+    st = g.stats()
+    assert g.rounds_done() == o_rounds == 3
+    assert g.counts() == o.counts()
+    assert g.export() == o.export()
+    assert st["wide_batches"] > 0
+    if wide == "2":
+        assert st["wide_fallbacks"] >= 3
+    g.close()
+
+
 def _mg_text(po):
     return fastq(po, G=80000, cov=30, err=0.004, n_rate=0.0003, seed=77)
 

@@ -304,6 +304,19 @@ def run_workload(args, name, steps, warmup, local_rank, want_unitigs, want_cpu):
     ms_e2e = max(e2.elapsed_time(e3), 1000 * (time.perf_counter() - t0)) / e2e_steps
     st2 = q.stats()
 
+    # the floor of the e2e leg on this box: the same bytes through the same host link with nothing else to do
+    scratch = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    f0.record()
+    for off in range(0, n_bytes, 1 << 30):
+        m = min(1 << 30, n_bytes - off)
+        scratch[:m].copy_(h_text[off:off + m], non_blocking=True)
+    f1.record()
+    torch.cuda.synchronize()
+    h2d_floor_ms = f0.elapsed_time(f1)
+    del scratch
+
     # parity: the image the e2e leg just exported against the digest of the unmodified reference core
     gold = golden_digest(name, 1)
     sha = hashlib.sha256(memoryview(img)).hexdigest()
@@ -323,11 +336,15 @@ def run_workload(args, name, steps, warmup, local_rank, want_unitigs, want_cpu):
             "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic", "config": config_dict(w, 1, p, name), "clocks": clocks,
             "e2e": {"value": n_total / (ms_e2e / 1e3), "unit": "k-mers/s", "h2d_bytes_per_step": int(st2["h2d_bytes"] // e2e_steps),
-                    "d2h_bytes_per_step": int(st2["d2h_bytes"] // e2e_steps), "ms_per_step": ms_e2e, "steps": e2e_steps},
+                    "d2h_bytes_per_step": int(st2["d2h_bytes"] // e2e_steps), "ms_per_step": ms_e2e, "steps": e2e_steps,
+                    "h2d_floor_ms": h2d_floor_ms, "batches_per_step": st2["batches"] / e2e_steps, "wide_batches": int(st2["wide_batches"]),
+                    "wide_fallbacks": int(st2["wide_fallbacks"]), "spec_rejected": int(st2["spec_rejected"]),
+                    "gpu_busy_ms_per_step": sum(st2[k] for k in st2 if k.startswith("ms_")) / e2e_steps},
             "gpu_launches": int(stats["kernels_launched"]), "roofline": roofline(stats, steps, value, a_ins, table_bytes),
             "result": {"ndistinct": int(ndistinct), "nelts": int(nelts), "denoise_rounds": int(rounds), "kmers_per_step": int(n_total),
                        "batches_per_step": stats["batches"] / steps, "host_syncs_per_step": stats["host_syncs"] / steps,
-                       "bin_fallbacks": int(stats["bin_fallbacks"])},
+                       "bin_fallbacks": int(stats["bin_fallbacks"]), "wide_batches": int(stats["wide_batches"]),
+                       "wide_fallbacks": int(stats["wide_fallbacks"]), "spec_rejected": int(stats["spec_rejected"])},
             "parity": parity}
     if want_unitigs:
         line["unitig"] = bench_unitigs(args, shq, q, text, ends, h_ptr, K)

@@ -9,6 +9,8 @@
 #include <time.h>
 
 #include <algorithm>
+#include <chrono>
+#include <deque>
 
 #include "shq_aggregate.cuh"
 #include "shq_common.cuh"
@@ -75,13 +77,16 @@ struct shq_handle_s {
   // progress lines of the reference scheduler on stderr (cqf/CQF_mt.h:867-868, 912)
   bool log_progress = false; uint64_t ndistinct_true = 0;
 
-  // pinned-source pipeline: copy stream + 3 rotating device text buffers
-  struct PinBatch { int buf; size_t bytes; std::vector<uint64_t> ends; int K; cudaEvent_t ev; };
+  // Pinned pipeline (shq_insert_fastq_pinned): a device RING that the chunks are copied into as they are handed over
+  // (copy stream), decoupled from the batches: a batch is whatever run of chunks has ARRIVED when the GPU is free for
+  // the next one.  pin_chunks = chunks copied (or being copied) and not yet processed, in order.
+  struct PinChunk { size_t off, n; int K; cudaEvent_t ev; };
   cudaStream_t cstream = nullptr;
-  DevBuf pin_buf[4];
-  size_t pin_cap = 0, pin_chunk_cap = 1;
-  int pin_cur = 0; size_t pin_fill = 0; std::vector<uint64_t> pin_ends; int pin_K = 0;
-  std::vector<PinBatch> pin_queue;
+  DevBuf pin_ring; size_t pin_ring_size = 0;
+  size_t pin_head = 0;           // next write offset
+  size_t pin_unproc = 0;         // bytes of pin_chunks
+  std::deque<PinChunk> pin_chunks;
+  std::vector<cudaEvent_t> pin_ev_pool;
 
   // scratch
   DevBuf d_text, d_nl_tiles, d_nl_pos, d_chunk_ends, d_chunk_line_end, d_chunk_keys, d_chunk_hist, d_slow;
@@ -241,7 +246,8 @@ int pick_bin_bits(shq_handle_s* h, uint64_t est_keys, int chunk_bits_needed) {
 // start small; and the distinct keys of a batch must fit the aggregator's per-bin tables (~6500 keys x 4096 bins).
 size_t batch_target_bytes(shq_handle_s* h) {
   if (h->batch_fixed) return h->max_batch_bytes;
-  double t = (double)h->max_batch_bytes * std::max(1.0, (double)h->n_state / 8.0e6);
+  // (a small state merges in no time: E. coli-size jobs keep 256 MiB batches, whose bins need no second level)
+  double t = (double)h->max_batch_bytes * (h->n_state < 25000000 ? 1.0 : (double)h->n_state / 8.0e6);
   t = std::min(t, (double)h->batch_cap_bytes);
   return (size_t)t;
 }
@@ -273,8 +279,8 @@ void batch_limits(shq_handle_s* h, size_t* bytes, size_t* chunks) {
     else if (h->wide_batches && h->new_rate >= 0 && h->n_state > 0 && h->ndistinct < h->trigger) {
       const double room = (double)(h->trigger - h->ndistinct) / std::max(h->new_rate * 1.3, 1e-9);   // k-mers until the predicted crossing
       double pending = 0;                                   // text already queued behind the state (pinned pipeline)
-      for (const auto& b : h->pin_queue) pending += (double)b.bytes;
-      const double room_bytes = room * h->bytes_per_kmer - pending;
+      pending = 0;   // (the pinned pipeline sizes a batch when it is about to be processed: nothing is queued ahead of that decision)
+      const double room_bytes = std::max(0.0, room * h->bytes_per_kmer - pending);
       if (h->armed_chunk_cap > 0 || (t > armed_bytes && room_bytes > 1.5 * (double)armed_bytes)) {
         t = (size_t)std::min((double)t, room_bytes); c = (size_t)1 << 20; wide = true;
       }
@@ -1049,26 +1055,44 @@ size_t hash_to_keylist(shq_handle_s* h, const char* d_text, size_t n, int K, uin
   return (size_t)total;
 }
 
-void pin_process_oldest(shq_handle_s* h) {
-  shq_handle_s::PinBatch b = h->pin_queue.front();
-  h->pin_queue.erase(h->pin_queue.begin());
-  SHQ_CUDA(cudaStreamWaitEvent(h->stream, b.ev, 0));
-  SHQ_CUDA(cudaEventSynchronize(b.ev));
-  cudaEventDestroy(b.ev);
-  process_batch(h, h->pin_buf[b.buf].as<char>(), b.bytes, b.ends.data(), (int)b.ends.size(), b.K, nullptr, 0);
-}
-void pin_seal(shq_handle_s* h) {
-  if (h->pin_fill == 0) return;
-  shq_handle_s::PinBatch b;
-  b.buf = h->pin_cur; b.bytes = h->pin_fill; b.ends.swap(h->pin_ends); b.K = h->pin_K;
-  SHQ_CUDA(cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming));
-  SHQ_CUDA(cudaEventRecord(b.ev, h->cstream));
-  h->pin_queue.push_back(b);
-  h->pin_cur = (h->pin_cur + 1) % 4; h->pin_fill = 0; h->pin_ends.clear();
+// Process ONE batch out of the ring: the longest run of chunks at the front of pin_chunks that is contiguous, of one K,
+// within the batch limits and -- unless `all` -- already copied; at least kPinMinBatch bytes of it are waited for.
+constexpr size_t kPinMinBatch = (size_t)256 << 20;
+void pin_process_next(shq_handle_s* h, bool all) {
+  if (h->pin_chunks.empty()) return;
+  size_t lim_bytes, lim_chunks;
+  batch_limits(h, &lim_bytes, &lim_chunks);
+  const size_t min_bytes = std::min(kPinMinBatch, lim_bytes);
+  const shq_handle_s::PinChunk first = h->pin_chunks.front();
+  std::vector<uint64_t> ends;
+  size_t bytes = 0, taken = 0;
+  for (const auto& c : h->pin_chunks) {
+    if (taken) {
+      if (c.K != first.K || c.off != first.off + bytes || bytes + c.n > lim_bytes || taken >= lim_chunks) break;
+      if (!all && bytes >= min_bytes && cudaEventQuery(c.ev) != cudaSuccess) break;   // not there yet: the next batch takes it
+    }
+    bytes += c.n; taken++; ends.push_back(bytes);
+  }
+  const cudaEvent_t last = h->pin_chunks[taken - 1].ev;
+  SHQ_CUDA(cudaStreamWaitEvent(h->stream, last, 0));
+  SHQ_CUDA(cudaEventSynchronize(last));
+  for (size_t i = 0; i < taken; i++) { h->pin_ev_pool.push_back(h->pin_chunks.front().ev); h->pin_chunks.pop_front(); }
+  h->pin_unproc -= bytes;
+  process_batch(h, h->pin_ring.as<char>() + first.off, bytes, ends.data(), (int)ends.size(), first.K, nullptr, 0);
 }
 void pin_drain(shq_handle_s* h) {
-  pin_seal(h);
-  while (!h->pin_queue.empty()) pin_process_oldest(h);
+  while (!h->pin_chunks.empty()) pin_process_next(h, true);
+}
+// room for n more bytes at the head of the ring without touching unprocessed text?  (may wrap the head to 0)
+bool pin_make_room(shq_handle_s* h, size_t n) {
+  if (h->pin_chunks.empty()) { h->pin_head = 0; return n <= h->pin_ring_size; }
+  const size_t tail = h->pin_chunks.front().off;
+  if (h->pin_head >= tail) {                           // unprocessed text is [tail, head)
+    if (h->pin_head + n <= h->pin_ring_size) return true;
+    if (n < tail) { h->pin_head = 0; return true; }    // wrap: the next batch starts at the front of the ring
+    return false;
+  }
+  return h->pin_head + n < tail;                       // wrapped: unprocessed text is [tail, ...) and [0, head)
 }
 
 void flush_stage(shq_handle_s* h) {
@@ -1150,12 +1174,13 @@ void free_handle(shq_handle_s* h) {
                     &h->d_scan_scratch, &h->d_misc, &h->d_pairs, &h->d_pos, &h->d_flags, &h->d_keep, &h->d_q_in, &h->d_q_cnt, &h->d_q_was,
                     &h->d_tmp_keys2, &h->d_tmp_counts2, &h->d_run2_keys, &h->d_run2_counts, &h->d_seg, &h->d_fine, &h->d_fine_cur, &h->d_packed2, &h->d_bases, &h->d_sample, &h->d_fine2, &h->d_walk, &h->d_aggctl};
   for (DevBuf* b : bufs) b->release();
-  for (auto& b : h->pin_buf) b.release();
+  h->pin_ring.release();
   for (void* p : h->mg_opened) cudaIpcCloseMemHandle(p);
   for (void* p : h->img_opened) cudaIpcCloseMemHandle(p);
   h->d_img_peer.release();
   for (uint32_t* p : h->mg_send) if (p) cudaFree(p);
-  for (auto& b : h->pin_queue) cudaEventDestroy(b.ev);
+  for (auto& c : h->pin_chunks) cudaEventDestroy(c.ev);
+  for (auto e : h->pin_ev_pool) cudaEventDestroy(e);
   if (h->cstream) { cudaStreamSynchronize(h->cstream); cudaStreamDestroy(h->cstream); }
   if (h->d_err) cudaFree(h->d_err);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -1252,8 +1277,8 @@ int shq_reset(shq_t h) {
   h->image_valid = false; h->image_only = false;
   h->trigger = 0; h->rounds_left = 0; h->end_denoise = false; h->rounds_done = 0; h->finished = false;
   h->h_stage_fill = 0; h->stage_chunk_ends.clear();
-  for (auto& b : h->pin_queue) cudaEventDestroy(b.ev);
-  h->pin_queue.clear(); h->pin_fill = 0; h->pin_ends.clear();
+  for (auto& c : h->pin_chunks) h->pin_ev_pool.push_back(c.ev);
+  h->pin_chunks.clear(); h->pin_head = 0; h->pin_unproc = 0;
   if (h->cstream) cudaStreamSynchronize(h->cstream);
   return SHQ_OK;
 }
@@ -1302,23 +1327,32 @@ int shq_insert_fastq_pinned(shq_t h, const char* text, size_t n, int K) {
     if (h->h_stage_fill || !h->stage_chunk_ends.empty()) flush_stage(h);     // keep chunk order if the staged path was used before
     if (a.n >= ((size_t)1 << 31)) SHQ_FAIL(SHQ_ERR_ARG, "chunk too large");
     if (!h->cstream) SHQ_CUDA(cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking));
-    if (h->pin_fill && (h->pin_K != a.K || h->pin_fill + a.n > h->pin_cap || h->pin_ends.size() >= h->pin_chunk_cap)) {
-      pin_seal(h);
-      // keep two sealed batches in flight behind the one being processed: process_batch blocks this thread, and only
-      // copies that were issued before it starts can overlap it -- with one batch ahead the copy engine idles whenever a
-      // batch computes for longer than the next one copies
-      while (h->pin_queue.size() >= 3) pin_process_oldest(h);
+    // how far the copies may run ahead of the GPU: one full-size batch plus 1 GiB (so that the copy engine stays busy
+    // while process_batch blocks this thread); the ring holds twice that, a batch never wraps
+    const size_t cap = h->batch_fixed ? h->max_batch_bytes : h->batch_cap_bytes;
+    const size_t ahead = cap + std::min(cap, kArmedBatchBytes);
+    if (h->pin_ring_size < 2 * ahead + a.n || h->pin_ring_size < 4 * a.n) {
+      pin_drain(h);
+      SHQ_CUDA(cudaStreamSynchronize(h->cstream));
+      h->pin_ring_size = std::max(2 * ahead + std::max(a.n, (size_t)64 << 20), 4 * a.n);
+      h->pin_ring.reserve(h->pin_ring_size + 64);
+      h->pin_head = 0;
     }
-    if (h->pin_fill == 0) {      // a new batch: its size is fixed now (the buffer must not move under copies in flight)
-      size_t lim_bytes, lim_chunks;
-      batch_limits(h, &lim_bytes, &lim_chunks);
-      h->pin_cap = std::max(lim_bytes, a.n); h->pin_chunk_cap = lim_chunks;
-      h->pin_buf[h->pin_cur].reserve(h->pin_cap + 64);
-    }
-    // 16-byte alignment of every batch start holds because each batch starts at offset 0 of its buffer
-    SHQ_CUDA(cudaMemcpyAsync(h->pin_buf[h->pin_cur].as<char>() + h->pin_fill, a.text, a.n, cudaMemcpyHostToDevice, h->cstream));
+    while (!pin_make_room(h, a.n)) pin_process_next(h, false);
+    cudaEvent_t ev;
+    if (h->pin_ev_pool.empty()) SHQ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    else { ev = h->pin_ev_pool.back(); h->pin_ev_pool.pop_back(); }
+    SHQ_CUDA(cudaMemcpyAsync(h->pin_ring.as<char>() + h->pin_head, a.text, a.n, cudaMemcpyHostToDevice, h->cstream));
+    SHQ_CUDA(cudaEventRecord(ev, h->cstream));
     h->stats.h2d_bytes += a.n;
-    h->pin_fill += a.n; h->pin_ends.push_back(h->pin_fill); h->pin_K = a.K;
+    h->pin_chunks.push_back({h->pin_head, a.n, a.K, ev});
+    h->pin_head += a.n; h->pin_unproc += a.n;
+    // the GPU takes its next batch when the copies are a full window ahead (fast producer: the batch is what has arrived
+    // by now, so compute and copies balance out) or when a full-size batch has arrived (slow producer)
+    size_t lim_bytes, lim_chunks;
+    batch_limits(h, &lim_bytes, &lim_chunks);
+    if (h->pin_unproc >= ahead) pin_process_next(h, false);
+    else if (h->pin_unproc >= lim_bytes && cudaEventQuery(h->pin_chunks.back().ev) == cudaSuccess) pin_process_next(h, false);
   SHQ_API_END
 }
 
@@ -1823,6 +1857,10 @@ int shq_mg_bin_local(shq_t h, const char* d_text, size_t n, int K, int parity, u
   if (!h || (!d_text && n) || !d_fine_hist || !n_words || parity < 0 || parity > 1) return SHQ_ERR_ARG;
   struct { const char* t; size_t n; int K, par; uint32_t* fh; size_t* nw; } args{d_text, n, K, parity, d_fine_hist, n_words};
   SHQ_API_BEGIN(h)
+    // Bins this rank's text over the WHOLE key space into 2^cb coarse bins inside its exchange buffer and publishes the
+    // layout: meta[b] = first word of coarse bin b, meta[2^cb + b] = one past its last (2^(cb+1) words; the caller
+    // all-gathers them).  One hashing pass into fixed-capacity bins; if a bin overflows (skewed keys) the batch is binned
+    // again with a counting pass and exact offsets -- the owners only ever see (begin, end) pairs.
     flush_stage(h);
     if (!h->mg_send[0]) SHQ_FAIL(SHQ_ERR_STATE, "shq_mg_setup first");
     cudaStream_t st = h->stream;
@@ -1830,12 +1868,10 @@ int shq_mg_bin_local(shq_t h, const char* d_text, size_t n, int K, int parity, u
     *a.nw = 0;
     int shard_bits = 0; while ((1 << shard_bits) < h->nshards) shard_bits++;
     const int cb = kMgCoarseBits > shard_bits ? kMgCoarseBits : shard_bits + 1;
-    const int gfb = shard_bits + kMgFineBits;                 // fine bins over the whole key space
-    const int fb = gfb - cb;
-    const int nfg = 1 << gfb, ncoarse = 1 << cb;
-    const int lbf = h->hb - gfb, lbc = h->hb - cb;
-    if (lbf < 1 || lbc > 31 || fb < 0 || fb > 5) SHQ_FAIL(SHQ_ERR_ARG, "hb=%d does not fit the exchange geometry of %d shards", h->hb, h->nshards);
-    SHQ_CUDA(cudaMemsetAsync(a.fh, 0, (size_t)nfg * 4, st));
+    const int ncoarse = 1 << cb;
+    const int lbc = h->hb - cb;
+    if (lbc < 1 || lbc > 31) SHQ_FAIL(SHQ_ERR_ARG, "hb=%d does not fit the exchange geometry of %d shards", h->hb, h->nshards);
+    SHQ_CUDA(cudaMemsetAsync(a.fh, 0, (size_t)ncoarse * 8, st));
     if (a.n == 0) { SHQ_CUDA(cudaStreamSynchronize(st)); return; }
     if (a.K < 1 || a.K > 1024) SHQ_FAIL(SHQ_ERR_ARG, "K=%d outside [1,1024]", a.K);
     if (a.n >= ((size_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "batch text of %zu bytes exceeds 4 GiB", a.n);
@@ -1849,33 +1885,154 @@ int shq_mg_bin_local(shq_t h, const char* d_text, size_t n, int K, int parity, u
     HashParams hp{};
     hp.text = src; hp.nl_pos = h->d_nl_pos.as<uint32_t>(); hp.n_reads = n_lines / 4; hp.K = a.K;
     hp.hb = h->hb; hp.key_lo = 0; hp.key_hi = 1ULL << h->hb; hp.nchunks = 1;
+    hp.lb = lbc; hp.n_bins = ncoarse;
     h->d_hist.reserve((size_t)(ncoarse + 1) * 4); h->d_binoff.reserve((size_t)(ncoarse + 2) * 4); h->d_tot.reserve((size_t)(ncoarse + 2) * 4);
-    {
-      Phase ph(h, &h->stats.ms_hash_count);
-      hp.lb = lbf; hp.n_bins = nfg;
-      size_t smem_count = sizeof(RollTables) + (size_t)nfg * 4;
-      SHQ_CUDA(cudaFuncSetAttribute(roll_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
-      roll_count_kernel<true><<<kNumSMs * (smem_count > 100000 ? 1 : 2), kRollThreads, smem_count, st>>>(hp, a.fh); L++;
-      coarse_from_fine_kernel<<<cdiv(ncoarse, 256), 256, 0, st>>>(a.fh, ncoarse, fb, h->d_binoff.as<uint32_t>()); L++;
-      exclusive_scan_inplace<SumU32>(h->d_binoff.as<uint32_t>(), ncoarse, h->d_scan_scratch, st, h->d_binoff.as<uint32_t>() + ncoarse, &L);
-      SHQ_CUDA(cudaMemcpyAsync(h->d_tot.p, h->d_binoff.p, (size_t)ncoarse * 4, cudaMemcpyDeviceToDevice, st));
+    h->d_misc.reserve(256);
+    unsigned long long* d_ub = h->d_misc.as<unsigned long long>() + 12;       // [12] window total, [13] words held
+    int* d_ovf = h->d_misc.as<int>() + 20;
+    const size_t smem_scatter = sizeof(RollTables) + ((size_t)3 * ncoarse + 1) * 4 + (size_t)kScatThreads * 16 * 14 + 16;
+    SHQ_CUDA(cudaFuncSetAttribute(roll_scatter_kernel<kScatThreads, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
+    unsigned long long n_keys = 0;
+    bool done = false;
+    if (h->spec_bins) {
+      SHQ_CUDA(cudaMemsetAsync(d_ub, 0, 16, st));
+      SHQ_CUDA(cudaMemsetAsync(d_ovf, 0, 4, st));
+      window_total_kernel<<<kNumSMs * 4, 256, 0, st>>>(hp.nl_pos, hp.n_reads, a.K, d_ub); L++;
+      unsigned long long n_ub = 0; int dev_err = 0;
+      read_pair(h, d_ub, &n_ub, h->d_err, &dev_err);
+      if (dev_err) { SHQ_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(int), st)); SHQ_FAIL(dev_err, "device reported: %s", shq_strerror(dev_err)); }
+      const uint64_t capbin = bin_capacity(h, n_ub / (uint64_t)ncoarse);
+      const uint64_t span = capbin * (uint64_t)ncoarse, round = (uint64_t)kScatThreads * 16;
+      if (n_ub > 0 && span + round + 64 <= h->mg_cap_words) {
+        fixed_bin_offsets_kernel<<<cdiv(ncoarse + 1, 256), 256, 0, st>>>(h->d_binoff.as<uint32_t>(), h->d_tot.as<uint32_t>(), ncoarse, (uint32_t)capbin); L++;
+        {
+          Phase ph(h, &h->stats.ms_scatter);
+          roll_scatter_kernel<kScatThreads, 16, true><<<kNumSMs, kScatThreads, smem_scatter, st>>>(hp, h->d_tot.as<uint32_t>(), h->mg_send[a.par],
+                                                                                               (uint32_t)capbin, (uint32_t)span, d_ovf); L++;
+        }
+        layout_meta_kernel<<<cdiv(ncoarse, 256), 256, 0, st>>>(h->d_binoff.as<uint32_t>(), h->d_tot.as<uint32_t>(), ncoarse, a.fh, d_ub + 1); L++;
+        SHQ_CUDA(cudaGetLastError());
+        int ovf = 0;
+        read_pair(h, d_ub + 1, &n_keys, d_ovf, &ovf);      // also: the buffer is complete once this returns
+        if (!ovf) done = true; else h->stats.bin_fallbacks++;
+      } else if (n_ub == 0) {
+        done = true;
+      }
     }
-    uint32_t n_keys = 0; int dev_err = 0;
-    read_pair(h, h->d_binoff.as<uint32_t>() + ncoarse, &n_keys, h->d_err, &dev_err);
-    if (dev_err) { SHQ_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(int), st)); SHQ_FAIL(dev_err, "device reported: %s", shq_strerror(dev_err)); }
-    if (n_keys > h->mg_cap_words) SHQ_FAIL(SHQ_ERR_CAPACITY, "%u k-mers in one batch, exchange buffers hold %zu", n_keys, h->mg_cap_words);
-    {
-      Phase ph(h, &h->stats.ms_scatter);
-      hp.lb = lbc; hp.n_bins = ncoarse;
-      size_t smem_scatter = sizeof(RollTables) + ((size_t)3 * ncoarse + 1) * 4 + (size_t)kScatThreads * 16 * 14 + 16;
-      SHQ_CUDA(cudaFuncSetAttribute(roll_scatter_kernel<kScatThreads, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
-      roll_scatter_kernel<kScatThreads, 16, true><<<kNumSMs, kScatThreads, smem_scatter, st>>>(hp, h->d_tot.as<uint32_t>(), h->mg_send[a.par]); L++;
+    if (!done) {
+      {
+        Phase ph(h, &h->stats.ms_hash_count);
+        SHQ_CUDA(cudaMemsetAsync(h->d_hist.p, 0, (size_t)(ncoarse + 1) * 4, st));
+        size_t smem_count = sizeof(RollTables) + (size_t)ncoarse * 4;
+        SHQ_CUDA(cudaFuncSetAttribute(roll_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
+        roll_count_kernel<true><<<kNumSMs * 2, kRollThreads, smem_count, st>>>(hp, h->d_hist.as<uint32_t>()); L++;
+        SHQ_CUDA(cudaMemcpyAsync(h->d_binoff.p, h->d_hist.p, (size_t)ncoarse * 4, cudaMemcpyDeviceToDevice, st));
+        exclusive_scan_inplace<SumU32>(h->d_binoff.as<uint32_t>(), ncoarse, h->d_scan_scratch, st, h->d_binoff.as<uint32_t>() + ncoarse, &L);
+        SHQ_CUDA(cudaMemcpyAsync(h->d_tot.p, h->d_binoff.p, (size_t)ncoarse * 4, cudaMemcpyDeviceToDevice, st));
+      }
+      uint32_t nk = 0; int dev_err = 0;
+      read_pair(h, h->d_binoff.as<uint32_t>() + ncoarse, &nk, h->d_err, &dev_err);
+      if (dev_err) { SHQ_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(int), st)); SHQ_FAIL(dev_err, "device reported: %s", shq_strerror(dev_err)); }
+      if (nk > h->mg_cap_words) SHQ_FAIL(SHQ_ERR_CAPACITY, "%u k-mers in one batch, exchange buffers hold %zu", nk, h->mg_cap_words);
+      {
+        Phase ph(h, &h->stats.ms_scatter);
+        roll_scatter_kernel<kScatThreads, 16, true><<<kNumSMs, kScatThreads, smem_scatter, st>>>(hp, h->d_tot.as<uint32_t>(), h->mg_send[a.par]); L++;
+      }
+      SHQ_CUDA(cudaMemsetAsync(d_ub + 1, 0, 8, st));
+      layout_meta_kernel<<<cdiv(ncoarse, 256), 256, 0, st>>>(h->d_binoff.as<uint32_t>(), nullptr, ncoarse, a.fh, d_ub + 1); L++;
+      SHQ_CUDA(cudaGetLastError());
+      SHQ_CUDA(cudaStreamSynchronize(st));
+      n_keys = nk;
     }
-    SHQ_CUDA(cudaGetLastError());
-    SHQ_CUDA(cudaStreamSynchronize(st));
     h->stats.batches++; h->stats.keys_hashed += n_keys;
-    *a.nw = n_keys;
+    h->stats.scatter_launches++; h->stats.scatter_text_bytes += a.n; h->stats.scatter_words += n_keys;
+    *a.nw = (size_t)n_keys;
   SHQ_API_END
+}
+
+// Owner side of the pull exchange: from the all-gathered layouts (row r = shq_mg_bin_local's metadata of rank r, row
+// stride 2^(shard_bits + kMgFineBits) words) pull my coarse bins out of every source's buffer and split them into my
+// kMgFineBits fine bins in one kernel.  The fine bins have a fixed capacity (the total is known, ntHash keys are uniform);
+// exact = true runs a counting pass over the same peer memory first and uses exact offsets instead.
+// Returns the number of words pulled; bb describes the fine bins.
+static uint64_t mg_pull_split(shq_handle_s* h, const uint32_t* d_all_meta, int parity, bool exact, BatchBins* bb) {
+  cudaStream_t st = h->stream;
+  uint64_t& L = h->stats.kernels_launched;
+  const int world = h->nshards;
+  int shard_bits = 0; while ((1 << shard_bits) < world) shard_bits++;
+  const int cb = kMgCoarseBits > shard_bits ? kMgCoarseBits : shard_bits + 1;
+  const int gfb = shard_bits + kMgFineBits, fb = gfb - cb;
+  const int nfg = 1 << gfb, ncoarse = 1 << cb, cps = 1 << (cb - shard_bits), F = 1 << kMgFineBits;
+  const int lbc = h->hb - cb, lbf = lbc - fb;
+  if (lbf < 1 || lbc > 31 || fb < 0 || fb > 5) SHQ_FAIL(SHQ_ERR_ARG, "hb=%d does not fit the exchange geometry of %d shards", h->hb, h->nshards);
+  Phase ph(h, &h->stats.ms_split);
+  h->d_bases.reserve((size_t)world * 8 + 64);
+  std::vector<const uint32_t*> b((size_t)world);
+  for (int r = 0; r < world; r++) b[r] = h->mg_peer[r * 2 + parity];
+  SHQ_CUDA(cudaMemcpyAsync(h->d_bases.p, b.data(), (size_t)world * 8, cudaMemcpyHostToDevice, st));
+  h->d_seg.reserve(((size_t)world * cps * 2 + 8) * 8);
+  uint64_t* seg_beg = h->d_seg.as<uint64_t>(); uint64_t* seg_end = seg_beg + (size_t)world * cps;
+  h->d_misc.reserve(256);
+  unsigned long long* d_tot = h->d_misc.as<unsigned long long>() + 14;
+  int* d_ovf = h->d_misc.as<int>() + 20;
+  SHQ_CUDA(cudaMemsetAsync(d_tot, 0, 8, st));
+  SHQ_CUDA(cudaMemsetAsync(d_ovf, 0, 4, st));
+  pull_layout_kernel<<<cdiv(world * cps, 256), 256, 0, st>>>(d_all_meta, (size_t)nfg, world, h->shard, cps, ncoarse, seg_beg, seg_end, d_tot); L++;
+  const uint64_t n = read_scalar(h, (const uint64_t*)d_tot);
+  bb->n_bins = F; bb->lb = lbf; bb->n_keys = (uint32_t)n; bb->armed = false; bb->nchunks = 1; bb->fine_bits = 0;
+  bb->spec = false; bb->level1_spec = false; bb->span = 0; bb->end = nullptr;
+  if (n == 0) return 0;
+  if (n >= ((uint64_t)1 << 32)) SHQ_FAIL(SHQ_ERR_ARG, "%llu words in one exchange batch", (unsigned long long)n);
+  h->d_fine.reserve(((size_t)F + 2) * 4); h->d_binoff.reserve(((size_t)F + 2) * 4);
+  int parts = 1; while (cps * parts < 4 * kNumSMs) parts *= 2;
+  const uint64_t capfine = bin_capacity(h, n / (uint64_t)F);
+  const uint64_t span = capfine * (uint64_t)F;
+  if (!exact && span + kSplitTile + 64 < ((uint64_t)1 << 32)) {
+    h->d_packed.reserve((size_t)(span + kSplitTile + 64) * 4);
+    fine_bin_offsets_kernel<<<cdiv(F + 1, 256), 256, 0, st>>>(h->d_binoff.as<uint32_t>(), h->d_fine.as<uint32_t>(), (uint32_t)F, (uint32_t)capfine); L++;
+    resplit_kernel<false><<<cps * parts, kSplitThreads, 0, st>>>(h->d_bases.as<const uint32_t*>(), seg_beg, world, cps, parts, lbc, fb,
+                                                               h->d_fine.as<uint32_t>(), h->d_packed.as<uint32_t>(), seg_end, (uint32_t)capfine,
+                                                               (uint32_t)span, d_ovf); L++;
+    bb->spec = true; bb->level1_spec = true; bb->span = (uint32_t)span; bb->end = h->d_fine.as<uint32_t>();
+  } else {
+    SHQ_CUDA(cudaMemsetAsync(h->d_binoff.p, 0, ((size_t)F + 2) * 4, st));
+    resplit_kernel<true><<<cps * parts, kSplitThreads, 0, st>>>(h->d_bases.as<const uint32_t*>(), seg_beg, world, cps, parts, lbc, fb,
+                                                              h->d_binoff.as<uint32_t>(), nullptr, seg_end); L++;
+    exclusive_scan_inplace<SumU32>(h->d_binoff.as<uint32_t>(), F, h->d_scan_scratch, st, h->d_binoff.as<uint32_t>() + F, &L);
+    SHQ_CUDA(cudaMemcpyAsync(h->d_fine.p, h->d_binoff.p, (size_t)F * 4, cudaMemcpyDeviceToDevice, st));
+    h->d_packed.reserve((n + 4) * 4);
+    resplit_kernel<false><<<cps * parts, kSplitThreads, 0, st>>>(h->d_bases.as<const uint32_t*>(), seg_beg, world, cps, parts, lbc, fb,
+                                                               h->d_fine.as<uint32_t>(), h->d_packed.as<uint32_t>(), seg_end); L++;
+  }
+  SHQ_CUDA(cudaGetLastError());
+  bb->words = h->d_packed.as<uint32_t>(); bb->off = h->d_binoff.as<uint32_t>();
+  h->stats.split_launches++; h->stats.split_words += n;
+  return n;
+}
+// Pull + split + aggregate into run A.  The peers' buffers of this parity have been read completely once this returns
+// (aggregate_bins ends with a host round trip): a source may refill its buffer two batches later only because every
+// owner passed this point (and the all-gather in between) before.
+static uint64_t mg_pull_aggregate(shq_handle_s* h, const uint32_t* d_all_meta, int parity, Run* A) {
+  uint64_t n = 0;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    BatchBins bb;
+    n = mg_pull_split(h, d_all_meta, parity, attempt == 1, &bb);
+    if (n == 0) { SHQ_CUDA(cudaStreamSynchronize(h->stream)); return 0; }
+    const int forced = h->fine_bits_forced;
+    if (attempt == 1) h->fine_bits_forced = 0;        // fixed-capacity bins overflowed: exact offsets, bins aggregated as received
+    try {
+      refine_bins(h, &bb, (uint32_t)std::min<uint64_t>(n, (n / (uint64_t)bb.n_bins) * 4 + 65536));
+      h->fine_bits_forced = forced;
+      aggregate_bins(h, bb, 0, 0xFFFFFFFFu, false, 0, A, nullptr, nullptr);
+      break;
+    } catch (const BinOverflow&) {
+      h->fine_bits_forced = forced;
+      h->stats.bin_fallbacks++;
+      if (attempt == 1) SHQ_FAIL(SHQ_ERR_STATE, "binning overflow without fixed-capacity bins");
+    }
+  }
+  if (A->occ != n) SHQ_FAIL(SHQ_ERR_STATE, "exchange batch: %llu words aggregated, %llu expected", (unsigned long long)A->occ, (unsigned long long)n);
+  return n;
 }
 
 int shq_mg_insert_pull(shq_t h, const uint32_t* d_all_fine_hist, int parity) {
@@ -1884,51 +2041,13 @@ int shq_mg_insert_pull(shq_t h, const uint32_t* d_all_fine_hist, int parity) {
   SHQ_API_BEGIN(h)
     flush_stage(h); ensure_state(h);
     if (h->mg_peer.empty()) SHQ_FAIL(SHQ_ERR_STATE, "shq_mg_open_peers first");
-    cudaStream_t st = h->stream;
-    uint64_t& L = h->stats.kernels_launched;
-    const int world = h->nshards;
-    int shard_bits = 0; while ((1 << shard_bits) < world) shard_bits++;
-    const int cb = kMgCoarseBits > shard_bits ? kMgCoarseBits : shard_bits + 1;
-    const int gfb = shard_bits + kMgFineBits, fb = gfb - cb;
-    const int nfg = 1 << gfb, cps = 1 << (cb - shard_bits), F = 1 << kMgFineBits;
-    const int lbc = h->hb - cb, lbf = lbc - fb;
-    uint64_t n = 0;
-    {
-      Phase ph(h, &h->stats.ms_scatter);
-      h->d_bases.reserve((size_t)world * 8 + 64);
-      std::vector<const uint32_t*> b((size_t)world);
-      for (int r = 0; r < world; r++) b[r] = h->mg_peer[r * 2 + a.par];
-      SHQ_CUDA(cudaMemcpyAsync(h->d_bases.p, b.data(), (size_t)world * 8, cudaMemcpyHostToDevice, st));
-      SHQ_CUDA(cudaStreamSynchronize(st));
-      h->d_seg.reserve(((size_t)world * (cps + 1) + 8) * 8);
-      uint64_t* seg_beg = h->d_seg.as<uint64_t>();
-      h->d_fine.reserve(((size_t)F + 2) * 4); h->d_binoff.reserve(((size_t)F + 2) * 4);
-      pull_table_kernel<<<world, kScanThreads, 0, st>>>(a.fh, world, h->shard, cps, fb, nfg, seg_beg, h->d_binoff.as<uint32_t>()); L++;
-      exclusive_scan_inplace<SumU32>(h->d_binoff.as<uint32_t>(), F, h->d_scan_scratch, st, h->d_binoff.as<uint32_t>() + F, &L);
-      SHQ_CUDA(cudaMemcpyAsync(h->d_fine.p, h->d_binoff.p, (size_t)F * 4, cudaMemcpyDeviceToDevice, st));
-      n = read_scalar(h, h->d_binoff.as<uint32_t>() + F);
-      if (n == 0) return;
-      h->d_packed.reserve((n + 4) * 4);
-      int parts = 1; while (cps * parts < 4 * kNumSMs) parts *= 2;
-      resplit_kernel<false><<<cps * parts, kSplitThreads, 0, st>>>(h->d_bases.as<const uint32_t*>(), seg_beg, world, cps, parts, lbc, fb,
-                                                                 h->d_fine.as<uint32_t>(), h->d_packed.as<uint32_t>()); L++;
-      SHQ_CUDA(cudaGetLastError());
-      // the peers' buffers of this parity have been read completely once this returns: a source may refill its buffer
-      // two batches later only because every owner passed this point (and the all-gather in between) before
-      SHQ_CUDA(cudaStreamSynchronize(st));
-    }
-    BatchBins bb;
-    bb.n_bins = F; bb.lb = lbf; bb.n_keys = (uint32_t)n; bb.armed = false; bb.nchunks = 1;
-    bb.words = h->d_packed.as<uint32_t>(); bb.off = h->d_binoff.as<uint32_t>(); bb.end = nullptr;
     Run A{&h->d_run_keys, &h->d_run_counts, &h->d_run_chunk};
-    aggregate_bins(h, bb, 0, 0xFFFFFFFFu, false, 0, &A, nullptr, nullptr);
-    if (A.occ != n) SHQ_FAIL(SHQ_ERR_STATE, "exchange batch: %llu words aggregated, %llu expected", (unsigned long long)A.occ, (unsigned long long)n);
+    if (mg_pull_aggregate(h, a.fh, a.par, &A) == 0) return;
     uint64_t n_new = merge_run(h, A);
     h->ndistinct += n_new; h->nelts += A.occ;
     check_err_flag(h);
   SHQ_API_END
 }
-
 
 // ---- staged exchange batches + sharded deNoise: the building blocks of "the same job at every N" -----------------------
 // While deNoise rounds are pending, a batch may only be committed if the GLOBAL number of distinct keys stays below
@@ -1946,60 +2065,12 @@ int shq_mg_stage_pull(shq_t h, const uint32_t* d_all_fine_hist, int parity, uint
     cudaStream_t st = h->stream;
     uint64_t& L = h->stats.kernels_launched;
     *a.nn = 0; *a.no = 0;
-    const int world = h->nshards;
-    int shard_bits = 0; while ((1 << shard_bits) < world) shard_bits++;
-    const int cb = kMgCoarseBits > shard_bits ? kMgCoarseBits : shard_bits + 1;
-    const int gfb = shard_bits + kMgFineBits, fb = gfb - cb;
-    const int nfg = 1 << gfb, cps = 1 << (cb - shard_bits), F = 1 << kMgFineBits;
-    const int lbc = h->hb - cb, lbf = lbc - fb;
-    uint64_t n = 0;
-    {
-      Phase ph(h, &h->stats.ms_scatter);
-      h->d_bases.reserve((size_t)world * 8 + 64);
-      std::vector<const uint32_t*> b((size_t)world);
-      for (int r = 0; r < world; r++) b[r] = h->mg_peer[r * 2 + a.par];
-      SHQ_CUDA(cudaMemcpyAsync(h->d_bases.p, b.data(), (size_t)world * 8, cudaMemcpyHostToDevice, st));
-      SHQ_CUDA(cudaStreamSynchronize(st));
-      h->d_seg.reserve(((size_t)world * (cps + 1) + 8) * 8);
-      uint64_t* seg_beg = h->d_seg.as<uint64_t>();
-      h->d_fine.reserve(((size_t)F + 2) * 4); h->d_binoff.reserve(((size_t)F + 2) * 4);
-      pull_table_kernel<<<world, kScanThreads, 0, st>>>(a.fh, world, h->shard, cps, fb, nfg, seg_beg, h->d_binoff.as<uint32_t>()); L++;
-      exclusive_scan_inplace<SumU32>(h->d_binoff.as<uint32_t>(), F, h->d_scan_scratch, st, h->d_binoff.as<uint32_t>() + F, &L);
-      SHQ_CUDA(cudaMemcpyAsync(h->d_fine.p, h->d_binoff.p, (size_t)F * 4, cudaMemcpyDeviceToDevice, st));
-      n = read_scalar(h, h->d_binoff.as<uint32_t>() + F);
-      if (n) {
-        h->d_packed.reserve((n + 4) * 4);
-        int parts = 1; while (cps * parts < 4 * kNumSMs) parts *= 2;
-        resplit_kernel<false><<<cps * parts, kSplitThreads, 0, st>>>(h->d_bases.as<const uint32_t*>(), seg_beg, world, cps, parts, lbc, fb,
-                                                                   h->d_fine.as<uint32_t>(), h->d_packed.as<uint32_t>()); L++;
-        SHQ_CUDA(cudaGetLastError());
-      }
-      // the peers' buffers of this parity have been read completely once this returns (see shq_mg_insert_pull)
-      SHQ_CUDA(cudaStreamSynchronize(st));
-    }
+    Run A{&h->d_run_keys, &h->d_run_counts, &h->d_run_chunk};
+    const uint64_t n = mg_pull_aggregate(h, a.fh, a.par, &A);
     h->stats.batches++;
     h->mg_pending = {};
     h->mg_pending.valid = true;
     if (n == 0) return;
-    Run A{&h->d_run_keys, &h->d_run_counts, &h->d_run_chunk};
-    for (int attempt = 0; attempt < 2; attempt++) {
-      BatchBins bb;
-      bb.n_bins = F; bb.lb = lbf; bb.n_keys = (uint32_t)n; bb.armed = false; bb.nchunks = 1;
-      bb.words = h->d_packed.as<uint32_t>(); bb.off = h->d_binoff.as<uint32_t>(); bb.end = nullptr;
-      const int forced = h->fine_bits_forced;
-      if (attempt == 1) h->fine_bits_forced = 0;        // the fixed-capacity fine bins overflowed: aggregate the bins as received
-      try {
-        refine_bins(h, &bb, (uint32_t)std::min<uint64_t>(n, (n / F) * 4 + 65536));
-        h->fine_bits_forced = forced;
-        aggregate_bins(h, bb, 0, 0xFFFFFFFFu, false, 0, &A, nullptr, nullptr);
-        break;
-      } catch (const BinOverflow&) {
-        h->fine_bits_forced = forced;
-        h->stats.bin_fallbacks++;
-        if (attempt == 1) SHQ_FAIL(SHQ_ERR_STATE, "binning overflow without fixed-capacity bins");
-      }
-    }
-    if (A.occ != n) SHQ_FAIL(SHQ_ERR_STATE, "exchange batch: %llu words aggregated, %llu expected", (unsigned long long)A.occ, (unsigned long long)n);
     h->mg_pending.run_n = A.n; h->mg_pending.run_occ = A.occ;
     if (h->n_state == 0) {
       h->mg_pending.n_new = A.n;

@@ -68,6 +68,39 @@ __global__ void __launch_bounds__(kScanThreads) pull_table_kernel(const uint32_t
     fine_tot[f] = t;
   }
 }
+// ---- layout metadata: what a source publishes about its binned array, whatever way it was laid out ----------------
+// meta[b] = first word of GLOBAL coarse bin b inside the source's array, meta[ncoarse + b] = one past its last word.
+// Fixed-capacity bins (one hashing pass): begin = b * capbin, end = the scatter cursor.  Exact bins: begin = prefix, end =
+// next prefix.  *total += words held.
+__global__ void layout_meta_kernel(const uint32_t* __restrict__ bin_off, const uint32_t* __restrict__ bin_end, int ncoarse,
+                                   uint32_t* __restrict__ meta, unsigned long long* __restrict__ total) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t len = 0;
+  if (b < ncoarse) {
+    const uint32_t beg = bin_off[b];
+    uint32_t end = bin_off[b + 1];
+    if (bin_end) { const uint32_t e = bin_end[b]; end = e < end ? e : end; }
+    meta[b] = beg; meta[ncoarse + b] = end; len = end - beg;
+  }
+  for (int d = 16; d; d >>= 1) len += __shfl_down_sync(0xffffffffu, len, d);
+  if ((threadIdx.x & 31) == 0 && len) atomicAdd(total, (unsigned long long)len);
+}
+// Owner side: seg_beg / seg_end[s * cps + c] = range of MY coarse bin c inside source s's array, from the all-gathered
+// metadata (row s = meta of source s, row stride = meta_stride words); *total += words to pull.
+__global__ void pull_layout_kernel(const uint32_t* __restrict__ all_meta, size_t meta_stride, int world, int rank, int cps, int ncoarse,
+                                   uint64_t* __restrict__ seg_beg, uint64_t* __restrict__ seg_end, unsigned long long* __restrict__ total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t len = 0;
+  if (i < world * cps) {
+    const int s = i / cps, c = i % cps;
+    const uint32_t* row = all_meta + (size_t)s * meta_stride;
+    const uint32_t beg = row[rank * cps + c], end = row[ncoarse + rank * cps + c];
+    seg_beg[i] = beg; seg_end[i] = end; len = end - beg;
+  }
+  for (int d = 16; d; d >>= 1) len += __shfl_down_sync(0xffffffffu, len, d);
+  if ((threadIdx.x & 31) == 0 && len) atomicAdd(total, (unsigned long long)len);
+}
+
 // coarse[b] = sum of the 2^fb fine bins of global coarse bin b
 __global__ void coarse_from_fine_kernel(const uint32_t* __restrict__ fine, int ncoarse, int fb, uint32_t* __restrict__ coarse) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -85,9 +118,14 @@ constexpr int kSplitMaxFine = 32;           // fb <= 5
 // grid = cps * parts; CTA (c, part) walks every parts-th tile of the sub-segments of coarse bin c.
 // COUNT: g_fine[c << fb | sub] += occurrences.   !COUNT: g_fine holds running cursors (start = fine bin offset);
 // the tile is counting-sorted by sub in shared memory and written out linearly.
+// seg_end == nullptr: segments are contiguous, seg_beg has cps + 1 entries per source (end = next begin); otherwise
+// seg_beg / seg_end hold cps entries per source (pull_layout_kernel).  capfine > 0: the fine bins have a fixed capacity --
+// a reservation that does not fit raises *ovf and lands in a scratch area at slack_base (one tile long).
 template <bool COUNT>
 __global__ void __launch_bounds__(kSplitThreads) resplit_kernel(const uint32_t* const* __restrict__ bases, const uint64_t* __restrict__ seg_beg, int world, int cps,
-                                                               int parts, int lbc, int fb, uint32_t* __restrict__ g_fine, uint32_t* __restrict__ out) {
+                                                               int parts, int lbc, int fb, uint32_t* __restrict__ g_fine, uint32_t* __restrict__ out,
+                                                               const uint64_t* __restrict__ seg_end = nullptr, uint32_t capfine = 0,
+                                                               uint32_t slack_base = 0, int* __restrict__ ovf = nullptr) {
   __shared__ uint32_t s_cnt[kSplitMaxFine], s_off[kSplitMaxFine + 1], s_delta[kSplitMaxFine];
   __shared__ uint32_t s_sorted[kSplitTile];
   __shared__ uint8_t s_sub[kSplitTile];
@@ -100,7 +138,8 @@ __global__ void __launch_bounds__(kSplitThreads) resplit_kernel(const uint32_t* 
   __syncthreads();
   uint32_t tile_no = 0;
   for (int s = 0; s < world; s++) {
-    const uint64_t beg = seg_beg[(size_t)s * (cps + 1) + c], end = seg_beg[(size_t)s * (cps + 1) + c + 1];
+    const uint64_t beg = seg_end ? seg_beg[(size_t)s * cps + c] : seg_beg[(size_t)s * (cps + 1) + c];
+    const uint64_t end = seg_end ? seg_end[(size_t)s * cps + c] : seg_beg[(size_t)s * (cps + 1) + c + 1];
     const uint32_t* __restrict__ recv = bases[s];      // the receive buffer, or source s's own binned array (peer memory)
     for (uint64_t t0 = beg; t0 < end; t0 += kSplitTile, tile_no++) {
       if ((int)(tile_no % (uint32_t)parts) != part) continue;
@@ -128,8 +167,11 @@ __global__ void __launch_bounds__(kSplitThreads) resplit_kernel(const uint32_t* 
         for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
         if (lane < nfine) {
           const uint32_t o = inc - n;
+          const uint32_t f = ((uint32_t)c << fb) | (uint32_t)lane;
+          uint32_t bs = n ? atomicAdd(&g_fine[f], n) : 0;
+          if (capfine && n && (uint64_t)bs + n > (uint64_t)(f + 1) * capfine) { *ovf = 1; bs = slack_base + o; }
           s_off[lane] = o;
-          s_delta[lane] = (n ? atomicAdd(&g_fine[((size_t)c << fb) | lane], n) : 0) - o;
+          s_delta[lane] = bs - o;
           s_cnt[lane] = 0;
         }
         if (lane == 31) s_off[nfine] = inc;

@@ -218,7 +218,7 @@ class ShardedCounter:
         # (CUDA IPC, one node); "nccl" = one all-to-all of the binned 32-bit words
         self.mode = os.environ.get("SHQ_MG_EXCHANGE", "pull")
         self.parity = 0
-        self.max_batch_bytes = 1 << 30
+        self.max_batch_bytes = 2 << 30
         if self.mode == "pull":
             # every rank must end up in the same mode: if mapping a peer's buffer fails anywhere (no CUDA IPC / no peer
             # access in this environment), all ranks switch to the all-to-all exchange -- same results, more traffic
@@ -487,8 +487,10 @@ class ShardedCounter:
         self.search = ts
         j = 0
         while j < R:
-            # rounds per batch: 32 (256 MiB of text per rank) while the shards are small, up to 128 (1 GiB) as they grow
-            grow = max(1.0, min(4.0, (ts.ndistinct / self.world) / 2.5e7))
+            # rounds per batch: 32 (256 MiB of text per rank) while the shards are small, up to 256 (2 GiB) as they grow --
+            # every batch pays one merge over the whole shard (same rule as batch_target_bytes on one GPU)
+            per_shard = ts.ndistinct / self.world
+            grow = 1.0 if per_shard < 2.5e7 else min(8.0, per_shard / 8.0e6)
             rb = int(32 * grow) if not os.environ.get("SHQ_MG_ROUNDS") else int(os.environ["SHQ_MG_ROUNDS"])
             j1 = min(R, j + rb)
             ts.feed(j * self.world, j1 * self.world)

@@ -263,10 +263,12 @@ def test_pull_exchange_and_shard_image_world1(po, shq):
     cut = text.rfind(b"\n@", 0, half) + 1          # a record boundary ('@' cannot start a quality line here: all 'I')
     for parity, (a, b) in enumerate([(0, cut), (cut, len(t))]):
         nw = g.mg_bin_local(d.data_ptr() + a, b - a, K, parity, hist.data_ptr())
-        assert nw > 0 and int(hist.sum().item()) == nw
+        # published layout: begin / end of each of the 2048 global coarse bins inside the exchange buffer
+        assert nw > 0 and int((hist[2048:4096] - hist[:2048]).sum().item()) == nw
         g.mg_insert_pull(hist.data_ptr(), parity)
     assert g.counts() == o.counts()
     assert g.export() == o.export()
+    assert g.stats()["bin_fallbacks"] == 0          # one hashing pass, fixed-capacity bins on both sides
     # shard image (world 1: no carry, no spill) == the blocks of the exported file
     agg = g.mg_layout_aggregate()
     NEG = -(1 << 60)
@@ -278,6 +280,31 @@ def test_pull_exchange_and_shard_image_world1(po, shq):
     out = torch.empty(nb * 89, dtype=torch.uint8, device="cuda")
     g.copy_device(out.data_ptr(), img, nb * 89)
     assert g.header(*g.counts()) + out.cpu().numpy().tobytes() == o.export()
+    g.close()
+
+
+def test_pull_exchange_skewed_bins_fall_back(po, shq):
+    """The exchange bins in one hashing pass into fixed-capacity bins on the source and on the owner; a read set dominated
+    by one k-mer overflows both and each side redoes its step with exact offsets (counting pass) -- same image."""
+    import torch
+    K, qb = 31, 20
+    base = fastq(po, G=30000, cov=10, err=0.003, seed=93)
+    rep = b"".join(b"@p%d\n%s\n+\n%s\n" % (i, b"A" * 150, b"I" * 150) for i in range(6000))
+    text = base + rep
+    o, _ = po.count_run([text], K, qb, qb + 8, 0, 0, False)
+    t = np.frombuffer(text, np.uint8)
+    d = torch.empty(len(t) + 64, dtype=torch.uint8, device="cuda")
+    d[:len(t)].copy_(torch.from_numpy(t.copy()))
+    torch.cuda.synchronize()
+    g = shq.CQF(qb, qb + 8)
+    g.mg_open_peers(g.mg_setup(2 * len(t)), 1)
+    hist = torch.zeros(4096, dtype=torch.int32, device="cuda")
+    nw = g.mg_bin_local(d.data_ptr(), len(t), K, 0, hist.data_ptr())
+    assert int((hist[2048:4096] - hist[:2048]).sum().item()) == nw
+    g.mg_insert_pull(hist.data_ptr(), 0)
+    assert g.stats()["bin_fallbacks"] >= 2
+    assert g.counts() == o.counts()
+    assert g.export() == o.export()
     g.close()
 
 

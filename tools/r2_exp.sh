@@ -4,8 +4,8 @@ out=gpurun_out
 i=0
 for v in "$@"; do
   i=$((i+1))
-  env $v python bench.py --steps 3 --warmup 2 --cpu-seconds 1 --unitigs 0 --secondary "" --e2e-steps 1 > $out/exp_$i.json 2> $out/exp_$i.err
+  env $v python bench.py --steps 3 --warmup 2 --cpu-seconds 1 --unitigs 0 --secondary "" --e2e-steps ${E2E:-1} > $out/exp_$i.json 2> $out/exp_$i.err
   echo "== $v rc=$?" >> $out/exp.log
-  python tools/show_bench.py $out/exp_$i.json 2>&1 | head -3 >> $out/exp.log
+  python tools/show_bench.py $out/exp_$i.json 2>&1 | head -4 >> $out/exp.log
 done
 cat $out/exp.log

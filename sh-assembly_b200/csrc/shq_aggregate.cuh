@@ -459,10 +459,10 @@ __device__ __forceinline__ size_t merge_path_search(const uint64_t* A, size_t na
 }
 
 __global__ void merge_partition_kernel(const uint64_t* __restrict__ A, size_t na, const uint64_t* __restrict__ B, size_t nb,
-                                       uint64_t* __restrict__ a_split, size_t ntiles) {
+                                       uint64_t* __restrict__ a_split, size_t ntiles, int tile = kMergeTile) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t > ntiles) return;
-  size_t diag = t * kMergeTile;
+  size_t diag = t * (size_t)tile;
   if (diag > na + nb) diag = na + nb;
   a_split[t] = merge_path_search(A, na, B, nb, diag);
 }
@@ -547,7 +547,11 @@ __global__ void __launch_bounds__(kMergeThreads) merge_tiles_kernel(
 // HIST: B carries the first chunk of every key (Bchunk); chunk_hist[c] += keys of B that are NOT in A ("new" keys) whose
 // first chunk is c -- the by-product that lets the host find the deNoise boundary chunk of an armed batch.
 constexpr unsigned long long kLbValue = (1ULL << 62) - 1;
-constexpr size_t kMergeLbSmem = (size_t)(2 * (kMergeTile + 2)) * 8 + (size_t)(2 * (kMergeTile + 2)) * 4;
+constexpr int kLbItems = 12;                         // merged elements per thread
+constexpr int kLbTile = kMergeThreads * kLbItems;    // ... and per tile: the per-tile costs (merge-path search, block scan, look-back) are paid half as often as with 6
+// one array of keys and one of counts: the tile's A part (with the key before it) followed by its B part (with the key
+// after it) -- la + lbn = tile, so both inputs fit whatever the split
+constexpr size_t kMergeLbSmem = (size_t)(kLbTile + 2) * 8 + (size_t)(kLbTile + 2) * 4;
 template <bool HIST>
 __global__ void __launch_bounds__(kMergeThreads) merge_tiles_lookback_kernel(
     const uint64_t* __restrict__ A, const uint32_t* __restrict__ Ac, size_t na, const uint64_t* __restrict__ B,
@@ -556,10 +560,8 @@ __global__ void __launch_bounds__(kMergeThreads) merge_tiles_lookback_kernel(
     uint32_t* __restrict__ out_counts, unsigned long long* __restrict__ n_out_total, int* __restrict__ err,
     const uint16_t* __restrict__ Bchunk = nullptr, uint32_t* __restrict__ chunk_hist = nullptr) {
   extern __shared__ __align__(16) unsigned char merge_smem[];
-  uint64_t* s_a = reinterpret_cast<uint64_t*>(merge_smem);          // kMergeTile + 2 keys of A (s_a[0] = the key before the tile)
-  uint64_t* s_b = s_a + kMergeTile + 2;                             // kMergeTile + 2 keys of B (one key past the tile at the end)
-  uint32_t* s_ac = reinterpret_cast<uint32_t*>(s_b + kMergeTile + 2);
-  uint32_t* s_bc = s_ac + kMergeTile + 2;
+  uint64_t* s_k = reinterpret_cast<uint64_t*>(merge_smem);
+  uint32_t* s_c = reinterpret_cast<uint32_t*>(s_k + kLbTile + 2);
   __shared__ unsigned int s_tile;
   __shared__ unsigned long long s_prefix;
   __shared__ uint32_t s_hist[HIST ? kMergeHistMax : 1];
@@ -567,7 +569,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_tiles_lookback_kernel(
   if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
   __syncthreads();
   const size_t t = s_tile;
-  size_t diag0 = t * kMergeTile, diag1 = diag0 + kMergeTile;
+  size_t diag0 = t * kLbTile, diag1 = diag0 + kLbTile;
   if (diag1 > na + nb) diag1 = na + nb;
   const size_t a0 = a_split[t], a1 = a_split[t + 1];
   const size_t b0 = diag0 - a0, b1 = diag1 - a1;
@@ -575,33 +577,39 @@ __global__ void __launch_bounds__(kMergeThreads) merge_tiles_lookback_kernel(
   const uint64_t kNone = ~0ULL;
   const int total = la + lbn;
   {
-    // staging: la + 1 keys of A (from a0 - 1) followed by lbn + 1 keys of B, and the matching counts (one count past
-    // the tile's B range: an A key at the very end of the tile may match B[b1]).  Fixed trip count, loads first and
-    // shared-memory stores after, so that all of a thread's loads are in flight together.
-    constexpr int kLd = kMergeItems + 1;           // (total + 2) / kMergeThreads rounded up
-    uint64_t vk[kLd]; uint32_t vc[kLd];
+    // staging: s_k[0] = A[a0 - 1] (or none), s_k[1 .. la] = the tile's A keys, s_k[la + 1 .. la + lbn] = its B keys,
+    // s_k[la + 1 + lbn] = B[b1] (or none: an A key at the very end of the tile may match it); counts alike.  Fixed trip
+    // count, loads first and shared-memory stores after, so that all loads of a half are in flight together.
+    constexpr int kHalf = (kLbItems + 2) / 2;      // 2 x 7 rounds of 256 entries >= tile + 2
 #pragma unroll
-    for (int j = 0; j < kLd; j++) {
-      const int i = threadIdx.x + j * kMergeThreads;
-      uint64_t k = kNone; uint32_t c = 0;
-      if (i <= la) {
-        if (i > 0) { k = A[a0 + i - 1]; c = Ac[a0 + i - 1]; }
-        else if (a0 > 0) k = A[a0 - 1];
-      } else if (i < total + 2) {
-        const size_t bj = b0 + (size_t)(i - la - 1);
-        if (bj < nb) { k = B[bj]; c = Bc[bj]; }
+    for (int half = 0; half < 2; half++) {
+      uint64_t vk[kHalf]; uint32_t vc[kHalf];
+#pragma unroll
+      for (int j = 0; j < kHalf; j++) {
+        const int i = threadIdx.x + (half * kHalf + j) * kMergeThreads;
+        uint64_t k = kNone; uint32_t c = 0;
+        if (i <= la) {
+          if (i > 0) { k = A[a0 + i - 1]; c = Ac[a0 + i - 1]; }
+          else if (a0 > 0) k = A[a0 - 1];
+        } else if (i < total + 2) {
+          const size_t bj = b0 + (size_t)(i - la - 1);
+          if (bj < nb) { k = B[bj]; c = Bc[bj]; }
+        }
+        vk[j] = k; vc[j] = c;
       }
-      vk[j] = k; vc[j] = c;
-    }
 #pragma unroll
-    for (int j = 0; j < kLd; j++) {
-      const int i = threadIdx.x + j * kMergeThreads;
-      if (i <= la) { s_a[i] = vk[j]; if (i > 0) s_ac[i - 1] = vc[j]; }
-      else if (i < total + 2) { s_b[i - la - 1] = vk[j]; s_bc[i - la - 1] = vc[j]; }
+      for (int j = 0; j < kHalf; j++) {
+        const int i = threadIdx.x + (half * kHalf + j) * kMergeThreads;
+        if (i < total + 2) { s_k[i] = vk[j]; s_c[i] = vc[j]; }
+      }
     }
   }
   __syncthreads();
-  int d0 = min(threadIdx.x * kMergeItems, total), d1 = min(d0 + kMergeItems, total);
+  const uint64_t* s_a = s_k;                 // s_a[1 + ai] = A key ai of the tile, s_a[0] = the key before the tile
+  const uint64_t* s_b = s_k + la + 1;        // s_b[bi] = B key bi, s_b[lbn] = one key past the tile
+  const uint32_t* s_ac = s_c + 1;
+  const uint32_t* s_bc = s_c + la + 1;
+  int d0 = min(threadIdx.x * kLbItems, total), d1 = min(d0 + kLbItems, total);
   int lo = max(0, d0 - lbn), hi = min(d0, la);
   while (lo < hi) {
     int mid = (lo + hi) >> 1;
@@ -609,7 +617,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_tiles_lookback_kernel(
   }
   int ai = lo, bi = d0 - lo;
   uint32_t nheads = 0;
-  uint64_t okey[kMergeItems]; uint32_t ocnt[kMergeItems];
+  uint64_t okey[kLbItems]; uint32_t ocnt[kLbItems];
   for (int d = d0; d < d1; d++) {
     bool takeA = (bi >= lbn) || (ai < la && s_a[1 + ai] <= s_b[bi]);
     if (takeA) {
@@ -634,7 +642,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_tiles_lookback_kernel(
   uint32_t rank = block_exclusive_scan<SumU32>(nheads, &tot);      // ends with a barrier: every thread is done with s_a / s_b, s_hist is complete
   if (HIST) for (int i = threadIdx.x; i < kMergeHistMax; i += blockDim.x) { const uint32_t v = s_hist[i]; if (v) atomicAdd(&chunk_hist[i], v); }
   // the merged tile, assembled in place of the inputs
-  uint64_t* s_ok = s_a; uint32_t* s_oc = s_ac;
+  uint64_t* s_ok = s_k; uint32_t* s_oc = s_c;
   for (uint32_t i = 0; i < nheads; i++) { s_ok[rank + i] = okey[i]; s_oc[rank + i] = ocnt[i]; }
   if (threadIdx.x < 32) {               // warp 0: publish, then look back 32 predecessors at a time
     const int lane = threadIdx.x;

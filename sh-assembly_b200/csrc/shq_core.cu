@@ -226,13 +226,20 @@ struct BinOverflow {};          // a fixed-capacity bin overflowed: redo the bat
 struct Run { DevBuf* keys; DevBuf* counts; DevBuf* chunk; size_t n = 0; uint64_t occ = 0; };
 
 int pick_bin_bits(shq_handle_s* h, uint64_t est_keys, int chunk_bits_needed) {
-  // aim at ~64K occurrences per bin (8 per bin and scatter round) AND at most ~4500 distinct keys per bin (what the
-  // aggregator's table is sized for; with no batch seen yet every occurrence may be distinct), 2^8 .. 2^12 bins, and
-  // (key bits below the bin) + chunk bits <= 32.  More bins than 2^12 come from the second binning level.
+  // The hashing pass is the faster the fewer bins it scatters into (per round of 12 288 keys it pays one reservation and
+  // three shared-memory words per bin: 83 -> 66 ms per step from 4096 to 2048 bins on configs[2]); the aggregator wants at
+  // most ~3000 distinct keys per bin, which the second binning level provides (up to 128 fine bins per coarse bin).  So:
+  // the fewest coarse bins (2^10 .. 2^12) that need no second level, and if one is needed anyway, the fewest that let it
+  // reach the target.  Distinct keys are estimated with the ratio of the previous batch (+30 %).
+  // The chunk id of an armed batch shares the 32-bit word with the key bits below the bin: that may ask for more bins.
   int shard_bits = 0; while ((1 << shard_bits) < h->nshards) shard_bits++;
   int local_bits = h->hb - shard_bits;
-  int pb = 8;
-  while (pb < 12 && (est_keys >> pb) > 16384) pb++;
+  const double est_d = (double)est_keys * (h->ratio_seen ? std::min(1.0, h->distinct_ratio * 1.3) : 1.0);
+  int pb = -1;
+  if (!h->ratio_seen) pb = 12;          // first batch of a job: nothing known, as many bins as the hashing pass takes
+  for (int b = 10; b <= 12 && pb < 0; b++) if (est_d / (double)(1 << b) <= h->fine_target) pb = b;
+  if (pb < 0) { pb = 10; while (pb < 12 && est_d / (double)((uint64_t)1 << (pb + 7)) > 3000.0) pb++; }
+  while (pb > 8 && (est_keys >> pb) < 2048) pb--;          // small batches: at least ~2000 words per bin
   if (h->bin_bits) pb = h->bin_bits;
   if (pb > local_bits) pb = local_bits;
   // the low key bits share a 32-bit word with the chunk id, and 0xFFFFFFFF is the aggregator's empty marker
@@ -376,8 +383,8 @@ void refine_bins(shq_handle_s* h, BatchBins* bb, uint32_t max_bin_words) {
   const double ratio = bb->ratio >= 0 ? std::min(1.0, bb->ratio * 1.1) : 1.0;
   const double est_d = (double)n_ub / (double)n_bins * ratio;
   int fb = 0;
-  while (fb < 5 && lb - fb > 1 && est_d / (double)(1 << fb) > h->fine_target) fb++;      // load factor of the aggregator's table <= ~0.45
-  if (h->fine_bits_forced >= 0) fb = std::min(h->fine_bits_forced, std::min(5, lb - 1));
+  while (fb < 7 && lb - fb > 1 && est_d / (double)(1 << fb) > h->fine_target) fb++;      // load factor of the aggregator's table <= ~0.45
+  if (h->fine_bits_forced >= 0) fb = std::min(h->fine_bits_forced, std::min(7, lb - 1));
   const uint64_t n_fine = (uint64_t)n_bins << fb;
   const uint64_t capfine = bin_capacity(h, n_ub / n_fine);
   const uint64_t span2 = capfine * n_fine;
@@ -648,7 +655,9 @@ uint64_t merge_shadow(shq_handle_s* h, const Run& R, int nchunks, std::vector<ui
   const uint16_t* Bch = (chunk_hist_host && R.chunk) ? R.chunk->as<uint16_t>() : nullptr;
   if (chunk_hist_host && !Bch) SHQ_FAIL(SHQ_ERR_STATE, "merge: first chunks requested from a run without them");
   if (chunk_hist_host && nchunks > kMergeHistMax) SHQ_FAIL(SHQ_ERR_ARG, "too many chunks in one batch (max %d)", kMergeHistMax);
-  const size_t ntiles = (total + kMergeTile - 1) / kMergeTile;
+  const bool lookback = h->merge_lookback && total < ((uint64_t)1 << 32);
+  const int tile = (lookback && !h->merge_tma) ? kLbTile : kMergeTile;
+  const size_t ntiles = (total + tile - 1) / tile;
   h->d_split.reserve((ntiles + 2) * 8);
   h->d_heads.reserve((ntiles + 2) * 4);
   h->d_heads64.reserve((ntiles + 4) * 8);
@@ -660,9 +669,9 @@ uint64_t merge_shadow(shq_handle_s* h, const Run& R, int nchunks, std::vector<ui
     d_hist = h->d_chunk_hist.as<uint32_t>();
     SHQ_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)kMergeHistMax * 4, st));
   }
-  merge_partition_kernel<<<cdiv(ntiles + 1, 128), 128, 0, st>>>(A, na, Bk, nb, h->d_split.as<uint64_t>(), ntiles); L++;
+  merge_partition_kernel<<<cdiv(ntiles + 1, 128), 128, 0, st>>>(A, na, Bk, nb, h->d_split.as<uint64_t>(), ntiles, tile); L++;
   uint64_t n_out = 0;
-  if (h->merge_lookback && total < ((uint64_t)1 << 32)) {
+  if (lookback) {
     // single pass: the output can hold na + nb entries at most; the real size comes back with the last tile
     unsigned long long* status = h->d_heads64.as<unsigned long long>();
     unsigned long long* d_nout = status + ntiles; unsigned int* ticket = (unsigned int*)(status + ntiles + 1);

@@ -113,7 +113,7 @@ __global__ void coarse_from_fine_kernel(const uint32_t* __restrict__ fine, int n
 constexpr int kSplitThreads = 256;
 constexpr int kSplitItems = 16;
 constexpr int kSplitTile = kSplitThreads * kSplitItems;
-constexpr int kSplitMaxFine = 32;           // fb <= 5
+constexpr int kSplitMaxFine = 128;          // fb <= 7 on one GPU (split_bins_kernel); the exchange's resplit_kernel uses fb <= 5
 
 // grid = cps * parts; CTA (c, part) walks every parts-th tile of the sub-segments of coarse bin c.
 // COUNT: g_fine[c << fb | sub] += occurrences.   !COUNT: g_fine holds running cursors (start = fine bin offset);
@@ -238,21 +238,26 @@ __global__ void __launch_bounds__(kSplitThreads) split_bins_kernel(const uint32_
       sr[i] = idx < end ? ((sub << 16) | atomicAdd(&s_cnt[sub], 1u)) : 0xFFFFFFFFu;
     }
     __syncthreads();
-    if (threadIdx.x < 32) {  // nfine <= 32: lane j owns fine bin j -- one global reservation each, offsets by a warp scan
-      const uint32_t n = lane < nfine ? s_cnt[lane] : 0;
-      uint32_t inc = n;
+    if (threadIdx.x < 32) {  // nfine <= 128: lane j owns fine bins j, j + 32, ... -- one global reservation per bin, offsets by warp scans
+      uint32_t carry = 0;
+      for (int q0 = 0; q0 < nfine; q0 += 32) {          // one pass for fb <= 5
+        const int b = q0 + lane;
+        const uint32_t n = b < nfine ? s_cnt[b] : 0;
+        const uint32_t f = ((uint32_t)c << fb) | (uint32_t)b;
+        uint32_t bs = n ? atomicAdd(&fine_cursor[f], n) : 0;      // in flight while the scan runs
+        uint32_t inc = n;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
-      if (lane < nfine) {
-        const uint32_t o = inc - n;
-        const uint32_t f = ((uint32_t)c << fb) | (uint32_t)lane;
-        uint32_t bs = n ? atomicAdd(&fine_cursor[f], n) : 0;
-        if (n && (uint64_t)bs + n > (uint64_t)(f + 1) * capfine) { *ovf = 1; bs = slack_base + o; }
-        s_off[lane] = o;
-        s_delta[lane] = bs - o;
-        s_cnt[lane] = 0;
+        for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+        const uint32_t o = carry + inc - n;
+        if (b < nfine) {
+          if (n && (uint64_t)bs + n > (uint64_t)(f + 1) * capfine) { *ovf = 1; bs = slack_base + o; }
+          s_off[b] = o;
+          s_delta[b] = bs - o;
+          s_cnt[b] = 0;
+        }
+        carry += __shfl_sync(0xffffffffu, inc, 31);
       }
-      if (lane == 31) s_off[nfine] = inc;
+      if (lane == 0) s_off[nfine] = carry;
     }
     __syncthreads();
     const uint32_t total = s_off[nfine];

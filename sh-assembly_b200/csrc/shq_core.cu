@@ -1145,7 +1145,7 @@ int guard(shq_handle_s* h, void (*fn)(shq_handle_s*, void*), void* arg) {
 
 void init_handle(shq_handle_s* h, int qb, int hb, uint32_t seed, int device, int shard, int nshards) {
   if (qb < 1 || qb > 40 || hb - qb != 8) SHQ_FAIL(SHQ_ERR_ARG, "need 1 <= qb <= 40 and hb - qb == 8 (got qb=%d hb=%d)", qb, hb);
-  if (nshards < 1 || (nshards & (nshards - 1)) || shard < 0 || shard >= nshards || (1 << qb) < nshards * 64)
+  if (nshards < 1 || (nshards & (nshards - 1)) || shard < 0 || shard >= nshards || (1ULL << qb) < (unsigned long long)nshards * 64)
     SHQ_FAIL(SHQ_ERR_ARG, "bad shard %d of %d", shard, nshards);
   if (const char* e = getenv("SHQ_MAX_BATCH_MB")) { long v = atol(e); if (v >= 1 && v <= 3072) { h->max_batch_bytes = (size_t)v << 20; h->batch_fixed = true; } }
   if (const char* e = getenv("SHQ_BATCH_CAP_MB")) { long v = atol(e); if (v >= 64 && v <= 3072) h->batch_cap_bytes = (size_t)v << 20; }
@@ -1970,10 +1970,11 @@ static uint64_t mg_pull_split(shq_handle_s* h, const uint32_t* d_all_meta, int p
   const int world = h->nshards;
   int shard_bits = 0; while ((1 << shard_bits) < world) shard_bits++;
   const int cb = kMgCoarseBits > shard_bits ? kMgCoarseBits : shard_bits + 1;
-  const int gfb = shard_bits + kMgFineBits, fb = gfb - cb;
-  const int nfg = 1 << gfb, ncoarse = 1 << cb, cps = 1 << (cb - shard_bits), F = 1 << kMgFineBits;
-  const int lbc = h->hb - cb, lbf = lbc - fb;
-  if (lbf < 1 || lbc > 31 || fb < 0 || fb > 5) SHQ_FAIL(SHQ_ERR_ARG, "hb=%d does not fit the exchange geometry of %d shards", h->hb, h->nshards);
+  const int gfb = shard_bits + kMgFineBits;
+  const int nfg = 1 << gfb, ncoarse = 1 << cb, cps = 1 << (cb - shard_bits);
+  const int lbc = h->hb - cb;
+  int fb = gfb - cb;                           // kMgFineBits fine bins per shard ...
+  if (lbc - fb < 1 || lbc > 31 || fb < 0 || fb > 5) SHQ_FAIL(SHQ_ERR_ARG, "hb=%d does not fit the exchange geometry of %d shards", h->hb, h->nshards);
   Phase ph(h, &h->stats.ms_split);
   h->d_bases.reserve((size_t)world * 8 + 64);
   std::vector<const uint32_t*> b((size_t)world);
@@ -1988,6 +1989,12 @@ static uint64_t mg_pull_split(shq_handle_s* h, const uint32_t* d_all_meta, int p
   SHQ_CUDA(cudaMemsetAsync(d_ovf, 0, 4, st));
   pull_layout_kernel<<<cdiv(world * cps, 256), 256, 0, st>>>(d_all_meta, (size_t)nfg, world, h->shard, cps, ncoarse, seg_beg, seg_end, d_tot); L++;
   const uint64_t n = read_scalar(h, (const uint64_t*)d_tot);
+  // ... or more, when the distinct ratio of the previous batch says that 4096 bins would each hold more keys than the
+  // aggregator's table takes: the pull then splits all the way (up to 128 fine bins per coarse bin) and the second
+  // split pass over the received words is not needed
+  if (h->ratio_seen && h->fine_bits_forced < 0)
+    while (fb < 7 && lbc - fb > 2 && (double)n * std::min(1.0, h->distinct_ratio * 1.3) / (double)((uint64_t)cps << fb) > 3000.0) fb++;
+  const int F = cps << fb, lbf = lbc - fb;
   bb->n_bins = F; bb->lb = lbf; bb->n_keys = (uint32_t)n; bb->armed = false; bb->nchunks = 1; bb->fine_bits = 0;
   bb->spec = false; bb->level1_spec = false; bb->span = 0; bb->end = nullptr;
   if (n == 0) return 0;

@@ -160,21 +160,26 @@ __global__ void __launch_bounds__(kSplitThreads) resplit_kernel(const uint32_t* 
       }
       if (COUNT) continue;     // counts accumulate over all tiles of this CTA (one barrier at the end)
       __syncthreads();
-      if (threadIdx.x < 32) {  // nfine <= 32: lane j owns fine bin j -- one global reservation each, offsets by a warp scan
-        const uint32_t n = lane < nfine ? s_cnt[lane] : 0;
-        uint32_t inc = n;
+      if (threadIdx.x < 32) {  // nfine <= 128: lane j owns fine bins j, j + 32, ... -- one global reservation per bin, offsets by warp scans
+        uint32_t carry = 0;
+        for (int q0 = 0; q0 < nfine; q0 += 32) {          // one pass for fb <= 5
+          const int b = q0 + lane;
+          const uint32_t n = b < nfine ? s_cnt[b] : 0;
+          const uint32_t f = ((uint32_t)c << fb) | (uint32_t)b;
+          uint32_t bs = n ? atomicAdd(&g_fine[f], n) : 0;      // in flight while the scan runs
+          uint32_t inc = n;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
-        if (lane < nfine) {
-          const uint32_t o = inc - n;
-          const uint32_t f = ((uint32_t)c << fb) | (uint32_t)lane;
-          uint32_t bs = n ? atomicAdd(&g_fine[f], n) : 0;
-          if (capfine && n && (uint64_t)bs + n > (uint64_t)(f + 1) * capfine) { *ovf = 1; bs = slack_base + o; }
-          s_off[lane] = o;
-          s_delta[lane] = bs - o;
-          s_cnt[lane] = 0;
+          for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+          const uint32_t o = carry + inc - n;
+          if (b < nfine) {
+            if (capfine && n && (uint64_t)bs + n > (uint64_t)(f + 1) * capfine) { *ovf = 1; bs = slack_base + o; }
+            s_off[b] = o;
+            s_delta[b] = bs - o;
+            s_cnt[b] = 0;
+          }
+          carry += __shfl_sync(0xffffffffu, inc, 31);
         }
-        if (lane == 31) s_off[nfine] = inc;
+        if (lane == 0) s_off[nfine] = carry;
       }
       __syncthreads();
       const uint32_t total = s_off[nfine];
@@ -194,7 +199,7 @@ __global__ void __launch_bounds__(kSplitThreads) resplit_kernel(const uint32_t* 
   }
   if (COUNT) {
     __syncthreads();
-    if (threadIdx.x < nfine) { uint32_t v = s_cnt[threadIdx.x]; if (v) atomicAdd(&g_fine[((size_t)c << fb) | threadIdx.x], v); }
+    if (threadIdx.x < nfine) { uint32_t v = s_cnt[threadIdx.x]; if (v) atomicAdd(&g_fine[((size_t)c << fb) | threadIdx.x], v); }      // nfine <= 128 < kSplitThreads
   }
 }
 

@@ -216,6 +216,14 @@ def test_wide_batches_match_oracle(po, shq, wide, path, monkeypatch):
     g.close()
 
 
+def test_shard_handles_of_large_filters(shq):
+    """configs[2] scaled to 4 and 8 ranks is a qb = 31 / 32 filter: the shard geometry must not go through 32-bit shifts."""
+    for qb, n in [(31, 4), (32, 8), (34, 8)]:
+        g = shq.CQF(qb, qb + 8, shard=n - 1, nshards=n)
+        assert g.nblocks > (1 << (qb - 6))
+        g.close()
+
+
 def _mg_text(po):
     return fastq(po, G=80000, cov=30, err=0.004, n_rate=0.0003, seed=77)
 

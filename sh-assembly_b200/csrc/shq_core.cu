@@ -1993,7 +1993,7 @@ static uint64_t mg_pull_split(shq_handle_s* h, const uint32_t* d_all_meta, int p
   // aggregator's table takes: the pull then splits all the way (up to 128 fine bins per coarse bin) and the second
   // split pass over the received words is not needed
   if (h->ratio_seen && h->fine_bits_forced < 0)
-    while (fb < 7 && lbc - fb > 2 && (double)n * std::min(1.0, h->distinct_ratio * 1.3) / (double)((uint64_t)cps << fb) > 3000.0) fb++;
+    while (fb < 7 && lbc - fb > 2 && (double)n * std::min(1.0, h->distinct_ratio * 1.1) / (double)((uint64_t)cps << fb) > h->fine_target) fb++;   // refine_bins' rule
   const int F = cps << fb, lbf = lbc - fb;
   bb->n_bins = F; bb->lb = lbf; bb->n_keys = (uint32_t)n; bb->armed = false; bb->nchunks = 1; bb->fine_bits = 0;
   bb->spec = false; bb->level1_spec = false; bb->span = 0; bb->end = nullptr;

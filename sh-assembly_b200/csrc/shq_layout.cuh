@@ -188,6 +188,24 @@ __device__ __forceinline__ size_t warp_first_false(size_t lo, size_t hi, int lan
   }
   return lo;
 }
+// The same when the answer is expected close to `guess` (within `radius`): the chain walk knows where it is going -- the
+// next range ends 2^20 slots ahead and the entries are spread evenly over the slots (ntHash), the next range starts
+// right behind the last one's end -- so most searches need 1-4 dependent loads instead of log32(n) = 6.
+template <class Pred>
+__device__ __forceinline__ size_t warp_first_false_near(size_t lo, size_t hi, size_t guess, size_t radius, int lane, Pred&& pred) {
+  if (hi - lo <= 2 * radius) return warp_first_false(lo, hi, lane, pred);
+  size_t wlo = guess > lo + radius ? guess - radius : lo;
+  if (wlo > hi - 2 * radius) wlo = hi - 2 * radius;
+  const size_t whi = wlo + 2 * radius;
+  // the answer lies in [wlo, whi] iff the predicate holds just below wlo and fails at whi
+  bool ok = true;
+  if (lane == 0) ok = wlo == lo || pred(wlo - 1);
+  if (lane == 1) ok = whi == hi || !pred(whi);
+  const uint32_t bad = __ballot_sync(0xffffffffu, !ok);
+  if (bad == 0) return warp_first_false(wlo, whi, lane, pred);
+  if (bad & 1u) return warp_first_false(lo, wlo, lane, pred);       // already false below the window
+  return warp_first_false(whi, hi, lane, pred);
+}
 __global__ void __launch_bounds__(32) denoise_ranges_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts,
                                       const uint64_t* __restrict__ pos, size_t n, uint64_t nslots, uint64_t xnslots,
                                       uint32_t* __restrict__ keep_idx, uint32_t* __restrict__ n_keep, uint32_t keep_cap) {
@@ -197,11 +215,19 @@ __global__ void __launch_bounds__(32) denoise_ranges_kernel(const uint64_t* __re
   uint32_t nk = 0;
   if (n == 0) { if (lane == 0) *n_keep = 0; return; }
   uint64_t cur = keys[0] >> 8;  // find_first_nonempty_slot(qf, 0)
+  size_t at = 0;                // first entry whose quotient is >= cur
+  const double density = (double)n / (double)(pos[n - 1] - pos[0] + 1);
   while (cur < nslots) {
     uint64_t start = cur;
     uint64_t e0 = (start + min_len) > nslots ? nslots : (start + min_len);
-    // lo = number of entries with pos <= e0
-    size_t lo = warp_first_false(0, n, lane, [&](size_t i) { return pos[i] <= e0; });
+    // lo = number of entries with pos <= e0: an entry takes at least one slot, so it is at most e0 - start + 1 entries past
+    // the range's first entry (at) and, the entries being spread evenly, close to the interpolated index
+    size_t lo;
+    {
+      const size_t hi = (size_t)std::min<uint64_t>((uint64_t)n, (uint64_t)at + (e0 - start) + 2);
+      const size_t guess = at + (size_t)((double)(e0 - start) * density);
+      lo = warp_first_false_near(at, hi, guess, 4096, lane, [&](size_t i) { return pos[i] <= e0; });
+    }
     uint64_t end;
     size_t last = (size_t)-1;   // entry holding slot `end`, if any
     uint64_t prev_end = lo > 0 ? entry_end(keys, counts, pos, lo - 1) : 0;
@@ -229,9 +255,11 @@ __global__ void __launch_bounds__(32) denoise_ranges_kernel(const uint64_t* __re
         nk++;
       }
     }
-    // find_first_nonempty_slot(end + 1): next occupied quotient >= end+1
-    size_t nx = warp_first_false(0, n, lane, [&](size_t i) { return (keys[i] >> 8) < end + 1; });
+    // find_first_nonempty_slot(end + 1): next occupied quotient >= end+1 -- an entry or two past the one holding `end`
+    const size_t from = last != (size_t)-1 ? last : (lo > 0 ? lo - 1 : 0);
+    size_t nx = warp_first_false_near(from, n, from, 16, lane, [&](size_t i) { return (keys[i] >> 8) < end + 1; });
     cur = nx < n ? (keys[nx] >> 8) : xnslots;
+    at = nx;
   }
   if (lane == 0) *n_keep = nk;
 }
@@ -287,17 +315,24 @@ __global__ void __launch_bounds__(32) denoise_walk_kernel(const uint64_t* __rest
     else S.protect_mask |= 1ULL << L.owner;
   };
   size_t i = 0;
+  const double density = n > 1 ? (double)n / (double)(pos[n - 1] - pos[0] + 1) : 1.0;
   while (i < n || false) {
     if (S.phase == 0) {
       const unsigned long long need = S.need_q;
-      const size_t j = warp_first_false(i, n, lane, [&](size_t x) { return (keys[x] >> 8) < need; });
+      const size_t j = warp_first_false_near(i, n, i, 16, lane, [&](size_t x) { return (keys[x] >> 8) < need; });
       if (j == n) { i = n; break; }
       S.start = keys[j] >> 8;
       S.e0 = S.start + min_len > S.nslots ? S.nslots : S.start + min_len;
       S.phase = 1; i = j;
     } else if (S.phase == 1) {
       const unsigned long long e0 = S.e0;
-      const size_t lo = warp_first_false(i, n, lane, [&](size_t x) { return pos[x] <= e0; });
+      size_t lo;
+      {   // an entry takes at least one slot; the entries are spread evenly over the slots
+        const uint64_t pi = pos[i];
+        const size_t hi = pi <= e0 ? (size_t)std::min<uint64_t>((uint64_t)n, (uint64_t)i + (e0 - pi) + 2) : i + 1;
+        const size_t guess = pi <= e0 ? i + (size_t)((double)(e0 - pi) * density) : i;
+        lo = warp_first_false_near(i, hi > n ? n : hi, guess, 4096, lane, [&](size_t x) { return pos[x] <= e0; });
+      }
       if (lo == n) { i = n; break; }
       WalkEntry P;
       bool have = true;

@@ -394,8 +394,18 @@ class ShardedCounter:
             self.dist.all_gather(parts, hist.cpu())
             allh.copy_(self.torch.cat(parts))
 
+    def _tick(self, key, t0):
+        """host wall clock per call site (every one of them ends with a device or collective round trip)"""
+        import time
+        t1 = time.perf_counter()
+        W = self.wall = getattr(self, "wall", {})
+        W[key] = W.get(key, 0.0) + (t1 - t0) * 1e3
+        return t1
+
     def _stage_interval(self, c0, c1):
         """stage global chunks [c0, c1): every rank bins its local share, owners pull, aggregate and count new keys"""
+        import time
+        t = time.perf_counter()
         torch = self.torch
         dev = torch.device("cuda", self.device)
         lo, hi = local_chunk_range(c0, c1, self.rank, self.world, len(self._ends))
@@ -410,16 +420,24 @@ class ShardedCounter:
                 if off >= b:
                     break
         self.shard.mg_bin_local(self._text_ptr + a, b - a, self._K, self.parity, hist.data_ptr())
+        t = self._tick("bin_local", t)
         allh = self._buf("all_hist", self.world * nfg, torch.int32)[:self.world * nfg]
         self._ctl_allgather_hist(hist, allh)
         torch.cuda.ExternalStream(self.shard.stream(), device=dev).wait_stream(torch.cuda.current_stream())
+        torch.cuda.current_stream().synchronize()
+        t = self._tick("allgather_layouts(wait for peers)", t)
         nn, no = self.shard.mg_stage_pull(allh.data_ptr(), self.parity)
+        t = self._tick("stage_pull", t)
         self.parity ^= 1
         tot = self._ctl_allreduce([nn, no])
+        self._tick("allreduce_counts(wait for peers)", t)
         return tot[0], tot[1]
 
     def _commit(self):
+        import time
+        t = time.perf_counter()
         self.shard.mg_commit()
+        self._tick("commit", t)
 
     def _discard(self):
         self.shard.mg_discard()
@@ -428,6 +446,8 @@ class ShardedCounter:
         """One deNoise sweep over the sharded filter (exact: the reference's range hand-out incl. the range-end rule).
         Layout carry (max-plus) -> the range walk handed from rank to rank -> local compaction.  Returns the number of
         keys removed over all shards."""
+        import time
+        t = time.perf_counter()
         torch = self.torch
         a, b = self.shard.mg_layout_aggregate()
         aggs = self._ctl_allgather_pairs((a, b))
@@ -440,7 +460,9 @@ class ShardedCounter:
         self.shq.lib().shq_mg_denoise_finalize(state.ctypes.data)
         protect = (int(state[11]) >> self.rank) & 1
         removed = self.shard.mg_denoise_apply(protect)
-        return self._ctl_allreduce([removed])[0]
+        r = self._ctl_allreduce([removed])[0]
+        self._tick("denoise_sweep", t)
+        return r
 
     def _allgather_dev(self, allb, buf):
         """all_gather_into_tensor for device tensors on any backend (gloo: staged through the host)"""
@@ -573,6 +595,8 @@ class ShardedCounter:
         scan, so a shard needs the composed map of its predecessors (2 x int64, all-gathered) and the handful of
         entries of the previous shard whose slots reach across the boundary (boundary stitch).
         Returns (device pointer of the shard image, first block, number of blocks)."""
+        import time
+        t_mat = time.perf_counter()
         torch = self.torch
         dev = torch.device("cuda", self.device)
         a, b = self.shard.mg_layout_aggregate()
@@ -593,7 +617,9 @@ class ShardedCounter:
             n_spill = int(prev[0].item())
             sk, sp, sc = prev[1:1 + cap].data_ptr(), prev[1 + cap:1 + 2 * cap].data_ptr(), prev[1 + 2 * cap:1 + 3 * cap].data_ptr()
         torch.cuda.synchronize()
-        return self.shard.mg_materialize_shard(sk, sc, sp, n_spill)
+        r = self.shard.mg_materialize_shard(sk, sc, sp, n_spill)
+        self._tick("materialize_shard", t_mat)
+        return r
 
     def export_sharded(self):
         """Rank 0 returns the reference-format .cqf bytes assembled from the shard images; other ranks return None."""
@@ -698,6 +724,7 @@ def bench_sharded(args, rank, world, local_rank, B):
     torch.cuda.synchronize()
     dist.barrier()
     sc._timing = {}
+    sc.wall = {}
     sc.shard.reset_stats()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -714,6 +741,7 @@ def bench_sharded(args, rank, world, local_rank, B):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     clocks = sampler.stop()
     st = sc.shard.stats()
+    wall = {k: v / args.steps for k, v in sc.wall.items()}
     launches = torch.tensor([st["kernels_launched"]], dtype=torch.int64, device=dev)
     dist.all_reduce(launches)
     search = (sc.search.attempts, sc.search.rejected)
@@ -796,7 +824,8 @@ def bench_sharded(args, rank, world, local_rank, B):
                 "roofline": {"bound": "hbm", "kernel": "whole sharded insert path", "achieved": value * a_ins / 1e9 / world, "peak": peak, "unit": "GB/s",
                              "frac": value * a_ins / 1e9 / world / peak, "traffic": None, "note": "per GPU, against SURVEY 8(d) A_ins",
                              "phase_ms_per_step_rank0": {k: st[k] / args.steps for k in st if k.startswith("ms_")},
-                             "host_syncs_per_step_rank0": st["host_syncs"] / args.steps, "batches_per_step": st["batches"] / args.steps},
+                             "host_syncs_per_step_rank0": st["host_syncs"] / args.steps, "batches_per_step": st["batches"] / args.steps,
+                             "host_wall_ms_per_step_rank0": wall},
                 "result": {"ndistinct": int(nd), "nelts": int(ne), "denoise_rounds": int(sweeps), "kmers_per_step": int(n_total),
                            "boundary_search": {"staged_intervals": search[0], "rejected": search[1]}},
                 "parity": parity}

@@ -150,12 +150,15 @@ int shq_header(shq_t h, uint64_t ndistinct, uint64_t nelts, uint8_t out[128]);
  * shq_mg_setup: two fixed buffers of max_words 32-bit words for this rank's binned k-mers; their CUDA IPC handles
  *   (2 x 64 bytes) go to ipc_handles_out.  shq_mg_open_peers: all ranks' handles (world x 2 x 64 bytes, rank-major)
  *   are mapped into this process.
- * shq_mg_bin_local: hash the text; d_fine_hist (caller's device buffer, world * 4096 words) receives the histogram
- *   over the fine bins of the WHOLE key space; the k-mers are binned (2048 coarse bins) into buffer `parity`.
- * shq_mg_insert_pull: d_all_fine_hist = the all-gathered histograms [world][world * 4096].  The owner reads its
+ * shq_mg_bin_local: hash the text ONCE and bin the k-mers over the WHOLE key space (2048 fixed-capacity coarse bins)
+ *   into buffer `parity`; d_fine_hist (caller's device buffer, world * 4096 words) receives the LAYOUT of that buffer:
+ *   word b = first word of coarse bin b, word 2048 + b = one past its last (a bin that overflows makes this call bin
+ *   again with a counting pass and exact offsets; the owners only ever see (begin, end) pairs).
+ * shq_mg_insert_pull: d_all_fine_hist = the all-gathered layouts [world][world * 4096].  The owner reads its
  *   coarse bins straight out of every source's buffer `parity` (P2P loads inside the split kernel), splits them into
- *   its 4096 fine bins and inserts.  A source may refill a buffer two batches later (the histogram all-gather of
- *   the batch in between orders the accesses).                                                                   */
+ *   its fine bins (fixed capacity; exact offsets after a counting pass over the same peer memory if one overflows)
+ *   and inserts.  A source may refill a buffer two batches later (the layout all-gather of the batch in between
+ *   orders the accesses).                                                                                        */
 int shq_mg_setup(shq_t h, size_t max_words, void* ipc_handles_out);
 int shq_mg_open_peers(shq_t h, const void* all_handles, int world);
 int shq_mg_bin_local(shq_t h, const char* d_text, size_t n, int K, int parity, uint32_t* d_fine_hist, size_t* n_words);
@@ -168,10 +171,13 @@ int shq_mg_insert_pull(shq_t h, const uint32_t* d_all_fine_hist, int parity);
  * shq_mg_denoise_walk / _finalize / _apply: one sharded sweep (cqf/CQF_mt.h:884-922, cqf/gqf.c:2792-3040): the chain of
  * 2^20-slot ranges runs over global slot positions, so rank r walks its entries (laid out behind `carry`, see
  * shq_mg_layout_aggregate) and hands the 16-word chain state to rank r + 1; after the last rank _finalize closes the
- * open range; _apply drops the count-1 entries except the protected ones (protect_last = bit `rank` of state[11]).  */
+ * open range; _apply drops the count-1 entries except the protected ones (protect_last = bit `rank` of state[11]).
+ * shq_mg_denoise_positions (optional, before the walk): lays the shard out behind `carry` -- on all ranks at once, so
+ * that the chain, which is serial from rank to rank, only runs the walk itself.                                     */
 int shq_mg_stage_pull(shq_t h, const uint32_t* d_all_fine_hist, int parity, uint64_t* n_new, uint64_t* n_occ);
 int shq_mg_commit(shq_t h);
 int shq_mg_discard(shq_t h);
+int shq_mg_denoise_positions(shq_t h, const int64_t carry[2]);
 int shq_mg_denoise_walk(shq_t h, const int64_t carry[2], uint64_t state[16]);
 int shq_mg_denoise_finalize(uint64_t state[16]);
 int shq_mg_denoise_apply(shq_t h, int protect_last, uint64_t* removed);

@@ -76,7 +76,7 @@ EXPORTS = [
     "shq_materialize", "shq_param_block", "shq_cdfpoi_positive", "shq_cdfpoi",
     "shq_mg_setup", "shq_mg_open_peers", "shq_mg_bin_local", "shq_mg_insert_pull",
     "shq_mg_image_ipc", "shq_mg_open_image_peers", "shq_mg_close_image_peers", "shq_unitigs_begin_sharded",
-    "shq_mg_stage_pull", "shq_mg_commit", "shq_mg_discard", "shq_mg_denoise_walk", "shq_mg_denoise_finalize", "shq_mg_denoise_apply",
+    "shq_mg_stage_pull", "shq_mg_commit", "shq_mg_discard", "shq_mg_denoise_positions", "shq_mg_denoise_walk", "shq_mg_denoise_finalize", "shq_mg_denoise_apply",
     "shq_mg_bin_fastq_device", "shq_mg_insert_binned", "shq_mg_layout_aggregate", "shq_mg_layout_tail", "shq_mg_materialize_shard", "shq_header",
     "shq_hash_fastq_device", "shq_partition_keys_device", "shq_state_view", "shq_adopt_state", "shq_set_counts", "shq_copy_device",
 ]
@@ -151,6 +151,7 @@ def lib():
         L.shq_mg_commit.argtypes = [vp]
         L.shq_mg_discard.argtypes = [vp]
         L.shq_mg_denoise_walk.argtypes = [vp, C.POINTER(C.c_int64), vp]
+        L.shq_mg_denoise_positions.argtypes = [vp, C.POINTER(C.c_int64)]
         L.shq_mg_denoise_finalize.argtypes = [vp]
         L.shq_mg_denoise_apply.argtypes = [vp, C.c_int, C.POINTER(u64)]
         L.shq_mg_layout_aggregate.argtypes = [vp, C.POINTER(C.c_int64)]
@@ -489,6 +490,10 @@ class CQF:
 
     def mg_discard(self):
         self._check(self.L.shq_mg_discard(self.h))
+
+    def mg_denoise_positions(self, carry):
+        g = (C.c_int64 * 2)(int(carry[0]), int(carry[1]))
+        self._check(self.L.shq_mg_denoise_positions(self.h, g))
 
     def mg_denoise_walk(self, carry, state):
         """state: numpy uint64[16], updated in place"""

@@ -66,6 +66,7 @@ struct shq_handle_s {
   size_t batch_cap_bytes = (size_t)3 << 30;   // ... up to this much text (SHQ_BATCH_CAP_MB)
   int wide_batches = 1;          // SHQ_WIDE: 0 = never batch past the armed chunk cap while rounds are pending, 1 = when the trigger is
                                  // predicted to be far away, 2 = always (tests: exercises the fallback)
+  bool walk_pos_ready = false; size_t walk_pos_n = 0; int64_t walk_pos_carry[2] = {0, 0};   // shq_mg_denoise_positions ran for this state
   int armed_chunk_cap = 0;       // SHQ_ARMED_CHUNKS: override of the chunks an armed batch may hold (tests)
   double bytes_per_kmer = 3.0;   // text bytes per k-mer, from the last batch
   bool batch_fixed = false;                   // SHQ_MAX_BATCH_MB given: every batch at most that size
@@ -2138,6 +2139,25 @@ int shq_mg_discard(shq_t h) {
 //      previous rank (zeros for rank 0) and goes on to the next one.
 //  shq_mg_denoise_finalize : after the last rank, closes the range that was open at the end of all entries (host only).
 //  shq_mg_denoise_apply : drops the count-1 entries except the protected ones; protect_last = bit `rank` of state[11].
+int shq_mg_denoise_positions(shq_t h, const int64_t carry[2]) {
+  if (!h || !carry) return SHQ_ERR_ARG;
+  struct { const int64_t* c; } args{carry};
+  SHQ_API_BEGIN(h)
+    // global slot positions of this shard's entries behind the carry of its predecessors -- all ranks at once, BEFORE the
+    // chain walk goes from rank to rank (shq_mg_denoise_walk then only runs the walk; it computes the positions itself
+    // when this was not called)
+    flush_stage(h); ensure_state(h);
+    if (h->mg_pending.valid) SHQ_FAIL(SHQ_ERR_STATE, "a staged batch is waiting for shq_mg_commit / shq_mg_discard");
+    h->walk_pos_ready = false;
+    if (h->n_state == 0) return;
+    Phase ph(h, &h->stats.ms_denoise);
+    MaxPlus init{a.c[0], a.c[1]};
+    compute_positions(h, 0, init);
+    SHQ_CUDA(cudaStreamSynchronize(h->stream));
+    h->walk_pos_ready = true; h->walk_pos_n = h->n_state; h->walk_pos_carry[0] = a.c[0]; h->walk_pos_carry[1] = a.c[1];
+  SHQ_API_END
+}
+
 int shq_mg_denoise_walk(shq_t h, const int64_t carry[2], uint64_t state[16]) {
   if (!h || !carry || !state) return SHQ_ERR_ARG;
   struct { const int64_t* c; uint64_t* s; } args{carry, state};
@@ -2154,8 +2174,9 @@ int shq_mg_denoise_walk(shq_t h, const int64_t carry[2], uint64_t state[16]) {
     uint32_t* n_keep = h->d_keep.as<uint32_t>(); uint32_t* keep_idx = n_keep + 4;
     SHQ_CUDA(cudaMemsetAsync(n_keep, 0, 16, st));
     if (n == 0) return;       // nothing to walk: the chain passes through unchanged
-    MaxPlus init{a.c[0], a.c[1]};
-    compute_positions(h, 0, init);
+    const bool ready = h->walk_pos_ready && h->walk_pos_n == n && h->walk_pos_carry[0] == a.c[0] && h->walk_pos_carry[1] == a.c[1];
+    h->walk_pos_ready = false;
+    if (!ready) { MaxPlus init{a.c[0], a.c[1]}; compute_positions(h, 0, init); }
     h->d_walk.reserve(256);
     SHQ_CUDA(cudaMemcpyAsync(h->d_walk.p, a.s, 128, cudaMemcpyHostToDevice, st));
     denoise_walk_kernel<<<1, 32, 0, st>>>(h->st_keys.as<uint64_t>(), h->st_counts.as<uint32_t>(), h->d_pos.as<uint64_t>(), n,

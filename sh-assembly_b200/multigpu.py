@@ -452,6 +452,7 @@ class ShardedCounter:
         a, b = self.shard.mg_layout_aggregate()
         aggs = self._ctl_allgather_pairs((a, b))
         carry = carry_before(aggs, self.rank)
+        self.shard.mg_denoise_positions(carry)      # every rank lays its shard out now; the chain below is serial
         state = np.zeros(16, np.uint64)
         for r in range(self.world):
             if self.rank == r:

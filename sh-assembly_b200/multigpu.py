@@ -419,18 +419,35 @@ class ShardedCounter:
                 ev.synchronize()
                 if off >= b:
                     break
-        self.shard.mg_bin_local(self._text_ptr + a, b - a, self._K, self.parity, hist.data_ptr())
+        # a rank-local failure (malformed text, exchange buffer too small ...) must not leave the peers waiting in a
+        # collective: the status rides in the last word of the layout buffer (the layout uses the first 4096) and in the
+        # count all-reduce, and every rank raises together
+        err = None
+        try:
+            self.shard.mg_bin_local(self._text_ptr + a, b - a, self._K, self.parity, hist.data_ptr())
+        except self.shq.ShqError as e:
+            err = e
+        if self.world > 1:
+            hist[nfg - 1] = 1 if err else 0
         t = self._tick("bin_local", t)
         allh = self._buf("all_hist", self.world * nfg, torch.int32)[:self.world * nfg]
         self._ctl_allgather_hist(hist, allh)
         torch.cuda.ExternalStream(self.shard.stream(), device=dev).wait_stream(torch.cuda.current_stream())
-        torch.cuda.current_stream().synchronize()
+        failed = int(allh.view(self.world, nfg)[:, nfg - 1].sum().item()) if self.world > 1 else (1 if err else 0)
         t = self._tick("allgather_layouts(wait for peers)", t)
-        nn, no = self.shard.mg_stage_pull(allh.data_ptr(), self.parity)
+        if failed:
+            raise err if err else RuntimeError("rank %d: a peer failed while binning chunks [%d, %d)" % (self.rank, c0, c1))
+        nn = no = 0
+        try:
+            nn, no = self.shard.mg_stage_pull(allh.data_ptr(), self.parity)
+        except self.shq.ShqError as e:
+            err = e
         t = self._tick("stage_pull", t)
         self.parity ^= 1
-        tot = self._ctl_allreduce([nn, no])
+        tot = self._ctl_allreduce([nn, no, 1 if err else 0])
         self._tick("allreduce_counts(wait for peers)", t)
+        if tot[2]:
+            raise err if err else RuntimeError("rank %d: a peer failed while inserting chunks [%d, %d)" % (self.rank, c0, c1))
         return tot[0], tot[1]
 
     def _commit(self):

@@ -180,20 +180,23 @@ PHASES = {
 }
 
 
-def measured_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture of
-    this bench command (profiles/r2_traffic.json, written by tools/ncu_summary.py); None if absent."""
-    for f in ("r2_traffic.json",):
-        try:
-            t = json.load(open(os.path.join(ROOT, "profiles", f)))
-            if kernel in t:
-                return t[kernel]
-        except Exception:
-            pass
-    return None
+def measured_traffic(kernel, workload=None):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture
+    (profiles/r2_traffic.json, written by tools/ncu_summary.py + the workload it was taken on).  Returns (bytes per launch
+    or None, capture description): the per-launch figure is only comparable with this run's algorithmic bytes per launch
+    when the capture was taken on the same workload -- otherwise `traffic` stays null and the capture is reported beside it."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+    except Exception:
+        return None, None
+    if kernel not in t:
+        return None, None
+    cap = {"workload": t.get("_workload"), "bytes_per_launch": t[kernel], "source": "profiles/r2_traffic.json (ncu --set full)"}
+    same = workload is not None and t.get("_workload") == workload
+    return (t[kernel] if same else None), cap
 
 
-def roofline(stats, steps, value, a_ins, table_bytes):
+def roofline(stats, steps, value, a_ins, table_bytes, workload=None):
     peak, peak_src = peak_hbm()
     phases = {k: stats[k] / steps for k in PHASES}
     dom = max(phases, key=phases.get)
@@ -205,8 +208,9 @@ def roofline(stats, steps, value, a_ins, table_bytes):
     nl = max(1, stats[lkey])
     ms_launch = stats[dom] / nl
     achieved = (alg / nl) / (ms_launch / 1e3) / 1e9 if ms_launch > 0 else 0.0
+    traffic, capture = measured_traffic(kernel, workload)
     return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": measured_traffic(kernel), "peak_source": peak_src,
+            "traffic": traffic, "traffic_capture": capture, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg / nl, "launches_per_step": nl / steps, "ms_per_launch": ms_launch,
             "note": "achieved = algorithmic bytes of the phase's launches (work counters of shq_stats, summed per launch) / CUDA-event time "
                     "of the phase on the handle's stream; the path is bound by instruction issue and shared-memory latency (DESIGN.md 4)",
@@ -340,7 +344,7 @@ def run_workload(args, name, steps, warmup, local_rank, want_unitigs, want_cpu):
                     "h2d_floor_ms": h2d_floor_ms, "batches_per_step": st2["batches"] / e2e_steps, "wide_batches": int(st2["wide_batches"]),
                     "wide_fallbacks": int(st2["wide_fallbacks"]), "spec_rejected": int(st2["spec_rejected"]),
                     "gpu_busy_ms_per_step": sum(st2[k] for k in st2 if k.startswith("ms_")) / e2e_steps},
-            "gpu_launches": int(stats["kernels_launched"]), "roofline": roofline(stats, steps, value, a_ins, table_bytes),
+            "gpu_launches": int(stats["kernels_launched"]), "roofline": roofline(stats, steps, value, a_ins, table_bytes, name),
             "result": {"ndistinct": int(ndistinct), "nelts": int(nelts), "denoise_rounds": int(rounds), "kmers_per_step": int(n_total),
                        "batches_per_step": stats["batches"] / steps, "host_syncs_per_step": stats["host_syncs"] / steps,
                        "bin_fallbacks": int(stats["bin_fallbacks"]), "wide_batches": int(stats["wide_batches"]),

@@ -28,7 +28,12 @@ if "--traffic" in sys.argv:
     for d in data:
         name = re.split(r'[<(]', d[hdr.index('Kernel Name')])[0].split('::')[-1].replace('void ', '').strip()
         acc[name].append(_bytes(d[ir], units[ir]) + _bytes(d[iw], units[iw]))
-    json.dump({k: sum(v) / len(v) for k, v in acc.items()}, open(out, 'w'), indent=1, sort_keys=True)
+    tr = {k: sum(v) / len(v) for k, v in acc.items()}
+    if "--workload" in sys.argv:      # the workload the capture was taken on (bench.py compares per-launch figures only on the same one)
+        wname = sys.argv[sys.argv.index("--workload") + 1]
+        tr["_workload"] = wname
+        sys.argv = [a for a in sys.argv if a not in ("--workload", wname)]
+    json.dump(tr, open(out, 'w'), indent=1, sort_keys=True)
     sys.argv = [a for a in sys.argv if a not in ("--traffic", out)]
 if len(sys.argv) > 2:
     src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout

@@ -12,7 +12,7 @@ timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"bin_aggregate|merge_tiles|roll_scatter|split_bins|denoise_tiles|layout_scan|image_tiles|nl_write" -s 50 -c 16 \
     -o /tmp/r2_full python bench.py --workload celegans20 --secondary "" --steps 1 --warmup 0 --cpu-seconds 1 --unitigs 0 --e2e-steps 1 > $out/r2_full.log 2>&1
 ls -la /tmp/r2_full.ncu-rep
-timeout 300 python tools/ncu_summary.py /tmp/r2_full.ncu-rep $out/r2_full.pkl --traffic $out/r2_traffic.json > $out/r2_full.summary.txt 2>&1
+timeout 300 python tools/ncu_summary.py /tmp/r2_full.ncu-rep $out/r2_full.pkl --traffic $out/r2_traffic.json --workload celegans20 > $out/r2_full.summary.txt 2>&1
 for i in 0 2 4 6 8 10 12 14 16 18 20 22 24 26 28 30; do timeout 60 python tools/line_profile.py $out/r2_full.pkl $i sh-assembly_b200/libshq.so 16 >> $out/r2_line_profiles.txt 2>&1; done
 cuobjdump -sass sh-assembly_b200/libshq.so | grep -E "Function :|UBLKCP|SYNCS|UTMALDG" | grep -B1 -E "UBLKCP|SYNCS|UTMALDG" | head -60 > $out/r2_sass_tma.txt
 du -sh $out; ls -la $out | tail -12

@@ -67,6 +67,7 @@ struct shq_handle_s {
   int wide_batches = 1;          // SHQ_WIDE: 0 = never batch past the armed chunk cap while rounds are pending, 1 = when the trigger is
                                  // predicted to be far away, 2 = always (tests: exercises the fallback)
   bool walk_pos_ready = false; size_t walk_pos_n = 0; int64_t walk_pos_carry[2] = {0, 0};   // shq_mg_denoise_positions ran for this state
+  bool armed_near = true;        // SHQ_ARMED_NEAR=0: armed batches always at full size
   int armed_chunk_cap = 0;       // SHQ_ARMED_CHUNKS: override of the chunks an armed batch may hold (tests)
   double bytes_per_kmer = 3.0;   // text bytes per k-mer, from the last batch
   bool batch_fixed = false;                   // SHQ_MAX_BATCH_MB given: every batch at most that size
@@ -278,22 +279,31 @@ size_t batch_chunk_cap(shq_handle_s* h) {
 // the trigger be reached after all, process_batch() drops the shadow and redoes the batch in halves.  Fewer, larger
 // batches mean fewer passes over the resident state.
 constexpr size_t kArmedBatchBytes = (size_t)1 << 30;
+constexpr size_t kNearBatch = (size_t)256 << 20;
 void batch_limits(shq_handle_s* h, size_t* bytes, size_t* chunks) {
   size_t t = batch_target_bytes(h), c = batch_chunk_cap(h);
   if (h->rounds_left > 0) {
     const size_t armed_bytes = std::min(t, kArmedBatchBytes);
     bool wide = false;
+    double room_bytes = -1.0;                               // text until the predicted crossing (< 0: no prediction)
+    if (h->new_rate >= 0 && h->n_state > 0 && h->ndistinct < h->trigger) {
+      const double room = (double)(h->trigger - h->ndistinct) / std::max(h->new_rate * 1.3, 1e-9);   // k-mers, 30 % margin
+      room_bytes = room * h->bytes_per_kmer;
+    }
     if (h->wide_batches == 2) { c = (size_t)1 << 20; wide = true; }
-    else if (h->wide_batches && h->new_rate >= 0 && h->n_state > 0 && h->ndistinct < h->trigger) {
-      const double room = (double)(h->trigger - h->ndistinct) / std::max(h->new_rate * 1.3, 1e-9);   // k-mers until the predicted crossing
-      double pending = 0;                                   // text already queued behind the state (pinned pipeline)
-      pending = 0;   // (the pinned pipeline sizes a batch when it is about to be processed: nothing is queued ahead of that decision)
-      const double room_bytes = std::max(0.0, room * h->bytes_per_kmer - pending);
+    else if (h->wide_batches && room_bytes >= 0) {
       if (h->armed_chunk_cap > 0 || (t > armed_bytes && room_bytes > 1.5 * (double)armed_bytes)) {
         t = (size_t)std::min((double)t, room_bytes); c = (size_t)1 << 20; wide = true;
       }
     }
-    if (!wide) t = armed_bytes;
+    if (!wide) {
+      t = armed_bytes;
+      // The batch that holds the boundary is aggregated twice more (first chunks, then both sides of c*) and merged three
+      // times: keep it small.  A batch that is predicted to stay below the trigger ends short of the crossing (it commits
+      // as a whole); once the crossing is nearer than kNearBatch the batches are that small.
+      if (h->armed_near && room_bytes >= 0 && !h->batch_fixed && h->armed_chunk_cap == 0)
+        t = std::min(armed_bytes, (size_t)std::max(room_bytes, (double)kNearBatch));
+    }
   }
   *bytes = t; *chunks = c;
 }
@@ -1153,6 +1163,7 @@ void init_handle(shq_handle_s* h, int qb, int hb, uint32_t seed, int device, int
     SHQ_FAIL(SHQ_ERR_ARG, "bad shard %d of %d", shard, nshards);
   if (const char* e = getenv("SHQ_MAX_BATCH_MB")) { long v = atol(e); if (v >= 1 && v <= 3072) { h->max_batch_bytes = (size_t)v << 20; h->batch_fixed = true; } }
   if (const char* e = getenv("SHQ_BATCH_CAP_MB")) { long v = atol(e); if (v >= 64 && v <= 3072) h->batch_cap_bytes = (size_t)v << 20; }
+  if (const char* e = getenv("SHQ_ARMED_NEAR")) h->armed_near = atoi(e) != 0;
   if (const char* e = getenv("SHQ_WIDE")) { int v = atoi(e); if (v >= 0 && v <= 2) h->wide_batches = v; }
   if (const char* e = getenv("SHQ_ARMED_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 1024) h->armed_chunk_cap = v; }
   if (const char* e = getenv("SHQ_SPEC_BINS")) h->spec_bins = atoi(e) != 0;
